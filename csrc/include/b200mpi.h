@@ -1,0 +1,187 @@
+/*
+ * b200mpi — Blackwell-native collective runtime (C ABI).
+ *
+ * This is the data plane that the reference delegates to external software
+ * (Horovod -> NCCL inside user images; reference: examples/v2beta1/
+ * tensorflow-benchmarks/tensorflow-benchmarks.yaml:26-42).
+ * Here it is first-party: one process per GPU, peers mapped through CUDA VMM
+ * (POSIX-fd export + SCM_RIGHTS) or cudaIpc, NVLS multicast objects when the
+ * host exposes them, and hand-written sm_100a kernels that read/write peer
+ * HBM directly over NVSwitch.
+ *
+ * All functions return 0 on success or a negative B200MPI_ERR_* code;
+ * b200mpi_last_error() returns a thread-local human readable message.
+ */
+#ifndef B200MPI_H_
+#define B200MPI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MPI_MAX_RANKS 8
+#define B200MPI_VERSION "0.1.0"
+
+typedef struct b200mpi_comm* b200mpi_comm_t;
+
+typedef enum {
+  B200MPI_F32 = 0,
+  B200MPI_BF16 = 1,
+  B200MPI_F16 = 2,
+} b200mpi_dtype_t;
+
+typedef enum {
+  B200MPI_SUM = 0,
+  B200MPI_MAX = 1,
+  B200MPI_MIN = 2,
+} b200mpi_op_t;
+
+typedef enum {
+  B200MPI_ALGO_AUTO = 0,
+  B200MPI_ALGO_ONESHOT = 1, /* push one-shot: 1 NVLink traversal + flag   */
+  B200MPI_ALGO_TWOSHOT = 2, /* reduce-scatter(pull) + all-gather(push)    */
+  B200MPI_ALGO_NVLS = 3,    /* multimem.ld_reduce + multimem.st in-switch */
+} b200mpi_algo_t;
+
+enum {
+  B200MPI_OK = 0,
+  B200MPI_ERR_INVALID = -1,
+  B200MPI_ERR_CUDA = -2,
+  B200MPI_ERR_SYS = -3,
+  B200MPI_ERR_TIMEOUT = -4,
+  B200MPI_ERR_UNSUPPORTED = -5,
+  B200MPI_ERR_PEER = -6,
+};
+
+/* flags for b200mpi_comm_init */
+enum {
+  B200MPI_FLAG_NO_MULTICAST = 1u << 0, /* never create NVLS multicast objects */
+  B200MPI_FLAG_FORCE_IPC = 1u << 1,    /* cudaIpc instead of VMM fd export    */
+};
+
+const char* b200mpi_last_error(void);
+const char* b200mpi_version(void);
+
+/*
+ * Multi-process communicator: `rank` of `world` on CUDA `device`. Ranks of the
+ * same job find each other through the POSIX shm rendezvous segment
+ * "/b200mpi-<job_id>" (replaces ssh + DNS + ncclUniqueId broadcast of the
+ * reference stack). staging_bytes is the per-rank staging
+ * window used by collectives on unregistered pointers (0 = default 64 MiB).
+ */
+int b200mpi_comm_init(b200mpi_comm_t* comm, int rank, int world, int device,
+                      const char* job_id, size_t staging_bytes, unsigned flags);
+
+/*
+ * Emulated communicator: `world` virtual ranks inside ONE process on ONE
+ * device. Every collective is a single launch with gridDim.y == world, each
+ * y-slice of CTAs playing one rank. Exercises the exact same kernels with no
+ * second GPU (unit tests, compute-sanitizer, ncu). Pointer arguments of the
+ * collectives become arrays of `world` pointers (see each call).
+ */
+int b200mpi_comm_init_local(b200mpi_comm_t* comm, int world, int device,
+                            size_t staging_bytes, unsigned flags);
+
+int b200mpi_comm_destroy(b200mpi_comm_t comm);
+int b200mpi_comm_rank(b200mpi_comm_t comm);
+int b200mpi_comm_world(b200mpi_comm_t comm);
+int b200mpi_comm_is_local(b200mpi_comm_t comm);
+int b200mpi_comm_has_multicast(b200mpi_comm_t comm);
+/* host-side barrier through the shm segment (no GPU work) */
+int b200mpi_comm_host_barrier(b200mpi_comm_t comm);
+/* host-side small allgather through the shm segment: each rank contributes
+ * `bytes` (<= 256) and receives world*bytes. */
+int b200mpi_comm_host_allgather(b200mpi_comm_t comm, const void* in, void* out, size_t bytes);
+/* non-zero if a device-side wait timed out since the last call (watchdog) */
+int b200mpi_comm_check_error(b200mpi_comm_t comm);
+/* number of b200mpi kernels launched so far on this communicator */
+uint64_t b200mpi_comm_launch_count(b200mpi_comm_t comm);
+
+/*
+ * Symmetric windows: every rank allocates `bytes`, all ranks map all peers,
+ * and (when available) the window is bound to an NVLS multicast object.
+ * Collective call. window ids are small integers, identical on all ranks.
+ */
+int b200mpi_window_alloc(b200mpi_comm_t comm, size_t bytes, int* win);
+int b200mpi_window_free(b200mpi_comm_t comm, int win);
+/* VA (in this process) of `rank`'s copy of the window; rank = -1 -> own copy.
+ * In emulated mode `rank` selects the virtual rank. */
+void* b200mpi_window_ptr(b200mpi_comm_t comm, int win, int rank);
+void* b200mpi_window_mc_ptr(b200mpi_comm_t comm, int win);
+size_t b200mpi_window_size(b200mpi_comm_t comm, int win);
+
+/*
+ * In-place allreduce on a symmetric window region [offset, offset+count*esz).
+ * out = scale * reduce_over_ranks(in). `scale` is fused into the reduction
+ * (1/world for Horovod's Average; reference call site: examples/v2beta1/
+ * horovod/tensorflow_mnist.py:133). offset must be 16-byte aligned.
+ */
+int b200mpi_allreduce_sym(b200mpi_comm_t comm, int win, size_t offset, size_t count,
+                          b200mpi_dtype_t dtype, b200mpi_op_t op, float scale,
+                          b200mpi_algo_t algo, void* stream);
+
+/*
+ * Allreduce on arbitrary device pointers (staged through the comm's staging
+ * window inside the same kernel). in == out allowed. In emulated mode `in`
+ * and `out` are `const void* const*` / `void* const*` arrays of world ptrs.
+ */
+int b200mpi_allreduce(b200mpi_comm_t comm, const void* in, void* out, size_t count,
+                      b200mpi_dtype_t dtype, b200mpi_op_t op, float scale,
+                      b200mpi_algo_t algo, void* stream);
+
+/* Fused gradient-allreduce + SGD(momentum, weight decay, nesterov) step:
+ *   g   = scale * sum_r grad_r[i]           (each rank owns a 1/world slice)
+ *   g  += wd * p ; m = mu*m + g ; p -= lr * (nesterov ? g + mu*m : m)
+ * and the updated parameter slice is pushed to every rank's parameter window
+ * (multimem.st on NVLS). Momentum is sharded: `momentum` points at this rank's
+ * slice buffer of ceil(count/world) fp32 elements rounded up to 4
+ * (b200mpi_slice_elems). grad window dtype = gdtype, param window fp32.
+ * If `lowp_win` >= 0 a bf16 copy of the parameters is also pushed there.
+ * Emulated mode: `momentum` is an array of world pointers. */
+int b200mpi_allreduce_sgd_sym(b200mpi_comm_t comm, int grad_win, size_t grad_off,
+                              int param_win, size_t param_off, int lowp_win, size_t lowp_off,
+                              void* momentum, size_t count, b200mpi_dtype_t gdtype, float scale,
+                              float lr, float mu, float wd, int nesterov, int first_step,
+                              b200mpi_algo_t algo, void* stream);
+size_t b200mpi_slice_elems(size_t count, int world, b200mpi_dtype_t dtype);
+
+int b200mpi_broadcast(b200mpi_comm_t comm, void* buf, size_t count, b200mpi_dtype_t dtype,
+                      int root, void* stream);
+int b200mpi_broadcast_bytes(b200mpi_comm_t comm, void* buf, size_t bytes, int root, void* stream);
+/* out has world*count elements */
+int b200mpi_allgather(b200mpi_comm_t comm, const void* in, void* out, size_t count,
+                      b200mpi_dtype_t dtype, void* stream);
+/* in has world*count elements, out count */
+int b200mpi_reduce_scatter(b200mpi_comm_t comm, const void* in, void* out, size_t count,
+                           b200mpi_dtype_t dtype, b200mpi_op_t op, float scale, void* stream);
+int b200mpi_reduce(b200mpi_comm_t comm, const void* in, void* out, size_t count,
+                   b200mpi_dtype_t dtype, b200mpi_op_t op, float scale, int root, void* stream);
+/* in/out have world*count elements; block j of in goes to rank j */
+int b200mpi_alltoall(b200mpi_comm_t comm, const void* in, void* out, size_t count,
+                     b200mpi_dtype_t dtype, void* stream);
+int b200mpi_barrier(b200mpi_comm_t comm, void* stream);
+
+/* fused local elementwise helpers used by the front-ends (same .so) */
+int b200mpi_scale_cast(const void* in, b200mpi_dtype_t in_dtype, void* out,
+                       b200mpi_dtype_t out_dtype, size_t count, float scale, void* stream);
+
+/* tuning */
+int b200mpi_set_tuning(b200mpi_comm_t comm, size_t oneshot_max_bytes, size_t nvls_min_bytes,
+                       int max_blocks, int timeout_ms);
+int b200mpi_get_tuning(b200mpi_comm_t comm, size_t* oneshot_max_bytes, size_t* nvls_min_bytes,
+                       int* max_blocks, int* timeout_ms);
+/* which algorithm would AUTO pick */
+int b200mpi_select_algo(b200mpi_comm_t comm, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op,
+                        int symmetric);
+
+/* trace: per-collective records (op, bytes, algo, host enqueue ns) as JSONL */
+int b200mpi_trace_enable(b200mpi_comm_t comm, int on);
+int b200mpi_trace_dump(b200mpi_comm_t comm, const char* path);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MPI_H_ */

@@ -1,0 +1,537 @@
+// b200mpi collective kernels for sm_100a: NVSwitch peer-memory allreduce
+// (push one-shot, pull/push two-shot, NVLS multimem), fused allreduce+SGD,
+// allgather, broadcast, reduce-scatter, reduce, all-to-all, barrier.
+//
+// Call sites these serve in the reference's workloads:
+//   K2 barrier        examples/v2beta1/pi/pi.cc:49
+//   K3 broadcast      examples/v2beta1/horovod/tensorflow_mnist.py:143
+//   K4 allreduce(avg) examples/v2beta1/horovod/tensorflow_mnist.py:133,
+//                     examples/v2beta1/tensorflow-benchmarks/tensorflow-benchmarks.yaml:42
+//   K5 allgather      Horovod API surface
+// In the reference these are NCCL library calls plus a separate scale kernel;
+// here the 1/N scale, the dtype handling and (optionally) the optimizer step
+// run inside the same kernel that moves the bytes over NVLink.
+//
+// Work partition invariant (needed because CTAs only synchronise with the
+// CTA of the same blockIdx.x on the other ranks): in every phase CTA b touches
+// the vector indices C_b = { i : grid-stride from b } *within each slice*, so
+// whatever CTA b reads after a barrier was written by CTA b of some rank.
+#include "kernels.h"
+
+namespace b200mpi {
+
+#define EMU_ARGS const KArgs& a = (emu != nullptr) ? emu[blockIdx.y] : a0
+
+__device__ __forceinline__ size_t gtid() { return (size_t)blockIdx.x * blockDim.x + threadIdx.x; }
+__device__ __forceinline__ size_t gstride() { return (size_t)gridDim.x * blockDim.x; }
+__device__ __forceinline__ int wrap(int x, int world) { return x >= world ? x - world : x; }
+
+template <typename T>
+__device__ __forceinline__ uint4 reduce_op_vec(const uint4& x, const uint4& y, int op) {
+  float a[VecTraits<T>::N], b[VecTraits<T>::N];
+  VecTraits<T>::unpack(x, a);
+  VecTraits<T>::unpack(y, b);
+#pragma unroll
+  for (int j = 0; j < VecTraits<T>::N; j++)
+    a[j] = op == OP_SUM ? a[j] + b[j] : (op == OP_MAX ? fmaxf(a[j], b[j]) : fminf(a[j], b[j]));
+  return VecTraits<T>::pack(a);
+}
+
+template <typename T>
+__device__ __forceinline__ void accum(float* acc, const uint4& v, int op, bool first) {
+  float f[VecTraits<T>::N];
+  VecTraits<T>::unpack(v, f);
+#pragma unroll
+  for (int j = 0; j < VecTraits<T>::N; j++)
+    acc[j] = first ? f[j] : (op == OP_SUM ? acc[j] + f[j] : (op == OP_MAX ? fmaxf(acc[j], f[j]) : fminf(acc[j], f[j])));
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 nvls_ld_reduce(const void* mc, int op) {
+  if (MultiMem<T>::kHasMinMax) {
+    if (op == OP_MAX) return MultiMem<T>::template ld_reduce<OP_MAX>(mc);
+    if (op == OP_MIN) return MultiMem<T>::template ld_reduce<OP_MIN>(mc);
+  }
+  return MultiMem<T>::template ld_reduce<OP_SUM>(mc);
+}
+
+template <typename T>
+__device__ __forceinline__ uint4 scale_vec(const uint4& v, float s) {
+  float f[VecTraits<T>::N];
+  VecTraits<T>::unpack(v, f);
+#pragma unroll
+  for (int j = 0; j < VecTraits<T>::N; j++) f[j] *= s;
+  return VecTraits<T>::pack(f);
+}
+
+// ===========================================================================
+// Two-shot allreduce. Rank r owns slice r: it pulls slice r from every peer
+// (reduce-scatter), reduces in fp32, applies `scale`, and pushes the result
+// into slice r of every peer (all-gather) — one kernel, two cross-rank
+// barriers. MODE_NVLS replaces the N loads by one multimem.ld_reduce (the
+// NVSwitch adds) and the N stores by one multimem.st (the switch fans out).
+// STAGED: user pointers are copied into / out of the staging window here.
+// ===========================================================================
+template <typename T, int MODE, bool STAGED>
+__global__ void __launch_bounds__(kThreads)
+k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const size_t per = a.per, nvec = a.nvec;
+  char* const mine = a.buf.p[rank];
+
+  if (STAGED) {
+    for (int r = 0; r < world; r++) {
+      const size_t base = (size_t)r * per;
+      for (size_t i = gtid(); i < per && base + i < nvec; i += gstride())
+        *reinterpret_cast<uint4*>(mine + (base + i) * 16) = user_load(a.in, base + i, a.nbytes, a.in_aligned);
+    }
+  }
+  rank_barrier(a.c, ++e);
+
+  {
+    const size_t base = (size_t)rank * per;
+    const size_t lim = base < nvec ? (nvec - base < per ? nvec - base : per) : 0;
+    const bool do_scale = a.scale != 1.0f;
+    if (MODE == MODE_NVLS) {
+      char* const mc = a.buf.mc + base * 16;
+      constexpr int U = 4;
+      for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim) v[u] = nvls_ld_reduce<T>(mc + i * 16, a.op);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim) multimem_st_v4(mc + i * 16, do_scale ? scale_vec<T>(v[u], a.scale) : v[u]);
+        }
+      }
+    } else {
+      char* pp[kMaxRanks];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
+      constexpr int U = 2;
+      for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+        uint4 v[U][kMaxRanks];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+#pragma unroll
+          for (int k = 0; k < kMaxRanks; k++)
+            if (k < world && i < lim) v[u][k] = ld_sys_v4(pp[k] + i * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim) {
+            float acc[VecTraits<T>::N];
+#pragma unroll
+            for (int k = 0; k < kMaxRanks; k++)
+              if (k < world) accum<T>(acc, v[u][k], a.op, k == 0);
+            if (do_scale) {
+#pragma unroll
+              for (int j = 0; j < VecTraits<T>::N; j++) acc[j] *= a.scale;
+            }
+            const uint4 o = VecTraits<T>::pack(acc);
+#pragma unroll
+            for (int k = 0; k < kMaxRanks; k++)
+              if (k < world) st_peer_v4(pp[k] + i * 16, o);
+          }
+        }
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+
+  if (STAGED) {
+    for (int r = 0; r < world; r++) {
+      const size_t base = (size_t)r * per;
+      for (size_t i = gtid(); i < per && base + i < nvec; i += gstride())
+        user_store(a.out, base + i, a.nbytes, a.out_aligned, ld_sys_v4(mine + (base + i) * 16));
+    }
+  }
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+// ===========================================================================
+// Push one-shot allreduce (latency path). Every rank stores its input straight
+// into a private slot of every peer's staging window, signals, then reduces
+// the `world` slots that landed in its own HBM — one NVLink traversal and one
+// flag per rank. Slots are double-buffered on a per-CTA use counter and the
+// staging area is statically partitioned per CTA, so no trailing barrier is
+// needed: a peer can only reach use k+2 of a CTA slot after this rank's kernel
+// for use k has completed (see DESIGN.md "one-shot slot reuse").
+// ===========================================================================
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_allreduce_oneshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const uint32_t use = a.c.epoch[kMaxBlocks + blockIdx.x];
+  const size_t cap = a.per;  // vectors per (parity, block, rank) slot
+  const size_t cv = (a.nvec + gridDim.x - 1) / gridDim.x;
+  const size_t v0 = (size_t)blockIdx.x * cv;
+  const size_t v1 = v0 + cv < a.nvec ? v0 + cv : a.nvec;
+  const size_t slot0 = ((size_t)(use & 1u) * kOneshotBlocks + blockIdx.x) * world * cap;
+
+  for (size_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+    const uint4 v = user_load(a.in, i, a.nbytes, a.in_aligned);
+    const size_t off = (slot0 + (size_t)rank * cap + (i - v0)) * 16;
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++)
+      if (k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + off, v);
+  }
+  rank_barrier(a.c, ++e);
+
+  const char* mine = a.buf.p[rank] + slot0 * 16;
+  const bool do_scale = a.scale != 1.0f;
+  for (size_t i = v0 + threadIdx.x; i < v1; i += blockDim.x) {
+    uint4 v[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; r++)
+      if (r < world) v[r] = ld_sys_v4(mine + ((size_t)r * cap + (i - v0)) * 16);
+    float acc[VecTraits<T>::N];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; r++)
+      if (r < world) accum<T>(acc, v[r], a.op, r == 0);
+    if (do_scale) {
+#pragma unroll
+      for (int j = 0; j < VecTraits<T>::N; j++) acc[j] *= a.scale;
+    }
+    user_store(a.out, i, a.nbytes, a.out_aligned, VecTraits<T>::pack(acc));
+  }
+  if (threadIdx.x == 0) {
+    a.c.epoch[blockIdx.x] = e;
+    a.c.epoch[kMaxBlocks + blockIdx.x] = use + 1;
+  }
+}
+
+// ===========================================================================
+// Fused gradient allreduce + SGD. The reduce-scatter half of the two-shot
+// produces the averaged gradient slice in registers; instead of writing it
+// back, the owner applies weight decay + momentum + the parameter update to
+// its fp32 slice (momentum lives only on the owner: 1/world of the state) and
+// the all-gather half pushes the *updated parameters* to every rank. The
+// gradient never returns to HBM and the optimizer kernel disappears.
+// ===========================================================================
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_allreduce_sgd(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  constexpr int N = VecTraits<T>::N;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const size_t per = a.per, nvec = a.nvec;
+  rank_barrier(a.c, ++e);
+
+  const size_t base = (size_t)rank * per;
+  const size_t lim = base < nvec ? (nvec - base < per ? nvec - base : per) : 0;
+  char* gp[kMaxRanks];
+#pragma unroll
+  for (int k = 0; k < kMaxRanks; k++) gp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
+  const char* gmc = a.buf.mc ? a.buf.mc + base * 16 : nullptr;
+  const bool has_lowp = a.lowp.p[0] != nullptr;
+
+  for (size_t i = gtid(); i < lim; i += gstride()) {
+    float g[N];
+    if (MODE == MODE_NVLS) {
+      VecTraits<T>::unpack(nvls_ld_reduce<T>(gmc + i * 16, OP_SUM), g);
+    } else {
+      uint4 v[kMaxRanks];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++)
+        if (k < world) v[k] = ld_sys_v4(gp[k] + i * 16);
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++)
+        if (k < world) accum<T>(g, v[k], OP_SUM, k == 0);
+    }
+    const size_t el = (base + i) * N;  // first element index of this vector
+    float p[N], m[N];
+    const float* pl = reinterpret_cast<const float*>(a.param.p[rank]) + el;
+    float* ml = a.mom + i * N;
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) {
+      float4 t = *reinterpret_cast<const float4*>(pl + 4 * q);
+      p[4 * q] = t.x; p[4 * q + 1] = t.y; p[4 * q + 2] = t.z; p[4 * q + 3] = t.w;
+      if (!a.first_step) {
+        float4 s = *reinterpret_cast<const float4*>(ml + 4 * q);
+        m[4 * q] = s.x; m[4 * q + 1] = s.y; m[4 * q + 2] = s.z; m[4 * q + 3] = s.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      float gj = g[j] * a.scale + a.wd * p[j];
+      float mj = a.first_step ? gj : a.mu * m[j] + gj;
+      m[j] = mj;
+      p[j] -= a.lr * (a.nesterov ? gj + a.mu * mj : mj);
+    }
+#pragma unroll
+    for (int q = 0; q < N / 4; q++) {
+      *reinterpret_cast<float4*>(ml + 4 * q) = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+      const uint4 o = make_uint4(__float_as_uint(p[4 * q]), __float_as_uint(p[4 * q + 1]),
+                                 __float_as_uint(p[4 * q + 2]), __float_as_uint(p[4 * q + 3]));
+      const size_t boff = (el + 4 * q) * 4;
+      if (MODE == MODE_NVLS) {
+        multimem_st_v4(a.param.mc + boff, o);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k < world) st_peer_v4(a.param.p[wrap(rank + k, world)] + boff, o);
+      }
+    }
+    if (has_lowp) {
+      // bf16 shadow of the parameters for bf16-weight models: N bf16 = 2N bytes
+      uint32_t w[N / 2];
+#pragma unroll
+      for (int j = 0; j < N / 2; j++) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+        w[j] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      const size_t boff = el * 2;
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++) {
+        if (k < world) {
+          char* dst = a.lowp.p[wrap(rank + k, world)] + boff;
+          if constexpr (N == 8) st_peer_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
+          else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+        }
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+// ===========================================================================
+// Staged byte-wise collectives. Pattern: push/copy into staging -> barrier ->
+// consume from own staging -> trailing barrier (staging is reused next call).
+// ===========================================================================
+__global__ void __launch_bounds__(kThreads)
+k_allgather(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const size_t per = a.per;
+  for (size_t i = gtid(); i < a.nvec; i += gstride()) {
+    const uint4 v = user_load(a.in, i, a.nbytes, a.in_aligned);
+    const size_t off = ((size_t)rank * per + i) * 16;
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++)
+      if (k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + off, v);
+  }
+  rank_barrier(a.c, ++e);
+  const char* mine = a.buf.p[rank];
+  for (int r = 0; r < world; r++)
+    for (size_t i = gtid(); i < a.nvec; i += gstride())
+      user_store(a.out + (size_t)r * a.ustride, i, a.nbytes, a.out_aligned, ld_sys_v4(mine + ((size_t)r * per + i) * 16));
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_broadcast(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  if (rank == a.root) {
+    for (size_t i = gtid(); i < a.nvec; i += gstride()) {
+      const uint4 v = user_load(a.in, i, a.nbytes, a.in_aligned);
+      if (MODE == MODE_NVLS) {
+        multimem_st_v4(a.buf.mc + i * 16, v);
+      } else {
+#pragma unroll
+        for (int k = 1; k < kMaxRanks; k++)
+          if (k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + i * 16, v);
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (rank != a.root) {
+    const char* mine = a.buf.p[rank];
+    for (size_t i = gtid(); i < a.nvec; i += gstride())
+      user_store(a.out, i, a.nbytes, a.out_aligned, ld_sys_v4(mine + i * 16));
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_reduce_scatter(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const size_t per = a.per;
+  char* const mine = a.buf.p[rank];
+  for (int r = 0; r < world; r++)
+    for (size_t i = gtid(); i < a.nvec; i += gstride())
+      *reinterpret_cast<uint4*>(mine + ((size_t)r * per + i) * 16) =
+          user_load(a.in + (size_t)r * a.ustride, i, a.nbytes, a.in_aligned);
+  rank_barrier(a.c, ++e);
+  const bool do_scale = a.scale != 1.0f;
+  for (size_t i = gtid(); i < a.nvec; i += gstride()) {
+    uint4 v[kMaxRanks];
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++)
+      if (k < world) v[k] = ld_sys_v4(a.buf.p[k] + ((size_t)rank * per + i) * 16);
+    float acc[VecTraits<T>::N];
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++)
+      if (k < world) accum<T>(acc, v[k], a.op, k == 0);
+    if (do_scale) {
+#pragma unroll
+      for (int j = 0; j < VecTraits<T>::N; j++) acc[j] *= a.scale;
+    }
+    user_store(a.out, i, a.nbytes, a.out_aligned, VecTraits<T>::pack(acc));
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_reduce(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  char* const mine = a.buf.p[rank];
+  for (size_t i = gtid(); i < a.nvec; i += gstride())
+    *reinterpret_cast<uint4*>(mine + i * 16) = user_load(a.in, i, a.nbytes, a.in_aligned);
+  rank_barrier(a.c, ++e);
+  if (rank == a.root) {
+    const bool do_scale = a.scale != 1.0f;
+    for (size_t i = gtid(); i < a.nvec; i += gstride()) {
+      uint4 v[kMaxRanks];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++)
+        if (k < world) v[k] = ld_sys_v4(a.buf.p[k] + i * 16);
+      float acc[VecTraits<T>::N];
+#pragma unroll
+      for (int k = 0; k < kMaxRanks; k++)
+        if (k < world) accum<T>(acc, v[k], a.op, k == 0);
+      if (do_scale) {
+#pragma unroll
+        for (int j = 0; j < VecTraits<T>::N; j++) acc[j] *= a.scale;
+      }
+      user_store(a.out, i, a.nbytes, a.out_aligned, VecTraits<T>::pack(acc));
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_alltoall(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  const size_t per = a.per;
+  for (int k = 0; k < world; k++) {
+    const int dst = wrap(rank + k, world);
+    for (size_t i = gtid(); i < a.nvec; i += gstride())
+      st_peer_v4(a.buf.p[dst] + ((size_t)rank * per + i) * 16,
+                 user_load(a.in + (size_t)dst * a.ustride, i, a.nbytes, a.in_aligned));
+  }
+  rank_barrier(a.c, ++e);
+  const char* mine = a.buf.p[rank];
+  for (int r = 0; r < world; r++)
+    for (size_t i = gtid(); i < a.nvec; i += gstride())
+      user_store(a.out + (size_t)r * a.ustride, i, a.nbytes, a.out_aligned, ld_sys_v4(mine + ((size_t)r * per + i) * 16));
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_barrier(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+// --------------------------------------------------------- local helpers ----
+template <typename TI, typename TO>
+__global__ void k_scale_cast(const TI* __restrict__ in, TO* __restrict__ out, size_t n, float scale) {
+  for (size_t i = gtid(); i < n; i += gstride()) out[i] = static_cast<TO>(static_cast<float>(in[i]) * scale);
+}
+__global__ void k_fill_u32(uint32_t* p, uint32_t v, size_t n) {
+  for (size_t i = gtid(); i < n; i += gstride()) p[i] = v;
+}
+
+// ------------------------------------------------------------- launchers ----
+template <typename K>
+static cudaError_t go(K kernel, const Launch& l, const KArgs& a) {
+  dim3 grid(l.blocks, l.emu_world > 0 ? l.emu_world : 1, 1);
+  kernel<<<grid, kThreads, 0, l.stream>>>(a, l.emu_world > 0 ? l.emu_args : nullptr);
+  return cudaGetLastError();
+}
+
+#define DISPATCH_T(dtype, EXPR)                                   \
+  switch (dtype) {                                                \
+    case DT_F32: { using T = float; return EXPR; }                \
+    case DT_BF16: { using T = __nv_bfloat16; return EXPR; }       \
+    case DT_F16: { using T = __half; return EXPR; }               \
+    default: return cudaErrorInvalidValue;                        \
+  }
+
+cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype, int mode, bool staged) {
+  if (mode == MODE_NVLS) {
+    if (staged) DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_NVLS, true>, l, a))
+    DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_NVLS, false>, l, a))
+  }
+  if (staged) DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, true>, l, a))
+  DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, false>, l, a))
+}
+cudaError_t launch_allreduce_oneshot(const Launch& l, const KArgs& a, int dtype) {
+  DISPATCH_T(dtype, go(k_allreduce_oneshot<T>, l, a))
+}
+cudaError_t launch_allreduce_sgd(const Launch& l, const KArgs& a, int dtype, int mode) {
+  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_allreduce_sgd<T, MODE_NVLS>, l, a))
+  DISPATCH_T(dtype, go(k_allreduce_sgd<T, MODE_P2P>, l, a))
+}
+cudaError_t launch_allgather(const Launch& l, const KArgs& a) { return go(k_allgather, l, a); }
+cudaError_t launch_broadcast(const Launch& l, const KArgs& a, int mode) {
+  return mode == MODE_NVLS ? go(k_broadcast<MODE_NVLS>, l, a) : go(k_broadcast<MODE_P2P>, l, a);
+}
+cudaError_t launch_reduce_scatter(const Launch& l, const KArgs& a, int dtype) {
+  DISPATCH_T(dtype, go(k_reduce_scatter<T>, l, a))
+}
+cudaError_t launch_reduce(const Launch& l, const KArgs& a, int dtype) {
+  DISPATCH_T(dtype, go(k_reduce<T>, l, a))
+}
+cudaError_t launch_alltoall(const Launch& l, const KArgs& a) { return go(k_alltoall, l, a); }
+cudaError_t launch_barrier(const Launch& l, const KArgs& a) { return go(k_barrier, l, a); }
+
+template <typename TI>
+static cudaError_t scale_cast_out(cudaStream_t s, const void* in, void* out, int out_dt, size_t n, float scale) {
+  const int blocks = (int)((n + 1023) / 1024 < 1184 ? (n + 1023) / 1024 : 1184);
+  if (n == 0) return cudaSuccess;
+  switch (out_dt) {
+    case DT_F32: k_scale_cast<TI, float><<<blocks, 256, 0, s>>>((const TI*)in, (float*)out, n, scale); break;
+    case DT_BF16: k_scale_cast<TI, __nv_bfloat16><<<blocks, 256, 0, s>>>((const TI*)in, (__nv_bfloat16*)out, n, scale); break;
+    case DT_F16: k_scale_cast<TI, __half><<<blocks, 256, 0, s>>>((const TI*)in, (__half*)out, n, scale); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+cudaError_t launch_scale_cast(cudaStream_t s, const void* in, int in_dt, void* out, int out_dt, size_t n, float scale) {
+  switch (in_dt) {
+    case DT_F32: return scale_cast_out<float>(s, in, out, out_dt, n, scale);
+    case DT_BF16: return scale_cast_out<__nv_bfloat16>(s, in, out, out_dt, n, scale);
+    case DT_F16: return scale_cast_out<__half>(s, in, out, out_dt, n, scale);
+    default: return cudaErrorInvalidValue;
+  }
+}
+cudaError_t launch_fill_u32(cudaStream_t s, uint32_t* p, uint32_t v, size_t n) {
+  if (n == 0) return cudaSuccess;
+  k_fill_u32<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, s>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+}  // namespace b200mpi

@@ -1,0 +1,857 @@
+// b200mpi communicator: peer-memory windows (CUDA VMM + NVLS multicast, cudaIpc
+// fallback), algorithm selection, kernel launch plumbing and the C ABI.
+//
+// Reference parity: SURVEY.md §5.9 (B200-native replacement for the
+// Horovod -> NCCL data plane the reference launches but does not contain).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <string.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../include/b200mpi.h"
+#include "../kernels/kernels.h"
+#include "rendezvous.h"
+
+namespace b200mpi {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  if (getenv("B200MPI_DEBUG")) fprintf(stderr, "[b200mpi] error %d: %s\n", code, msg.c_str());
+  return code;
+}
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(B200MPI_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+  } while (0)
+
+// ---------------------------------------------------------------- driver ----
+struct Driver {
+  bool ok = false;
+#define DRV(name) decltype(&name) name##_ = nullptr
+  DRV(cuMemCreate); DRV(cuMemRelease); DRV(cuMemAddressReserve); DRV(cuMemAddressFree);
+  DRV(cuMemMap); DRV(cuMemUnmap); DRV(cuMemSetAccess); DRV(cuMemExportToShareableHandle);
+  DRV(cuMemImportFromShareableHandle); DRV(cuMemGetAllocationGranularity);
+  DRV(cuMulticastCreate); DRV(cuMulticastAddDevice); DRV(cuMulticastBindMem);
+  DRV(cuMulticastUnbind); DRV(cuMulticastGetGranularity); DRV(cuDeviceGetAttribute);
+  DRV(cuGetErrorString);
+#undef DRV
+};
+static Driver& driver() {
+  static Driver d;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFree(0);
+    bool all = true;
+#define LOAD(name)                                                                               \
+  do {                                                                                           \
+    void* fn = nullptr;                                                                          \
+    cudaDriverEntryPointQueryResult qr;                                                          \
+    if (cudaGetDriverEntryPoint(#name, &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn) {     \
+      all = false;                                                                               \
+      cudaGetLastError();                                                                        \
+    }                                                                                            \
+    d.name##_ = reinterpret_cast<decltype(&name)>(fn);                                           \
+  } while (0)
+    LOAD(cuMemCreate); LOAD(cuMemRelease); LOAD(cuMemAddressReserve); LOAD(cuMemAddressFree);
+    LOAD(cuMemMap); LOAD(cuMemUnmap); LOAD(cuMemSetAccess); LOAD(cuMemExportToShareableHandle);
+    LOAD(cuMemImportFromShareableHandle); LOAD(cuMemGetAllocationGranularity);
+    LOAD(cuMulticastCreate); LOAD(cuMulticastAddDevice); LOAD(cuMulticastBindMem);
+    LOAD(cuMulticastUnbind); LOAD(cuMulticastGetGranularity); LOAD(cuDeviceGetAttribute);
+    LOAD(cuGetErrorString);
+#undef LOAD
+    d.ok = all;
+  });
+  return d;
+}
+static std::string cu_err(CUresult r) {
+  const char* s = nullptr;
+  if (driver().cuGetErrorString_) driver().cuGetErrorString_(r, &s);
+  return s ? s : ("CUresult " + std::to_string((int)r));
+}
+#define CU_TRY(expr)                                                                 \
+  do {                                                                               \
+    CUresult _r = (expr);                                                            \
+    if (_r != CUDA_SUCCESS) return fail(B200MPI_ERR_CUDA, std::string(#expr) + ": " + cu_err(_r)); \
+  } while (0)
+
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+static size_t env_size(const char* name, size_t dflt) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  char* end = nullptr;
+  double x = strtod(v, &end);
+  if (end && (*end == 'k' || *end == 'K')) x *= 1024.0;
+  else if (end && (*end == 'm' || *end == 'M')) x *= 1024.0 * 1024.0;
+  else if (end && (*end == 'g' || *end == 'G')) x *= 1024.0 * 1024.0 * 1024.0;
+  return (size_t)x;
+}
+
+// ---------------------------------------------------------------- window ----
+struct Window {
+  bool live = false;
+  size_t bytes = 0;      // usable
+  size_t mapped = 0;     // rounded to granularity
+  bool vmm = false;
+  char* ptr[kMaxRanks] = {};                          // local VA of each rank's copy
+  CUmemGenericAllocationHandle h[kMaxRanks] = {};     // vmm handles (own + imported)
+  char* mc = nullptr;
+  CUmemGenericAllocationHandle mch = 0;
+};
+
+struct TraceRec { const char* op; size_t bytes; int algo; int blocks; uint64_t t_ns; };
+
+}  // namespace b200mpi
+
+using namespace b200mpi;
+
+struct b200mpi_comm {
+  int rank = 0, world = 1, device = 0;
+  bool local = false;       // emulated: `world` virtual ranks in this process
+  bool vmm = false;         // windows are VMM allocations (else cudaMalloc/cudaIpc)
+  bool multicast = false;
+  unsigned flags = 0;
+  Rendezvous rv;
+  std::vector<Window> wins;
+  int sig_win = -1, stage_win = -1;
+  uint32_t* epoch[kMaxRanks] = {};   // real mode: only [rank]
+  int* err_host = nullptr;           // pinned, mapped
+  int* err_dev = nullptr;
+  KArgs* emu_ring = nullptr;
+  int emu_slot = 0;
+  static constexpr int kEmuRing = 64;
+  // staging layout
+  size_t stage_bytes = 0, oneshot_region = 0, oneshot_cap_vecs = 0, twoshot_off = 0, twoshot_bytes = 0;
+  // tuning
+  size_t oneshot_max = 256 << 10;
+  size_t nvls_min = 0;
+  int max_blocks = 64;
+  int nvls_blocks = 32;
+  int timeout_ms = 30000;
+  std::atomic<uint64_t> launches{0};
+  bool trace_on = false;
+  std::vector<TraceRec> trace;
+  uint32_t next_tag = 1;
+};
+
+namespace b200mpi {
+
+static int emu_max_blocks(const b200mpi_comm* c) {
+  // all gridDim.x * world CTAs of an emulated launch must be co-resident (1 CTA/SM worst case)
+  int b = 132 / c->world;
+  return b < 1 ? 1 : b;
+}
+
+static DevComm dev_comm(b200mpi_comm* c, int r) {
+  DevComm d;
+  d.rank = r;
+  d.world = c->world;
+  for (int p = 0; p < kMaxRanks; p++) d.sig[p] = p < c->world ? reinterpret_cast<uint32_t*>(c->wins[c->sig_win].ptr[p]) : nullptr;
+  d.epoch = c->epoch[r];
+  d.err = c->err_dev;
+  d.timeout_ns = (unsigned long long)c->timeout_ms * 1000000ull;
+  return d;
+}
+
+static Win win_region(b200mpi_comm* c, int win, size_t off) {
+  Win w;
+  const Window& W = c->wins[win];
+  for (int p = 0; p < kMaxRanks; p++) w.p[p] = p < c->world ? W.ptr[p] + off : nullptr;
+  w.mc = W.mc ? W.mc + off : nullptr;
+  return w;
+}
+
+// Launch helper: real mode passes this rank's args by value; emulated mode
+// uploads `world` arg blocks into a device ring and launches gridDim.y=world.
+template <typename F>
+static int run(b200mpi_comm* c, cudaStream_t stream, int blocks, const char* opname, size_t bytes, int algo,
+               const std::vector<KArgs>& args, F&& launcher) {
+  Launch l;
+  l.stream = stream;
+  l.blocks = blocks;
+  l.emu_world = 0;
+  l.emu_args = nullptr;
+  if (c->local) {
+    blocks = std::min(blocks, emu_max_blocks(c));
+    l.blocks = blocks;
+    KArgs* slot = c->emu_ring + (size_t)c->emu_slot * kMaxRanks;
+    c->emu_slot = (c->emu_slot + 1) % b200mpi_comm::kEmuRing;
+    if (c->emu_slot == 0) CUDA_TRY(cudaStreamSynchronize(stream));  // ring wrap: stay safe
+    CUDA_TRY(cudaMemcpyAsync(slot, args.data(), sizeof(KArgs) * c->world, cudaMemcpyHostToDevice, stream));
+    l.emu_world = c->world;
+    l.emu_args = slot;
+  }
+  cudaError_t e = launcher(l, args[0]);
+  if (e != cudaSuccess) return fail(B200MPI_ERR_CUDA, std::string(opname) + " launch: " + cudaGetErrorString(e));
+  c->launches.fetch_add(1, std::memory_order_relaxed);
+  if (c->trace_on) c->trace.push_back(TraceRec{opname, bytes, algo, blocks, now_ns()});
+  return 0;
+}
+
+static int esize(int dt) { return dt == B200MPI_F32 ? 4 : 2; }
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------ window allocation ----
+static int window_alloc_local(b200mpi_comm* c, Window& W, size_t bytes) {
+  W.bytes = bytes;
+  W.mapped = round_up(bytes, 256);
+  W.vmm = false;
+  for (int r = 0; r < c->world; r++) {
+    void* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, W.mapped));
+    CUDA_TRY(cudaMemset(p, 0, W.mapped));
+    W.ptr[r] = (char*)p;
+  }
+  W.live = true;
+  return 0;
+}
+
+static int window_alloc_ipc(b200mpi_comm* c, Window& W, size_t bytes) {
+  W.bytes = bytes;
+  W.mapped = round_up(bytes, 2 << 20);
+  W.vmm = false;
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, W.mapped));
+  CUDA_TRY(cudaMemset(p, 0, W.mapped));
+  CUDA_TRY(cudaDeviceSynchronize());
+  W.ptr[c->rank] = (char*)p;
+  cudaIpcMemHandle_t mine;
+  CUDA_TRY(cudaIpcGetMemHandle(&mine, p));
+  std::vector<cudaIpcMemHandle_t> all(c->world);
+  std::string err;
+  if (c->rv.allgather(&mine, all.data(), sizeof(mine), c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+  for (int r = 0; r < c->world; r++) {
+    if (r == c->rank) continue;
+    void* q = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess));
+    W.ptr[r] = (char*)q;
+  }
+  W.live = true;
+  return 0;
+}
+
+static int window_alloc_vmm(b200mpi_comm* c, Window& W, size_t bytes, bool want_mc) {
+  Driver& d = driver();
+  std::string err;
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = c->device;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  CU_TRY(d.cuMemGetAllocationGranularity_(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  CUmulticastObjectProp mprop;
+  memset(&mprop, 0, sizeof(mprop));
+  if (want_mc) {
+    mprop.numDevices = c->world;
+    mprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    mprop.size = round_up(bytes, gran);
+    size_t mg = 0;
+    if (d.cuMulticastGetGranularity_(&mg, &mprop, CU_MULTICAST_GRANULARITY_MINIMUM) == CUDA_SUCCESS && mg > gran) gran = mg;
+  }
+  W.bytes = bytes;
+  W.mapped = round_up(bytes, gran);
+  W.vmm = true;
+  mprop.size = W.mapped;
+  const uint32_t tag = c->next_tag;
+  c->next_tag += 2;
+
+  CU_TRY(d.cuMemCreate_(&W.h[c->rank], W.mapped, &prop, 0));
+  int myfd = -1;
+  CU_TRY(d.cuMemExportToShareableHandle_(&myfd, W.h[c->rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
+  for (int r = 0; r < c->world; r++)
+    if (r != c->rank && c->rv.send_fd(r, tag, myfd, &err)) return fail(B200MPI_ERR_SYS, err);
+  for (int r = 0; r < c->world; r++) {
+    if (r == c->rank) continue;
+    int fd = -1;
+    if (c->rv.recv_fd(r, tag, c->timeout_ms, &fd, &err)) return fail(B200MPI_ERR_SYS, err);
+    CUresult cr = d.cuMemImportFromShareableHandle_(&W.h[r], (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+    close(fd);
+    if (cr != CUDA_SUCCESS) return fail(B200MPI_ERR_PEER, "import peer window: " + cu_err(cr));
+  }
+  if (c->rv.barrier(c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);  // everyone imported -> fds may close
+  close(myfd);
+
+  CUmemAccessDesc acc;
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = c->device;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  for (int r = 0; r < c->world; r++) {
+    CUdeviceptr va = 0;
+    CU_TRY(d.cuMemAddressReserve_(&va, W.mapped, gran, 0, 0));
+    CU_TRY(d.cuMemMap_(va, W.mapped, 0, W.h[r], 0));
+    CU_TRY(d.cuMemSetAccess_(va, W.mapped, &acc, 1));
+    W.ptr[r] = reinterpret_cast<char*>(va);
+  }
+  CUDA_TRY(cudaMemset(W.ptr[c->rank], 0, W.mapped));
+  CUDA_TRY(cudaDeviceSynchronize());
+
+  // NVLS: rank 0 creates the multicast object, everyone adds its device and binds its memory.
+  int mc_ok = want_mc ? 1 : 0;
+  if (want_mc) {
+    int mcfd = -1;
+    if (c->rank == 0) {
+      CUresult cr = d.cuMulticastCreate_(&W.mch, &mprop);
+      if (cr == CUDA_SUCCESS) cr = d.cuMemExportToShareableHandle_(&mcfd, W.mch, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+      if (cr != CUDA_SUCCESS) { mc_ok = 0; mcfd = -1; }
+    }
+    // rank 0 tells everyone whether creation worked before any fd is expected
+    int flag0 = mc_ok;
+    std::vector<int> flags(c->world);
+    if (c->rv.allgather(&flag0, flags.data(), sizeof(int), c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+    if (!flags[0]) mc_ok = 0;
+    if (mc_ok) {
+      if (c->rank == 0) {
+        for (int r = 1; r < c->world; r++)
+          if (c->rv.send_fd(r, tag + 1, mcfd, &err)) return fail(B200MPI_ERR_SYS, err);
+      } else {
+        int fd = -1;
+        if (c->rv.recv_fd(0, tag + 1, c->timeout_ms, &fd, &err)) return fail(B200MPI_ERR_SYS, err);
+        CUresult cr = d.cuMemImportFromShareableHandle_(&W.mch, (void*)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+        close(fd);
+        if (cr != CUDA_SUCCESS) mc_ok = 0;
+      }
+      if (mc_ok && d.cuMulticastAddDevice_(W.mch, c->device) != CUDA_SUCCESS) mc_ok = 0;
+    }
+    int mine = mc_ok;
+    if (c->rv.allgather(&mine, flags.data(), sizeof(int), c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+    if (c->rank == 0 && mcfd >= 0) close(mcfd);
+    for (int r = 0; r < c->world; r++) if (!flags[r]) mc_ok = 0;
+    if (mc_ok) {  // all devices added: bind + map
+      CUresult cr = d.cuMulticastBindMem_(W.mch, 0, W.h[c->rank], 0, W.mapped, 0);
+      CUdeviceptr va = 0;
+      if (cr == CUDA_SUCCESS) cr = d.cuMemAddressReserve_(&va, W.mapped, gran, 0, 0);
+      if (cr == CUDA_SUCCESS) cr = d.cuMemMap_(va, W.mapped, 0, W.mch, 0);
+      if (cr == CUDA_SUCCESS) cr = d.cuMemSetAccess_(va, W.mapped, &acc, 1);
+      if (cr == CUDA_SUCCESS) W.mc = reinterpret_cast<char*>(va);
+      else mc_ok = 0;
+    }
+    mine = mc_ok;
+    if (c->rv.allgather(&mine, flags.data(), sizeof(int), c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+    for (int r = 0; r < c->world; r++) if (!flags[r]) mc_ok = 0;
+    if (!mc_ok) W.mc = nullptr;  // (leaks the half-built object; harmless, freed at exit)
+  }
+  W.live = true;
+  return 0;
+}
+
+static int window_alloc(b200mpi_comm* c, size_t bytes, int* out) {
+  if (bytes == 0) return fail(B200MPI_ERR_INVALID, "window_alloc: zero bytes");
+  int id = -1;
+  for (size_t i = 0; i < c->wins.size(); i++) if (!c->wins[i].live) { id = (int)i; break; }
+  if (id < 0) { c->wins.emplace_back(); id = (int)c->wins.size() - 1; }
+  Window W;
+  int rc;
+  if (c->local) rc = window_alloc_local(c, W, bytes);
+  else if (c->vmm) rc = window_alloc_vmm(c, W, bytes, c->multicast);
+  else rc = window_alloc_ipc(c, W, bytes);
+  if (rc) return rc;
+  c->wins[id] = W;
+  *out = id;
+  return 0;
+}
+
+static void window_release(b200mpi_comm* c, Window& W) {
+  if (!W.live) return;
+  Driver& d = driver();
+  if (c->local) {
+    for (int r = 0; r < c->world; r++) if (W.ptr[r]) cudaFree(W.ptr[r]);
+  } else if (W.vmm) {
+    if (W.mc) {
+      d.cuMemUnmap_((CUdeviceptr)W.mc, W.mapped);
+      d.cuMemAddressFree_((CUdeviceptr)W.mc, W.mapped);
+      d.cuMulticastUnbind_(W.mch, c->device, 0, W.mapped);
+    }
+    if (W.mch) d.cuMemRelease_(W.mch);
+    for (int r = 0; r < c->world; r++) {
+      if (W.ptr[r]) { d.cuMemUnmap_((CUdeviceptr)W.ptr[r], W.mapped); d.cuMemAddressFree_((CUdeviceptr)W.ptr[r], W.mapped); }
+      if (W.h[r]) d.cuMemRelease_(W.h[r]);
+    }
+  } else {
+    for (int r = 0; r < c->world; r++) {
+      if (!W.ptr[r]) continue;
+      if (r == c->rank) cudaFree(W.ptr[r]);
+      else cudaIpcCloseMemHandle(W.ptr[r]);
+    }
+  }
+  W = Window();
+}
+
+// --------------------------------------------------------------- set-up ----
+static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
+  c->timeout_ms = env_int("B200MPI_TIMEOUT_MS", 30000);
+  c->oneshot_max = env_size("B200MPI_ONESHOT_MAX_BYTES", c->oneshot_max);
+  c->nvls_min = env_size("B200MPI_NVLS_MIN_BYTES", c->nvls_min);
+  c->max_blocks = std::min(env_int("B200MPI_MAX_BLOCKS", c->max_blocks), kMaxBlocks);
+  c->nvls_blocks = std::min(env_int("B200MPI_NVLS_BLOCKS", c->nvls_blocks), kMaxBlocks);
+  if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", (size_t)64 << 20);
+  // one-shot region: 2 parities x kOneshotBlocks CTAs x kMaxRanks slots x cap
+  c->oneshot_cap_vecs = 2048;  // 32 KiB per slot -> 1 MiB max one-shot payload
+  c->oneshot_region = (size_t)2 * kOneshotBlocks * kMaxRanks * c->oneshot_cap_vecs * 16;
+  if (staging_bytes < c->oneshot_region + ((size_t)4 << 20)) staging_bytes = c->oneshot_region + ((size_t)4 << 20);
+  c->stage_bytes = staging_bytes;
+  c->twoshot_off = c->oneshot_region;
+  c->twoshot_bytes = (staging_bytes - c->oneshot_region) / 4096 * 4096;
+  c->oneshot_max = std::min(c->oneshot_max, (size_t)kOneshotBlocks * c->oneshot_cap_vecs * 16);
+
+  CUDA_TRY(cudaHostAlloc((void**)&c->err_host, sizeof(int), cudaHostAllocMapped));
+  *c->err_host = 0;
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&c->err_dev, c->err_host, 0));
+  const int nlocal = c->local ? c->world : 1;
+  for (int i = 0; i < nlocal; i++) {
+    const int r = c->local ? i : c->rank;
+    CUDA_TRY(cudaMalloc((void**)&c->epoch[r], kEpochWords * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(c->epoch[r], 0, kEpochWords * sizeof(uint32_t)));
+  }
+  if (c->local) CUDA_TRY(cudaMalloc((void**)&c->emu_ring, sizeof(KArgs) * kMaxRanks * b200mpi_comm::kEmuRing));
+  int rc = window_alloc(c, kSigWords * sizeof(uint32_t), &c->sig_win);
+  if (rc) return rc;
+  rc = window_alloc(c, c->stage_bytes, &c->stage_win);
+  if (rc) return rc;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (!c->local) {
+    std::string err;
+    if (c->rv.barrier(c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+  }
+  return 0;
+}
+
+static int select_algo(b200mpi_comm* c, size_t bytes, int dtype, int op, bool symmetric) {
+  (void)symmetric;
+  if (bytes <= c->oneshot_max) return B200MPI_ALGO_ONESHOT;
+  const bool nvls_ok = c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32);
+  if (nvls_ok && bytes >= c->nvls_min) return B200MPI_ALGO_NVLS;
+  return B200MPI_ALGO_TWOSHOT;
+}
+
+static int blocks_for(b200mpi_comm* c, size_t vecs_per_rank, int per_thread, int cap) {
+  size_t b = (vecs_per_rank + (size_t)kThreads * per_thread - 1) / ((size_t)kThreads * per_thread);
+  if (b < 1) b = 1;
+  if (b > (size_t)cap) b = cap;
+  return (int)b;
+}
+
+// pointer argument helper: real mode -> the pointer itself; emulated -> ptrs[r]
+static const char* in_ptr(b200mpi_comm* c, const void* p, int r) {
+  return c->local ? reinterpret_cast<const char* const*>(p)[r] : reinterpret_cast<const char*>(p);
+}
+static char* out_ptr(b200mpi_comm* c, void* p, int r) {
+  return c->local ? reinterpret_cast<char* const*>(p)[r] : reinterpret_cast<char*>(p);
+}
+static std::vector<int> my_ranks(b200mpi_comm* c) {
+  std::vector<int> v;
+  if (c->local) for (int r = 0; r < c->world; r++) v.push_back(r);
+  else v.push_back(c->rank);
+  return v;
+}
+
+static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const void* in, void* out, size_t count,
+                        int dtype, int op, float scale, int algo, cudaStream_t stream) {
+  if (count == 0) return 0;
+  if (dtype < 0 || dtype > 2 || op < 0 || op > 2) return fail(B200MPI_ERR_INVALID, "allreduce: bad dtype/op");
+  const size_t nbytes = count * esize(dtype);
+  if (sym) {
+    if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return fail(B200MPI_ERR_INVALID, "allreduce_sym: bad window");
+    if (off % 16 || nbytes % 16 || off + nbytes > c->wins[win].bytes)
+      return fail(B200MPI_ERR_INVALID, "allreduce_sym: region must be 16-byte aligned/sized and inside the window");
+  }
+  if (algo == B200MPI_ALGO_AUTO) algo = select_algo(c, nbytes, dtype, op, sym);
+  if (algo == B200MPI_ALGO_NVLS && !(c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32))) algo = B200MPI_ALGO_TWOSHOT;
+  if (algo == B200MPI_ALGO_ONESHOT && nbytes > (size_t)kOneshotBlocks * c->oneshot_cap_vecs * 16) algo = B200MPI_ALGO_TWOSHOT;
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+
+  if (algo == B200MPI_ALGO_ONESHOT) {
+    const size_t nvec = (nbytes + 15) / 16;
+    int blocks = blocks_for(c, nvec, 1, kOneshotBlocks);
+    if (c->local) blocks = std::min(blocks, emu_max_blocks(c));
+    if ((nvec + blocks - 1) / blocks > c->oneshot_cap_vecs) return fail(B200MPI_ERR_INVALID, "oneshot: message exceeds slot capacity");
+    for (size_t k = 0; k < ranks.size(); k++) {
+      const int r = ranks[k];
+      KArgs& a = args[k];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, r);
+      a.buf = win_region(c, c->stage_win, 0);
+      a.in = sym ? c->wins[win].ptr[r] + off : in_ptr(c, in, r);
+      a.out = sym ? c->wins[win].ptr[r] + off : out_ptr(c, out, r);
+      a.nbytes = nbytes; a.nvec = nvec; a.per = c->oneshot_cap_vecs;
+      a.scale = scale; a.op = op;
+      a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
+    }
+    return run(c, stream, blocks, "allreduce", nbytes, algo, args,
+               [&](const Launch& l, const KArgs& a) { return launch_allreduce_oneshot(l, a, dtype); });
+  }
+
+  const int mode = algo == B200MPI_ALGO_NVLS ? MODE_NVLS : MODE_P2P;
+  const int cap = mode == MODE_NVLS ? c->nvls_blocks : c->max_blocks;
+  if (sym) {
+    const size_t nvec = nbytes / 16;
+    const size_t per = (nvec + c->world - 1) / c->world;
+    const int blocks = blocks_for(c, per, mode == MODE_NVLS ? 4 : 2, cap);
+    for (size_t k = 0; k < ranks.size(); k++) {
+      KArgs& a = args[k];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, ranks[k]);
+      a.buf = win_region(c, win, off);
+      a.nbytes = nbytes; a.nvec = nvec; a.per = per; a.scale = scale; a.op = op;
+    }
+    return run(c, stream, blocks, "allreduce", nbytes, algo, args,
+               [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, mode, false); });
+  }
+  // staged: chunk through the two-shot staging region
+  const size_t chunk_max = c->twoshot_bytes / 16 * 16;
+  for (size_t done = 0; done < nbytes; done += chunk_max) {
+    const size_t nb = std::min(chunk_max, nbytes - done);
+    const size_t nvec = (nb + 15) / 16;
+    const size_t per = (nvec + c->world - 1) / c->world;
+    const int blocks = blocks_for(c, per, mode == MODE_NVLS ? 4 : 2, cap);
+    for (size_t k = 0; k < ranks.size(); k++) {
+      const int r = ranks[k];
+      KArgs& a = args[k];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, r);
+      a.buf = win_region(c, c->stage_win, c->twoshot_off);
+      a.in = in_ptr(c, in, r) + done;
+      a.out = out_ptr(c, out, r) + done;
+      a.nbytes = nb; a.nvec = nvec; a.per = per; a.scale = scale; a.op = op;
+      a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
+    }
+    int rc = run(c, stream, blocks, "allreduce", nb, algo, args,
+                 [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, mode, true); });
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// generic staged op over a per-rank payload of `nbytes`, chunked so that
+// `slots` staging slots of the chunk fit the two-shot staging region.
+template <typename Fill, typename L>
+static int staged_op(b200mpi_comm* c, const char* name, size_t nbytes, int slots, cudaStream_t stream, Fill&& fill, L&& launcher) {
+  if (nbytes == 0) return 0;
+  const size_t chunk_max = (c->twoshot_bytes / slots) / 4096 * 4096;
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  for (size_t done = 0; done < nbytes; done += chunk_max) {
+    const size_t nb = std::min(chunk_max, nbytes - done);
+    const size_t nvec = (nb + 15) / 16;
+    const int blocks = blocks_for(c, nvec, 2, c->max_blocks);
+    for (size_t k = 0; k < ranks.size(); k++) {
+      KArgs& a = args[k];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, ranks[k]);
+      a.buf = win_region(c, c->stage_win, c->twoshot_off);
+      a.nbytes = nb; a.nvec = nvec; a.per = nvec; a.scale = 1.0f;
+      fill(a, ranks[k], done, nb);
+    }
+    int rc = run(c, stream, blocks, name, nb, 0, args, launcher);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace b200mpi
+
+// =============================================================== C ABI ====
+extern "C" {
+
+const char* b200mpi_last_error(void) { return g_err.c_str(); }
+const char* b200mpi_version(void) { return B200MPI_VERSION; }
+
+int b200mpi_comm_init(b200mpi_comm_t* out, int rank, int world, int device, const char* job_id,
+                      size_t staging_bytes, unsigned flags) {
+  if (!out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world) return fail(B200MPI_ERR_INVALID, "comm_init: bad rank/world (max 8 ranks per box)");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(0));
+  auto* c = new b200mpi_comm;
+  c->rank = rank; c->world = world; c->device = device; c->flags = flags;
+  std::string err;
+  const int timeout = env_int("B200MPI_TIMEOUT_MS", 30000);
+  if (c->rv.attach(job_id ? job_id : "default", rank, world, device, timeout, &err)) { delete c; return fail(B200MPI_ERR_SYS, err); }
+  // capability consensus: VMM fd export + multicast need every rank to agree
+  Driver& d = driver();
+  int caps[2] = {0, 0};
+  if (d.ok && !(flags & B200MPI_FLAG_FORCE_IPC) && !env_int("B200MPI_FORCE_IPC", 0)) {
+    int v = 0;
+    if (d.cuDeviceGetAttribute_(&v, CU_DEVICE_ATTRIBUTE_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR_SUPPORTED, device) == CUDA_SUCCESS && v) caps[0] = 1;
+    v = 0;
+    if (caps[0] && !(flags & B200MPI_FLAG_NO_MULTICAST) && !env_int("B200MPI_NO_MULTICAST", 0) &&
+        d.cuDeviceGetAttribute_(&v, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, device) == CUDA_SUCCESS && v) caps[1] = 1;
+  }
+  struct Cap { int vmm, mc, dev; } mine{caps[0], caps[1], device};
+  std::vector<Cap> all(world);
+  if (c->rv.allgather(&mine, all.data(), sizeof(Cap), timeout, &err)) { delete c; return fail(B200MPI_ERR_SYS, err); }
+  bool vmm = true, mc = world > 1;
+  std::set<int> devs;
+  for (auto& x : all) { vmm = vmm && x.vmm; mc = mc && x.mc; devs.insert(x.dev); }
+  if ((int)devs.size() != world) mc = false;  // ranks sharing a device: NVLS needs distinct devices
+  c->vmm = vmm;
+  c->multicast = vmm && mc;
+  for (auto& x : all) {
+    if (x.dev != device) {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, device, x.dev);
+      if (!can) { delete c; return fail(B200MPI_ERR_PEER, "no P2P access to device " + std::to_string(x.dev)); }
+    }
+  }
+  int rc = comm_finish_init(c, staging_bytes);
+  if (rc) { std::string keep = g_err; b200mpi_comm_destroy(c); g_err = keep; return rc; }
+  // multicast may have been demoted during window creation: agree on the final state
+  int have = (c->wins[c->stage_win].mc && c->wins[c->sig_win].mc) ? 1 : 0;
+  std::vector<int> haves(world);
+  if (c->rv.allgather(&have, haves.data(), sizeof(int), timeout, &err)) return fail(B200MPI_ERR_SYS, err);
+  for (int h : haves) if (!h) c->multicast = false;
+  if (getenv("B200MPI_DEBUG") && rank == 0)
+    fprintf(stderr, "[b200mpi] comm up: world=%d vmm=%d multicast(NVLS)=%d staging=%zu MiB\n", world, (int)c->vmm, (int)c->multicast, c->stage_bytes >> 20);
+  *out = c;
+  return 0;
+}
+
+int b200mpi_comm_init_local(b200mpi_comm_t* out, int world, int device, size_t staging_bytes, unsigned flags) {
+  if (!out || world < 1 || world > kMaxRanks) return fail(B200MPI_ERR_INVALID, "comm_init_local: bad world");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaFree(0));
+  auto* c = new b200mpi_comm;
+  c->rank = 0; c->world = world; c->device = device; c->flags = flags; c->local = true;
+  int rc = comm_finish_init(c, staging_bytes);
+  if (rc) { std::string keep = g_err; b200mpi_comm_destroy(c); g_err = keep; return rc; }
+  *out = c;
+  return 0;
+}
+
+int b200mpi_comm_destroy(b200mpi_comm_t c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (!c->local && c->rv.header()) { std::string err; c->rv.barrier(2000, &err); }
+  for (auto& W : c->wins) window_release(c, W);
+  for (int r = 0; r < kMaxRanks; r++) if (c->epoch[r]) cudaFree(c->epoch[r]);
+  if (c->emu_ring) cudaFree(c->emu_ring);
+  if (c->err_host) cudaFreeHost(c->err_host);
+  c->rv.detach(c->rank == 0);
+  delete c;
+  return 0;
+}
+
+int b200mpi_comm_rank(b200mpi_comm_t c) { return c->rank; }
+int b200mpi_comm_world(b200mpi_comm_t c) { return c->world; }
+int b200mpi_comm_is_local(b200mpi_comm_t c) { return c->local ? 1 : 0; }
+int b200mpi_comm_has_multicast(b200mpi_comm_t c) { return c->multicast ? 1 : 0; }
+uint64_t b200mpi_comm_launch_count(b200mpi_comm_t c) { return c->launches.load(); }
+int b200mpi_comm_check_error(b200mpi_comm_t c) {
+  int e = *(volatile int*)c->err_host;
+  if (e) { *c->err_host = 0; return fail(B200MPI_ERR_TIMEOUT, "device-side wait timed out waiting for rank " + std::to_string(e - 1)); }
+  return 0;
+}
+int b200mpi_comm_host_barrier(b200mpi_comm_t c) {
+  if (c->local) return 0;
+  std::string err;
+  if (c->rv.barrier(c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+  return 0;
+}
+int b200mpi_comm_host_allgather(b200mpi_comm_t c, const void* in, void* out, size_t bytes) {
+  if (c->local) { for (int r = 0; r < c->world; r++) memcpy((char*)out + r * bytes, in, bytes); return 0; }
+  std::string err;
+  if (c->rv.allgather(in, out, bytes, c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+  return 0;
+}
+
+int b200mpi_window_alloc(b200mpi_comm_t c, size_t bytes, int* win) { return window_alloc(c, bytes, win); }
+int b200mpi_window_free(b200mpi_comm_t c, int win) {
+  if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return fail(B200MPI_ERR_INVALID, "window_free: bad window");
+  cudaDeviceSynchronize();
+  if (!c->local) { std::string err; if (c->rv.barrier(c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err); }
+  window_release(c, c->wins[win]);
+  return 0;
+}
+void* b200mpi_window_ptr(b200mpi_comm_t c, int win, int rank) {
+  if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return nullptr;
+  if (rank < 0) rank = c->rank;
+  if (rank >= c->world) return nullptr;
+  return c->wins[win].ptr[rank];
+}
+void* b200mpi_window_mc_ptr(b200mpi_comm_t c, int win) {
+  if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return nullptr;
+  return c->wins[win].mc;
+}
+size_t b200mpi_window_size(b200mpi_comm_t c, int win) {
+  if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return 0;
+  return c->wins[win].bytes;
+}
+
+int b200mpi_allreduce_sym(b200mpi_comm_t c, int win, size_t offset, size_t count, b200mpi_dtype_t dtype,
+                          b200mpi_op_t op, float scale, b200mpi_algo_t algo, void* stream) {
+  return do_allreduce(c, true, win, offset, nullptr, nullptr, count, dtype, op, scale, algo, (cudaStream_t)stream);
+}
+int b200mpi_allreduce(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype,
+                      b200mpi_op_t op, float scale, b200mpi_algo_t algo, void* stream) {
+  return do_allreduce(c, false, -1, 0, in, out, count, dtype, op, scale, algo, (cudaStream_t)stream);
+}
+
+size_t b200mpi_slice_elems(size_t count, int world, b200mpi_dtype_t dtype) {
+  const size_t n = dtype == B200MPI_F32 ? 4 : 8;
+  const size_t nvec = (count + n - 1) / n;
+  return (nvec + world - 1) / world * n;
+}
+
+int b200mpi_allreduce_sgd_sym(b200mpi_comm_t c, int gwin, size_t goff, int pwin, size_t poff, int lwin, size_t loff,
+                              void* momentum, size_t count, b200mpi_dtype_t gdtype, float scale, float lr, float mu,
+                              float wd, int nesterov, int first_step, b200mpi_algo_t algo, void* stream) {
+  if (count == 0) return 0;
+  const size_t n = gdtype == B200MPI_F32 ? 4 : 8;
+  auto okwin = [&](int w) { return w >= 0 && w < (int)c->wins.size() && c->wins[w].live; };
+  if (!okwin(gwin) || !okwin(pwin) || (lwin >= 0 && !okwin(lwin))) return fail(B200MPI_ERR_INVALID, "allreduce_sgd: bad window");
+  if (count % n || goff % 16 || poff % 16 || (lwin >= 0 && loff % 16)) return fail(B200MPI_ERR_INVALID, "allreduce_sgd: count must be a multiple of the 16-byte vector and offsets 16-byte aligned");
+  if (goff + count * esize(gdtype) > c->wins[gwin].bytes || poff + count * 4 > c->wins[pwin].bytes) return fail(B200MPI_ERR_INVALID, "allreduce_sgd: region outside window");
+  int mode = MODE_P2P;
+  if (algo == B200MPI_ALGO_NVLS || (algo == B200MPI_ALGO_AUTO && c->multicast && count * esize(gdtype) >= c->nvls_min && count * esize(gdtype) > c->oneshot_max)) mode = MODE_NVLS;
+  if (mode == MODE_NVLS && !(c->multicast && c->wins[gwin].mc && c->wins[pwin].mc)) mode = MODE_P2P;
+  const size_t nvec = count / n, per = (nvec + c->world - 1) / c->world;
+  const int blocks = blocks_for(c, per, 1, mode == MODE_NVLS ? c->nvls_blocks : c->max_blocks);
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  for (size_t k = 0; k < ranks.size(); k++) {
+    const int r = ranks[k];
+    KArgs& a = args[k];
+    memset(&a, 0, sizeof(a));
+    a.c = dev_comm(c, r);
+    a.buf = win_region(c, gwin, goff);
+    a.param = win_region(c, pwin, poff);
+    if (lwin >= 0) a.lowp = win_region(c, lwin, loff);
+    a.mom = reinterpret_cast<float*>(c->local ? reinterpret_cast<void* const*>(momentum)[r] : momentum);
+    a.nbytes = count * esize(gdtype); a.nvec = nvec; a.per = per;
+    a.scale = scale; a.lr = lr; a.mu = mu; a.wd = wd; a.nesterov = nesterov; a.first_step = first_step;
+  }
+  return run(c, (cudaStream_t)stream, blocks, "allreduce_sgd", count * esize(gdtype), mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT, args,
+             [&](const Launch& l, const KArgs& a) { return launch_allreduce_sgd(l, a, gdtype, mode); });
+}
+
+int b200mpi_broadcast_bytes(b200mpi_comm_t c, void* buf, size_t bytes, int root, void* stream) {
+  if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "broadcast: bad root");
+  const int mode = c->multicast ? MODE_NVLS : MODE_P2P;
+  return staged_op(c, "broadcast", bytes, 1, (cudaStream_t)stream,
+                   [&](KArgs& a, int r, size_t done, size_t) {
+                     a.root = root;
+                     a.in = out_ptr(c, buf, r) + done; a.out = out_ptr(c, buf, r) + done;
+                     a.in_aligned = a.out_aligned = aligned16(a.in);
+                   },
+                   [&](const Launch& l, const KArgs& a) { return launch_broadcast(l, a, mode); });
+}
+int b200mpi_broadcast(b200mpi_comm_t c, void* buf, size_t count, b200mpi_dtype_t dtype, int root, void* stream) {
+  return b200mpi_broadcast_bytes(c, buf, count * esize(dtype), root, stream);
+}
+
+int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream) {
+  const size_t total = count * esize(dtype);
+  // chunks of the per-rank payload land at out + r*total + done
+  return staged_op(c, "allgather", total, c->world, (cudaStream_t)stream,
+                   [&](KArgs& a, int r, size_t done, size_t nb) {
+                     a.in = in_ptr(c, in, r) + done;
+                     a.out = out_ptr(c, out, r) + done;
+                     a.in_aligned = aligned16(a.in);
+                     a.out_aligned = aligned16(a.out) && (total % 16 == 0);
+                     a.ustride = total;
+                     (void)nb;
+                   },
+                   [&](const Launch& l, const KArgs& a) {
+                     return launch_allgather(l, a);
+                   });
+}
+
+int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype,
+                           b200mpi_op_t op, float scale, void* stream) {
+  const size_t total = count * esize(dtype);
+  return staged_op(c, "reduce_scatter", total, c->world, (cudaStream_t)stream,
+                   [&](KArgs& a, int r, size_t done, size_t) {
+                     a.in = in_ptr(c, in, r) + done; a.out = out_ptr(c, out, r) + done;
+                     a.in_aligned = aligned16(a.in) && (total % 16 == 0); a.out_aligned = aligned16(a.out);
+                     a.op = op; a.scale = scale; a.ustride = total;
+                   },
+                   [&](const Launch& l, const KArgs& a) { return launch_reduce_scatter(l, a, dtype); });
+}
+
+int b200mpi_reduce(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, b200mpi_op_t op,
+                   float scale, int root, void* stream) {
+  if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "reduce: bad root");
+  return staged_op(c, "reduce", count * esize(dtype), 1, (cudaStream_t)stream,
+                   [&](KArgs& a, int r, size_t done, size_t) {
+                     a.in = in_ptr(c, in, r) + done;
+                     a.out = (c->local || out) ? out_ptr(c, out, r) + done : nullptr;
+                     a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
+                     a.op = op; a.scale = scale; a.root = root;
+                   },
+                   [&](const Launch& l, const KArgs& a) { return launch_reduce(l, a, dtype); });
+}
+
+int b200mpi_alltoall(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream) {
+  const size_t total = count * esize(dtype);
+  return staged_op(c, "alltoall", total, c->world, (cudaStream_t)stream,
+                   [&](KArgs& a, int r, size_t done, size_t) {
+                     a.in = in_ptr(c, in, r) + done; a.out = out_ptr(c, out, r) + done;
+                     a.in_aligned = aligned16(a.in) && (total % 16 == 0);
+                     a.out_aligned = aligned16(a.out) && (total % 16 == 0);
+                     a.ustride = total;
+                   },
+                   [&](const Launch& l, const KArgs& a) { return launch_alltoall(l, a); });
+}
+
+int b200mpi_barrier(b200mpi_comm_t c, void* stream) {
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  for (size_t k = 0; k < ranks.size(); k++) { memset(&args[k], 0, sizeof(KArgs)); args[k].c = dev_comm(c, ranks[k]); }
+  return run(c, (cudaStream_t)stream, 1, "barrier", 0, 0, args, [&](const Launch& l, const KArgs& a) { return launch_barrier(l, a); });
+}
+
+int b200mpi_scale_cast(const void* in, b200mpi_dtype_t idt, void* out, b200mpi_dtype_t odt, size_t count, float scale, void* stream) {
+  cudaError_t e = launch_scale_cast((cudaStream_t)stream, in, idt, out, odt, count, scale);
+  if (e != cudaSuccess) return fail(B200MPI_ERR_CUDA, std::string("scale_cast: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+int b200mpi_set_tuning(b200mpi_comm_t c, size_t oneshot_max, size_t nvls_min, int max_blocks, int timeout_ms) {
+  if (oneshot_max != (size_t)-1) c->oneshot_max = std::min(oneshot_max, (size_t)kOneshotBlocks * c->oneshot_cap_vecs * 16);
+  if (nvls_min != (size_t)-1) c->nvls_min = nvls_min;
+  if (max_blocks > 0) { c->max_blocks = std::min(max_blocks, kMaxBlocks); c->nvls_blocks = std::min(max_blocks, kMaxBlocks); }
+  if (timeout_ms > 0) c->timeout_ms = timeout_ms;
+  return 0;
+}
+int b200mpi_get_tuning(b200mpi_comm_t c, size_t* oneshot_max, size_t* nvls_min, int* max_blocks, int* timeout_ms) {
+  if (oneshot_max) *oneshot_max = c->oneshot_max;
+  if (nvls_min) *nvls_min = c->nvls_min;
+  if (max_blocks) *max_blocks = c->max_blocks;
+  if (timeout_ms) *timeout_ms = c->timeout_ms;
+  return 0;
+}
+int b200mpi_select_algo(b200mpi_comm_t c, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op, int symmetric) {
+  return select_algo(c, bytes, dtype, op, symmetric != 0);
+}
+
+int b200mpi_trace_enable(b200mpi_comm_t c, int on) { c->trace_on = on != 0; return 0; }
+int b200mpi_trace_dump(b200mpi_comm_t c, const char* path) {
+  FILE* f = fopen(path, "a");
+  if (!f) return fail(B200MPI_ERR_SYS, std::string("trace_dump: cannot open ") + path);
+  static const char* algos[] = {"auto", "oneshot", "twoshot", "nvls"};
+  for (auto& t : c->trace)
+    fprintf(f, "{\"rank\": %d, \"op\": \"%s\", \"bytes\": %zu, \"algo\": \"%s\", \"blocks\": %d, \"t_ns\": %llu}\n", c->rank, t.op,
+            t.bytes, algos[t.algo & 3], t.blocks, (unsigned long long)t.t_ns);
+  fclose(f);
+  c->trace.clear();
+  return 0;
+}
+
+}  // extern "C"

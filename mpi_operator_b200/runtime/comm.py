@@ -1,0 +1,291 @@
+"""Python face of the b200mpi collective runtime.
+
+``Communicator`` wraps one ``b200mpi_comm_t``:
+
+* ``Communicator.from_env()`` — one process per GPU (ranks found through the
+  shm rendezvous; rank/world read from the launcher env, see
+  ``mpi_operator_b200.launch.env`` and SURVEY.md Appendix B).
+* ``Communicator.local(world)`` — ``world`` virtual ranks in this process on
+  one device (every collective is ONE launch with ``gridDim.y == world``);
+  used by unit tests, compute-sanitizer and ncu.
+
+Symmetric windows are exposed as zero-copy ``torch`` tensors, so gradients can
+be produced by autograd directly inside peer-visible memory.
+
+Reference parity: the reference has no data plane; this replaces the
+Horovod/NCCL calls its examples make (examples/v2beta1/horovod/
+tensorflow_mnist.py:90-159).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Union
+
+from . import _lib
+from ._lib import (ALGO_AUTO, ALGO_NAMES, ALGO_NVLS, ALGO_ONESHOT, ALGO_TWOSHOT, BF16, F16, F32, MAX, MIN, SUM,
+                   B200MPIError, check)
+
+_ALGOS = {"auto": ALGO_AUTO, "oneshot": ALGO_ONESHOT, "twoshot": ALGO_TWOSHOT, "nvls": ALGO_NVLS}
+_OPS = {"sum": SUM, "max": MAX, "min": MIN, "avg": SUM, "average": SUM}
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def dtype_code(dtype) -> int:
+    torch = _torch()
+    if dtype == torch.float32:
+        return F32
+    if dtype == torch.bfloat16:
+        return BF16
+    if dtype == torch.float16:
+        return F16
+    raise B200MPIError(f"unsupported dtype {dtype} (float32, bfloat16, float16)")
+
+
+def _esize(code: int) -> int:
+    return 4 if code == F32 else 2
+
+
+class _CudaBlob:
+    """Minimal ``__cuda_array_interface__`` carrier for a raw device pointer."""
+
+    def __init__(self, ptr: int, nbytes: int, owner):
+        self._owner = owner
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3, "strides": None,
+        }
+
+
+def _stream_ptr(stream) -> int:
+    torch = _torch()
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return int(stream.cuda_stream)
+
+
+def resolve_algo(algo: Union[str, int, None]) -> int:
+    if algo is None:
+        algo = os.environ.get("B200MPI_ALGO", "auto")
+    if isinstance(algo, str):
+        if algo not in _ALGOS:
+            raise B200MPIError(f"unknown algorithm {algo!r} (auto|oneshot|twoshot|nvls)")
+        return _ALGOS[algo]
+    return int(algo)
+
+
+class Window:
+    """A symmetric allocation: same size on every rank, all peers mapped."""
+
+    def __init__(self, comm: "Communicator", win: int, nbytes: int):
+        self.comm, self.id, self.nbytes = comm, win, nbytes
+
+    def ptr(self, rank: int = -1) -> int:
+        return int(_lib.lib().b200mpi_window_ptr(self.comm._h, self.id, rank) or 0)
+
+    @property
+    def has_multicast(self) -> bool:
+        return bool(_lib.lib().b200mpi_window_mc_ptr(self.comm._h, self.id))
+
+    def tensor(self, dtype=None, rank: int = -1, offset: int = 0, numel: Optional[int] = None):
+        """Zero-copy torch view of ``rank``'s copy (own copy by default)."""
+        torch = _torch()
+        dtype = dtype or torch.uint8
+        esz = torch.empty((), dtype=dtype).element_size()
+        if numel is None:
+            numel = (self.nbytes - offset) // esz
+        blob = _CudaBlob(self.ptr(rank) + offset, numel * esz, self)
+        t = torch.as_tensor(blob, device=torch.device("cuda", self.comm.device))
+        return t.view(dtype)
+
+    def free(self) -> None:
+        check(_lib.lib().b200mpi_window_free(self.comm._h, self.id), "window_free")
+
+
+class Communicator:
+    def __init__(self, handle: C.c_void_p, device: int):
+        self._h = handle
+        self.device = device
+        L = _lib.lib()
+        self.rank = L.b200mpi_comm_rank(handle)
+        self.world = L.b200mpi_comm_world(handle)
+        self.is_local = bool(L.b200mpi_comm_is_local(handle))
+        self.has_multicast = bool(L.b200mpi_comm_has_multicast(handle))
+        self._keep: list = []
+
+    # ------------------------------------------------------------ creation --
+    @classmethod
+    def create(cls, rank: int, world: int, device: int, job_id: str, staging_bytes: int = 0, flags: int = 0):
+        h = C.c_void_p()
+        check(_lib.lib().b200mpi_comm_init(C.byref(h), rank, world, device, job_id.encode(), staging_bytes, flags),
+              "comm_init")
+        return cls(h, device)
+
+    @classmethod
+    def from_env(cls, device: Optional[int] = None, staging_bytes: int = 0, flags: int = 0):
+        from ..launch.env import rank_info_from_env
+        info = rank_info_from_env()
+        if device is None:
+            device = info.local_rank
+        return cls.create(info.rank, info.world_size, device, info.job_id, staging_bytes, flags)
+
+    @classmethod
+    def local(cls, world: int, device: int = 0, staging_bytes: int = 0):
+        h = C.c_void_p()
+        check(_lib.lib().b200mpi_comm_init_local(C.byref(h), world, device, staging_bytes, 0), "comm_init_local")
+        return cls(h, device)
+
+    def destroy(self) -> None:
+        if self._h:
+            _lib.lib().b200mpi_comm_destroy(self._h)
+            self._h = None
+
+    # --------------------------------------------------------------- misc --
+    @property
+    def launch_count(self) -> int:
+        return int(_lib.lib().b200mpi_comm_launch_count(self._h))
+
+    def check_error(self) -> None:
+        check(_lib.lib().b200mpi_comm_check_error(self._h), "collective watchdog")
+
+    def host_barrier(self) -> None:
+        check(_lib.lib().b200mpi_comm_host_barrier(self._h), "host_barrier")
+
+    def host_allgather(self, payload: bytes) -> List[bytes]:
+        n = len(payload)
+        out = C.create_string_buffer(n * self.world)
+        check(_lib.lib().b200mpi_comm_host_allgather(self._h, payload, out, n), "host_allgather")
+        return [out.raw[i * n:(i + 1) * n] for i in range(self.world)]
+
+    def set_tuning(self, oneshot_max_bytes: int = -1, nvls_min_bytes: int = -1, max_blocks: int = 0,
+                   timeout_ms: int = 0) -> None:
+        as_sz = lambda v: C.c_size_t(-1).value if v < 0 else v  # noqa: E731
+        check(_lib.lib().b200mpi_set_tuning(self._h, as_sz(oneshot_max_bytes), as_sz(nvls_min_bytes), max_blocks,
+                                            timeout_ms))
+
+    def get_tuning(self) -> dict:
+        a, b, c_, d = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_int()
+        _lib.lib().b200mpi_get_tuning(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d))
+        return {"oneshot_max_bytes": a.value, "nvls_min_bytes": b.value, "max_blocks": c_.value, "timeout_ms": d.value}
+
+    def select_algo(self, nbytes: int, dtype_code_: int = F32, op: int = SUM, symmetric: bool = True) -> str:
+        return ALGO_NAMES[_lib.lib().b200mpi_select_algo(self._h, nbytes, dtype_code_, op, int(symmetric))]
+
+    def trace(self, on: bool = True) -> None:
+        _lib.lib().b200mpi_trace_enable(self._h, int(on))
+
+    def trace_dump(self, path: str) -> None:
+        check(_lib.lib().b200mpi_trace_dump(self._h, path.encode()), "trace_dump")
+
+    # ------------------------------------------------------------ windows --
+    def alloc_window(self, nbytes: int) -> Window:
+        w = C.c_int()
+        check(_lib.lib().b200mpi_window_alloc(self._h, nbytes, C.byref(w)), "window_alloc")
+        return Window(self, w.value, nbytes)
+
+    # -------------------------------------------------------- collectives --
+    def _ptrs(self, tensors):
+        """real mode: one tensor -> its pointer; emulated: list of world tensors -> void*[world]."""
+        if self.is_local:
+            if not isinstance(tensors, (list, tuple)) or len(tensors) != self.world:
+                raise B200MPIError("emulated communicator expects a list of `world` tensors")
+            arr = (C.c_void_p * self.world)(*[t.data_ptr() for t in tensors])
+            self._keep.append(arr)
+            if len(self._keep) > 256:
+                del self._keep[:128]
+            return C.cast(arr, C.c_void_p), tensors[0]
+        return C.c_void_p(tensors.data_ptr()), tensors
+
+    @staticmethod
+    def _scale(op: str, world: int, scale: Optional[float]) -> float:
+        s = 1.0 if scale is None else float(scale)
+        if op in ("avg", "average"):
+            s /= world
+        return s
+
+    def allreduce_window(self, win: Window, offset: int, count: int, dtype, op: str = "sum",
+                         scale: Optional[float] = None, algo=None, stream=None) -> None:
+        """In-place allreduce of a 16-byte aligned window region."""
+        check(_lib.lib().b200mpi_allreduce_sym(self._h, win.id, offset, count, dtype_code(dtype), _OPS[op],
+                                               self._scale(op, self.world, scale), resolve_algo(algo),
+                                               _stream_ptr(stream)), "allreduce_sym")
+
+    def allreduce(self, tensor, out=None, op: str = "sum", scale: Optional[float] = None, algo=None, stream=None):
+        """Allreduce on arbitrary contiguous CUDA tensors (in place when ``out`` is None)."""
+        out = tensor if out is None else out
+        pin, t0 = self._ptrs(tensor)
+        pout, _ = self._ptrs(out)
+        if not t0.is_contiguous():
+            raise B200MPIError("allreduce needs contiguous tensors")
+        check(_lib.lib().b200mpi_allreduce(self._h, pin, pout, t0.numel(), dtype_code(t0.dtype), _OPS[op],
+                                           self._scale(op, self.world, scale), resolve_algo(algo),
+                                           _stream_ptr(stream)), "allreduce")
+        return out
+
+    def allreduce_sgd_window(self, grad_win: Window, grad_off: int, param_win: Window, param_off: int, momentum,
+                             count: int, grad_dtype, lr: float, momentum_coef: float = 0.0, weight_decay: float = 0.0,
+                             nesterov: bool = False, first_step: bool = False, scale: Optional[float] = None,
+                             lowp_win: Optional[Window] = None, lowp_off: int = 0, algo=None, stream=None) -> None:
+        """Fused gradient-average + SGD step; see b200mpi_allreduce_sgd_sym."""
+        pm, _ = self._ptrs(momentum)
+        s = (1.0 / self.world) if scale is None else float(scale)
+        check(_lib.lib().b200mpi_allreduce_sgd_sym(
+            self._h, grad_win.id, grad_off, param_win.id, param_off, lowp_win.id if lowp_win else -1, lowp_off, pm,
+            count, dtype_code(grad_dtype), s, lr, momentum_coef, weight_decay, int(nesterov), int(first_step),
+            resolve_algo(algo), _stream_ptr(stream)), "allreduce_sgd_sym")
+
+    def slice_elems(self, count: int, dtype) -> int:
+        return int(_lib.lib().b200mpi_slice_elems(count, self.world, dtype_code(dtype)))
+
+    def broadcast(self, tensor, root: int = 0, stream=None):
+        p, t0 = self._ptrs(tensor)
+        check(_lib.lib().b200mpi_broadcast_bytes(self._h, p, t0.numel() * t0.element_size(), root,
+                                                 _stream_ptr(stream)), "broadcast")
+        return tensor
+
+    def allgather(self, tensor, out, stream=None):
+        pin, t0 = self._ptrs(tensor)
+        pout, _ = self._ptrs(out)
+        nbytes = t0.numel() * t0.element_size()
+        if nbytes % 2:
+            raise B200MPIError("allgather payload must be an even number of bytes")
+        # the kernel is byte-wise; express the payload in 2-byte units
+        check(_lib.lib().b200mpi_allgather(self._h, pin, pout, nbytes // 2, BF16, _stream_ptr(stream)), "allgather")
+        return out
+
+    def reduce_scatter(self, tensor, out, op: str = "sum", scale: Optional[float] = None, stream=None):
+        pin, _ = self._ptrs(tensor)
+        pout, o0 = self._ptrs(out)
+        check(_lib.lib().b200mpi_reduce_scatter(self._h, pin, pout, o0.numel(), dtype_code(o0.dtype), _OPS[op],
+                                                self._scale(op, self.world, scale), _stream_ptr(stream)),
+              "reduce_scatter")
+        return out
+
+    def reduce(self, tensor, out=None, root: int = 0, op: str = "sum", scale: Optional[float] = None, stream=None):
+        out = tensor if out is None else out
+        pin, t0 = self._ptrs(tensor)
+        pout, _ = self._ptrs(out)
+        check(_lib.lib().b200mpi_reduce(self._h, pin, pout, t0.numel(), dtype_code(t0.dtype), _OPS[op],
+                                        self._scale(op, self.world, scale), root, _stream_ptr(stream)), "reduce")
+        return out
+
+    def alltoall(self, tensor, out, stream=None):
+        pin, t0 = self._ptrs(tensor)
+        pout, _ = self._ptrs(out)
+        per = t0.numel() // self.world
+        check(_lib.lib().b200mpi_alltoall(self._h, pin, pout, per, dtype_code(t0.dtype), _stream_ptr(stream)),
+              "alltoall")
+        return out
+
+    def barrier(self, stream=None) -> None:
+        check(_lib.lib().b200mpi_barrier(self._h, _stream_ptr(stream)), "barrier")
+
+
+def scale_cast(src, dst, scale: float = 1.0, stream=None):
+    """dst = cast(src * scale) in one kernel (used by the bucketing engine)."""
+    check(_lib.lib().b200mpi_scale_cast(src.data_ptr(), dtype_code(src.dtype), dst.data_ptr(), dtype_code(dst.dtype),
+                                        src.numel(), scale, _stream_ptr(stream)), "scale_cast")
+    return dst

@@ -1,0 +1,26 @@
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a real CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: test needs >= 2 CUDA devices")
+
+
+def pytest_collection_modifyitems(config, items):
+    try:
+        import torch
+        ngpu = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:  # pragma: no cover
+        ngpu = 0
+    skip_gpu = pytest.mark.skip(reason="no CUDA device")
+    skip_multi = pytest.mark.skip(reason="needs >= 2 CUDA devices")
+    for item in items:
+        if "gpu" in item.keywords and ngpu == 0:
+            item.add_marker(skip_gpu)
+        if "multigpu" in item.keywords and ngpu < 2:
+            item.add_marker(skip_multi)

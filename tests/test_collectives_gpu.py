@@ -1,0 +1,206 @@
+"""Numerics of every b200mpi collective kernel against a plain PyTorch fp32
+reference, using the emulated communicator (world virtual ranks, ONE launch
+per collective with gridDim.y == world) so a single GPU exercises the real
+multi-rank kernels.  SURVEY.md §4 [NEW] GPU tier."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", params=[2, 4, 8])
+def comm(request):
+    from mpi_operator_b200.runtime.comm import Communicator
+    c = Communicator.local(request.param, device=0)
+    c.set_tuning(timeout_ms=5000)
+    yield c
+    c.destroy()
+
+
+def _rand(world, n, dtype, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return [torch.randn(n, device="cuda", dtype=torch.float32, generator=g).to(dtype) for _ in range(world)]
+
+
+def _ref(xs, op, scale=1.0):
+    st = torch.stack([x.float() for x in xs])
+    r = {"sum": st.sum(0), "avg": st.mean(0), "max": st.max(0).values, "min": st.min(0).values}[op]
+    return r * scale
+
+
+TOL = {torch.float32: (1e-5, 1e-5), torch.bfloat16: (2e-2, 2e-2), torch.float16: (2e-3, 2e-3)}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot"])
+@pytest.mark.parametrize("n", [1, 7, 1024, 4099, 65536 + 3])
+@pytest.mark.parametrize("op", ["sum", "avg", "max"])
+def test_allreduce_generic(comm, dtype, algo, n, op):
+    xs = _rand(comm.world, n, dtype, seed=n)
+    want = _ref(xs, op)
+    outs = [torch.empty_like(x) for x in xs]
+    comm.allreduce(xs, outs, op=op, algo=algo)
+    torch.cuda.synchronize()
+    comm.check_error()
+    rtol, atol = TOL[dtype]
+    for o in outs:
+        torch.testing.assert_close(o.float(), want.to(dtype).float(), rtol=rtol, atol=atol * max(1.0, comm.world / 2))
+    for o in outs[1:]:  # every rank must hold bit-identical results
+        assert torch.equal(o, outs[0])
+
+
+def test_allreduce_inplace_unaligned(comm):
+    base = [torch.randn(1000 + 3, device="cuda") for _ in range(comm.world)]
+    xs = [b[3:] for b in base]  # 12-byte offset: exercises the byte-wise slow path
+    want = _ref(xs, "sum")
+    comm.allreduce(xs, None if False else xs, op="sum", algo="twoshot")
+    torch.cuda.synchronize()
+    for x in xs:
+        torch.testing.assert_close(x, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("algo", ["oneshot", "twoshot", "auto"])
+def test_allreduce_window(comm, dtype, algo):
+    n = 1 << 18
+    esz = torch.empty((), dtype=dtype).element_size()
+    win = comm.alloc_window(n * esz + 4096)
+    views = [win.tensor(dtype, rank=r, offset=4096, numel=n) for r in range(comm.world)]
+    xs = _rand(comm.world, n, dtype, seed=3)
+    for v, x in zip(views, xs):
+        v.copy_(x)
+    want = _ref(xs, "avg")
+    comm.allreduce_window(win, 4096, n, dtype, op="avg", algo=algo)
+    torch.cuda.synchronize()
+    comm.check_error()
+    rtol, atol = TOL[dtype]
+    for v in views:
+        torch.testing.assert_close(v.float(), want.to(dtype).float(), rtol=rtol, atol=atol)
+        assert torch.equal(v, views[0])
+    win.free()
+
+
+def test_back_to_back_stress(comm):
+    """10^3 back-to-back small allreduces of random sizes must stay bit-exact
+    (flag/epoch reuse, one-shot slot double-buffering)."""
+    g = torch.Generator().manual_seed(1)
+    sizes = torch.randint(1, 5000, (300,), generator=g).tolist()
+    bufs = _rand(comm.world, 5000, torch.float32, seed=9)
+    ints = [(b * 8).round() for b in bufs]  # small integers: fp32 sums are exact in any order
+    for i, n in enumerate(sizes):
+        xs = [t[:n].clone() for t in ints]
+        want = torch.stack(xs).sum(0)
+        comm.allreduce(xs, xs, algo="oneshot" if i % 3 else "twoshot")
+        if i % 50 == 49:
+            torch.cuda.synchronize()
+        for x in xs:
+            assert torch.equal(x, want), f"iteration {i} n={n}"
+    torch.cuda.synchronize()
+    comm.check_error()
+
+
+def test_broadcast(comm):
+    for root in (0, comm.world - 1):
+        xs = _rand(comm.world, 10007, torch.float32, seed=root)
+        want = xs[root].clone()
+        comm.broadcast(xs, root=root)
+        torch.cuda.synchronize()
+        for x in xs:
+            assert torch.equal(x, want)
+
+
+def test_allgather(comm):
+    n = 3001
+    xs = _rand(comm.world, n, torch.bfloat16, seed=5)
+    outs = [torch.empty(comm.world * n, device="cuda", dtype=torch.bfloat16) for _ in range(comm.world)]
+    comm.allgather(xs, outs)
+    torch.cuda.synchronize()
+    want = torch.cat(xs)
+    for o in outs:
+        assert torch.equal(o, want)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_reduce_scatter(comm, dtype):
+    n = 2048 + 4
+    xs = _rand(comm.world, comm.world * n, dtype, seed=6)
+    outs = [torch.empty(n, device="cuda", dtype=dtype) for _ in range(comm.world)]
+    comm.reduce_scatter(xs, outs, op="sum")
+    torch.cuda.synchronize()
+    want = _ref(xs, "sum")
+    rtol, atol = TOL[dtype]
+    for r, o in enumerate(outs):
+        torch.testing.assert_close(o.float(), want[r * n:(r + 1) * n].to(dtype).float(), rtol=rtol, atol=atol * comm.world)
+
+
+def test_reduce_to_root(comm):
+    xs = _rand(comm.world, 5000, torch.float32, seed=7)
+    outs = [torch.zeros_like(x) for x in xs]
+    comm.reduce(xs, outs, root=1 % comm.world, op="sum")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(outs[1 % comm.world], _ref(xs, "sum"), rtol=1e-5, atol=1e-5)
+
+
+def test_alltoall(comm):
+    n = 513
+    xs = _rand(comm.world, comm.world * n, torch.float32, seed=8)
+    outs = [torch.empty_like(x) for x in xs]
+    comm.alltoall(xs, outs)
+    torch.cuda.synchronize()
+    for r in range(comm.world):
+        for s in range(comm.world):
+            assert torch.equal(outs[r][s * n:(s + 1) * n], xs[s][r * n:(r + 1) * n])
+
+
+def test_barrier_and_launch_count(comm):
+    before = comm.launch_count
+    comm.barrier()
+    comm.barrier()
+    torch.cuda.synchronize()
+    assert comm.launch_count == before + 2
+
+
+@pytest.mark.parametrize("gdtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_fused_allreduce_sgd(comm, gdtype, nesterov):
+    """Fused grad-average + SGD(momentum, wd) == torch.optim.SGD on the averaged gradient."""
+    n = 8 * 1000
+    W = comm.world
+    gesz = torch.empty((), dtype=gdtype).element_size()
+    gwin, pwin, lwin = comm.alloc_window(n * gesz), comm.alloc_window(n * 4), comm.alloc_window(n * 2)
+    p0 = torch.randn(n, device="cuda")
+    pv = [pwin.tensor(torch.float32, rank=r, numel=n) for r in range(W)]
+    gv = [gwin.tensor(gdtype, rank=r, numel=n) for r in range(W)]
+    lv = [lwin.tensor(torch.bfloat16, rank=r, numel=n) for r in range(W)]
+    for v in pv:
+        v.copy_(p0)
+    sl = comm.slice_elems(n, gdtype)
+    moms = [torch.zeros(sl, device="cuda") for _ in range(W)]
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([ref_p], lr=0.1, momentum=0.9, weight_decay=1e-4, nesterov=nesterov)
+    for step in range(3):
+        gs = _rand(W, n, gdtype, seed=100 + step)
+        for v, g in zip(gv, gs):
+            v.copy_(g)
+        ref_p.grad = torch.stack([g.float() for g in gs]).mean(0)
+        opt.step()
+        comm.allreduce_sgd_window(gwin, 0, pwin, 0, moms, n, gdtype, lr=0.1, momentum_coef=0.9, weight_decay=1e-4,
+                                  nesterov=nesterov, first_step=(step == 0), lowp_win=lwin, algo="twoshot")
+        torch.cuda.synchronize()
+        comm.check_error()
+        for v in pv:
+            torch.testing.assert_close(v, ref_p.data, rtol=1e-5, atol=1e-5)
+            assert torch.equal(v, pv[0])
+        for v in lv:
+            assert torch.equal(v, pv[0].to(torch.bfloat16))
+    for w in (gwin, pwin, lwin):
+        w.free()
+
+
+def test_scale_cast():
+    from mpi_operator_b200.runtime.comm import scale_cast
+    x = torch.randn(10001, device="cuda")
+    y = torch.empty(10001, device="cuda", dtype=torch.bfloat16)
+    scale_cast(x, y, 0.5)
+    torch.cuda.synchronize()
+    assert torch.equal(y, (x * 0.5).to(torch.bfloat16))
