@@ -17,9 +17,25 @@ from mpi_operator_b200.launch.env import rank_info_from_env  # noqa: E402
 from mpi_operator_b200.runtime.comm import Communicator  # noqa: E402
 
 
-def time_op(fn, iters, warmup, comm, flush=None):
-    for _ in range(warmup):
-        fn()
+def time_op(fn, iters, warmup, comm, flush=None, inner=1):
+    """Median/best device time of one call. `inner` back-to-back calls are captured
+    in a CUDA graph and replayed, so the number is device time, not Python/launch
+    overhead (all b200mpi kernels keep their epochs on the device and are capturable)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warmup):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    comm.host_barrier()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, capture_error_mode="thread_local"):
+        for _ in range(inner):
+            fn()
+    torch.cuda.synchronize()
+    comm.host_barrier()
+    g.replay()
     torch.cuda.synchronize()
     comm.host_barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
@@ -27,10 +43,10 @@ def time_op(fn, iters, warmup, comm, flush=None):
         if flush is not None:
             flush.add_(1.0)  # rewrite a >L2 buffer between timed iterations
         a.record()
-        fn()
+        g.replay()
         b.record()
     torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in ev)
+    ts = sorted(a.elapsed_time(b) / inner for a, b in ev)
     return ts[len(ts) // 2], ts[0]
 
 
@@ -78,9 +94,9 @@ def main():
                 algos["nccl"] = lambda: dist.all_reduce(t, op=dist.ReduceOp.AVG)
             iters = a.iters if size <= (64 << 20) else max(5, a.iters // 4)
             for name, fn in algos.items():
-                med, best = time_op(fn, iters, a.warmup, comm, flush)
+                inner = 20 if size <= (1 << 20) else (4 if size <= (32 << 20) else 1)
+                med, best = time_op(fn, iters, a.warmup, comm, flush, inner)
                 tt = torch.tensor([med, best], device="cuda", dtype=torch.float64)
-                allt = [bytes(8 * 2)] * W
                 got = comm.host_allgather(tt.cpu().numpy().tobytes())
                 import numpy as np
                 arr = np.frombuffer(b"".join(got), dtype=np.float64).reshape(W, 2)

@@ -147,6 +147,10 @@ int b200mpi_allreduce_sgd_sym(b200mpi_comm_t comm, int grad_win, size_t grad_off
                               float lr, float mu, float wd, int nesterov, int first_step,
                               b200mpi_algo_t algo, void* stream);
 size_t b200mpi_slice_elems(size_t count, int world, b200mpi_dtype_t dtype);
+/* Optional device-resident hyper-parameters {lr, momentum, weight_decay} (3 floats)
+ * read by the fused kernels instead of the by-value arguments: a captured CUDA
+ * graph then follows LR schedules without re-capture. NULL restores by-value. */
+int b200mpi_set_hyper_ptr(b200mpi_comm_t comm, const float* device_hyper);
 
 int b200mpi_broadcast(b200mpi_comm_t comm, void* buf, size_t count, b200mpi_dtype_t dtype,
                       int root, void* stream);

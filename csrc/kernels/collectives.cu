@@ -81,11 +81,21 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
   const size_t per = a.per, nvec = a.nvec;
   char* const mine = a.buf.p[rank];
 
+  // U consecutive blockDim-sized chunks per CTA per trip: the SAME index->CTA map
+  // in the copy-in, reduce and copy-out phases (partition invariant above).
+  constexpr int U = (MODE == MODE_NVLS) ? 4 : 2;
   if (STAGED) {
     for (int r = 0; r < world; r++) {
       const size_t base = (size_t)r * per;
-      for (size_t i = gtid(); i < per && base + i < nvec; i += gstride())
-        *reinterpret_cast<uint4*>(mine + (base + i) * 16) = user_load(a.in, base + i, a.nbytes, a.in_aligned);
+      const size_t lim = base < nvec ? (nvec - base < per ? nvec - base : per) : 0;
+      for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim)
+            *reinterpret_cast<uint4*>(mine + (base + i) * 16) = user_load(a.in, base + i, a.nbytes, a.in_aligned);
+        }
+      }
     }
   }
   rank_barrier(a.c, ++e);
@@ -96,7 +106,6 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
     const bool do_scale = a.scale != 1.0f;
     if (MODE == MODE_NVLS) {
       char* const mc = a.buf.mc + base * 16;
-      constexpr int U = 4;
       for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
         uint4 v[U];
 #pragma unroll
@@ -114,7 +123,6 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
       char* pp[kMaxRanks];
 #pragma unroll
       for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
-      constexpr int U = 2;
       for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
         uint4 v[U][kMaxRanks];
 #pragma unroll
@@ -150,8 +158,20 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
   if (STAGED) {
     for (int r = 0; r < world; r++) {
       const size_t base = (size_t)r * per;
-      for (size_t i = gtid(); i < per && base + i < nvec; i += gstride())
-        user_store(a.out, base + i, a.nbytes, a.out_aligned, ld_sys_v4(mine + (base + i) * 16));
+      const size_t lim = base < nvec ? (nvec - base < per ? nvec - base : per) : 0;
+      for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim) v[u] = ld_sys_v4(mine + (base + i) * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < lim) user_store(a.out, base + i, a.nbytes, a.out_aligned, v[u]);
+        }
+      }
     }
   }
   if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
@@ -236,6 +256,9 @@ k_allreduce_sgd(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu)
   for (int k = 0; k < kMaxRanks; k++) gp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
   const char* gmc = a.buf.mc ? a.buf.mc + base * 16 : nullptr;
   const bool has_lowp = a.lowp.p[0] != nullptr;
+  const float lr = a.hyper ? __ldg(a.hyper) : a.lr;
+  const float mu = a.hyper ? __ldg(a.hyper + 1) : a.mu;
+  const float wd = a.hyper ? __ldg(a.hyper + 2) : a.wd;
 
   for (size_t i = gtid(); i < lim; i += gstride()) {
     float g[N];
@@ -265,10 +288,10 @@ k_allreduce_sgd(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu)
     }
 #pragma unroll
     for (int j = 0; j < N; j++) {
-      float gj = g[j] * a.scale + a.wd * p[j];
-      float mj = a.first_step ? gj : a.mu * m[j] + gj;
+      float gj = g[j] * a.scale + wd * p[j];
+      float mj = a.first_step ? gj : mu * m[j] + gj;
       m[j] = mj;
-      p[j] -= a.lr * (a.nesterov ? gj + a.mu * mj : mj);
+      p[j] -= lr * (a.nesterov ? gj + mu * mj : mj);
     }
 #pragma unroll
     for (int q = 0; q < N / 4; q++) {

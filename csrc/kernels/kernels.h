@@ -27,6 +27,7 @@ struct KArgs {
   Win lowp;         // optional bf16 parameter shadow (p[0]==nullptr: absent)
   float* mom;       // this rank's momentum slice
   float lr, mu, wd;
+  const float* hyper;  // optional device {lr, mu, wd}: lets a captured CUDA graph follow LR schedules
   int nesterov;
   int first_step;
 };

@@ -147,6 +147,7 @@ struct b200mpi_comm {
   bool trace_on = false;
   std::vector<TraceRec> trace;
   uint32_t next_tag = 1;
+  const float* hyper = nullptr;
 };
 
 namespace b200mpi {
@@ -736,10 +737,13 @@ int b200mpi_allreduce_sgd_sym(b200mpi_comm_t c, int gwin, size_t goff, int pwin,
     a.mom = reinterpret_cast<float*>(c->local ? reinterpret_cast<void* const*>(momentum)[r] : momentum);
     a.nbytes = count * esize(gdtype); a.nvec = nvec; a.per = per;
     a.scale = scale; a.lr = lr; a.mu = mu; a.wd = wd; a.nesterov = nesterov; a.first_step = first_step;
+    a.hyper = c->hyper;
   }
   return run(c, (cudaStream_t)stream, blocks, "allreduce_sgd", count * esize(gdtype), mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT, args,
              [&](const Launch& l, const KArgs& a) { return launch_allreduce_sgd(l, a, gdtype, mode); });
 }
+
+int b200mpi_set_hyper_ptr(b200mpi_comm_t c, const float* p) { c->hyper = p; return 0; }
 
 int b200mpi_broadcast_bytes(b200mpi_comm_t c, void* buf, size_t bytes, int root, void* stream) {
   if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "broadcast: bad root");

@@ -1,0 +1,282 @@
+"""Data-parallel training engine over the b200mpi runtime.
+
+The reference's only parallelism strategy is synchronous data parallelism by
+delegation to Horovod (``hvd.DistributedOptimizer`` averaging
+gradients, ``BroadcastGlobalVariablesHook(0)``; examples/v2beta1/horovod/
+tensorflow_mnist.py:133,143).  Horovod's engine = negotiate -> pack ready
+tensors into a fusion buffer -> ncclAllReduce -> scale -> unpack -> optimizer.
+
+B200-first redesign:
+
+* parameters and gradients live *inside symmetric windows* (peer-mapped, NVLS
+  bound): autograd writes gradients straight into NVLink-visible memory, so
+  there is no fusion-buffer pack/unpack copy at all;
+* buckets are contiguous window regions in reverse-parameter order; when the
+  last gradient of a bucket lands, ONE kernel on the comm stream does
+  reduce-scatter + 1/N scale + weight-decay + momentum + parameter update +
+  all-gather of the *updated parameters* (``b200mpi_allreduce_sgd_sym``) —
+  no separate scale kernel, no optimizer kernel, momentum sharded 1/N;
+* the whole step (forward, backward, hooks, comm kernels) is captured once in
+  a CUDA graph and replayed: no per-step launch overhead, no tracing compiler.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+from typing import Callable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from ..runtime.comm import Communicator, Window
+
+
+def _align(n: int, a: int) -> int:
+    return (n + a - 1) // a * a
+
+
+@dataclass
+class Bucket:
+    index: int
+    start: int            # element offset in the flat buffers
+    numel: int            # padded to a multiple of 8 elements (16-byte vectors for fp32 and bf16)
+    params: List[nn.Parameter] = field(default_factory=list)
+    pending: int = 0
+    momentum: Optional[torch.Tensor] = None  # this rank's shard
+
+
+class FlatModelState:
+    """Re-homes a module's parameters and gradients into two symmetric windows
+    with identical element layout (fp32), bucketed in reverse registration order
+    (the order backward produces them)."""
+
+    def __init__(self, module: nn.Module, comm: Communicator, bucket_bytes: int = 32 << 20):
+        self.comm = comm
+        params = [p for p in module.parameters() if p.requires_grad]
+        if any(p.dtype != torch.float32 for p in params):
+            raise ValueError("FlatModelState expects fp32 master parameters (use autocast for bf16 compute)")
+        order = list(reversed(params))
+        self.buckets: List[Bucket] = []
+        self.param_slot = {}
+        off = 0
+        cur = Bucket(0, 0, 0)
+        cap = max(bucket_bytes // 4, 1)
+        for p in order:
+            n = _align(p.numel(), 4)  # keep every tensor 16-byte aligned
+            if cur.params and cur.numel + n > cap:
+                cur.numel = _align(cur.numel, 8)
+                off = cur.start + cur.numel
+                self.buckets.append(cur)
+                cur = Bucket(len(self.buckets), off, 0)
+            self.param_slot[p] = (cur.index, cur.start + cur.numel)
+            cur.params.append(p)
+            cur.numel += n
+        cur.numel = _align(cur.numel, 8)
+        self.buckets.append(cur)
+        self.total = cur.start + cur.numel
+        self.param_win: Window = comm.alloc_window(self.total * 4)
+        self.grad_win: Window = comm.alloc_window(self.total * 4)
+        self.flat_param = self.param_win.tensor(torch.float32, numel=self.total)
+        self.flat_grad = self.grad_win.tensor(torch.float32, numel=self.total)
+        self.flat_param.zero_()
+        self.flat_grad.zero_()
+        for p in params:
+            _, start = self.param_slot[p]
+            n = p.numel()
+            pv = self.flat_param[start:start + n].as_strided(p.size(), p.stride())
+            pv.copy_(p.data)
+            p.data = pv
+            p.grad = self.flat_grad[start:start + n].as_strided(p.size(), p.stride())
+        for b in self.buckets:
+            b.momentum = torch.zeros(comm.slice_elems(b.numel, torch.float32), device=self.flat_param.device)
+
+    def broadcast_parameters(self, root: int = 0) -> None:
+        """K3: rank-0 state to everyone (tensorflow_mnist.py:143)."""
+        if self.comm.world > 1:
+            self.comm.broadcast(self.flat_param, root=root)
+
+    def zero_grad(self) -> None:
+        self.flat_grad.zero_()
+
+
+class DataParallelTrainer:
+    """User-facing training loop object.
+
+    >>> trainer = DataParallelTrainer(model, loss_fn, comm, lr=0.1, momentum=0.9)
+    >>> loss = trainer.step(images_pinned_cpu, labels_pinned_cpu)   # returns a device scalar
+
+    ``step`` performs, every call: H2D copy of the batch (from the caller's
+    pinned host tensors), forward + backward under bf16 autocast, bucketed fused
+    allreduce+SGD on the comm stream overlapped with backward, and leaves the
+    loss on the device (``float(loss)`` is the D2H read).
+    """
+
+    def __init__(self, model: nn.Module, loss_fn: Callable, comm: Communicator, *, lr: float, momentum: float = 0.9,
+                 weight_decay: float = 0.0, nesterov: bool = False, bucket_bytes: Optional[int] = None,
+                 autocast_dtype: Optional[torch.dtype] = torch.bfloat16, channels_last: bool = True,
+                 cuda_graph: bool = True, fused_optimizer: bool = True, algo: Optional[str] = None,
+                 comm_backend: str = "b200mpi"):
+        self.comm = comm
+        self.device = torch.device("cuda", comm.device)
+        self.loss_fn = loss_fn
+        self.autocast_dtype = autocast_dtype
+        self.channels_last = channels_last
+        self.use_graph = cuda_graph
+        self.fused = fused_optimizer and comm_backend == "b200mpi"
+        self.algo = algo
+        self.backend = comm_backend  # "b200mpi" | "nccl" (baseline: stock NCCL via torch.distributed)
+        self.nesterov = nesterov
+        model = model.to(self.device)
+        if channels_last:
+            model = model.to(memory_format=torch.channels_last)
+        self.model = model
+        bucket_bytes = bucket_bytes or int(os.environ.get("B200MPI_BUCKET_BYTES", 32 << 20))
+        self.state = FlatModelState(model, comm, bucket_bytes)
+        self.state.broadcast_parameters(0)
+        # {lr, momentum, weight_decay} on the device: graph replays follow schedules
+        self.hyper = torch.tensor([lr, momentum, weight_decay], device=self.device, dtype=torch.float32)
+        comm.set_hyper(self.hyper)
+        self._lr, self._mu, self._wd = lr, momentum, weight_decay
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self._graph: Optional[torch.cuda.CUDAGraph] = None
+        self._static_x = self._static_y = None
+        self._loss = torch.zeros((), device=self.device)
+        self._launches_per_step = 0
+        self._sync = True
+        for b in self.state.buckets:
+            for p in b.params:
+                p.register_post_accumulate_grad_hook(self._make_hook(b))
+        if self.backend == "nccl":
+            import torch.distributed as dist
+            self._dist = dist
+        torch.cuda.synchronize(self.device)
+        if comm.world > 1:
+            comm.host_barrier()
+
+    # ---------------------------------------------------------- hyper --
+    def set_lr(self, lr: float) -> None:
+        self._lr = lr
+        self.hyper[0] = lr
+
+    @property
+    def launches_per_step(self) -> int:
+        return self._launches_per_step
+
+    # ---------------------------------------------------------- hooks --
+    def _make_hook(self, bucket: Bucket):
+        def hook(_param):
+            if not self._sync:
+                return
+            bucket.pending -= 1
+            if bucket.pending == 0:
+                self._reduce_bucket(bucket)
+        return hook
+
+    def _reduce_bucket(self, b: Bucket) -> None:
+        main = torch.cuda.current_stream(self.device)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.comm_stream.wait_event(ev)
+        st = self.state
+        with torch.cuda.stream(self.comm_stream):
+            if self.backend == "nccl":
+                g = st.flat_grad[b.start:b.start + b.numel]
+                if self.comm.world > 1:
+                    self._dist.all_reduce(g, op=self._dist.ReduceOp.AVG)
+            elif self.fused:
+                self.comm.allreduce_sgd_window(st.grad_win, b.start * 4, st.param_win, b.start * 4, b.momentum,
+                                               b.numel, torch.float32, lr=self._lr, momentum_coef=self._mu,
+                                               weight_decay=self._wd, nesterov=self.nesterov, algo=self.algo,
+                                               stream=self.comm_stream)
+            else:
+                self.comm.allreduce_window(st.grad_win, b.start * 4, b.numel, torch.float32, op="avg",
+                                           algo=self.algo, stream=self.comm_stream)
+        b.pending = -1  # fired
+
+    def _unfused_sgd(self) -> None:
+        """Plain flat SGD (used by the NCCL baseline and fused_optimizer=False)."""
+        st = self.state
+        if not hasattr(self, "_flat_mom"):
+            self._flat_mom = torch.zeros_like(st.flat_param)
+        g = st.flat_grad
+        if self._wd:
+            g = g.add(st.flat_param, alpha=self._wd)
+        self._flat_mom.mul_(self.hyper[1]).add_(g)
+        upd = g.add(self._flat_mom, alpha=self._mu) if self.nesterov else self._flat_mom
+        st.flat_param.sub_(upd * self.hyper[0])
+
+    # ----------------------------------------------------------- step --
+    def _fwd_bwd(self, x, y):
+        st = self.state
+        st.zero_grad()
+        for b in st.buckets:
+            b.pending = len(b.params)
+        if self.autocast_dtype is not None:
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                out = self.model(x)
+                loss = self.loss_fn(out, y)
+        else:
+            loss = self.loss_fn(self.model(x), y)
+        loss.backward()
+        for b in st.buckets:  # parameters that received no gradient this step
+            if b.pending != -1:
+                self._reduce_bucket(b)
+        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        if not self.fused:
+            self._unfused_sgd()
+        self._loss.copy_(loss.detach())
+
+    def _ensure_static(self, x, y):
+        if self._static_x is None or self._static_x.shape != x.shape:
+            self._static_x = torch.empty(x.shape, dtype=x.dtype, device=self.device)
+            if self.channels_last and x.dim() == 4:
+                self._static_x = self._static_x.contiguous(memory_format=torch.channels_last)
+            self._static_y = torch.empty(y.shape, dtype=y.dtype, device=self.device)
+            self._graph = None
+
+    def step(self, x, y):
+        """One optimizer step on a batch given as (pinned) host or device tensors."""
+        self._ensure_static(x, y)
+        self._static_x.copy_(x, non_blocking=True)
+        self._static_y.copy_(y, non_blocking=True)
+        if not self.use_graph:
+            n0 = self.comm.launch_count
+            self._fwd_bwd(self._static_x, self._static_y)
+            self._launches_per_step = self.comm.launch_count - n0
+            return self._loss
+        if self._graph is None:
+            self._capture()
+        self._graph.replay()
+        return self._loss
+
+    def _capture(self):
+        # warm up eagerly on a side stream (cuDNN autotune, allocator) before capture
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self._fwd_bwd(self._static_x, self._static_y)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
+        if self.comm.world > 1:
+            self.comm.host_barrier()
+        g = torch.cuda.CUDAGraph()
+        n0 = self.comm.launch_count
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self._fwd_bwd(self._static_x, self._static_y)
+        self._launches_per_step = self.comm.launch_count - n0
+        self._graph = g
+        torch.cuda.synchronize(self.device)
+        if self.comm.world > 1:
+            self.comm.host_barrier()
+
+    def no_sync(self):
+        trainer = self
+
+        class _Ctx:
+            def __enter__(self_inner):
+                trainer._sync = False
+
+            def __exit__(self_inner, *exc):
+                trainer._sync = True
+        return _Ctx()

@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.b200mpi_allreduce_sgd_sym.argtypes = [vp, i, sz, i, sz, i, sz, vp, sz, i, f, f, f, f, i, i, i, vp]
     L.b200mpi_slice_elems.argtypes = [sz, i, i]
     L.b200mpi_slice_elems.restype = sz
+    L.b200mpi_set_hyper_ptr.argtypes = [vp, vp]
     L.b200mpi_broadcast.argtypes = [vp, vp, sz, i, i, vp]
     L.b200mpi_broadcast_bytes.argtypes = [vp, vp, sz, i, vp]
     L.b200mpi_allgather.argtypes = [vp, vp, vp, sz, i, vp]

@@ -237,6 +237,11 @@ class Communicator:
             count, dtype_code(grad_dtype), s, lr, momentum_coef, weight_decay, int(nesterov), int(first_step),
             resolve_algo(algo), _stream_ptr(stream)), "allreduce_sgd_sym")
 
+    def set_hyper(self, tensor) -> None:
+        """Device tensor {lr, momentum, weight_decay} read by the fused SGD kernels (None: by-value)."""
+        self._hyper = tensor
+        check(_lib.lib().b200mpi_set_hyper_ptr(self._h, tensor.data_ptr() if tensor is not None else None))
+
     def slice_elems(self, count: int, dtype) -> int:
         return int(_lib.lib().b200mpi_slice_elems(count, self.world, dtype_code(dtype)))
 

@@ -204,3 +204,16 @@ def test_scale_cast():
     scale_cast(x, y, 0.5)
     torch.cuda.synchronize()
     assert torch.equal(y, (x * 0.5).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("n", [300007, 1 << 20])
+def test_allreduce_staged_many_blocks(comm, n):
+    """Regression: copy-in / reduce / copy-out phases must share one CTA->index map."""
+    xs = _rand(comm.world, n, torch.bfloat16, seed=n)
+    want = _ref(xs, "sum").to(torch.bfloat16)
+    comm.allreduce(xs, xs, op="sum", algo="twoshot")
+    torch.cuda.synchronize()
+    comm.check_error()
+    for x in xs:
+        torch.testing.assert_close(x.float(), want.float(), rtol=2e-2, atol=2e-2 * comm.world)
+        assert torch.equal(x, xs[0])
