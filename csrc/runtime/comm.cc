@@ -482,7 +482,12 @@ static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const vo
     const size_t nvec = (nbytes + 15) / 16;
     int blocks = blocks_for(c, nvec, 1, kOneshotBlocks);
     if (c->local) blocks = std::min(blocks, emu_max_blocks(c));
-    if ((nvec + blocks - 1) / blocks > c->oneshot_cap_vecs) return fail(B200MPI_ERR_INVALID, "oneshot: message exceeds slot capacity");
+    if ((nvec + blocks - 1) / blocks > c->oneshot_cap_vecs) algo = B200MPI_ALGO_TWOSHOT;  // does not fit the per-CTA slots
+  }
+  if (algo == B200MPI_ALGO_ONESHOT) {
+    const size_t nvec = (nbytes + 15) / 16;
+    int blocks = blocks_for(c, nvec, 1, kOneshotBlocks);
+    if (c->local) blocks = std::min(blocks, emu_max_blocks(c));
     for (size_t k = 0; k < ranks.size(); k++) {
       const int r = ranks[k];
       KArgs& a = args[k];
