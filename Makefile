@@ -17,8 +17,22 @@ $(LIBDIR)/libb200mpi.so: $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -x cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread
 
-native:
-	@true
+native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi
+
+$(BINDIR)/mpirun: csrc/spawner/mpirun.cc
+	@mkdir -p $(BINDIR)
+	$(CXX) $(CXXFLAGS) -o $@ $<
+	ln -sf mpirun $(BINDIR)/mpiexec
+	ln -sf mpirun $(BINDIR)/mpiexec.hydra
+	ln -sf mpirun $(BINDIR)/orterun
+
+$(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
+	@mkdir -p $(LIBDIR) mpi_operator_b200/include
+	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/runtime/rendezvous.cc -lrt -lpthread
+	cp csrc/mpi_shim/mpi.h mpi_operator_b200/include/mpi.h
+
+$(BINDIR)/pi: examples/pi/pi.cc $(LIBDIR)/libmpi.so
+	$(CXX) -std=c++17 -O2 -Impi_operator_b200/include -o $@ $< -L$(LIBDIR) -lmpi -Wl,-rpath,'$$ORIGIN/../lib'
 
 sass: $(LIBDIR)/libb200mpi.so
 	@mkdir -p profiles

@@ -1,0 +1,87 @@
+/*
+ * mpi.h — the MPI subset provided by libmpi (b200mpi shim).
+ *
+ * The reference's only native workload (examples/v2beta1/pi/pi.cc:19-52) needs
+ * MPI_Init / Comm_rank / Comm_size / Get_processor_name / Reduce / Barrier /
+ * Finalize; Horovod-style bootstraps add Bcast / Allreduce / Allgather
+ * (SURVEY.md §2.2).  Transport: the job's POSIX-shm rendezvous segment
+ * (csrc/runtime/rendezvous.h) — CPU path, no ssh, no network.
+ */
+#ifndef B200MPI_MPI_H_
+#define B200MPI_MPI_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR, count_; } MPI_Status;
+
+#define MPI_COMM_WORLD 0
+#define MPI_COMM_SELF 1
+#define MPI_COMM_NULL (-1)
+
+#define MPI_SUCCESS 0
+#define MPI_ERR_OTHER 15
+#define MPI_ERR_ARG 12
+#define MPI_ERR_COMM 5
+#define MPI_ERR_TYPE 3
+#define MPI_ERR_OP 9
+
+#define MPI_MAX_PROCESSOR_NAME 256
+#define MPI_MAX_ERROR_STRING 256
+#define MPI_IN_PLACE ((void*)1)
+#define MPI_STATUS_IGNORE ((MPI_Status*)0)
+#define MPI_ANY_SOURCE (-1)
+#define MPI_ANY_TAG (-1)
+
+enum {
+  MPI_CHAR = 1, MPI_SIGNED_CHAR, MPI_UNSIGNED_CHAR, MPI_BYTE, MPI_SHORT, MPI_UNSIGNED_SHORT, MPI_INT, MPI_UNSIGNED,
+  MPI_LONG, MPI_UNSIGNED_LONG, MPI_LONG_LONG, MPI_UNSIGNED_LONG_LONG, MPI_FLOAT, MPI_DOUBLE, MPI_INT32_T, MPI_INT64_T,
+  MPI_UINT32_T, MPI_UINT64_T, MPI_C_BOOL
+};
+#define MPI_LONG_LONG_INT MPI_LONG_LONG
+enum { MPI_SUM = 1, MPI_MAX, MPI_MIN, MPI_PROD, MPI_LAND, MPI_LOR, MPI_BAND, MPI_BOR };
+
+#define MPI_THREAD_SINGLE 0
+#define MPI_THREAD_FUNNELED 1
+#define MPI_THREAD_SERIALIZED 2
+#define MPI_THREAD_MULTIPLE 3
+
+int MPI_Init(int* argc, char*** argv);
+int MPI_Init_thread(int* argc, char*** argv, int required, int* provided);
+int MPI_Initialized(int* flag);
+int MPI_Finalized(int* flag);
+int MPI_Finalize(void);
+int MPI_Abort(MPI_Comm comm, int errorcode);
+int MPI_Comm_rank(MPI_Comm comm, int* rank);
+int MPI_Comm_size(MPI_Comm comm, int* size);
+int MPI_Comm_dup(MPI_Comm comm, MPI_Comm* newcomm);
+int MPI_Comm_free(MPI_Comm* comm);
+int MPI_Get_processor_name(char* name, int* resultlen);
+int MPI_Get_version(int* version, int* subversion);
+int MPI_Get_library_version(char* version, int* resultlen);
+int MPI_Type_size(MPI_Datatype datatype, int* size);
+int MPI_Error_string(int errorcode, char* string, int* resultlen);
+double MPI_Wtime(void);
+double MPI_Wtick(void);
+
+int MPI_Barrier(MPI_Comm comm);
+int MPI_Bcast(void* buffer, int count, MPI_Datatype datatype, int root, MPI_Comm comm);
+int MPI_Reduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, int root, MPI_Comm comm);
+int MPI_Allreduce(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm);
+int MPI_Allgather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                  MPI_Datatype recvtype, MPI_Comm comm);
+int MPI_Gather(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+               MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Scatter(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Alltoall(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                 MPI_Datatype recvtype, MPI_Comm comm);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200MPI_MPI_H_ */

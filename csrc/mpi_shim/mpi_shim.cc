@@ -1,0 +1,249 @@
+// libmpi (b200mpi shim): the MPI subset of mpi.h over the shm rendezvous.
+// Every collective is built from one primitive — a chunked allgather through
+// the per-rank mailboxes of the segment — which is plenty for CPU control
+// traffic (pi's 8-byte MPI_Reduce, Horovod-style bootstrap exchanges).
+#include "mpi.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../runtime/rendezvous.h"
+
+using b200mpi::Rendezvous;
+
+namespace {
+Rendezvous* g_rv = nullptr;
+int g_rank = 0, g_size = 1;
+bool g_init = false, g_final = false;
+int g_timeout_ms = 60000;
+
+int env_first(std::initializer_list<const char*> names, int dflt) {
+  for (const char* n : names) {
+    const char* v = getenv(n);
+    if (v && *v) return atoi(v);
+  }
+  return dflt;
+}
+
+int fail(const std::string& what) {
+  fprintf(stderr, "[libmpi b200mpi rank %d] %s\n", g_rank, what.c_str());
+  return MPI_ERR_OTHER;
+}
+
+size_t type_size(MPI_Datatype t) {
+  switch (t) {
+    case MPI_CHAR: case MPI_SIGNED_CHAR: case MPI_UNSIGNED_CHAR: case MPI_BYTE: case MPI_C_BOOL: return 1;
+    case MPI_SHORT: case MPI_UNSIGNED_SHORT: return 2;
+    case MPI_INT: case MPI_UNSIGNED: case MPI_FLOAT: case MPI_INT32_T: case MPI_UINT32_T: return 4;
+    case MPI_LONG: case MPI_UNSIGNED_LONG: case MPI_LONG_LONG: case MPI_UNSIGNED_LONG_LONG: case MPI_DOUBLE:
+    case MPI_INT64_T: case MPI_UINT64_T: return 8;
+    default: return 0;
+  }
+}
+
+template <typename T>
+void combine(T* acc, const T* x, size_t n, MPI_Op op) {
+  for (size_t i = 0; i < n; i++) {
+    switch (op) {
+      case MPI_SUM: acc[i] = acc[i] + x[i]; break;
+      case MPI_PROD: acc[i] = acc[i] * x[i]; break;
+      case MPI_MAX: acc[i] = std::max(acc[i], x[i]); break;
+      case MPI_MIN: acc[i] = std::min(acc[i], x[i]); break;
+      case MPI_LAND: acc[i] = (T)(acc[i] && x[i]); break;
+      case MPI_LOR: acc[i] = (T)(acc[i] || x[i]); break;
+      default: break;
+    }
+  }
+}
+template <typename T>
+void combine_bits(T* acc, const T* x, size_t n, MPI_Op op) {
+  for (size_t i = 0; i < n; i++) acc[i] = op == MPI_BAND ? (T)(acc[i] & x[i]) : (T)(acc[i] | x[i]);
+}
+
+bool reduce_into(void* acc, const void* x, size_t n, MPI_Datatype t, MPI_Op op) {
+#define CASE(MT, CT) case MT: if (op == MPI_BAND || op == MPI_BOR) combine_bits((CT*)acc, (const CT*)x, n, op); else combine((CT*)acc, (const CT*)x, n, op); return true;
+#define CASEF(MT, CT) case MT: if (op == MPI_BAND || op == MPI_BOR) return false; combine((CT*)acc, (const CT*)x, n, op); return true;
+  switch (t) {
+    CASE(MPI_CHAR, char) CASE(MPI_SIGNED_CHAR, signed char) CASE(MPI_UNSIGNED_CHAR, unsigned char) CASE(MPI_BYTE, unsigned char)
+    CASE(MPI_C_BOOL, unsigned char) CASE(MPI_SHORT, short) CASE(MPI_UNSIGNED_SHORT, unsigned short) CASE(MPI_INT, int)
+    CASE(MPI_INT32_T, int) CASE(MPI_UNSIGNED, unsigned) CASE(MPI_UINT32_T, unsigned) CASE(MPI_LONG, long)
+    CASE(MPI_UNSIGNED_LONG, unsigned long) CASE(MPI_LONG_LONG, long long) CASE(MPI_INT64_T, long long)
+    CASE(MPI_UNSIGNED_LONG_LONG, unsigned long long) CASE(MPI_UINT64_T, unsigned long long)
+    CASEF(MPI_FLOAT, float) CASEF(MPI_DOUBLE, double)
+    default: return false;
+  }
+#undef CASE
+#undef CASEF
+}
+
+// out[r*bytes .. ] = rank r's `in` (bytes each), any size, chunked through the mailboxes
+int allgather_bytes(const void* in, void* out, size_t bytes) {
+  if (g_size == 1) { if (out != in) memmove(out, in, bytes); return MPI_SUCCESS; }
+  std::string err;
+  const size_t chunk = b200mpi::kRvMailbox;
+  std::vector<unsigned char> tmp(chunk * g_size);
+  for (size_t done = 0; done < bytes || (bytes == 0 && done == 0); done += chunk) {
+    const size_t n = std::min(chunk, bytes - done);
+    if (g_rv->allgather((const char*)in + done, tmp.data(), n, g_timeout_ms, &err)) return fail(err);
+    for (int r = 0; r < g_size; r++) memcpy((char*)out + (size_t)r * bytes + done, tmp.data() + (size_t)r * n, n);
+    if (bytes == 0) break;
+  }
+  return MPI_SUCCESS;
+}
+
+int check(MPI_Comm c) {
+  if (!g_init || g_final) return fail("MPI call outside MPI_Init/MPI_Finalize");
+  if (c != MPI_COMM_WORLD && c != MPI_COMM_SELF) return MPI_ERR_COMM;
+  return MPI_SUCCESS;
+}
+}  // namespace
+
+extern "C" {
+
+int MPI_Init(int*, char***) {
+  if (g_init) return MPI_SUCCESS;
+  g_rank = env_first({"B200MPI_RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "RANK"}, 0);
+  g_size = env_first({"B200MPI_WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE"}, 1);
+  g_timeout_ms = env_first({"B200MPI_TIMEOUT_MS"}, 60000);
+  if (g_size > 1) {
+    const char* job = getenv("B200MPI_JOB_ID");
+    std::string id = std::string("mpi-") + (job && *job ? job : "default");
+    g_rv = new Rendezvous;
+    std::string err;
+    if (g_rv->attach(id, g_rank, g_size, -1, g_timeout_ms, &err)) { fail("MPI_Init: " + err); return MPI_ERR_OTHER; }
+  }
+  g_init = true;
+  return MPI_SUCCESS;
+}
+int MPI_Init_thread(int* a, char*** b, int required, int* provided) {
+  if (provided) *provided = required < MPI_THREAD_SERIALIZED ? required : MPI_THREAD_SERIALIZED;
+  return MPI_Init(a, b);
+}
+int MPI_Initialized(int* f) { *f = g_init; return MPI_SUCCESS; }
+int MPI_Finalized(int* f) { *f = g_final; return MPI_SUCCESS; }
+int MPI_Finalize(void) {
+  if (!g_init || g_final) return MPI_SUCCESS;
+  if (g_rv) {
+    std::string err;
+    g_rv->barrier(g_timeout_ms, &err);
+    g_rv->detach(g_rank == 0);
+    delete g_rv;
+    g_rv = nullptr;
+  }
+  g_final = true;
+  return MPI_SUCCESS;
+}
+int MPI_Abort(MPI_Comm, int code) {
+  if (g_rv) g_rv->set_abort();
+  fprintf(stderr, "[libmpi b200mpi rank %d] MPI_Abort(%d)\n", g_rank, code);
+  _exit(code ? code : 1);
+}
+int MPI_Comm_rank(MPI_Comm c, int* r) { int e = check(c); if (e) return e; *r = c == MPI_COMM_SELF ? 0 : g_rank; return MPI_SUCCESS; }
+int MPI_Comm_size(MPI_Comm c, int* s) { int e = check(c); if (e) return e; *s = c == MPI_COMM_SELF ? 1 : g_size; return MPI_SUCCESS; }
+int MPI_Comm_dup(MPI_Comm c, MPI_Comm* n) { *n = c; return MPI_SUCCESS; }
+int MPI_Comm_free(MPI_Comm* c) { *c = MPI_COMM_NULL; return MPI_SUCCESS; }
+int MPI_Get_processor_name(char* name, int* len) {
+  const char* h = getenv("B200MPI_HOSTNAME");
+  char buf[MPI_MAX_PROCESSOR_NAME];
+  if (!h || !*h) { gethostname(buf, sizeof(buf)); buf[sizeof(buf) - 1] = 0; h = buf; }
+  strncpy(name, h, MPI_MAX_PROCESSOR_NAME - 1);
+  name[MPI_MAX_PROCESSOR_NAME - 1] = 0;
+  *len = (int)strlen(name);
+  return MPI_SUCCESS;
+}
+int MPI_Get_version(int* v, int* s) { *v = 3; *s = 1; return MPI_SUCCESS; }
+int MPI_Get_library_version(char* v, int* len) {
+  *len = snprintf(v, 256, "b200mpi libmpi shim 0.1.0 (shm rendezvous transport)");
+  return MPI_SUCCESS;
+}
+int MPI_Type_size(MPI_Datatype t, int* s) { *s = (int)type_size(t); return *s ? MPI_SUCCESS : MPI_ERR_TYPE; }
+int MPI_Error_string(int code, char* s, int* len) { *len = snprintf(s, MPI_MAX_ERROR_STRING, "MPI error %d", code); return MPI_SUCCESS; }
+double MPI_Wtime(void) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
+double MPI_Wtick(void) { return 1e-9; }
+
+int MPI_Barrier(MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  if (c == MPI_COMM_SELF || g_size == 1) return MPI_SUCCESS;
+  std::string err;
+  if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+  return MPI_SUCCESS;
+}
+int MPI_Bcast(void* buf, int count, MPI_Datatype t, int root, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  if (c == MPI_COMM_SELF || g_size == 1) return MPI_SUCCESS;
+  const size_t es = type_size(t);
+  if (!es) return MPI_ERR_TYPE;
+  std::string err;
+  if (g_rv->bcast(buf, es * count, root, g_timeout_ms, &err)) return fail(err);
+  return MPI_SUCCESS;
+}
+static int reduce_impl(const void* send, void* recv, int count, MPI_Datatype t, MPI_Op op, int root, bool all) {
+  const size_t es = type_size(t);
+  if (!es) return MPI_ERR_TYPE;
+  const size_t bytes = es * (size_t)count;
+  const void* mine = send == MPI_IN_PLACE ? recv : send;
+  std::vector<unsigned char> gathered(bytes * g_size);
+  int e = allgather_bytes(mine, gathered.data(), bytes);
+  if (e) return e;
+  if (all || g_rank == root) {
+    std::vector<unsigned char> acc(gathered.begin(), gathered.begin() + bytes);  // rank order: deterministic
+    for (int r = 1; r < g_size; r++)
+      if (!reduce_into(acc.data(), gathered.data() + (size_t)r * bytes, count, t, op)) return MPI_ERR_OP;
+    memcpy(recv, acc.data(), bytes);
+  }
+  return MPI_SUCCESS;
+}
+int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  return reduce_impl(s, r, n, t, op, c == MPI_COMM_SELF ? g_rank : root, false);
+}
+int MPI_Allreduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  return reduce_impl(s, r, n, t, op, 0, true);
+}
+int MPI_Allgather(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  const size_t bytes = type_size(st) * (size_t)sn;
+  if (s == MPI_IN_PLACE) {
+    std::vector<unsigned char> mine((unsigned char*)r + g_rank * bytes, (unsigned char*)r + (g_rank + 1) * bytes);
+    return allgather_bytes(mine.data(), r, bytes);
+  }
+  return allgather_bytes(s, r, bytes);
+}
+int MPI_Gather(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, int root, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  const size_t bytes = type_size(st) * (size_t)sn;
+  std::vector<unsigned char> all(bytes * g_size);
+  e = allgather_bytes(s, all.data(), bytes);
+  if (!e && g_rank == root) memcpy(r, all.data(), all.size());
+  return e;
+}
+int MPI_Scatter(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, int root, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  const size_t bytes = type_size(st) * (size_t)sn;
+  std::vector<unsigned char> all(bytes * g_size);
+  if (g_rank == root) memcpy(all.data(), s, all.size());
+  std::string err;
+  if (g_size > 1 && g_rv->bcast(all.data(), all.size(), root, g_timeout_ms, &err)) return fail(err);
+  memcpy(r, all.data() + (size_t)g_rank * bytes, bytes);
+  return MPI_SUCCESS;
+}
+int MPI_Alltoall(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  const size_t bytes = type_size(st) * (size_t)sn;
+  std::vector<unsigned char> all(bytes * g_size * g_size);
+  e = allgather_bytes(s, all.data(), bytes * g_size);
+  if (e) return e;
+  for (int src = 0; src < g_size; src++)
+    memcpy((char*)r + (size_t)src * bytes, all.data() + ((size_t)src * g_size + g_rank) * bytes, bytes);
+  return MPI_SUCCESS;
+}
+
+}  // extern "C"

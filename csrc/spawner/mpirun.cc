@@ -1,0 +1,410 @@
+// b200mpi-mpirun: native single-box replacement for mpirun / orterun / Hydra
+// mpiexec, the launcher every reference example invokes
+// (examples/v2beta1/pi/pi.yaml:21-26,
+//  examples/v2beta1/tensorflow-benchmarks/tensorflow-benchmarks.yaml:17-42).
+//
+// The reference reaches workers over ssh and lets orted fork the ranks
+// (SURVEY.md §3.3). On one NVSwitch box there is nothing to ssh into: this
+// binary reads the same hostfile the controller generated, places ranks "by
+// slot", gang-spawns them as local process groups with the per-rank
+// environment of every dialect workloads read (OMPI_COMM_WORLD_*, PMI_*,
+// RANK/WORLD_SIZE/LOCAL_RANK, HOROVOD_*), pins GPUs from the node agent's slot
+// map, multiplexes stdio, forwards signals and propagates the first failure —
+// the contract mpirun gives the launcher pod.
+#include <errno.h>
+#include <fcntl.h>
+#include <poll.h>
+#include <signal.h>
+#include <string.h>
+#include <sys/syscall.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+extern char** environ;
+
+struct Host { std::string name; int slots; };
+struct Rank {
+  int rank = 0, local_rank = 0, node = 0;
+  std::string host;
+  pid_t pid = -1;
+  int pidfd = -1, out = -1, err = -1;
+  bool exited = false;
+  int status = 0;
+  std::string obuf, ebuf;
+};
+
+static volatile sig_atomic_t g_signal = 0;
+static void on_signal(int s) { g_signal = s; }
+
+static void die(const std::string& m, int code = 1) {
+  fprintf(stderr, "mpirun (b200mpi): %s\n", m.c_str());
+  exit(code);
+}
+
+static std::string short_host(const std::string& fqdn) {
+  size_t d = fqdn.find('.');
+  return d == std::string::npos ? fqdn : fqdn.substr(0, d);
+}
+
+static std::vector<Host> read_hostfile(const std::string& path, int default_slots) {
+  std::vector<Host> hosts;
+  std::ifstream f(path);
+  if (!f) die("cannot open hostfile " + path);
+  std::string line;
+  while (std::getline(f, line)) {
+    size_t h = line.find('#');
+    if (h != std::string::npos) line = line.substr(0, h);
+    std::istringstream is(line);
+    std::string name, tok;
+    if (!(is >> name)) continue;
+    int slots = default_slots;
+    size_t colon = name.find(':');  // Hydra "host:n"
+    if (colon != std::string::npos) {
+      slots = atoi(name.c_str() + colon + 1);
+      name = name.substr(0, colon);
+    }
+    while (is >> tok) {  // Open MPI "host slots=n max_slots=m"
+      if (tok.rfind("slots=", 0) == 0) slots = atoi(tok.c_str() + 6);
+    }
+    hosts.push_back({name, slots > 0 ? slots : 1});
+  }
+  return hosts;
+}
+
+// minimal parser for {"hosts": {"name": [0,1], ...}}
+static std::map<std::string, std::vector<int>> read_slots_file(const char* path) {
+  std::map<std::string, std::vector<int>> out;
+  if (!path || !*path) return out;
+  std::ifstream f(path);
+  if (!f) return out;
+  std::stringstream ss;
+  ss << f.rdbuf();
+  std::string s = ss.str();
+  size_t p = s.find("\"hosts\"");
+  if (p == std::string::npos) return out;
+  p = s.find('{', p);
+  if (p == std::string::npos) return out;
+  ++p;
+  while (p < s.size()) {
+    size_t q1 = s.find('"', p);
+    if (q1 == std::string::npos) break;
+    size_t close = s.find('}', p);
+    if (close != std::string::npos && close < q1) break;
+    size_t q2 = s.find('"', q1 + 1);
+    std::string name = s.substr(q1 + 1, q2 - q1 - 1);
+    size_t b1 = s.find('[', q2), b2 = s.find(']', b1);
+    if (b1 == std::string::npos || b2 == std::string::npos) break;
+    std::vector<int> v;
+    std::string nums = s.substr(b1 + 1, b2 - b1 - 1);
+    std::istringstream is(nums);
+    std::string t;
+    while (std::getline(is, t, ',')) {
+      bool digit = false;
+      for (char c : t) digit = digit || isdigit((unsigned char)c);
+      if (digit) v.push_back(atoi(t.c_str()));
+    }
+    out[name] = v;
+    p = b2 + 1;
+  }
+  return out;
+}
+
+static void flush_lines(std::string& buf, FILE* to, bool tag, int rank, const char* chan, bool final) {
+  size_t pos;
+  while ((pos = buf.find('\n')) != std::string::npos) {
+    if (tag) fprintf(to, "[1,%d]<%s>:", rank, chan);
+    fwrite(buf.data(), 1, pos + 1, to);
+    buf.erase(0, pos + 1);
+  }
+  if (final && !buf.empty()) {
+    if (tag) fprintf(to, "[1,%d]<%s>:", rank, chan);
+    fwrite(buf.data(), 1, buf.size(), to);
+    fputc('\n', to);
+    buf.clear();
+  }
+  fflush(to);
+}
+
+static bool drain(int& fd, std::string& buf) {
+  char tmp[65536];
+  for (;;) {
+    ssize_t n = read(fd, tmp, sizeof(tmp));
+    if (n > 0) { buf.append(tmp, n); continue; }
+    if (n == 0) { close(fd); fd = -1; return false; }
+    if (errno == EAGAIN || errno == EWOULDBLOCK) return true;
+    if (errno == EINTR) continue;
+    close(fd); fd = -1; return false;
+  }
+}
+
+int main(int argc, char** argv) {
+  int np = -1, ppn = -1, timeout_s = 0;
+  bool tag_output = false, oversubscribe = false;
+  std::string hostfile, hostlist, wdir;
+  std::vector<std::pair<std::string, std::string>> xenv;  // -x / -genv / -env
+  std::vector<std::string> passthrough_unset;
+  int i = 1;
+  auto need = [&](int k) { if (i + k >= argc) die(std::string("option ") + argv[i] + " needs an argument"); };
+  for (; i < argc; i++) {
+    std::string a = argv[i];
+    if (a.size() > 2 && a[0] == '-' && a[1] == '-') a = a.substr(1);  // --np == -np
+    if (a == "-n" || a == "-np" || a == "-c") { need(1); np = atoi(argv[++i]); }
+    else if (a == "-allow-run-as-root" || a == "-oversubscribe" || a == "-q" || a == "-quiet" || a == "-nooversubscribe" ||
+             a == "-display-map" || a == "-display-allocation" || a == "-report-bindings" || a == "-keep-fqdn-hostnames" ||
+             a == "-enable-recovery" || a == "-disable-recovery" || a == "-l") {
+      if (a == "-oversubscribe") oversubscribe = true;
+      if (a == "-l") tag_output = true;
+    }
+    else if (a == "-tag-output" || a == "-prepend-rank") tag_output = true;
+    else if (a == "-bind-to" || a == "-map-by" || a == "-rank-by" || a == "-prefix" || a == "-launcher" || a == "-launcher-exec" ||
+             a == "-bootstrap" || a == "-bootstrap-exec" || a == "-iface" || a == "-output-filename" || a == "-report-pid" ||
+             a == "-cpus-per-proc" || a == "-cpus-per-rank") { need(1); ++i; }
+    else if (a == "-mca" || a == "-gmca" || a == "-omca" || a == "-pmixmca" || a == "-prtemca") {
+      need(2);
+      std::string k = argv[i + 1], v = argv[i + 2];
+      xenv.push_back({"OMPI_MCA_" + k, v});  // what orted exports for -mca
+      i += 2;
+    }
+    else if (a == "-x") {
+      need(1);
+      std::string kv = argv[++i];
+      size_t eq = kv.find('=');
+      if (eq != std::string::npos) xenv.push_back({kv.substr(0, eq), kv.substr(eq + 1)});
+      else if (const char* v = getenv(kv.c_str())) xenv.push_back({kv, v});
+    }
+    else if (a == "-genv" || a == "-env") { need(2); xenv.push_back({argv[i + 1], argv[i + 2]}); i += 2; }
+    else if (a == "-genvall" || a == "-envall") {}
+    else if (a == "-hostfile" || a == "-machinefile" || a == "-f" || a == "-default-hostfile") { need(1); hostfile = argv[++i]; }
+    else if (a == "-host" || a == "-H" || a == "-hosts") { need(1); hostlist = argv[++i]; }
+    else if (a == "-ppn" || a == "-perhost" || a == "-npernode" || a == "-N") { need(1); ppn = atoi(argv[++i]); }
+    else if (a == "-wdir" || a == "-wd") { need(1); wdir = argv[++i]; }
+    else if (a == "-timeout") { need(1); timeout_s = atoi(argv[++i]); }
+    else if (a == "-V" || a == "-version") { printf("mpirun (b200mpi) 0.1.0 — Open MPI/Hydra-compatible single-box launcher\n"); return 0; }
+    else if (a == "-h" || a == "-help") {
+      printf("usage: mpirun [-n N] [-x VAR[=v]] [-mca k v] [--hostfile f] [--tag-output] [-bind-to x] [-map-by x] prog [args]\n");
+      return 0;
+    }
+    else if (!a.empty() && a[0] == '-') { fprintf(stderr, "mpirun (b200mpi): note: ignoring unknown option %s\n", argv[i]); }
+    else break;
+  }
+  if (i >= argc) die("no program to launch");
+  std::vector<char*> prog(argv + i, argv + argc);
+  prog.push_back(nullptr);
+
+  // ---- hosts -------------------------------------------------------------
+  int default_slots = 1;
+  if (const char* s = getenv("OMPI_MCA_orte_set_default_slots")) default_slots = std::max(1, atoi(s));
+  else if (const char* s2 = getenv("I_MPI_PERHOST")) default_slots = std::max(1, atoi(s2));
+  if (ppn > 0) default_slots = ppn;
+  if (hostfile.empty()) {
+    for (const char* v : {"OMPI_MCA_orte_default_hostfile", "I_MPI_HYDRA_HOST_FILE", "HYDRA_HOST_FILE"})
+      if (const char* p = getenv(v)) { if (access(p, R_OK) == 0) { hostfile = p; break; } }
+  }
+  std::vector<Host> hosts;
+  if (!hostlist.empty()) {
+    std::istringstream is(hostlist);
+    std::string h;
+    while (std::getline(is, h, ',')) {
+      int slots = default_slots;
+      size_t c = h.find(':');
+      if (c != std::string::npos) { slots = atoi(h.c_str() + c + 1); h = h.substr(0, c); }
+      hosts.push_back({h, slots});
+    }
+  } else if (!hostfile.empty()) {
+    hosts = read_hostfile(hostfile, default_slots);
+  }
+  if (hosts.empty()) {
+    char hn[256] = "localhost";
+    gethostname(hn, sizeof(hn));
+    hosts.push_back({hn, np > 0 ? np : default_slots});
+  }
+  if (ppn > 0) for (auto& h : hosts) h.slots = ppn;
+  int total_slots = 0;
+  for (auto& h : hosts) total_slots += h.slots;
+  if (np <= 0) np = total_slots;
+  if (np > total_slots && !oversubscribe && getenv("B200MPI_STRICT_SLOTS"))
+    die("not enough slots: requested " + std::to_string(np) + ", hostfile provides " + std::to_string(total_slots));
+
+  // ---- placement by slot -----------------------------------------------------
+  std::vector<Rank> ranks(np);
+  {
+    int r = 0;
+    std::vector<int> used(hosts.size(), 0);
+    while (r < np) {
+      bool placed = false;
+      for (size_t h = 0; h < hosts.size() && r < np; h++) {
+        int cap = hosts[h].slots;
+        int start = used[h];
+        // fill this host's remaining slots (first pass), or one more round when oversubscribed
+        for (int s = start; s < ((start / cap) + 1) * cap && r < np; s++) {
+          ranks[r].rank = r; ranks[r].host = hosts[h].name; ranks[r].node = (int)h; ranks[r].local_rank = s;
+          used[h]++; r++; placed = true;
+        }
+      }
+      if (!placed) break;
+    }
+  }
+  std::vector<int> local_size(hosts.size(), 0);
+  for (auto& rk : ranks) local_size[rk.node]++;
+
+  // ---- GPU map from the node agent ---------------------------------------------
+  auto slots = read_slots_file(getenv("B200MPI_SLOTS_FILE"));
+  std::vector<int> job_gpus;
+  for (auto& h : hosts) {
+    auto it = slots.find(short_host(h.name));
+    if (it != slots.end()) job_gpus.insert(job_gpus.end(), it->second.begin(), it->second.end());
+  }
+  std::string cvd;
+  if ((int)job_gpus.size() >= np) {
+    for (int k = 0; k < np; k++) cvd += (k ? "," : "") + std::to_string(job_gpus[k]);
+  }
+
+  // ---- rendezvous identity -------------------------------------------------------
+  std::string job_id = getenv("B200MPI_JOB_ID") ? getenv("B200MPI_JOB_ID") : "mpirun";
+  job_id += "." + std::to_string((long)getpid());
+  unsigned hash = 5381;
+  for (char c : job_id) hash = hash * 33u + (unsigned char)c;
+  const int master_port = 20000 + (int)(hash % 20000u);
+
+  signal(SIGINT, on_signal);
+  signal(SIGTERM, on_signal);
+  signal(SIGHUP, on_signal);
+  signal(SIGPIPE, SIG_IGN);
+  if (!wdir.empty() && chdir(wdir.c_str()) != 0) die("cannot chdir to " + wdir);
+
+  // On one box the whole job is a single NVSwitch node: LOCAL_RANK == RANK indexes
+  // the job's GPU list.
+  const bool single_node_view = !cvd.empty() || getenv("B200MPI_SINGLE_NODE_VIEW");
+  for (auto& rk : ranks) {
+    int po[2], pe[2];
+    if (pipe2(po, O_CLOEXEC) || pipe2(pe, O_CLOEXEC)) die(std::string("pipe: ") + strerror(errno));
+    pid_t pid = fork();
+    if (pid < 0) die(std::string("fork: ") + strerror(errno));
+    if (pid == 0) {
+      setpgid(0, 0);
+      dup2(po[1], 1);
+      dup2(pe[1], 2);
+      signal(SIGPIPE, SIG_DFL);
+      signal(SIGINT, SIG_DFL);
+      signal(SIGTERM, SIG_DFL);
+      const int lrank = single_node_view ? rk.rank : rk.local_rank;
+      const int lsize = single_node_view ? np : local_size[rk.node];
+      const int node = single_node_view ? 0 : rk.node;
+      auto set = [](const char* k, const std::string& v) { setenv(k, v.c_str(), 1); };
+      auto seti = [&](const char* k, int v) { set(k, std::to_string(v)); };
+      for (auto& kv : xenv) set(kv.first.c_str(), kv.second);
+      set("B200MPI_JOB_ID", job_id);
+      seti("B200MPI_RANK", rk.rank); seti("B200MPI_WORLD_SIZE", np);
+      seti("B200MPI_LOCAL_RANK", lrank); seti("B200MPI_LOCAL_SIZE", lsize);
+      seti("OMPI_COMM_WORLD_RANK", rk.rank); seti("OMPI_COMM_WORLD_SIZE", np);
+      seti("OMPI_COMM_WORLD_LOCAL_RANK", lrank); seti("OMPI_COMM_WORLD_LOCAL_SIZE", lsize);
+      seti("OMPI_COMM_WORLD_NODE_RANK", lrank); seti("OMPI_UNIVERSE_SIZE", total_slots);
+      seti("PMI_RANK", rk.rank); seti("PMI_SIZE", np); seti("MPI_LOCALRANKID", lrank); seti("MPI_LOCALNRANKS", lsize);
+      seti("PMIX_RANK", rk.rank);
+      seti("RANK", rk.rank); seti("WORLD_SIZE", np); seti("LOCAL_RANK", lrank); seti("LOCAL_WORLD_SIZE", lsize);
+      seti("GROUP_RANK", node); set("MASTER_ADDR", "127.0.0.1"); seti("MASTER_PORT", master_port);
+      seti("HOROVOD_RANK", rk.rank); seti("HOROVOD_SIZE", np); seti("HOROVOD_LOCAL_RANK", lrank);
+      seti("HOROVOD_LOCAL_SIZE", lsize); seti("HOROVOD_CROSS_RANK", node); set("HOROVOD_CROSS_SIZE", "1");
+      set("HOROVOD_HOSTNAME", rk.host);
+      set("K_MPI_JOB_ROLE", "worker");
+      set("B200MPI_HOSTNAME", short_host(rk.host));
+      set("HOSTNAME", short_host(rk.host));
+      if (!cvd.empty()) {
+        set("CUDA_VISIBLE_DEVICES", cvd);
+        seti("B200MPI_GPU", job_gpus[rk.rank]);
+        unsetenv("NVIDIA_VISIBLE_DEVICES");
+        unsetenv("NVIDIA_DRIVER_CAPABILITIES");
+      } else if (getenv("CUDA_VISIBLE_DEVICES") && !*getenv("CUDA_VISIBLE_DEVICES") && getenv("B200MPI_GPUS") && *getenv("B200MPI_GPUS")) {
+        set("CUDA_VISIBLE_DEVICES", getenv("B200MPI_GPUS"));
+      }
+      if (const char* inj = getenv("B200MPI_INJECT_LIB")) {  // LD-inject the collective runtime
+        if (*inj && access(inj, R_OK) == 0) {
+          std::string pre = inj;
+          if (const char* old = getenv("LD_PRELOAD")) if (*old) pre += std::string(":") + old;
+          set("LD_PRELOAD", pre);
+        }
+      }
+      execvp(prog[0], prog.data());
+      fprintf(stderr, "mpirun (b200mpi): could not exec %s: %s\n", prog[0], strerror(errno));
+      _exit(127);
+    }
+    setpgid(pid, pid);
+    close(po[1]); close(pe[1]);
+    fcntl(po[0], F_SETFL, O_NONBLOCK);
+    fcntl(pe[0], F_SETFL, O_NONBLOCK);
+    rk.pid = pid; rk.out = po[0]; rk.err = pe[0];
+    rk.pidfd = (int)syscall(SYS_pidfd_open, pid, 0);  // -1 on old kernels: waitpid polling below still works
+  }
+
+  // ---- supervise --------------------------------------------------------------------
+  int alive = np, first_fail_rank = -1, first_fail_status = 0;
+  bool killing = false;
+  time_t t_start = time(nullptr), t_kill = 0;
+  auto kill_all = [&](int sig) {
+    for (auto& rk : ranks) if (!rk.exited && rk.pid > 0) kill(-rk.pid, sig);
+  };
+  while (alive > 0 || std::any_of(ranks.begin(), ranks.end(), [](const Rank& r) { return r.out >= 0 || r.err >= 0; })) {
+    std::vector<pollfd> pf;
+    for (auto& rk : ranks) {
+      if (rk.out >= 0) pf.push_back({rk.out, POLLIN, 0});
+      if (rk.err >= 0) pf.push_back({rk.err, POLLIN, 0});
+      if (!rk.exited && rk.pidfd >= 0) pf.push_back({rk.pidfd, POLLIN, 0});
+    }
+    poll(pf.data(), pf.size(), 100);
+    for (auto& rk : ranks) {
+      if (rk.out >= 0) { bool open = drain(rk.out, rk.obuf); flush_lines(rk.obuf, stdout, tag_output, rk.rank, "stdout", !open); }
+      if (rk.err >= 0) { bool open = drain(rk.err, rk.ebuf); flush_lines(rk.ebuf, stderr, tag_output, rk.rank, "stderr", !open); }
+      if (!rk.exited) {
+        int st = 0;
+        pid_t w = waitpid(rk.pid, &st, WNOHANG);
+        if (w == rk.pid) {
+          rk.exited = true; rk.status = st; alive--;
+          if (rk.pidfd >= 0) { close(rk.pidfd); rk.pidfd = -1; }
+          const bool bad = !(WIFEXITED(st) && WEXITSTATUS(st) == 0);
+          if (bad && first_fail_rank < 0 && !killing) { first_fail_rank = rk.rank; first_fail_status = st; }
+        }
+      }
+    }
+    if ((first_fail_rank >= 0 || g_signal || (timeout_s > 0 && time(nullptr) - t_start > timeout_s)) && !killing && alive > 0) {
+      killing = true; t_kill = time(nullptr);
+      kill_all(g_signal ? (int)g_signal : SIGTERM);
+    }
+    if (killing && alive > 0 && time(nullptr) - t_kill >= 3) kill_all(SIGKILL);
+    if (alive == 0) {
+      // children may leave grandchildren holding the pipes: don't wait for them forever
+      bool pending = false;
+      for (auto& rk : ranks) pending = pending || rk.out >= 0 || rk.err >= 0;
+      if (pending) {
+        usleep(50000);
+        for (auto& rk : ranks) {
+          if (rk.out >= 0) { drain(rk.out, rk.obuf); flush_lines(rk.obuf, stdout, tag_output, rk.rank, "stdout", true); if (rk.out >= 0) { close(rk.out); rk.out = -1; } }
+          if (rk.err >= 0) { drain(rk.err, rk.ebuf); flush_lines(rk.ebuf, stderr, tag_output, rk.rank, "stderr", true); if (rk.err >= 0) { close(rk.err); rk.err = -1; } }
+        }
+      }
+    }
+  }
+  if (g_signal) return 128 + (int)g_signal;
+  if (timeout_s > 0 && killing && first_fail_rank < 0) { fprintf(stderr, "mpirun (b200mpi): job exceeded --timeout %d s\n", timeout_s); return 124; }
+  if (first_fail_rank >= 0) {
+    int code = WIFEXITED(first_fail_status) ? WEXITSTATUS(first_fail_status) : 128 + WTERMSIG(first_fail_status);
+    fprintf(stderr,
+            "--------------------------------------------------------------------------\n"
+            "mpirun (b200mpi) detected that one or more processes exited with non-zero status,\n"
+            "thus causing the job to be terminated. The first process to do so was:\n\n"
+            "  Process name: [[b200mpi],%d]\n  Exit code:    %d\n"
+            "--------------------------------------------------------------------------\n",
+            first_fail_rank, code);
+    return code ? code : 1;
+  }
+  return 0;
+}

@@ -1,0 +1,60 @@
+"""Event recording (record.EventRecorder of client-go; the reference's user
+facing audit trail).  Events are stored as ``v1.Event``
+objects in the namespace of the involved object and mirrored to the log."""
+from __future__ import annotations
+
+import logging
+from typing import List, Optional
+
+from ..api import meta as M
+from ..client.store import ObjectStore
+
+log = logging.getLogger("mpi-job-controller")
+
+EVENT_TYPE_NORMAL = "Normal"
+EVENT_TYPE_WARNING = "Warning"
+
+
+def _ref(obj) -> dict:
+    d = obj.to_dict() if hasattr(obj, "to_dict") else obj
+    md = d.get("metadata", {})
+    return {"apiVersion": d.get("apiVersion", ""), "kind": d.get("kind", ""), "name": md.get("name", ""),
+            "namespace": md.get("namespace", ""), "uid": md.get("uid", "")}
+
+
+class EventRecorder:
+    def __init__(self, store: Optional[ObjectStore], component: str = "mpi-job-controller"):
+        self.store, self.component = store, component
+        self._seq = 0
+
+    def event(self, obj, etype: str, reason: str, message: str) -> None:
+        ref = _ref(obj)
+        log.info("Event(%s/%s): type: '%s' reason: '%s' %s", ref["namespace"], ref["name"], etype, reason, message)
+        if self.store is None:
+            return
+        self._seq += 1
+        now = M.now_rfc3339()
+        ev = {
+            "apiVersion": "v1", "kind": "Event",
+            "metadata": {"name": f"{ref['name']}.{self._seq:08x}{M.new_uid()[:4]}", "namespace": ref["namespace"] or "default"},
+            "involvedObject": ref, "reason": reason, "message": message, "type": etype,
+            "source": {"component": self.component}, "firstTimestamp": now, "lastTimestamp": now, "count": 1,
+        }
+        try:
+            self.store.create("events", ev)
+        except Exception:  # events are best effort
+            log.exception("could not record event")
+
+    def eventf(self, obj, etype: str, reason: str, fmt: str, *args) -> None:
+        self.event(obj, etype, reason, fmt % args if args else fmt)
+
+
+class FakeRecorder(EventRecorder):
+    """record.FakeRecorder: collects "<type> <reason> <message>" strings."""
+
+    def __init__(self):
+        super().__init__(None)
+        self.events: List[str] = []
+
+    def event(self, obj, etype: str, reason: str, message: str) -> None:
+        self.events.append(f"{etype} {reason} {message}")

@@ -1,0 +1,31 @@
+"""Prometheus metrics with the reference's metric names (part of the surface;
+README.md:227-239, pkg/controller/mpi_job_controller.go:125-140,
+cmd/mpi-operator/app/server.go:73-77) plus data-plane additions
+(SURVEY.md §5.5 [NEW])."""
+from __future__ import annotations
+
+from prometheus_client import CollectorRegistry, Counter, Gauge, Histogram, generate_latest
+
+REGISTRY = CollectorRegistry()
+
+# prometheus_client appends "_total" to counters: declare them without the suffix
+mpi_jobs_created = Counter("mpi_operator_jobs_created", "Counts number of MPI jobs created", registry=REGISTRY)
+mpi_jobs_successful = Counter("mpi_operator_jobs_successful", "Counts number of MPI jobs successful", registry=REGISTRY)
+mpi_jobs_failed = Counter("mpi_operator_jobs_failed", "Counts number of MPI jobs failed", registry=REGISTRY)
+mpi_job_info = Gauge("mpi_operator_job_info", "Information about MPIJob", ["launcher", "namespace"], registry=REGISTRY)
+is_leader = Gauge("mpi_operator_is_leader", "Is this client the leader of this mpi-operator client set?", registry=REGISTRY)
+
+# data plane (new)
+allreduce_bytes = Counter("b200mpi_allreduce_bytes", "Bytes reduced by b200mpi allreduce kernels", ["algo"], registry=REGISTRY)
+ranks_active = Gauge("b200mpi_ranks_active", "Ranks currently running under the node agent", registry=REGISTRY)
+gpu_slots_free = Gauge("b200mpi_gpu_slots_free", "Unallocated GPU slots on this box", registry=REGISTRY)
+reconcile_seconds = Histogram("mpi_operator_reconcile_duration_seconds", "Wall time of one syncHandler call",
+                              buckets=(0.001, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5), registry=REGISTRY)
+
+
+def render() -> bytes:
+    return generate_latest(REGISTRY)
+
+
+def counter_value(counter) -> float:
+    return counter._value.get()  # test helper

@@ -1,0 +1,650 @@
+"""NodeAgent = scheduler + kubelet + batch/v1 Job controller for one box.
+
+What Kubernetes does for the reference between "controller created a Pod/Job
+object" and "controller observes its phase" (the k8s boundary
+line) happens here:
+
+* Job controller: one active pod per launcher Job, ``backoffLimit`` (default 6),
+  ``activeDeadlineSeconds``, ``suspend``, ``ttlSecondsAfterFinished``,
+  ``Complete`` / ``Failed`` conditions (reasons BackoffLimitExceeded /
+  DeadlineExceeded) — the fields the reference copies into the launcher Job at
+  pkg/controller/mpi_job_controller.go:1540-1545 and reads back at :1103-1130.
+* Scheduler: GPU slots from the discovered topology; PodGroup members are
+  granted all-or-nothing (gang); unschedulable pods stay Pending.
+* Kubelet: volumes (ConfigMap/Secret) materialised under the pod directory,
+  container[0] started as a process group, phases Pending -> Running ->
+  Succeeded/Failed, Ready condition, restartPolicy OnFailure/Never, logs.
+  A worker whose command is ``sshd`` (the reference default,
+  mpi_job_controller.go:1503-1505) is an idle placeholder: on one box ranks are
+  spawned by the native mpirun, no ssh needed.
+"""
+from __future__ import annotations
+
+import base64
+import copy
+import json
+import logging
+import os
+import random
+import signal
+import string
+import subprocess
+import threading
+import time
+from typing import Dict, List, Optional
+
+from ..api import constants as C
+from ..api import meta as M
+from ..client import errors
+from ..client.store import ADDED, DELETED, MODIFIED, ObjectStore
+from ..controller import metrics
+from .allocator import GangAllocator, SlotRequest
+from .topology import Topology, discover_topology
+
+log = logging.getLogger("node-agent")
+
+NODE_NAME = "localhost"
+GPU_ANNOTATION = "b200mpi.kubeflow.org/gpus"
+JOB_UID_LABEL = "batch.kubernetes.io/controller-uid"
+JOB_NAME_LABEL = "batch.kubernetes.io/job-name"
+DEFAULT_BACKOFF_LIMIT = 6
+PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN_DIR = os.path.join(PKG_DIR, "bin")
+
+
+def _rand(n=5):
+    return "".join(random.choice(string.ascii_lowercase + string.digits) for _ in range(n))
+
+
+class _Proc:
+    def __init__(self):
+        self.popen: Optional[subprocess.Popen] = None
+        self.virtual = False
+        self.restarts = 0
+        self.started_at = ""
+        self.next_restart = 0.0
+        self.log_path = ""
+        self.pod_dir = ""
+
+
+class NodeAgent:
+    def __init__(self, store: ObjectStore, topology: Optional[Topology] = None, state_dir: Optional[str] = None,
+                 clock=None, tick: float = 0.05, extra_env: Optional[Dict[str, str]] = None):
+        self.store = store
+        self.topology = topology or discover_topology()
+        self.alloc = GangAllocator(self.topology)
+        self.state_dir = state_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), f"b200mpi-node-{os.getpid()}")
+        os.makedirs(self.state_dir, exist_ok=True)
+        self.tick = tick
+        self.extra_env = dict(extra_env or {})
+        self._procs: Dict[str, _Proc] = {}
+        self._lock = threading.RLock()
+        self._wake = threading.Event()
+        self._stop = threading.Event()
+        self._thread: Optional[threading.Thread] = None
+        self._cancels = []
+        self._job_backoff: Dict[str, float] = {}
+        self._unsched_since: Dict[str, float] = {}
+
+    # ------------------------------------------------------------ lifecycle --
+    def start(self) -> None:
+        for res in ("pods", "jobs", "configmaps", "volcano-podgroups", "sched-podgroups"):
+            self._cancels.append(self.store.watch(res, self._on_event, replay=True))
+        self._thread = threading.Thread(target=self._loop, name="node-agent", daemon=True)
+        self._thread.start()
+
+    def stop(self) -> None:
+        self._stop.set()
+        self._wake.set()
+        if self._thread:
+            self._thread.join(timeout=5)
+        for c in self._cancels:
+            c()
+        with self._lock:
+            for key in list(self._procs):
+                self._kill(key, grace=0.5)
+
+    def _on_event(self, etype, obj, old) -> None:
+        if obj.get("kind") == "Pod" and etype == DELETED:
+            key = M.key_of(obj)
+            with self._lock:
+                self._kill(key)
+                self.alloc.release(key)
+                self._write_all_slots()
+        if obj.get("kind") == "ConfigMap" and etype == MODIFIED:
+            self._cm_dirty = True
+        self._wake.set()
+
+    def _loop(self) -> None:
+        while not self._stop.is_set():
+            self._wake.wait(self.tick)
+            self._wake.clear()
+            try:
+                self.sync_once()
+            except Exception:  # noqa: BLE001
+                log.exception("node agent sync failed")
+
+    # ---------------------------------------------------------------- sync --
+    def sync_once(self) -> None:
+        with self._lock:
+            if getattr(self, "_cm_dirty", False):
+                self._cm_dirty = False
+                self.refresh_config_volumes()
+            self._sync_jobs()
+            self._schedule()
+            self._sync_pods()
+            metrics.gpu_slots_free.set(self.alloc.free_gpus)
+            metrics.ranks_active.set(sum(1 for p in self._procs.values() if p.popen is not None and p.popen.poll() is None))
+
+    # ------------------------------------------------------- Job controller --
+    def _sync_jobs(self) -> None:
+        now = time.time()
+        for job in self.store.list("jobs"):
+            try:
+                self._sync_job(job, now)
+            except errors.ApiError as e:
+                if not (errors.is_not_found(e) or errors.is_conflict(e)):
+                    raise
+
+    def _job_pods(self, job: dict) -> List[dict]:
+        return [p for p in self.store.list("pods", M.namespace_of(job)) if M.is_controlled_by(p, job)]
+
+    @staticmethod
+    def _cond(job: dict, ctype: str) -> Optional[dict]:
+        for c in job.get("status", {}).get("conditions", []) or []:
+            if c["type"] == ctype:
+                return c
+        return None
+
+    def _finished(self, job: dict) -> bool:
+        return any((self._cond(job, t) or {}).get("status") == "True" for t in ("Complete", "Failed"))
+
+    def _set_job_cond(self, st: dict, ctype: str, status: str, reason: str = "", message: str = "") -> None:
+        conds = [c for c in st.get("conditions", []) if c["type"] != ctype]
+        now = M.now_rfc3339()
+        conds.append({"type": ctype, "status": status, "reason": reason, "message": message,
+                      "lastProbeTime": now, "lastTransitionTime": now})
+        st["conditions"] = conds
+
+    def _sync_job(self, job: dict, now: float) -> None:
+        ns, name = M.namespace_of(job), M.name_of(job)
+        spec = job.get("spec", {})
+        uid = M.meta(job)["uid"]
+        # admission defaults: selector + pod labels (what the apiserver/job controller add)
+        if "selector" not in spec:
+            job = copy.deepcopy(job)
+            job["spec"]["selector"] = {"matchLabels": {JOB_UID_LABEL: uid}}
+            tl = job["spec"]["template"].setdefault("metadata", {}).setdefault("labels", {})
+            tl.update({JOB_UID_LABEL: uid, JOB_NAME_LABEL: name, "controller-uid": uid, "job-name": name})
+            job = self.store.update("jobs", job)
+            spec = job["spec"]
+        st = copy.deepcopy(job.get("status", {}))
+        pods = self._job_pods(job)
+        if self._finished(job):
+            ttl = spec.get("ttlSecondsAfterFinished")
+            if ttl is not None:
+                done_at = st.get("completionTime") or (self._cond(job, "Failed") or {}).get("lastTransitionTime")
+                if done_at and now - M.parse_rfc3339(done_at) >= ttl:
+                    log.info("TTL expired for job %s/%s: deleting", ns, name)
+                    self.store.delete("jobs", ns, name)
+            return
+        active = [p for p in pods if p.get("status", {}).get("phase") in (None, "", "Pending", "Running")]
+        succeeded = [p for p in pods if p.get("status", {}).get("phase") == "Succeeded"]
+        failed = [p for p in pods if p.get("status", {}).get("phase") == "Failed"]
+        restarts = sum(int(cs.get("restartCount", 0)) for p in active for cs in p.get("status", {}).get("containerStatuses", []) or [])
+        if spec.get("suspend"):
+            for p in active:
+                self.store.delete("pods", ns, M.name_of(p))
+            st["active"] = 0
+            st.pop("startTime", None)
+            if (self._cond({"status": st}, "Suspended") or {}).get("status") != "True":
+                self._set_job_cond(st, "Suspended", "True", "JobSuspended", "Job suspended")
+            self._put_job_status(job, st)
+            return
+        if (self._cond({"status": st}, "Suspended") or {}).get("status") == "True":
+            self._set_job_cond(st, "Suspended", "False", "JobResumed", "Job resumed")
+        if not st.get("startTime"):
+            st["startTime"] = M.now_rfc3339(now)
+        st["succeeded"] = len(succeeded)
+        st["failed"] = len(failed)
+        backoff_limit = spec.get("backoffLimit", DEFAULT_BACKOFF_LIMIT)
+        deadline = spec.get("activeDeadlineSeconds")
+        if succeeded:
+            for p in active:
+                self.store.delete("pods", ns, M.name_of(p))
+            st["active"] = 0
+            st["completionTime"] = M.now_rfc3339(now)
+            self._set_job_cond(st, "Complete", "True", "", "")
+        elif deadline is not None and now - M.parse_rfc3339(st["startTime"]) >= deadline:
+            for p in active:
+                self.store.delete("pods", ns, M.name_of(p))
+            st["active"] = 0
+            self._set_job_cond(st, "Failed", "True", "DeadlineExceeded", "Job was active longer than specified deadline")
+        elif len(failed) + restarts > backoff_limit:
+            for p in active:
+                self.store.delete("pods", ns, M.name_of(p))
+            st["active"] = 0
+            self._set_job_cond(st, "Failed", "True", "BackoffLimitExceeded", "Job has reached the specified backoff limit")
+        else:
+            if not active:
+                key = f"{ns}/{name}"
+                nfail = len(failed)
+                ready_at = self._job_backoff.get(key, 0.0)
+                if nfail and ready_at == 0.0:
+                    ready_at = self._job_backoff[key] = now + min(0.25 * (2 ** (nfail - 1)), 10.0)
+                if now >= ready_at:
+                    self._job_backoff.pop(key, None)
+                    self._create_job_pod(job)
+                    st["active"] = 1
+                else:
+                    st["active"] = 0
+            else:
+                st["active"] = len(active)
+        self._put_job_status(job, st)
+
+    def _put_job_status(self, job: dict, st: dict) -> None:
+        if st != job.get("status", {}):
+            j = copy.deepcopy(job)
+            j["status"] = st
+            M.meta(j).pop("resourceVersion", None)
+            self.store.update_status("jobs", j)
+
+    def _create_job_pod(self, job: dict) -> None:
+        tmpl = copy.deepcopy(job["spec"]["template"])
+        md = tmpl.get("metadata", {})
+        pod = {
+            "apiVersion": "v1", "kind": "Pod",
+            "metadata": {"name": f"{M.name_of(job)}-{_rand()}", "namespace": M.namespace_of(job),
+                         "labels": copy.deepcopy(md.get("labels") or {}),
+                         "ownerReferences": [M.new_controller_ref(job, "batch/v1", "Job")]},
+            "spec": tmpl["spec"],
+        }
+        if md.get("annotations"):
+            pod["metadata"]["annotations"] = copy.deepcopy(md["annotations"])
+        self.store.create("pods", pod)
+
+    # ------------------------------------------------------------ scheduler --
+    @staticmethod
+    def _gpu_request(pod: dict) -> int:
+        n = 0
+        for c in pod["spec"].get("containers", []):
+            res = c.get("resources") or {}
+            v = (res.get("limits") or {}).get(C.GPU_RESOURCE, (res.get("requests") or {}).get(C.GPU_RESOURCE, 0))
+            n += int(v)
+        return n
+
+    @staticmethod
+    def _group_of(pod: dict) -> str:
+        md = M.meta(pod)
+        g = (md.get("annotations") or {}).get(C.VOLCANO_GROUP_NAME_ANNOTATION) or (md.get("labels") or {}).get(C.SCHED_PLUGINS_POD_GROUP_LABEL)
+        return f"{md.get('namespace', '')}/{g}" if g else ""
+
+    def _pod_group(self, key: str) -> Optional[dict]:
+        ns, name = M.split_key(key)
+        for res in ("volcano-podgroups", "sched-podgroups"):
+            try:
+                return self.store.get(res, ns, name)
+            except errors.ApiError:
+                continue
+        return None
+
+    def _priority(self, pod: dict, pg: Optional[dict]) -> int:
+        name = (pg or {}).get("spec", {}).get("priorityClassName") or pod["spec"].get("priorityClassName")
+        if not name:
+            return 0
+        try:
+            return int(self.store.get("priorityclasses", "", name).get("value", 0))
+        except errors.ApiError:
+            return 0
+
+    def _schedule(self) -> None:
+        pending = [p for p in self.store.list("pods")
+                   if not p["spec"].get("nodeName") and p.get("status", {}).get("phase") in (None, "", "Pending")
+                   and not M.meta(p).get("deletionTimestamp")]
+        if not pending:
+            return
+        groups: Dict[str, List[dict]] = {}
+        singles: List[dict] = []
+        for p in pending:
+            g = self._group_of(p)
+            (groups.setdefault(g, []) if g else singles).append(p)
+        order = []
+        for g, members in groups.items():
+            pg = self._pod_group(g)
+            order.append((-self._priority(members[0], pg), min(M.meta(m).get("creationTimestamp", "") for m in members), g, members, pg))
+        order.sort(key=lambda t: (t[0], t[1], t[2]))
+        now = time.time()
+        for _, _, g, members, pg in order:
+            all_members = [p for p in self.store.list("pods", M.split_key(g)[0]) if self._group_of(p) == g
+                           and p.get("status", {}).get("phase") not in ("Succeeded", "Failed")]
+            reqs = [SlotRequest(M.key_of(p), self._gpu_request(p), g) for p in all_members]
+            spec = (pg or {}).get("spec", {})
+            min_member = int(spec.get("minMember", len(reqs)) or 0)
+            min_gpus = int((spec.get("minResources") or {}).get(C.GPU_RESOURCE, 0) or 0)
+            feasible = min_gpus <= self.topology.gpu_count if self.topology.gpu_count or min_gpus else True
+            grant = self.alloc.allocate_gang(reqs, min_member, min_gpus) if feasible and pg is not None else None
+            if grant is None:
+                since = self._unsched_since.setdefault(g, now)
+                timeout = int(spec.get("scheduleTimeoutSeconds", 0) or 0)
+                why = "PodGroup not found" if pg is None else (
+                    f"gang of {len(reqs)}/{min_member} members needs {max(min_gpus, sum(r.gpus for r in reqs))} GPUs, {self.alloc.free_gpus} free")
+                if timeout and now - since > timeout:
+                    why += f" (scheduleTimeoutSeconds={timeout} exceeded)"
+                for p in members:
+                    self._mark_unschedulable(p, why)
+                continue
+            self._unsched_since.pop(g, None)
+            for p in members:
+                self._bind(p, grant[M.key_of(p)])
+        for p in sorted(singles, key=lambda p: M.meta(p).get("creationTimestamp", "")):
+            got = self.alloc.allocate(SlotRequest(M.key_of(p), self._gpu_request(p)))
+            if got is None:
+                self._mark_unschedulable(p, f"needs {self._gpu_request(p)} GPUs, {self.alloc.free_gpus} free")
+            else:
+                self._bind(p, got)
+        self._write_all_slots()
+
+    def _mark_unschedulable(self, pod: dict, why: str) -> None:
+        st = copy.deepcopy(pod.get("status", {}))
+        st["phase"] = "Pending"
+        conds = [c for c in st.get("conditions", []) if c["type"] != "PodScheduled"]
+        conds.append({"type": "PodScheduled", "status": "False", "reason": "Unschedulable", "message": why})
+        st["conditions"] = conds
+        if st != pod.get("status", {}):
+            p = copy.deepcopy(pod)
+            p["status"] = st
+            M.meta(p).pop("resourceVersion", None)
+            try:
+                self.store.update_status("pods", p)
+            except errors.ApiError:
+                pass
+
+    def _bind(self, pod: dict, gpus: List[int]) -> None:
+        p = copy.deepcopy(pod)
+        p["spec"]["nodeName"] = NODE_NAME
+        M.meta(p).setdefault("annotations", {})[GPU_ANNOTATION] = ",".join(str(g) for g in gpus)
+        M.meta(p).pop("resourceVersion", None)
+        try:
+            p = self.store.update("pods", p)
+            st = copy.deepcopy(p.get("status", {}))
+            st["phase"] = "Pending"
+            st["conditions"] = [c for c in st.get("conditions", []) if c["type"] != "PodScheduled"] + [
+                {"type": "PodScheduled", "status": "True"}]
+            p["status"] = st
+            M.meta(p).pop("resourceVersion", None)
+            self.store.update_status("pods", p)
+        except errors.ApiError as e:
+            if not errors.is_not_found(e):
+                raise
+            self.alloc.release(M.key_of(pod))
+
+    # -------------------------------------------------------------- kubelet --
+    def _sync_pods(self) -> None:
+        for pod in self.store.list("pods"):
+            key = M.key_of(pod)
+            if not pod["spec"].get("nodeName"):
+                continue
+            phase = pod.get("status", {}).get("phase")
+            if phase in ("Succeeded", "Failed"):
+                if key in self._procs and self._procs[key].popen is None and not self._procs[key].virtual:
+                    pass
+                continue
+            try:
+                if key not in self._procs:
+                    self._start_pod(pod)
+                else:
+                    self._poll_pod(pod)
+            except errors.ApiError as e:
+                if not (errors.is_not_found(e) or errors.is_conflict(e)):
+                    raise
+
+    def pod_dir(self, pod: dict) -> str:
+        return os.path.join(self.state_dir, "pods", M.namespace_of(pod), M.name_of(pod))
+
+    def _materialize_volumes(self, pod: dict, pdir: str) -> Dict[str, str]:
+        """Returns mountPath -> real directory for container[0]."""
+        vols = {v["name"]: v for v in pod["spec"].get("volumes", []) or []}
+        mounts: Dict[str, str] = {}
+        c0 = pod["spec"]["containers"][0]
+        ns = M.namespace_of(pod)
+        for m in c0.get("volumeMounts", []) or []:
+            v = vols.get(m["name"])
+            if v is None:
+                continue
+            real = os.path.join(pdir, "rootfs", m["mountPath"].lstrip("/"))
+            os.makedirs(real, exist_ok=True)
+            try:
+                if "configMap" in v:
+                    cm = self.store.get("configmaps", ns, v["configMap"]["name"])
+                    items = v["configMap"].get("items") or [{"key": k, "path": k} for k in cm.get("data", {})]
+                    for it in items:
+                        if it["key"] in cm.get("data", {}):
+                            self._write_file(os.path.join(real, it["path"]), cm["data"][it["key"]].encode(), it.get("mode", v["configMap"].get("defaultMode", 0o644)))
+                elif "secret" in v:
+                    sec = self.store.get("secrets", ns, v["secret"]["secretName"])
+                    items = v["secret"].get("items") or [{"key": k, "path": k} for k in sec.get("data", {})]
+                    for it in items:
+                        if it["key"] in sec.get("data", {}):
+                            self._write_file(os.path.join(real, it["path"]), base64.b64decode(sec["data"][it["key"]]), it.get("mode", v["secret"].get("defaultMode", 0o644)))
+            except errors.ApiError:
+                pass  # kubelet would keep the container in ContainerCreating; the next sync retries content
+            mounts[m["mountPath"]] = real
+        return mounts
+
+    @staticmethod
+    def _write_file(path: str, data: bytes, mode: int) -> None:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        tmp = path + ".tmp"
+        with open(tmp, "wb") as f:
+            f.write(data)
+        os.chmod(tmp, mode | 0o200)  # keep owner-writable so refreshes can replace it
+        os.replace(tmp, path)
+
+    def _job_slots_path(self, ns: str, job_name: str) -> str:
+        return os.path.join(self.state_dir, "jobs", ns, job_name, "slots.json")
+
+    def _write_all_slots(self) -> None:
+        """hostname -> GPU list per MPIJob, read by the native mpirun to pin ranks."""
+        by_job: Dict[tuple, Dict[str, List[int]]] = {}
+        for pod in self.store.list("pods"):
+            labels = M.meta(pod).get("labels") or {}
+            jn = labels.get(C.JOB_NAME_LABEL)
+            if not jn:
+                continue
+            ann = (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION)
+            if ann is None or pod.get("status", {}).get("phase") in ("Succeeded", "Failed"):
+                continue
+            host = pod["spec"].get("hostname") or M.name_of(pod)
+            by_job.setdefault((M.namespace_of(pod), jn), {})[host] = [int(x) for x in ann.split(",") if x != ""]
+        for (ns, jn), hosts in by_job.items():
+            path = self._job_slots_path(ns, jn)
+            data = json.dumps({"hosts": hosts}, sort_keys=True).encode()
+            try:
+                with open(path, "rb") as f:
+                    if f.read() == data:
+                        continue
+            except OSError:
+                pass
+            self._write_file(path, data, 0o644)
+
+    def _build_env(self, pod: dict, pdir: str, mounts: Dict[str, str]) -> Dict[str, str]:
+        c0 = pod["spec"]["containers"][0]
+        env = dict(os.environ)
+        env["PATH"] = BIN_DIR + os.pathsep + env.get("PATH", "")
+        env.update(self.extra_env)
+        labels = M.meta(pod).get("labels") or {}
+        for e in c0.get("env", []) or []:
+            env[e["name"]] = str(e.get("value", "") or "")
+        # mount-path rewriting: /etc/mpi/hostfile -> <pod rootfs>/etc/mpi/hostfile
+        for k, v in list(env.items()):
+            for mp, real in mounts.items():
+                if isinstance(v, str) and v.startswith(mp.rstrip("/") + "/"):
+                    env[k] = real + v[len(mp.rstrip("/")):]
+        env["HOSTNAME"] = pod["spec"].get("hostname") or M.name_of(pod)
+        env["B200MPI_POD_NAME"] = M.name_of(pod)
+        env["B200MPI_POD_NAMESPACE"] = M.namespace_of(pod)
+        env["B200MPI_POD_DIR"] = pdir
+        env["B200MPI_POD_ROOTFS"] = os.path.join(pdir, "rootfs")
+        env["PYTHONPATH"] = os.path.dirname(PKG_DIR) + os.pathsep + env.get("PYTHONPATH", "")
+        jn = labels.get(C.JOB_NAME_LABEL)
+        if jn:
+            env["B200MPI_MPIJOB_NAME"] = jn
+            env["B200MPI_SLOTS_FILE"] = self._job_slots_path(M.namespace_of(pod), jn)
+            env.setdefault("B200MPI_JOB_ID", f"{M.namespace_of(pod)}.{jn}.{M.meta(pod).get('uid', '')[:8]}")
+        gpus = (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION, "")
+        env["B200MPI_GPUS"] = gpus
+        if env.get("NVIDIA_VISIBLE_DEVICES", None) == "" and "NVIDIA_VISIBLE_DEVICES" in {e["name"] for e in c0.get("env", []) or []}:
+            env["CUDA_VISIBLE_DEVICES"] = ""  # launcher kept off the GPUs (controller.go:1600-1606)
+        elif gpus:
+            env["CUDA_VISIBLE_DEVICES"] = gpus
+        return env
+
+    def _start_pod(self, pod: dict) -> None:
+        key = M.key_of(pod)
+        pdir = self.pod_dir(pod)
+        os.makedirs(os.path.join(pdir, "logs"), exist_ok=True)
+        pr = _Proc()
+        pr.pod_dir = pdir
+        pr.log_path = os.path.join(pdir, "logs", "0.log")
+        c0 = pod["spec"]["containers"][0]
+        argv = list(c0.get("command") or []) + list(c0.get("args") or [])
+        mounts = self._materialize_volumes(pod, pdir)
+        self._procs[key] = pr
+        if argv and os.path.basename(argv[0]) == "sshd":
+            pr.virtual = True
+            pr.started_at = M.now_rfc3339()
+            self._set_running(pod, pr)
+            return
+        if not argv:
+            self._set_terminal(pod, pr, "Failed", 128, "ContainerCannotRun",
+                               "container has no command/args and images are not used on a single box")
+            return
+        env = self._build_env(pod, pdir, mounts)
+        self._launch(pod, pr, argv, env, c0.get("workingDir"))
+
+    def _launch(self, pod: dict, pr: _Proc, argv: List[str], env: Dict[str, str], cwd: Optional[str]) -> None:
+        logf = open(pr.log_path, "ab")
+        try:
+            pr.popen = subprocess.Popen(argv, env=env, cwd=cwd or None, stdout=logf, stderr=subprocess.STDOUT,
+                                        stdin=subprocess.DEVNULL, start_new_session=True)
+        except OSError as e:
+            logf.write(f"exec failed: {e}\n".encode())
+            logf.close()
+            pr.popen = None
+            self._set_terminal(pod, pr, "Failed", 127, "ContainerCannotRun", f"exec {argv[0]!r}: {e}")
+            return
+        logf.close()
+        pr._argv, pr._env, pr._cwd = argv, env, cwd  # for OnFailure restarts
+        pr.started_at = M.now_rfc3339()
+        self._set_running(pod, pr)
+
+    def _container_status(self, pod: dict, pr: _Proc, state: dict, ready: bool) -> List[dict]:
+        return [{"name": pod["spec"]["containers"][0].get("name", "main"), "state": state, "ready": ready,
+                 "restartCount": pr.restarts, "started": "running" in state}]
+
+    def _set_running(self, pod: dict, pr: _Proc) -> None:
+        p = copy.deepcopy(pod)
+        st = p.setdefault("status", {})
+        st["phase"] = "Running"
+        st.setdefault("startTime", pr.started_at)
+        st["hostIP"] = st["podIP"] = "127.0.0.1"
+        conds = [c for c in st.get("conditions", []) if c["type"] not in ("Ready", "ContainersReady", "Initialized")]
+        conds += [{"type": "Initialized", "status": "True"}, {"type": "ContainersReady", "status": "True"}, {"type": "Ready", "status": "True"}]
+        st["conditions"] = conds
+        st["containerStatuses"] = self._container_status(pod, pr, {"running": {"startedAt": pr.started_at}}, True)
+        M.meta(p).pop("resourceVersion", None)
+        self.store.update_status("pods", p)
+
+    def _set_terminal(self, pod: dict, pr: _Proc, phase: str, code: int, reason: str, message: str = "") -> None:
+        p = copy.deepcopy(pod)
+        st = p.setdefault("status", {})
+        st["phase"] = phase
+        if phase == "Failed":
+            st["reason"], st["message"] = reason, message
+        conds = [c for c in st.get("conditions", []) if c["type"] not in ("Ready", "ContainersReady")]
+        conds += [{"type": "ContainersReady", "status": "False", "reason": "PodCompleted" if phase == "Succeeded" else "PodFailed"},
+                  {"type": "Ready", "status": "False", "reason": "PodCompleted" if phase == "Succeeded" else "PodFailed"}]
+        st["conditions"] = conds
+        st["containerStatuses"] = self._container_status(pod, pr, {"terminated": {
+            "exitCode": code, "reason": reason, "message": message, "startedAt": pr.started_at, "finishedAt": M.now_rfc3339()}}, False)
+        M.meta(p).pop("resourceVersion", None)
+        self.store.update_status("pods", p)
+        self.alloc.release(M.key_of(pod))
+        self._write_all_slots()
+
+    def _tail(self, path: str, n: int = 512) -> str:
+        try:
+            with open(path, "rb") as f:
+                f.seek(0, 2)
+                size = f.tell()
+                f.seek(max(0, size - n))
+                return f.read().decode(errors="replace").strip()
+        except OSError:
+            return ""
+
+    def _poll_pod(self, pod: dict) -> None:
+        pr = self._procs[M.key_of(pod)]
+        if pr.virtual:
+            return
+        if pr.popen is None:
+            if pr.next_restart and time.time() >= pr.next_restart:
+                pr.next_restart = 0.0
+                self._launch(pod, pr, pr._argv, pr._env, pr._cwd)
+            return
+        rc = pr.popen.poll()
+        if rc is None:
+            return
+        pr.popen = None
+        if rc == 0:
+            self._set_terminal(pod, pr, "Succeeded", 0, "Completed")
+            return
+        policy = pod["spec"].get("restartPolicy", "Never")
+        code = rc if rc > 0 else 128 - rc
+        msg = self._tail(pr.log_path) or f"exit code {code}"
+        if policy == "OnFailure":
+            pr.restarts += 1
+            pr.next_restart = time.time() + min(0.2 * (2 ** (pr.restarts - 1)), 10.0)
+            p = copy.deepcopy(pod)
+            st = p.setdefault("status", {})
+            st["containerStatuses"] = self._container_status(pod, pr, {"waiting": {"reason": "CrashLoopBackOff", "message": msg}}, False)
+            st["containerStatuses"][0]["lastState"] = {"terminated": {"exitCode": code, "reason": "Error", "message": msg}}
+            M.meta(p).pop("resourceVersion", None)
+            self.store.update_status("pods", p)
+        else:
+            self._set_terminal(pod, pr, "Failed", code, "Error", msg)
+
+    def _kill(self, key: str, grace: float = 2.0) -> None:
+        pr = self._procs.pop(key, None)
+        if pr is None or pr.popen is None:
+            return
+        try:
+            pgid = os.getpgid(pr.popen.pid)
+            os.killpg(pgid, signal.SIGTERM)
+            t0 = time.time()
+            while pr.popen.poll() is None and time.time() - t0 < grace:
+                time.sleep(0.02)
+            if pr.popen.poll() is None:
+                os.killpg(pgid, signal.SIGKILL)
+                pr.popen.wait(timeout=2)
+        except (ProcessLookupError, PermissionError, subprocess.TimeoutExpired):
+            pass
+
+    # ----------------------------------------------------- volume refresh --
+    def refresh_config_volumes(self) -> None:
+        """ConfigMap volume propagation (discover_hosts.sh refresh for elastic Horovod)."""
+        with self._lock:
+            for key in list(self._procs):
+                ns, name = M.split_key(key)
+                try:
+                    pod = self.store.get("pods", ns, name)
+                except errors.ApiError:
+                    continue
+                self._materialize_volumes(pod, self._procs[key].pod_dir)
+
+    def logs(self, namespace: str, pod_name: str) -> str:
+        path = os.path.join(self.state_dir, "pods", namespace, pod_name, "logs", "0.log")
+        try:
+            with open(path, "r", errors="replace") as f:
+                return f.read()
+        except OSError:
+            return ""
