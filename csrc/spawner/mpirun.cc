@@ -335,6 +335,11 @@ int main(int argc, char** argv) {
         }
       }
       execvp(prog[0], prog.data());
+      if (errno == ENOENT && strchr(prog[0], '/')) {
+        // image-relative path (e.g. /home/mpiuser/pi from the reference YAML): fall back to PATH lookup
+        const char* base = strrchr(prog[0], '/') + 1;
+        execvp(base, prog.data());
+      }
       fprintf(stderr, "mpirun (b200mpi): could not exec %s: %s\n", prog[0], strerror(errno));
       _exit(127);
     }

@@ -1,0 +1,301 @@
+"""mpijobctl — kubectl-shaped CLI for the single-box MPIJob operator.
+
+    mpijobctl apply -f examples/pi/pi.yaml        # create or update
+    mpijobctl get mpijobs | pods | jobs | events  # list
+    mpijobctl describe mpijob pi                  # spec summary, status, conditions, events
+    mpijobctl logs pi [--worker N]                # launcher (or a pod's) output
+    mpijobctl scale pi --replicas 8               # elastic rescale
+    mpijobctl suspend|resume pi                   # runPolicy.suspend
+    mpijobctl wait pi --for Succeeded --timeout 300
+    mpijobctl delete mpijob pi
+    mpijobctl topology
+    mpijobctl run -f job.yaml [--gpus N]          # no daemon: in-process operator, wait, print logs
+
+Talks to the daemon's REST API (``--server host:port`` or $MPIJOB_SERVER), the
+local replacement for ``kubectl`` + kube-apiserver in the reference workflow
+(README.md:63-170).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from typing import List, Optional
+
+import yaml
+
+from ..api import constants as C
+from ..sdk.client import MPIJobClient, ApiException
+
+KIND_ALIASES = {"mpijob": "mpijobs", "mpijobs": "mpijobs", "mj": "mpijobs", "pod": "pods", "pods": "pods", "po": "pods",
+                "job": "jobs", "jobs": "jobs", "svc": "services", "service": "services", "services": "services",
+                "cm": "configmaps", "configmap": "configmaps", "configmaps": "configmaps", "secret": "secrets",
+                "secrets": "secrets", "event": "events", "events": "events", "ev": "events", "podgroup": "podgroups",
+                "podgroups": "podgroups", "pg": "podgroups", "lease": "leases", "leases": "leases"}
+
+
+def _age(ts: Optional[str]) -> str:
+    if not ts:
+        return "<none>"
+    from ..api.meta import parse_rfc3339
+    d = int(time.time() - parse_rfc3339(ts))
+    return f"{d}s" if d < 120 else (f"{d // 60}m" if d < 7200 else f"{d // 3600}h")
+
+
+def _job_state(j: dict) -> str:
+    conds = j.get("status", {}).get("conditions", []) or []
+    for t in ("Failed", "Succeeded", "Suspended", "Running", "Created"):
+        if any(c["type"] == t and c["status"] == "True" for c in conds):
+            return t
+    return "Pending"
+
+
+def cmd_apply(cli: MPIJobClient, a) -> int:
+    rc = 0
+    for path in a.filename:
+        text = sys.stdin.read() if path == "-" else open(path).read()
+        for doc in yaml.safe_load_all(text):
+            if not doc:
+                continue
+            doc.setdefault("metadata", {}).setdefault("namespace", a.namespace)
+            if doc.get("kind") != C.KIND:
+                print(f"skipping {doc.get('kind')}: only MPIJob documents are applied", file=sys.stderr)
+                continue
+            try:
+                out, verb = cli.apply(doc)
+                print(f"mpijob.kubeflow.org/{out['metadata']['name']} {verb}")
+            except ApiException as e:
+                print(f"error: {e}", file=sys.stderr)
+                rc = 1
+    return rc
+
+
+def cmd_get(cli: MPIJobClient, a) -> int:
+    res = KIND_ALIASES.get(a.kind.lower())
+    if res is None:
+        print(f"error: unknown resource type {a.kind!r}", file=sys.stderr)
+        return 1
+    try:
+        items = [cli.get_resource(res, a.namespace, a.name)] if a.name else cli.list_resource(res, None if a.all_namespaces else a.namespace)
+    except ApiException as e:
+        print(f"Error from server ({e.reason}): {e}", file=sys.stderr)
+        return 1
+    if a.output == "json":
+        print(json.dumps(items[0] if a.name else {"items": items}, indent=2))
+        return 0
+    if a.output == "yaml":
+        print(yaml.safe_dump(items[0] if a.name else {"items": items}, sort_keys=False))
+        return 0
+    if res == "mpijobs":
+        print(f"{'NAME':24} {'STATE':10} {'WORKERS':8} {'AGE':6}")
+        for j in items:
+            w = ((j.get("spec", {}).get("mpiReplicaSpecs") or {}).get("Worker") or {}).get("replicas", 0)
+            print(f"{j['metadata']['name']:24} {_job_state(j):10} {str(w):8} {_age(j['metadata'].get('creationTimestamp')):6}")
+    elif res == "pods":
+        print(f"{'NAME':36} {'STATUS':10} {'RESTARTS':8} {'GPUS':10} {'AGE':6}")
+        for p in items:
+            cs = (p.get("status", {}).get("containerStatuses") or [{}])[0]
+            gp = (p["metadata"].get("annotations") or {}).get("b200mpi.kubeflow.org/gpus", "")
+            print(f"{p['metadata']['name']:36} {p.get('status', {}).get('phase', 'Pending'):10} {str(cs.get('restartCount', 0)):8} {gp or '-':10} {_age(p['metadata'].get('creationTimestamp')):6}")
+    elif res == "events":
+        print(f"{'LAST SEEN':10} {'TYPE':8} {'REASON':28} {'OBJECT':28} MESSAGE")
+        for e in sorted(items, key=lambda e: e.get("lastTimestamp", "")):
+            io = e.get("involvedObject", {})
+            print(f"{_age(e.get('lastTimestamp')):10} {e.get('type', ''):8} {e.get('reason', ''):28} {(io.get('kind', '') + '/' + io.get('name', '')).lower():28} {e.get('message', '')}")
+    else:
+        print(f"{'NAME':40} {'AGE':6}")
+        for o in items:
+            print(f"{o['metadata']['name']:40} {_age(o['metadata'].get('creationTimestamp')):6}")
+    return 0
+
+
+def cmd_describe(cli: MPIJobClient, a) -> int:
+    try:
+        j = cli.get(a.name, a.namespace)
+    except ApiException as e:
+        print(f"Error from server ({e.reason}): {e}", file=sys.stderr)
+        return 1
+    md, spec, st = j["metadata"], j.get("spec", {}), j.get("status", {})
+    print(f"Name:         {md['name']}\nNamespace:    {md.get('namespace', '')}\nAPI Version:  {j.get('apiVersion')}\nKind:         {j.get('kind')}")
+    print(f"UID:          {md.get('uid', '')}\nCreated:      {md.get('creationTimestamp', '')}")
+    print("Spec:")
+    for k in ("slotsPerWorker", "mpiImplementation", "launcherCreationPolicy", "runLauncherAsWorker", "sshAuthMountPath"):
+        if k in spec:
+            print(f"  {k}: {spec[k]}")
+    print(f"  runPolicy: {json.dumps(spec.get('runPolicy', {}))}")
+    for rt, rs in (spec.get("mpiReplicaSpecs") or {}).items():
+        c0 = ((rs.get("template", {}).get("spec", {}).get("containers")) or [{}])[0]
+        print(f"  {rt}: replicas={rs.get('replicas')} restartPolicy={rs.get('restartPolicy', '')} "
+              f"command={' '.join((c0.get('command') or []) + (c0.get('args') or []))!r}")
+    print("Status:")
+    for k in ("startTime", "completionTime"):
+        if st.get(k):
+            print(f"  {k}: {st[k]}")
+    print(f"  replicaStatuses: {json.dumps(st.get('replicaStatuses', {}))}")
+    print("  Conditions:")
+    print(f"    {'TYPE':10} {'STATUS':7} {'REASON':32} MESSAGE")
+    for c in st.get("conditions", []) or []:
+        print(f"    {c['type']:10} {c['status']:7} {c.get('reason', ''):32} {c.get('message', '')}")
+    print("Events:")
+    for e in sorted(cli.list_resource("events", a.namespace), key=lambda e: e.get("lastTimestamp", "")):
+        if e.get("involvedObject", {}).get("name") == a.name:
+            print(f"  {e.get('type', ''):8} {e.get('reason', ''):28} x{e.get('count', 1):<3} {e.get('message', '')}")
+    return 0
+
+
+def cmd_delete(cli: MPIJobClient, a) -> int:
+    res = KIND_ALIASES.get(a.kind.lower(), a.kind)
+    try:
+        cli.delete_resource(res, a.namespace, a.name)
+        print(f"{a.kind}/{a.name} deleted")
+        return 0
+    except ApiException as e:
+        print(f"Error from server ({e.reason}): {e}", file=sys.stderr)
+        return 1
+
+
+def cmd_logs(cli: MPIJobClient, a) -> int:
+    try:
+        print(cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod), end="")
+        return 0
+    except ApiException as e:
+        print(f"error: {e}", file=sys.stderr)
+        return 1
+
+
+def cmd_scale(cli: MPIJobClient, a) -> int:
+    cli.patch(a.name, {"spec": {"mpiReplicaSpecs": {"Worker": {"replicas": a.replicas}}}}, a.namespace)
+    print(f"mpijob.kubeflow.org/{a.name} scaled")
+    return 0
+
+
+def cmd_suspend(cli: MPIJobClient, a, value: bool) -> int:
+    cli.patch(a.name, {"spec": {"runPolicy": {"suspend": value}}}, a.namespace)
+    print(f"mpijob.kubeflow.org/{a.name} {'suspended' if value else 'resumed'}")
+    return 0
+
+
+def cmd_wait(cli: MPIJobClient, a) -> int:
+    try:
+        j = cli.wait_for_condition(a.name, a.condition, a.namespace, timeout=a.timeout)
+        print(f"mpijob.kubeflow.org/{a.name} condition met: {_job_state(j)}")
+        return 0
+    except TimeoutError as e:
+        print(f"error: {e}", file=sys.stderr)
+        return 1
+
+
+def cmd_run(a) -> int:
+    """Standalone: in-process operator, apply, wait for completion, print launcher logs."""
+    import logging
+    from ..cmd.options import ServerOption
+    from ..cmd.server import Operator
+    from ..api import yaml_io
+    logging.basicConfig(level=logging.INFO if a.verbose else logging.WARNING)
+    op = Operator(ServerOption(fake_gpus=a.fake_gpus, leader_elect=False, gang_scheduling_name=a.gang_scheduling or ""))
+    op.start()
+    rc = 0
+    try:
+        for path in a.filename:
+            for job in yaml_io.load_file(path):
+                job.metadata.setdefault("namespace", a.namespace)
+                if a.replicas is not None and job.spec.replica("Worker") is not None:
+                    job.spec.replica("Worker").replicas = a.replicas
+                c = op.clientset.kubeflow_v2beta1().mpijobs(job.namespace)
+                c.create(job)
+                t0 = time.time()
+                state = "Pending"
+                while time.time() - t0 < a.timeout:
+                    j = c.get(job.name).to_dict()
+                    state = _job_state(j)
+                    if state in ("Succeeded", "Failed"):
+                        break
+                    time.sleep(0.05)
+                for p in op.store.list("pods", job.namespace):
+                    if p["metadata"].get("labels", {}).get(C.JOB_ROLE_LABEL) == "launcher":
+                        sys.stdout.write(op.agent.logs(job.namespace, p["metadata"]["name"]))
+                print(f"mpijob.kubeflow.org/{job.name}: {state} after {time.time() - t0:.2f}s")
+                rc = rc or (0 if state == "Succeeded" else 1)
+    finally:
+        op.stop()
+    return rc
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    ap = argparse.ArgumentParser(prog="mpijobctl")
+    ap.add_argument("--server", default=os.environ.get("MPIJOB_SERVER", "127.0.0.1:8087"))
+    ap.add_argument("-n", "--namespace", default="default")
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    for name in ("apply", "create"):
+        p = sub.add_parser(name)
+        p.add_argument("-f", "--filename", action="append", required=True)
+    p = sub.add_parser("get")
+    p.add_argument("kind")
+    p.add_argument("name", nargs="?")
+    p.add_argument("-o", "--output", default="")
+    p.add_argument("-A", "--all-namespaces", action="store_true")
+    p = sub.add_parser("describe")
+    p.add_argument("kind", nargs="?", default="mpijob")
+    p.add_argument("name")
+    p = sub.add_parser("delete")
+    p.add_argument("kind")
+    p.add_argument("name")
+    p = sub.add_parser("logs")
+    p.add_argument("name")
+    p.add_argument("--worker", type=int, default=None)
+    p.add_argument("--pod", default=None)
+    p = sub.add_parser("scale")
+    p.add_argument("name")
+    p.add_argument("--replicas", type=int, required=True)
+    for name in ("suspend", "resume"):
+        p = sub.add_parser(name)
+        p.add_argument("name")
+    p = sub.add_parser("wait")
+    p.add_argument("name")
+    p.add_argument("--for", dest="condition", default="Succeeded")
+    p.add_argument("--timeout", type=float, default=300)
+    sub.add_parser("topology")
+    sub.add_parser("version")
+    p = sub.add_parser("run")
+    p.add_argument("-f", "--filename", action="append", required=True)
+    p.add_argument("--timeout", type=float, default=600)
+    p.add_argument("--fake-gpus", type=int, default=None)
+    p.add_argument("--replicas", type=int, default=None)
+    p.add_argument("--gang-scheduling", default="")
+    p.add_argument("-v", "--verbose", action="store_true")
+    a = ap.parse_args(argv)
+    if a.cmd == "run":
+        return cmd_run(a)
+    if a.cmd == "version":
+        from .. import version
+        print(json.dumps(version.info()))
+        return 0
+    cli = MPIJobClient(a.server)
+    if a.cmd in ("apply", "create"):
+        return cmd_apply(cli, a)
+    if a.cmd == "get":
+        return cmd_get(cli, a)
+    if a.cmd == "describe":
+        return cmd_describe(cli, a)
+    if a.cmd == "delete":
+        return cmd_delete(cli, a)
+    if a.cmd == "logs":
+        return cmd_logs(cli, a)
+    if a.cmd == "scale":
+        return cmd_scale(cli, a)
+    if a.cmd == "suspend":
+        return cmd_suspend(cli, a, True)
+    if a.cmd == "resume":
+        return cmd_suspend(cli, a, False)
+    if a.cmd == "wait":
+        return cmd_wait(cli, a)
+    if a.cmd == "topology":
+        print(json.dumps(cli.raw_get("/topology"), indent=2))
+        return 0
+    return 2
+
+
+if __name__ == "__main__":
+    sys.exit(main())

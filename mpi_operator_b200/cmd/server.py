@@ -1,0 +1,375 @@
+"""Operator process: leader election, health, metrics, REST API, controller +
+node agent wiring (reference: cmd/mpi-operator/app/server.go:79-314,
+cmd/mpi-operator/main.go:29-53)."""
+from __future__ import annotations
+
+import fcntl
+import json
+import logging
+import os
+import signal
+import socket
+import sys
+import threading
+import time
+import urllib.parse
+import uuid
+from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
+from typing import Optional
+
+from .. import version
+from ..api import constants as C
+from ..api import meta as M
+from ..api.register import scheme
+from ..api.types import MPIJob
+from ..api.validation import validate_mpijob
+from ..client import errors
+from ..client.clientset import Clientset, KubeClient
+from ..client.informers import SharedInformerFactory
+from ..client.store import RESOURCES, ObjectStore
+from ..controller import metrics
+from ..controller.controller import MPIJobController
+from ..node.agent import NodeAgent
+from ..node.topology import discover_topology
+from .options import ServerOption
+
+log = logging.getLogger("mpi-operator")
+
+# leader election timings (server.go:61-63)
+LEASE_DURATION = 15.0
+RENEW_DURATION = 5.0
+RETRY_DURATION = 3.0
+LEADER_LOCK_NAME = "mpi-operator"
+
+# REST prefixes -> store resource
+API_GROUPS = {
+    ("api/v1", "pods"): "pods", ("api/v1", "services"): "services", ("api/v1", "configmaps"): "configmaps",
+    ("api/v1", "secrets"): "secrets", ("api/v1", "events"): "events",
+    ("apis/batch/v1", "jobs"): "jobs", ("apis/kubeflow.org/v2beta1", "mpijobs"): "mpijobs",
+    ("apis/coordination.k8s.io/v1", "leases"): "leases",
+    ("apis/scheduling.k8s.io/v1", "priorityclasses"): "priorityclasses",
+    ("apis/scheduling.volcano.sh/v1beta1", "podgroups"): "volcano-podgroups",
+    ("apis/scheduling.x-k8s.io/v1alpha1", "podgroups"): "sched-podgroups",
+}
+
+
+class LeaderElector:
+    """Lease lock: an flock()ed file is the mutual exclusion, a Lease object in the
+    store is the observable record (holderIdentity / renewTime), renewed every
+    RENEW_DURATION; candidates retry every RETRY_DURATION."""
+
+    def __init__(self, store: ObjectStore, state_dir: str, lock_namespace: str, identity: Optional[str] = None):
+        self.store, self.ns = store, lock_namespace
+        self.identity = identity or f"{socket.gethostname()}_{uuid.uuid4()}"
+        os.makedirs(os.path.join(state_dir, "leases"), exist_ok=True)
+        self.path = os.path.join(state_dir, "leases", f"{lock_namespace}.{LEADER_LOCK_NAME}.lock")
+        self._fd: Optional[int] = None
+        self.last_renew = 0.0
+        self._stop = threading.Event()
+
+    def try_acquire(self) -> bool:
+        fd = os.open(self.path, os.O_CREAT | os.O_RDWR, 0o600)
+        try:
+            fcntl.flock(fd, fcntl.LOCK_EX | fcntl.LOCK_NB)
+        except OSError:
+            os.close(fd)
+            return False
+        self._fd = fd
+        self._renew()
+        return True
+
+    def _renew(self) -> None:
+        now = M.now_rfc3339()
+        lease = {"apiVersion": "coordination.k8s.io/v1", "kind": "Lease",
+                 "metadata": {"name": LEADER_LOCK_NAME, "namespace": self.ns},
+                 "spec": {"holderIdentity": self.identity, "leaseDurationSeconds": int(LEASE_DURATION), "renewTime": now}}
+        try:
+            cur = self.store.get("leases", self.ns, LEADER_LOCK_NAME)
+            if cur["spec"].get("holderIdentity") != self.identity:
+                lease["spec"]["acquireTime"] = now
+                lease["spec"]["leaseTransitions"] = int(cur["spec"].get("leaseTransitions", 0)) + 1
+            else:
+                lease["spec"]["acquireTime"] = cur["spec"].get("acquireTime", now)
+                lease["spec"]["leaseTransitions"] = cur["spec"].get("leaseTransitions", 0)
+            lease["metadata"]["resourceVersion"] = cur["metadata"]["resourceVersion"]
+            self.store.update("leases", lease)
+        except errors.ApiError:
+            lease["spec"]["acquireTime"] = now
+            self.store.create("leases", lease)
+        self.last_renew = time.time()
+
+    def run(self, on_started, on_stopped) -> None:
+        while not self._stop.is_set() and not self.try_acquire():
+            log.info("failed to acquire lease %s/%s; retrying in %.0fs", self.ns, LEADER_LOCK_NAME, RETRY_DURATION)
+            self._stop.wait(RETRY_DURATION)
+        if self._stop.is_set():
+            return
+        log.info("successfully acquired lease %s/%s", self.ns, LEADER_LOCK_NAME)
+        metrics.is_leader.set(1)
+        on_started()
+        while not self._stop.wait(RENEW_DURATION):
+            try:
+                self._renew()
+            except Exception:  # noqa: BLE001
+                log.exception("failed to renew lease")
+                if time.time() - self.last_renew > LEASE_DURATION:
+                    break
+        metrics.is_leader.set(0)
+        on_stopped()
+
+    def healthy(self, slack: float = 20.0) -> bool:
+        """LeaderHealthzAdaptor: unhealthy if we hold the lease but failed to renew for lease+slack."""
+        return self._fd is None or time.time() - self.last_renew < LEASE_DURATION + slack
+
+    def release(self) -> None:
+        self._stop.set()
+        if self._fd is not None:
+            try:
+                fcntl.flock(self._fd, fcntl.LOCK_UN)
+                os.close(self._fd)
+            except OSError:
+                pass
+            self._fd = None
+
+
+class Operator:
+    """Everything app.Run wires together, usable in-process (tests, `mpijobctl run`)."""
+
+    def __init__(self, opt: Optional[ServerOption] = None, store: Optional[ObjectStore] = None, clock=None):
+        self.opt = opt or ServerOption()
+        self.state_dir = self.opt.state_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), f"b200mpi-operator-{os.getpid()}")
+        os.makedirs(self.state_dir, exist_ok=True)
+        if self.opt.fake_gpus is not None:
+            os.environ["B200MPI_FAKE_GPUS"] = str(self.opt.fake_gpus)
+        self.store = store or ObjectStore(os.path.join(self.state_dir, "store.json") if self.opt.state_dir else None)
+        self.kube = KubeClient(self.store)
+        self.clientset = Clientset(self.store)
+        self.informers = SharedInformerFactory(self.store, self.opt.namespace)
+        self.controller = MPIJobController(
+            self.kube, self.clientset, self.informers, gang_scheduling=self.opt.gang_scheduling_name,
+            cluster_domain=self.opt.cluster_domain, clock=clock, queue_rate_limit=self.opt.controller_rate_limit,
+            queue_burst=self.opt.controller_burst, namespace=self.opt.namespace)
+        self.agent = NodeAgent(self.store, discover_topology(), os.path.join(self.state_dir, "node"))
+        self.elector = LeaderElector(self.store, self.state_dir, self.opt.lock_namespace)
+        self._http: list = []
+        self._started = False
+
+    def check_crd_exists(self) -> bool:
+        """server.go:302-314: the daemon refuses to run without the MPIJob kind registered."""
+        return self.clientset.discovery_has_mpijob_crd() and scheme.recognizes(C.API_VERSION, C.KIND)
+
+    def start(self, leader_elect: Optional[bool] = None) -> None:
+        if not self.check_crd_exists():
+            log.error("CRD doesn't exist. Exiting")
+            raise SystemExit(1)
+        if self._started:
+            return
+        self._started = True
+        if leader_elect is None:
+            leader_elect = self.opt.leader_elect
+        if leader_elect:
+            t = threading.Thread(target=self.elector.run, args=(self._run_leading, self._stopped_leading), daemon=True)
+            t.start()
+        else:
+            self._run_leading()
+
+    def _run_leading(self) -> None:
+        self.controller.run(self.opt.threadiness)
+        self.agent.start()
+
+    def _stopped_leading(self) -> None:
+        log.critical("leader election lost")
+        os._exit(1)
+
+    def stop(self) -> None:
+        for s in self._http:
+            s.shutdown()
+        self.controller.stop()
+        self.agent.stop()
+        self.informers.stop()
+        self.elector.release()
+
+    # ------------------------------------------------------------- serving --
+    def serve(self, listen: str, block: bool = False):
+        host, _, port = listen.rpartition(":")
+        srv = ThreadingHTTPServer((host or "127.0.0.1", int(port)), _make_handler(self))
+        srv.daemon_threads = True
+        self._http.append(srv)
+        t = threading.Thread(target=srv.serve_forever, daemon=True)
+        t.start()
+        if block:
+            t.join()
+        return srv
+
+
+def _make_handler(op: Operator):
+    store = op.store
+
+    class H(BaseHTTPRequestHandler):
+        protocol_version = "HTTP/1.1"
+
+        def log_message(self, fmt, *args):  # quiet
+            log.debug("http: " + fmt, *args)
+
+        def _send(self, code: int, body, ctype="application/json"):
+            data = body if isinstance(body, bytes) else (json.dumps(body).encode() if ctype == "application/json" else str(body).encode())
+            self.send_response(code)
+            self.send_header("Content-Type", ctype)
+            self.send_header("Content-Length", str(len(data)))
+            self.end_headers()
+            self.wfile.write(data)
+
+        def _body(self):
+            n = int(self.headers.get("Content-Length", 0) or 0)
+            return json.loads(self.rfile.read(n) or b"{}") if n else {}
+
+        def _route(self):
+            u = urllib.parse.urlparse(self.path)
+            parts = [p for p in u.path.split("/") if p]
+            q = urllib.parse.parse_qs(u.query)
+            return parts, q
+
+        def _resolve(self, parts):
+            """-> (resource, namespace, name, subresource) or None."""
+            for (prefix, plural), res in API_GROUPS.items():
+                pp = prefix.split("/")
+                if parts[:len(pp)] != pp:
+                    continue
+                rest = parts[len(pp):]
+                ns = ""
+                if len(rest) >= 2 and rest[0] == "namespaces":
+                    ns, rest = rest[1], rest[2:]
+                if not rest or rest[0] != plural:
+                    continue
+                name = rest[1] if len(rest) > 1 else ""
+                sub = rest[2] if len(rest) > 2 else ""
+                return res, ns, name, sub
+            return None
+
+        def do_GET(self):  # noqa: N802
+            parts, q = self._route()
+            try:
+                if parts == ["healthz"]:
+                    ok = op.elector.healthy()
+                    return self._send(200 if ok else 500, b"ok" if ok else b"leader election lease expired", "text/plain")
+                if parts == ["metrics"]:
+                    return self._send(200, metrics.render(), "text/plain; version=0.0.4")
+                if parts == ["version"]:
+                    return self._send(200, version.info())
+                if parts == ["topology"]:
+                    t = op.agent.topology.to_dict()
+                    t["free_gpus"] = op.agent.alloc.free_gpus
+                    return self._send(200, t)
+                r = self._resolve(parts)
+                if r is None:
+                    return self._send(404, errors.not_found("path", self.path).to_status())
+                res, ns, name, sub = r
+                if res == "pods" and sub == "log":
+                    return self._send(200, op.agent.logs(ns, name).encode(), "text/plain")
+                if name:
+                    return self._send(200, store.get(res, ns, name))
+                sel = None
+                if "labelSelector" in q:
+                    sel = dict(kv.split("=", 1) for kv in q["labelSelector"][0].split(",") if "=" in kv)
+                items = store.list(res, ns or None, sel)
+                api_version, kind, _ = RESOURCES[res]
+                return self._send(200, {"apiVersion": api_version, "kind": kind + "List", "metadata": {}, "items": items})
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+
+        def _admit(self, res, obj):
+            """API-server side admission for MPIJobs: CRD schema defaults + structural validation."""
+            if res == "mpijobs":
+                if obj.get("kind", C.KIND) != C.KIND or obj.get("apiVersion", C.API_VERSION) != C.API_VERSION:
+                    raise errors.invalid("mpijobs", M.name_of(obj), f"expected {C.API_VERSION}/{C.KIND}")
+                if not (obj.get("spec") or {}).get("mpiReplicaSpecs"):
+                    raise errors.invalid("mpijobs", M.name_of(obj), "spec.mpiReplicaSpecs: Required value")
+
+        def do_POST(self):  # noqa: N802
+            parts, _ = self._route()
+            try:
+                r = self._resolve(parts)
+                if r is None:
+                    return self._send(404, errors.not_found("path", self.path).to_status())
+                res, ns, _, _ = r
+                obj = self._body()
+                if ns:
+                    M.meta(obj).setdefault("namespace", ns)
+                self._admit(res, obj)
+                return self._send(201, store.create(res, obj))
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+
+        def do_PUT(self):  # noqa: N802
+            parts, _ = self._route()
+            try:
+                r = self._resolve(parts)
+                if r is None or not r[2]:
+                    return self._send(404, errors.not_found("path", self.path).to_status())
+                res, ns, name, sub = r
+                obj = self._body()
+                M.meta(obj)["name"] = name
+                if ns:
+                    M.meta(obj)["namespace"] = ns
+                out = store.update_status(res, obj) if sub == "status" else store.update(res, obj)
+                return self._send(200, out)
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+
+        def do_PATCH(self):  # noqa: N802
+            parts, _ = self._route()
+            try:
+                r = self._resolve(parts)
+                if r is None or not r[2]:
+                    return self._send(404, errors.not_found("path", self.path).to_status())
+                res, ns, name, sub = r
+                return self._send(200, store.patch(res, ns, name, self._body(), status=(sub == "status")))
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+
+        def do_DELETE(self):  # noqa: N802
+            parts, _ = self._route()
+            try:
+                r = self._resolve(parts)
+                if r is None:
+                    return self._send(404, errors.not_found("path", self.path).to_status())
+                res, ns, name, _ = r
+                if name:
+                    return self._send(200, store.delete(res, ns, name))
+                n = store.delete_collection(res, ns or None)
+                return self._send(200, {"kind": "Status", "status": "Success", "details": {"deleted": n}})
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+
+    return H
+
+
+def run(opt: ServerOption) -> int:
+    """app.Run (server.go:79-256)."""
+    if opt.print_version:
+        version.print_version_and_exit()
+    logging.basicConfig(level=logging.DEBUG if opt.verbosity >= 4 else logging.INFO,
+                        format="%(levelname).1s%(asctime)s %(name)s] %(message)s", datefmt="%m%d %H:%M:%S")
+    log.info("%s", version.info())
+    log.info("Server options: %s", opt)
+    if opt.namespace == "":
+        log.info("Using cluster scoped operator")
+    else:
+        log.info("Scoping operator to namespace %s", opt.namespace)
+    stop = threading.Event()
+    signal.signal(signal.SIGTERM, lambda *_: stop.set())
+    signal.signal(signal.SIGINT, lambda *_: stop.set())
+    op = Operator(opt)
+    op.serve(opt.listen)
+    log.info("REST API on http://%s", opt.listen)
+    if opt.healthz_port:
+        try:
+            op.serve(f"127.0.0.1:{opt.healthz_port}")
+        except OSError as e:
+            log.warning("healthz port %d unavailable: %s", opt.healthz_port, e)
+    if opt.monitoring_port:
+        op.serve(f"0.0.0.0:{opt.monitoring_port}")
+    op.start()
+    stop.wait()
+    op.stop()
+    return 0

@@ -26,14 +26,27 @@ class EventRecorder:
     def __init__(self, store: Optional[ObjectStore], component: str = "mpi-job-controller"):
         self.store, self.component = store, component
         self._seq = 0
+        self._recent = {}
 
     def event(self, obj, etype: str, reason: str, message: str) -> None:
         ref = _ref(obj)
         log.info("Event(%s/%s): type: '%s' reason: '%s' %s", ref["namespace"], ref["name"], etype, reason, message)
         if self.store is None:
             return
-        self._seq += 1
         now = M.now_rfc3339()
+        # event correlation (client-go EventCorrelator): identical events bump count/lastTimestamp
+        agg_key = (ref["uid"], ref["name"], etype, reason, message)
+        prev = self._recent.get(agg_key)
+        if prev is not None:
+            try:
+                ev = self.store.get("events", prev[0], prev[1])
+                ev["count"] = int(ev.get("count", 1)) + 1
+                ev["lastTimestamp"] = now
+                self.store.update("events", ev)
+                return
+            except Exception:  # noqa: BLE001 - fall through to a fresh event
+                self._recent.pop(agg_key, None)
+        self._seq += 1
         ev = {
             "apiVersion": "v1", "kind": "Event",
             "metadata": {"name": f"{ref['name']}.{self._seq:08x}{M.new_uid()[:4]}", "namespace": ref["namespace"] or "default"},
@@ -42,6 +55,9 @@ class EventRecorder:
         }
         try:
             self.store.create("events", ev)
+            self._recent[agg_key] = (ev["metadata"]["namespace"], ev["metadata"]["name"])
+            if len(self._recent) > 4096:
+                self._recent.pop(next(iter(self._recent)))
         except Exception:  # events are best effort
             log.exception("could not record event")
 
