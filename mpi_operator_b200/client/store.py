@@ -53,6 +53,8 @@ class ObjectStore:
         self._persist_path = persist_path
         self._pending: List[Tuple[str, str, dict, Optional[dict]]] = []
         self._dispatch_lock = threading.RLock()
+        self._save_lock = threading.Lock()
+        self._saved_rv = -1
         if persist_path and os.path.exists(persist_path):
             self._load()
 
@@ -241,12 +243,19 @@ class ObjectStore:
     def _save(self) -> None:
         if not self._persist_path:
             return
-        with self._lock:
-            snap = {"rv": self._rv, "objects": {r: list(o.values()) for r, o in self._objs.items() if o}}
-        tmp = self._persist_path + ".tmp"
-        with open(tmp, "w") as f:
-            json.dump(snap, f)
-        os.replace(tmp, self._persist_path)
+        with self._save_lock:
+            with self._lock:
+                if self._saved_rv == self._rv:
+                    return
+                snap = {"rv": self._rv, "objects": {r: list(o.values()) for r, o in self._objs.items() if o}}
+                self._saved_rv = self._rv
+            tmp = f"{self._persist_path}.tmp{os.getpid()}"
+            try:
+                with open(tmp, "w") as f:
+                    json.dump(snap, f)
+                os.replace(tmp, self._persist_path)
+            except OSError:
+                pass  # state dir removed underneath us (shutdown): persistence is best effort
 
     def _load(self) -> None:
         with open(self._persist_path) as f:

@@ -21,6 +21,7 @@ line) happens here:
 from __future__ import annotations
 
 import base64
+import collections
 import copy
 import json
 import logging
@@ -85,6 +86,7 @@ class NodeAgent:
         self._cancels = []
         self._job_backoff: Dict[str, float] = {}
         self._unsched_since: Dict[str, float] = {}
+        self._deleted = collections.deque()
 
     # ------------------------------------------------------------ lifecycle --
     def start(self) -> None:
@@ -105,12 +107,10 @@ class NodeAgent:
                 self._kill(key, grace=0.5)
 
     def _on_event(self, etype, obj, old) -> None:
+        # Never take the agent lock here: watch handlers run under the store's dispatch lock,
+        # while the sync loop calls into the store holding the agent lock (lock-order inversion).
         if obj.get("kind") == "Pod" and etype == DELETED:
-            key = M.key_of(obj)
-            with self._lock:
-                self._kill(key)
-                self.alloc.release(key)
-                self._write_all_slots()
+            self._deleted.append(M.key_of(obj))
         if obj.get("kind") == "ConfigMap" and etype == MODIFIED:
             self._cm_dirty = True
         self._wake.set()
@@ -127,6 +127,14 @@ class NodeAgent:
     # ---------------------------------------------------------------- sync --
     def sync_once(self) -> None:
         with self._lock:
+            reaped = False
+            while self._deleted:
+                key = self._deleted.popleft()
+                self._kill(key)
+                self.alloc.release(key)
+                reaped = True
+            if reaped:
+                self._write_all_slots()
             if getattr(self, "_cm_dirty", False):
                 self._cm_dirty = False
                 self.refresh_config_volumes()

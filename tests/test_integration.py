@@ -1,0 +1,234 @@
+"""Integration tier: the real operator (controller + node agent) driving real
+CPU processes on localhost — analogue of the reference's envtest + e2e tiers
+(test/integration/mpi_job_controller_test.go:50-977, test/e2e/mpi_job_test.go:92-584)."""
+import os
+import time
+
+import pytest
+
+from helpers import conds, new_mpijob
+from mpi_operator_b200.api import constants as C
+from mpi_operator_b200.api import yaml_io
+from mpi_operator_b200.api.types import SchedulingPolicy
+from mpi_operator_b200.cmd.options import ServerOption
+from mpi_operator_b200.cmd.server import Operator
+from mpi_operator_b200.controller import metrics
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_native = pytest.mark.skipif(not os.path.exists(os.path.join(REPO, "mpi_operator_b200/bin/mpirun")),
+                                  reason="native launcher not built (run make)")
+
+
+@pytest.fixture
+def op(tmp_path):
+    o = Operator(ServerOption(fake_gpus=8, leader_elect=False, state_dir=str(tmp_path)))
+    o.start()
+    yield o
+    o.stop()
+
+
+@pytest.fixture
+def gang_op(tmp_path):
+    o = Operator(ServerOption(fake_gpus=4, leader_elect=False, state_dir=str(tmp_path), gang_scheduling_name="volcano"))
+    o.start()
+    yield o
+    o.stop()
+
+
+def wait_for(fn, timeout=20.0, what="condition"):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        v = fn()
+        if v:
+            return v
+        time.sleep(0.02)
+    raise AssertionError(f"timed out waiting for {what}")
+
+
+def events(op, name):
+    return [(e["type"], e["reason"]) for e in sorted(op.store.list("events"), key=lambda e: e["metadata"]["creationTimestamp"] + e["metadata"]["name"])
+            if e["involvedObject"]["name"] == name]
+
+
+def submit(op, job):
+    return op.clientset.kubeflow_v2beta1().mpijobs(job.namespace).create(job)
+
+
+def get(op, job):
+    return op.clientset.kubeflow_v2beta1().mpijobs(job.namespace).get(job.name)
+
+
+@needs_native
+def test_pi_job_happy_path_events_and_cleanup(op):
+    job = yaml_io.load_file(os.path.join(REPO, "examples/pi/pi.yaml"))[0]
+    job.metadata["namespace"] = "default"
+    t0 = time.time()
+    submit(op, job)
+    done = wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True" and get(op, job), what="Succeeded")
+    assert time.time() - t0 < 30  # reference e2e budget: 200 s per wait
+    assert done.status.completion_time and done.status.start_time
+    assert done.status.replica_statuses["Launcher"].succeeded == 1
+    ev = [r for _, r in events(op, "pi")]
+    assert ev[0] == "MPIJobCreated" and "MPIJobRunning" in ev and ev[-1] == "MPIJobSucceeded"
+    pods = op.store.list("pods", "default")
+    launcher = [p for p in pods if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    log = op.agent.logs("default", launcher["metadata"]["name"])
+    assert "pi is approximately 3.1" in log and "Worker 1/2 on pi-worker-1" in log
+    # cleanPodPolicy: Running -> idle (Running) workers are deleted after completion
+    wait_for(lambda: not [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "worker"], what="worker cleanup")
+    # hostfile + discover_hosts.sh were mounted into the launcher sandbox with the reference's modes
+    root = os.path.join(op.agent.pod_dir(launcher), "rootfs", "etc", "mpi")
+    assert open(os.path.join(root, "hostfile")).read() == "pi-worker-0.pi.default.svc slots=1\npi-worker-1.pi.default.svc slots=1\n"
+    assert os.stat(os.path.join(root, "discover_hosts.sh")).st_mode & 0o111
+    assert os.path.exists(os.path.join(op.agent.pod_dir(launcher), "rootfs", "home/mpiuser/.ssh", "id_rsa"))
+
+
+@needs_native
+def test_malformed_command_backoff_limit_failed(op):
+    job = new_mpijob("bad", workers=1, launcher_cmd=("mpirun",), launcher_args=("-n", "1", "sh", "-c", "echo boom >&2; exit 7"),
+                     worker_cmd=("/usr/sbin/sshd", "-De"), backoff_limit=1)
+    job.spec.replica("Launcher").restart_policy = "Never"
+    before = metrics.counter_value(metrics.mpi_jobs_failed)
+    submit(op, job)
+    failed = wait_for(lambda: conds(get(op, job)).get("Failed") == "True" and get(op, job), what="Failed")
+    c = [c for c in failed.status.conditions if c.type == "Failed"][0]
+    assert c.reason == "BackoffLimitExceeded/Error" and "boom" in c.message
+    assert failed.status.replica_statuses["Launcher"].failed == 2  # backoffLimit 1 -> two failed pods
+    assert metrics.counter_value(metrics.mpi_jobs_failed) == before + 1
+    assert failed.status.completion_time is not None
+
+
+@needs_native
+def test_single_launcher_pod_failure_is_not_job_failure(op):
+    marker = os.path.join(op.state_dir, "once")
+    script = f"if [ ! -e {marker} ]; then touch {marker}; exit 1; fi; exit 0"
+    job = new_mpijob("flaky", workers=1, launcher_cmd=("sh", "-c", script), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    job.spec.replica("Launcher").restart_policy = "Never"
+    submit(op, job)
+    ok = wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True" and get(op, job), what="Succeeded after one retry")
+    assert ok.status.replica_statuses["Launcher"].failed == 1 and "Failed" not in conds(ok)
+
+
+@needs_native
+def test_on_failure_restarts_in_place(op):
+    marker = os.path.join(op.state_dir, "once2")
+    script = f"if [ ! -e {marker} ]; then touch {marker}; exit 3; fi; exit 0"
+    job = new_mpijob("inplace", workers=None, launcher_cmd=("sh", "-c", script), launcher_args=None)  # default launcher policy OnFailure
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
+    pods = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("inplace-launcher")]
+    assert len(pods) == 1 and pods[0]["status"]["containerStatuses"][0]["restartCount"] == 1
+
+
+def test_created_suspended_has_no_pods_until_resumed(op):
+    job = new_mpijob("susp", workers=2, launcher_cmd=("sh", "-c", "sleep 0.2"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",), suspend=True)
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Suspended") == "True", what="Suspended")
+    time.sleep(0.3)
+    assert op.store.list("pods", "default") == []
+    assert get(op, job).status.start_time is None
+    j = get(op, job)
+    j.spec.run_policy.suspend = False
+    op.clientset.kubeflow_v2beta1().mpijobs("default").update(j)
+    done = wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True" and get(op, job), what="Succeeded after resume")
+    assert conds(done)["Suspended"] == "False" and done.status.start_time is not None
+    assert ("Normal", "MPIJobResumed") in events(op, "susp")
+
+
+def test_suspend_running_job_kills_processes(op):
+    job = new_mpijob("longrun", workers=2, launcher_cmd=("sh", "-c", "sleep 60"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Running") == "True", what="Running")
+    j = get(op, job)
+    j.spec.run_policy.suspend = True
+    op.clientset.kubeflow_v2beta1().mpijobs("default").update(j)
+    wait_for(lambda: not op.store.list("pods", "default"), what="all pods deleted on suspend")
+    c = conds(get(op, job))
+    assert c["Suspended"] == "True" and c["Running"] == "False"
+    assert op.agent.alloc.free_gpus == 8
+
+
+def test_managed_by_multikueue_is_untouched(op):
+    job = new_mpijob("ext", workers=1, managed_by=C.MULTIKUEUE_CONTROLLER)
+    submit(op, job)
+    time.sleep(0.4)
+    assert get(op, job).status.conditions == [] and op.store.list("pods") == [] and op.store.list("jobs") == []
+
+
+def test_wait_for_workers_ready(op):
+    job = new_mpijob("wfw", workers=2, launcher_cmd=("sh", "-c", "true"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    job.spec.launcher_creation_policy = C.LAUNCHER_CREATION_POLICY_WAIT_FOR_WORKERS_READY
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
+    lj = op.store.get("jobs", "default", "wfw-launcher")
+    workers = [p for p in op.store.list("pods", "default") if "worker" in p["metadata"]["name"]]
+    # the launcher Job was created only after both workers reported Ready
+    assert all(lj["metadata"]["creationTimestamp"] >= w["status"]["startTime"] for w in workers) or not workers
+
+
+def test_gpu_slots_gang_and_release(gang_op):
+    op = gang_op
+    # 4 GPUs on the box. job A: 2 workers x 2 GPUs (needs all 4); job B: 2 workers x 1 GPU must wait for A.
+    a = new_mpijob("a", workers=2, launcher_cmd=("sh", "-c", "sleep 0.8"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    a.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 2}}
+    b = new_mpijob("b", workers=2, launcher_cmd=("sh", "-c", "cat $B200MPI_SLOTS_FILE"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    b.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+    for j in (a, b):
+        j.spec.run_policy.clean_pod_policy = "All"
+    submit(op, a)
+    wait_for(lambda: conds(get(op, a)).get("Running") == "True", what="A running")
+    assert op.agent.alloc.free_gpus == 0
+    pg = op.store.get("volcano-podgroups", "default", "a")
+    assert pg["spec"]["minMember"] == 3 and pg["spec"]["minResources"] == {"nvidia.com/gpu": "4"}
+    submit(op, b)
+    time.sleep(0.3)
+    bw = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-")]
+    assert bw and all(p["status"]["phase"] == "Pending" for p in bw)  # whole gang pending, nothing partially started
+    assert any(c.get("reason") == "Unschedulable" for p in bw for c in p["status"].get("conditions", []))
+    wait_for(lambda: conds(get(op, b)).get("Succeeded") == "True", timeout=30, what="B runs after A released its GPUs")
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-launcher")][0]
+    assert '"b-worker-0": [' in op.agent.logs("default", launcher["metadata"]["name"])
+    wait_for(lambda: op.agent.alloc.free_gpus == 4, what="all GPUs released")
+    assert op.store.list("volcano-podgroups", "default") == []  # PodGroup deleted on finish-with-cleanup
+
+
+def test_unschedulable_min_resources_then_cleared(gang_op):
+    op = gang_op
+    j = new_mpijob("big", workers=1, launcher_cmd=("sh", "-c", "true"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    j.spec.run_policy.scheduling_policy = SchedulingPolicy(min_resources={"nvidia.com/gpu": "64"})
+    submit(op, j)
+    time.sleep(0.4)
+    assert "Running" not in conds(get(op, j)) and "Succeeded" not in conds(get(op, j))
+    cur = get(op, j)
+    cur.spec.run_policy.scheduling_policy = None
+    op.clientset.kubeflow_v2beta1().mpijobs("default").update(cur)
+    wait_for(lambda: conds(get(op, j)).get("Succeeded") == "True", what="Succeeded once minResources cleared")
+
+
+@needs_native
+def test_elastic_scale_updates_discover_hosts_in_launcher(op):
+    script = 'for i in $(seq 1 200); do n=$(sh $B200MPI_POD_ROOTFS/etc/mpi/discover_hosts.sh | wc -l); echo hosts=$n; if [ "$n" = "4" ]; then exit 0; fi; sleep 0.05; done; exit 1'
+    job = new_mpijob("elastic", workers=2, launcher_cmd=("sh", "-c", script), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Running") == "True", what="Running")
+    j = get(op, job)
+    j.spec.replica("Worker").replicas = 4
+    op.clientset.kubeflow_v2beta1().mpijobs("default").update(j)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="launcher saw 4 hosts")
+    assert get(op, job).status.replica_statuses["Launcher"].succeeded == 1
+
+
+def test_active_deadline_and_ttl(op):
+    job = new_mpijob("deadline", workers=None, launcher_cmd=("sh", "-c", "sleep 30"), launcher_args=None,
+                     active_deadline_seconds=1, ttl_seconds_after_finished=1)
+    submit(op, job)
+    failed = wait_for(lambda: conds(get(op, job)).get("Failed") == "True" and get(op, job), timeout=15, what="DeadlineExceeded")
+    assert [c.reason for c in failed.status.conditions if c.type == "Failed"] == ["DeadlineExceeded"]
+    wait_for(lambda: not op.store.list("jobs", "default"), timeout=10, what="launcher Job removed by TTL")
+
+
+def test_metrics_text_has_reference_names(op):
+    text = metrics.render().decode()
+    for name in ("mpi_operator_jobs_created_total", "mpi_operator_jobs_successful_total", "mpi_operator_jobs_failed_total",
+                 "mpi_operator_job_info", "mpi_operator_is_leader"):
+        assert name in text
