@@ -119,6 +119,9 @@ def main() -> int:
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
 
+    if os.environ.get("B200MPI_FAULTHANDLER"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["B200MPI_FAULTHANDLER"]), exit=True)
     import torch
     import torch.nn as nn
     from mpi_operator_b200.launch.env import rank_info_from_env

@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--out", default="")
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--flush-l2", action="store_true")
+    ap.add_argument("--tune-blocks", default="", help="comma list of CTA counts to try for twoshot/nvls at sizes >= 16 MiB")
     a = ap.parse_args()
     info = rank_info_from_env()
     dev = info.local_rank % torch.cuda.device_count()
@@ -72,6 +73,7 @@ def main():
     flush = torch.zeros(160 << 20, device="cuda", dtype=torch.float32) if a.flush_l2 else None
     win = comm.alloc_window(a.max)
     rows = []
+    default_blocks = comm.get_tuning()["max_blocks"]
     factor = 2.0 * (W - 1) / W if W > 1 else 1.0
     for dname in a.dtype.split(","):
         dtype = getattr(torch, dname)
@@ -92,6 +94,17 @@ def main():
                 algos["twoshot_staged"] = lambda: comm.allreduce(t, t, op="avg", algo="twoshot")
             if use_nccl:
                 algos["nccl"] = lambda: dist.all_reduce(t, op=dist.ReduceOp.AVG)
+            if a.tune_blocks and size >= (16 << 20):
+                for nb in [int(x) for x in a.tune_blocks.split(",")]:
+                    def mk(algo, nb=nb):
+                        def run():
+                            comm.set_tuning(max_blocks=nb)
+                            comm.allreduce_window(win, 0, n, dtype, op="avg", algo=algo)
+                        return run
+                    algos[f"twoshot@{nb}"] = mk("twoshot")
+                    if comm.has_multicast:
+                        algos[f"nvls@{nb}"] = mk("nvls")
+            comm.set_tuning(max_blocks=default_blocks)
             iters = a.iters if size <= (64 << 20) else max(5, a.iters // 4)
             for name, fn in algos.items():
                 inner = 20 if size <= (1 << 20) else (4 if size <= (32 << 20) else 1)

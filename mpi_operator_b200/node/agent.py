@@ -53,6 +53,26 @@ PKG_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN_DIR = os.path.join(PKG_DIR, "bin")
 
 
+REPO_ROOT = os.path.dirname(PKG_DIR)
+# "Images" on a single box: a container image is a directory + command remaps. The reference's
+# example images resolve to the in-repo equivalents of what those images contain.
+IMAGE_REGISTRY = {
+    "mpioperator/tensorflow-benchmarks": {"workingDir": os.path.join(REPO_ROOT, "examples", "tensorflow-benchmarks")},
+    "mpioperator/mpi-pi": {},
+    "docker.io/kubeflow/mpi-horovod-mnist": {"remap": {"/examples/tensorflow_mnist.py": os.path.join(REPO_ROOT, "examples", "horovod", "torch_mnist.py")}},
+}
+
+
+def image_config(image: str) -> dict:
+    base = (image or "").split(":")[0]
+    extra = os.environ.get("B200MPI_IMAGE_REGISTRY")
+    reg = dict(IMAGE_REGISTRY)
+    if extra and os.path.exists(extra):
+        with open(extra) as f:
+            reg.update(json.load(f))
+    return reg.get(base, {})
+
+
 def _rand(n=5):
     return "".join(random.choice(string.ascii_lowercase + string.digits) for _ in range(n))
 
@@ -528,7 +548,13 @@ class NodeAgent:
                                "container has no command/args and images are not used on a single box")
             return
         env = self._build_env(pod, pdir, mounts)
-        self._launch(pod, pr, argv, env, c0.get("workingDir"))
+        img = image_config(c0.get("image", ""))
+        argv = [img.get("remap", {}).get(a, a) for a in argv]
+        if argv[0] in ("python", "python3"):
+            import sys as _sys
+            argv[0] = _sys.executable
+        env["B200MPI_PYTHON"] = __import__("sys").executable
+        self._launch(pod, pr, argv, env, c0.get("workingDir") or img.get("workingDir"))
 
     def _launch(self, pod: dict, pr: _Proc, argv: List[str], env: Dict[str, str], cwd: Optional[str]) -> None:
         logf = open(pr.log_path, "ab")
