@@ -254,7 +254,17 @@ def main() -> int:
         print(json.dumps(out), flush=True)
     barrier()
     if use_dist:
-        dist.destroy_process_group()
+        # NCCL communicators referenced by a captured CUDA graph can block destroy_process_group:
+        # drop the graph first and never let teardown hang the run.
+        if args.impl == "nccl":
+            trainer._graph = None
+        torch.cuda.synchronize()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(15)
+        if t.is_alive():
+            sys.stdout.flush()
+            os._exit(0)
     comm.destroy()
     return 0
 

@@ -203,6 +203,13 @@ def cmd_run(a) -> int:
                 job.metadata.setdefault("namespace", a.namespace)
                 if a.replicas is not None and job.spec.replica("Worker") is not None:
                     job.spec.replica("Worker").replicas = a.replicas
+                if a.np is not None:  # rewrite the launcher's -np/-n value (scaling the same YAML)
+                    c0 = job.spec.replica("Launcher").main_container()
+                    for key in ("command", "args"):
+                        argv = c0.get(key) or []
+                        for i, tok in enumerate(argv[:-1]):
+                            if tok in ("-np", "-n", "--np", "--n"):
+                                argv[i + 1] = str(a.np)
                 c = op.clientset.kubeflow_v2beta1().mpijobs(job.namespace)
                 c.create(job)
                 t0 = time.time()
@@ -263,6 +270,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     p.add_argument("--timeout", type=float, default=600)
     p.add_argument("--fake-gpus", type=int, default=None)
     p.add_argument("--replicas", type=int, default=None)
+    p.add_argument("--np", type=int, default=None, help="rewrite the launcher mpirun -np value")
     p.add_argument("--gang-scheduling", default="")
     p.add_argument("-v", "--verbose", action="store_true")
     a = ap.parse_args(argv)
