@@ -141,7 +141,7 @@ struct b200mpi_comm {
   size_t oneshot_max = 256 << 10;
   size_t nvls_min = 0;
   int max_blocks = 64;
-  int nvls_blocks = 32;
+  int nvls_blocks = 16;  // the switch does the adds: 16 CTAs saturate NVLS (sweep: nvls@16 >= nvls@32 > nvls@128)
   int timeout_ms = 30000;
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
@@ -397,6 +397,12 @@ static void window_release(b200mpi_comm* c, Window& W) {
 // --------------------------------------------------------------- set-up ----
 static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   c->timeout_ms = env_int("B200MPI_TIMEOUT_MS", 30000);
+  // Crossovers measured on 8xB200 / NVSwitch (profiles/allreduce_sweep_n{2,8}_f32.json):
+  //  world 2 : push one-shot wins to 1 MiB, then P2P two-shot; NVLS never pays (1.5 S vs 1.0 S link bytes)
+  //  world 8 : one-shot to 64 KiB, NVLS above (S(1+1/N) vs 2S(N-1)/N link bytes per direction)
+  if (c->world <= 2) { c->oneshot_max = (size_t)1 << 20; c->nvls_min = (size_t)-1; }
+  else if (c->world <= 4) { c->oneshot_max = (size_t)256 << 10; c->nvls_min = (size_t)1 << 20; }
+  else { c->oneshot_max = (size_t)64 << 10; c->nvls_min = 0; }
   c->oneshot_max = env_size("B200MPI_ONESHOT_MAX_BYTES", c->oneshot_max);
   c->nvls_min = env_size("B200MPI_NVLS_MIN_BYTES", c->nvls_min);
   c->max_blocks = std::min(env_int("B200MPI_MAX_BLOCKS", c->max_blocks), kMaxBlocks);
@@ -835,7 +841,7 @@ int b200mpi_scale_cast(const void* in, b200mpi_dtype_t idt, void* out, b200mpi_d
 int b200mpi_set_tuning(b200mpi_comm_t c, size_t oneshot_max, size_t nvls_min, int max_blocks, int timeout_ms) {
   if (oneshot_max != (size_t)-1) c->oneshot_max = std::min(oneshot_max, (size_t)kOneshotBlocks * c->oneshot_cap_vecs * 16);
   if (nvls_min != (size_t)-1) c->nvls_min = nvls_min;
-  if (max_blocks > 0) { c->max_blocks = std::min(max_blocks, kMaxBlocks); c->nvls_blocks = std::min(max_blocks, kMaxBlocks); }
+  if (max_blocks > 0) { c->max_blocks = std::min(max_blocks, kMaxBlocks); c->nvls_blocks = std::min(max_blocks, kMaxBlocks); }  // explicit tuning applies to both paths
   if (timeout_ms > 0) c->timeout_ms = timeout_ms;
   return 0;
 }
