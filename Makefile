@@ -11,11 +11,15 @@ BINDIR    := mpi_operator_b200/bin
 RUNTIME_SRCS := csrc/kernels/collectives.cu csrc/runtime/comm.cc csrc/runtime/rendezvous.cc
 RUNTIME_HDRS := csrc/include/b200mpi.h csrc/kernels/device.cuh csrc/kernels/kernels.h csrc/runtime/rendezvous.h
 
-all: $(LIBDIR)/libb200mpi.so native
+all: $(LIBDIR)/libb200mpi.so $(LIBDIR)/libb200mpi_nccl.so native
 
 $(LIBDIR)/libb200mpi.so: $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -x cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread
+
+$(LIBDIR)/libb200mpi_nccl.so: csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) $(RUNTIME_HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -x cu csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread -ldl
 
 native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi
 

@@ -1,0 +1,504 @@
+// libb200mpi_nccl.so — NCCL C-ABI front-end of the b200mpi runtime, meant to be
+// LD_PRELOADed into unmodified torch.distributed / Horovod processes.
+//
+// PyTorch's libtorch_cuda.so links libnccl.so.2 dynamically, so preloaded
+// definitions of ncclAllReduce & co. win symbol resolution: the gradient
+// allreduce / allgather / broadcast a training script issues through
+// ProcessGroupNCCL then execute as b200mpi peer-memory / NVLS kernels with the
+// scale (ncclAvg, PreMulSum) fused in — "LD-injected collective runtime" of the
+// north star (BASELINE.json; SURVEY.md §5.9 front-end (2), §7.3 item 4).
+// Anything outside the implemented subset (P2P send/recv, >8 ranks, exotic
+// dtypes/ops on a failed fast path) is forwarded to the real NCCL found with
+// dlsym(RTLD_NEXT); B200MPI_ALGO=nccl forwards everything (the baseline mode).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../include/b200mpi.h"
+
+extern "C" {
+// ---- the slice of nccl.h we implement (ABI-compatible declarations) -------------
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0, ncclUnhandledCudaError = 1, ncclSystemError = 2, ncclInternalError = 3,
+               ncclInvalidArgument = 4, ncclInvalidUsage = 5, ncclRemoteError = 6, ncclInProgress = 7 } ncclResult_t;
+typedef enum { ncclInt8 = 0, ncclUint8 = 1, ncclInt32 = 2, ncclUint32 = 3, ncclInt64 = 4, ncclUint64 = 5,
+               ncclFloat16 = 6, ncclFloat32 = 7, ncclFloat64 = 8, ncclBfloat16 = 9 } ncclDataType_t;
+typedef enum { ncclSum = 0, ncclProd = 1, ncclMax = 2, ncclMin = 3, ncclAvg = 4, ncclNumOps = 5 } ncclRedOp_t;
+typedef enum { ncclScalarDevice = 0, ncclScalarHostImmediate = 1 } ncclScalarResidence_t;
+struct ncclConfig_v;  // opaque
+}
+
+namespace {
+
+struct Shim {
+  b200mpi_comm_t mine = nullptr;  // b200mpi communicator (nullptr => forwarded)
+  ncclComm_t real = nullptr;      // real NCCL communicator when forwarding
+  int rank = 0, world = 1, device = 0;
+  std::string id;
+  int splits = 0;
+};
+
+std::mutex g_mu;
+std::map<int, float> g_premul;  // dynamic ncclRedOp_t -> scalar
+int g_next_op = 16;
+std::atomic<uint64_t> g_calls{0}, g_forwarded{0};
+thread_local std::string g_last_error;
+thread_local int g_group_depth = 0;
+
+bool forward_all() {
+  static int v = -1;
+  if (v < 0) {
+    const char* a = getenv("B200MPI_ALGO");
+    v = (a && strcmp(a, "nccl") == 0) ? 1 : 0;
+  }
+  return v == 1;
+}
+bool debug() { static int v = getenv("B200MPI_DEBUG") ? 1 : 0; return v; }
+
+template <typename F>
+F real_fn(const char* name) {
+  void* p = dlsym(RTLD_NEXT, name);
+  if (!p) {
+    static void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) p = dlsym(h, name);
+  }
+  return reinterpret_cast<F>(p);
+}
+#define REAL(name, ...) real_fn<ncclResult_t (*)(__VA_ARGS__)>(#name)
+
+ncclResult_t err(ncclResult_t code, const std::string& msg) {
+  g_last_error = msg;
+  if (debug()) fprintf(stderr, "[b200mpi nccl shim] %s\n", msg.c_str());
+  return code;
+}
+ncclResult_t from_rc(int rc, const char* what) {
+  if (rc == 0) return ncclSuccess;
+  return err(rc == B200MPI_ERR_CUDA ? ncclUnhandledCudaError : (rc == B200MPI_ERR_INVALID ? ncclInvalidArgument : ncclSystemError),
+             std::string(what) + ": " + b200mpi_last_error());
+}
+
+size_t dt_size(ncclDataType_t t) {
+  switch (t) {
+    case ncclInt8: case ncclUint8: return 1;
+    case ncclFloat16: case ncclBfloat16: return 2;
+    case ncclInt32: case ncclUint32: case ncclFloat32: return 4;
+    case ncclInt64: case ncclUint64: case ncclFloat64: return 8;
+    default: return (int)t >= 10 && (int)t <= 11 ? 1 : 0;  // fp8 variants: byte-wise only
+  }
+}
+bool native_dt(ncclDataType_t t, b200mpi_dtype_t* out) {
+  if (t == ncclFloat32) { *out = B200MPI_F32; return true; }
+  if (t == ncclBfloat16) { *out = B200MPI_BF16; return true; }
+  if (t == ncclFloat16) { *out = B200MPI_F16; return true; }
+  return false;
+}
+// -> (op, scale) for the fused kernels; false when the generic path is needed
+bool native_op(int op, int world, b200mpi_op_t* out, float* scale) {
+  *scale = 1.0f;
+  if (op == ncclSum) { *out = B200MPI_SUM; return true; }
+  if (op == ncclAvg) { *out = B200MPI_SUM; *scale = 1.0f / world; return true; }
+  if (op == ncclMax) { *out = B200MPI_MAX; return true; }
+  if (op == ncclMin) { *out = B200MPI_MIN; return true; }
+  if (op >= 16) {
+    std::lock_guard<std::mutex> l(g_mu);
+    auto it = g_premul.find(op);
+    if (it != g_premul.end()) { *out = B200MPI_SUM; *scale = it->second; return true; }
+  }
+  return false;
+}
+
+// generic reduction of `world` gathered blocks for dtypes/ops the fused kernels do not cover
+template <typename T>
+__global__ void k_reduce_gathered(const T* __restrict__ in, T* __restrict__ out, size_t n, size_t stride, int world, int op, double post) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    T acc = in[i];
+    for (int r = 1; r < world; r++) {
+      const T x = in[(size_t)r * stride + i];
+      acc = op == ncclProd ? (T)(acc * x) : (op == ncclMax ? (x > acc ? x : acc) : (op == ncclMin ? (x < acc ? x : acc) : (T)(acc + x)));
+    }
+    if (op == ncclAvg) acc = (T)(acc / (T)world);
+    if (post != 1.0) acc = (T)((double)acc * post);
+    out[i] = acc;
+  }
+}
+template <typename T>
+void launch_rg(const void* in, void* out, size_t n, size_t stride, int world, int op, double post, cudaStream_t s) {
+  const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+  k_reduce_gathered<T><<<blocks ? blocks : 1, 256, 0, s>>>((const T*)in, (T*)out, n, stride, world, op, post);
+}
+
+ncclResult_t generic_allreduce(Shim* s, const void* send, void* recv, size_t count, ncclDataType_t dt, int op, cudaStream_t st) {
+  const size_t es = dt_size(dt);
+  if (!es) return err(ncclInvalidArgument, "unsupported datatype");
+  double post = 1.0;
+  int eff = op;
+  if (op >= 16) { std::lock_guard<std::mutex> l(g_mu); auto it = g_premul.find(op); if (it == g_premul.end()) return err(ncclInvalidArgument, "unknown reduction op"); post = it->second; eff = ncclSum; }
+  void* tmp = nullptr;
+  size_t bytes = count * es;
+  size_t padded = (bytes + 1) / 2 * 2;
+  if (cudaMallocAsync(&tmp, padded * s->world, st) != cudaSuccess) return err(ncclUnhandledCudaError, "cudaMallocAsync failed");
+  const void* src = send;
+  void* pad_src = nullptr;
+  if (padded != bytes) {  // odd byte counts: the byte-wise allgather moves 2-byte units
+    cudaMallocAsync(&pad_src, padded, st);
+    cudaMemsetAsync(pad_src, 0, padded, st);
+    cudaMemcpyAsync(pad_src, send, bytes, cudaMemcpyDeviceToDevice, st);
+    src = pad_src;
+  }
+  int rc = b200mpi_allgather(s->mine, src, tmp, padded / 2, B200MPI_BF16, st);
+  if (rc) { cudaFreeAsync(tmp, st); return from_rc(rc, "allgather"); }
+  if (padded != bytes) {
+    // gathered blocks are `padded` apart: compact is unnecessary when we reduce with stride = padded/es only if divisible
+    cudaFreeAsync(pad_src, st);
+    if (padded % es) { cudaFreeAsync(tmp, st); return err(ncclInvalidArgument, "odd-sized reduction not supported"); }
+  }
+  const size_t stride_elems = padded / es;
+  switch (dt) {
+    case ncclInt8: launch_rg<int8_t>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclUint8: launch_rg<uint8_t>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclInt32: launch_rg<int32_t>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclUint32: launch_rg<uint32_t>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclInt64: launch_rg<long long>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclUint64: launch_rg<unsigned long long>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclFloat64: launch_rg<double>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    case ncclFloat32: launch_rg<float>(tmp, recv, count, stride_elems, s->world, eff, post, st); break;
+    default: cudaFreeAsync(tmp, st); return err(ncclInvalidArgument, "reduction op not supported for this datatype");
+  }
+  cudaFreeAsync(tmp, st);
+  return cudaGetLastError() == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "reduce_gathered launch failed");
+}
+
+std::string id_to_job(const ncclUniqueId* id) {
+  char buf[80];
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(id->internal);
+  int n = snprintf(buf, sizeof(buf), "nccl-");
+  for (int i = 0; i < 16; i++) n += snprintf(buf + n, sizeof(buf) - n, "%02x", b[i]);
+  return buf;
+}
+
+ncclResult_t init_common(ncclComm_t* out, int nranks, const ncclUniqueId* id, int rank, const void* config,
+                         bool have_config) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  auto* s = new Shim;
+  s->rank = rank; s->world = nranks; s->device = dev; s->id = id_to_job(id);
+  if (!forward_all() && nranks <= B200MPI_MAX_RANKS) {
+    int rc = b200mpi_comm_init(&s->mine, rank, nranks, dev, s->id.c_str(), 0, 0);
+    if (rc != 0) {
+      // every rank fails the same way (capability consensus) -> fall back together
+      if (debug()) fprintf(stderr, "[b200mpi nccl shim] b200mpi init failed (%s); forwarding to NCCL\n", b200mpi_last_error());
+      s->mine = nullptr;
+    }
+  }
+  if (!s->mine) {
+    g_forwarded++;
+    ncclResult_t r;
+    if (have_config) {
+      auto f = REAL(ncclCommInitRankConfig, ncclComm_t*, int, ncclUniqueId, int, const void*);
+      if (!f) { delete s; return err(ncclSystemError, "real NCCL not found for pass-through"); }
+      r = f(&s->real, nranks, *id, rank, config);
+    } else {
+      auto f = REAL(ncclCommInitRank, ncclComm_t*, int, ncclUniqueId, int);
+      if (!f) { delete s; return err(ncclSystemError, "real NCCL not found for pass-through"); }
+      r = f(&s->real, nranks, *id, rank);
+    }
+    if (r != ncclSuccess && r != ncclInProgress) { delete s; return r; }
+  } else if (debug() && rank == 0) {
+    fprintf(stderr, "[b200mpi nccl shim] communicator %s: %d ranks on b200mpi kernels (NVLS=%d)\n", s->id.c_str(), nranks,
+            b200mpi_comm_has_multicast(s->mine));
+  }
+  *out = reinterpret_cast<ncclComm_t>(s);
+  return ncclSuccess;
+}
+
+inline Shim* S(ncclComm_t c) { return reinterpret_cast<Shim*>(c); }
+
+}  // namespace
+
+extern "C" {
+
+// exported for tests / stats
+uint64_t b200mpi_shim_calls(void) { return g_calls.load(); }
+uint64_t b200mpi_shim_forwarded(void) { return g_forwarded.load(); }
+
+ncclResult_t ncclGetVersion(int* v) { *v = 22809; return ncclSuccess; }
+const char* ncclGetErrorString(ncclResult_t r) {
+  switch (r) {
+    case ncclSuccess: return "no error";
+    case ncclUnhandledCudaError: return "unhandled cuda error (run with B200MPI_DEBUG=1 for details)";
+    case ncclSystemError: return "unhandled system error (run with B200MPI_DEBUG=1 for details)";
+    case ncclInternalError: return "internal error";
+    case ncclInvalidArgument: return "invalid argument";
+    case ncclInvalidUsage: return "invalid usage";
+    case ncclRemoteError: return "remote process exited or there was a network error";
+    case ncclInProgress: return "NCCL operation in progress";
+    default: return "unknown result code";
+  }
+}
+const char* ncclGetLastError(ncclComm_t) { return g_last_error.c_str(); }
+
+ncclResult_t ncclGetUniqueId(ncclUniqueId* id) {
+  if (forward_all()) {
+    auto f = REAL(ncclGetUniqueId, ncclUniqueId*);
+    if (f) return f(id);
+  }
+  memset(id, 0, sizeof(*id));
+  FILE* f = fopen("/dev/urandom", "rb");
+  size_t got = f ? fread(id->internal, 1, 32, f) : 0;
+  if (f) fclose(f);
+  if (got < 32) { uint64_t t = (uint64_t)time(nullptr) ^ ((uint64_t)getpid() << 32); memcpy(id->internal, &t, 8); }
+  memcpy(id->internal + 32, "b200mpi", 8);
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommInitRank(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank) { return init_common(comm, nranks, &id, rank, nullptr, false); }
+ncclResult_t ncclCommInitRankConfig(ncclComm_t* comm, int nranks, ncclUniqueId id, int rank, const void* config) { return init_common(comm, nranks, &id, rank, config, true); }
+ncclResult_t ncclCommInitRankScalable(ncclComm_t* comm, int nranks, int rank, int nid, ncclUniqueId* ids, const void* config) {
+  if (nid < 1) return err(ncclInvalidArgument, "no unique ids");
+  return init_common(comm, nranks, &ids[0], rank, config, true);
+}
+ncclResult_t ncclCommInitAll(ncclComm_t* comms, int ndev, const int* devlist) {
+  auto f = REAL(ncclCommInitAll, ncclComm_t*, int, const int*);
+  if (!f) return err(ncclInvalidUsage, "ncclCommInitAll (single process, many GPUs) is not provided: b200mpi is one process per GPU");
+  std::vector<ncclComm_t> real(ndev);
+  ncclResult_t r = f(real.data(), ndev, devlist);
+  if (r != ncclSuccess) return r;
+  for (int i = 0; i < ndev; i++) { auto* s = new Shim; s->real = real[i]; s->rank = i; s->world = ndev; comms[i] = reinterpret_cast<ncclComm_t>(s); }
+  g_forwarded++;
+  return ncclSuccess;
+}
+
+ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, const void* config) {
+  Shim* s = S(comm);
+  if (s->real) {
+    auto f = REAL(ncclCommSplit, ncclComm_t, int, int, ncclComm_t*, const void*);
+    if (!f) return err(ncclSystemError, "real ncclCommSplit missing");
+    ncclComm_t r = nullptr;
+    ncclResult_t rc = f(s->real, color, key, &r, config);
+    if (rc != ncclSuccess) return rc;
+    if (!r) { *newcomm = nullptr; return ncclSuccess; }
+    auto* n = new Shim; n->real = r; *newcomm = reinterpret_cast<ncclComm_t>(n);
+    return ncclSuccess;
+  }
+  struct CK { int color, key, rank; } mine{color, key, s->rank};
+  std::vector<CK> all(s->world);
+  if (b200mpi_comm_host_allgather(s->mine, &mine, all.data(), sizeof(CK))) return from_rc(-1, "split allgather");
+  const int seq = s->splits++;
+  if (color < 0) { *newcomm = nullptr; return ncclSuccess; }
+  std::vector<CK> members;
+  for (auto& x : all) if (x.color == color) members.push_back(x);
+  std::stable_sort(members.begin(), members.end(), [](const CK& a, const CK& b) { return a.key != b.key ? a.key < b.key : a.rank < b.rank; });
+  int nrank = -1;
+  for (size_t i = 0; i < members.size(); i++) if (members[i].rank == s->rank) nrank = (int)i;
+  auto* n = new Shim;
+  n->rank = nrank; n->world = (int)members.size(); n->device = s->device;
+  n->id = s->id + "-s" + std::to_string(seq) + "c" + std::to_string(color);
+  int rc = b200mpi_comm_init(&n->mine, nrank, n->world, n->device, n->id.c_str(), 0, 0);
+  if (rc) { delete n; return from_rc(rc, "ncclCommSplit"); }
+  *newcomm = reinterpret_cast<ncclComm_t>(n);
+  return ncclSuccess;
+}
+ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t*, const void*, int) { return err(ncclInvalidUsage, "ncclCommShrink is not provided; re-form the communicator (elastic rescale re-spawns ranks)"); }
+
+static ncclResult_t destroy(ncclComm_t comm, const char* realname) {
+  Shim* s = S(comm);
+  if (!s) return ncclSuccess;
+  ncclResult_t r = ncclSuccess;
+  if (s->real) { auto f = real_fn<ncclResult_t (*)(ncclComm_t)>(realname); if (f) r = f(s->real); }
+  if (s->mine) {
+    if (debug() && s->rank == 0) fprintf(stderr, "[b200mpi nccl shim] %s: %llu b200mpi kernel launches\n", s->id.c_str(), (unsigned long long)b200mpi_comm_launch_count(s->mine));
+    b200mpi_comm_destroy(s->mine);
+  }
+  delete s;
+  return r;
+}
+ncclResult_t ncclCommDestroy(ncclComm_t c) { return destroy(c, "ncclCommDestroy"); }
+ncclResult_t ncclCommAbort(ncclComm_t c) { return destroy(c, "ncclCommAbort"); }
+ncclResult_t ncclCommFinalize(ncclComm_t c) {
+  Shim* s = S(c);
+  if (s && s->real) { auto f = REAL(ncclCommFinalize, ncclComm_t); return f ? f(s->real) : ncclSuccess; }
+  return ncclSuccess;
+}
+ncclResult_t ncclCommCount(const ncclComm_t c, int* n) { Shim* s = S(c); if (s->real) { auto f = REAL(ncclCommCount, ncclComm_t, int*); return f(s->real, n); } *n = s->world; return ncclSuccess; }
+ncclResult_t ncclCommUserRank(const ncclComm_t c, int* r) { Shim* s = S(c); if (s->real) { auto f = REAL(ncclCommUserRank, ncclComm_t, int*); return f(s->real, r); } *r = s->rank; return ncclSuccess; }
+ncclResult_t ncclCommCuDevice(const ncclComm_t c, int* d) { Shim* s = S(c); if (s->real) { auto f = REAL(ncclCommCuDevice, ncclComm_t, int*); return f(s->real, d); } *d = s->device; return ncclSuccess; }
+ncclResult_t ncclCommGetAsyncError(ncclComm_t c, ncclResult_t* e) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclCommGetAsyncError, ncclComm_t, ncclResult_t*); return f(s->real, e); }
+  *e = b200mpi_comm_check_error(s->mine) ? ncclRemoteError : ncclSuccess;
+  return ncclSuccess;
+}
+
+ncclResult_t ncclRedOpCreatePreMulSum(ncclRedOp_t* op, void* scalar, ncclDataType_t dt, ncclScalarResidence_t res, ncclComm_t c) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclRedOpCreatePreMulSum, ncclRedOp_t*, void*, ncclDataType_t, ncclScalarResidence_t, ncclComm_t); return f(op, scalar, dt, res, s->real); }
+  float v;
+  if (res == ncclScalarHostImmediate) {
+    if (dt == ncclFloat32) v = *(float*)scalar;
+    else if (dt == ncclFloat64) v = (float)*(double*)scalar;
+    else if (dt == ncclFloat16) v = __half2float(*(__half*)scalar);
+    else if (dt == ncclBfloat16) v = __bfloat162float(*(__nv_bfloat16*)scalar);
+    else return err(ncclInvalidArgument, "PreMulSum scalar dtype");
+  } else {
+    if (dt != ncclFloat32) return err(ncclInvalidArgument, "device-resident PreMulSum scalar must be float32");
+    if (cudaMemcpy(&v, scalar, 4, cudaMemcpyDeviceToHost) != cudaSuccess) return err(ncclUnhandledCudaError, "reading PreMulSum scalar");
+  }
+  std::lock_guard<std::mutex> l(g_mu);
+  const int id = g_next_op++;
+  g_premul[id] = v;
+  *op = (ncclRedOp_t)id;
+  return ncclSuccess;
+}
+ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t c) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclRedOpDestroy, ncclRedOp_t, ncclComm_t); return f(op, s->real); }
+  std::lock_guard<std::mutex> l(g_mu);
+  g_premul.erase((int)op);
+  return ncclSuccess;
+}
+
+ncclResult_t ncclGroupStart(void) {
+  g_group_depth++;
+  if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) if (g_forwarded.load()) return f();
+  return ncclSuccess;
+}
+ncclResult_t ncclGroupEnd(void) {
+  if (g_group_depth > 0) g_group_depth--;
+  if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupEnd")) if (g_forwarded.load()) return f();
+  return ncclSuccess;  // b200mpi collectives were enqueued eagerly, in order, on their streams
+}
+ncclResult_t ncclGroupSimulateEnd(void*) { return ncclSuccess; }
+
+ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclAllReduce, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, op, s->real, st); }
+  b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
+  if (native_dt(dt, &bdt) && native_op((int)op, s->world, &bop, &scale))
+    return from_rc(b200mpi_allreduce(s->mine, send, recv, count, bdt, bop, scale, B200MPI_ALGO_AUTO, st), "ncclAllReduce");
+  return generic_allreduce(s, send, recv, count, dt, (int)op, st);
+}
+
+ncclResult_t ncclBroadcast(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclBroadcast, const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, root, s->real, st); }
+  const size_t bytes = count * dt_size(dt);
+  if (s->rank == root && send != recv) cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st);
+  return from_rc(b200mpi_broadcast_bytes(s->mine, recv, bytes, root, st), "ncclBroadcast");
+}
+ncclResult_t ncclBcast(void* buf, size_t count, ncclDataType_t dt, int root, ncclComm_t c, cudaStream_t st) { return ncclBroadcast(buf, buf, count, dt, root, c, st); }
+
+ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, int root, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclReduce, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, op, root, s->real, st); }
+  b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
+  if (native_dt(dt, &bdt) && native_op((int)op, s->world, &bop, &scale))
+    return from_rc(b200mpi_reduce(s->mine, send, recv, count, bdt, bop, scale, root, st), "ncclReduce");
+  // generic: allreduce into a scratch buffer, keep it on the root only
+  void* tmp = recv;
+  if (s->rank != root) { if (cudaMallocAsync(&tmp, count * dt_size(dt), st) != cudaSuccess) return err(ncclUnhandledCudaError, "scratch"); }
+  ncclResult_t r = generic_allreduce(s, send, tmp, count, dt, (int)op, st);
+  if (s->rank != root) cudaFreeAsync(tmp, st);
+  return r;
+}
+
+ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t dt, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclAllGather, const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t); return f(send, recv, sendcount, dt, s->real, st); }
+  const size_t bytes = sendcount * dt_size(dt);
+  if (bytes % 2 == 0) return from_rc(b200mpi_allgather(s->mine, send, recv, bytes / 2, B200MPI_BF16, st), "ncclAllGather");
+  // odd byte count: go through padded scratch
+  void *in = nullptr, *out = nullptr;
+  cudaMallocAsync(&in, bytes + 1, st);
+  cudaMallocAsync(&out, (bytes + 1) * s->world, st);
+  cudaMemsetAsync(in, 0, bytes + 1, st);
+  cudaMemcpyAsync(in, send, bytes, cudaMemcpyDeviceToDevice, st);
+  int rc = b200mpi_allgather(s->mine, in, out, (bytes + 1) / 2, B200MPI_BF16, st);
+  if (!rc) cudaMemcpy2DAsync(recv, bytes, out, bytes + 1, bytes, s->world, cudaMemcpyDeviceToDevice, st);
+  cudaFreeAsync(in, st);
+  cudaFreeAsync(out, st);
+  return from_rc(rc, "ncclAllGather");
+}
+
+ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclReduceScatter, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); return f(send, recv, recvcount, dt, op, s->real, st); }
+  b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
+  if (native_dt(dt, &bdt) && native_op((int)op, s->world, &bop, &scale))
+    return from_rc(b200mpi_reduce_scatter(s->mine, send, recv, recvcount, bdt, bop, scale, st), "ncclReduceScatter");
+  const size_t es = dt_size(dt);
+  void* tmp = nullptr;
+  if (cudaMallocAsync(&tmp, recvcount * s->world * es, st) != cudaSuccess) return err(ncclUnhandledCudaError, "scratch");
+  ncclResult_t r = generic_allreduce(s, send, tmp, recvcount * s->world, dt, (int)op, st);
+  if (r == ncclSuccess) cudaMemcpyAsync(recv, (char*)tmp + (size_t)s->rank * recvcount * es, recvcount * es, cudaMemcpyDeviceToDevice, st);
+  cudaFreeAsync(tmp, st);
+  return r;
+}
+
+ncclResult_t ncclAlltoAll(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclAlltoAll, const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t); return f ? f(send, recv, count, dt, s->real, st) : err(ncclInvalidUsage, "ncclAlltoAll missing in real NCCL"); }
+  const size_t bytes = count * dt_size(dt);
+  if (bytes % 2) return err(ncclInvalidArgument, "alltoall payload must be an even number of bytes");
+  return from_rc(b200mpi_alltoall(s->mine, send, recv, bytes / 2, B200MPI_BF16, st), "ncclAlltoAll");
+}
+
+ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclSend, const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(buf, count, dt, peer, s->real, st); }
+  return err(ncclInvalidUsage, "point-to-point ncclSend on a b200mpi communicator: not provided (set B200MPI_ALGO=nccl for this process group)");
+}
+ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclRecv, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(buf, count, dt, peer, s->real, st); }
+  return err(ncclInvalidUsage, "point-to-point ncclRecv on a b200mpi communicator: not provided (set B200MPI_ALGO=nccl for this process group)");
+}
+
+ncclResult_t ncclMemAlloc(void** ptr, size_t size) { return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemAlloc"); }
+ncclResult_t ncclMemFree(void* ptr) { return cudaFree(ptr) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemFree"); }
+ncclResult_t ncclCommRegister(const ncclComm_t c, void* buff, size_t size, void** handle) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclCommRegister, ncclComm_t, void*, size_t, void**); return f(s->real, buff, size, handle); }
+  if (handle) *handle = nullptr;  // unregistered buffers go through the staging window inside the kernel
+  return ncclSuccess;
+}
+ncclResult_t ncclCommDeregister(const ncclComm_t c, void* handle) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclCommDeregister, ncclComm_t, void*); return f(s->real, handle); }
+  return ncclSuccess;
+}
+ncclResult_t ncclCommWindowRegister(ncclComm_t c, void* buff, size_t size, void** win, int flags) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclCommWindowRegister, ncclComm_t, void*, size_t, void**, int); return f ? f(s->real, buff, size, win, flags) : ncclSuccess; }
+  if (win) *win = nullptr;
+  return ncclSuccess;
+}
+ncclResult_t ncclCommWindowDeregister(ncclComm_t c, void* win) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclCommWindowDeregister, ncclComm_t, void*); return f ? f(s->real, win) : ncclSuccess; }
+  return ncclSuccess;
+}
+ncclResult_t ncclDevCommCreate(ncclComm_t, const void*, void*) { return err(ncclInvalidUsage, "device-side communicators are not provided by the b200mpi shim"); }
+ncclResult_t ncclDevCommDestroy(ncclComm_t, const void*) { return ncclSuccess; }
+
+}  // extern "C"

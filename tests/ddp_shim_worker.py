@@ -1,0 +1,85 @@
+"""Unmodified torch.distributed (ProcessGroupNCCL) + DDP script, run with
+LD_PRELOAD=libb200mpi_nccl.so: its NCCL calls must resolve to b200mpi kernels and
+give the same numbers as plain NCCL semantics."""
+import ctypes
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dev = int(os.environ["LOCAL_RANK"]) % torch.cuda.device_count()
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    fails = 0
+    # allreduce: float sum / avg / max, int64 sum, bool-ish uint8
+    for dtype in (torch.float32, torch.bfloat16, torch.float16):
+        x = torch.full((100003,), float(rank + 1), device="cuda", dtype=dtype)
+        dist.all_reduce(x)
+        fails += int(not torch.allclose(x.float(), torch.full_like(x, world * (world + 1) / 2).float()))
+    x = torch.full((1000,), float(rank + 1), device="cuda")
+    dist.all_reduce(x, op=dist.ReduceOp.AVG)
+    fails += int(not torch.allclose(x, torch.full_like(x, (world + 1) / 2)))
+    x = torch.arange(10, device="cuda", dtype=torch.float32) * (rank + 1)
+    dist.all_reduce(x, op=dist.ReduceOp.MAX)
+    fails += int(not torch.equal(x, torch.arange(10, device="cuda", dtype=torch.float32) * world))
+    xi = torch.full((17,), rank + 1, device="cuda", dtype=torch.int64)
+    dist.all_reduce(xi)
+    fails += int(not torch.equal(xi, torch.full_like(xi, world * (world + 1) // 2)))
+    xb = torch.tensor([rank == 0, True, False], device="cuda", dtype=torch.uint8)
+    dist.all_reduce(xb, op=dist.ReduceOp.MIN)
+    fails += int(xb.tolist() != [1 if world == 1 else 0, 1, 0])
+    # broadcast / allgather / reduce_scatter / reduce / barrier
+    b = torch.arange(1001, device="cuda", dtype=torch.float64) if rank == 0 else torch.zeros(1001, device="cuda", dtype=torch.float64)
+    dist.broadcast(b, src=0)
+    fails += int(not torch.equal(b, torch.arange(1001, device="cuda", dtype=torch.float64)))
+    g = [torch.empty(5, device="cuda", dtype=torch.int32) for _ in range(world)]
+    dist.all_gather(g, torch.full((5,), rank, device="cuda", dtype=torch.int32))
+    fails += int([int(t[0]) for t in g] != list(range(world)))
+    out = torch.empty(8, device="cuda")
+    dist.reduce_scatter_tensor(out, torch.ones(8 * world, device="cuda") * (rank + 1))
+    fails += int(not torch.allclose(out, torch.full_like(out, world * (world + 1) / 2)))
+    r = torch.ones(33, device="cuda") * (rank + 1)
+    dist.reduce(r, dst=0)
+    if rank == 0:
+        fails += int(not torch.allclose(r, torch.full_like(r, world * (world + 1) / 2)))
+    dist.barrier()
+    # DDP training: identical to a single-process run on the concatenated batch
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 10)).cuda()
+    ref = nn.Sequential(nn.Linear(64, 128), nn.ReLU(), nn.Linear(128, 10)).cuda()
+    ref.load_state_dict(model.state_dict())
+    ddp = nn.parallel.DistributedDataParallel(model, device_ids=[dev])
+    opt, ropt = torch.optim.SGD(ddp.parameters(), lr=0.1), torch.optim.SGD(ref.parameters(), lr=0.1)
+    g0 = torch.Generator(device="cuda").manual_seed(5)
+    for _ in range(5):
+        xs = torch.randn(world * 16, 64, device="cuda", generator=g0)
+        ys = torch.randint(0, 10, (world * 16,), device="cuda", generator=g0)
+        opt.zero_grad()
+        nn.functional.cross_entropy(ddp(xs[rank * 16:(rank + 1) * 16]), ys[rank * 16:(rank + 1) * 16]).backward()
+        opt.step()
+        ropt.zero_grad()
+        nn.functional.cross_entropy(ref(xs), ys).backward()
+        ropt.step()
+    for p, q in zip(model.parameters(), ref.parameters()):
+        fails += int(not torch.allclose(p, q, rtol=1e-4, atol=1e-5))
+    torch.cuda.synchronize()
+    injected = "b200mpi" in os.environ.get("LD_PRELOAD", "")
+    calls = fwd = -1
+    if injected:
+        lib = ctypes.CDLL(os.environ["LD_PRELOAD"].split(":")[0])
+        lib.b200mpi_shim_calls.restype = lib.b200mpi_shim_forwarded.restype = ctypes.c_uint64
+        calls, fwd = lib.b200mpi_shim_calls(), lib.b200mpi_shim_forwarded()
+        if os.environ.get("B200MPI_ALGO") != "nccl":
+            fails += int(calls == 0 or fwd != 0)  # our kernels ran, nothing fell through to real NCCL
+    print(f"[rank {rank}] ddp_shim_worker failures={fails} shim_calls={calls} forwarded={fwd}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()

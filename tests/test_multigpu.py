@@ -14,3 +14,17 @@ def test_multiprocess_collectives():
     n = min(torch.cuda.device_count(), 8)
     rcs = launch(n, [os.path.join(HERE, "mp_worker.py")], timeout=240)
     assert rcs == [0] * n
+
+
+def test_ld_preload_nccl_shim_under_torch_ddp():
+    """Unmodified torch.distributed + DDP with LD_PRELOAD=libb200mpi_nccl.so (north star: LD-injection)."""
+    sys.path.insert(0, HERE)
+    from mp_launch import launch
+    shim = os.path.join(os.path.dirname(HERE), "mpi_operator_b200", "lib", "libb200mpi_nccl.so")
+    assert os.path.exists(shim), "libb200mpi_nccl.so not built"
+    n = min(torch.cuda.device_count(), 8)
+    rcs = launch(n, [os.path.join(HERE, "ddp_shim_worker.py")], timeout=240, extra_env={"LD_PRELOAD": shim})
+    assert rcs == [0] * n
+    # baseline mode: same shim, everything forwarded to the real NCCL
+    rcs = launch(n, [os.path.join(HERE, "ddp_shim_worker.py")], timeout=240, extra_env={"LD_PRELOAD": shim, "B200MPI_ALGO": "nccl"})
+    assert rcs == [0] * n
