@@ -45,4 +45,26 @@ sass: $(LIBDIR)/libb200mpi.so
 clean:
 	rm -rf $(LIBDIR)/*.so $(BINDIR)/*
 
-.PHONY: all native sass clean
+# ---- developer targets (reference Makefile:64-98: fmt, vet, test, test_e2e, generate, verify-generate) ----
+test:
+	python -m pytest tests -x -q -m "not gpu"
+
+test_gpu:
+	python -m pytest tests -x -q -m gpu
+
+test_e2e: all
+	python -m mpi_operator_b200.cmd.mpijobctl run -f examples/pi/pi.yaml --fake-gpus 0
+
+generate:
+	python hack/generate.py
+
+verify-generate:
+	python hack/generate.py --verify
+
+lint:
+	python -m compileall -q mpi_operator_b200 tests bench.py __graft_entry__.py
+
+sanitize: all
+	compute-sanitizer --tool racecheck python tools/profile_kernels.py
+
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize

@@ -32,6 +32,8 @@ class _ApplyConfiguration:
             return
         for f in dataclasses.fields(cls._model):
             json_name = f.metadata.get("json", _camel(f.name))
+            if f"with_{f.name}" in cls.__dict__:
+                continue  # hand-written accumulating setter wins
 
             def setter(self, value, _k=json_name):
                 self._fields[_k] = value

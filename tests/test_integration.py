@@ -189,7 +189,7 @@ def test_gpu_slots_gang_and_release(gang_op):
     launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-launcher")][0]
     assert '"b-worker-0": [' in op.agent.logs("default", launcher["metadata"]["name"])
     wait_for(lambda: op.agent.alloc.free_gpus == 4, what="all GPUs released")
-    assert op.store.list("volcano-podgroups", "default") == []  # PodGroup deleted on finish-with-cleanup
+    wait_for(lambda: op.store.list("volcano-podgroups", "default") == [], what="PodGroups deleted on finish-with-cleanup")
 
 
 def test_unschedulable_min_resources_then_cleared(gang_op):

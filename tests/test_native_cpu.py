@@ -1,0 +1,135 @@
+"""Native CPU components: mpirun (csrc/spawner/mpirun.cc), libmpi shim + pi, shm rendezvous,
+launch env contract, OpenAPI/CRD generation, entrypoint.sh."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(REPO, "mpi_operator_b200", "bin")
+MPIRUN = os.path.join(BIN, "mpirun")
+pytestmark = pytest.mark.skipif(not os.path.exists(MPIRUN), reason="native binaries not built (run make)")
+
+
+def run(args, env=None, timeout=60):
+    e = dict(os.environ)
+    e.pop("OMPI_MCA_orte_default_hostfile", None)
+    e.update(env or {})
+    return subprocess.run(args, env=e, capture_output=True, text=True, timeout=timeout)
+
+
+def test_mpirun_rank_env_all_dialects_and_flags():
+    r = run([MPIRUN, "--allow-run-as-root", "-np", "3", "-bind-to", "none", "-map-by", "slot", "-x", "FOO=bar", "-x", "PATH",
+             "-mca", "pml", "ob1", "-mca", "btl", "^openib", "--tag-output", "sh", "-c",
+             "echo $OMPI_COMM_WORLD_RANK/$OMPI_COMM_WORLD_SIZE $PMI_RANK/$PMI_SIZE $RANK/$WORLD_SIZE $HOROVOD_RANK $LOCAL_RANK "
+             "$FOO $OMPI_MCA_pml $OMPI_MCA_btl $K_MPI_JOB_ROLE $MASTER_ADDR"])
+    assert r.returncode == 0, r.stderr
+    lines = sorted(r.stdout.strip().splitlines())
+    assert lines == [f"[1,{i}]<stdout>:{i}/3 {i}/3 {i}/3 {i} {i} bar ob1 ^openib worker 127.0.0.1" for i in range(3)]
+
+
+def test_mpirun_hostfile_dialects_and_slot_placement(tmp_path):
+    hf = tmp_path / "hostfile"
+    hf.write_text("job-worker-0.job.ns.svc slots=2\njob-worker-1.job.ns.svc slots=2\n")
+    r = run([MPIRUN, "--hostfile", str(hf), "sh", "-c", "echo $OMPI_COMM_WORLD_RANK $B200MPI_HOSTNAME $OMPI_COMM_WORLD_LOCAL_RANK $OMPI_COMM_WORLD_LOCAL_SIZE"])
+    assert sorted(r.stdout.split("\n")[:-1]) == ["0 job-worker-0 0 2", "1 job-worker-0 1 2", "2 job-worker-1 0 2", "3 job-worker-1 1 2"]
+    hydra = tmp_path / "hydra"
+    hydra.write_text("a.b.c:1\nd.e.f:1\n")
+    r = run([MPIRUN, "sh", "-c", "echo $PMI_RANK $B200MPI_HOSTNAME"], env={"HYDRA_HOST_FILE": str(hydra)})
+    assert sorted(r.stdout.split()) == sorted("0 a 1 d".split())
+    r = run([MPIRUN, "sh", "-c", "echo $PMI_SIZE"], env={"I_MPI_HYDRA_HOST_FILE": str(hydra), "I_MPI_PERHOST": "3"})
+    assert r.stdout.split() == ["2", "2"]  # explicit host:n wins over I_MPI_PERHOST
+
+
+def test_mpirun_gpu_pinning_from_slots_file(tmp_path):
+    hf = tmp_path / "hostfile"
+    hf.write_text("j-worker-0.j.d.svc slots=1\nj-worker-1.j.d.svc slots=1\n")
+    slots = tmp_path / "slots.json"
+    slots.write_text(json.dumps({"hosts": {"j-worker-0": [3], "j-worker-1": [5]}}))
+    r = run([MPIRUN, "--hostfile", str(hf), "sh", "-c", "echo $RANK $LOCAL_RANK $CUDA_VISIBLE_DEVICES $B200MPI_GPU"],
+            env={"B200MPI_SLOTS_FILE": str(slots), "CUDA_VISIBLE_DEVICES": "", "NVIDIA_VISIBLE_DEVICES": ""})
+    assert sorted(r.stdout.strip().splitlines()) == ["0 0 3,5 3", "1 1 3,5 5"]
+
+
+def test_mpirun_failure_propagation_kills_siblings_and_reports():
+    r = run([MPIRUN, "-np", "3", "sh", "-c", "if [ $RANK = 1 ]; then echo dying >&2; exit 7; fi; sleep 30"], timeout=20)
+    assert r.returncode == 7 and "dying" in r.stderr and "exited with non-zero status" in r.stderr
+    r = run([MPIRUN, "-np", "1", "/definitely/not/here"])
+    assert r.returncode == 127
+
+
+def test_mpirun_image_relative_path_falls_back_to_path_lookup():
+    r = run([MPIRUN, "-n", "2", "/home/mpiuser/pi", "20000"], env={"PATH": BIN + os.pathsep + os.environ["PATH"], "B200MPI_JOB_ID": f"t-{os.getpid()}"})
+    assert r.returncode == 0 and "pi is approximately 3." in r.stdout
+
+
+def test_libmpi_collectives_via_c_program(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <mpi.h>
+#include <stdio.h>
+#include <string.h>
+int main(int argc, char** argv) {
+  MPI_Init(&argc, &argv);
+  int r, n; MPI_Comm_rank(MPI_COMM_WORLD, &r); MPI_Comm_size(MPI_COMM_WORLD, &n);
+  double x = r + 1.0, s = 0; MPI_Allreduce(&x, &s, 1, MPI_DOUBLE, MPI_SUM, MPI_COMM_WORLD);
+  int mx = r, gmx = -1; MPI_Reduce(&mx, &gmx, 1, MPI_INT, MPI_MAX, 0, MPI_COMM_WORLD);
+  char big[200000]; memset(big, r == 2 ? 'z' : 'a', sizeof big); MPI_Bcast(big, sizeof big, MPI_CHAR, 2, MPI_COMM_WORLD);
+  int all[16]; MPI_Allgather(&r, 1, MPI_INT, all, 1, MPI_INT, MPI_COMM_WORLD);
+  long long v = 5; MPI_Allreduce(MPI_IN_PLACE, &v, 1, MPI_LONG_LONG, MPI_PROD, MPI_COMM_WORLD);
+  MPI_Barrier(MPI_COMM_WORLD);
+  int ok = (s == n * (n + 1) / 2.0) && big[199999] == 'z' && all[n - 1] == n - 1 && (r != 0 || gmx == n - 1) && v == 625;
+  printf("rank %d ok=%d\n", r, ok);
+  MPI_Finalize();
+  return ok ? 0 : 1;
+}''')
+    exe = tmp_path / "t"
+    inc, lib = os.path.join(REPO, "mpi_operator_b200", "include"), os.path.join(REPO, "mpi_operator_b200", "lib")
+    subprocess.run(["gcc", "-O1", f"-I{inc}", str(src), "-o", str(exe), f"-L{lib}", "-lmpi", f"-Wl,-rpath,{lib}"], check=True)
+    r = run([MPIRUN, "-np", "4", str(exe)], env={"B200MPI_JOB_ID": f"libmpi-{os.getpid()}"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert sorted(r.stdout.strip().splitlines()) == [f"rank {i} ok=1" for i in range(4)]
+
+
+def test_launch_env_contract_roundtrip():
+    from mpi_operator_b200.launch.env import build_rank_env, rank_info_from_env
+    e = build_rank_env(rank=3, world_size=8, local_rank=1, local_size=2, node_rank=1, job_id="ns.job", gpu=5)
+    for k in ("OMPI_COMM_WORLD_RANK", "PMI_RANK", "RANK", "HOROVOD_RANK", "B200MPI_RANK"):
+        assert e[k] == "3"
+    assert e["K_MPI_JOB_ROLE"] == "worker" and e["B200MPI_GPU"] == "5"
+    info = rank_info_from_env(e)
+    assert (info.rank, info.world_size, info.local_rank, info.local_size, info.job_id) == (3, 8, 1, 2, "ns.job")
+    assert rank_info_from_env({"PMI_RANK": "2", "PMI_SIZE": "4", "MPI_LOCALRANKID": "0"}).rank == 2  # Hydra dialect alone
+    assert rank_info_from_env({"MASTER_PORT": "29500", "RANK": "1", "WORLD_SIZE": "2"}).job_id.startswith("torch-127.0.0.1-29500")
+
+
+def test_openapi_crd_and_generated_files_are_current():
+    from mpi_operator_b200.api import openapi
+    crd = openapi.crd()
+    v = crd["spec"]["versions"][0]
+    assert crd["spec"]["scope"] == "Namespaced" and v["served"] and v["storage"] and v["subresources"] == {"status": {}}
+    spec = v["schema"]["openAPIV3Schema"]["properties"]["spec"]
+    assert spec["required"] == ["mpiReplicaSpecs"]
+    assert spec["properties"]["mpiImplementation"]["enum"] == ["OpenMPI", "Intel", "MPICH"] and spec["properties"]["mpiImplementation"]["default"] == "OpenMPI"
+    assert spec["properties"]["slotsPerWorker"]["default"] == 1 and spec["properties"]["sshAuthMountPath"]["default"] == "/root/.ssh"
+    assert spec["properties"]["runPolicy"]["properties"]["suspend"]["default"] is False
+    conds = v["schema"]["openAPIV3Schema"]["properties"]["status"]["properties"]["conditions"]
+    assert conds["x-kubernetes-list-type"] == "map" and conds["x-kubernetes-list-map-keys"] == ["type"]
+    assert len(openapi.swagger()["definitions"]) == 9
+    assert subprocess.run([sys.executable, os.path.join(REPO, "hack/generate.py"), "--verify"]).returncode == 0
+    assert subprocess.run([sys.executable, os.path.join(REPO, "hack/gen_sdk.py")], capture_output=True).returncode == 0
+
+
+def test_entrypoint_waits_for_slot_map(tmp_path):
+    hf = tmp_path / "hostfile"
+    hf.write_text("j-worker-0.j.d.svc:1\n")
+    slots = tmp_path / "slots.json"
+    slots.write_text('{"hosts": {"j-worker-0": [0]}}')
+    ep = os.path.join(REPO, "build/base/entrypoint.sh")
+    r = run(["bash", ep, "echo", "started"], env={"K_MPI_JOB_ROLE": "launcher", "HYDRA_HOST_FILE": str(hf), "B200MPI_SLOTS_FILE": str(slots)})
+    assert r.returncode == 0 and r.stdout.strip() == "started"
+    slots.write_text('{"hosts": {"other": [0]}}')
+    r = run(["bash", ep, "echo", "started"], env={"K_MPI_JOB_ROLE": "launcher", "HYDRA_HOST_FILE": str(hf), "B200MPI_SLOTS_FILE": str(slots)}, timeout=240)
+    assert r.returncode != 0 and "never became ready" in r.stderr

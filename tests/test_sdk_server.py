@@ -1,0 +1,112 @@
+"""SDK models / ApiClient (reference: sdk/python/v2beta1/test/*.py stubs + mpijob/api_client.py) and the
+daemon's REST surface, leader election, healthz, metrics (cmd/mpi-operator/app/server.go)."""
+import json
+import socket
+import time
+import urllib.request
+
+import pytest
+
+import mpijob
+from mpi_operator_b200.cmd.options import ServerOption, parse
+from mpi_operator_b200.cmd.server import LeaderElector, Operator
+from mpi_operator_b200.client import ObjectStore
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_models_required_fields_equality_and_serialisation():
+    with pytest.raises(ValueError):
+        mpijob.V2beta1JobCondition(type="Created")  # status is required
+    with pytest.raises(ValueError):
+        mpijob.V2beta1MPIJobSpec()  # mpi_replica_specs is required
+    with pytest.raises(ValueError):
+        mpijob.V2beta1MPIJobList()
+    a = mpijob.V2beta1RunPolicy(clean_pod_policy="Running", backoff_limit=3)
+    b = mpijob.V2beta1RunPolicy(clean_pod_policy="Running", backoff_limit=3)
+    assert a == b and not (a != b) and a != mpijob.V2beta1RunPolicy(clean_pod_policy="All")
+    assert a.to_dict()["clean_pod_policy"] == "Running" and "Running" in a.to_str() and repr(a) == a.to_str()
+    assert mpijob.V2beta1MPIJobSpec.attribute_map["ssh_auth_mount_path"] == "sshAuthMountPath"
+    assert mpijob.V2beta1MPIJobSpec.openapi_types["mpi_replica_specs"] == "dict(str, V2beta1ReplicaSpec)"
+    job = mpijob.V2beta1MPIJob(api_version="kubeflow.org/v2beta1", kind="MPIJob", metadata=mpijob.V1ObjectMeta(name="x"),
+                               spec=mpijob.V2beta1MPIJobSpec(slots_per_worker=2, mpi_replica_specs={
+                                   "Launcher": mpijob.V2beta1ReplicaSpec(replicas=1, template={"spec": {"containers": [{"name": "c"}]}})}))
+    body = mpijob.ApiClient().sanitize_for_serialization(job)
+    assert body == {"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "x"},
+                    "spec": {"slotsPerWorker": 2, "mpiReplicaSpecs": {"Launcher": {"replicas": 1, "template": {"spec": {"containers": [{"name": "c"}]}}}}}}
+    back = mpijob.ApiClient().deserialize(json.dumps(body), "V2beta1MPIJob")
+    assert isinstance(back.spec.mpi_replica_specs["Launcher"], mpijob.V2beta1ReplicaSpec) and back.spec.slots_per_worker == 2
+
+
+def test_configuration_and_exceptions():
+    c = mpijob.Configuration(host="http://127.0.0.1:1")
+    mpijob.Configuration.set_default(c)
+    assert mpijob.Configuration.get_default_copy().host == "http://127.0.0.1:1"
+    mpijob.Configuration.set_default(None)
+    assert "Python SDK Debug Report" in c.to_debug_report()
+    with pytest.raises(mpijob.ApiException) as e:
+        mpijob.MPIJobClient("127.0.0.1:1").list()
+    assert e.value.status == 0 and "daemon running" in str(e.value)
+    assert str(mpijob.ApiValueError("bad", path_to_item=["a", 0, "b"])) == "bad at ['a'][0]['b']"
+
+
+def test_options_defaults_match_reference_flags():
+    o = parse([])
+    assert (o.threadiness, o.monitoring_port, o.lock_namespace, o.qps, o.burst, o.controller_rate_limit, o.controller_burst) == (2, 0, "mpi-operator", 5, 10, 10, 100)
+    o = parse(["--gang-scheduling", "volcano", "--namespace", "ns", "--cluster-domain", "cluster.local", "--threadiness", "4",
+               "--kube-api-qps", "50", "--master", "https://x", "--kubeConfig", "/k", "-alsologtostderr".replace("-a", "--a")])
+    assert (o.gang_scheduling_name, o.namespace, o.cluster_domain, o.threadiness, o.qps) == ("volcano", "ns", "cluster.local", 4, 50)
+
+
+def test_leader_election_is_exclusive_and_records_lease(tmp_path):
+    store = ObjectStore()
+    a = LeaderElector(store, str(tmp_path), "mpi-operator", "a")
+    b = LeaderElector(store, str(tmp_path), "mpi-operator", "b")
+    assert a.try_acquire() and not b.try_acquire()
+    lease = store.get("leases", "mpi-operator", "mpi-operator")
+    assert lease["spec"]["holderIdentity"] == "a" and lease["spec"]["leaseDurationSeconds"] == 15
+    assert a.healthy()
+    a.release()
+    assert b.try_acquire()
+    assert store.get("leases", "mpi-operator", "mpi-operator")["spec"]["leaseTransitions"] == 1
+    b.release()
+
+
+def test_rest_api_end_to_end_with_sdk_client(tmp_path):
+    port = _free_port()
+    op = Operator(ServerOption(fake_gpus=2, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    op.start()
+    try:
+        base = f"http://127.0.0.1:{port}"
+        assert urllib.request.urlopen(base + "/healthz").read() == b"ok"
+        assert "version" in json.load(urllib.request.urlopen(base + "/version"))
+        assert json.load(urllib.request.urlopen(base + "/topology"))["free_gpus"] == 2
+        cli = mpijob.MPIJobClient(f"127.0.0.1:{port}")
+        with pytest.raises(mpijob.ApiException):  # admission: structural validation like a CRD schema
+            cli.create({"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "bad"}, "spec": {}})
+        body = {"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "rest"},
+                "spec": {"mpiReplicaSpecs": {"Launcher": {"replicas": 1, "template": {"spec": {"containers": [
+                    {"name": "l", "command": ["sh", "-c", "echo hello from launcher"]}]}}}}}}
+        out, verb = cli.apply(body)
+        assert verb == "created" and cli.apply(body)[1] == "unchanged"
+        done = cli.wait_for_condition("rest", "Succeeded", timeout=20)
+        assert done["status"]["replicaStatuses"]["Launcher"]["succeeded"] == 1
+        assert "hello from launcher" in cli.logs("rest")
+        assert [j["metadata"]["name"] for j in cli.list()] == ["rest"]
+        assert any(e["reason"] == "MPIJobSucceeded" for e in cli.list_resource("events"))
+        text = urllib.request.urlopen(base + "/metrics").read().decode()
+        assert "mpi_operator_jobs_successful_total" in text and 'mpi_operator_job_info{launcher="rest-launcher",namespace="default"} 1.0' in text
+        cli.delete("rest")
+        time.sleep(0.2)
+        assert cli.list() == [] and cli.list_resource("jobs") == []  # owner-reference GC
+        with pytest.raises(mpijob.exceptions.NotFoundException):
+            cli.get("rest")
+    finally:
+        op.stop()
