@@ -172,6 +172,25 @@ int b200mpi_barrier(b200mpi_comm_t comm, void* stream);
 int b200mpi_scale_cast(const void* in, b200mpi_dtype_t in_dtype, void* out,
                        b200mpi_dtype_t out_dtype, size_t count, float scale, void* stream);
 
+/*
+ * Fused BatchNorm(+residual add)+ReLU, training mode, channels-last bf16 activations
+ * viewed as [M = N*H*W, C]; fp32 affine parameters and statistics (csrc/kernels/bn_act.cu).
+ * forward: z = relu(bn(x) [+ residual]); writes a 1-bit/element ReLU mask ([M*C/8] bytes),
+ * save_mean/save_invstd, updates running stats. backward: dx, optional dres (gradient of the
+ * residual branch), dweight, dbias. `workspace`: b200mpi_bn_workspace_floats(C) floats,
+ * zero-initialised once; the kernels leave it zeroed (CUDA-graph safe).
+ */
+size_t b200mpi_bn_workspace_floats(int C);
+int b200mpi_bn_supported(long long M, int C);
+int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask, const float* weight,
+                       const float* bias, float* running_mean, float* running_var, float* save_mean,
+                       float* save_invstd, float* workspace, long long M, int C, float eps, float momentum,
+                       int relu, void* stream);
+int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx, void* dres,
+                       const float* weight, const float* save_mean, const float* save_invstd,
+                       float* dweight, float* dbias, float* workspace, long long M, int C, int relu,
+                       void* stream);
+
 /* tuning */
 int b200mpi_set_tuning(b200mpi_comm_t comm, size_t oneshot_max_bytes, size_t nvls_min_bytes,
                        int max_blocks, int timeout_ms);

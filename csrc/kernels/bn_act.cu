@@ -1,0 +1,389 @@
+// Fused BatchNorm(+residual add)+ReLU for channels-last bf16 activations (sm_100a).
+//
+// Why it exists: the launch list of the flagship step (profiles/launches_resnet101_step.md)
+// shows ATen's batch-norm + elementwise kernels at ~70 % of ResNet-101's device
+// time (convolutions: ~20 %). The reference delegates the whole model to
+// tf_cnn_benchmarks/cuDNN; here the memory-bound glue between
+// convolutions is hand-written so every activation tensor is touched the
+// minimum number of times:
+//   forward : stats pass  (read x)                    + apply pass (read x [,res], write z, 1-bit mask)
+//   backward: reduce pass (read dz, x, mask)          + elemt pass (read dz, x, mask, write dx [,dres])
+// vs ATen: stats, normalise, (add,) relu  /  relu-bwd, reduce, elemt — 13 T of traffic per BN+ReLU
+// layer becomes 8 T, and the extra passes mostly hit the 126 MB L2.
+//
+// Layout: x is [M = N*H*W, C] (channels_last memory), bf16; statistics and
+// affine parameters fp32. A thread owns 8 consecutive channels (one 16-byte
+// vector); C/8 threads cover a row; a 256-thread CTA covers 2048/C rows per
+// pass. Per-channel sums are accumulated in registers with a per-channel shift
+// (first row) against cancellation, reduced through shared memory, then merged
+// across CTAs with fp32 REDG atomics; the last CTA (ticket) finalises the
+// statistics and resets the workspace, so the op is CUDA-graph capturable.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../include/b200mpi.h"
+
+namespace b200mpi {
+namespace bn {
+
+constexpr int kThreadsBN = 256;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// workspace layout (floats): acc[2][C] | coef[4][C] | ticket (as uint)
+struct WS {
+  float* acc;
+  float* coef;
+  unsigned* ticket;
+  __device__ __host__ WS(float* base, int C) : acc(base), coef(base + 2 * C), ticket(reinterpret_cast<unsigned*>(base + 6 * C)) {}
+};
+
+// Block-level reduction of two 8-channel accumulators over the `rpp` row-groups of the CTA,
+// followed by REDG atomics into the global per-channel accumulators.
+__device__ __forceinline__ void block_reduce_to_global(float (&s1)[8], float (&s2)[8], float* acc, int C, int tpr, int r, int cg, int rpp) {
+  __shared__ float red[2][kThreadsBN * 8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    red[0][(r * tpr + cg) * 8 + j] = s1[j];
+    red[1][(r * tpr + cg) * 8 + j] = s2[j];
+  }
+  __syncthreads();
+  if (r == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float a = 0.f, b = 0.f;
+      for (int q = 0; q < rpp; q++) {
+        a += red[0][(q * tpr + cg) * 8 + j];
+        b += red[1][(q * tpr + cg) * 8 + j];
+      }
+      atomicAdd(acc + cg * 8 + j, a);
+      atomicAdd(acc + C + cg * 8 + j, b);
+    }
+  }
+}
+
+__device__ __forceinline__ bool last_cta(unsigned* ticket) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// ---------------------------------------------------------------- forward ----
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_fwd_stats(const uint4* __restrict__ x, float* ws_base, long long M, int C, long long rows_per_cta,
+               const float* __restrict__ weight, const float* __restrict__ bias, float* running_mean, float* running_var,
+               float* save_mean, float* save_invstd, float eps, float momentum) {
+  WS ws(ws_base, C);
+  const int tpr = C >> 3, rpp = kThreadsBN / tpr;
+  const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
+  float K[8], s1[8], s2[8];
+  unpack8(x[cg], K);  // per-channel shift = first row: sums of (x-K) do not cancel catastrophically
+#pragma unroll
+  for (int j = 0; j < 8; j++) s1[j] = s2[j] = 0.f;
+  const long long m0 = (long long)blockIdx.x * rows_per_cta;
+  const long long m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  for (long long m = m0 + r; m < m1; m += (long long)rpp * kUnroll) {
+    uint4 v[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) v[u] = ldg_stream(x + mm * tpr + cg);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float d = f[j] - K[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+      }
+    }
+  }
+  block_reduce_to_global(s1, s2, ws.acc, C, tpr, r, cg, rpp);
+  if (last_cta(ws.ticket)) {
+    const float inv_m = 1.0f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float S1 = __ldcg(ws.acc + c), S2 = __ldcg(ws.acc + C + c);
+      const float k = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[c]);
+      const float d = S1 * inv_m;
+      const float mean = k + d;
+      float var = fmaf(-d, d, S2 * inv_m);
+      var = var > 0.f ? var : 0.f;
+      const float invstd = rsqrtf(var + eps);
+      save_mean[c] = mean;
+      save_invstd[c] = invstd;
+      if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+      }
+      const float a = (weight ? weight[c] : 1.f) * invstd;
+      ws.coef[c] = a;
+      ws.coef[C + c] = (bias ? bias[c] : 0.f) - mean * a;
+      ws.acc[c] = 0.f;
+      ws.acc[C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *ws.ticket = 0u;
+  }
+}
+
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_fwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ y, uint8_t* __restrict__ mask,
+               const float* __restrict__ coef, long long M, int C, long long rows_per_cta) {
+  const int tpr = C >> 3, rpp = kThreadsBN / tpr;
+  const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = coef[cg * 8 + j];
+    b[j] = coef[C + cg * 8 + j];
+  }
+  const long long m0 = (long long)blockIdx.x * rows_per_cta;
+  const long long m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  for (long long m = m0 + r; m < m1; m += (long long)rpp * kUnroll) {
+    uint4 v[kUnroll], w[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        v[u] = ldg_stream(x + mm * tpr + cg);
+        if (RES) w[u] = ldg_stream(res + mm * tpr + cg);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        float f[8], g[8];
+        unpack8(v[u], f);
+        if (RES) unpack8(w[u], g);
+        unsigned bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          float z = fmaf(a[j], f[j], b[j]);
+          if (RES) z += g[j];
+          if (RELU) {
+            bits |= (z > 0.f ? 1u : 0u) << j;
+            z = z > 0.f ? z : 0.f;
+          }
+          f[j] = z;
+        }
+        stg_stream(y + mm * tpr + cg, pack8(f));
+        if (RELU) mask[mm * tpr + cg] = (uint8_t)bits;
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------- backward ----
+template <bool RELU>
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_bwd_reduce(const uint4* __restrict__ dz, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, float* ws_base,
+                long long M, int C, long long rows_per_cta, const float* __restrict__ weight, const float* __restrict__ save_mean,
+                const float* __restrict__ save_invstd, float* dweight, float* dbias) {
+  WS ws(ws_base, C);
+  const int tpr = C >> 3, rpp = kThreadsBN / tpr;
+  const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
+  float mu[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    mu[j] = save_mean[cg * 8 + j];
+    s1[j] = s2[j] = 0.f;
+  }
+  const long long m0 = (long long)blockIdx.x * rows_per_cta;
+  const long long m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  for (long long m = m0 + r; m < m1; m += (long long)rpp * kUnroll) {
+    uint4 g4[kUnroll], x4[kUnroll];
+    unsigned mk[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        g4[u] = ldg_stream(dz + mm * tpr + cg);
+        x4[u] = ldg_stream(x + mm * tpr + cg);
+        mk[u] = RELU ? mask[mm * tpr + cg] : 0xffu;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        float g[8], f[8];
+        unpack8(g4[u], g);
+        unpack8(x4[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gj = (mk[u] >> j) & 1u ? g[j] : 0.f;
+          s1[j] += gj;
+          s2[j] = fmaf(gj, f[j] - mu[j], s2[j]);  // * invstd applied once at finalise
+        }
+      }
+    }
+  }
+  block_reduce_to_global(s1, s2, ws.acc, C, tpr, r, cg, rpp);
+  if (last_cta(ws.ticket)) {
+    const float inv_m = 1.0f / (float)M;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float S1 = __ldcg(ws.acc + c);
+      const float invstd = save_invstd[c];
+      const float S2 = __ldcg(ws.acc + C + c) * invstd;  // sum g * xhat
+      if (dbias) dbias[c] = S1;
+      if (dweight) dweight[c] = S2;
+      ws.coef[c] = (weight ? weight[c] : 1.f) * invstd;  // a
+      ws.coef[C + c] = S1 * inv_m;                        // mean(g)
+      ws.coef[2 * C + c] = S2 * inv_m * invstd;           // mean(g*xhat) * invstd
+      ws.coef[3 * C + c] = save_mean[c];
+      ws.acc[c] = 0.f;
+      ws.acc[C + c] = 0.f;
+    }
+    if (threadIdx.x == 0) *ws.ticket = 0u;
+  }
+}
+
+template <bool RELU, bool RES>
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_bwd_elemt(const uint4* __restrict__ dz, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, uint4* __restrict__ dx,
+               uint4* __restrict__ dres, const float* __restrict__ coef, long long M, int C, long long rows_per_cta) {
+  const int tpr = C >> 3, rpp = kThreadsBN / tpr;
+  const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
+  float a[8], gm[8], c3[8], mu[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = coef[cg * 8 + j];
+    gm[j] = coef[C + cg * 8 + j];
+    c3[j] = coef[2 * C + cg * 8 + j];
+    mu[j] = coef[3 * C + cg * 8 + j];
+  }
+  const long long m0 = (long long)blockIdx.x * rows_per_cta;
+  const long long m1 = m0 + rows_per_cta < M ? m0 + rows_per_cta : M;
+  for (long long m = m0 + r; m < m1; m += (long long)rpp * kUnroll) {
+    uint4 g4[kUnroll], x4[kUnroll];
+    unsigned mk[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        g4[u] = ldg_stream(dz + mm * tpr + cg);
+        x4[u] = ldg_stream(x + mm * tpr + cg);
+        mk[u] = RELU ? mask[mm * tpr + cg] : 0xffu;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; u++) {
+      const long long mm = m + (long long)u * rpp;
+      if (mm < m1) {
+        float g[8], f[8];
+        unpack8(g4[u], g);
+        unpack8(x4[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float gj = (mk[u] >> j) & 1u ? g[j] : 0.f;
+          g[j] = gj;                                              // gradient w.r.t. the residual branch
+          f[j] = a[j] * (gj - gm[j] - (f[j] - mu[j]) * c3[j]);    // gradient w.r.t. the BN input
+        }
+        stg_stream(dx + mm * tpr + cg, pack8(f));
+        if (RES) stg_stream(dres + mm * tpr + cg, pack8(g));
+      }
+    }
+  }
+}
+
+static void plan(long long M, int C, int cap, int* grid, long long* rows_per_cta) {
+  const int tpr = C / 8, rpp = kThreadsBN / tpr;
+  const long long min_rows = (long long)rpp * kUnroll;
+  long long g = (M + min_rows - 1) / min_rows;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  long long rows = (M + g - 1) / g;
+  rows = (rows + rpp - 1) / rpp * rpp;
+  g = (M + rows - 1) / rows;
+  *grid = (int)g;
+  *rows_per_cta = rows;
+}
+
+}  // namespace bn
+}  // namespace b200mpi
+
+using namespace b200mpi::bn;
+
+extern "C" {
+
+size_t b200mpi_bn_workspace_floats(int C) { return (size_t)6 * C + 4; }
+
+int b200mpi_bn_supported(long long M, int C) { return (C % 8 == 0 && C >= 8 && C / 8 <= kThreadsBN && kThreadsBN % (C / 8) == 0 && M >= 1) ? 1 : 0; }
+
+int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask, const float* weight, const float* bias,
+                       float* running_mean, float* running_var, float* save_mean, float* save_invstd, float* workspace,
+                       long long M, int C, float eps, float momentum, int relu, void* stream_) {
+  if (!b200mpi_bn_supported(M, C)) return B200MPI_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream_;
+  int grid;
+  long long rows;
+  plan(M, C, 296, &grid, &rows);
+  k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, workspace, M, C, rows, weight, bias, running_mean, running_var,
+                                             save_mean, save_invstd, eps, momentum);
+  plan(M, C, 1184, &grid, &rows);
+  const float* coef = workspace + 2 * C;
+  if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
+  else if (relu) k_bn_fwd_apply<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
+  else if (residual) k_bn_fwd_apply<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, nullptr, coef, M, C, rows);
+  else k_bn_fwd_apply<false, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, nullptr, coef, M, C, rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : B200MPI_ERR_CUDA;
+}
+
+int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx, void* dres, const float* weight,
+                       const float* save_mean, const float* save_invstd, float* dweight, float* dbias, float* workspace,
+                       long long M, int C, int relu, void* stream_) {
+  if (!b200mpi_bn_supported(M, C)) return B200MPI_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream_;
+  int grid;
+  long long rows;
+  plan(M, C, 296, &grid, &rows);
+  if (relu) k_bn_bwd_reduce<true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, workspace, M, C, rows, weight, save_mean, save_invstd, dweight, dbias);
+  else k_bn_bwd_reduce<false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, workspace, M, C, rows, weight, save_mean, save_invstd, dweight, dbias);
+  plan(M, C, 1184, &grid, &rows);
+  const float* coef = workspace + 2 * C;
+  if (relu && dres) k_bn_bwd_elemt<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, (uint4*)dres, coef, M, C, rows);
+  else if (relu) k_bn_bwd_elemt<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, nullptr, coef, M, C, rows);
+  else if (dres) k_bn_bwd_elemt<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, (uint4*)dx, (uint4*)dres, coef, M, C, rows);
+  else k_bn_bwd_elemt<false, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, (uint4*)dx, nullptr, coef, M, C, rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : B200MPI_ERR_CUDA;
+}
+
+}  // extern "C"

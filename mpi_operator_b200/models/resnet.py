@@ -12,6 +12,8 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
+from ..ops.bn_act import bn_act
+
 
 class BasicBlock(nn.Module):
     expansion = 1
@@ -27,9 +29,8 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.bn2(self.conv2(out))
-        return self.relu(out + idt)
+        out = bn_act(self.bn1, self.conv1(x))
+        return bn_act(self.bn2, self.conv2(out), residual=idt)  # fused BN + add + ReLU
 
 
 class Bottleneck(nn.Module):
@@ -49,10 +50,19 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         idt = x if self.downsample is None else self.downsample(x)
-        out = self.relu(self.bn1(self.conv1(x)))
-        out = self.relu(self.bn2(self.conv2(out)))
-        out = self.bn3(self.conv3(out))
-        return self.relu(out + idt)
+        out = bn_act(self.bn1, self.conv1(x))
+        out = bn_act(self.bn2, self.conv2(out))
+        return bn_act(self.bn3, self.conv3(out), residual=idt)  # fused BN + add + ReLU
+
+
+class _Downsample(nn.Sequential):
+    """1x1 conv + BN on the shortcut (same parameter names as nn.Sequential(conv, bn): '0', '1')."""
+
+    def __init__(self, inplanes: int, outplanes: int, stride: int):
+        super().__init__(nn.Conv2d(inplanes, outplanes, 1, stride, bias=False), nn.BatchNorm2d(outplanes))
+
+    def forward(self, x):
+        return bn_act(self[1], self[0](x), relu=False)
 
 
 class ResNet(nn.Module):
@@ -81,15 +91,14 @@ class ResNet(nn.Module):
     def _make(self, block, planes, blocks, stride):
         down = None
         if stride != 1 or self.inplanes != planes * block.expansion:
-            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * block.expansion, 1, stride, bias=False),
-                                 nn.BatchNorm2d(planes * block.expansion))
+            down = _Downsample(self.inplanes, planes * block.expansion, stride)
         layers = [block(self.inplanes, planes, stride, down)]
         self.inplanes = planes * block.expansion
         layers += [block(self.inplanes, planes) for _ in range(1, blocks)]
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        x = self.maxpool(bn_act(self.bn1, self.conv1(x)))
         x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
         return self.fc(torch.flatten(self.avgpool(x), 1))
 

@@ -1,0 +1,96 @@
+"""Fused BatchNorm(+residual)+ReLU autograd op over csrc/kernels/bn_act.cu.
+
+``bn_act(bn_module, x, residual=None, relu=True)`` computes
+``relu(batch_norm(x) [+ residual])`` with the module's parameters and running
+statistics. The fused kernels run when x is a CUDA bf16 channels-last tensor in
+training mode with a supported channel count; anything else (CPU, eval, fp32)
+takes the plain PyTorch path, so models stay runnable everywhere and
+``state_dict`` layout is untouched.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn.functional as F
+
+
+def _lib():
+    from ..runtime import _lib as L
+    return L.lib()
+
+
+_ENABLED = os.environ.get("B200MPI_FUSED_BN", "1") != "0"
+
+
+def fused_bn_available(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
+    if not (_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and bn.training and bn.affine
+            and bn.track_running_stats and bn.momentum is not None):
+        return False
+    n, c, h, w = x.shape
+    return bool(_lib().b200mpi_bn_supported(n * h * w, c)) and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def _ws(bn: torch.nn.BatchNorm2d, device) -> torch.Tensor:
+    ws = getattr(bn, "_b200_ws", None)
+    if ws is None or ws.device != device:
+        ws = torch.zeros(int(_lib().b200mpi_bn_workspace_floats(bn.num_features)), dtype=torch.float32, device=device)
+        bn._b200_ws = ws  # plain attribute: not part of state_dict
+    return ws
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None else None
+
+
+class _BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, eps, momentum, relu):
+        n, c, h, w = x.shape
+        m = n * h * w
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        mask = torch.empty(m * c // 8, dtype=torch.uint8, device=x.device) if relu else None
+        save_mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty(c, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib().b200mpi_bn_act_fwd(x.data_ptr(), _ptr(residual), y.data_ptr(), _ptr(mask), weight.data_ptr(), bias.data_ptr(),
+                                       running_mean.data_ptr(), running_var.data_ptr(), save_mean.data_ptr(), save_invstd.data_ptr(),
+                                       ws.data_ptr(), m, c, eps, momentum, int(relu), stream)
+        if rc != 0:
+            raise RuntimeError(f"b200mpi_bn_act_fwd failed ({rc})")
+        ctx.save_for_backward(x, mask, weight, save_mean, save_invstd, ws)
+        ctx.relu, ctx.has_res = relu, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dz):
+        x, mask, weight, save_mean, save_invstd, ws = ctx.saved_tensors
+        n, c, h, w = x.shape
+        m = n * h * w
+        if dz.dtype != torch.bfloat16 or not dz.is_contiguous(memory_format=torch.channels_last):
+            dz = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty_like(x, memory_format=torch.channels_last)
+        dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
+        dw = torch.empty(c, dtype=torch.float32, device=x.device)
+        db = torch.empty(c, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib().b200mpi_bn_act_bwd(dz.data_ptr(), x.data_ptr(), _ptr(mask), dx.data_ptr(), _ptr(dres), weight.data_ptr(),
+                                       save_mean.data_ptr(), save_invstd.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                       m, c, int(ctx.relu), stream)
+        if rc != 0:
+            raise RuntimeError(f"b200mpi_bn_act_bwd failed ({rc})")
+        return dx, dres, dw, db, None, None, None, None, None, None
+
+
+def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = None, relu: bool = True) -> torch.Tensor:
+    if fused_bn_available(x, bn) and (residual is None or (residual.dtype == torch.bfloat16 and residual.shape == x.shape)):
+        if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        return _BNAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, _ws(bn, x.device), bn.eps,
+                            bn.momentum, relu)
+    out = bn(x)
+    if residual is not None:
+        out = out + residual
+    return F.relu(out) if relu else out

@@ -81,6 +81,11 @@ def lib() -> C.CDLL:
     L.b200mpi_alltoall.argtypes = [vp, vp, vp, sz, i, vp]
     L.b200mpi_barrier.argtypes = [vp, vp]
     L.b200mpi_scale_cast.argtypes = [vp, i, vp, i, sz, f, vp]
+    L.b200mpi_bn_workspace_floats.argtypes = [i]
+    L.b200mpi_bn_workspace_floats.restype = sz
+    L.b200mpi_bn_supported.argtypes = [C.c_longlong, i]
+    L.b200mpi_bn_act_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_longlong, i, f, f, i, vp]
+    L.b200mpi_bn_act_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_longlong, i, i, vp]
     L.b200mpi_set_tuning.argtypes = [vp, sz, sz, i, i]
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
     L.b200mpi_select_algo.argtypes = [vp, sz, i, i, i]
