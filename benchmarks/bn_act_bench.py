@@ -10,7 +10,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import mpi_operator_b200.ops.bn_act as ops  # noqa: E402
+import mpi_operator_b200.ops.fused_bn as ops  # noqa: E402
 
 SHAPES = [(64, 64, 112, 112, False), (64, 64, 56, 56, False), (64, 256, 56, 56, True), (64, 128, 28, 28, False),
           (64, 512, 28, 28, True), (64, 256, 14, 14, False), (64, 1024, 14, 14, True), (64, 512, 7, 7, False), (64, 2048, 7, 7, True)]

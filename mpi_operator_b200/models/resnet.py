@@ -12,7 +12,7 @@ from typing import List, Type
 import torch
 import torch.nn as nn
 
-from ..ops.bn_act import bn_act
+from ..ops.fused_bn import bn_act
 
 
 class BasicBlock(nn.Module):
