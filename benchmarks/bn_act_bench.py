@@ -40,7 +40,9 @@ def main():
         pass
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     rows = []
-    for n, c, h, w, res in SHAPES:
+    sel = os.environ.get("BN_SHAPES")
+    shapes = [SHAPES[int(i)] for i in sel.split(",")] if sel else SHAPES
+    for n, c, h, w, res in shapes:
         bn = nn.BatchNorm2d(c).cuda()
         x = torch.randn(n, c, h, w, device="cuda").to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
         r = torch.randn_like(x).requires_grad_(True) if res else None

@@ -15,9 +15,11 @@
 // affine parameters fp32. A thread owns 8 consecutive channels (one 16-byte
 // vector); C/8 threads cover a row; a 256-thread CTA covers 2048/C rows per
 // pass. Per-channel sums are accumulated in registers with a per-channel shift
-// (first row) against cancellation, reduced through shared memory, then merged
-// across CTAs with fp32 REDG atomics; the last CTA (ticket) finalises the
-// statistics and resets the workspace, so the op is CUDA-graph capturable.
+// (first row) against cancellation, reduced through shared memory with all
+// threads active, stored as one coalesced partial row per CTA (no atomics, no
+// fences: the first version's MEMBAR + same-address REDG tail cost ~20 us per
+// launch, profiles/ncu_bn_act.md) and merged by a tiny finalize kernel —
+// deterministic and CUDA-graph capturable.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -56,54 +58,52 @@ __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-// workspace layout (floats): acc[2][C] | coef[4][C] | ticket (as uint)
-struct WS {
-  float* acc;
-  float* coef;
-  unsigned* ticket;
-  __device__ __host__ WS(float* base, int C) : acc(base), coef(base + 2 * C), ticket(reinterpret_cast<unsigned*>(base + 6 * C)) {}
-};
+// workspace layout (floats): coef[4][C] | partials[kMaxParts][2C]
+// The reduce-type kernels write one row of per-CTA partial sums (plain coalesced stores: no atomics,
+// no fences, deterministic); a tiny finalize kernel merges the rows with all its threads in parallel.
+constexpr int kMaxParts = 296;
 
-// Block-level reduction of two 8-channel accumulators over the `rpp` row-groups of the CTA,
-// followed by REDG atomics into the global per-channel accumulators.
-__device__ __forceinline__ void block_reduce_to_global(float (&s1)[8], float (&s2)[8], float* acc, int C, int tpr, int r, int cg, int rpp) {
-  __shared__ float red[2][kThreadsBN * 8];
+// Intra-CTA reduction over the `rpp` row-groups, all threads active: output o = cg*16 + 2*j + stat
+// is summed over q by thread o (conflict-free smem reads), then stored to this CTA's partial row.
+__device__ __forceinline__ void block_reduce_to_partial(float (&s1)[8], float (&s2)[8], float* part_row, int C, int tpr, int r, int cg, int rpp) {
+  __shared__ float red[kThreadsBN * 16];
+  const int nout = tpr * 16;  // == 2C
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    red[0][(r * tpr + cg) * 8 + j] = s1[j];
-    red[1][(r * tpr + cg) * 8 + j] = s2[j];
+    red[r * nout + cg * 16 + 2 * j] = s1[j];
+    red[r * nout + cg * 16 + 2 * j + 1] = s2[j];
   }
   __syncthreads();
-  if (r == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float a = 0.f, b = 0.f;
-      for (int q = 0; q < rpp; q++) {
-        a += red[0][(q * tpr + cg) * 8 + j];
-        b += red[1][(q * tpr + cg) * 8 + j];
-      }
-      atomicAdd(acc + cg * 8 + j, a);
-      atomicAdd(acc + C + cg * 8 + j, b);
-    }
+  for (int o = threadIdx.x; o < nout; o += kThreadsBN) {
+    float acc = 0.f;
+    for (int q = 0; q < rpp; q++) acc += red[q * nout + o];
+    part_row[o] = acc;
   }
 }
 
-__device__ __forceinline__ bool last_cta(unsigned* ticket) {
-  __shared__ bool is_last;
-  __threadfence();
+// Merge `parts` partial rows: CTA handles 32 outputs, its 8 warps split the rows, lanes = outputs.
+// Returns (for threads with warp==0) the total for output blockIdx.x*32 + lane.
+__device__ __forceinline__ float merge_partials(const float* __restrict__ partials, int parts, int nout, int* out_index) {
+  __shared__ float sm[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 32 + lane;
+  float acc = 0.f;
+  if (o < nout)
+    for (int b = warp; b < parts; b += 8) acc += __ldcg(partials + (size_t)b * nout + o);
+  sm[warp][lane] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last;
+  float tot = 0.f;
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 0; w < 8; w++) tot += sm[w][lane];
+  }
+  *out_index = o;
+  return tot;
 }
 
 // ---------------------------------------------------------------- forward ----
 __global__ void __launch_bounds__(kThreadsBN)
-k_bn_fwd_stats(const uint4* __restrict__ x, float* ws_base, long long M, int C, long long rows_per_cta,
-               const float* __restrict__ weight, const float* __restrict__ bias, float* running_mean, float* running_var,
-               float* save_mean, float* save_invstd, float eps, float momentum) {
-  WS ws(ws_base, C);
+k_bn_fwd_stats(const uint4* __restrict__ x, float* __restrict__ partials, long long M, int C, long long rows_per_cta) {
   const int tpr = C >> 3, rpp = kThreadsBN / tpr;
   const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
   float K[8], s1[8], s2[8];
@@ -134,32 +134,39 @@ k_bn_fwd_stats(const uint4* __restrict__ x, float* ws_base, long long M, int C, 
       }
     }
   }
-  block_reduce_to_global(s1, s2, ws.acc, C, tpr, r, cg, rpp);
-  if (last_cta(ws.ticket)) {
-    const float inv_m = 1.0f / (float)M;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const float S1 = __ldcg(ws.acc + c), S2 = __ldcg(ws.acc + C + c);
-      const float k = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[c]);
-      const float d = S1 * inv_m;
-      const float mean = k + d;
-      float var = fmaf(-d, d, S2 * inv_m);
-      var = var > 0.f ? var : 0.f;
-      const float invstd = rsqrtf(var + eps);
-      save_mean[c] = mean;
-      save_invstd[c] = invstd;
-      if (running_mean) {
-        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
-        const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
-        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-      }
-      const float a = (weight ? weight[c] : 1.f) * invstd;
-      ws.coef[c] = a;
-      ws.coef[C + c] = (bias ? bias[c] : 0.f) - mean * a;
-      ws.acc[c] = 0.f;
-      ws.acc[C + c] = 0.f;
-    }
-    if (threadIdx.x == 0) *ws.ticket = 0u;
+  block_reduce_to_partial(s1, s2, partials + (size_t)blockIdx.x * 2 * C, C, tpr, r, cg, rpp);
+}
+
+// grid = ceil(2C/32): merges the partial rows, then the threads owning the (S1,S2) pair of a channel
+// produce mean / invstd / running stats / affine coefficients a, b for the apply pass.
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_fwd_finalize(const __nv_bfloat16* __restrict__ x_row0, const float* __restrict__ partials, int parts, float* __restrict__ coef,
+                  long long M, int C, const float* __restrict__ weight, const float* __restrict__ bias, float* running_mean,
+                  float* running_var, float* save_mean, float* save_invstd, float eps, float momentum) {
+  int o;
+  const float tot = merge_partials(partials, parts, 2 * C, &o);
+  if ((threadIdx.x >> 5) != 0) return;
+  const float other = __shfl_xor_sync(0xffffffffu, tot, 1);  // lanes 2j / 2j+1 hold S1 / S2 of one channel
+  if (o >= 2 * C || (o & 1)) return;
+  const int cgi = o >> 4, j = (o & 15) >> 1, c = cgi * 8 + j;
+  const float S1 = tot, S2 = other;
+  const float inv_m = 1.0f / (float)M;
+  const float k = __bfloat162float(x_row0[c]);
+  const float d = S1 * inv_m;
+  const float mean = k + d;
+  float var = fmaf(-d, d, S2 * inv_m);
+  var = var > 0.f ? var : 0.f;
+  const float invstd = rsqrtf(var + eps);
+  save_mean[c] = mean;
+  save_invstd[c] = invstd;
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
   }
+  const float a = (weight ? weight[c] : 1.f) * invstd;
+  coef[c] = a;
+  coef[C + c] = (bias ? bias[c] : 0.f) - mean * a;
 }
 
 template <bool RELU, bool RES>
@@ -214,10 +221,8 @@ k_bn_fwd_apply(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4
 // --------------------------------------------------------------- backward ----
 template <bool RELU>
 __global__ void __launch_bounds__(kThreadsBN)
-k_bn_bwd_reduce(const uint4* __restrict__ dz, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, float* ws_base,
-                long long M, int C, long long rows_per_cta, const float* __restrict__ weight, const float* __restrict__ save_mean,
-                const float* __restrict__ save_invstd, float* dweight, float* dbias) {
-  WS ws(ws_base, C);
+k_bn_bwd_reduce(const uint4* __restrict__ dz, const uint4* __restrict__ x, const uint8_t* __restrict__ mask, float* __restrict__ partials,
+                long long M, int C, long long rows_per_cta, const float* __restrict__ save_mean) {
   const int tpr = C >> 3, rpp = kThreadsBN / tpr;
   const int r = threadIdx.x / tpr, cg = threadIdx.x % tpr;
   float mu[8], s1[8], s2[8];
@@ -256,24 +261,28 @@ k_bn_bwd_reduce(const uint4* __restrict__ dz, const uint4* __restrict__ x, const
       }
     }
   }
-  block_reduce_to_global(s1, s2, ws.acc, C, tpr, r, cg, rpp);
-  if (last_cta(ws.ticket)) {
-    const float inv_m = 1.0f / (float)M;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const float S1 = __ldcg(ws.acc + c);
-      const float invstd = save_invstd[c];
-      const float S2 = __ldcg(ws.acc + C + c) * invstd;  // sum g * xhat
-      if (dbias) dbias[c] = S1;
-      if (dweight) dweight[c] = S2;
-      ws.coef[c] = (weight ? weight[c] : 1.f) * invstd;  // a
-      ws.coef[C + c] = S1 * inv_m;                        // mean(g)
-      ws.coef[2 * C + c] = S2 * inv_m * invstd;           // mean(g*xhat) * invstd
-      ws.coef[3 * C + c] = save_mean[c];
-      ws.acc[c] = 0.f;
-      ws.acc[C + c] = 0.f;
-    }
-    if (threadIdx.x == 0) *ws.ticket = 0u;
-  }
+  block_reduce_to_partial(s1, s2, partials + (size_t)blockIdx.x * 2 * C, C, tpr, r, cg, rpp);
+}
+
+__global__ void __launch_bounds__(kThreadsBN)
+k_bn_bwd_finalize(const float* __restrict__ partials, int parts, float* __restrict__ coef, long long M, int C,
+                  const float* __restrict__ weight, const float* __restrict__ save_mean, const float* __restrict__ save_invstd,
+                  float* dweight, float* dbias) {
+  int o;
+  const float tot = merge_partials(partials, parts, 2 * C, &o);
+  if ((threadIdx.x >> 5) != 0) return;
+  const float other = __shfl_xor_sync(0xffffffffu, tot, 1);
+  if (o >= 2 * C || (o & 1)) return;
+  const int cgi = o >> 4, j = (o & 15) >> 1, c = cgi * 8 + j;
+  const float inv_m = 1.0f / (float)M;
+  const float invstd = save_invstd[c];
+  const float S1 = tot, S2 = other * invstd;  // sum g, sum g * xhat
+  if (dbias) dbias[c] = S1;
+  if (dweight) dweight[c] = S2;
+  coef[c] = (weight ? weight[c] : 1.f) * invstd;  // a
+  coef[C + c] = S1 * inv_m;                        // mean(g)
+  coef[2 * C + c] = S2 * inv_m * invstd;           // mean(g*xhat) * invstd
+  coef[3 * C + c] = save_mean[c];
 }
 
 template <bool RELU, bool RES>
@@ -324,10 +333,13 @@ k_bn_bwd_elemt(const uint4* __restrict__ dz, const uint4* __restrict__ x, const 
   }
 }
 
-static void plan(long long M, int C, int cap, int* grid, long long* rows_per_cta) {
+static void plan(long long M, int C, int cap, long long bytes_per_row, int* grid, long long* rows_per_cta) {
   const int tpr = C / 8, rpp = kThreadsBN / tpr;
   const long long min_rows = (long long)rpp * kUnroll;
+  // >= 64 KiB of traffic per CTA: small tensors get few CTAs (cheap merges), large ones fill the machine
+  long long by_bytes = (M * bytes_per_row + (64 << 10) - 1) / (64 << 10);
   long long g = (M + min_rows - 1) / min_rows;
+  if (g > by_bytes) g = by_bytes;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   long long rows = (M + g - 1) / g;
@@ -344,7 +356,7 @@ using namespace b200mpi::bn;
 
 extern "C" {
 
-size_t b200mpi_bn_workspace_floats(int C) { return (size_t)6 * C + 4; }
+size_t b200mpi_bn_workspace_floats(int C) { return (size_t)4 * C + (size_t)kMaxParts * 2 * C + 4; }
 
 int b200mpi_bn_supported(long long M, int C) { return (C % 8 == 0 && C >= 8 && C / 8 <= kThreadsBN && kThreadsBN % (C / 8) == 0 && M >= 1) ? 1 : 0; }
 
@@ -353,13 +365,15 @@ int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask,
                        long long M, int C, float eps, float momentum, int relu, void* stream_) {
   if (!b200mpi_bn_supported(M, C)) return B200MPI_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream_;
+  float* coef = workspace;
+  float* partials = workspace + 4 * C;
   int grid;
   long long rows;
-  plan(M, C, 296, &grid, &rows);
-  k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, workspace, M, C, rows, weight, bias, running_mean, running_var,
-                                             save_mean, save_invstd, eps, momentum);
-  plan(M, C, 1184, &grid, &rows);
-  const float* coef = workspace + 2 * C;
+  plan(M, C, kMaxParts, 2LL * C, &grid, &rows);
+  k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, partials, M, C, rows);
+  k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>((const __nv_bfloat16*)x, partials, grid, coef, M, C, weight, bias,
+                                                            running_mean, running_var, save_mean, save_invstd, eps, momentum);
+  plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows);
   if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
   else if (relu) k_bn_fwd_apply<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
   else if (residual) k_bn_fwd_apply<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, nullptr, coef, M, C, rows);
@@ -372,13 +386,15 @@ int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx
                        long long M, int C, int relu, void* stream_) {
   if (!b200mpi_bn_supported(M, C)) return B200MPI_ERR_UNSUPPORTED;
   cudaStream_t s = (cudaStream_t)stream_;
+  float* coef = workspace;
+  float* partials = workspace + 4 * C;
   int grid;
   long long rows;
-  plan(M, C, 296, &grid, &rows);
-  if (relu) k_bn_bwd_reduce<true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, workspace, M, C, rows, weight, save_mean, save_invstd, dweight, dbias);
-  else k_bn_bwd_reduce<false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, workspace, M, C, rows, weight, save_mean, save_invstd, dweight, dbias);
-  plan(M, C, 1184, &grid, &rows);
-  const float* coef = workspace + 2 * C;
+  plan(M, C, kMaxParts, 4LL * C, &grid, &rows);
+  if (relu) k_bn_bwd_reduce<true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, partials, M, C, rows, save_mean);
+  else k_bn_bwd_reduce<false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, partials, M, C, rows, save_mean);
+  k_bn_bwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>(partials, grid, coef, M, C, weight, save_mean, save_invstd, dweight, dbias);
+  plan(M, C, 1184, (dres ? 8LL : 6LL) * C, &grid, &rows);
   if (relu && dres) k_bn_bwd_elemt<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, (uint4*)dres, coef, M, C, rows);
   else if (relu) k_bn_bwd_elemt<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, nullptr, coef, M, C, rows);
   else if (dres) k_bn_bwd_elemt<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, (uint4*)dx, (uint4*)dres, coef, M, C, rows);

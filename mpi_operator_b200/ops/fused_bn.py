@@ -31,11 +31,18 @@ def fused_bn_available(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
     return bool(_lib().b200mpi_bn_supported(n * h * w, c)) and x.is_contiguous(memory_format=torch.channels_last)
 
 
+_WS_CACHE = {}
+
+
 def _ws(bn: torch.nn.BatchNorm2d, device) -> torch.Tensor:
-    ws = getattr(bn, "_b200_ws", None)
-    if ws is None or ws.device != device:
-        ws = torch.zeros(int(_lib().b200mpi_bn_workspace_floats(bn.num_features)), dtype=torch.float32, device=device)
-        bn._b200_ws = ws  # plain attribute: not part of state_dict
+    """Scratch for per-CTA partial sums + per-channel coefficients. BN kernels of one stream run
+    back to back, so one buffer per (device, stream) is shared by every layer (sized for the widest)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    need = int(_lib().b200mpi_bn_workspace_floats(bn.num_features))
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, int(_lib().b200mpi_bn_workspace_floats(2048))), dtype=torch.float32, device=device)
+        _WS_CACHE[key] = ws
     return ws
 
 
