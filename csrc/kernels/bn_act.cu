@@ -88,8 +88,19 @@ __device__ __forceinline__ float merge_partials(const float* __restrict__ partia
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  if (o < nout)
-    for (int b = warp; b < parts; b += 8) acc += __ldcg(partials + (size_t)b * nout + o);
+  if (o < nout) {
+    const float* p = partials + o;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // 4 independent loads in flight per lane
+    int b = warp;
+    for (; b + 24 < parts; b += 32) {
+      a0 += __ldcg(p + (size_t)b * nout);
+      a1 += __ldcg(p + (size_t)(b + 8) * nout);
+      a2 += __ldcg(p + (size_t)(b + 16) * nout);
+      a3 += __ldcg(p + (size_t)(b + 24) * nout);
+    }
+    for (; b < parts; b += 8) a0 += __ldcg(p + (size_t)b * nout);
+    acc = (a0 + a1) + (a2 + a3);
+  }
   sm[warp][lane] = acc;
   __syncthreads();
   float tot = 0.f;
@@ -336,8 +347,8 @@ k_bn_bwd_elemt(const uint4* __restrict__ dz, const uint4* __restrict__ x, const 
 static void plan(long long M, int C, int cap, long long bytes_per_row, int* grid, long long* rows_per_cta) {
   const int tpr = C / 8, rpp = kThreadsBN / tpr;
   const long long min_rows = (long long)rpp * kUnroll;
-  // >= 64 KiB of traffic per CTA: small tensors get few CTAs (cheap merges), large ones fill the machine
-  long long by_bytes = (M * bytes_per_row + (64 << 10) - 1) / (64 << 10);
+  // >= 128 KiB of traffic per CTA: small tensors get few CTAs (cheap merges), large ones fill the machine
+  long long by_bytes = (M * bytes_per_row + (128 << 10) - 1) / (128 << 10);
   long long g = (M + min_rows - 1) / min_rows;
   if (g > by_bytes) g = by_bytes;
   if (g > cap) g = cap;
