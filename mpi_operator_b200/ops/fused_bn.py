@@ -52,7 +52,7 @@ def _ptr(t):
 
 class _BNAct(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, eps, momentum, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, eps, momentum, relu, direct):
         n, c, h, w = x.shape
         m = n * h * w
         y = torch.empty_like(x, memory_format=torch.channels_last)
@@ -67,6 +67,7 @@ class _BNAct(torch.autograd.Function):
             raise RuntimeError(f"b200mpi_bn_act_fwd failed ({rc})")
         ctx.save_for_backward(x, mask, weight, save_mean, save_invstd, ws)
         ctx.relu, ctx.has_res = relu, residual is not None
+        ctx.direct, ctx.wb = direct, (weight, bias)
         return y
 
     @staticmethod
@@ -78,15 +79,25 @@ class _BNAct(torch.autograd.Function):
             dz = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
-        dw = torch.empty(c, dtype=torch.float32, device=x.device)
-        db = torch.empty(c, dtype=torch.float32, device=x.device)
+        direct = ctx.direct is not None and ctx.wb[0].grad is not None and ctx.wb[1].grad is not None
+        if direct:
+            # the trainer owns pre-zeroed flat gradient views: write dgamma/dbeta straight into them and
+            # skip autograd's AccumulateGrad add kernels (2 tiny launches per BN layer per step)
+            dw, db = ctx.wb[0].grad, ctx.wb[1].grad
+        else:
+            dw = torch.empty(c, dtype=torch.float32, device=x.device)
+            db = torch.empty(c, dtype=torch.float32, device=x.device)
         stream = torch.cuda.current_stream(x.device).cuda_stream
         rc = _lib().b200mpi_bn_act_bwd(dz.data_ptr(), x.data_ptr(), _ptr(mask), dx.data_ptr(), _ptr(dres), weight.data_ptr(),
                                        save_mean.data_ptr(), save_invstd.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
                                        m, c, int(ctx.relu), stream)
         if rc != 0:
             raise RuntimeError(f"b200mpi_bn_act_bwd failed ({rc})")
-        return dx, dres, dw, db, None, None, None, None, None, None
+        if direct:
+            ctx.direct(ctx.wb[0])
+            ctx.direct(ctx.wb[1])
+            return dx, dres, None, None, None, None, None, None, None, None, None
+        return dx, dres, dw, db, None, None, None, None, None, None, None
 
 
 def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = None, relu: bool = True) -> torch.Tensor:
@@ -96,7 +107,7 @@ def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = N
         if bn.num_batches_tracked is not None:
             bn.num_batches_tracked.add_(1)
         return _BNAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, _ws(bn, x.device), bn.eps,
-                            bn.momentum, relu)
+                            bn.momentum, relu, getattr(bn, "_b200_grad_ready", None))
     out = bn(x)
     if residual is not None:
         out = out + residual

@@ -143,9 +143,16 @@ class DataParallelTrainer:
         self._loss = torch.zeros((), device=self.device)
         self._launches_per_step = 0
         self._sync = True
+        hooks = {}
         for b in self.state.buckets:
             for p in b.params:
-                p.register_post_accumulate_grad_hook(self._make_hook(b))
+                hooks[p] = self._make_hook(b)
+                p.register_post_accumulate_grad_hook(hooks[p])
+        # fused BN layers write dgamma/dbeta directly into the flat gradient views and report readiness
+        # themselves (mpi_operator_b200.ops.fused_bn): no AccumulateGrad add kernels for 2 x #BN params
+        for mod in model.modules():
+            if isinstance(mod, nn.BatchNorm2d) and mod.affine and mod.weight in hooks:
+                mod._b200_grad_ready = (lambda param, _h=hooks: _h[param](param))
         if self.backend == "nccl":
             import torch.distributed as dist
             self._dist = dist
