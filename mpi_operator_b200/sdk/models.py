@@ -112,7 +112,7 @@ class V2beta1JobStatus(OpenApiModel):
 
 
 class V2beta1SchedulingPolicy(OpenApiModel):
-    openapi_types = {"min_available": "int", "min_resources": "dict(str, str)", "priority_class": "str", "queue": "str",
+    openapi_types = {"min_available": "int", "min_resources": "dict(str, object)", "priority_class": "str", "queue": "str",
                      "schedule_timeout_seconds": "int"}
     attribute_map = {"min_available": "minAvailable", "min_resources": "minResources", "priority_class": "priorityClass",
                      "queue": "queue", "schedule_timeout_seconds": "scheduleTimeoutSeconds"}
@@ -220,3 +220,8 @@ MODEL_CLASSES = {c.__name__: c for c in (
     V2beta1JobCondition, V2beta1ReplicaStatus, V2beta1JobStatus, V2beta1SchedulingPolicy, V2beta1RunPolicy,
     V2beta1ReplicaSpec, V2beta1MPIJobSpec, V2beta1MPIJob, V2beta1MPIJobList, V1ObjectMeta, V1ListMeta, V1OwnerReference,
     V1LabelSelectorRequirement, V1LabelSelector, V1Container, V1PodSpec, V1PodTemplateSpec)}
+
+# long apimachinery names used by the reference's generated SDK (sdk/python/v2beta1/mpijob/models/io_k8s_*.py)
+for _short in ("V1ObjectMeta", "V1ListMeta", "V1OwnerReference", "V1LabelSelector", "V1LabelSelectorRequirement"):
+    MODEL_CLASSES["IoK8sApimachineryPkgApisMeta" + _short] = MODEL_CLASSES[_short]
+    globals()["IoK8sApimachineryPkgApisMeta" + _short] = MODEL_CLASSES[_short]

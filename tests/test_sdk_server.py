@@ -110,3 +110,31 @@ def test_rest_api_end_to_end_with_sdk_client(tmp_path):
             cli.get("rest")
     finally:
         op.stop()
+
+
+def test_models_match_the_reference_sdk_when_installed():
+    """Parity against the UNMODIFIED reference SDK installed at baseline/_ref (pip --target of
+    /root/reference/sdk/python/v2beta1): same openapi_types and attribute_map for all 9 MPIJob models."""
+    import os
+    import subprocess
+    import sys
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "mpijob")):
+        pytest.skip("reference SDK not installed (baseline/_ref)")
+    code = ("import sys, json; sys.path.insert(0, %r)\n"
+            "import mpijob.models as m\n"
+            "names = [n for n in dir(m) if n.startswith('V2beta1')]\n"
+            "print(json.dumps({n: [getattr(m, n).openapi_types, getattr(m, n).attribute_map] for n in names}))\n") % ref
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    if r.returncode != 0:
+        pytest.skip("reference SDK not importable here: " + r.stderr[-200:])
+    theirs = json.loads(r.stdout)
+    assert sorted(theirs) == sorted(n for n in mpijob.models.MODEL_CLASSES if n.startswith("V2beta1"))
+    for name, (types, amap) in theirs.items():
+        ours = mpijob.models.MODEL_CLASSES[name]
+        assert ours.attribute_map == amap, name
+        # the reference generator spells apimachinery types IoK8sApimachineryPkgApisMetaV1X; we use the
+        # kubernetes-client names V1X (and export the long names as aliases)
+        norm = {k: v.replace("IoK8sApimachineryPkgApisMetaV1", "V1") for k, v in types.items()}
+        assert ours.openapi_types == norm, name
+    assert mpijob.models.MODEL_CLASSES["IoK8sApimachineryPkgApisMetaV1ObjectMeta"] is mpijob.V1ObjectMeta
