@@ -23,6 +23,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../include/b200mpi.h"
 
@@ -344,7 +345,14 @@ k_bn_bwd_elemt(const uint4* __restrict__ dz, const uint4* __restrict__ x, const 
   }
 }
 
-static void plan(long long M, int C, int cap, long long bytes_per_row, int* grid, long long* rows_per_cta, long long chunk = 128 << 10) {
+static long long env_chunk(const char* name, long long dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoll(v) : dflt;
+}
+static long long reduce_chunk() { static long long v = env_chunk("B200MPI_BN_REDUCE_CHUNK", 64 << 10); return v; }
+static long long elem_chunk() { static long long v = env_chunk("B200MPI_BN_ELEM_CHUNK", 64 << 10); return v; }
+
+static void plan(long long M, int C, int cap, long long bytes_per_row, int* grid, long long* rows_per_cta, long long chunk) {
   const int tpr = C / 8, rpp = kThreadsBN / tpr;
   const long long min_rows = (long long)rpp * kUnroll;
   // >= `chunk` bytes of traffic per CTA: reduce-type kernels use 128 KiB (few partial rows to merge),
@@ -381,11 +389,11 @@ int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask,
   float* partials = workspace + 4 * C;
   int grid;
   long long rows;
-  plan(M, C, kMaxParts, 2LL * C, &grid, &rows);
+  plan(M, C, kMaxParts, 2LL * C, &grid, &rows, reduce_chunk());
   k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, partials, M, C, rows);
   k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>((const __nv_bfloat16*)x, partials, grid, coef, M, C, weight, bias,
                                                             running_mean, running_var, save_mean, save_invstd, eps, momentum);
-  plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, 32 << 10);
+  plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, elem_chunk());
   if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
   else if (relu) k_bn_fwd_apply<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
   else if (residual) k_bn_fwd_apply<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, nullptr, coef, M, C, rows);
@@ -402,11 +410,11 @@ int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx
   float* partials = workspace + 4 * C;
   int grid;
   long long rows;
-  plan(M, C, kMaxParts, 4LL * C, &grid, &rows);
+  plan(M, C, kMaxParts, 4LL * C, &grid, &rows, reduce_chunk());
   if (relu) k_bn_bwd_reduce<true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, partials, M, C, rows, save_mean);
   else k_bn_bwd_reduce<false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, partials, M, C, rows, save_mean);
   k_bn_bwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>(partials, grid, coef, M, C, weight, save_mean, save_invstd, dweight, dbias);
-  plan(M, C, 1184, (dres ? 8LL : 6LL) * C, &grid, &rows, 32 << 10);
+  plan(M, C, 1184, (dres ? 8LL : 6LL) * C, &grid, &rows, elem_chunk());
   if (relu && dres) k_bn_bwd_elemt<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, (uint4*)dres, coef, M, C, rows);
   else if (relu) k_bn_bwd_elemt<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, nullptr, coef, M, C, rows);
   else if (dres) k_bn_bwd_elemt<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, (uint4*)dx, (uint4*)dres, coef, M, C, rows);

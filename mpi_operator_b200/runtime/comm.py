@@ -122,7 +122,26 @@ class Communicator:
         h = C.c_void_p()
         check(_lib.lib().b200mpi_comm_init(C.byref(h), rank, world, device, job_id.encode(), staging_bytes, flags),
               "comm_init")
-        return cls(h, device)
+        c = cls(h, device)
+        c._apply_tuning_file()
+        return c
+
+    def _apply_tuning_file(self) -> None:
+        """Measured crossovers (benchmarks/autotune.py -> runtime/tuning.json; B200MPI_TUNING_FILE overrides).
+        Explicit B200MPI_* env knobs win over the file."""
+        import json
+        path = os.environ.get("B200MPI_TUNING_FILE", os.path.join(os.path.dirname(os.path.abspath(__file__)), "tuning.json"))
+        try:
+            t = json.load(open(path))["by_world"].get(str(self.world))
+        except (OSError, ValueError, KeyError):
+            return
+        if not t:
+            return
+        one = t.get("oneshot_max_bytes", -1) if "B200MPI_ONESHOT_MAX_BYTES" not in os.environ else -1
+        nv = t.get("nvls_min_bytes", -1) if "B200MPI_NVLS_MIN_BYTES" not in os.environ else -1
+        if nv == -1 and "nvls_min_bytes" in t and "B200MPI_NVLS_MIN_BYTES" not in os.environ:
+            nv = (1 << 62)  # NVLS never wins at this world size
+        self.set_tuning(oneshot_max_bytes=one if one > 0 else -1, nvls_min_bytes=nv)
 
     @classmethod
     def from_env(cls, device: Optional[int] = None, staging_bytes: int = 0, flags: int = 0):
