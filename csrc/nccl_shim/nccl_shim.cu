@@ -374,12 +374,14 @@ ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t c) {
 
 ncclResult_t ncclGroupStart(void) {
   g_group_depth++;
-  if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) if (g_forwarded.load()) return f();
+  if (forward_all() || g_forwarded.load())
+    if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) return f();  // baseline mode groups communicator creation too
   return ncclSuccess;
 }
 ncclResult_t ncclGroupEnd(void) {
   if (g_group_depth > 0) g_group_depth--;
-  if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupEnd")) if (g_forwarded.load()) return f();
+  if (forward_all() || g_forwarded.load())
+    if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupEnd")) return f();
   return ncclSuccess;  // b200mpi collectives were enqueued eagerly, in order, on their streams
 }
 ncclResult_t ncclGroupSimulateEnd(void*) { return ncclSuccess; }
