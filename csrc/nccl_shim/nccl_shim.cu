@@ -59,6 +59,7 @@ int g_next_op = 16;
 std::atomic<uint64_t> g_calls{0}, g_forwarded{0};
 thread_local std::string g_last_error;
 thread_local int g_group_depth = 0;
+thread_local int g_group_fwd = 0;
 
 bool forward_all() {
   static int v = -1;
@@ -374,14 +375,19 @@ ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t c) {
 
 ncclResult_t ncclGroupStart(void) {
   g_group_depth++;
-  if (forward_all() || g_forwarded.load())
-    if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) return f();  // baseline mode groups communicator creation too
+  // Forward only when a real communicator exists (or everything is forwarded); remember it so the
+  // matching End is forwarded too and the real library never sees an unbalanced pair.
+  if (forward_all() || g_forwarded.load()) {
+    if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) { g_group_fwd++; return f(); }
+  }
   return ncclSuccess;
 }
 ncclResult_t ncclGroupEnd(void) {
   if (g_group_depth > 0) g_group_depth--;
-  if (forward_all() || g_forwarded.load())
+  if (g_group_fwd > 0) {
+    g_group_fwd--;
     if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupEnd")) return f();
+  }
   return ncclSuccess;  // b200mpi collectives were enqueued eagerly, in order, on their streams
 }
 ncclResult_t ncclGroupSimulateEnd(void*) { return ncclSuccess; }
