@@ -258,7 +258,18 @@ int main(int argc, char** argv) {
   for (auto& rk : ranks) local_size[rk.node]++;
 
   // ---- GPU map from the node agent ---------------------------------------------
+  // Like the reference's entrypoint.sh waiting for DNS (build/base/entrypoint.sh:8-34): give the node
+  // agent a moment to publish every host of the hostfile in the slot map (elastic scale-up races).
   auto slots = read_slots_file(getenv("B200MPI_SLOTS_FILE"));
+  if (getenv("B200MPI_SLOTS_FILE") && !slots.empty()) {
+    for (int attempt = 0; attempt < 50; attempt++) {
+      bool all = true;
+      for (auto& h : hosts) all = all && slots.count(short_host(h.name)) > 0;
+      if (all) break;
+      usleep(100000);
+      slots = read_slots_file(getenv("B200MPI_SLOTS_FILE"));
+    }
+  }
   std::vector<int> job_gpus;
   for (auto& h : hosts) {
     auto it = slots.find(short_host(h.name));
