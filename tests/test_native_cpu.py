@@ -131,5 +131,6 @@ def test_entrypoint_waits_for_slot_map(tmp_path):
     r = run(["bash", ep, "echo", "started"], env={"K_MPI_JOB_ROLE": "launcher", "HYDRA_HOST_FILE": str(hf), "B200MPI_SLOTS_FILE": str(slots)})
     assert r.returncode == 0 and r.stdout.strip() == "started"
     slots.write_text('{"hosts": {"other": [0]}}')
-    r = run(["bash", ep, "echo", "started"], env={"K_MPI_JOB_ROLE": "launcher", "HYDRA_HOST_FILE": str(hf), "B200MPI_SLOTS_FILE": str(slots)}, timeout=240)
+    r = run(["bash", ep, "echo", "started"], env={"K_MPI_JOB_ROLE": "launcher", "HYDRA_HOST_FILE": str(hf), "B200MPI_SLOTS_FILE": str(slots),
+                                                  "B200MPI_ENTRYPOINT_RETRIES": "3"}, timeout=60)
     assert r.returncode != 0 and "never became ready" in r.stderr
