@@ -260,68 +260,92 @@ k_allreduce_sgd(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu)
   const float mu = a.hyper ? __ldg(a.hyper + 1) : a.mu;
   const float wd = a.hyper ? __ldg(a.hyper + 2) : a.wd;
 
-  for (size_t i = gtid(); i < lim; i += gstride()) {
-    float g[N];
+  // U vectors per thread per trip: U NVLink reduce-loads (or U x world peer loads) are issued before any
+  // is consumed — with one vector per trip the NVLS variant was latency-bound (~45 GB/s per rank, 1.2 ms
+  // exposed per step at 8 GPUs).
+  constexpr int U = (MODE == MODE_NVLS) ? 4 : 2;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+    float gg[U][N];
     if (MODE == MODE_NVLS) {
-      VecTraits<T>::unpack(nvls_ld_reduce<T>(gmc + i * 16, OP_SUM), g);
-    } else {
-      uint4 v[kMaxRanks];
+      uint4 r[U];
 #pragma unroll
-      for (int k = 0; k < kMaxRanks; k++)
-        if (k < world) v[k] = ld_sys_v4(gp[k] + i * 16);
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; k++)
-        if (k < world) accum<T>(g, v[k], OP_SUM, k == 0);
-    }
-    const size_t el = (base + i) * N;  // first element index of this vector
-    float p[N], m[N];
-    const float* pl = reinterpret_cast<const float*>(a.param.p[rank]) + el;
-    float* ml = a.mom + i * N;
-#pragma unroll
-    for (int q = 0; q < N / 4; q++) {
-      float4 t = *reinterpret_cast<const float4*>(pl + 4 * q);
-      p[4 * q] = t.x; p[4 * q + 1] = t.y; p[4 * q + 2] = t.z; p[4 * q + 3] = t.w;
-      if (!a.first_step) {
-        float4 s = *reinterpret_cast<const float4*>(ml + 4 * q);
-        m[4 * q] = s.x; m[4 * q + 1] = s.y; m[4 * q + 2] = s.z; m[4 * q + 3] = s.w;
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) r[u] = nvls_ld_reduce<T>(gmc + i * 16, OP_SUM);
       }
-    }
 #pragma unroll
-    for (int j = 0; j < N; j++) {
-      float gj = g[j] * a.scale + wd * p[j];
-      float mj = a.first_step ? gj : mu * m[j] + gj;
-      m[j] = mj;
-      p[j] -= lr * (a.nesterov ? gj + mu * mj : mj);
-    }
+      for (int u = 0; u < U; u++) VecTraits<T>::unpack(r[u], gg[u]);
+    } else {
+      uint4 v[U][kMaxRanks];
 #pragma unroll
-    for (int q = 0; q < N / 4; q++) {
-      *reinterpret_cast<float4*>(ml + 4 * q) = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
-      const uint4 o = make_uint4(__float_as_uint(p[4 * q]), __float_as_uint(p[4 * q + 1]),
-                                 __float_as_uint(p[4 * q + 2]), __float_as_uint(p[4 * q + 3]));
-      const size_t boff = (el + 4 * q) * 4;
-      if (MODE == MODE_NVLS) {
-        multimem_st_v4(a.param.mc + boff, o);
-      } else {
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
 #pragma unroll
         for (int k = 0; k < kMaxRanks; k++)
-          if (k < world) st_peer_v4(a.param.p[wrap(rank + k, world)] + boff, o);
+          if (k < world && i < lim) v[u][k] = ld_sys_v4(gp[k] + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k < world) accum<T>(gg[u], v[u][k], OP_SUM, k == 0);
       }
     }
-    if (has_lowp) {
-      // bf16 shadow of the parameters for bf16-weight models: N bf16 = 2N bytes
-      uint32_t w[N / 2];
 #pragma unroll
-      for (int j = 0; j < N / 2; j++) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
-        w[j] = *reinterpret_cast<uint32_t*>(&h);
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i >= lim) continue;
+      float* g = gg[u];
+      const size_t el = (base + i) * N;  // first element index of this vector
+      float p[N], m[N];
+      const float* pl = reinterpret_cast<const float*>(a.param.p[rank]) + el;
+      float* ml = a.mom + i * N;
+  #pragma unroll
+      for (int q = 0; q < N / 4; q++) {
+        float4 t = *reinterpret_cast<const float4*>(pl + 4 * q);
+        p[4 * q] = t.x; p[4 * q + 1] = t.y; p[4 * q + 2] = t.z; p[4 * q + 3] = t.w;
+        if (!a.first_step) {
+          float4 s = *reinterpret_cast<const float4*>(ml + 4 * q);
+          m[4 * q] = s.x; m[4 * q + 1] = s.y; m[4 * q + 2] = s.z; m[4 * q + 3] = s.w;
+        }
       }
-      const size_t boff = el * 2;
-#pragma unroll
-      for (int k = 0; k < kMaxRanks; k++) {
-        if (k < world) {
-          char* dst = a.lowp.p[wrap(rank + k, world)] + boff;
-          if constexpr (N == 8) st_peer_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
-          else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+  #pragma unroll
+      for (int j = 0; j < N; j++) {
+        float gj = g[j] * a.scale + wd * p[j];
+        float mj = a.first_step ? gj : mu * m[j] + gj;
+        m[j] = mj;
+        p[j] -= lr * (a.nesterov ? gj + mu * mj : mj);
+      }
+  #pragma unroll
+      for (int q = 0; q < N / 4; q++) {
+        *reinterpret_cast<float4*>(ml + 4 * q) = make_float4(m[4 * q], m[4 * q + 1], m[4 * q + 2], m[4 * q + 3]);
+        const uint4 o = make_uint4(__float_as_uint(p[4 * q]), __float_as_uint(p[4 * q + 1]),
+                                   __float_as_uint(p[4 * q + 2]), __float_as_uint(p[4 * q + 3]));
+        const size_t boff = (el + 4 * q) * 4;
+        if (MODE == MODE_NVLS) {
+          multimem_st_v4(a.param.mc + boff, o);
+        } else {
+  #pragma unroll
+          for (int k = 0; k < kMaxRanks; k++)
+            if (k < world) st_peer_v4(a.param.p[wrap(rank + k, world)] + boff, o);
+        }
+      }
+      if (has_lowp) {
+        // bf16 shadow of the parameters for bf16-weight models: N bf16 = 2N bytes
+        uint32_t w[N / 2];
+  #pragma unroll
+        for (int j = 0; j < N / 2; j++) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(p[2 * j], p[2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const size_t boff = el * 2;
+  #pragma unroll
+        for (int k = 0; k < kMaxRanks; k++) {
+          if (k < world) {
+            char* dst = a.lowp.p[wrap(rank + k, world)] + boff;
+            if constexpr (N == 8) st_peer_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
+            else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
+          }
         }
       }
     }

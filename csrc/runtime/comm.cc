@@ -734,7 +734,7 @@ int b200mpi_allreduce_sgd_sym(b200mpi_comm_t c, int gwin, size_t goff, int pwin,
   if (algo == B200MPI_ALGO_NVLS || (algo == B200MPI_ALGO_AUTO && c->multicast && count * esize(gdtype) >= c->nvls_min && count * esize(gdtype) > c->oneshot_max)) mode = MODE_NVLS;
   if (mode == MODE_NVLS && !(c->multicast && c->wins[gwin].mc && c->wins[pwin].mc)) mode = MODE_P2P;
   const size_t nvec = count / n, per = (nvec + c->world - 1) / c->world;
-  const int blocks = blocks_for(c, per, 1, mode == MODE_NVLS ? c->nvls_blocks : c->max_blocks);
+  const int blocks = blocks_for(c, per, mode == MODE_NVLS ? 4 : 2, mode == MODE_NVLS ? c->nvls_blocks : c->max_blocks);
   const auto ranks = my_ranks(c);
   std::vector<KArgs> args(c->local ? c->world : 1);
   for (size_t k = 0; k < ranks.size(); k++) {
