@@ -219,6 +219,8 @@ ncclResult_t init_common(ncclComm_t* out, int nranks, const ncclUniqueId* id, in
       r = f(&s->real, nranks, *id, rank);
     }
     if (r != ncclSuccess && r != ncclInProgress) { delete s; return r; }
+    *out = reinterpret_cast<ncclComm_t>(s);
+    return r;  // non-blocking communicators (ncclConfig_t.blocking = 0) report ncclInProgress: pass it on
   } else if (debug() && rank == 0) {
     fprintf(stderr, "[b200mpi nccl shim] communicator %s: %d ranks on b200mpi kernels (NVLS=%d)\n", s->id.c_str(), nranks,
             b200mpi_comm_has_multicast(s->mine));
@@ -291,10 +293,10 @@ ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newc
     if (!f) return err(ncclSystemError, "real ncclCommSplit missing");
     ncclComm_t r = nullptr;
     ncclResult_t rc = f(s->real, color, key, &r, config);
-    if (rc != ncclSuccess) return rc;
-    if (!r) { *newcomm = nullptr; return ncclSuccess; }
+    if (rc != ncclSuccess && rc != ncclInProgress) return rc;
+    if (!r) { *newcomm = nullptr; return rc; }
     auto* n = new Shim; n->real = r; *newcomm = reinterpret_cast<ncclComm_t>(n);
-    return ncclSuccess;
+    return rc;
   }
   struct CK { int color, key, rank; } mine{color, key, s->rank};
   std::vector<CK> all(s->world);
