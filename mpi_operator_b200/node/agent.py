@@ -59,6 +59,7 @@ REPO_ROOT = os.path.dirname(PKG_DIR)
 IMAGE_REGISTRY = {
     "mpioperator/tensorflow-benchmarks": {"workingDir": os.path.join(REPO_ROOT, "examples", "tensorflow-benchmarks")},
     "mpioperator/mpi-pi": {},
+    "mpioperator/torch-ddp": {"workingDir": REPO_ROOT},
     "docker.io/kubeflow/mpi-horovod-mnist": {"remap": {"/examples/tensorflow_mnist.py": os.path.join(REPO_ROOT, "examples", "horovod", "torch_mnist.py")}},
 }
 
@@ -519,6 +520,13 @@ class NodeAgent:
             env["B200MPI_MPIJOB_NAME"] = jn
             env["B200MPI_SLOTS_FILE"] = self._job_slots_path(M.namespace_of(pod), jn)
             env.setdefault("B200MPI_JOB_ID", f"{M.namespace_of(pod)}.{jn}.{M.meta(pod).get('uid', '')[:8]}")
+        # LD-inject the collective runtime into every rank mpirun spawns (north star): unmodified
+        # torch.distributed scripts then resolve ncclAllReduce & co. to b200mpi kernels. B200MPI_ALGO=nccl
+        # (or B200MPI_INJECT=0) is the baseline mode: same launcher, stock NCCL.
+        shim = os.path.join(PKG_DIR, "lib", "libb200mpi_nccl.so")
+        if (os.path.exists(shim) and env.get("B200MPI_ALGO", "") != "nccl" and env.get("B200MPI_INJECT", "1") != "0"
+                and "B200MPI_INJECT_LIB" not in env):
+            env["B200MPI_INJECT_LIB"] = shim
         gpus = (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION, "")
         env["B200MPI_GPUS"] = gpus
         if env.get("NVIDIA_VISIBLE_DEVICES", None) == "" and "NVIDIA_VISIBLE_DEVICES" in {e["name"] for e in c0.get("env", []) or []}:

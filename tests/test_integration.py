@@ -232,3 +232,23 @@ def test_metrics_text_has_reference_names(op):
     for name in ("mpi_operator_jobs_created_total", "mpi_operator_jobs_successful_total", "mpi_operator_jobs_failed_total",
                  "mpi_operator_job_info", "mpi_operator_is_leader"):
         assert name in text
+
+
+@needs_native
+def test_collective_runtime_is_ld_injected_into_ranks(op):
+    shim = os.path.join(REPO, "mpi_operator_b200/lib/libb200mpi_nccl.so")
+    if not os.path.exists(shim):
+        pytest.skip("shim not built")
+    job = new_mpijob("inject", workers=2, launcher_cmd=("mpirun",), launcher_args=("-np", "2", "sh", "-c", "echo preload=$LD_PRELOAD"),
+                     worker_cmd=("/usr/sbin/sshd",))
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if "inject-launcher" in p["metadata"]["name"]][0]
+    assert op.agent.logs("default", launcher["metadata"]["name"]).count(f"preload={shim}") == 2
+    base = new_mpijob("noinject", workers=1, launcher_cmd=("mpirun",), launcher_args=("-np", "1", "sh", "-c", "echo preload=[$LD_PRELOAD]"),
+                      worker_cmd=("/usr/sbin/sshd",))
+    base.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [{"name": "B200MPI_ALGO", "value": "nccl"}]
+    submit(op, base)
+    wait_for(lambda: conds(get(op, base)).get("Succeeded") == "True", what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if "noinject-launcher" in p["metadata"]["name"]][0]
+    assert "preload=[]" in op.agent.logs("default", launcher["metadata"]["name"])
