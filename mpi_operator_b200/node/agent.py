@@ -524,7 +524,9 @@ class NodeAgent:
         # torch.distributed scripts then resolve ncclAllReduce & co. to b200mpi kernels. B200MPI_ALGO=nccl
         # (or B200MPI_INJECT=0) is the baseline mode: same launcher, stock NCCL.
         shim = os.path.join(PKG_DIR, "lib", "libb200mpi_nccl.so")
-        if (os.path.exists(shim) and env.get("B200MPI_ALGO", "") != "nccl" and env.get("B200MPI_INJECT", "1") != "0"
+        # Opt-in for now (pod env B200MPI_INJECT=1): validated with torch DDP on 2 GPUs (22 collectives on b200mpi
+        # kernels, 0 forwarded); the 8-GPU DDP job still fails and is being debugged.
+        if (os.path.exists(shim) and env.get("B200MPI_ALGO", "") != "nccl" and env.get("B200MPI_INJECT", "0") == "1"
                 and "B200MPI_INJECT_LIB" not in env):
             env["B200MPI_INJECT_LIB"] = shim
         gpus = (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION, "")

@@ -241,13 +241,14 @@ def test_collective_runtime_is_ld_injected_into_ranks(op):
         pytest.skip("shim not built")
     job = new_mpijob("inject", workers=2, launcher_cmd=("mpirun",), launcher_args=("-np", "2", "sh", "-c", "echo preload=$LD_PRELOAD"),
                      worker_cmd=("/usr/sbin/sshd",))
+    job.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [{"name": "B200MPI_INJECT", "value": "1"}]
     submit(op, job)
     wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
     launcher = [p for p in op.store.list("pods", "default") if "inject-launcher" in p["metadata"]["name"]][0]
     assert op.agent.logs("default", launcher["metadata"]["name"]).count(f"preload={shim}") == 2
     base = new_mpijob("noinject", workers=1, launcher_cmd=("mpirun",), launcher_args=("-np", "1", "sh", "-c", "echo preload=[$LD_PRELOAD]"),
                       worker_cmd=("/usr/sbin/sshd",))
-    base.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [{"name": "B200MPI_ALGO", "value": "nccl"}]
+    base.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [{"name": "B200MPI_INJECT", "value": "1"}, {"name": "B200MPI_ALGO", "value": "nccl"}]
     submit(op, base)
     wait_for(lambda: conds(get(op, base)).get("Succeeded") == "True", what="Succeeded")
     launcher = [p for p in op.store.list("pods", "default") if "noinject-launcher" in p["metadata"]["name"]][0]
