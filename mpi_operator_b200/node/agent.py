@@ -46,6 +46,7 @@ log = logging.getLogger("node-agent")
 
 NODE_NAME = "localhost"
 GPU_ANNOTATION = "b200mpi.kubeflow.org/gpus"
+PGID_ANNOTATION = "b200mpi.kubeflow.org/pgid"
 JOB_UID_LABEL = "batch.kubernetes.io/controller-uid"
 JOB_NAME_LABEL = "batch.kubernetes.io/job-name"
 DEFAULT_BACKOFF_LIMIT = 6
@@ -110,7 +111,38 @@ class NodeAgent:
         self._deleted = collections.deque()
 
     # ------------------------------------------------------------ lifecycle --
+    def _adopt_existing(self) -> None:
+        """Daemon restart: the persisted store may hold pods that were Running under the
+        previous daemon. Idle sshd placeholders are simply re-adopted (their GPU slots re-reserved); a pod whose
+        process the old daemon owned cannot be waited on any more: its recorded process group is reaped and the
+        pod is marked Failed (reason DaemonRestarted), so the Job controller starts a fresh launcher pod
+        (counted against backoffLimit) — level-triggered recovery, like a kubelet restart."""
+        for pod in self.store.list("pods"):
+            if not pod["spec"].get("nodeName") or pod.get("status", {}).get("phase") != "Running":
+                continue
+            key = M.key_of(pod)
+            gpus = [int(x) for x in (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION, "").split(",") if x != ""]
+            c0 = pod["spec"]["containers"][0]
+            argv = list(c0.get("command") or []) + list(c0.get("args") or [])
+            if argv and os.path.basename(argv[0]) == "sshd":
+                pr = _Proc()
+                pr.virtual, pr.pod_dir = True, self.pod_dir(pod)
+                pr.started_at = pod["status"].get("startTime", M.now_rfc3339())
+                self._procs[key] = pr
+                self.alloc.adopt(key, gpus)
+                continue
+            pgid = (M.meta(pod).get("annotations") or {}).get(PGID_ANNOTATION)
+            if pgid:
+                try:
+                    os.killpg(int(pgid), signal.SIGKILL)
+                except (ProcessLookupError, PermissionError, ValueError):
+                    pass
+            pr = _Proc()
+            pr.pod_dir, pr.log_path = self.pod_dir(pod), os.path.join(self.pod_dir(pod), "logs", "0.log")
+            self._set_terminal(pod, pr, "Failed", 137, "DaemonRestarted", "the operator daemon restarted while this pod was running")
+
     def start(self) -> None:
+        self._adopt_existing()
         for res in ("pods", "jobs", "configmaps", "volcano-podgroups", "sched-podgroups"):
             self._cancels.append(self.store.watch(res, self._on_event, replay=True))
         self._thread = threading.Thread(target=self._loop, name="node-agent", daemon=True)
@@ -580,6 +612,12 @@ class NodeAgent:
         logf.close()
         pr._argv, pr._env, pr._cwd = argv, env, cwd  # for OnFailure restarts
         pr.started_at = M.now_rfc3339()
+        try:  # remember the process group so a restarted daemon can reap it
+            cur = self.store.get("pods", M.namespace_of(pod), M.name_of(pod))
+            M.meta(cur).setdefault("annotations", {})[PGID_ANNOTATION] = str(pr.popen.pid)
+            pod = self.store.update("pods", cur)
+        except errors.ApiError:
+            pass
         self._set_running(pod, pr)
 
     def _container_status(self, pod: dict, pr: _Proc, state: dict, ready: bool) -> List[dict]:

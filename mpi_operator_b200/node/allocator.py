@@ -87,6 +87,12 @@ class GangAllocator:
                 out[r.key] = list(self._held[r.key])
             return out
 
+    def adopt(self, key: str, gpus: List[int]) -> None:
+        """Re-register a reservation that predates this allocator (daemon restart)."""
+        with self._lock:
+            self._held[key] = list(gpus)
+            self._free = [g for g in self._free if g not in gpus]
+
     def release(self, key: str) -> None:
         with self._lock:
             got = self._held.pop(key, None)

@@ -253,3 +253,35 @@ def test_collective_runtime_is_ld_injected_into_ranks(op):
     wait_for(lambda: conds(get(op, base)).get("Succeeded") == "True", what="Succeeded")
     launcher = [p for p in op.store.list("pods", "default") if "noinject-launcher" in p["metadata"]["name"]][0]
     assert "preload=[]" in op.agent.logs("default", launcher["metadata"]["name"])
+
+
+def test_daemon_restart_reaps_lost_processes_and_recovers(tmp_path):
+    """Persisted store + restarted daemon: idle workers are re-adopted with their GPU slots, the launcher the old
+    daemon owned is reaped and marked Failed(DaemonRestarted), the Job controller retries, the job succeeds."""
+    marker = tmp_path / "second-run"
+    script = f"if [ -e {marker} ]; then exit 0; fi; touch {marker}; sleep 60"
+    o1 = Operator(ServerOption(fake_gpus=4, leader_elect=False, state_dir=str(tmp_path / "s")))
+    o1.start()
+    job = new_mpijob("restart", workers=2, launcher_cmd=("sh", "-c", script), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
+    job.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+    job.spec.replica("Launcher").restart_policy = "Never"
+    submit(o1, job)
+    wait_for(lambda: conds(get(o1, job)).get("Running") == "True", what="Running")
+    old_launcher = [p for p in o1.store.list("pods", "default") if "restart-launcher" in p["metadata"]["name"]][0]
+    pgid = int(old_launcher["metadata"]["annotations"]["b200mpi.kubeflow.org/pgid"])
+    # simulate a daemon crash: threads stop, child processes survive
+    o1.controller.stop(); o1.agent._stop.set(); o1.agent._thread.join(2); o1.informers.stop()
+    os.kill(pgid, 0)  # the old launcher process is still alive
+    o2 = Operator(ServerOption(fake_gpus=4, leader_elect=False, state_dir=str(tmp_path / "s")))
+    o2.start()
+    try:
+        assert o2.agent.alloc.free_gpus == 2  # worker reservations re-adopted
+        lost = o2.store.get("pods", "default", old_launcher["metadata"]["name"])
+        assert lost["status"]["phase"] == "Failed" and lost["status"]["reason"] == "DaemonRestarted"
+        done = wait_for(lambda: conds(get(o2, job)).get("Succeeded") == "True" and get(o2, job), what="Succeeded after restart")
+        assert done.status.replica_statuses["Launcher"].failed == 1
+        # the orphan was SIGKILLed by the new daemon (it is a zombie child of this test process until reaped)
+        old_popen = o1.agent._procs[f"default/{old_launcher['metadata']['name']}"].popen
+        assert old_popen.wait(timeout=5) == -9
+    finally:
+        o2.stop()
