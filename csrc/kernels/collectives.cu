@@ -27,17 +27,6 @@ __device__ __forceinline__ size_t gstride() { return (size_t)gridDim.x * blockDi
 __device__ __forceinline__ int wrap(int x, int world) { return x >= world ? x - world : x; }
 
 template <typename T>
-__device__ __forceinline__ uint4 reduce_op_vec(const uint4& x, const uint4& y, int op) {
-  float a[VecTraits<T>::N], b[VecTraits<T>::N];
-  VecTraits<T>::unpack(x, a);
-  VecTraits<T>::unpack(y, b);
-#pragma unroll
-  for (int j = 0; j < VecTraits<T>::N; j++)
-    a[j] = op == OP_SUM ? a[j] + b[j] : (op == OP_MAX ? fmaxf(a[j], b[j]) : fminf(a[j], b[j]));
-  return VecTraits<T>::pack(a);
-}
-
-template <typename T>
 __device__ __forceinline__ void accum(float* acc, const uint4& v, int op, bool first) {
   float f[VecTraits<T>::N];
   VecTraits<T>::unpack(v, f);

@@ -499,7 +499,7 @@ class MPIJobController:
             for pod in full:
                 idx = (M.meta(pod).get("labels") or {}).get(C.REPLICA_INDEX_LABEL)
                 if idx is None:
-                    return None  # reference returns (nil, nil) here
+                    return []  # the reference bails out with (nil, nil) when a worker lacks its index label
                 try:
                     index = int(idx)
                 except ValueError:

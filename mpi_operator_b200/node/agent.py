@@ -37,7 +37,7 @@ from typing import Dict, List, Optional
 from ..api import constants as C
 from ..api import meta as M
 from ..client import errors
-from ..client.store import ADDED, DELETED, MODIFIED, ObjectStore
+from ..client.store import DELETED, MODIFIED, ObjectStore
 from ..controller import metrics
 from .allocator import GangAllocator, SlotRequest
 from .topology import Topology, discover_topology
@@ -447,8 +447,6 @@ class NodeAgent:
                 continue
             phase = pod.get("status", {}).get("phase")
             if phase in ("Succeeded", "Failed"):
-                if key in self._procs and self._procs[key].popen is None and not self._procs[key].virtual:
-                    pass
                 continue
             try:
                 if key not in self._procs:

@@ -20,7 +20,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Sequence, Union
+from typing import List, Optional, Union
 
 from . import _lib
 from ._lib import (ALGO_AUTO, ALGO_NAMES, ALGO_NVLS, ALGO_ONESHOT, ALGO_TWOSHOT, BF16, F16, F32, MAX, MIN, SUM,
@@ -44,10 +44,6 @@ def dtype_code(dtype) -> int:
     if dtype == torch.float16:
         return F16
     raise B200MPIError(f"unsupported dtype {dtype} (float32, bfloat16, float16)")
-
-
-def _esize(code: int) -> int:
-    return 4 if code == F32 else 2
 
 
 class _CudaBlob:

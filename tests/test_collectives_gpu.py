@@ -53,7 +53,7 @@ def test_allreduce_inplace_unaligned(comm):
     base = [torch.randn(1000 + 3, device="cuda") for _ in range(comm.world)]
     xs = [b[3:] for b in base]  # 12-byte offset: exercises the byte-wise slow path
     want = _ref(xs, "sum")
-    comm.allreduce(xs, None if False else xs, op="sum", algo="twoshot")
+    comm.allreduce(xs, xs, op="sum", algo="twoshot")
     torch.cuda.synchronize()
     for x in xs:
         torch.testing.assert_close(x, want, rtol=1e-5, atol=1e-5)
