@@ -19,7 +19,7 @@ from mpi_operator_b200.models import MnistConvNet
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--use-adasum", action="store_true", help="(reference flag) Adasum is not provided; Average is used")
+    ap.add_argument("--use-adasum", action="store_true", help="use the Adasum reduction instead of averaging (reference flag)")
     ap.add_argument("--steps", type=int, default=200, help="global steps; each rank runs steps // hvd.size()")
     ap.add_argument("--batch-size", type=int, default=100)
     ap.add_argument("--checkpoint-dir", default="")
@@ -28,9 +28,10 @@ def main():
     torch.cuda.set_device(hvd.local_rank() % torch.cuda.device_count())
     torch.manual_seed(42 + hvd.rank())
     model = MnistConvNet().cuda()
-    lr_scaler = hvd.size()  # tensorflow_mnist.py:123-130
+    # tensorflow_mnist.py:123-130: LR x size for Average; Adasum needs no scaling beyond the local size
+    lr_scaler = hvd.size() if not a.use_adasum else (hvd.local_size() if hvd.nccl_built() else 1)
     opt = torch.optim.Adam(model.parameters(), lr=0.001 * lr_scaler)
-    opt = hvd.DistributedOptimizer(opt, named_parameters=model.named_parameters(), op=hvd.Average)
+    opt = hvd.DistributedOptimizer(opt, named_parameters=model.named_parameters(), op=hvd.Adasum if a.use_adasum else hvd.Average)
     hvd.broadcast_parameters(model.state_dict(), root_rank=0)
     steps = max(1, a.steps // hvd.size())  # tensorflow_mnist.py:146
     # a fixed synthetic "dataset": class = brightest quadrant pattern, learnable

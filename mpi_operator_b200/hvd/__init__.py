@@ -96,7 +96,7 @@ def _op_name(op, average):
     if op == Max:
         return "max"
     if op == Adasum:
-        raise NotImplementedError("Adasum is optional in the reference example (--use-adasum) and not provided; use Average")
+        return "adasum"
     raise ValueError(f"unknown reduction op {op!r}")
 
 
@@ -108,6 +108,9 @@ def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, pos
 
 def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
     import torch
+    if _op_name(op, average) == "adasum":
+        from .adasum import adasum_allreduce_
+        return adasum_allreduce_(_comm(), tensor)
     t = tensor if tensor.is_contiguous() else tensor.contiguous()
     if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         f = t.float()

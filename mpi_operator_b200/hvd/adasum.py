@@ -1,0 +1,43 @@
+"""Adasum reduction (the optional ``--use-adasum`` flag of the reference example,
+examples/v2beta1/horovod/tensorflow_mnist.py:31-32,126-133).
+
+Adasum(a, b) = (1 - a.b / (2|a|^2)) a + (1 - a.b / (2|b|^2)) b, applied as a binary tree over the
+ranks: orthogonal gradients add, parallel gradients average. Here every rank gathers the N tensors
+(one b200mpi allgather kernel) and folds the tree locally in fp32 — identical bits on all ranks,
+O(N*S) scratch; meant for the example-scale models that use it, not the benchmark path.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import torch
+
+
+def adasum_pair(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    a32, b32 = a.float(), b.float()
+    dot = torch.dot(a32.flatten(), b32.flatten())
+    na, nb = a32.pow(2).sum(), b32.pow(2).sum()
+    ca = torch.where(na > 0, 1.0 - dot / (2.0 * na.clamp_min(1e-30)), torch.ones_like(dot))
+    cb = torch.where(nb > 0, 1.0 - dot / (2.0 * nb.clamp_min(1e-30)), torch.ones_like(dot))
+    return ca * a32 + cb * b32
+
+
+def adasum_tree(tensors: List[torch.Tensor]) -> torch.Tensor:
+    """Pairwise (recursive-halving order) fold; N need not be a power of two."""
+    level = [t.float() for t in tensors]
+    while len(level) > 1:
+        nxt = [adasum_pair(level[i], level[i + 1]) for i in range(0, len(level) - 1, 2)]
+        if len(level) % 2:
+            nxt.append(level[-1])
+        level = nxt
+    return level[0]
+
+
+def adasum_allreduce_(comm, tensor: torch.Tensor, stream=None) -> torch.Tensor:
+    flat = tensor.contiguous().view(-1)
+    work = flat if flat.dtype in (torch.float32, torch.bfloat16, torch.float16) else flat.float()
+    gathered = torch.empty(comm.world * work.numel(), dtype=work.dtype, device=work.device)
+    comm.allgather(work, gathered, stream=stream)
+    out = adasum_tree(list(gathered.view(comm.world, -1).unbind(0)))
+    tensor.copy_(out.view_as(tensor).to(tensor.dtype))
+    return tensor

@@ -73,8 +73,12 @@ class _DistributedOptimizer:
         self._stream.wait_event(ev)
         scale = 1.0 / self._passes if self._passes > 1 else None
         with torch.cuda.stream(self._stream):
-            self._comm.allreduce_window(self._win, b["start"] * 4, b["numel"], torch.float32, op=self._op, scale=scale,
-                                        stream=self._stream)
+            if self._op == "adasum":
+                from .adasum import adasum_allreduce_
+                adasum_allreduce_(self._comm, self._flat[b["start"]:b["start"] + b["numel"]], stream=self._stream)
+            else:
+                self._comm.allreduce_window(self._win, b["start"] * 4, b["numel"], torch.float32, op=self._op, scale=scale,
+                                            stream=self._stream)
         b["pending"] = -1
 
     def synchronize(self):

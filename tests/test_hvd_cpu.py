@@ -1,0 +1,64 @@
+"""CPU-checkable parts of the Horovod-compatible front-end: Adasum math, elastic State bookkeeping, API surface."""
+import os
+
+import pytest
+import torch
+
+import horovod.torch as hvd
+from mpi_operator_b200.hvd.adasum import adasum_pair, adasum_tree
+
+
+def test_adasum_properties():
+    a = torch.tensor([1.0, 0.0, 0.0])
+    b = torch.tensor([0.0, 2.0, 0.0])
+    torch.testing.assert_close(adasum_pair(a, b), a + b)          # orthogonal gradients add
+    torch.testing.assert_close(adasum_pair(a, a), a)              # identical gradients average
+    torch.testing.assert_close(adasum_pair(a, 3 * a), 2.0 * a)    # parallel gradients: (a + 3a)/2
+    z = torch.zeros(3)
+    torch.testing.assert_close(adasum_pair(a, z), a)              # zero gradient is neutral
+    ts = [torch.randn(50) for _ in range(5)]                      # non power-of-two tree is well defined
+    out = adasum_tree(ts)
+    assert out.shape == (50,) and torch.isfinite(out).all()
+    torch.testing.assert_close(adasum_tree([ts[0]]), ts[0])
+    torch.testing.assert_close(adasum_tree(ts[:2]), adasum_pair(ts[0], ts[1]))
+
+
+def test_hvd_surface_and_uninitialised_errors():
+    for name in ("init", "shutdown", "rank", "size", "local_rank", "local_size", "allreduce", "allreduce_", "allgather", "broadcast",
+                 "broadcast_", "broadcast_parameters", "broadcast_optimizer_state", "broadcast_object", "DistributedOptimizer",
+                 "Average", "Sum", "Adasum", "Compression", "elastic", "nccl_built", "mpi_built", "join", "barrier"):
+        assert hasattr(hvd, name), name
+    assert hvd.nccl_built() and hvd.Average == "average"
+    if not hvd.is_initialized():
+        with pytest.raises(RuntimeError):
+            hvd.rank()
+
+
+def test_elastic_state_commit_restore_and_host_update(tmp_path, monkeypatch):
+    from mpi_operator_b200.hvd import elastic
+    root = tmp_path / "rootfs"
+    (root / "etc/mpi").mkdir(parents=True)
+    script = root / "etc/mpi/discover_hosts.sh"
+    script.write_text("#!/bin/sh\necho a\n")
+    monkeypatch.setenv("B200MPI_POD_ROOTFS", str(root))
+    st = elastic.State(step=0, note="x")
+    st.step = 7
+    st.commit()                       # saves, host set unchanged
+    st.step = 9
+    st.restore()
+    assert st.step == 7
+    script.write_text("#!/bin/sh\necho a\necho b\n")
+    st.step = 8
+    with pytest.raises(elastic.HostsUpdatedInterrupt):
+        st.commit()                   # saved first, then the changed host set interrupts
+    st.step = 100
+    st.restore()
+    assert st.step == 8
+
+    @elastic.run
+    def train(state):
+        raise elastic.HostsUpdatedInterrupt("rescale")
+    monkeypatch.setattr(elastic.State, "sync", lambda self: None)
+    with pytest.raises(SystemExit) as e:
+        train(st)
+    assert e.value.code == 75
