@@ -62,3 +62,20 @@ def test_elastic_state_commit_restore_and_host_update(tmp_path, monkeypatch):
     with pytest.raises(SystemExit) as e:
         train(st)
     assert e.value.code == 75
+
+
+def test_trace_export_and_roofline_report(tmp_path):
+    import json
+    from mpi_operator_b200.utils import roofline, trace
+    p = tmp_path / "t.jsonl"
+    p.write_text("\n".join(json.dumps(r) for r in [
+        {"rank": 0, "op": "allreduce", "bytes": 1024, "algo": "oneshot", "blocks": 1, "t_ns": 1000},
+        {"rank": 1, "op": "allreduce", "bytes": 1024, "algo": "oneshot", "blocks": 1, "t_ns": 1500},
+        {"rank": 0, "op": "allreduce_sgd", "bytes": 1 << 25, "algo": "nvls", "blocks": 16, "t_ns": 9000}]))
+    out = tmp_path / "t.json"
+    assert trace.main([str(p), str(out)]) == 0
+    ev = json.load(open(out))["traceEvents"]
+    assert sum(1 for e in ev if e["ph"] == "X") == 3 and {e["pid"] for e in ev} == {0, 1}
+    assert trace.summarize(trace.load_jsonl(str(p)))["allreduce[oneshot]"] == {"calls": 2, "bytes": 2048}
+    md = roofline.report("/root/repo/profiles/allreduce_sweep_n8_f32.json")
+    assert "| float32 | 1073741824 | nvls" in md and "x |" in md
