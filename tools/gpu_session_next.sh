@@ -1,0 +1,14 @@
+#!/bin/bash
+# First GPU call of the next round: diagnose the 8-GPU LD_PRELOAD shim failure with per-rank logs.
+# Usage: gpurun --gpus 8 --timeout 600 -- 'tools/gpu_session_next.sh 8'
+N=${1:-8}
+export B200MPI_NO_AUTOBUILD=1 B200MPI_DEBUG=1
+SHIM=$PWD/mpi_operator_b200/lib/libb200mpi_nccl.so
+mkdir -p gpurun_out/shim_n$N
+echo "=== DDP worker under LD_PRELOAD, N=$N (per-rank logs in gpurun_out/shim_n$N) ==="
+LD_PRELOAD=$SHIM timeout 150 python tests/mp_launch.py -n $N --timeout 120 --log-dir gpurun_out/shim_n$N tests/ddp_shim_worker.py
+for f in gpurun_out/shim_n$N/*.log; do echo "--- $f"; grep -v "^frame\|^$" $f | tail -25; done
+echo "=== ResNet-50 DDP script under LD_PRELOAD, N=$N ==="
+mkdir -p gpurun_out/ddp_n$N
+LD_PRELOAD=$SHIM timeout 200 python tests/mp_launch.py -n $N --timeout 180 --log-dir gpurun_out/ddp_n$N examples/torch-ddp/torch_ddp_resnet50.py --steps 20 --warmup 5
+for f in gpurun_out/ddp_n$N/*.log; do echo "--- $f"; grep -v "^frame\|^$" $f | tail -12; done
