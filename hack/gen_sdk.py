@@ -17,7 +17,56 @@ def snake(name):
     return re.sub(r"(?<!^)(?=[A-Z])", "_", name).lower()
 
 
+PY_TYPES = {"integer": "int", "string": "str", "boolean": "bool", "object": "object", "number": "float"}
+
+
+def _py_type(prop):
+    """Swagger property -> (python type text, markdown link or None)."""
+    if "$ref" in prop:
+        ref = prop["$ref"].rsplit("/", 1)[1]
+        if ref.startswith("v2beta1."):
+            n = "V2beta1" + ref.split(".", 1)[1]
+            return n, f"[**{n}**]({n}.md)"
+        return "object", None
+    t = prop.get("type")
+    if t == "array":
+        inner, _ = _py_type(prop.get("items", {}))
+        return f"list[{inner}]", None
+    if t == "object" and "additionalProperties" in prop:
+        inner, _ = _py_type(prop["additionalProperties"])
+        return f"dict(str, {inner})", None
+    if t == "string" and prop.get("format") == "date-time":
+        return "datetime", None
+    return PY_TYPES.get(t, "object"), None
+
+
+def render_docs(sw):
+    """Per-model markdown reference (the role of sdk/python/v2beta1/docs/V2beta1*.md in the reference tree,
+    produced there by openapi-generator; here rendered straight from our swagger.json)."""
+    out = {}
+    for name, schema in sorted(sw["definitions"].items()):
+        cls = "V2beta1" + name.split(".", 1)[1]
+        req = set(schema.get("required", []))
+        lines = [f"# {cls}", "", schema.get("description", "").strip(), "", "## Properties",
+                 "Name | Type | Description | Notes", "------------ | ------------- | ------------- | -------------"]
+        for jname in sorted(schema["properties"], key=snake):
+            prop = schema["properties"][jname]
+            t, link = _py_type(prop)
+            desc = (prop.get("description") or "").replace("|", "\\|").replace("\n", " ")
+            lines.append(f"**{snake(jname)}** | {link or '**' + t + '**'} | {desc} | {'' if jname in req else '[optional]'}")
+        lines += ["", "[[Back to README]](../README.md)", ""]
+        out[f"sdk/python/v2beta1/docs/{cls}.md"] = "\n".join(lines)
+    return out
+
+
 def main():
+    if "--docs" in sys.argv:
+        sw = json.load(open(os.path.join(ROOT, "sdk/python/v2beta1/swagger.json")))
+        for rel, text in render_docs(sw).items():
+            os.makedirs(os.path.dirname(os.path.join(ROOT, rel)), exist_ok=True)
+            open(os.path.join(ROOT, rel), "w").write(text)
+            print("wrote", rel)
+        return
     sw = json.load(open(os.path.join(ROOT, "sdk/python/v2beta1/swagger.json")))
     bad = 0
     for name, schema in sw["definitions"].items():

@@ -14,13 +14,17 @@ from mpi_operator_b200.api import openapi  # noqa: E402
 
 
 def render():
+    sys.path.insert(0, os.path.join(ROOT, "hack"))
+    import gen_sdk
     crd = yaml.safe_dump(openapi.crd(), sort_keys=False)
     operator_cfg = open(os.path.join(ROOT, "manifests/base/operator-config.yaml")).read()
-    return {
+    out = {
         "manifests/base/kubeflow.org_mpijobs.yaml": "---\n" + crd,
         "sdk/python/v2beta1/swagger.json": json.dumps(openapi.swagger(), indent=2, sort_keys=True) + "\n",
         "deploy/v2beta1/mpi-operator.yaml": "# all-in-one: CRD schema + daemon config (hack/generate.py; reference: hack/generate-manifest.sh:24-37)\n---\n" + crd + "---\n" + operator_cfg,
     }
+    out.update(gen_sdk.render_docs(openapi.swagger()))  # per-model SDK docs (reference: sdk/python/v2beta1/docs/*.md)
+    return out
 
 
 def main():

@@ -57,9 +57,16 @@ BIN_DIR = os.path.join(PKG_DIR, "bin")
 REPO_ROOT = os.path.dirname(PKG_DIR)
 # "Images" on a single box: a container image is a directory + command remaps. The reference's
 # example images resolve to the in-repo equivalents of what those images contain.
+# An image may carry an "entrypoint" (used when the container sets no `command`, k8s ENTRYPOINT/CMD semantics) —
+# the reference's MPICH and Intel images use build/base/entrypoint.sh (build/base/mpich.Dockerfile, intel.Dockerfile).
+_ENTRYPOINT_SH = os.path.join(REPO_ROOT, "build", "base", "entrypoint.sh")
 IMAGE_REGISTRY = {
     "mpioperator/tensorflow-benchmarks": {"workingDir": os.path.join(REPO_ROOT, "examples", "tensorflow-benchmarks")},
     "mpioperator/mpi-pi": {},
+    "mpioperator/mpi-pi:mpich": {"entrypoint": ["bash", _ENTRYPOINT_SH]},
+    "mpioperator/mpi-pi:intel": {"entrypoint": ["bash", _ENTRYPOINT_SH]},
+    "mpioperator/mpich": {"entrypoint": ["bash", _ENTRYPOINT_SH]},
+    "mpioperator/intel": {"entrypoint": ["bash", _ENTRYPOINT_SH]},
     "mpioperator/torch-ddp": {"workingDir": REPO_ROOT},
     "docker.io/kubeflow/mpi-horovod-mnist": {"remap": {"/examples/tensorflow_mnist.py": os.path.join(REPO_ROOT, "examples", "horovod", "torch_mnist.py")}},
 }
@@ -72,7 +79,7 @@ def image_config(image: str) -> dict:
     if extra and os.path.exists(extra):
         with open(extra) as f:
             reg.update(json.load(f))
-    return reg.get(base, {})
+    return reg.get(image or "", reg.get(base, {}))
 
 
 def _rand(n=5):
@@ -575,7 +582,10 @@ class NodeAgent:
         pr.pod_dir = pdir
         pr.log_path = os.path.join(pdir, "logs", "0.log")
         c0 = pod["spec"]["containers"][0]
+        img = image_config(c0.get("image", ""))
         argv = list(c0.get("command") or []) + list(c0.get("args") or [])
+        if not c0.get("command") and c0.get("args") and img.get("entrypoint") and os.path.basename(argv[0]) != "sshd":
+            argv = list(img["entrypoint"]) + argv
         mounts = self._materialize_volumes(pod, pdir)
         self._procs[key] = pr
         if argv and os.path.basename(argv[0]) == "sshd":
@@ -588,7 +598,6 @@ class NodeAgent:
                                "container has no command/args and images are not used on a single box")
             return
         env = self._build_env(pod, pdir, mounts)
-        img = image_config(c0.get("image", ""))
         argv = [img.get("remap", {}).get(a, a) for a in argv]
         if argv[0] in ("python", "python3"):
             import sys as _sys

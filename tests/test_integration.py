@@ -84,6 +84,25 @@ def test_pi_job_happy_path_events_and_cleanup(op):
 
 
 @needs_native
+@pytest.mark.parametrize("flavour,hostfile_env,line", [("mpich", "HYDRA_HOST_FILE", "pi-worker-0.pi.default.svc:1"),
+                                                        ("intel", "I_MPI_HYDRA_HOST_FILE", "pi-worker-0.pi.default.svc:1")])
+def test_pi_job_hydra_flavours_run_through_image_entrypoint(op, flavour, hostfile_env, line):
+    """examples/pi/pi-{mpich,intel}.yaml (reference: examples/v2beta1/pi/pi-mpich.yaml, pi-intel.yaml; e2e
+    test/e2e/mpi_job_test.go:191-283): args-only launcher -> image ENTRYPOINT (entrypoint.sh) -> Hydra-dialect mpirun."""
+    job = yaml_io.load_file(os.path.join(REPO, f"examples/pi/pi-{flavour}.yaml"))[0]
+    job.metadata["namespace"] = "default"
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    env = {e["name"]: e.get("value") for e in launcher["spec"]["containers"][0]["env"]}
+    assert env[hostfile_env] == "/etc/mpi/hostfile"
+    root = os.path.join(op.agent.pod_dir(launcher), "rootfs", "etc", "mpi")
+    assert open(os.path.join(root, "hostfile")).read().splitlines()[0] == line
+    log = op.agent.logs("default", launcher["metadata"]["name"])
+    assert "pi is approximately 3.1" in log and "Worker 1/2 on pi-worker-1" in log
+
+
+@needs_native
 def test_malformed_command_backoff_limit_failed(op):
     job = new_mpijob("bad", workers=1, launcher_cmd=("mpirun",), launcher_args=("-n", "1", "sh", "-c", "echo boom >&2; exit 7"),
                      worker_cmd=("/usr/sbin/sshd", "-De"), backoff_limit=1)
