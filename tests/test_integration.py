@@ -103,6 +103,25 @@ def test_pi_job_hydra_flavours_run_through_image_entrypoint(op, flavour, hostfil
 
 
 @needs_native
+def test_pi_job_with_custom_cluster_domain(tmp_path):
+    """e2e 'with custom cluster-domain' (test/e2e/mpi_job_test.go:532-583): --cluster-domain is appended to every
+    hostfile FQDN and the launcher still resolves its workers."""
+    o = Operator(ServerOption(fake_gpus=0, leader_elect=False, state_dir=str(tmp_path), cluster_domain="cluster.local"))
+    o.start()
+    try:
+        job = yaml_io.load_file(os.path.join(REPO, "examples/pi/pi.yaml"))[0]
+        job.metadata["namespace"] = "default"
+        submit(o, job)
+        wait_for(lambda: conds(get(o, job)).get("Succeeded") == "True", what="Succeeded")
+        launcher = [p for p in o.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+        root = os.path.join(o.agent.pod_dir(launcher), "rootfs", "etc", "mpi")
+        assert open(os.path.join(root, "hostfile")).read().splitlines()[0] == "pi-worker-0.pi.default.svc.cluster.local slots=1"
+        assert "Worker 1/2 on pi-worker-1" in o.agent.logs("default", launcher["metadata"]["name"])
+    finally:
+        o.stop()
+
+
+@needs_native
 def test_malformed_command_backoff_limit_failed(op):
     job = new_mpijob("bad", workers=1, launcher_cmd=("mpirun",), launcher_args=("-n", "1", "sh", "-c", "echo boom >&2; exit 7"),
                      worker_cmd=("/usr/sbin/sshd", "-De"), backoff_limit=1)
