@@ -237,7 +237,9 @@ def main() -> int:
             "dtype": "bf16", "data": "synthetic", "impl": args.impl,
             "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": "3x224x224",
                        "parallelism": f"dp{world}", "optimizer": "sgd_momentum0.9", "layout": "channels_last",
-                       "params_dtype": "fp32 master, bf16 autocast compute",
+                       "params_dtype": "fp32 master, bf16 autocast compute" + (
+                           " (bf16 weight shadow refreshed by the fused SGD kernel)"
+                           if args.impl != "torchddp" and getattr(trainer, "bf16_params", False) else ""),
                        "l2": "256 MiB buffer rewritten between timed steps (inside the timed region); per-step "
                              "activations also exceed the 126 MB L2",
                        "baseline": "154.2 img/s/GPU x n_gpus (reference README.md:209, GPU unstated)",

@@ -50,6 +50,10 @@ def _ptr(t):
     return t.data_ptr() if t is not None else None
 
 
+def _never():
+    return False
+
+
 class _BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, residual, weight, bias, running_mean, running_var, ws, eps, momentum, relu, direct):
@@ -79,7 +83,8 @@ class _BNAct(torch.autograd.Function):
             dz = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         dx = torch.empty_like(x, memory_format=torch.channels_last)
         dres = torch.empty_like(x, memory_format=torch.channels_last) if ctx.has_res else None
-        direct = ctx.direct is not None and ctx.wb[0].grad is not None and ctx.wb[1].grad is not None
+        direct = (ctx.direct is not None and ctx.wb[0].grad is not None and ctx.wb[1].grad is not None
+                  and not getattr(ctx.direct, "accumulating", _never)())  # no_sync(): grads must add up, not overwrite
         if direct:
             # the trainer owns pre-zeroed flat gradient views: write dgamma/dbeta straight into them and
             # skip autograd's AccumulateGrad add kernels (2 tiny launches per BN layer per step)

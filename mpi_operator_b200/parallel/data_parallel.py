@@ -48,13 +48,22 @@ class Bucket:
 class FlatModelState:
     """Re-homes a module's parameters and gradients into two symmetric windows
     with identical element layout (fp32), bucketed in reverse registration order
-    (the order backward produces them)."""
+    (the order backward produces them).
 
-    def __init__(self, module: nn.Module, comm: Communicator, bucket_bytes: int = 32 << 20):
+    ``bf16_params=True`` adds a third window with the same element layout in bf16: matrix-shaped
+    parameters (conv / linear weights) become bf16 leaves that view it, their fp32 masters stay in
+    the parameter window and the fused SGD kernel refreshes the shadow in the same pass
+    (``lowp_win``). Forward then needs no per-layer fp32->bf16 weight cast and backward no
+    bf16->fp32 gradient cast + accumulate: ~3 small kernels per layer disappear from the step
+    (profiles/launches_resnet101_step_fusedbn.md: 13 % of device time in ATen elementwise kernels)."""
+
+    def __init__(self, module: nn.Module, comm: Communicator, bucket_bytes: int = 32 << 20, bf16_params: bool = False):
         self.comm = comm
+        self.bf16_params = bf16_params
         params = [p for p in module.parameters() if p.requires_grad]
         if any(p.dtype != torch.float32 for p in params):
             raise ValueError("FlatModelState expects fp32 master parameters (use autocast for bf16 compute)")
+        self.params = params
         order = list(reversed(params))
         self.buckets: List[Bucket] = []
         self.param_slot = {}
@@ -62,7 +71,9 @@ class FlatModelState:
         cur = Bucket(0, 0, 0)
         cap = max(bucket_bytes // 4, 1)
         for p in order:
-            n = _align(p.numel(), 4)  # keep every tensor 16-byte aligned
+            # keep every tensor 16-byte aligned; with a bf16 shadow, 64 elements so the bf16 views handed to
+            # cuDNN start on 128-byte boundaries as well
+            n = _align(p.numel(), 64 if bf16_params else 4)
             if cur.params and cur.numel + n > cap:
                 cur.numel = _align(cur.numel, 8)
                 off = cur.start + cur.numel
@@ -80,13 +91,30 @@ class FlatModelState:
         self.flat_grad = self.grad_win.tensor(torch.float32, numel=self.total)
         self.flat_param.zero_()
         self.flat_grad.zero_()
+        self.lowp_win: Optional[Window] = None
+        self.flat_lowp = None
+        self.lowp_params = set()
+        self.grad_view = {}
+        if bf16_params:
+            self.lowp_win = comm.alloc_window(self.total * 2)
+            self.flat_lowp = self.lowp_win.tensor(torch.bfloat16, numel=self.total)
+            self.flat_lowp.zero_()
         for p in params:
             _, start = self.param_slot[p]
             n = p.numel()
             pv = self.flat_param[start:start + n].as_strided(p.size(), p.stride())
             pv.copy_(p.data)
-            p.data = pv
-            p.grad = self.flat_grad[start:start + n].as_strided(p.size(), p.stride())
+            gv = self.flat_grad[start:start + n].as_strided(p.size(), p.stride())
+            self.grad_view[p] = gv
+            if bf16_params and p.dim() >= 2:
+                lv = self.flat_lowp[start:start + n].as_strided(p.size(), p.stride())
+                lv.copy_(pv)
+                p.data = lv      # bf16 leaf; master = flat_param slot; gradient arrives in bf16 and is
+                p.grad = None    # gathered into the fp32 window per bucket (DataParallelTrainer._gather_grads)
+                self.lowp_params.add(p)
+            else:
+                p.data = pv
+                p.grad = gv
         for b in self.buckets:
             b.momentum = torch.zeros(comm.slice_elems(b.numel, torch.float32), device=self.flat_param.device)
 
@@ -94,6 +122,22 @@ class FlatModelState:
         """K3: rank-0 state to everyone (tensorflow_mnist.py:143)."""
         if self.comm.world > 1:
             self.comm.broadcast(self.flat_param, root=root)
+        self.refresh_lowp()
+
+    def refresh_lowp(self) -> None:
+        """Re-derive the bf16 shadow from the fp32 masters (after a broadcast, a checkpoint load or an
+        optimizer that does not write it itself)."""
+        if self.flat_lowp is not None:
+            self.flat_lowp.copy_(self.flat_param)
+
+    def master_state(self) -> dict:
+        """fp32 master copy of every re-homed parameter, keyed by its index in ``module.parameters()`` order —
+        what a checkpoint should store when ``bf16_params`` is on (the module itself holds bf16 leaves)."""
+        out = {}
+        for i, p in enumerate(self.params):
+            start = self.param_slot[p][1]
+            out[i] = self.flat_param[start:start + p.numel()].as_strided(p.size(), p.stride())
+        return out
 
     def zero_grad(self) -> None:
         self.flat_grad.zero_()
@@ -115,9 +159,13 @@ class DataParallelTrainer:
                  weight_decay: float = 0.0, nesterov: bool = False, bucket_bytes: Optional[int] = None,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, channels_last: bool = True,
                  cuda_graph: bool = True, fused_optimizer: bool = True, algo: Optional[str] = None,
-                 comm_backend: str = "b200mpi"):
+                 comm_backend: str = "b200mpi", bf16_params: Optional[bool] = None):
         self.comm = comm
-        self.device = torch.device("cuda", comm.device)
+        self.device = torch.device("cuda", comm.device) if comm.device != "cpu" else torch.device("cpu")
+        self._cuda = self.device.type == "cuda"
+        if bf16_params is None:
+            bf16_params = os.environ.get("B200MPI_BF16_PARAMS", "0") == "1"
+        self.bf16_params = bool(bf16_params) and autocast_dtype == torch.bfloat16
         self.loss_fn = loss_fn
         self.autocast_dtype = autocast_dtype
         self.channels_last = channels_last
@@ -131,18 +179,19 @@ class DataParallelTrainer:
             model = model.to(memory_format=torch.channels_last)
         self.model = model
         bucket_bytes = bucket_bytes or int(os.environ.get("B200MPI_BUCKET_BYTES", 32 << 20))
-        self.state = FlatModelState(model, comm, bucket_bytes)
+        self.state = FlatModelState(model, comm, bucket_bytes, bf16_params=self.bf16_params)
         self.state.broadcast_parameters(0)
         # {lr, momentum, weight_decay} on the device: graph replays follow schedules
         self.hyper = torch.tensor([lr, momentum, weight_decay], device=self.device, dtype=torch.float32)
         comm.set_hyper(self.hyper)
         self._lr, self._mu, self._wd = lr, momentum, weight_decay
-        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1)
+        self.comm_stream = torch.cuda.Stream(device=self.device, priority=-1) if self._cuda else None
         self._graph: Optional[torch.cuda.CUDAGraph] = None
         self._static_x = self._static_y = None
         self._loss = torch.zeros((), device=self.device)
         self._launches_per_step = 0
         self._sync = True
+        self._carry = False
         hooks = {}
         for b in self.state.buckets:
             for p in b.params:
@@ -152,11 +201,14 @@ class DataParallelTrainer:
         # themselves (mpi_operator_b200.ops.fused_bn): no AccumulateGrad add kernels for 2 x #BN params
         for mod in model.modules():
             if isinstance(mod, nn.BatchNorm2d) and mod.affine and mod.weight in hooks:
-                mod._b200_grad_ready = (lambda param, _h=hooks: _h[param](param))
+                ready = (lambda param, _h=hooks: _h[param](param))
+                ready.accumulating = lambda: (not self._sync) or self._carry
+                mod._b200_grad_ready = ready
         if self.backend == "nccl":
             import torch.distributed as dist
             self._dist = dist
-        torch.cuda.synchronize(self.device)
+        if self._cuda:
+            torch.cuda.synchronize(self.device)
         if comm.world > 1:
             comm.host_barrier()
 
@@ -179,26 +231,54 @@ class DataParallelTrainer:
                 self._reduce_bucket(bucket)
         return hook
 
+    def _gather_grads(self, b: Bucket) -> None:
+        """bf16_params mode: autograd left each matrix parameter's gradient in a bf16 tensor of its own
+        (``p.grad`` was None, so AccumulateGrad stole the buffer instead of adding); one multi-tensor
+        copy per bucket casts them into the fp32 gradient window. Parameters that got no gradient keep
+        the zeros written by ``zero_grad``."""
+        st = self.state
+        dst, src = [], []
+        for p in b.params:
+            if p in st.lowp_params and p.grad is not None:
+                dst.append(st.grad_view[p])
+                src.append(p.grad)
+        if dst:
+            torch._foreach_copy_(dst, src)
+        for p in b.params:
+            if p in st.lowp_params:
+                p.grad = None
+
     def _reduce_bucket(self, b: Bucket) -> None:
+        st = self.state
+        if st.lowp_params:
+            self._gather_grads(b)
+        if not self._cuda:  # CPU debug path (tests/test_trainer_cpu.py): same bucket logic, no streams
+            self._reduce_bucket_body(b)
+            b.pending = -1
+            return
         main = torch.cuda.current_stream(self.device)
         ev = torch.cuda.Event()
         ev.record(main)
         self.comm_stream.wait_event(ev)
-        st = self.state
         with torch.cuda.stream(self.comm_stream):
-            if self.backend == "nccl":
-                g = st.flat_grad[b.start:b.start + b.numel]
-                if self.comm.world > 1:
-                    self._dist.all_reduce(g, op=self._dist.ReduceOp.AVG)
-            elif self.fused:
-                self.comm.allreduce_sgd_window(st.grad_win, b.start * 4, st.param_win, b.start * 4, b.momentum,
-                                               b.numel, torch.float32, lr=self._lr, momentum_coef=self._mu,
-                                               weight_decay=self._wd, nesterov=self.nesterov, algo=self.algo,
-                                               stream=self.comm_stream)
-            else:
-                self.comm.allreduce_window(st.grad_win, b.start * 4, b.numel, torch.float32, op="avg",
-                                           algo=self.algo, stream=self.comm_stream)
+            self._reduce_bucket_body(b)
         b.pending = -1  # fired
+
+    def _reduce_bucket_body(self, b: Bucket) -> None:
+        st = self.state
+        if self.backend == "nccl":
+            g = st.flat_grad[b.start:b.start + b.numel]
+            if self.comm.world > 1:
+                self._dist.all_reduce(g, op=self._dist.ReduceOp.AVG)
+        elif self.fused:
+            self.comm.allreduce_sgd_window(st.grad_win, b.start * 4, st.param_win, b.start * 4, b.momentum,
+                                           b.numel, torch.float32, lr=self._lr, momentum_coef=self._mu,
+                                           weight_decay=self._wd, nesterov=self.nesterov,
+                                           lowp_win=st.lowp_win, lowp_off=b.start * 2, algo=self.algo,
+                                           stream=self.comm_stream)
+        else:
+            self.comm.allreduce_window(st.grad_win, b.start * 4, b.numel, torch.float32, op="avg",
+                                       algo=self.algo, stream=self.comm_stream)
 
     def _unfused_sgd(self) -> None:
         """Plain flat SGD (used by the NCCL baseline and fused_optimizer=False)."""
@@ -211,27 +291,34 @@ class DataParallelTrainer:
         self._flat_mom.mul_(self.hyper[1]).add_(g)
         upd = g.add(self._flat_mom, alpha=self._mu) if self.nesterov else self._flat_mom
         st.flat_param.sub_(upd * self.hyper[0])
+        st.refresh_lowp()
 
     # ----------------------------------------------------------- step --
     def _fwd_bwd(self, x, y):
         st = self.state
-        st.zero_grad()
+        if not self._carry:  # gradients of a preceding no_sync() step are kept and added to
+            st.zero_grad()
         for b in st.buckets:
             b.pending = len(b.params)
         if self.autocast_dtype is not None:
-            with torch.autocast("cuda", dtype=self.autocast_dtype):
+            with torch.autocast(self.device.type, dtype=self.autocast_dtype):
                 out = self.model(x)
                 loss = self.loss_fn(out, y)
         else:
             loss = self.loss_fn(self.model(x), y)
         loss.backward()
+        self._loss.copy_(loss.detach())
+        if not self._sync:   # local accumulation only (Horovod: backward_passes_per_step > 1)
+            self._carry = True
+            return
         for b in st.buckets:  # parameters that received no gradient this step
             if b.pending != -1:
                 self._reduce_bucket(b)
-        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        if self._cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         if not self.fused:
             self._unfused_sgd()
-        self._loss.copy_(loss.detach())
+        self._carry = False
 
     def _ensure_static(self, x, y):
         if self._static_x is None or self._static_x.shape != x.shape:
@@ -246,7 +333,7 @@ class DataParallelTrainer:
         self._ensure_static(x, y)
         self._static_x.copy_(x, non_blocking=True)
         self._static_y.copy_(y, non_blocking=True)
-        if not self.use_graph:
+        if not self.use_graph or not self._cuda or not self._sync or self._carry:
             n0 = self.comm.launch_count
             self._fwd_bwd(self._static_x, self._static_y)
             self._launches_per_step = self.comm.launch_count - n0
@@ -278,6 +365,8 @@ class DataParallelTrainer:
             self.comm.host_barrier()
 
     def no_sync(self):
+        """Context manager: steps inside accumulate gradients locally (no collective, no update, run eagerly);
+        the first step after it reduces the accumulated sum and applies one update."""
         trainer = self
 
         class _Ctx:

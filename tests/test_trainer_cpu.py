@@ -1,0 +1,192 @@
+"""DataParallelTrainer bucket / optimizer / bf16-shadow / accumulation logic on CPU.
+
+The trainer normally runs on a GPU against the native runtime; here the Communicator is replaced
+by an in-memory fake whose fused allreduce+SGD does in PyTorch exactly what ``k_allreduce_sgd``
+does per element (csrc/kernels/collectives.cu), so the host-side logic — flat layout, reverse-order
+buckets, hook bookkeeping, the bf16 parameter shadow, ``no_sync`` accumulation — is verified against
+``torch.optim.SGD`` without a device. GPU numerics of the kernels themselves: test_collectives_gpu.py,
+test_trainer_gpu.py."""
+import copy
+
+import pytest
+import torch
+import torch.nn as nn
+
+from mpi_operator_b200.parallel.data_parallel import DataParallelTrainer
+
+
+class FakeWindow:
+    def __init__(self, wid, nbytes):
+        self.id, self.nbytes = wid, nbytes
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8)
+
+    def tensor(self, dtype=None, rank=-1, offset=0, numel=None):
+        dtype = dtype or torch.uint8
+        esz = torch.empty((), dtype=dtype).element_size()
+        if numel is None:
+            numel = (self.nbytes - offset) // esz
+        return self.buf[offset:offset + numel * esz].view(dtype)
+
+
+class FakeComm:
+    device = "cpu"
+    rank, world = 0, 1
+
+    def __init__(self):
+        self.windows, self.launch_count, self.hyper, self.calls = [], 0, None, []
+
+    def alloc_window(self, nbytes):
+        w = FakeWindow(len(self.windows), nbytes)
+        self.windows.append(w)
+        return w
+
+    def slice_elems(self, count, dtype):
+        return count
+
+    def set_hyper(self, t):
+        self.hyper = t
+
+    def broadcast(self, tensor, root=0, stream=None):
+        pass
+
+    def host_barrier(self):
+        pass
+
+    def allreduce_window(self, win, offset, count, dtype, op="sum", scale=None, algo=None, stream=None):
+        self.launch_count += 1  # world 1: avg of one rank is the identity
+
+    def allreduce_sgd_window(self, grad_win, grad_off, param_win, param_off, momentum, count, grad_dtype, lr,
+                             momentum_coef=0.0, weight_decay=0.0, nesterov=False, first_step=False, scale=None,
+                             lowp_win=None, lowp_off=0, algo=None, stream=None):
+        self.launch_count += 1
+        self.calls.append((grad_off, count, lowp_off if lowp_win is not None else None))
+        if self.hyper is not None:
+            lr, momentum_coef, weight_decay = (float(v) for v in self.hyper)
+        g = grad_win.tensor(torch.float32, offset=grad_off, numel=count) * (scale if scale is not None else 1.0 / self.world)
+        p = param_win.tensor(torch.float32, offset=param_off, numel=count)
+        g = g + weight_decay * p
+        momentum.copy_(g if first_step else momentum_coef * momentum + g)
+        p.sub_(lr * (g + momentum_coef * momentum if nesterov else momentum))
+        if lowp_win is not None:
+            lowp_win.tensor(torch.bfloat16, offset=lowp_off, numel=count).copy_(p)
+
+
+def small_cnn():
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU(),
+                         nn.Conv2d(8, 16, 3, padding=1, bias=True), nn.ReLU(), nn.AdaptiveAvgPool2d(1), nn.Flatten(),
+                         nn.Linear(16, 10))
+
+
+def batches(n, seed=1):
+    g = torch.Generator().manual_seed(seed)
+    return [(torch.randn(4, 3, 8, 8, generator=g), torch.randint(0, 10, (4,), generator=g)) for _ in range(n)]
+
+
+def reference_steps(model, data, lr, mu, wd, nesterov=False, autocast=False, accumulate=1):
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mu, weight_decay=wd, nesterov=nesterov)
+    lossf = nn.CrossEntropyLoss()
+    losses = []
+    for i, (x, y) in enumerate(data):
+        if i % accumulate == 0:
+            opt.zero_grad()
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast):
+            loss = lossf(model(x), y)
+        loss.backward()
+        losses.append(float(loss.detach()))
+        if i % accumulate == accumulate - 1:
+            opt.step()
+    return losses
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("nesterov", [False, True])
+def test_fp32_trainer_matches_torch_sgd_across_buckets(fused, nesterov):
+    ref = small_cnn()
+    model = copy.deepcopy(ref)
+    data = batches(4)
+    want = reference_steps(ref, data, 0.1, 0.9, 1e-3, nesterov)
+    comm = FakeComm()
+    tr = DataParallelTrainer(model, nn.CrossEntropyLoss(), comm, lr=0.1, momentum=0.9, weight_decay=1e-3, nesterov=nesterov,
+                             bucket_bytes=1024, autocast_dtype=None, channels_last=False, cuda_graph=False, fused_optimizer=fused)
+    assert len(tr.state.buckets) > 2
+    got = [float(tr.step(x, y)) for x, y in data]
+    assert got == pytest.approx(want, rel=1e-5)
+    for a, b in zip(model.parameters(), ref.parameters()):
+        torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    if fused:  # one fused kernel per bucket per step, regions tile the flat buffer in order
+        per_step = comm.calls[:len(tr.state.buckets)]
+        assert sorted(c[0] for c in per_step) == [b.start * 4 for b in tr.state.buckets]
+        assert tr.launches_per_step == len(tr.state.buckets)
+
+
+def test_bf16_params_shadow_matches_autocast_training():
+    ref = small_cnn()
+    model = copy.deepcopy(ref)
+    data = batches(4)
+    want = reference_steps(ref, data, 0.05, 0.9, 1e-4, autocast=True)
+    comm = FakeComm()
+    tr = DataParallelTrainer(model, nn.CrossEntropyLoss(), comm, lr=0.05, momentum=0.9, weight_decay=1e-4, bucket_bytes=2048,
+                             autocast_dtype=torch.bfloat16, channels_last=False, cuda_graph=False, bf16_params=True)
+    st = tr.state
+    mats = [p for p in model.parameters() if p.dim() >= 2]
+    assert mats and all(p.dtype == torch.bfloat16 for p in mats)
+    assert all(p.dtype == torch.float32 for p in model.parameters() if p.dim() < 2)
+    got = [float(tr.step(x, y)) for x, y in data]
+    # same bf16 weights in forward, same bf16 gradients widened to fp32: the trajectories coincide
+    assert got == pytest.approx(want, rel=2e-3)
+    masters = list(st.master_state().values())
+    for m, p, r in zip(masters, model.parameters(), ref.parameters()):
+        torch.testing.assert_close(m, r, rtol=2e-3, atol=2e-4)
+        if p.dim() >= 2:
+            assert torch.equal(p.detach(), m.to(torch.bfloat16))  # shadow == bf16(master), written by the fused kernel
+            assert p.grad is None                                  # stolen bf16 gradients were gathered and released
+    assert all(c[2] == c[0] // 2 for c in comm.calls)              # lowp region offset tracks the bucket offset
+
+
+def test_bf16_params_unfused_optimizer_refreshes_shadow():
+    model = small_cnn()
+    comm = FakeComm()
+    tr = DataParallelTrainer(model, nn.CrossEntropyLoss(), comm, lr=0.05, momentum=0.9, autocast_dtype=torch.bfloat16,
+                             channels_last=False, cuda_graph=False, fused_optimizer=False, bf16_params=True)
+    before = [p.detach().clone() for p in model.parameters()]
+    for x, y in batches(2):
+        tr.step(x, y)
+    for p, b, m in zip(model.parameters(), before, tr.state.master_state().values()):
+        assert not torch.equal(p.detach(), b)
+        if p.dim() >= 2:
+            assert torch.equal(p.detach(), m.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_no_sync_accumulates_then_applies_one_update(bf16):
+    ref = small_cnn()
+    model = copy.deepcopy(ref)
+    data = batches(4)
+    reference_steps(ref, data, 0.1, 0.9, 0.0, autocast=bf16, accumulate=2)
+    comm = FakeComm()
+    tr = DataParallelTrainer(model, nn.CrossEntropyLoss(), comm, lr=0.1, momentum=0.9, bucket_bytes=4096,
+                             autocast_dtype=torch.bfloat16 if bf16 else None, channels_last=False, cuda_graph=False, bf16_params=bf16)
+    for i, (x, y) in enumerate(data):
+        if i % 2 == 0:
+            with tr.no_sync():
+                n0 = comm.launch_count
+                tr.step(x, y)
+                assert comm.launch_count == n0  # no collective, no update inside no_sync
+        else:
+            tr.step(x, y)
+    tol = dict(rtol=1e-2, atol=1e-3) if bf16 else dict(rtol=1e-5, atol=1e-6)
+    for m, r in zip(tr.state.master_state().values(), ref.parameters()):
+        torch.testing.assert_close(m, r, **tol)
+
+
+def test_env_switch_and_dtype_guard(monkeypatch):
+    monkeypatch.setenv("B200MPI_BF16_PARAMS", "1")
+    tr = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, channels_last=False, cuda_graph=False)
+    assert tr.bf16_params and tr.state.lowp_win is not None
+    tr = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, autocast_dtype=None, channels_last=False,
+                             cuda_graph=False)
+    assert not tr.bf16_params and tr.state.lowp_win is None  # no shadow without bf16 compute
+    monkeypatch.delenv("B200MPI_BF16_PARAMS")
+    assert not DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, channels_last=False,
+                                   cuda_graph=False).bf16_params
