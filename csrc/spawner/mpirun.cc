@@ -362,6 +362,24 @@ int main(int argc, char** argv) {
     rk.pidfd = (int)syscall(SYS_pidfd_open, pid, 0);  // -1 on old kernels: waitpid polling below still works
   }
 
+  // ---- fault injection from outside the ranks (mpi_operator_b200/utils/fault.py documents the grammar):
+  // B200MPI_FAULT="kill_rank:R@time:SECONDS[;once]" — SIGKILL rank R's process group SECONDS after spawn.
+  int fault_rank = -1; double fault_after = 0; bool fault_done = false; std::string fault_marker;
+  if (const char* fs = getenv("B200MPI_FAULT")) {
+    int r = -1; double t = 0;
+    if (sscanf(fs, "kill_rank:%d@time:%lf", &r, &t) == 2 && r >= 0 && r < np) {
+      fault_rank = r; fault_after = t;
+      if (strstr(fs, ";once")) {
+        std::string dir = getenv("B200MPI_FAULT_DIR") ? getenv("B200MPI_FAULT_DIR") : "";
+        if (dir.empty() && getenv("B200MPI_SLOTS_FILE")) { dir = getenv("B200MPI_SLOTS_FILE"); size_t k = dir.rfind('/'); dir = k == std::string::npos ? "." : dir.substr(0, k); }
+        if (dir.empty()) dir = "/tmp";
+        fault_marker = dir + "/" + (getenv("B200MPI_MPIJOB_NAME") ? getenv("B200MPI_MPIJOB_NAME") : "job") + ".fault-mpirun.fired";
+        if (access(fault_marker.c_str(), F_OK) == 0) fault_done = true;
+      }
+    }
+  }
+  struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+
   // ---- supervise --------------------------------------------------------------------
   int alive = np, first_fail_rank = -1, first_fail_status = 0;
   bool killing = false;
@@ -377,6 +395,17 @@ int main(int argc, char** argv) {
       if (!rk.exited && rk.pidfd >= 0) pf.push_back({rk.pidfd, POLLIN, 0});
     }
     poll(pf.data(), pf.size(), 100);
+    if (fault_rank >= 0 && !fault_done) {
+      struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+      if ((ts.tv_sec - ts0.tv_sec) + (ts.tv_nsec - ts0.tv_nsec) * 1e-9 >= fault_after) {
+        fault_done = true;
+        if (!fault_marker.empty()) { FILE* mf = fopen(fault_marker.c_str(), "w"); if (mf) { fprintf(mf, "rank %d\n", fault_rank); fclose(mf); } }
+        for (auto& rk : ranks) if (rk.rank == fault_rank && !rk.exited && rk.pid > 0) {
+          fprintf(stderr, "mpirun (b200mpi): fault injection: SIGKILL rank %d\n", fault_rank);
+          kill(-rk.pid, SIGKILL);
+        }
+      }
+    }
     for (auto& rk : ranks) {
       if (rk.out >= 0) { bool open = drain(rk.out, rk.obuf); flush_lines(rk.obuf, stdout, tag_output, rk.rank, "stdout", !open); }
       if (rk.err >= 0) { bool open = drain(rk.err, rk.ebuf); flush_lines(rk.ebuf, stderr, tag_output, rk.rank, "stderr", !open); }

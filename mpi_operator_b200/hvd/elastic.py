@@ -38,6 +38,8 @@ class State:
         self._keys = list(kwargs)
 
     def commit(self):
+        from ..utils import fault
+        fault.injector().on_step()
         self.save()
         self.check_host_updates()
 

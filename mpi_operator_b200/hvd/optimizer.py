@@ -88,6 +88,8 @@ class _DistributedOptimizer:
         torch.cuda.current_stream().wait_stream(self._stream)
 
     def step(self, closure=None):
+        from ..utils import fault
+        fault.injector().on_step()
         self._pass += 1
         if self._pass < self._passes:
             return None

@@ -29,6 +29,7 @@ import torch
 import torch.nn as nn
 
 from ..runtime.comm import Communicator, Window
+from ..utils import fault
 
 
 def _align(n: int, a: int) -> int:
@@ -192,6 +193,7 @@ class DataParallelTrainer:
         self._launches_per_step = 0
         self._sync = True
         self._carry = False
+        self._fault = fault.injector(comm.rank)  # $B200MPI_FAULT recovery tests; disarmed when unset
         hooks = {}
         for b in self.state.buckets:
             for p in b.params:
@@ -330,6 +332,7 @@ class DataParallelTrainer:
 
     def step(self, x, y):
         """One optimizer step on a batch given as (pinned) host or device tensors."""
+        self._fault.on_step()
         self._ensure_static(x, y)
         self._static_x.copy_(x, non_blocking=True)
         self._static_y.copy_(y, non_blocking=True)
