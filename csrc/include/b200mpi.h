@@ -99,6 +99,9 @@ int b200mpi_comm_host_allgather(b200mpi_comm_t comm, const void* in, void* out, 
 int b200mpi_comm_check_error(b200mpi_comm_t comm);
 /* number of b200mpi kernels launched so far on this communicator */
 uint64_t b200mpi_comm_launch_count(b200mpi_comm_t comm);
+/* JSON counters by (op, algorithm): calls and payload bytes of every host-launched collective. snprintf-style:
+ * writes at most cap-1 bytes + NUL, returns the full length. */
+int b200mpi_comm_stats_json(b200mpi_comm_t comm, char* buf, size_t cap);
 
 /*
  * Symmetric windows: every rank allocates `bytes`, all ranks map all peers,

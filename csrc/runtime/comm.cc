@@ -115,6 +115,9 @@ struct Window {
 };
 
 struct TraceRec { const char* op; size_t bytes; int algo; int blocks; uint64_t t_ns; };
+// Per-communicator counters by (op, algorithm): what /metrics exports as b200mpi_collective_{calls,bytes}_total.
+// `op` is a string literal, so pointer identity is the key; a handful of entries, linear scan.
+struct OpStat { const char* op; int algo; uint64_t calls; uint64_t bytes; };
 
 }  // namespace b200mpi
 
@@ -146,6 +149,7 @@ struct b200mpi_comm {
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
   std::vector<TraceRec> trace;
+  std::vector<OpStat> stats;
   uint32_t next_tag = 1;
   const float* hyper = nullptr;
 };
@@ -200,6 +204,13 @@ static int run(b200mpi_comm* c, cudaStream_t stream, int blocks, const char* opn
   cudaError_t e = launcher(l, args[0]);
   if (e != cudaSuccess) return fail(B200MPI_ERR_CUDA, std::string(opname) + " launch: " + cudaGetErrorString(e));
   c->launches.fetch_add(1, std::memory_order_relaxed);
+  {
+    OpStat* st = nullptr;
+    for (auto& x : c->stats) if (x.op == opname && x.algo == (algo & 3)) { st = &x; break; }
+    if (!st) { c->stats.push_back(OpStat{opname, algo & 3, 0, 0}); st = &c->stats.back(); }
+    st->calls++;
+    st->bytes += bytes;
+  }
   if (c->trace_on) c->trace.push_back(TraceRec{opname, bytes, algo, blocks, now_ns()});
   return 0;
 }
@@ -854,6 +865,29 @@ int b200mpi_get_tuning(b200mpi_comm_t c, size_t* oneshot_max, size_t* nvls_min, 
 }
 int b200mpi_select_algo(b200mpi_comm_t c, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op, int symmetric) {
   return select_algo(c, bytes, dtype, op, symmetric != 0);
+}
+
+int b200mpi_comm_stats_json(b200mpi_comm_t c, char* buf, size_t cap) {
+  // {"rank":r,"world":w,"launches":n,"ops":[{"op":"allreduce","algo":"nvls","calls":k,"bytes":b},...]}; returns the length
+  // needed (excluding NUL), like snprintf. Kernels replayed from a CUDA graph are not host launches and are not counted
+  // here (DataParallelTrainer adds replays x per-capture counts on top).
+  static const char* algos[] = {"auto", "oneshot", "twoshot", "nvls"};
+  std::string o = "{\"rank\": " + std::to_string(c->rank) + ", \"world\": " + std::to_string(c->world) +
+                  ", \"launches\": " + std::to_string((unsigned long long)c->launches.load()) + ", \"ops\": [";
+  bool first = true;
+  for (auto& x : c->stats) {
+    if (!first) o += ", ";
+    first = false;
+    o += std::string("{\"op\": \"") + x.op + "\", \"algo\": \"" + algos[x.algo & 3] + "\", \"calls\": " +
+         std::to_string((unsigned long long)x.calls) + ", \"bytes\": " + std::to_string((unsigned long long)x.bytes) + "}";
+  }
+  o += "]}";
+  if (buf && cap) {
+    size_t n = o.size() < cap - 1 ? o.size() : cap - 1;
+    memcpy(buf, o.data(), n);
+    buf[n] = 0;
+  }
+  return (int)o.size();
 }
 
 int b200mpi_trace_enable(b200mpi_comm_t c, int on) { c->trace_on = on != 0; return 0; }

@@ -17,10 +17,25 @@ is_leader = Gauge("mpi_operator_is_leader", "Is this client the leader of this m
 
 # data plane (new)
 allreduce_bytes = Counter("b200mpi_allreduce_bytes", "Bytes reduced by b200mpi allreduce kernels", ["algo"], registry=REGISTRY)
+collective_calls = Counter("b200mpi_collective_calls", "Collective kernels launched by finished ranks", ["op", "algo"], registry=REGISTRY)
+collective_bytes = Counter("b200mpi_collective_bytes", "Payload bytes moved by collective kernels of finished ranks", ["op", "algo"],
+                           registry=REGISTRY)
 ranks_active = Gauge("b200mpi_ranks_active", "Ranks currently running under the node agent", registry=REGISTRY)
 gpu_slots_free = Gauge("b200mpi_gpu_slots_free", "Unallocated GPU slots on this box", registry=REGISTRY)
 reconcile_seconds = Histogram("mpi_operator_reconcile_duration_seconds", "Wall time of one syncHandler call",
                               buckets=(0.001, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5), registry=REGISTRY)
+
+
+def observe_rank_stats(stats: dict) -> None:
+    """Fold one rank's ``Communicator.stats()`` dump into the data-plane counters (node agent, on pod exit)."""
+    for o in stats.get("ops", []):
+        op, algo, calls, nbytes = str(o.get("op", "")), str(o.get("algo", "")), int(o.get("calls", 0)), int(o.get("bytes", 0))
+        if not op or calls <= 0:
+            continue
+        collective_calls.labels(op=op, algo=algo).inc(calls)
+        collective_bytes.labels(op=op, algo=algo).inc(nbytes)
+        if op.startswith("allreduce"):
+            allreduce_bytes.labels(algo=algo).inc(nbytes)
 
 
 def render() -> bytes:

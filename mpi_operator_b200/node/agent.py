@@ -551,6 +551,7 @@ class NodeAgent:
         env["B200MPI_POD_NAMESPACE"] = M.namespace_of(pod)
         env["B200MPI_POD_DIR"] = pdir
         env["B200MPI_POD_ROOTFS"] = os.path.join(pdir, "rootfs")
+        env.setdefault("B200MPI_STATS_DIR", os.path.join(pdir, "stats"))  # ranks drop collective counters here on exit
         env["PYTHONPATH"] = os.path.dirname(PKG_DIR) + os.pathsep + env.get("PYTHONPATH", "")
         jn = labels.get(C.JOB_NAME_LABEL)
         if jn:
@@ -661,6 +662,24 @@ class NodeAgent:
         self.alloc.release(M.key_of(pod))
         self._write_all_slots()
 
+    def _harvest_stats(self, pr: _Proc) -> None:
+        """Per-rank collective counters (runtime/comm.py: dump_stats) -> b200mpi_collective_*_total. Files are consumed
+        so an OnFailure restart of the same container is not counted twice."""
+        d = os.path.join(pr.pod_dir, "stats")
+        try:
+            names = [n for n in os.listdir(d) if n.startswith("stats-") and n.endswith(".json")]
+        except OSError:
+            return
+        from ..controller import metrics
+        for n in names:
+            path = os.path.join(d, n)
+            try:
+                with open(path) as f:
+                    metrics.observe_rank_stats(json.load(f))
+                os.replace(path, path + ".seen")
+            except (OSError, ValueError):
+                continue
+
     def _tail(self, path: str, n: int = 512) -> str:
         try:
             with open(path, "rb") as f:
@@ -684,6 +703,7 @@ class NodeAgent:
         if rc is None:
             return
         pr.popen = None
+        self._harvest_stats(pr)
         if rc == 0:
             self._set_terminal(pod, pr, "Succeeded", 0, "Completed")
             return

@@ -193,6 +193,11 @@ class DataParallelTrainer:
         self._launches_per_step = 0
         self._sync = True
         self._carry = False
+        self._graph_ops: list = []   # collectives recorded in the CUDA graph: replays launch them without the host
+        self._replays = 0
+        if hasattr(comm, "add_stat_source"):
+            comm.add_stat_source(self._replayed_ops)
+        self._folded_ops: list = []  # totals of graphs that were since re-captured
         self._fault = fault.injector(comm.rank)  # $B200MPI_FAULT recovery tests; disarmed when unset
         hooks = {}
         for b in self.state.buckets:
@@ -222,6 +227,14 @@ class DataParallelTrainer:
     @property
     def launches_per_step(self) -> int:
         return self._launches_per_step
+
+    def _replayed_ops(self) -> list:
+        out = {(o["op"], o["algo"]): dict(o) for o in self._folded_ops}
+        for o in self._graph_ops:
+            m = out.setdefault((o["op"], o["algo"]), {"op": o["op"], "algo": o["algo"], "calls": 0, "bytes": 0})
+            m["calls"] += o["calls"] * self._replays
+            m["bytes"] += o["bytes"] * self._replays
+        return list(out.values())
 
     # ---------------------------------------------------------- hooks --
     def _make_hook(self, bucket: Bucket):
@@ -344,6 +357,7 @@ class DataParallelTrainer:
         if self._graph is None:
             self._capture()
         self._graph.replay()
+        self._replays += 1
         return self._loss
 
     def _capture(self):
@@ -359,9 +373,18 @@ class DataParallelTrainer:
             self.comm.host_barrier()
         g = torch.cuda.CUDAGraph()
         n0 = self.comm.launch_count
+        before = {(o["op"], o["algo"]): o for o in self.comm.stats(native_only=True)["ops"]} if hasattr(self.comm, "stats") else {}
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._fwd_bwd(self._static_x, self._static_y)
         self._launches_per_step = self.comm.launch_count - n0
+        if hasattr(self.comm, "stats"):
+            self._folded_ops = self._replayed_ops()
+            self._graph_ops, self._replays = [], 0
+            for o in self.comm.stats(native_only=True)["ops"]:
+                b = before.get((o["op"], o["algo"]), {"calls": 0, "bytes": 0})
+                if o["calls"] > b["calls"]:
+                    self._graph_ops.append({"op": o["op"], "algo": o["algo"], "calls": o["calls"] - b["calls"],
+                                            "bytes": o["bytes"] - b["bytes"]})
         self._graph = g
         torch.cuda.synchronize(self.device)
         if self.comm.world > 1:

@@ -89,6 +89,9 @@ def lib() -> C.CDLL:
     L.b200mpi_set_tuning.argtypes = [vp, sz, sz, i, i]
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
     L.b200mpi_select_algo.argtypes = [vp, sz, i, i, i]
+    if hasattr(L, "b200mpi_comm_stats_json"):  # absent only in a stale build
+        L.b200mpi_comm_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
+        L.b200mpi_comm_stats_json.restype = C.c_int
     L.b200mpi_trace_enable.argtypes = [vp, i]
     L.b200mpi_trace_dump.argtypes = [vp, C.c_char_p]
     _lib = L

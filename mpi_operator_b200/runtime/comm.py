@@ -120,6 +120,11 @@ class Communicator:
               "comm_init")
         c = cls(h, device)
         c._apply_tuning_file()
+        if os.environ.get("B200MPI_STATS_DIR"):  # scripts that never call destroy() still report their counters
+            import atexit
+            import weakref
+            ref = weakref.ref(c)
+            atexit.register(lambda: ref() is not None and ref().dump_stats())
         return c
 
     def _apply_tuning_file(self) -> None:
@@ -155,8 +160,53 @@ class Communicator:
 
     def destroy(self) -> None:
         if self._h:
+            self.dump_stats()
             _lib.lib().b200mpi_comm_destroy(self._h)
             self._h = None
+
+    # -------------------------------------------------------------- stats --
+    def stats(self, native_only: bool = False) -> dict:
+        """Counters by (op, algorithm) of every host-launched collective, plus whatever registered sources add
+        (a DataParallelTrainer reports the kernels its CUDA graph replays). Feeds ``b200mpi_collective_*_total``
+        on the operator's /metrics."""
+        import json
+        L = _lib.lib()
+        out = {"rank": self.rank, "world": self.world, "launches": 0, "ops": []}
+        if self._h and hasattr(L, "b200mpi_comm_stats_json"):
+            n = L.b200mpi_comm_stats_json(self._h, None, 0)
+            buf = C.create_string_buffer(n + 1)
+            L.b200mpi_comm_stats_json(self._h, buf, n + 1)
+            out = json.loads(buf.value.decode())
+        merged = {(o["op"], o["algo"]): dict(o) for o in out["ops"]}
+        for src in ([] if native_only else getattr(self, "_stat_sources", [])):
+            for o in src():
+                m = merged.setdefault((o["op"], o["algo"]), {"op": o["op"], "algo": o["algo"], "calls": 0, "bytes": 0})
+                m["calls"] += o["calls"]
+                m["bytes"] += o["bytes"]
+        out["ops"] = sorted(merged.values(), key=lambda o: (o["op"], o["algo"]))
+        return out
+
+    def add_stat_source(self, fn) -> None:
+        if not hasattr(self, "_stat_sources"):
+            self._stat_sources = []
+        self._stat_sources.append(fn)
+
+    def dump_stats(self, directory: Optional[str] = None) -> Optional[str]:
+        """Write ``stats()`` to ``<dir>/stats-rank<r>-<pid>.json`` (dir defaults to $B200MPI_STATS_DIR, which the node
+        agent sets per launcher pod and harvests when the pod finishes). No-op without a directory."""
+        import json
+        directory = directory or os.environ.get("B200MPI_STATS_DIR")
+        if not directory or not self._h or self.is_local:
+            return None
+        try:
+            os.makedirs(directory, exist_ok=True)
+            path = os.path.join(directory, f"stats-rank{self.rank}-{os.getpid()}.json")
+            with open(path + ".tmp", "w") as f:
+                json.dump(self.stats(), f)
+            os.replace(path + ".tmp", path)
+            return path
+        except OSError:
+            return None
 
     # --------------------------------------------------------------- misc --
     @property

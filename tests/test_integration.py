@@ -265,6 +265,26 @@ def test_active_deadline_and_ttl(op):
     wait_for(lambda: not op.store.list("jobs", "default"), timeout=10, what="launcher Job removed by TTL")
 
 
+@needs_native
+def test_rank_collective_counters_reach_the_metrics_endpoint(op):
+    """SURVEY.md §5.5 [NEW]: ranks drop Communicator.stats() into $B200MPI_STATS_DIR, the node agent folds them into
+    b200mpi_collective_{calls,bytes}_total when the launcher exits (a CPU stand-in writes the file a GPU rank would)."""
+    script = ("import json,os;d=os.environ['B200MPI_STATS_DIR'];os.makedirs(d,exist_ok=True);"
+              "json.dump({'rank':0,'world':2,'launches':3,'ops':[{'op':'allreduce_sgd','algo':'nvls','calls':2,'bytes':4096},"
+              "{'op':'broadcast','algo':'auto','calls':1,'bytes':128}]},open(os.path.join(d,'stats-rank0-1.json'),'w'))")
+    job = new_mpijob("stats", workers=1, launcher_cmd=("python",), launcher_args=("-c", script), worker_cmd=("/usr/sbin/sshd", "-De"))
+    before = metrics.collective_bytes.labels(op="allreduce_sgd", algo="nvls")._value.get()
+    ar_before = metrics.allreduce_bytes.labels(algo="nvls")._value.get()
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", what="Succeeded")
+    assert metrics.collective_bytes.labels(op="allreduce_sgd", algo="nvls")._value.get() - before == 4096
+    assert metrics.allreduce_bytes.labels(algo="nvls")._value.get() - ar_before == 4096
+    text = metrics.render().decode()
+    assert 'b200mpi_collective_calls_total{algo="auto",op="broadcast"}' in text
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    assert os.listdir(os.path.join(op.agent.pod_dir(launcher), "stats")) == ["stats-rank0-1.json.seen"]  # consumed once
+
+
 def test_metrics_text_has_reference_names(op):
     text = metrics.render().decode()
     for name in ("mpi_operator_jobs_created_total", "mpi_operator_jobs_successful_total", "mpi_operator_jobs_failed_total",

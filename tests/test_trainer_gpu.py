@@ -76,3 +76,25 @@ def test_bf16_params_trainer_tracks_the_fp32_master_trainer(graph):
         if p.dim() >= 2:
             assert torch.equal(p.data, m.to(torch.bfloat16))
     comm.destroy()
+
+
+def test_collective_counters_cover_eager_launches_and_graph_replays():
+    """Communicator.stats(): host launches counted natively, CUDA-graph replays added by the trainer (what the node
+    agent exports as b200mpi_collective_*_total)."""
+    from mpi_operator_b200.parallel.data_parallel import DataParallelTrainer
+    from mpi_operator_b200.runtime.comm import Communicator
+    comm = Communicator.create(0, 1, 0, f"t-stats-{os.getpid()}")
+    t = torch.ones(1024, device="cuda")
+    comm.allreduce(t)
+    ops = {(o["op"], o["algo"]): o for o in comm.stats()["ops"]}
+    assert sum(o["calls"] for o in ops.values()) == 1 and sum(o["bytes"] for o in ops.values()) == 4096
+    tr = DataParallelTrainer(_small_model(), nn.CrossEntropyLoss(), comm, lr=0.05, autocast_dtype=None, cuda_graph=True, bucket_bytes=2048)
+    x, y = torch.randn(8, 3, 16, 16).pin_memory(), torch.randint(0, 10, (8,)).pin_memory()
+    for _ in range(4):
+        tr.step(x, y)
+    torch.cuda.synchronize()
+    nb = len(tr.state.buckets)
+    sgd = [o for o in comm.stats()["ops"] if o["op"].startswith("allreduce_sgd")]
+    # 3 eager warm-ups + 1 capture are host launches; 4 replays come from the trainer's graph accounting
+    assert sum(o["calls"] for o in sgd) == nb * (3 + 1 + 4)
+    comm.destroy()
