@@ -1,5 +1,6 @@
 # b200mpi native build (sm_100a only). `make` builds everything in-tree; the
 # built artefacts are git-ignored but travel to the GPU box with gpurun.
+comma     := ,
 NVCC      ?= /usr/local/cuda/bin/nvcc
 CXX       ?= g++
 ARCH      := -gencode arch=compute_100a,code=sm_100a
@@ -67,4 +68,24 @@ lint:
 sanitize: all
 	compute-sanitizer --tool racecheck python tools/profile_kernels.py
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize
+# Host-side runtime under the compiler sanitizers: launcher, shm rendezvous, libmpi shim.
+SAN_CXX  ?= /usr/bin/g++
+SAN_SRCS := csrc/mpi_shim/mpi_shim.cc csrc/runtime/rendezvous.cc
+define san_build
+	@mkdir -p build/san/$(1)
+	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -o build/san/$(1)/mpirun csrc/spawner/mpirun.cc
+	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/mpi_stress csrc/tests/mpi_stress.cc $(SAN_SRCS) -lrt -lpthread
+	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/pi examples/pi/pi.cc $(SAN_SRCS) -lrt -lpthread
+endef
+
+asan:
+	$(call san_build,asan,-fsanitize=address$(comma)undefined -fno-sanitize-recover=undefined)
+	ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 build/san/asan/mpirun -n 4 build/san/asan/mpi_stress 200
+	build/san/asan/mpirun -n 2 --tag-output build/san/asan/pi
+
+tsan:
+	$(call san_build,tsan,-fsanitize=thread)
+	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
+	build/san/tsan/mpirun -n 2 build/san/tsan/pi
+
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan
