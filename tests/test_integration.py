@@ -230,6 +230,35 @@ def test_gpu_slots_gang_and_release(gang_op):
     wait_for(lambda: op.store.list("volcano-podgroups", "default") == [], what="PodGroups deleted on finish-with-cleanup")
 
 
+def test_pending_gangs_are_admitted_in_priority_order(gang_op):
+    """priorityClass orders the pending list (Volcano PodGroup.spec.priorityClassName, podgroup.go:311-334).
+    A holds the whole box; `low` is submitted before `high`; when A finishes, `high` must run first."""
+    op = gang_op
+    for name, value in (("high", 1000), ("low", 1)):
+        op.store.create("priorityclasses", {"apiVersion": "scheduling.k8s.io/v1", "kind": "PriorityClass", "metadata": {"name": name}, "value": value})
+
+    def gang(name, cmd, prio=None):
+        j = new_mpijob(name, workers=1, launcher_cmd=("sh", "-c", cmd), launcher_args=None, worker_cmd=("/usr/sbin/sshd",), clean="All")
+        j.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 4}}
+        if prio:
+            j.spec.run_policy.scheduling_policy = SchedulingPolicy(priority_class=prio)
+        return j
+    a = gang("a", "sleep 1.0")
+    submit(op, a)
+    wait_for(lambda: conds(get(op, a)).get("Running") == "True", what="A running")
+    low, high = gang("lo", "date +%s.%N", "low"), gang("hi", "date +%s.%N; sleep 0.3", "high")
+    submit(op, low)
+    time.sleep(0.2)
+    submit(op, high)
+    for j in (low, high):
+        wait_for(lambda: conds(get(op, j)).get("Succeeded") == "True", timeout=40, what=f"{j.name} Succeeded")
+    started = {}
+    for j in (low, high):
+        pod = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith(j.name + "-launcher")]
+        started[j.name] = get(op, j).status.start_time if not pod else float(op.agent.logs("default", pod[0]["metadata"]["name"]).split()[0])
+    assert started["hi"] < started["lo"], started
+
+
 def test_unschedulable_min_resources_then_cleared(gang_op):
     op = gang_op
     j = new_mpijob("big", workers=1, launcher_cmd=("sh", "-c", "true"), launcher_args=None, worker_cmd=("/usr/sbin/sshd",))
