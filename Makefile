@@ -12,7 +12,7 @@ BINDIR    := mpi_operator_b200/bin
 RUNTIME_SRCS := csrc/kernels/collectives.cu csrc/kernels/bn_act.cu csrc/runtime/comm.cc csrc/runtime/rendezvous.cc
 RUNTIME_HDRS := csrc/include/b200mpi.h csrc/kernels/device.cuh csrc/kernels/kernels.h csrc/runtime/rendezvous.h
 
-all: $(LIBDIR)/libb200mpi.so $(LIBDIR)/libb200mpi_nccl.so native
+all: $(LIBDIR)/libb200mpi.so $(LIBDIR)/libb200mpi_nccl.so $(LIBDIR)/libb200mpi_gemm.so native
 
 $(LIBDIR)/libb200mpi.so: $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)
@@ -21,6 +21,12 @@ $(LIBDIR)/libb200mpi.so: $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 $(LIBDIR)/libb200mpi_nccl.so: csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared -x cu csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread -ldl
+
+# tcgen05/TMA GEMM with fused BN statistics: a library of its own so that the experimental kernel cannot affect
+# the validated runtime library
+$(LIBDIR)/libb200mpi_gemm.so: csrc/kernels/gemm_bnstats.cu csrc/include/b200mpi.h
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared csrc/kernels/gemm_bnstats.cu -o $@
 
 native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi
 

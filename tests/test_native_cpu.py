@@ -145,3 +145,19 @@ def test_host_runtime_is_clean_under_address_and_ub_sanitizers():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "mpi_stress: all 200 iterations verified on 4 ranks" in r.stdout
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error:" not in r.stderr
+
+
+def test_tcgen05_gemm_library_builds_loads_and_validates_shapes():
+    """libb200mpi_gemm.so (csrc/kernels/gemm_bnstats.cu) is cross-compiled for sm_100a by `make`; its shape contract is
+    checked on the host: N and K multiples of 64, at most 148 column blocks, M below 2^31."""
+    from mpi_operator_b200.ops import gemm_bnstats as g
+    if not g.LIB_PATH.exists():
+        pytest.skip("native libraries not built (run make)")
+    assert g.supported(200704, 256, 64) and g.supported(1, 64, 64) and g.supported(50176, 2048, 512)
+    assert not g.supported(128, 96, 64) and not g.supported(128, 64, 32) and not g.supported(0, 64, 64)
+    assert not g.supported(128, 148 * 128 + 128, 64)
+    assert g.lib().b200mpi_gemm_bnstats_partial_floats(256) == 148 * 2 * 256
+    sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(g.LIB_PATH)], capture_output=True, text=True)
+    if sass.returncode == 0:  # the tensor-core / TMA / TMEM instructions are really there
+        for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR"):
+            assert mnemonic in sass.stdout, mnemonic
