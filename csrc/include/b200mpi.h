@@ -189,6 +189,12 @@ int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask,
                        const float* bias, float* running_mean, float* running_var, float* save_mean,
                        float* save_invstd, float* workspace, long long M, int C, float eps, float momentum,
                        int relu, void* stream);
+/* Same as b200mpi_bn_act_fwd but the per-channel statistics arrive as `parts` rows of {sum, sum of squares} (2*C floats
+ * per row, unshifted) produced by the epilogue of b200mpi_gemm_bnstats: no statistics pass over x. */
+int b200mpi_bn_act_fwd_prestats(const void* x, const void* residual, void* y, void* mask, const float* weight, const float* bias,
+                                float* running_mean, float* running_var, float* save_mean, float* save_invstd, float* workspace,
+                                const float* partials, int parts, long long M, int C, float eps, float momentum, int relu,
+                                void* stream);
 int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx, void* dres,
                        const float* weight, const float* save_mean, const float* save_invstd,
                        float* dweight, float* dbias, float* workspace, long long M, int C, int relu,

@@ -163,7 +163,7 @@ k_bn_fwd_finalize(const __nv_bfloat16* __restrict__ x_row0, const float* __restr
   const int cgi = o >> 4, j = (o & 15) >> 1, c = cgi * 8 + j;
   const float S1 = tot, S2 = other;
   const float inv_m = 1.0f / (float)M;
-  const float k = __bfloat162float(x_row0[c]);
+  const float k = x_row0 ? __bfloat162float(x_row0[c]) : 0.f;  // nullptr: partials are plain (unshifted) sums
   const float d = S1 * inv_m;
   const float mean = k + d;
   float var = fmaf(-d, d, S2 * inv_m);
@@ -393,6 +393,28 @@ int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask,
   k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, partials, M, C, rows);
   k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>((const __nv_bfloat16*)x, partials, grid, coef, M, C, weight, bias,
                                                             running_mean, running_var, save_mean, save_invstd, eps, momentum);
+  plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, elem_chunk());
+  if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
+  else if (relu) k_bn_fwd_apply<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
+  else if (residual) k_bn_fwd_apply<false, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, nullptr, coef, M, C, rows);
+  else k_bn_fwd_apply<false, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, nullptr, coef, M, C, rows);
+  return cudaGetLastError() == cudaSuccess ? 0 : B200MPI_ERR_CUDA;
+}
+
+// Forward with the statistics already reduced to `parts` rows of per-channel {sum, sum of squares} (unshifted) by the
+// producer of x — the epilogue of the tcgen05 1x1-convolution GEMM (gemm_bnstats.cu): finalize + apply only, the
+// statistics pass over x is gone.
+int b200mpi_bn_act_fwd_prestats(const void* x, const void* residual, void* y, void* mask, const float* weight, const float* bias,
+                                float* running_mean, float* running_var, float* save_mean, float* save_invstd, float* workspace,
+                                const float* partials, int parts, long long M, int C, float eps, float momentum, int relu,
+                                void* stream_) {
+  if (!b200mpi_bn_supported(M, C) || parts < 1 || !partials) return B200MPI_ERR_UNSUPPORTED;
+  cudaStream_t s = (cudaStream_t)stream_;
+  float* coef = workspace;
+  int grid;
+  long long rows;
+  k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>(nullptr, partials, parts, coef, M, C, weight, bias, running_mean,
+                                                            running_var, save_mean, save_invstd, eps, momentum);
   plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, elem_chunk());
   if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
   else if (relu) k_bn_fwd_apply<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, nullptr, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);

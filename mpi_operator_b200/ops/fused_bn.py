@@ -117,3 +117,96 @@ def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = N
     if residual is not None:
         out = out + residual
     return F.relu(out) if relu else out
+
+
+# --------------------------------------------------------------------------------------------------------------
+# 1x1 convolution + BatchNorm(+residual)+ReLU with the BN statistics taken in the GEMM epilogue
+# (csrc/kernels/gemm_bnstats.cu: TMA + tcgen05 + TMEM). EXPERIMENTAL, opt-in with B200MPI_FUSED_CONV1X1=1: the GEMM
+# kernel has not run on hardware yet. Forward = 3 launches (GEMM+stats, finalize, apply) instead of conv + 3;
+# backward = the fused BN backward kernels + two library GEMMs (dgrad, wgrad).
+_CONV1X1 = os.environ.get("B200MPI_FUSED_CONV1X1", "0") == "1"
+
+
+def _conv1x1_eligible(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, x: torch.Tensor) -> bool:
+    if not (conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.padding == (0, 0) and conv.dilation == (1, 1)
+            and conv.groups == 1 and conv.bias is None and x.is_cuda and x.dim() == 4 and x.dtype == torch.bfloat16
+            and x.is_contiguous(memory_format=torch.channels_last) and bn.training and bn.affine and bn.track_running_stats
+            and bn.momentum is not None and _ENABLED):
+        return False
+    from . import gemm_bnstats
+    n, c, h, w = x.shape
+    return (gemm_bnstats.supported(n * h * w, conv.out_channels, c)
+            and bool(_lib().b200mpi_bn_supported(n * h * w, conv.out_channels)))
+
+
+class _Conv1x1BNAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, w2d, weight, bias, running_mean, running_var, ws, eps, momentum, relu, direct):
+        from . import gemm_bnstats
+        n, cin, h, w = x.shape
+        cout = w2d.shape[0]
+        m = n * h * w
+        x2d = x.permute(0, 2, 3, 1).reshape(m, cin)      # a view: channels-last memory is [M, Cin] row-major
+        yconv, partials, parts = gemm_bnstats.gemm_bnstats_raw(x2d, w2d)
+        z = torch.empty((n, cout, h, w), dtype=torch.bfloat16, device=x.device, memory_format=torch.channels_last)
+        mask = torch.empty(m * cout // 8, dtype=torch.uint8, device=x.device) if relu else None
+        save_mean = torch.empty(cout, dtype=torch.float32, device=x.device)
+        save_invstd = torch.empty(cout, dtype=torch.float32, device=x.device)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        rc = _lib().b200mpi_bn_act_fwd_prestats(yconv.data_ptr(), _ptr(residual), z.data_ptr(), _ptr(mask), weight.data_ptr(),
+                                                bias.data_ptr(), running_mean.data_ptr(), running_var.data_ptr(),
+                                                save_mean.data_ptr(), save_invstd.data_ptr(), ws.data_ptr(), partials.data_ptr(),
+                                                parts, m, cout, eps, momentum, int(relu), stream)
+        if rc != 0:
+            raise RuntimeError(f"b200mpi_bn_act_fwd_prestats failed ({rc})")
+        ctx.save_for_backward(x2d, w2d, yconv, mask, weight, save_mean, save_invstd, ws)
+        ctx.relu, ctx.has_res, ctx.shape = relu, residual is not None, (n, cin, cout, h, w)
+        ctx.direct, ctx.wb = direct, (weight, bias)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        x2d, w2d, yconv, mask, weight, save_mean, save_invstd, ws = ctx.saved_tensors
+        n, cin, cout, h, w = ctx.shape
+        m = n * h * w
+        if dz.dtype != torch.bfloat16 or not dz.is_contiguous(memory_format=torch.channels_last):
+            dz = dz.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dy = torch.empty(m, cout, dtype=torch.bfloat16, device=dz.device)          # gradient w.r.t. the convolution output
+        dres = torch.empty_like(dz, memory_format=torch.channels_last) if ctx.has_res else None
+        direct = (ctx.direct is not None and ctx.wb[0].grad is not None and ctx.wb[1].grad is not None
+                  and not getattr(ctx.direct, "accumulating", _never)())
+        if direct:
+            dw, db = ctx.wb[0].grad, ctx.wb[1].grad
+        else:
+            dw = torch.empty(cout, dtype=torch.float32, device=dz.device)
+            db = torch.empty(cout, dtype=torch.float32, device=dz.device)
+        stream = torch.cuda.current_stream(dz.device).cuda_stream
+        rc = _lib().b200mpi_bn_act_bwd(dz.data_ptr(), yconv.data_ptr(), _ptr(mask), dy.data_ptr(), _ptr(dres), weight.data_ptr(),
+                                       save_mean.data_ptr(), save_invstd.data_ptr(), dw.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                       m, cout, int(ctx.relu), stream)
+        if rc != 0:
+            raise RuntimeError(f"b200mpi_bn_act_bwd failed ({rc})")
+        dx = (dy @ w2d).view(n, h, w, cin).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None   # dgrad: [M,Cout] x [Cout,Cin]
+        dw2d = dy.t() @ x2d if ctx.needs_input_grad[2] else None                                          # wgrad: [Cout,M] x [M,Cin]
+        if direct:
+            ctx.direct(ctx.wb[0])
+            ctx.direct(ctx.wb[1])
+            return dx, dres, dw2d, None, None, None, None, None, None, None, None, None
+        return dx, dres, dw2d, dw, db, None, None, None, None, None, None, None
+
+
+def conv_bn_act(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = None,
+                relu: bool = True) -> torch.Tensor:
+    """``relu(bn(conv(x)) [+ residual])``. With B200MPI_FUSED_CONV1X1=1 an eligible 1x1 stride-1 convolution runs on the
+    tcgen05 GEMM whose epilogue already produces the BatchNorm statistics; everything else is ``bn_act(bn, conv(x), ...)``."""
+    if (_CONV1X1 and _conv1x1_eligible(conv, bn, x)
+            and (residual is None or (residual.dtype == torch.bfloat16 and residual.shape[0] == x.shape[0]
+                                      and residual.shape[1] == conv.out_channels and residual.shape[2:] == x.shape[2:]))):
+        if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        if bn.num_batches_tracked is not None:
+            bn.num_batches_tracked.add_(1)
+        w2d = conv.weight.to(torch.bfloat16).reshape(conv.out_channels, conv.in_channels)
+        return _Conv1x1BNAct.apply(x, residual, w2d, bn.weight, bn.bias, bn.running_mean, bn.running_var, _ws(bn, x.device), bn.eps,
+                                   bn.momentum, relu, getattr(bn, "_b200_grad_ready", None))
+    return bn_act(bn, conv(x), residual=residual, relu=relu)

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.b200mpi_bn_workspace_floats.restype = sz
     L.b200mpi_bn_supported.argtypes = [C.c_longlong, i]
     L.b200mpi_bn_act_fwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_longlong, i, f, f, i, vp]
+    if hasattr(L, "b200mpi_bn_act_fwd_prestats"):
+        L.b200mpi_bn_act_fwd_prestats.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i, C.c_longlong, i, f, f, i, vp]
     L.b200mpi_bn_act_bwd.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_longlong, i, i, vp]
     L.b200mpi_set_tuning.argtypes = [vp, sz, sz, i, i]
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
