@@ -1,0 +1,20 @@
+#!/bin/bash
+# First 1-GPU call of the next round: validate everything that was written after the GPU budget ran out.
+# Usage: gpurun --timeout 900 -- 'tools/gpu_session_r2_1gpu.sh'
+export B200MPI_NO_AUTOBUILD=1
+mkdir -p gpurun_out
+echo "=== 1. GPU tier as the driver runs it ==="
+timeout 600 python -m pytest tests -x -q -m gpu --timeout=300 2>&1 | tail -5
+echo "=== 2. bf16 parameter shadow: numerics (xfail marker removed by --runxfail) + bench ==="
+timeout 200 python -m pytest tests/test_trainer_gpu.py -q --runxfail -k bf16_params --timeout=150 2>&1 | tail -5
+timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_default.json
+B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_bf16params.json
+echo "=== 3. tcgen05 GEMM + BN statistics (each case in its own process, bounded waits) ==="
+B200MPI_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_gemm_bnstats_gpu.py -q --timeout=200 2>&1 | tail -15
+echo "=== 4. bench with the tensor-core 1x1 path (only meaningful if step 3 passed) ==="
+B200MPI_FUSED_CONV1X1=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1.json
+B200MPI_FUSED_CONV1X1=1 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1_bf16params.json
+echo "=== 5. launch list of the best configuration ==="
+B200MPI_BF16_PARAMS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 5000 -c 2400 --csv --log-file gpurun_out/launches_bf16params.csv \
+  python bench.py --steps 3 --warmup 3 --no-graph > gpurun_out/ncu_bench.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_bf16params.csv 2>/dev/null | head -30
