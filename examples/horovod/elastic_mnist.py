@@ -28,12 +28,13 @@ def main():
     a = ap.parse_args()
     hvd.init()
     torch.manual_seed(1)
-    model = MnistConvNet().cuda()
+    dev = torch.device("cuda") if torch.cuda.is_available() and os.environ.get("B200MPI_HVD_DEVICE") != "cpu" else torch.device("cpu")
+    model = MnistConvNet().to(dev)
     base_opt = torch.optim.SGD(model.parameters(), lr=0.01 * hvd.size(), momentum=0.9)
     opt = hvd.DistributedOptimizer(base_opt, named_parameters=model.named_parameters(), op=hvd.Average)
     state = hvd.elastic.TorchState(model=model, optimizer=base_opt, checkpoint_path=a.checkpoint, step=0, worlds=[])
     g = torch.Generator().manual_seed(7)
-    protos = torch.randn(10, 784, generator=g).cuda()
+    protos = torch.randn(10, 784, generator=g).to(dev)
 
     @hvd.elastic.run
     def train(state):
@@ -42,8 +43,8 @@ def main():
         if hvd.rank() == 0:
             print(f"[elastic] (re)started at step {state.step} with world size {hvd.size()}; worlds so far {state.worlds}", flush=True)
         while state.step < a.total_steps:
-            y = torch.randint(0, 10, (64,), device="cuda")
-            x = protos[y] + 0.5 * torch.randn(64, 784, device="cuda")
+            y = torch.randint(0, 10, (64,), device=dev)
+            x = protos[y] + 0.5 * torch.randn(64, 784, device=dev)
             opt.zero_grad()
             loss = F.cross_entropy(model(x), y)
             loss.backward()

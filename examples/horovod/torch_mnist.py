@@ -25,9 +25,13 @@ def main():
     ap.add_argument("--checkpoint-dir", default="")
     a = ap.parse_args()
     hvd.init()
-    torch.cuda.set_device(hvd.local_rank() % torch.cuda.device_count())
+    if torch.cuda.is_available() and os.environ.get("B200MPI_HVD_DEVICE") != "cpu":   # GPU pinned by local rank (tensorflow_mnist.py:155); the reference's YAML is a CPU job
+        torch.cuda.set_device(hvd.local_rank() % torch.cuda.device_count())
+        dev = torch.device("cuda")
+    else:
+        dev = torch.device("cpu")   # collectives then run over the libmpi shim (hvd/host_backend.py)
     torch.manual_seed(42 + hvd.rank())
-    model = MnistConvNet().cuda()
+    model = MnistConvNet().to(dev)
     # tensorflow_mnist.py:123-130: LR x size for Average; Adasum needs no scaling beyond the local size
     lr_scaler = hvd.size() if not a.use_adasum else (hvd.local_size() if hvd.nccl_built() else 1)
     opt = torch.optim.Adam(model.parameters(), lr=0.001 * lr_scaler)
@@ -36,10 +40,10 @@ def main():
     steps = max(1, a.steps // hvd.size())  # tensorflow_mnist.py:146
     # a fixed synthetic "dataset": class = brightest quadrant pattern, learnable
     g = torch.Generator().manual_seed(7)
-    protos = torch.randn(10, 784, generator=g).cuda()
+    protos = torch.randn(10, 784, generator=g).to(dev)
     for i in range(steps):
-        y = torch.randint(0, 10, (a.batch_size,), device="cuda")
-        x = protos[y] + 0.5 * torch.randn(a.batch_size, 784, device="cuda")
+        y = torch.randint(0, 10, (a.batch_size,), device=dev)
+        x = protos[y] + 0.5 * torch.randn(a.batch_size, 784, device=dev)
         opt.zero_grad()
         loss = F.cross_entropy(model(x), y)
         loss.backward()

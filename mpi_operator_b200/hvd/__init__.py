@@ -48,8 +48,11 @@ def init(comm=None) -> None:
     if comm is not None:
         _state["comm"] = comm
         return
-    if not torch.cuda.is_available():
-        raise RuntimeError("mpi_operator_b200.hvd needs a CUDA device (the CPU path is the libmpi shim)")
+    if not torch.cuda.is_available() or os.environ.get("B200MPI_HVD_DEVICE", "") == "cpu":
+        # CPU job (the reference's Horovod MNIST example runs on CPU workers): collectives over the libmpi shim
+        from .host_backend import HostCommunicator
+        _state["comm"] = HostCommunicator()
+        return
     dev = info.local_rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     _state["comm"] = Communicator.create(info.rank, info.world_size, dev, info.job_id)
@@ -78,7 +81,9 @@ def mpi_enabled() -> bool: return True  # noqa: E704
 def gloo_built() -> bool: return False  # noqa: E704
 def gloo_enabled() -> bool: return False  # noqa: E704
 def nccl_built() -> int: return 1  # noqa: E704  (tensorflow_mnist.py:127 checks this before Adasum)
-def cuda_built() -> bool: return True  # noqa: E704
+def cuda_built() -> bool:
+    import torch
+    return torch.cuda.is_available()
 def rocm_built() -> bool: return False  # noqa: E704
 def ddl_built() -> bool: return False  # noqa: E704
 def ccl_built() -> bool: return False  # noqa: E704
@@ -166,10 +171,19 @@ def reducescatter(tensor, op=None, name=None):
     return out
 
 
+def _on_gpu() -> bool:
+    return _comm().device != "cpu"
+
+
+def _dev():
+    return "cuda" if _on_gpu() else "cpu"
+
+
 def barrier():
     import torch
     _comm().barrier()
-    torch.cuda.synchronize()
+    if _on_gpu():
+        torch.cuda.synchronize()
 
 
 def join(device=-1) -> int:
@@ -179,7 +193,8 @@ def join(device=-1) -> int:
 
 def synchronize(handle=None):
     import torch
-    torch.cuda.current_stream().synchronize()
+    if _on_gpu():
+        torch.cuda.current_stream().synchronize()
     return handle
 
 
@@ -203,7 +218,7 @@ def broadcast_parameters(params, root_rank: int = 0) -> None:
     else:
         items = list(params)
     for _, p in items:
-        if isinstance(p, torch.Tensor) and p.is_cuda:
+        if isinstance(p, torch.Tensor) and (p.is_cuda or not _on_gpu()):
             t = p.data if p.is_contiguous() else p.data.contiguous()
             if t.numel():
                 _comm().broadcast(t, root=root_rank)
@@ -215,12 +230,12 @@ def broadcast_object(obj, root_rank: int = 0, name=None):
     import pickle
     import torch
     payload = pickle.dumps(obj) if rank() == root_rank else b""
-    n = torch.tensor([len(payload)], dtype=torch.float32, device="cuda")
+    n = torch.tensor([len(payload)], dtype=torch.float32, device=_dev())
     _comm().broadcast(n, root=root_rank)
     ln = int(n.item())
-    buf = torch.zeros(ln + (-ln) % 2, dtype=torch.uint8, device="cuda")
+    buf = torch.zeros(ln + (-ln) % 2, dtype=torch.uint8, device=_dev())
     if rank() == root_rank:
-        buf[:ln] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).cuda()
+        buf[:ln] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(_dev())
     _comm().broadcast(buf, root=root_rank)
     return pickle.loads(bytes(buf[:ln].cpu().numpy()))
 

@@ -84,7 +84,7 @@ class TorchState(State):
     def restore(self):
         super().restore()
         if self._model_sd is None and self.checkpoint_path and os.path.exists(self.checkpoint_path):
-            ck = torch.load(self.checkpoint_path, map_location="cuda", weights_only=False)
+            ck = torch.load(self.checkpoint_path, map_location="cuda" if torch.cuda.is_available() else "cpu", weights_only=False)
             self._model_sd, self._opt_sd, self._saved = ck["model"], ck["optimizer"], ck.get("extra", {})
             super().restore()
         if self.model is not None and self._model_sd is not None:

@@ -52,7 +52,8 @@ class _DistributedOptimizer:
         for p in params:
             _, start = self._slot[p]
             p.grad = self._flat[start:start + p.numel()].as_strided(p.size(), p.stride())
-        self._stream = torch.cuda.Stream(priority=-1)
+        self._gpu = self._comm.device != "cpu"   # CPU jobs (libmpi shim backend): same buckets, synchronous collectives
+        self._stream = torch.cuda.Stream(priority=-1) if self._gpu else None
         for b in self._buckets:
             b["pending"] = len(b["params"])
             for p in b["params"]:
@@ -68,11 +69,13 @@ class _DistributedOptimizer:
         return fn
 
     def _fire(self, b):
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream())
-        self._stream.wait_event(ev)
+        import contextlib
         scale = 1.0 / self._passes if self._passes > 1 else None
-        with torch.cuda.stream(self._stream):
+        if self._gpu:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._stream.wait_event(ev)
+        with (torch.cuda.stream(self._stream) if self._gpu else contextlib.nullcontext()):
             if self._op == "adasum":
                 from .adasum import adasum_allreduce_
                 adasum_allreduce_(self._comm, self._flat[b["start"]:b["start"] + b["numel"]], stream=self._stream)
@@ -85,7 +88,8 @@ class _DistributedOptimizer:
         for b in self._buckets:
             if b["pending"] != -1:
                 self._fire(b)
-        torch.cuda.current_stream().wait_stream(self._stream)
+        if self._gpu:
+            torch.cuda.current_stream().wait_stream(self._stream)
 
     def step(self, closure=None):
         from ..utils import fault

@@ -1,0 +1,83 @@
+"""Rank script (run under the native mpirun): the horovod.torch API surface on the CPU backend."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn as nn
+
+import horovod.torch as hvd
+
+hvd.init()
+r, n = hvd.rank(), hvd.size()
+assert hvd.is_initialized() and hvd.local_rank() == r and hvd.local_size() == n and not hvd.cuda_built()
+
+# allreduce flavours
+t = torch.arange(10, dtype=torch.float32) + r
+assert torch.equal(hvd.allreduce(t, op=hvd.Sum), n * torch.arange(10.) + n * (n - 1) / 2)
+assert torch.allclose(hvd.allreduce(t), torch.arange(10.) + (n - 1) / 2)                 # Average is the default
+assert torch.equal(hvd.allreduce(t, op=hvd.Max), torch.arange(10.) + n - 1)
+assert torch.equal(hvd.allreduce(t, op=hvd.Min), torch.arange(10.))
+h = (torch.ones(7, dtype=torch.bfloat16) * (r + 1))
+assert torch.equal(hvd.allreduce(h, op=hvd.Sum), torch.full((7,), n * (n + 1) / 2, dtype=torch.bfloat16))
+i64 = torch.tensor([r, 2 * r], dtype=torch.int64)
+assert torch.equal(hvd.allreduce(i64, op=hvd.Sum), torch.tensor([n * (n - 1) // 2, n * (n - 1)]))
+assert torch.allclose(hvd.allreduce(t, op=hvd.Sum, prescale_factor=0.5), 0.5 * (n * torch.arange(10.) + n * (n - 1) / 2))
+inplace = t.clone()
+hvd.allreduce_(inplace, op=hvd.Sum)
+assert torch.equal(inplace, n * torch.arange(10.) + n * (n - 1) / 2)
+
+# allgather / broadcast / alltoall / reducescatter
+g = hvd.allgather(torch.full((2, 3), float(r)))
+assert g.shape == (2 * n, 3) and all(torch.equal(g[2 * k:2 * k + 2], torch.full((2, 3), float(k))) for k in range(n))
+b = hvd.broadcast(torch.full((5,), float(r)), root_rank=n - 1)
+assert torch.equal(b, torch.full((5,), float(n - 1)))
+a2a = hvd.alltoall(torch.arange(n, dtype=torch.float32) + 100 * r)
+assert torch.equal(a2a, torch.tensor([100. * k + r for k in range(n)]))
+rs = hvd.reducescatter(torch.arange(2 * n, dtype=torch.float32) * (r + 1), op=hvd.Sum)
+assert torch.equal(rs, torch.arange(2 * n, dtype=torch.float32).view(n, 2)[r] * (n * (n + 1) / 2))
+assert hvd.broadcast_object({"epoch": 3, "who": r} if r == 0 else None, root_rank=0) == {"epoch": 3, "who": 0}
+hvd.barrier()
+
+# DistributedOptimizer == SGD on the rank-averaged gradient, identical parameters on every rank afterwards
+torch.manual_seed(0)
+ref = nn.Sequential(nn.Linear(6, 8), nn.Tanh(), nn.Linear(8, 3))
+model = nn.Sequential(nn.Linear(6, 8), nn.Tanh(), nn.Linear(8, 3))
+torch.manual_seed(100 + r)
+for p in model.parameters():
+    p.data.normal_()                                # ranks start different...
+hvd.broadcast_parameters(model.state_dict(), root_rank=0)   # ...and agree after the broadcast (K3)
+w0 = hvd.allgather(model[0].weight.data.flatten()[None])
+assert all(torch.equal(w0[0], w0[k]) for k in range(n))
+ref.load_state_dict(model.state_dict())
+opt = hvd.DistributedOptimizer(torch.optim.SGD(model.parameters(), lr=0.1, momentum=0.9), named_parameters=model.named_parameters(),
+                               bucket_bytes=128)
+ropt = torch.optim.SGD(ref.parameters(), lr=0.1, momentum=0.9)
+for step in range(3):
+    xs = [torch.randn(4, 6, generator=torch.Generator().manual_seed(1000 * step + k)) for k in range(n)]
+    opt.zero_grad()
+    model(xs[r]).pow(2).mean().backward()
+    opt.step()
+    ropt.zero_grad()
+    (sum(ref(x).pow(2).mean() for x in xs) / n).backward()      # the gradient every rank should have applied
+    ropt.step()
+for p, q in zip(model.parameters(), ref.parameters()):
+    assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (p - q).abs().max()
+
+# Adasum: orthogonal gradients add, parallel gradients average
+e = torch.zeros(n)
+e[r] = 1.0
+assert torch.allclose(hvd.allreduce(e, op=hvd.Adasum), torch.ones(n))
+assert torch.allclose(hvd.allreduce(torch.ones(4), op=hvd.Adasum), torch.ones(4))
+
+# elastic state: commit / restore / sync
+state = hvd.elastic.TorchState(model=model, optimizer=None, epoch=r, batch=7)
+state.sync()
+assert state.epoch == 0
+state.epoch = 5
+state.commit()
+state.epoch = 9
+state.restore()
+assert state.epoch == 5
+print(f"rank {r}/{n} hvd cpu ok", flush=True)
+hvd.shutdown()

@@ -79,3 +79,27 @@ def test_trace_export_and_roofline_report(tmp_path):
     assert trace.summarize(trace.load_jsonl(str(p)))["allreduce[oneshot]"] == {"calls": 2, "bytes": 2048}
     md = roofline.report("/root/repo/profiles/allreduce_sweep_n8_f32.json")
     assert "| float32 | 1073741824 | nvls" in md and "x |" in md
+
+
+def _repo():
+    import os as _os
+    return _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("np_", [1, 3])
+def test_horovod_api_on_the_cpu_backend_under_mpirun(np_):
+    """The reference's Horovod example is a CPU job (examples/v2beta1/horovod/tensorflow-mnist.yaml: cpu-only workers).
+    Without CUDA, hvd.init() builds the libmpi-shim communicator (hvd/host_backend.py); tests/hvd_cpu_worker.py checks
+    every collective, DistributedOptimizer against SGD on the averaged gradient, Adasum and the elastic State."""
+    import os
+    import subprocess
+    import sys
+    repo = _repo()
+    mpirun = os.path.join(repo, "mpi_operator_b200/bin/mpirun")
+    if not os.path.exists(mpirun):
+        pytest.skip("native launcher not built (run make)")
+    env = dict(os.environ, B200MPI_HVD_DEVICE="cpu")
+    r = subprocess.run([mpirun, "-np", str(np_), sys.executable, os.path.join(repo, "tests/hvd_cpu_worker.py")],
+                       capture_output=True, text=True, timeout=180, env=env, cwd="/tmp")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("hvd cpu ok") == np_

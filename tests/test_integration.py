@@ -122,6 +122,57 @@ def test_pi_job_with_custom_cluster_domain(tmp_path):
 
 
 @needs_native
+def test_elastic_horovod_rescales_2_4_2_and_resumes_from_committed_steps(op, tmp_path):
+    """SURVEY.md §3.4 / proposals/elastic-horovod.md end to end with real rank processes (CPU backend): `scale` changes
+    Worker.replicas, the controller regenerates discover_hosts.sh, the ranks notice at their next commit and leave with
+    the rescale code, the launcher restarts mpirun on the new world, state resumes from rank 0's checkpoint.
+    (GPU version: test_elastic_gpu.py.)"""
+    ckpt = str(tmp_path / "ckpt.pt")
+    job = new_mpijob("elastic", workers=2, launcher_cmd=("mpirun",), worker_cmd=("/usr/sbin/sshd", "-De"),
+                     launcher_args=("python", os.path.join(REPO, "examples/horovod/elastic_mnist.py"), "--total-steps", "120",
+                                    "--commit-every", "4", "--step-sleep", "0.02", "--checkpoint", ckpt))
+    job.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [{"name": "B200MPI_HVD_DEVICE", "value": "cpu"}]
+    c = op.clientset.kubeflow_v2beta1().mpijobs("default")
+    c.create(job)
+
+    def logs():
+        return "".join(op.agent.logs("default", p["metadata"]["name"]) for p in op.store.list("pods", "default")
+                       if "launcher" in p["metadata"]["name"])
+
+    def scale(n):
+        j = c.get("elastic")
+        j.spec.replica("Worker").replicas = n
+        c.update(j)
+
+    wait_for(lambda: "world size 2" in logs(), timeout=60, what="first incarnation")
+    scale(4)
+    wait_for(lambda: "world size 4" in logs(), timeout=90, what="scaled-up incarnation")
+    scale(2)
+    wait_for(lambda: logs().count("with world size 2") >= 2, timeout=90, what="scaled-down incarnation")
+    wait_for(lambda: conds(c.get("elastic")).get("Succeeded") == "True", timeout=180, what="job success")
+    text = logs()
+    assert "world sizes seen: [2, 4, 2]" in text, text[-3000:]
+    restarts = [ln for ln in text.splitlines() if "(re)started at step" in ln]
+    assert len(restarts) == 3 and all(int(ln.split("step ")[1].split()[0]) > 0 for ln in restarts[1:]), restarts
+
+
+@needs_native
+def test_horovod_mnist_example_runs_as_a_cpu_job(op):
+    """F3: examples/horovod/tensorflow-mnist.yaml — `mpirun -np 2 ... python /examples/tensorflow_mnist.py`,
+    the image path remapped to the torch script; on a host without CUDA the hvd collectives run over the libmpi shim."""
+    job = yaml_io.load_file(os.path.join(REPO, "examples/horovod/tensorflow-mnist.yaml"))[0]
+    job.metadata["namespace"] = "default"
+    c0 = job.spec.replica("Launcher").template["spec"]["containers"][0]
+    c0["args"] = list(c0["args"]) + ["--steps", "20", "--batch-size", "32"]      # keep the CPU test short
+    c0["env"] = list(c0.get("env", [])) + [{"name": "B200MPI_HVD_DEVICE", "value": "cpu"}]
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", timeout=120, what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    log = op.agent.logs("default", launcher["metadata"]["name"])
+    assert "step 0 loss" in log and "final loss (averaged over 2 ranks)" in log
+
+
+@needs_native
 def test_malformed_command_backoff_limit_failed(op):
     job = new_mpijob("bad", workers=1, launcher_cmd=("mpirun",), launcher_args=("-n", "1", "sh", "-c", "echo boom >&2; exit 7"),
                      worker_cmd=("/usr/sbin/sshd", "-De"), backoff_limit=1)
