@@ -84,6 +84,12 @@ define san_build
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/pi examples/pi/pi.cc $(SAN_SRCS) -lrt -lpthread
 endef
 
+# launch planning / counters of the runtime, checked on the host (no GPU): includes comm.cc, kernels come from the .so
+test_comm_host: $(LIBDIR)/libb200mpi.so
+	@mkdir -p build/san
+	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -x cu csrc/tests/comm_host_test.cu -o build/san/comm_host_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
+	build/san/comm_host_test
+
 asan:
 	$(call san_build,asan,-fsanitize=address$(comma)undefined -fno-sanitize-recover=undefined)
 	ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 build/san/asan/mpirun -n 4 build/san/asan/mpi_stress 200
@@ -94,4 +100,4 @@ tsan:
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host

@@ -1,0 +1,66 @@
+// Host-only checks of the runtime's launch planning (no GPU needed: nothing here calls into CUDA). The translation unit
+// includes comm.cc so that its file-static helpers are visible; kernel launchers resolve from libb200mpi.so.
+// Built and run by `make test_comm_host` and tests/test_native_cpu.py.
+#include "../runtime/comm.cc"
+
+#include <cstdio>
+#include <cstring>
+
+static int g_failed = 0;
+#define EXPECT(cond)                                                        \
+  do {                                                                      \
+    if (!(cond)) { printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); g_failed++; } \
+  } while (0)
+
+int main() {
+  b200mpi_comm* c = new b200mpi_comm;
+  c->rank = 3;
+  c->world = 8;
+  c->multicast = true;
+  c->oneshot_max = 64 << 10;
+  c->nvls_min = 0;
+
+  // ---- algorithm selection: measured crossovers (tuning.json) are thresholds on the message size
+  EXPECT(select_algo(c, 1024, B200MPI_F32, B200MPI_SUM, true) == B200MPI_ALGO_ONESHOT);
+  EXPECT(select_algo(c, 64 << 10, B200MPI_F32, B200MPI_SUM, true) == B200MPI_ALGO_ONESHOT);
+  EXPECT(select_algo(c, (64 << 10) + 16, B200MPI_F32, B200MPI_SUM, true) == B200MPI_ALGO_NVLS);
+  EXPECT(select_algo(c, 1 << 30, B200MPI_BF16, B200MPI_SUM, false) == B200MPI_ALGO_NVLS);
+  EXPECT(select_algo(c, 1 << 20, B200MPI_F32, B200MPI_MAX, true) == B200MPI_ALGO_TWOSHOT);   // no f32 min/max in the switch
+  EXPECT(select_algo(c, 1 << 20, B200MPI_BF16, B200MPI_MAX, true) == B200MPI_ALGO_NVLS);
+  c->multicast = false;
+  EXPECT(select_algo(c, 1 << 20, B200MPI_F32, B200MPI_SUM, true) == B200MPI_ALGO_TWOSHOT);
+  c->multicast = true;
+  c->nvls_min = (size_t)-1;   // world <= 2 default: NVLS never wins
+  EXPECT(select_algo(c, 1 << 30, B200MPI_F32, B200MPI_SUM, true) == B200MPI_ALGO_TWOSHOT);
+
+  // ---- grid sizing: ceil(vectors / (threads x vectors-per-thread)) clamped to [1, cap]
+  EXPECT(blocks_for(c, 0, 1, 32) == 1);
+  EXPECT(blocks_for(c, 1, 4, 16) == 1);
+  EXPECT(blocks_for(c, (size_t)kThreads * 4, 4, 16) == 1);
+  EXPECT(blocks_for(c, (size_t)kThreads * 4 + 1, 4, 16) == 2);
+  EXPECT(blocks_for(c, (size_t)1 << 30, 2, 64) == 64);
+  EXPECT(emu_max_blocks(c) == 132 / 8);
+  EXPECT(esize(B200MPI_F32) == 4 && esize(B200MPI_BF16) == 2 && esize(B200MPI_F16) == 2);
+
+  // ---- per-(op, algorithm) counters -> JSON
+  EXPECT(b200mpi_comm_stats_json(c, nullptr, 0) > 0);
+  c->stats.push_back(OpStat{"allreduce", B200MPI_ALGO_NVLS, 2, 4096});
+  c->stats.push_back(OpStat{"allreduce_sgd", B200MPI_ALGO_TWOSHOT, 9, 123456789012ull});
+  c->launches = 11;
+  const int n = b200mpi_comm_stats_json(c, nullptr, 0);
+  char* buf = new char[n + 1];
+  EXPECT(b200mpi_comm_stats_json(c, buf, n + 1) == n && (int)strlen(buf) == n);
+  EXPECT(strstr(buf, "\"rank\": 3") && strstr(buf, "\"launches\": 11"));
+  EXPECT(strstr(buf, "{\"op\": \"allreduce\", \"algo\": \"nvls\", \"calls\": 2, \"bytes\": 4096}"));
+  EXPECT(strstr(buf, "{\"op\": \"allreduce_sgd\", \"algo\": \"twoshot\", \"calls\": 9, \"bytes\": 123456789012}"));
+  char tiny[10];
+  EXPECT(b200mpi_comm_stats_json(c, tiny, sizeof(tiny)) == n && strlen(tiny) == sizeof(tiny) - 1);   // truncates, NUL-terminated
+
+  // ---- argument validation happens before anything touches the device
+  EXPECT(b200mpi_slice_elems(1000, 8, B200MPI_F32) > 0);
+  EXPECT(b200mpi_bn_supported(12544, 256) == 1 && b200mpi_bn_supported(12544, 12) == 0 && b200mpi_bn_supported(0, 64) == 0);
+  EXPECT(b200mpi_bn_workspace_floats(64) == (size_t)4 * 64 + (size_t)296 * 2 * 64 + 4);
+
+  printf(g_failed ? "comm_host_test: %d check(s) FAILED\n" : "comm_host_test: all checks passed\n", g_failed);
+  return g_failed ? 1 : 0;
+}

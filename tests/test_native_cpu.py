@@ -161,3 +161,12 @@ def test_tcgen05_gemm_library_builds_loads_and_validates_shapes():
     if sass.returncode == 0:  # the tensor-core / TMA / TMEM instructions are really there
         for mnemonic in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR"):
             assert mnemonic in sass.stdout, mnemonic
+
+
+def test_runtime_launch_planning_on_the_host():
+    """`make test_comm_host`: algorithm selection thresholds, grid sizing, per-(op, algo) counters -> JSON and argument
+    validation of libb200mpi — the parts of csrc/runtime/comm.cc that decide what gets launched, without a GPU."""
+    if not os.path.exists(os.path.join(REPO, "mpi_operator_b200/lib/libb200mpi.so")):
+        pytest.skip("native libraries not built (run make)")
+    r = subprocess.run(["make", "test_comm_host"], cwd=REPO, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "comm_host_test: all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
