@@ -199,11 +199,19 @@ ncclResult_t init_common(ncclComm_t* out, int nranks, const ncclUniqueId* id, in
   auto* s = new Shim;
   s->rank = rank; s->world = nranks; s->device = dev; s->id = id_to_job(id);
   if (!forward_all() && nranks <= B200MPI_MAX_RANKS) {
+    // torch ranks reach their first collective at very different times (model build, cuDNN init, page-cache misses on a
+    // fresh box): give the rendezvous longer than the collective watchdog unless the user set a timeout
+    if (!getenv("B200MPI_TIMEOUT_MS")) setenv("B200MPI_INIT_TIMEOUT_MS", "180000", 0);
     int rc = b200mpi_comm_init(&s->mine, rank, nranks, dev, s->id.c_str(), 0, 0);
     if (rc != 0) {
-      // every rank fails the same way (capability consensus) -> fall back together
-      if (debug()) fprintf(stderr, "[b200mpi nccl shim] b200mpi init failed (%s); forwarding to NCCL\n", b200mpi_last_error());
-      s->mine = nullptr;
+      // The unique id was minted by this shim (ncclGetUniqueId below), real NCCL cannot bootstrap from it, and a rank that
+      // fell back alone would deadlock its peers: fail loudly, on every rank that sees the failure.
+      fprintf(stderr, "[b200mpi nccl shim] rank %d/%d: communicator %s could not be created on the b200mpi runtime: %s\n"
+                      "[b200mpi nccl shim] set B200MPI_ALGO=nccl to run this job on stock NCCL, B200MPI_DEBUG=1 for details\n",
+              rank, nranks, s->id.c_str(), b200mpi_last_error());
+      std::string why = std::string("b200mpi communicator init failed: ") + b200mpi_last_error();
+      delete s;
+      return err(ncclSystemError, why.c_str());
     }
   }
   if (!s->mine) {
@@ -471,6 +479,41 @@ ncclResult_t ncclAlltoAll(const void* send, void* recv, size_t count, ncclDataTy
   const size_t bytes = count * dt_size(dt);
   if (bytes % 2) return err(ncclInvalidArgument, "alltoall payload must be an even number of bytes");
   return from_rc(b200mpi_alltoall(s->mine, send, recv, bytes / 2, B200MPI_BF16, st), "ncclAlltoAll");
+}
+
+// NCCL 2.28 rooted collectives. Built from the staged all-gather / broadcast kernels: every rank moves the full payload, which
+// is fine for the metadata-sized tensors frameworks use them for.
+ncclResult_t ncclGather(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclGather, const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f ? f(send, recv, count, dt, root, s->real, st) : err(ncclInvalidUsage, "ncclGather missing in real NCCL"); }
+  const size_t bytes = count * dt_size(dt);
+  if (bytes % 2) return err(ncclInvalidArgument, "gather payload must be an even number of bytes");
+  if (s->rank == root) return from_rc(b200mpi_allgather(s->mine, send, recv, bytes / 2, B200MPI_BF16, st), "ncclGather");
+  void* tmp = nullptr;
+  if (cudaMallocAsync(&tmp, bytes * s->world, st) != cudaSuccess) return err(ncclUnhandledCudaError, "cudaMallocAsync failed");
+  int rc = b200mpi_allgather(s->mine, send, tmp, bytes / 2, B200MPI_BF16, st);
+  cudaFreeAsync(tmp, st);
+  return from_rc(rc, "ncclGather");
+}
+ncclResult_t ncclScatter(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t c, cudaStream_t st) {
+  Shim* s = S(c);
+  g_calls++;
+  if (s->real) { auto f = REAL(ncclScatter, const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f ? f(send, recv, count, dt, root, s->real, st) : err(ncclInvalidUsage, "ncclScatter missing in real NCCL"); }
+  const size_t bytes = count * dt_size(dt);
+  if (bytes % 2) return err(ncclInvalidArgument, "scatter payload must be an even number of bytes");
+  void* tmp = nullptr;
+  if (cudaMallocAsync(&tmp, bytes * s->world, st) != cudaSuccess) return err(ncclUnhandledCudaError, "cudaMallocAsync failed");
+  if (s->rank == root) cudaMemcpyAsync(tmp, send, bytes * s->world, cudaMemcpyDeviceToDevice, st);
+  int rc = b200mpi_broadcast_bytes(s->mine, tmp, bytes * s->world, root, st);
+  if (!rc) cudaMemcpyAsync(recv, (const char*)tmp + (size_t)s->rank * bytes, bytes, cudaMemcpyDeviceToDevice, st);
+  cudaFreeAsync(tmp, st);
+  return from_rc(rc, "ncclScatter");
+}
+ncclResult_t ncclCommRevoke(ncclComm_t c, int flags) {
+  Shim* s = S(c);
+  if (s && s->real) { auto f = REAL(ncclCommRevoke, ncclComm_t, int); return f ? f(s->real, flags) : err(ncclInvalidUsage, "ncclCommRevoke missing in real NCCL"); }
+  return ncclSuccess;  // nothing in flight on the host side: kernels are stream-ordered and bounded by the device watchdog
 }
 
 ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t c, cudaStream_t st) {

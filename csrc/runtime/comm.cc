@@ -604,7 +604,8 @@ int b200mpi_comm_init(b200mpi_comm_t* out, int rank, int world, int device, cons
   auto* c = new b200mpi_comm;
   c->rank = rank; c->world = world; c->device = device; c->flags = flags;
   std::string err;
-  const int timeout = env_int("B200MPI_TIMEOUT_MS", 30000);
+  // rendezvous / setup timeout: B200MPI_INIT_TIMEOUT_MS, else the collective timeout, else 30 s
+  const int timeout = env_int("B200MPI_INIT_TIMEOUT_MS", env_int("B200MPI_TIMEOUT_MS", 30000));
   if (c->rv.attach(job_id ? job_id : "default", rank, world, device, timeout, &err)) { delete c; return fail(B200MPI_ERR_SYS, err); }
   // capability consensus: VMM fd export + multicast need every rank to agree
   Driver& d = driver();
