@@ -24,9 +24,11 @@ class Indexer:
         self._lock = threading.RLock()
         self._items: Dict[str, dict] = {}
 
+    # Cached objects are replaced wholesale, never mutated in place, so copies are taken outside the lock.
     def add(self, obj: dict) -> None:
+        mine = copy.deepcopy(obj)
         with self._lock:
-            self._items[M.key_of(obj)] = copy.deepcopy(obj)
+            self._items[M.key_of(obj)] = mine
 
     update = add
 
@@ -37,11 +39,21 @@ class Indexer:
     def get_by_key(self, key: str) -> Optional[dict]:
         with self._lock:
             o = self._items.get(key)
-            return copy.deepcopy(o) if o is not None else None
+        return copy.deepcopy(o) if o is not None else None
 
-    def list(self) -> List[dict]:
+    def list(self, namespace: str = "", selector: Optional[Dict[str, str]] = None) -> List[dict]:
+        """Sorted by key. Namespace and label selector are applied before anything is copied: a reconcile lists
+        "the pods of this job" several times and must not pay for every object in the cache."""
         with self._lock:
-            return [copy.deepcopy(o) for _, o in sorted(self._items.items())]
+            hits = []
+            for key in sorted(self._items):
+                o = self._items[key]
+                if namespace and M.namespace_of(o) != namespace:
+                    continue
+                if selector and not M.label_selector_matches(selector, M.meta(o).get("labels")):
+                    continue
+                hits.append(o)
+        return [copy.deepcopy(o) for o in hits]
 
 
 class SharedIndexInformer:
@@ -95,14 +107,7 @@ class NamespaceLister:
         return self._conv(o)
 
     def list(self, selector: Optional[Dict[str, str]] = None) -> list:
-        out = []
-        for o in self._ix.list():
-            if self._ns and M.namespace_of(o) != self._ns:
-                continue
-            if selector and not M.label_selector_matches(selector, M.meta(o).get("labels")):
-                continue
-            out.append(self._conv(o))
-        return out
+        return [self._conv(o) for o in self._ix.list(self._ns, selector)]
 
 
 class Lister:

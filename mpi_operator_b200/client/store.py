@@ -55,7 +55,11 @@ class ObjectStore:
         self._dispatch_lock = threading.RLock()
         self._save_lock = threading.Lock()
         self._saved_rv = -1
-        if persist_path and os.path.exists(persist_path):
+        # Persistence = snapshot file + append-only journal of mutations (O(1) work per write instead of re-serialising
+        # the whole store); the journal is folded into a fresh snapshot every kCompactEvery records and at load time.
+        self._journal: List[str] = []
+        self._journal_records = 0
+        if persist_path and (os.path.exists(persist_path) or os.path.exists(persist_path + ".wal")):
             self._load()
 
     # ------------------------------------------------------------ helpers --
@@ -74,6 +78,13 @@ class ObjectStore:
     def _emit(self, resource: str, etype: str, obj: dict, old: Optional[dict]) -> None:
         # Handlers run outside the mutation that produced the event and never re-entrantly.
         self._pending.append((resource, etype, copy.deepcopy(obj), copy.deepcopy(old) if old else None))
+        if self._persist_path:
+            namespaced = RESOURCES[resource][2]
+            key = self._key(M.namespace_of(obj) if namespaced else "", M.name_of(obj))
+            rec = {"rv": self._rv, "r": resource, "k": key}
+            if etype != DELETED:
+                rec["o"] = obj
+            self._journal.append(json.dumps(rec))
 
     def _flush(self) -> None:
         with self._dispatch_lock:  # ordered delivery; re-entrant for handlers that mutate the store
@@ -240,32 +251,82 @@ class ObjectStore:
         return cancel
 
     # --------------------------------------------------------- persistence --
+    kCompactEvery = 4000
+
     def _save(self) -> None:
+        """Append the pending journal records (or compact). One writer at a time; a thread that finds the writer busy
+        leaves its records to it — the writer re-checks after releasing, so nothing stays behind."""
         if not self._persist_path:
             return
-        with self._save_lock:
-            with self._lock:
-                if self._saved_rv == self._rv:
-                    return
-                snap = {"rv": self._rv, "objects": {r: list(o.values()) for r, o in self._objs.items() if o}}
-                self._saved_rv = self._rv
-            tmp = f"{self._persist_path}.tmp{os.getpid()}"
+        while True:
+            if not self._save_lock.acquire(blocking=False):
+                return
             try:
-                with open(tmp, "w") as f:
-                    json.dump(snap, f)
-                os.replace(tmp, self._persist_path)
-            except OSError:
-                pass  # state dir removed underneath us (shutdown): persistence is best effort
+                with self._lock:
+                    lines, self._journal = self._journal, []
+                    compact = self._journal_records + len(lines) >= self.kCompactEvery
+                    snap = None
+                    if compact:
+                        snap = {"rv": self._rv, "objects": {r: list(o.values()) for r, o in self._objs.items() if o}}
+                try:
+                    if compact:
+                        self._write_snapshot(snap)
+                    elif lines:
+                        with open(self._persist_path + ".wal", "a") as f:
+                            f.write("\n".join(lines) + "\n")
+                        self._journal_records += len(lines)
+                except OSError:
+                    pass  # state dir removed underneath us (shutdown): persistence is best effort
+            finally:
+                self._save_lock.release()
+            if not self._journal:
+                return
+
+    def _write_snapshot(self, snap: dict) -> None:
+        tmp = f"{self._persist_path}.tmp{os.getpid()}"
+        with open(tmp, "w") as f:
+            json.dump(snap, f)
+        os.replace(tmp, self._persist_path)
+        try:
+            os.unlink(self._persist_path + ".wal")   # records up to snap["rv"] are in the snapshot now
+        except OSError:
+            pass
+        self._journal_records = 0
 
     def _load(self) -> None:
-        with open(self._persist_path) as f:
-            snap = json.load(f)
+        snap = {"rv": 0, "objects": {}}
+        if os.path.exists(self._persist_path):
+            with open(self._persist_path) as f:
+                snap = json.load(f)
         self._rv = int(snap.get("rv", 0))
         for r, objs in snap.get("objects", {}).items():
             if r in self._objs:
                 for o in objs:
                     ns = M.namespace_of(o) if RESOURCES[r][2] else ""
                     self._objs[r][self._key(ns, M.name_of(o))] = o
+        base_rv, replayed = self._rv, 0
+        try:
+            with open(self._persist_path + ".wal") as f:
+                for line in f:
+                    try:
+                        rec = json.loads(line)
+                    except ValueError:
+                        break  # torn last record of a crashed writer
+                    if int(rec.get("rv", 0)) <= base_rv or rec.get("r") not in self._objs:
+                        continue  # already contained in the snapshot
+                    if "o" in rec:
+                        self._objs[rec["r"]][rec["k"]] = rec["o"]
+                    else:
+                        self._objs[rec["r"]].pop(rec["k"], None)
+                    self._rv = max(self._rv, int(rec["rv"]))
+                    replayed += 1
+        except OSError:
+            pass
+        if replayed:  # start the new process from a clean snapshot
+            try:
+                self._write_snapshot({"rv": self._rv, "objects": {r: list(o.values()) for r, o in self._objs.items() if o}})
+            except OSError:
+                pass
 
 
 def _merge_patch(target: Any, patch: Any) -> Any:

@@ -199,6 +199,7 @@ class NodeAgent:
                 self._cm_dirty = False
                 self.refresh_config_volumes()
             self._sync_jobs()
+            self._pods_by_owner = None   # snapshot is only valid inside _sync_jobs
             self._schedule()
             self._sync_pods()
             metrics.gpu_slots_free.set(self.alloc.free_gpus)
@@ -207,7 +208,16 @@ class NodeAgent:
     # ------------------------------------------------------- Job controller --
     def _sync_jobs(self) -> None:
         now = time.time()
-        for job in self.store.list("jobs"):
+        jobs = self.store.list("jobs")
+        # one pod snapshot per tick, indexed by controller uid: listing (and deep-copying) every pod once per Job made the
+        # loop quadratic (benchmarks/controller_bench.py: 50 jobs x 8 workers)
+        self._pods_by_owner = {}
+        if jobs:
+            for p in self.store.list("pods"):
+                for ref in M.meta(p).get("ownerReferences", []) or []:
+                    if ref.get("controller"):
+                        self._pods_by_owner.setdefault(ref.get("uid"), []).append(p)
+        for job in jobs:
             try:
                 self._sync_job(job, now)
             except errors.ApiError as e:
@@ -215,6 +225,9 @@ class NodeAgent:
                     raise
 
     def _job_pods(self, job: dict) -> List[dict]:
+        snap = getattr(self, "_pods_by_owner", None)
+        if snap is not None:
+            return [p for p in snap.get(M.meta(job).get("uid"), []) if M.is_controlled_by(p, job)]
         return [p for p in self.store.list("pods", M.namespace_of(job)) if M.is_controlled_by(p, job)]
 
     @staticmethod
@@ -578,7 +591,6 @@ class NodeAgent:
     def _start_pod(self, pod: dict) -> None:
         key = M.key_of(pod)
         pdir = self.pod_dir(pod)
-        os.makedirs(os.path.join(pdir, "logs"), exist_ok=True)
         pr = _Proc()
         pr.pod_dir = pdir
         pr.log_path = os.path.join(pdir, "logs", "0.log")
@@ -587,13 +599,14 @@ class NodeAgent:
         argv = list(c0.get("command") or []) + list(c0.get("args") or [])
         if not c0.get("command") and c0.get("args") and img.get("entrypoint") and os.path.basename(argv[0]) != "sshd":
             argv = list(img["entrypoint"]) + argv
-        mounts = self._materialize_volumes(pod, pdir)
         self._procs[key] = pr
         if argv and os.path.basename(argv[0]) == "sshd":
-            pr.virtual = True
+            pr.virtual = True   # idle worker placeholder: nothing runs in it, so nothing to mount either
             pr.started_at = M.now_rfc3339()
             self._set_running(pod, pr)
             return
+        os.makedirs(os.path.join(pdir, "logs"), exist_ok=True)
+        mounts = self._materialize_volumes(pod, pdir)
         if not argv:
             self._set_terminal(pod, pr, "Failed", 128, "ContainerCannotRun",
                                "container has no command/args and images are not used on a single box")
