@@ -23,10 +23,29 @@ def _ref(obj) -> dict:
 
 
 class EventRecorder:
-    def __init__(self, store: Optional[ObjectStore], component: str = "mpi-job-controller"):
+    def __init__(self, store: Optional[ObjectStore], component: str = "mpi-job-controller", ttl_seconds: float = 3600.0):
         self.store, self.component = store, component
         self._seq = 0
         self._recent = {}
+        self.ttl_seconds = ttl_seconds   # kube-apiserver --event-ttl default: 1 h
+        self._since_prune = 0
+
+    def prune(self, now: Optional[float] = None) -> int:
+        """Delete events whose lastTimestamp is older than the TTL (the apiserver does this for the reference; without it
+        a long-running daemon's store and journal grow with every job ever run). Returns the number removed."""
+        if self.store is None or self.ttl_seconds <= 0:
+            return 0
+        import time
+        cutoff = M.now_rfc3339((time.time() if now is None else now) - self.ttl_seconds)
+        n = 0
+        for ev in self.store.list("events"):
+            if (ev.get("lastTimestamp") or ev.get("firstTimestamp") or "") < cutoff:
+                try:
+                    self.store.delete("events", M.namespace_of(ev), M.name_of(ev))
+                    n += 1
+                except Exception:  # noqa: BLE001 - already gone
+                    pass
+        return n
 
     def event(self, obj, etype: str, reason: str, message: str) -> None:
         ref = _ref(obj)
@@ -53,6 +72,10 @@ class EventRecorder:
             "involvedObject": ref, "reason": reason, "message": message, "type": etype,
             "source": {"component": self.component}, "firstTimestamp": now, "lastTimestamp": now, "count": 1,
         }
+        self._since_prune += 1
+        if self._since_prune >= 256:
+            self._since_prune = 0
+            self.prune()
         try:
             self.store.create("events", ev)
             self._recent[agg_key] = (ev["metadata"]["namespace"], ev["metadata"]["name"])

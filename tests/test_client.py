@@ -240,3 +240,18 @@ def test_workqueue_single_worker_per_key_under_threads():
     q.shut_down()
     [t.join() for t in ts]
     assert overlap == [] and set(done) == {f"k{i}" for i in range(5)}
+
+
+def test_event_ttl_prunes_old_events():
+    from mpi_operator_b200.controller.events import EventRecorder
+    s = ObjectStore()
+    rec = EventRecorder(s, ttl_seconds=60)
+    job = {"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "j", "namespace": "default", "uid": "u"}}
+    rec.event(job, "Normal", "MPIJobCreated", "created")
+    rec.event(job, "Normal", "MPIJobRunning", "running")
+    assert len(s.list("events")) == 2
+    assert rec.prune() == 0
+    import time
+    assert rec.prune(now=time.time() + 3600) == 2 and s.list("events") == []
+    rec.event(job, "Normal", "MPIJobRunning", "running")      # the correlator's stale entry falls back to a fresh event
+    assert len(s.list("events")) == 1
