@@ -154,13 +154,32 @@ def broadcast_(tensor, root_rank, name=None):
 
 
 def alltoall(tensor, splits=None, name=None):
+    """Even alltoall in one kernel; with ``splits`` (rows of dim 0 sent to each rank, horovod semantics) the rows are
+    padded to the largest split so the same even kernel moves them, and ``(output, received_splits)`` is returned."""
     import torch
-    if splits is not None:
-        raise NotImplementedError("uneven alltoall splits")
     t = tensor.contiguous()
-    out = torch.empty_like(t)
-    _comm().alltoall(t, out)
-    return out
+    if splits is None:
+        out = torch.empty_like(t)
+        _comm().alltoall(t, out)
+        return out
+    n = size()
+    sp = [int(v) for v in (splits.tolist() if hasattr(splits, "tolist") else splits)]
+    if len(sp) != n or sum(sp) != t.shape[0] or min(sp) < 0:
+        raise ValueError("alltoall: splits must have one non-negative entry per rank and sum to tensor.shape[0]")
+    mine = torch.tensor(sp, dtype=torch.int32, device=t.device)
+    all_splits = allgather(mine.view(1, n)).view(n, n)            # all_splits[src][dst]
+    recv = [int(all_splits[src][rank()]) for src in range(n)]
+    width = max(1, int(all_splits.max()))
+    row = t.shape[1:]
+    send = torch.zeros((n, width) + tuple(row), dtype=t.dtype, device=t.device)
+    off = 0
+    for dst in range(n):
+        send[dst, :sp[dst]] = t[off:off + sp[dst]]
+        off += sp[dst]
+    got = torch.empty_like(send)
+    _comm().alltoall(send, got)
+    out = torch.cat([got[src, :recv[src]] for src in range(n)], dim=0) if sum(recv) else t.new_empty((0,) + tuple(row))
+    return out, torch.tensor(recv, dtype=torch.int32)
 
 
 def reducescatter(tensor, op=None, name=None):
@@ -238,6 +257,19 @@ def broadcast_object(obj, root_rank: int = 0, name=None):
         buf[:ln] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(_dev())
     _comm().broadcast(buf, root=root_rank)
     return pickle.loads(bytes(buf[:ln].cpu().numpy()))
+
+
+def allgather_object(obj, name=None) -> list:
+    """One picklable object per rank -> list indexed by rank."""
+    import pickle
+    import torch
+    payload = pickle.dumps(obj)
+    lens = allgather(torch.tensor([len(payload)], dtype=torch.int64, device=_dev()))
+    width = int(lens.max()) + (-int(lens.max())) % 2
+    buf = torch.zeros(1, width, dtype=torch.uint8, device=_dev())
+    buf[0, :len(payload)] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(_dev())
+    rows = allgather(buf).cpu()
+    return [pickle.loads(bytes(rows[r, :int(lens[r])].numpy())) for r in range(size())]
 
 
 def broadcast_optimizer_state(optimizer, root_rank: int = 0) -> None:

@@ -37,6 +37,12 @@ assert torch.equal(a2a, torch.tensor([100. * k + r for k in range(n)]))
 rs = hvd.reducescatter(torch.arange(2 * n, dtype=torch.float32) * (r + 1), op=hvd.Sum)
 assert torch.equal(rs, torch.arange(2 * n, dtype=torch.float32).view(n, 2)[r] * (n * (n + 1) / 2))
 assert hvd.broadcast_object({"epoch": 3, "who": r} if r == 0 else None, root_rank=0) == {"epoch": 3, "who": 0}
+# uneven alltoall: rank r sends (dst + 1) rows to dst, each row tagged with its source
+send = torch.cat([torch.full((d + 1, 2), float(r)) for d in range(n)])
+got, recv_splits = hvd.alltoall(send, splits=[d + 1 for d in range(n)])
+assert recv_splits.tolist() == [r + 1] * n and got.shape == (n * (r + 1), 2)
+assert torch.equal(got, torch.cat([torch.full((r + 1, 2), float(src)) for src in range(n)]))
+assert hvd.allgather_object({"rank": r, "blob": "x" * (r * 3)}) == [{"rank": k, "blob": "x" * (k * 3)} for k in range(n)]
 hvd.barrier()
 
 # DistributedOptimizer == SGD on the rank-averaged gradient, identical parameters on every rank afterwards
