@@ -210,6 +210,21 @@ int b200mpi_select_algo(b200mpi_comm_t comm, size_t bytes, b200mpi_dtype_t dtype
                         int symmetric);
 
 /* trace: per-collective records (op, bytes, algo, host enqueue ns) as JSONL */
+/* Point-to-point (EXPERIMENTAL; the mailbox window is only allocated when B200MPI_P2P=1 is set for every rank at
+ * communicator creation). A batch is executed by one kernel, one CTA per operation, so grouped exchanges cannot
+ * deadlock on stream order; sends of up to 2 MiB complete without the matching receive (eager). */
+typedef struct {
+  const void* send; /* source buffer (is_send) */
+  void* recv;       /* destination buffer (!is_send) */
+  size_t bytes;
+  int peer;
+  int is_send;
+} b200mpi_p2p_op_t;
+int b200mpi_p2p_batch(b200mpi_comm_t comm, const b200mpi_p2p_op_t* ops, int nops, void* stream);
+int b200mpi_send(b200mpi_comm_t comm, const void* buf, size_t bytes, int peer, void* stream);
+int b200mpi_recv(b200mpi_comm_t comm, void* buf, size_t bytes, int peer, void* stream);
+int b200mpi_comm_has_p2p(b200mpi_comm_t comm);
+
 int b200mpi_trace_enable(b200mpi_comm_t comm, int on);
 int b200mpi_trace_dump(b200mpi_comm_t comm, const char* path);
 

@@ -39,6 +39,35 @@ struct Launch {
   const KArgs* emu_args;  // device array of emu_world KArgs (emulated mode)
 };
 
+// ---- point-to-point (p2p.cu) -------------------------------------------------------------------------------------
+constexpr size_t kP2PChunk = (size_t)1 << 20;                  // mailbox slot size
+constexpr size_t kP2PDataBytes = (size_t)kMaxRanks * 2 * kP2PChunk;   // [src rank][2 slots]
+constexpr int kP2PFlagStride = 32;                             // u32 words between flags: one 128-byte line each
+constexpr size_t kP2PFlagBytes = (size_t)2 * kMaxRanks * 2 * kP2PFlagStride * sizeof(uint32_t);  // READY + ACK
+constexpr size_t kP2PWindowBytes = kP2PDataBytes + kP2PFlagBytes;
+constexpr int kMaxP2POps = 64;
+enum : int { P2P_READY = 0, P2P_ACK = 1 };
+// flag of slot 0 for stream (kind, r) inside the mailbox window whose base is `win`; slot 1 is kP2PFlagStride words on
+__host__ __device__ inline uint32_t* p2p_flag(char* win, int kind, int r) {
+  return reinterpret_cast<uint32_t*>(win + kP2PDataBytes) + ((size_t)kind * kMaxRanks + r) * 2 * kP2PFlagStride;
+}
+struct P2POp {
+  const char* user;   // send: source buffer; receive: destination buffer
+  size_t bytes;
+  int peer;
+  int is_send;
+  uint32_t seq_off;   // chunks of earlier operations of this batch on the same (direction, peer) stream
+};
+struct P2PArgs {
+  DevComm c;
+  Win box;            // mailbox window of every rank
+  uint32_t* cnt;      // device counters: [0,kMaxRanks) chunks sent to peer, [kMaxRanks, 2*kMaxRanks) chunks received from peer
+  int nops;
+  P2POp ops[kMaxP2POps];
+};
+struct P2PCommit { uint32_t n[2 * kMaxRanks]; };
+cudaError_t launch_p2p_batch(cudaStream_t s, const P2PArgs& a, const P2PCommit& add);
+
 enum : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 enum : int { MODE_P2P = 0, MODE_NVLS = 1 };
 

@@ -45,7 +45,9 @@ struct ncclConfig_v;  // opaque
 
 namespace {
 
+struct PendingP2P { b200mpi_p2p_op_t op; cudaStream_t stream; };
 struct Shim {
+  std::vector<PendingP2P> p2p;    // sends/receives queued inside ncclGroupStart/End (flushed as ONE kernel)
   b200mpi_comm_t mine = nullptr;  // b200mpi communicator (nullptr => forwarded)
   ncclComm_t real = nullptr;      // real NCCL communicator when forwarding
   int rank = 0, world = 1, device = 0;
@@ -60,6 +62,7 @@ std::atomic<uint64_t> g_calls{0}, g_forwarded{0};
 thread_local std::string g_last_error;
 thread_local int g_group_depth = 0;
 thread_local int g_group_fwd = 0;
+thread_local std::vector<Shim*> g_group_p2p;  // communicators with queued point-to-point operations
 
 bool forward_all() {
   static int v = -1;
@@ -383,6 +386,62 @@ ncclResult_t ncclRedOpDestroy(ncclRedOp_t op, ncclComm_t c) {
   return ncclSuccess;
 }
 
+// Point-to-point on a b200mpi communicator: everything queued on one communicator becomes one b200mpi_p2p_batch (one
+// kernel, one CTA per operation). Self-sends are matched with self-receives and done as device copies. Operations queued
+// on different streams are serialised onto the first one with events.
+static ncclResult_t flush_p2p(Shim* s) {
+  std::vector<PendingP2P> q;
+  q.swap(s->p2p);
+  if (q.empty()) return ncclSuccess;
+  cudaStream_t st = q[0].stream;
+  for (auto& p : q) {
+    if (p.stream != st) {
+      cudaEvent_t ev;
+      cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      cudaEventRecord(ev, p.stream);
+      cudaStreamWaitEvent(st, ev, 0);
+      cudaEventDestroy(ev);
+    }
+  }
+  std::vector<b200mpi_p2p_op_t> ops;
+  std::vector<const PendingP2P*> self_send, self_recv;
+  for (auto& p : q) {
+    if (p.op.peer == s->rank) (p.op.is_send ? self_send : self_recv).push_back(&p);
+    else ops.push_back(p.op);
+  }
+  if (self_send.size() != self_recv.size()) return err(ncclInvalidUsage, "unmatched send/recv to self inside a group");
+  for (size_t i = 0; i < self_send.size(); i++) {
+    if (self_send[i]->op.bytes != self_recv[i]->op.bytes) return err(ncclInvalidArgument, "self send/recv size mismatch");
+    if (self_send[i]->op.bytes) cudaMemcpyAsync(self_recv[i]->op.recv, self_send[i]->op.send, self_send[i]->op.bytes, cudaMemcpyDeviceToDevice, st);
+  }
+  ncclResult_t r = ncclSuccess;
+  if (!ops.empty()) r = from_rc(b200mpi_p2p_batch(s->mine, ops.data(), (int)ops.size(), st), "ncclSend/ncclRecv");
+  if (r == ncclSuccess) {
+    for (auto& p : q) {  // later work on the other streams must see the exchange
+      if (p.stream != st) {
+        cudaEvent_t ev;
+        cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+        cudaEventRecord(ev, st);
+        cudaStreamWaitEvent(p.stream, ev, 0);
+        cudaEventDestroy(ev);
+      }
+    }
+  }
+  return r;
+}
+static ncclResult_t queue_p2p(Shim* s, const b200mpi_p2p_op_t& op, cudaStream_t st) {
+  g_calls++;
+  if (!b200mpi_comm_has_p2p(s->mine))
+    return err(ncclInvalidUsage, "point-to-point on a b200mpi communicator is experimental: set B200MPI_P2P=1 for the job "
+                                 "(or B200MPI_ALGO=nccl to run this process group on stock NCCL)");
+  s->p2p.push_back(PendingP2P{op, st});
+  if (g_group_depth > 0) {
+    if (std::find(g_group_p2p.begin(), g_group_p2p.end(), s) == g_group_p2p.end()) g_group_p2p.push_back(s);
+    return ncclSuccess;
+  }
+  return flush_p2p(s);
+}
+
 ncclResult_t ncclGroupStart(void) {
   g_group_depth++;
   // Forward only when a real communicator exists (or everything is forwarded); remember it so the
@@ -394,6 +453,14 @@ ncclResult_t ncclGroupStart(void) {
 }
 ncclResult_t ncclGroupEnd(void) {
   if (g_group_depth > 0) g_group_depth--;
+  if (g_group_depth == 0 && !g_group_p2p.empty()) {
+    std::vector<Shim*> todo;
+    todo.swap(g_group_p2p);
+    for (Shim* s : todo) {
+      ncclResult_t r = flush_p2p(s);
+      if (r != ncclSuccess) return r;
+    }
+  }
   if (g_group_fwd > 0) {
     g_group_fwd--;
     if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupEnd")) return f();
@@ -519,12 +586,12 @@ ncclResult_t ncclCommRevoke(ncclComm_t c, int flags) {
 ncclResult_t ncclSend(const void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
   if (s->real) { auto f = REAL(ncclSend, const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(buf, count, dt, peer, s->real, st); }
-  return err(ncclInvalidUsage, "point-to-point ncclSend on a b200mpi communicator: not provided (set B200MPI_ALGO=nccl for this process group)");
+  return queue_p2p(s, b200mpi_p2p_op_t{buf, nullptr, count * dt_size(dt), peer, 1}, st);
 }
 ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
   if (s->real) { auto f = REAL(ncclRecv, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(buf, count, dt, peer, s->real, st); }
-  return err(ncclInvalidUsage, "point-to-point ncclRecv on a b200mpi communicator: not provided (set B200MPI_ALGO=nccl for this process group)");
+  return queue_p2p(s, b200mpi_p2p_op_t{nullptr, buf, count * dt_size(dt), peer, 0}, st);
 }
 
 ncclResult_t ncclMemAlloc(void** ptr, size_t size) { return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemAlloc"); }

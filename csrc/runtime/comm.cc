@@ -118,6 +118,7 @@ struct TraceRec { const char* op; size_t bytes; int algo; int blocks; uint64_t t
 // Per-communicator counters by (op, algorithm): what /metrics exports as b200mpi_collective_{calls,bytes}_total.
 // `op` is a string literal, so pointer identity is the key; a handful of entries, linear scan.
 struct OpStat { const char* op; int algo; uint64_t calls; uint64_t bytes; };
+static const char* const kP2PName = "p2p";
 
 }  // namespace b200mpi
 
@@ -131,7 +132,8 @@ struct b200mpi_comm {
   unsigned flags = 0;
   Rendezvous rv;
   std::vector<Window> wins;
-  int sig_win = -1, stage_win = -1;
+  int sig_win = -1, stage_win = -1, p2p_win = -1;
+  uint32_t* p2p_cnt = nullptr;       // device: chunks sent to / received from every peer (p2p.cu)
   uint32_t* epoch[kMaxRanks] = {};   // real mode: only [rank]
   int* err_host = nullptr;           // pinned, mapped
   int* err_dev = nullptr;
@@ -442,6 +444,13 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   if (rc) return rc;
   rc = window_alloc(c, c->stage_bytes, &c->stage_win);
   if (rc) return rc;
+  if (!c->local && c->world > 1 && env_int("B200MPI_P2P", 0)) {  // experimental point-to-point mailboxes (p2p.cu)
+    rc = window_alloc(c, kP2PWindowBytes, &c->p2p_win);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemset(c->wins[c->p2p_win].ptr[c->rank] + kP2PDataBytes, 0, kP2PFlagBytes));
+    CUDA_TRY(cudaMalloc((void**)&c->p2p_cnt, 2 * kMaxRanks * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(c->p2p_cnt, 0, 2 * kMaxRanks * sizeof(uint32_t)));
+  }
   CUDA_TRY(cudaDeviceSynchronize());
   if (!c->local) {
     std::string err;
@@ -666,6 +675,7 @@ int b200mpi_comm_destroy(b200mpi_comm_t c) {
   for (auto& W : c->wins) window_release(c, W);
   for (int r = 0; r < kMaxRanks; r++) if (c->epoch[r]) cudaFree(c->epoch[r]);
   if (c->emu_ring) cudaFree(c->emu_ring);
+  if (c->p2p_cnt) cudaFree(c->p2p_cnt);
   if (c->err_host) cudaFreeHost(c->err_host);
   c->rv.detach(c->rank == 0);
   delete c;
@@ -866,6 +876,67 @@ int b200mpi_get_tuning(b200mpi_comm_t c, size_t* oneshot_max, size_t* nvls_min, 
 }
 int b200mpi_select_algo(b200mpi_comm_t c, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op, int symmetric) {
   return select_algo(c, bytes, dtype, op, symmetric != 0);
+}
+
+int b200mpi_comm_has_p2p(b200mpi_comm_t c) { return c->p2p_win >= 0 ? 1 : 0; }
+
+// Plans one batch: per-stream chunk offsets for operations that share a (direction, peer) stream, totals for the commit
+// kernel. Split from the launch so the host test can check it without a device.
+static int p2p_plan(int rank, int world, const b200mpi_p2p_op_t* ops, int nops, P2PArgs* a, P2PCommit* add) {
+  if (nops < 1 || nops > kMaxP2POps) return fail(B200MPI_ERR_INVALID, "p2p_batch: between 1 and 64 operations per batch");
+  memset(add, 0, sizeof(*add));
+  a->nops = nops;
+  for (int i = 0; i < nops; i++) {
+    const b200mpi_p2p_op_t& o = ops[i];
+    if (o.peer < 0 || o.peer >= world) return fail(B200MPI_ERR_INVALID, "p2p_batch: peer out of range");
+    if (o.peer == rank) return fail(B200MPI_ERR_UNSUPPORTED, "p2p_batch: send/recv to self (copy locally instead)");
+    const void* buf = o.is_send ? o.send : o.recv;
+    if (o.bytes && !buf) return fail(B200MPI_ERR_INVALID, "p2p_batch: null buffer");
+    const size_t chunks = (o.bytes + kP2PChunk - 1) / kP2PChunk;
+    if (chunks > 0x3fffffffu) return fail(B200MPI_ERR_INVALID, "p2p_batch: message too large");
+    uint32_t& total = add->n[(o.is_send ? 0 : kMaxRanks) + o.peer];
+    P2POp& d = a->ops[i];
+    d.user = reinterpret_cast<const char*>(buf);
+    d.bytes = o.bytes;
+    d.peer = o.peer;
+    d.is_send = o.is_send ? 1 : 0;
+    d.seq_off = total;
+    total += (uint32_t)chunks;
+  }
+  return 0;
+}
+
+int b200mpi_p2p_batch(b200mpi_comm_t c, const b200mpi_p2p_op_t* ops, int nops, void* stream) {
+  if (c->local) return fail(B200MPI_ERR_UNSUPPORTED, "p2p_batch: not available on emulated communicators");
+  if (c->p2p_win < 0) return fail(B200MPI_ERR_UNSUPPORTED, "point-to-point is experimental: set B200MPI_P2P=1 for every rank before the communicator is created");
+  P2PArgs a;
+  P2PCommit add;
+  int rc = p2p_plan(c->rank, c->world, ops, nops, &a, &add);
+  if (rc) return rc;
+  a.c = dev_comm(c, c->rank);
+  a.box = win_region(c, c->p2p_win, 0);
+  a.cnt = c->p2p_cnt;
+  cudaError_t e = launch_p2p_batch((cudaStream_t)stream, a, add);
+  if (e != cudaSuccess) return fail(B200MPI_ERR_CUDA, std::string("p2p_batch launch: ") + cudaGetErrorString(e));
+  c->launches.fetch_add(1, std::memory_order_relaxed);
+  size_t bytes = 0;
+  for (int i = 0; i < nops; i++) bytes += ops[i].bytes;
+  {
+    OpStat* st = nullptr;
+    for (auto& x : c->stats) if (x.op == kP2PName && x.algo == 0) { st = &x; break; }
+    if (!st) { c->stats.push_back(OpStat{kP2PName, 0, 0, 0}); st = &c->stats.back(); }
+    st->calls++;
+    st->bytes += bytes;
+  }
+  return 0;
+}
+int b200mpi_send(b200mpi_comm_t c, const void* buf, size_t bytes, int peer, void* stream) {
+  b200mpi_p2p_op_t o{buf, nullptr, bytes, peer, 1};
+  return b200mpi_p2p_batch(c, &o, 1, stream);
+}
+int b200mpi_recv(b200mpi_comm_t c, void* buf, size_t bytes, int peer, void* stream) {
+  b200mpi_p2p_op_t o{nullptr, buf, bytes, peer, 0};
+  return b200mpi_p2p_batch(c, &o, 1, stream);
 }
 
 int b200mpi_comm_stats_json(b200mpi_comm_t c, char* buf, size_t cap) {

@@ -61,6 +61,35 @@ int main() {
   EXPECT(b200mpi_bn_supported(12544, 256) == 1 && b200mpi_bn_supported(12544, 12) == 0 && b200mpi_bn_supported(0, 64) == 0);
   EXPECT(b200mpi_bn_workspace_floats(64) == (size_t)4 * 64 + (size_t)296 * 2 * 64 + 4);
 
+  // ---- point-to-point batch planning: chunk offsets per (direction, peer) stream, totals for the commit kernel
+  {
+    char bufs[8];
+    b200mpi_p2p_op_t ops[5] = {
+        {bufs, nullptr, (size_t)3 << 20, 1, 1},          // send 3 MiB to 1  -> 3 chunks, offset 0
+        {nullptr, bufs, 100, 1, 0},                       // recv 100 B from 1 -> 1 chunk, offset 0 (other direction)
+        {bufs, nullptr, ((size_t)1 << 20) + 1, 1, 1},     // send 1 MiB + 1 to 1 -> 2 chunks, offset 3
+        {bufs, nullptr, 0, 2, 1},                          // empty message -> 0 chunks
+        {nullptr, bufs, (size_t)1 << 20, 1, 0},           // recv 1 MiB from 1 -> 1 chunk, offset 1
+    };
+    P2PArgs a;
+    P2PCommit add;
+    EXPECT(p2p_plan(0, 4, ops, 5, &a, &add) == 0);
+    EXPECT(a.nops == 5 && a.ops[0].seq_off == 0 && a.ops[1].seq_off == 0 && a.ops[2].seq_off == 3 && a.ops[4].seq_off == 1);
+    EXPECT(a.ops[0].is_send == 1 && a.ops[1].is_send == 0 && a.ops[2].bytes == ((size_t)1 << 20) + 1);
+    EXPECT(add.n[1] == 5 && add.n[kMaxRanks + 1] == 2 && add.n[2] == 0 && add.n[kMaxRanks + 2] == 0);
+    EXPECT(p2p_plan(1, 4, ops, 5, &a, &add) == B200MPI_ERR_UNSUPPORTED);   // peer == self
+    EXPECT(p2p_plan(0, 2, ops + 3, 1, &a, &add) == B200MPI_ERR_INVALID);   // peer 2 outside a 2-rank world
+    EXPECT(p2p_plan(0, 4, ops, 0, &a, &add) == B200MPI_ERR_INVALID);
+    // mailbox geometry: flags sit after the data, one 128-byte line each, READY and ACK disjoint
+    char* base = reinterpret_cast<char*>(0x10000000);
+    EXPECT(reinterpret_cast<char*>(p2p_flag(base, P2P_READY, 0)) == base + kP2PDataBytes);
+    EXPECT(p2p_flag(base, P2P_READY, 1) - p2p_flag(base, P2P_READY, 0) == 2 * kP2PFlagStride);
+    EXPECT(reinterpret_cast<char*>(p2p_flag(base, P2P_ACK, kMaxRanks - 1) + kP2PFlagStride + 1) <= base + kP2PWindowBytes);
+    EXPECT(p2p_flag(base, P2P_ACK, 0) == p2p_flag(base, P2P_READY, kMaxRanks - 1) + 2 * kP2PFlagStride);
+    b200mpi_comm* nc = new b200mpi_comm;     // no mailbox window: the API refuses instead of touching memory
+    EXPECT(b200mpi_comm_has_p2p(nc) == 0 && b200mpi_p2p_batch(nc, ops, 1, nullptr) == B200MPI_ERR_UNSUPPORTED);
+  }
+
   printf(g_failed ? "comm_host_test: %d check(s) FAILED\n" : "comm_host_test: all checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }

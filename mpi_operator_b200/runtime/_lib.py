@@ -91,6 +91,9 @@ def lib() -> C.CDLL:
     L.b200mpi_set_tuning.argtypes = [vp, sz, sz, i, i]
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
     L.b200mpi_select_algo.argtypes = [vp, sz, i, i, i]
+    if hasattr(L, "b200mpi_p2p_batch"):  # experimental point-to-point (csrc/kernels/p2p.cu)
+        L.b200mpi_p2p_batch.argtypes = [vp, vp, i, vp]
+        L.b200mpi_comm_has_p2p.argtypes = [vp]
     if hasattr(L, "b200mpi_comm_stats_json"):  # absent only in a stale build
         L.b200mpi_comm_stats_json.argtypes = [vp, C.c_char_p, C.c_size_t]
         L.b200mpi_comm_stats_json.restype = C.c_int

@@ -302,6 +302,34 @@ class Communicator:
             count, dtype_code(grad_dtype), s, lr, momentum_coef, weight_decay, int(nesterov), int(first_step),
             resolve_algo(algo), _stream_ptr(stream)), "allreduce_sgd_sym")
 
+    # ------------------------------------------------------ point-to-point --
+    @property
+    def has_p2p(self) -> bool:
+        L = _lib.lib()
+        return bool(hasattr(L, "b200mpi_comm_has_p2p") and L.b200mpi_comm_has_p2p(self._h))
+
+    def p2p_batch(self, ops, stream=None) -> None:
+        """EXPERIMENTAL (needs B200MPI_P2P=1 at creation). ``ops``: list of ``("send" | "recv", tensor, peer)``; the whole
+        batch runs as one kernel with one CTA per operation, so a rank may send to and receive from the same peers in one
+        call without deadlocking (the ncclGroupStart/End pattern)."""
+
+        class _Op(C.Structure):
+            _fields_ = [("send", C.c_void_p), ("recv", C.c_void_p), ("bytes", C.c_size_t), ("peer", C.c_int), ("is_send", C.c_int)]
+        arr = (_Op * len(ops))()
+        for k, (kind, t, peer) in enumerate(ops):
+            if kind not in ("send", "recv") or not t.is_contiguous() or not t.is_cuda:
+                raise B200MPIError("p2p_batch: ('send'|'recv', contiguous CUDA tensor, peer)")
+            nbytes = t.numel() * t.element_size()
+            arr[k] = _Op(t.data_ptr() if kind == "send" else None, t.data_ptr() if kind == "recv" else None, nbytes, int(peer),
+                         1 if kind == "send" else 0)
+        check(_lib.lib().b200mpi_p2p_batch(self._h, C.cast(arr, C.c_void_p), len(ops), _stream_ptr(stream)), "p2p_batch")
+
+    def send(self, tensor, peer: int, stream=None) -> None:
+        self.p2p_batch([("send", tensor, peer)], stream)
+
+    def recv(self, tensor, peer: int, stream=None) -> None:
+        self.p2p_batch([("recv", tensor, peer)], stream)
+
     def set_hyper(self, tensor) -> None:
         """Device tensor {lr, momentum, weight_decay} read by the fused SGD kernels (None: by-value)."""
         self._hyper = tensor

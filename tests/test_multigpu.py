@@ -45,3 +45,14 @@ def test_ld_preload_shim_passthrough_mode():
     n = min(torch.cuda.device_count(), 8)
     rcs = launch(n, [os.path.join(HERE, "ddp_shim_worker.py")], timeout=240, extra_env={"LD_PRELOAD": shim, "B200MPI_ALGO": "nccl"})
     assert rcs == [0] * n
+
+
+@pytest.mark.xfail(strict=False, reason="experimental point-to-point path (B200MPI_P2P=1): written after the round's GPU budget was spent, "
+                                        "host-side planning is covered by `make test_comm_host`")
+def test_point_to_point_mailboxes():
+    """ncclSend/ncclRecv substrate: ring shift, eager send, all-to-all by batches, CUDA-graph replay (tests/p2p_worker.py)."""
+    sys.path.insert(0, HERE)
+    from mp_launch import launch
+    n = min(torch.cuda.device_count(), 8)
+    rcs = launch(n, [os.path.join(HERE, "p2p_worker.py")], timeout=240, extra_env={"B200MPI_P2P": "1"})
+    assert rcs == [0] * n
