@@ -12,3 +12,7 @@ echo "=== ResNet-50 DDP script under LD_PRELOAD, N=$N ==="
 mkdir -p gpurun_out/ddp_n$N
 LD_PRELOAD=$SHIM timeout 200 python tests/mp_launch.py -n $N --timeout 180 --log-dir gpurun_out/ddp_n$N examples/torch-ddp/torch_ddp_resnet50.py --steps 20 --warmup 5
 for f in gpurun_out/ddp_n$N/*.log; do echo "--- $f"; grep -v "^frame\|^$" $f | tail -12; done
+echo "=== experimental point-to-point (B200MPI_P2P=1), N=$N ==="
+mkdir -p gpurun_out/p2p_n$N
+B200MPI_P2P=1 timeout 150 python tests/mp_launch.py -n $N --timeout 120 --log-dir gpurun_out/p2p_n$N tests/p2p_worker.py
+for f in gpurun_out/p2p_n$N/*.log; do echo "--- $f"; tail -6 $f; done
