@@ -190,3 +190,25 @@ def test_env_switch_and_dtype_guard(monkeypatch):
     monkeypatch.delenv("B200MPI_BF16_PARAMS")
     assert not DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, channels_last=False,
                                    cuda_graph=False).bf16_params
+
+
+def test_graph_replay_accounting_folds_recaptures():
+    """CUDA-graph replays launch collectives without the host: the trainer reports replays x per-capture counts to
+    Communicator.stats() through a stat source, and keeps the totals of graphs that were re-captured since."""
+    sources = []
+
+    class CountingComm(FakeComm):
+        def add_stat_source(self, fn):
+            sources.append(fn)
+
+    tr = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), CountingComm(), lr=0.1, channels_last=False, cuda_graph=False,
+                             autocast_dtype=None)
+    assert len(sources) == 1 and sources[0]() == []
+    tr._graph_ops = [{"op": "allreduce_sgd", "algo": "nvls", "calls": 9, "bytes": 1000}]
+    tr._replays = 5
+    assert sources[0]() == [{"op": "allreduce_sgd", "algo": "nvls", "calls": 45, "bytes": 5000}]
+    tr._folded_ops = tr._replayed_ops()                 # what _capture() does before recording a new graph
+    tr._graph_ops, tr._replays = [{"op": "allreduce_sgd", "algo": "nvls", "calls": 3, "bytes": 10},
+                                  {"op": "allreduce", "algo": "oneshot", "calls": 1, "bytes": 4}], 2
+    got = {(o["op"], o["algo"]): (o["calls"], o["bytes"]) for o in sources[0]()}
+    assert got == {("allreduce_sgd", "nvls"): (51, 5020), ("allreduce", "oneshot"): (2, 8)}
