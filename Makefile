@@ -90,6 +90,13 @@ test_comm_host: $(LIBDIR)/libb200mpi.so
 	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -x cu csrc/tests/comm_host_test.cu -o build/san/comm_host_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
 	build/san/comm_host_test
 
+# hand-packed tcgen05 descriptors vs CuTe's (headers vendored with flashinfer in this image; pass CUTLASS_INC=... elsewhere)
+CUTLASS_INC ?= $(shell python -c "import flashinfer,os;print(os.path.join(os.path.dirname(flashinfer.__file__),'data','cutlass','include'))" 2>/dev/null)
+test_umma_desc:
+	@mkdir -p build/san
+	$(NVCC) -std=c++17 -O1 $(ARCH) --expt-relaxed-constexpr -Icsrc/include -I$(CUTLASS_INC) -x cu csrc/tests/umma_desc_test.cu -o build/san/umma_desc_test
+	build/san/umma_desc_test 2>/dev/null
+
 asan:
 	$(call san_build,asan,-fsanitize=address$(comma)undefined -fno-sanitize-recover=undefined)
 	ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 build/san/asan/mpirun -n 4 build/san/asan/mpi_stress 200
@@ -100,4 +107,4 @@ tsan:
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc

@@ -97,7 +97,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 //   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1: unused for swizzled K-major) |
 //   [32,46) stride byte offset >> 4 (=64: 8 rows x 128 B between core-matrix groups) | [46,48) version = 1 (sm_100) |
 //   [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
+__host__ __device__ __forceinline__ uint64_t make_desc_kmajor_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)64 << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // Instruction descriptor (InstrDescriptor): c_format F32 (1) at [4,6), a/b format BF16 (1) at [7,10)/[10,13),

@@ -170,3 +170,18 @@ def test_runtime_launch_planning_on_the_host():
         pytest.skip("native libraries not built (run make)")
     r = subprocess.run(["make", "test_comm_host"], cwd=REPO, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "comm_host_test: all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_tcgen05_descriptors_match_cute():
+    """`make test_umma_desc`: the instruction descriptor and the K-major / 128-byte-swizzle shared-memory descriptor packed by
+    hand in csrc/kernels/gemm_bnstats.cu are bit-identical to what CuTe builds for the same tile (host-only check)."""
+    try:
+        import flashinfer
+        inc = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass", "include")
+    except ImportError:
+        inc = ""
+    if not os.path.exists(os.path.join(inc, "cute", "arch", "mma_sm100_desc.hpp")):
+        pytest.skip("CUTLASS/CuTe headers not available")
+    r = subprocess.run(["make", "test_umma_desc"], cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "umma_desc_test: descriptors match CuTe" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
