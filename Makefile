@@ -91,7 +91,7 @@ test_comm_host: $(LIBDIR)/libb200mpi.so
 	build/san/comm_host_test
 
 # hand-packed tcgen05 descriptors vs CuTe's (headers vendored with flashinfer in this image; pass CUTLASS_INC=... elsewhere)
-CUTLASS_INC ?= $(shell python -c "import flashinfer,os;print(os.path.join(os.path.dirname(flashinfer.__file__),'data','cutlass','include'))" 2>/dev/null)
+CUTLASS_INC ?= $(shell python -c "import importlib.util,os;s=importlib.util.find_spec('flashinfer');print(os.path.join(os.path.dirname(s.origin),'data','cutlass','include'))" 2>/dev/null)
 test_umma_desc:
 	@mkdir -p build/san
 	$(NVCC) -std=c++17 -O1 $(ARCH) --expt-relaxed-constexpr -Icsrc/include -I$(CUTLASS_INC) -x cu csrc/tests/umma_desc_test.cu -o build/san/umma_desc_test

@@ -175,11 +175,9 @@ def test_runtime_launch_planning_on_the_host():
 def test_tcgen05_descriptors_match_cute():
     """`make test_umma_desc`: the instruction descriptor and the K-major / 128-byte-swizzle shared-memory descriptor packed by
     hand in csrc/kernels/gemm_bnstats.cu are bit-identical to what CuTe builds for the same tile (host-only check)."""
-    try:
-        import flashinfer
-        inc = os.path.join(os.path.dirname(flashinfer.__file__), "data", "cutlass", "include")
-    except ImportError:
-        inc = ""
+    import importlib.util
+    spec = importlib.util.find_spec("flashinfer")   # located, not imported
+    inc = os.path.join(os.path.dirname(spec.origin), "data", "cutlass", "include") if spec and spec.origin else ""
     if not os.path.exists(os.path.join(inc, "cute", "arch", "mma_sm100_desc.hpp")):
         pytest.skip("CUTLASS/CuTe headers not available")
     r = subprocess.run(["make", "test_umma_desc"], cwd=REPO, capture_output=True, text=True, timeout=600)
