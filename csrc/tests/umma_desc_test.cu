@@ -31,6 +31,20 @@ int main() {
   check("smem desc B [64 x 64] (no addr)", b200mpi::gemm::make_desc_kmajor_sw128(0) & addr_mask, UMMA::make_umma_desc<UMMA::Major::K>(b64).desc_ & addr_mask);
   check("smem desc address field", b200mpi::gemm::make_desc_kmajor_sw128(0x2A400) & 0x3FFFull, 0x2A40ull);
   check("K advance of 16 bf16 (+32 B)", (b200mpi::gemm::make_desc_kmajor_sw128(0x400) + 2) & 0x3FFFull, (0x400ull + 32) >> 4);
+  // the epilogue writes the bf16 tile into shared memory by hand in the 128-byte-swizzle layout the TMA store expects:
+  //   byte offset(row r, column j) = r*128 + ((j/8) ^ (r & 7))*16 + (j % 8)*2     (gemm_bnstats.cu, epilogue + column sums)
+  {
+    // CuTe applies Sw<3,4,3> to the byte address of the (1024-byte aligned) tile: compare real element addresses
+    long bad = 0;
+    const char* base = reinterpret_cast<const char*>(&a128(0, 0));
+    for (int r = 0; r < 128; r++)
+      for (int j = 0; j < 64; j++) {
+        const unsigned long long ours = (unsigned long long)r * 128 + (unsigned long long)(((j >> 3) ^ (r & 7)) << 4) + (unsigned long long)(j & 7) * 2;
+        const unsigned long long theirs = (unsigned long long)(reinterpret_cast<const char*>(&a128(r, j)) - base);
+        if (ours != theirs) bad++;
+      }
+    check("swizzled tile offsets (mismatches)", (unsigned long long)bad, 0);
+  }
   printf(failed ? "umma_desc_test: %d MISMATCH(ES)\n" : "umma_desc_test: descriptors match CuTe\n", failed);
   return failed ? 1 : 0;
 }
