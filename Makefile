@@ -90,6 +90,12 @@ test_comm_host: $(LIBDIR)/libb200mpi.so
 	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -x cu csrc/tests/comm_host_test.cu -o build/san/comm_host_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
 	build/san/comm_host_test
 
+# the point-to-point protocol of p2p.cu run with host threads instead of CTAs (same template, host platform)
+test_p2p_protocol: $(LIBDIR)/libb200mpi.so
+	@mkdir -p build/san
+	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -Xcudafe --diag_suppress=20011,--diag_suppress=20014 -x cu csrc/tests/p2p_protocol_test.cu -o build/san/p2p_protocol_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
+	build/san/p2p_protocol_test
+
 # hand-packed tcgen05 descriptors vs CuTe's (headers vendored with flashinfer in this image; pass CUTLASS_INC=... elsewhere)
 CUTLASS_INC ?= $(shell python -c "import importlib.util,os;s=importlib.util.find_spec('flashinfer');print(os.path.join(os.path.dirname(s.origin),'data','cutlass','include'))" 2>/dev/null)
 test_umma_desc:
@@ -107,4 +113,4 @@ tsan:
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol

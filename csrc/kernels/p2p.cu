@@ -20,73 +20,93 @@
 
 namespace b200mpi {
 
-__device__ __forceinline__ bool p2p_wait_ge(const uint32_t* flag, uint32_t want, const DevComm& c, int peer) {
-  unsigned long long t0 = 0;
-  uint32_t spins = 0;
-  while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
-    if ((++spins & 0x3ffu) == 0) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > c.timeout_ns) {
-        *c.err = 1 + peer;
-        return false;
-      }
-    }
-  }
-  return true;
-}
-
-__global__ void __launch_bounds__(kThreads)
-k_p2p_batch(const __grid_constant__ P2PArgs a) {
-  const P2POp op = a.ops[blockIdx.x];
-  const int rank = a.c.rank, peer = op.peer;
-  __shared__ int s_ok;
+// The protocol itself is platform-neutral: P supplies the thread geometry, the CTA barrier, flag wait/release and the two
+// copy loops. The device platform below is what the kernel runs; csrc/tests/p2p_protocol_test.cc instantiates the same
+// function with host threads and atomics (one thread per operation, ranks = buffers in one process) to check sequence
+// numbers, slot reuse, eager sends and multi-batch counter hand-over without a GPU.
+template <typename P>
+__host__ __device__ inline void p2p_run_op(const P2POp& op, int rank, char* const* box, const uint32_t* cnt, P& pf) {
+  const int peer = op.peer;
   if (op.bytes == 0) return;
   const size_t nchunks = (op.bytes + kP2PChunk - 1) / kP2PChunk;
   if (op.is_send) {
-    const uint32_t base = a.cnt[peer] + op.seq_off;                       // chunks already sent to `peer`
-    char* box = a.box.p[peer] + (size_t)rank * 2 * kP2PChunk;             // my two slots in the peer's mailbox
-    uint32_t* ready = p2p_flag(a.box.p[peer], P2P_READY, rank);           // in the peer's window
-    const uint32_t* ack = p2p_flag(a.box.p[rank], P2P_ACK, peer);         // in my window, written by the peer
-    const bool aligned = (reinterpret_cast<uintptr_t>(op.user) & 15u) == 0;
+    const uint32_t base = cnt[peer] + op.seq_off;                         // chunks already sent to `peer`
+    char* slots = box[peer] + (size_t)rank * 2 * kP2PChunk;               // my two slots in the peer's mailbox
+    uint32_t* ready = p2p_flag(box[peer], P2P_READY, rank);               // in the peer's window
+    uint32_t* ack = p2p_flag(box[rank], P2P_ACK, peer);                   // in my window, written by the peer
     for (size_t k = 0; k < nchunks; k++) {
       const uint32_t q = base + (uint32_t)k;
       const int slot = (int)(q & 1u);
-      if (q >= 2) {  // the slot still holds chunk q-2 until the receiver acknowledges it with value q-1
-        if (threadIdx.x == 0) s_ok = p2p_wait_ge(ack + slot * kP2PFlagStride, q - 1, a.c, peer) ? 1 : 0;
-        __syncthreads();
-        if (!s_ok) return;
-      }
+      // the slot still holds chunk q-2 until the receiver acknowledges it with value q-1
+      if (q >= 2 && !pf.wait_ge(ack + slot * kP2PFlagStride, q - 1, peer)) return;
       const size_t off = k * kP2PChunk;
       const size_t n = op.bytes - off < kP2PChunk ? op.bytes - off : kP2PChunk;
-      const size_t nvec = (n + 15) / 16;
-      char* dst = box + (size_t)slot * kP2PChunk;
-      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) st_peer_v4(dst + i * 16, user_load(op.user + off, i, n, aligned));
-      __syncthreads();  // every thread's pushes are ordered before thread 0's release (cumulativity through bar.sync)
-      if (threadIdx.x == 0) st_release_sys(ready + slot * kP2PFlagStride, q + 1);
+      pf.push(slots + (size_t)slot * kP2PChunk, op.user + off, n);
+      pf.sync();  // every thread's pushes are ordered before the release (cumulativity through bar.sync)
+      pf.release(ready + slot * kP2PFlagStride, q + 1);
     }
   } else {
-    const uint32_t base = a.cnt[kMaxRanks + peer] + op.seq_off;           // chunks already received from `peer`
-    const char* box = a.box.p[rank] + (size_t)peer * 2 * kP2PChunk;       // the peer's two slots in my mailbox
-    const uint32_t* ready = p2p_flag(a.box.p[rank], P2P_READY, peer);
-    uint32_t* ack = p2p_flag(a.box.p[peer], P2P_ACK, rank);               // in the sender's window
+    const uint32_t base = cnt[kMaxRanks + peer] + op.seq_off;             // chunks already received from `peer`
+    const char* slots = box[rank] + (size_t)peer * 2 * kP2PChunk;         // the peer's two slots in my mailbox
+    uint32_t* ready = p2p_flag(box[rank], P2P_READY, peer);
+    uint32_t* ack = p2p_flag(box[peer], P2P_ACK, rank);                   // in the sender's window
     char* user = const_cast<char*>(op.user);
-    const bool aligned = (reinterpret_cast<uintptr_t>(user) & 15u) == 0;
     for (size_t k = 0; k < nchunks; k++) {
       const uint32_t q = base + (uint32_t)k;
       const int slot = (int)(q & 1u);
-      if (threadIdx.x == 0) s_ok = p2p_wait_ge(ready + slot * kP2PFlagStride, q + 1, a.c, peer) ? 1 : 0;
-      __syncthreads();
-      if (!s_ok) return;
+      if (!pf.wait_ge(ready + slot * kP2PFlagStride, q + 1, peer)) return;
       const size_t off = k * kP2PChunk;
       const size_t n = op.bytes - off < kP2PChunk ? op.bytes - off : kP2PChunk;
-      const size_t nvec = (n + 15) / 16;
-      const char* src = box + (size_t)slot * kP2PChunk;
-      for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) user_store(user + off, i, n, aligned, ld_sys_v4(src + i * 16));
-      __syncthreads();  // all reads of the slot are done before it is handed back
-      if (threadIdx.x == 0) st_release_sys(ack + slot * kP2PFlagStride, q + 1);
+      pf.pull(user + off, slots + (size_t)slot * kP2PChunk, n);
+      pf.sync();  // all reads of the slot are done before it is handed back
+      pf.release(ack + slot * kP2PFlagStride, q + 1);
     }
   }
+}
+
+#ifdef __CUDACC__
+struct P2PDevice {
+  const DevComm& c;
+  int* s_ok;
+  // thread 0 spins (acquire, .sys scope, bounded by the communicator watchdog); the CTA learns the outcome through smem
+  __device__ bool wait_ge(const uint32_t* flag, uint32_t want, int peer) {
+    if (threadIdx.x == 0) {
+      int ok = 1;
+      unsigned long long t0 = 0;
+      uint32_t spins = 0;
+      while ((int32_t)(ld_acquire_sys(flag) - want) < 0) {
+        if ((++spins & 0x3ffu) == 0) {
+          const unsigned long long now = globaltimer_ns();
+          if (t0 == 0) t0 = now;
+          else if (now - t0 > c.timeout_ns) { *c.err = 1 + peer; ok = 0; break; }
+        }
+      }
+      *s_ok = ok;
+    }
+    __syncthreads();
+    const bool ok = *s_ok != 0;
+    __syncthreads();  // s_ok may be rewritten by the next wait
+    return ok;
+  }
+  __device__ void sync() { __syncthreads(); }
+  __device__ void release(uint32_t* flag, uint32_t v) { if (threadIdx.x == 0) st_release_sys(flag, v); }
+  __device__ void push(char* dst, const char* src, size_t n) {      // local user buffer -> peer mailbox
+    const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+    const size_t nvec = (n + 15) / 16;
+    for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) st_peer_v4(dst + i * 16, user_load(src, i, n, aligned));
+  }
+  __device__ void pull(char* dst, const char* src, size_t n) {      // own mailbox -> local user buffer
+    const bool aligned = (reinterpret_cast<uintptr_t>(dst) & 15u) == 0;
+    const size_t nvec = (n + 15) / 16;
+    for (size_t i = threadIdx.x; i < nvec; i += blockDim.x) user_store(dst, i, n, aligned, ld_sys_v4(src + i * 16));
+  }
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_p2p_batch(const __grid_constant__ P2PArgs a) {
+  __shared__ int s_ok;
+  P2PDevice pf{a.c, &s_ok};
+  p2p_run_op(a.ops[blockIdx.x], a.c.rank, a.box.p, a.cnt, pf);
 }
 
 // Advances the per-peer chunk counters by what the batch moved (stream-ordered after k_p2p_batch).
@@ -102,5 +122,6 @@ cudaError_t launch_p2p_batch(cudaStream_t s, const P2PArgs& a, const P2PCommit& 
   k_p2p_commit<<<1, 32, 0, s>>>(a.cnt, add);
   return cudaGetLastError();
 }
+#endif  // __CUDACC__
 
 }  // namespace b200mpi

@@ -183,3 +183,13 @@ def test_tcgen05_descriptors_match_cute():
     r = subprocess.run(["make", "test_umma_desc"], cwd=REPO, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "umma_desc_test: descriptors match CuTe" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
     assert "MISMATCH" not in r.stdout
+
+
+def test_point_to_point_protocol_with_host_threads():
+    """`make test_p2p_protocol`: the p2p_run_op<> template of csrc/kernels/p2p.cu — the code the kernel runs — instantiated
+    with host threads and atomics: ring shifts over ragged sizes, eager sends, back-pressure on the third chunk, several
+    messages per peer in one batch, counters carried across batches."""
+    if not os.path.exists(os.path.join(REPO, "mpi_operator_b200/lib/libb200mpi.so")):
+        pytest.skip("native libraries not built (run make)")
+    r = subprocess.run(["make", "test_p2p_protocol"], cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "p2p_protocol_test: all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
