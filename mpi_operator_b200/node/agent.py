@@ -175,9 +175,18 @@ class NodeAgent:
             self._cm_dirty = True
         self._wake.set()
 
+    def _next_wait(self) -> float:
+        """Store events wake the loop at once; the timed wake-up only exists to poll child processes and restart back-offs
+        (every `tick`) and the second-granularity timers — deadlines, TTLs, schedule time-outs — for which an idle daemon
+        does not need to re-list every pod 20 times a second."""
+        for pr in list(self._procs.values()):
+            if (pr.popen is not None and not pr.virtual) or pr.next_restart:
+                return self.tick
+        return max(self.tick, 0.5)
+
     def _loop(self) -> None:
         while not self._stop.is_set():
-            self._wake.wait(self.tick)
+            self._wake.wait(self._next_wait())
             self._wake.clear()
             try:
                 self.sync_once()
