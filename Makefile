@@ -96,6 +96,12 @@ test_p2p_protocol: $(LIBDIR)/libb200mpi.so
 	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -Xcudafe --diag_suppress=20011,--diag_suppress=20014 -x cu csrc/tests/p2p_protocol_test.cu -o build/san/p2p_protocol_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
 	build/san/p2p_protocol_test
 
+# host model of the tcgen05 GEMM's three-role pipeline (shares gemm_bnstats_logic.h with the kernel)
+test_gemm_model:
+	@mkdir -p build/san
+	$(CXX) -std=c++17 -O2 -Wall -o build/san/gemm_pipeline_model csrc/tests/gemm_pipeline_model.cc -lpthread
+	build/san/gemm_pipeline_model
+
 # hand-packed tcgen05 descriptors vs CuTe's (headers vendored with flashinfer in this image; pass CUTLASS_INC=... elsewhere)
 CUTLASS_INC ?= $(shell python -c "import importlib.util,os;s=importlib.util.find_spec('flashinfer');print(os.path.join(os.path.dirname(s.origin),'data','cutlass','include'))" 2>/dev/null)
 test_umma_desc:
@@ -113,4 +119,4 @@ tsan:
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model

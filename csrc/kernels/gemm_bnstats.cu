@@ -28,14 +28,11 @@
 #include <stdint.h>
 
 #include "../include/b200mpi.h"
+#include "gemm_bnstats_logic.h"
 
 namespace b200mpi {
 namespace gemm {
 
-constexpr int BM = 128;          // rows per tile == TMEM lanes == UMMA M
-constexpr int BK = 64;           // 64 bf16 = 128 bytes = one swizzle-128B row
-constexpr int UMMA_K = 16;       // K per tcgen05.mma for 16-bit inputs
-constexpr int kStages = 4;
 constexpr int kThreads = 192;    // 6 warps: TMA, MMA, 4 x epilogue
 constexpr int kEpiThreads = 128;
 constexpr uint32_t kABytes = BM * BK * 2;   // 16 KiB
@@ -144,7 +141,7 @@ struct Smem {
   static constexpr uint32_t kBBytes = BN * BK * 2;
   static constexpr uint32_t kStageBytes = kABytes + kBBytes;
   static constexpr uint32_t kOutBoxes = BN / 64;                  // TMA store boxes of [128 rows x 64 cols] (128 B inner)
-  static constexpr uint32_t kOutBytes = kOutBoxes * BM * 128;
+  static constexpr uint32_t kOutBytes = kOutBoxes * kBoxBytes;
   static constexpr uint32_t kA = 0;
   static constexpr uint32_t kB = kStages * kABytes;
   static constexpr uint32_t kOut = kB + kStages * kBBytes;
@@ -171,11 +168,10 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + L::kTmemSlot);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_blk = blockIdx.x % num_n;
-  const int m_first = blockIdx.x / num_n, m_step = gridDim.x / num_n;
-  const int num_m = (M + BM - 1) / BM;
+  const TileWalk walk((int)blockIdx.x, (int)gridDim.x, num_n, M);
+  const int m_first = walk.m_first, m_step = walk.m_step, num_m = walk.num_m;
   const int num_k = K / BK;
-  const int n0 = n_blk * BN;
+  const int n0 = walk.n_blk * BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -206,15 +202,14 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp == 0) {
     // ===================================================== TMA producer ====
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
+      Ring st;
       for (int m_blk = m_first; m_blk < num_m; m_blk += m_step) {
         for (int kb = 0; kb < num_k; kb++) {
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_arrive_expect_tx(full_bar(s), L::kStageBytes);
-          tma_load_2d(sA + s * kABytes, &tmX, full_bar(s), kb * BK, m_blk * BM);
-          tma_load_2d(sB + s * L::kBBytes, &tmW, full_bar(s), kb * BK, n0);
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          mbar_wait(empty_bar(st.s), st.ph ^ 1u);
+          mbar_arrive_expect_tx(full_bar(st.s), L::kStageBytes);
+          tma_load_2d(sA + st.s * kABytes, &tmX, full_bar(st.s), kb * BK, m_blk * BM);
+          tma_load_2d(sB + st.s * L::kBBytes, &tmW, full_bar(st.s), kb * BK, n0);
+          st.advance(kStages);
         }
       }
     }
@@ -222,25 +217,24 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // ======================================================= MMA issuer ====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
-      int s = 0, ab = 0;
-      uint32_t ph = 0, aph = 0;
+      Ring st, acc;
       for (int m_blk = m_first; m_blk < num_m; m_blk += m_step) {
-        mbar_wait(tempty_bar(ab), aph ^ 1u);  // epilogue has drained this accumulator
+        mbar_wait(tempty_bar(acc.s), acc.ph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(ab * BN);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc.s * BN);
         for (int kb = 0; kb < num_k; kb++) {
-          mbar_wait(full_bar(s), ph);
+          mbar_wait(full_bar(st.s), st.ph);
           tc_fence_after();
-          const uint64_t adesc = make_desc_kmajor_sw128(sA + s * kABytes);
-          const uint64_t bdesc = make_desc_kmajor_sw128(sB + s * L::kBBytes);
+          const uint64_t adesc = make_desc_kmajor_sw128(sA + st.s * kABytes);
+          const uint64_t bdesc = make_desc_kmajor_sw128(sB + st.s * L::kBBytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++)  // +32 bytes along K inside the swizzle atom = +2 in the address field
             umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit(empty_bar(s));           // stage reusable once these MMAs have read it
-          if (++s == kStages) { s = 0; ph ^= 1u; }
+          umma_commit(empty_bar(st.s));        // stage reusable once these MMAs have read it
+          st.advance(kStages);
         }
-        umma_commit(tfull_bar(ab));            // accumulator complete
-        if (++ab == 2) { ab = 0; aph ^= 1u; }
+        umma_commit(tfull_bar(acc.s));         // accumulator complete
+        acc.advance(2);
       }
     }
   } else {
@@ -250,25 +244,22 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int row = q * 32 + lane;               // tile row held by this thread
     const bool col_owner = et < BN;              // thread `et` owns column n0 + et for the statistics
     float s1 = 0.f, s2 = 0.f;
-    int ab = 0;
-    uint32_t aph = 0;
+    Ring acc;
     for (int m_blk = m_first; m_blk < num_m; m_blk += m_step) {
       if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous tile's store has read the staging
       epi_bar_sync();
-      mbar_wait(tfull_bar(ab), aph);
+      mbar_wait(tfull_bar(acc.s), acc.ph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc.s * BN);
 #pragma unroll
       for (int c = 0; c < BN / 32; c++) {
         uint32_t v[32];
         tmem_ld_32x32(taddr + (uint32_t)(c * 32), v);
         tmem_ld_wait();
-        // 32 fp32 -> 32 bf16 = 4 chunks of 16 B; logical chunk lc in the 64-column box, physical = lc ^ (row & 7)
-        const uint32_t box = sOut + (uint32_t)(c >> 1) * (BM * 128) + (uint32_t)row * 128u;
+        // 32 fp32 -> 32 bf16 = 4 groups of 16 B in the swizzled staging layout (gemm_bnstats_logic.h)
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-          const uint32_t lc = (uint32_t)((c & 1) * 4 + g);
-          const uint32_t dst = box + ((lc ^ (uint32_t)(row & 7)) << 4);
+          const uint32_t dst = sOut + stage_group_byte(row, c, g);
           asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pack_bf16(v[8 * g + 0], v[8 * g + 1])),
                        "r"(pack_bf16(v[8 * g + 2], v[8 * g + 3])), "r"(pack_bf16(v[8 * g + 4], v[8 * g + 5])),
                        "r"(pack_bf16(v[8 * g + 6], v[8 * g + 7]))
@@ -277,23 +268,21 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(ab));  // accumulator free for the MMA warp (tile after next)
-      if (++ab == 2) { ab = 0; aph ^= 1u; }
+      if (lane == 0) mbar_arrive(tempty_bar(acc.s));  // accumulator free for the MMA warp (tile after next)
+      acc.advance(2);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
       epi_bar_sync();
       if (et == 0) {
 #pragma unroll
-        for (int b = 0; b < (int)L::kOutBoxes; b++) tma_store_2d(&tmY, sOut + (uint32_t)b * (BM * 128), n0 + b * 64, m_blk * BM);
+        for (int b = 0; b < (int)L::kOutBoxes; b++) tma_store_2d(&tmY, sOut + (uint32_t)b * kBoxBytes, n0 + b * 64, m_blk * BM);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       if (col_owner) {
         // column sums of the bf16-rounded tile (what the BN apply pass will read back). Rows past M are zero-filled by TMA.
-        const uint32_t colbase = sOut + (uint32_t)(et >> 6) * (BM * 128) + (uint32_t)((et & 7) * 2);
-        const uint32_t lc = (uint32_t)((et & 63) >> 3);
 #pragma unroll 8
         for (int r = 0; r < BM; r++) {
           uint16_t h;
-          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(colbase + (uint32_t)r * 128u + ((lc ^ (uint32_t)(r & 7)) << 4)));
+          asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(sOut + stage_elem_byte(et, r)));
           const float f = __uint_as_float((uint32_t)h << 16);
           s1 += f;
           s2 = fmaf(f, f, s2);
@@ -301,7 +290,7 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
     if (col_owner && m_first < num_m) {
-      float* row_out = partials + (size_t)m_first * 2 * N + 2 * (size_t)(n0 + et);
+      float* row_out = partials + partial_index(m_first, N, n0 + et);
       row_out[0] = s1;
       row_out[1] = s2;
     }

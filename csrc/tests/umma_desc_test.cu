@@ -39,9 +39,11 @@ int main() {
     const char* base = reinterpret_cast<const char*>(&a128(0, 0));
     for (int r = 0; r < 128; r++)
       for (int j = 0; j < 64; j++) {
-        const unsigned long long ours = (unsigned long long)r * 128 + (unsigned long long)(((j >> 3) ^ (r & 7)) << 4) + (unsigned long long)(j & 7) * 2;
         const unsigned long long theirs = (unsigned long long)(reinterpret_cast<const char*>(&a128(r, j)) - base);
-        if (ours != theirs) bad++;
+        if (b200mpi::gemm::operand_elem_byte(r, j) != theirs) bad++;              // operand tiles as TMA writes them
+        if (b200mpi::gemm::stage_elem_byte(j, r) != theirs) bad++;                // output staging, first 64-column box
+        if (b200mpi::gemm::stage_elem_byte(64 + j, r) != theirs + b200mpi::gemm::kBoxBytes) bad++;   // second box
+        if ((j & 7) == 0 && b200mpi::gemm::stage_group_byte(r, j >> 5, (j >> 3) & 3) != theirs) bad++;   // 16-byte group stores
       }
     check("swizzled tile offsets (mismatches)", (unsigned long long)bad, 0);
   }

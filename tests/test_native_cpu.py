@@ -193,3 +193,13 @@ def test_point_to_point_protocol_with_host_threads():
         pytest.skip("native libraries not built (run make)")
     r = subprocess.run(["make", "test_p2p_protocol"], cwd=REPO, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "p2p_protocol_test: all checks passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_tcgen05_gemm_pipeline_host_model():
+    """`make test_gemm_model`: the three warp roles of csrc/kernels/gemm_bnstats.cu (TMA producer, MMA issuer, 4 epilogue warps)
+    as host threads over emulated mbarriers / TMA / TMEM, sharing the kernel's index and phase arithmetic
+    (gemm_bnstats_logic.h). Ring wrap-around, accumulator double buffering, ragged M, both tile widths, the swizzled staging
+    layout, column sums and partial rows are checked against a plain GEMM."""
+    r = subprocess.run(["make", "test_gemm_model"], cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "gemm_pipeline_model: all cases match" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "MISMATCH" not in r.stdout
