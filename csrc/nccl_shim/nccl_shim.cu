@@ -46,7 +46,9 @@ struct ncclConfig_v;  // opaque
 namespace {
 
 struct PendingP2P { b200mpi_p2p_op_t op; cudaStream_t stream; };
+constexpr uint64_t kShimMagic = 0xB200C0DEC0117EC7ull;
 struct Shim {
+  uint64_t magic = kShimMagic;    // first word: tells our handles from real ncclComm pointers (see S())
   std::vector<PendingP2P> p2p;    // sends/receives queued inside ncclGroupStart/End (flushed as ONE kernel)
   b200mpi_comm_t mine = nullptr;  // b200mpi communicator (nullptr => forwarded)
   ncclComm_t real = nullptr;      // real NCCL communicator when forwarding
@@ -74,14 +76,34 @@ bool forward_all() {
 }
 bool debug() { static int v = getenv("B200MPI_DEBUG") ? 1 : 0; return v; }
 
+// libnccl calls some of its own public entry points through the PLT (objdump -R libnccl.so.2: ncclBroadcast,
+// ncclCommGetAsyncError, ncclCommRegister/Deregister, ncclCommWindowDeregister, ncclDevCommDestroy, ncclMemAlloc/Free,
+// ncclGetUniqueId, ncclGetVersion ...). With this library preloaded those internal calls land HERE, carrying real
+// ncclComm pointers. Two guards keep that transparent: (1) every forwarded call runs under a depth counter, and while
+// it is non-zero the comm-less entry points forward verbatim; (2) handles that do not start with kShimMagic are treated
+// as real communicators and forwarded untouched (S() below).
+thread_local int g_in_real = 0;
 template <typename F>
-F real_fn(const char* name) {
+struct RealCall;
+template <typename R, typename... A>
+struct RealCall<R (*)(A...)> {
+  R (*fn)(A...);
+  explicit operator bool() const { return fn != nullptr; }
+  R operator()(A... a) const {
+    g_in_real++;
+    R r = fn(a...);
+    g_in_real--;
+    return r;
+  }
+};
+template <typename F>
+RealCall<F> real_fn(const char* name) {
   void* p = dlsym(RTLD_NEXT, name);
   if (!p) {
     static void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (h) p = dlsym(h, name);
   }
-  return reinterpret_cast<F>(p);
+  return RealCall<F>{reinterpret_cast<F>(p)};
 }
 #define REAL(name, ...) real_fn<ncclResult_t (*)(__VA_ARGS__)>(#name)
 
@@ -240,7 +262,17 @@ ncclResult_t init_common(ncclComm_t* out, int nranks, const ncclUniqueId* id, in
   return ncclSuccess;
 }
 
-inline Shim* S(ncclComm_t c) { return reinterpret_cast<Shim*>(c); }
+inline bool is_shim(const void* c) { return c && *reinterpret_cast<const uint64_t*>(c) == kShimMagic; }
+// Our handle, or — for a real ncclComm that reached us through libnccl's own PLT — a per-thread stand-in whose `real`
+// is that communicator, so every `if (s->real) forward` path below forwards it unchanged.
+inline Shim* S(ncclComm_t c) {
+  if (is_shim(c)) return reinterpret_cast<Shim*>(c);
+  thread_local Shim foreign;
+  foreign.magic = 0;
+  foreign.real = c;
+  foreign.mine = nullptr;
+  return &foreign;
+}
 
 }  // namespace
 
@@ -250,7 +282,13 @@ extern "C" {
 uint64_t b200mpi_shim_calls(void) { return g_calls.load(); }
 uint64_t b200mpi_shim_forwarded(void) { return g_forwarded.load(); }
 
-ncclResult_t ncclGetVersion(int* v) { *v = 22809; return ncclSuccess; }
+ncclResult_t ncclGetVersion(int* v) {
+  if (forward_all() || g_in_real > 0 || g_forwarded.load()) {
+    if (auto f = REAL(ncclGetVersion, int*)) return f(v);
+  }
+  *v = 22809;  // the NCCL ABI level this shim implements
+  return ncclSuccess;
+}
 const char* ncclGetErrorString(ncclResult_t r) {
   switch (r) {
     case ncclSuccess: return "no error";
@@ -267,7 +305,7 @@ const char* ncclGetErrorString(ncclResult_t r) {
 const char* ncclGetLastError(ncclComm_t) { return g_last_error.c_str(); }
 
 ncclResult_t ncclGetUniqueId(ncclUniqueId* id) {
-  if (forward_all()) {
+  if (forward_all() || g_in_real > 0) {
     auto f = REAL(ncclGetUniqueId, ncclUniqueId*);
     if (f) return f(id);
   }
@@ -298,6 +336,10 @@ ncclResult_t ncclCommInitAll(ncclComm_t* comms, int ndev, const int* devlist) {
 }
 
 ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newcomm, const void* config) {
+  if (!is_shim(comm)) {  // internal call of real NCCL: its caller expects a real communicator back
+    auto f = REAL(ncclCommSplit, ncclComm_t, int, int, ncclComm_t*, const void*);
+    return f ? f(comm, color, key, newcomm, config) : err(ncclSystemError, "real ncclCommSplit missing");
+  }
   Shim* s = S(comm);
   if (s->real) {
     auto f = REAL(ncclCommSplit, ncclComm_t, int, int, ncclComm_t*, const void*);
@@ -330,14 +372,16 @@ ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newc
 ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t*, const void*, int) { return err(ncclInvalidUsage, "ncclCommShrink is not provided; re-form the communicator (elastic rescale re-spawns ranks)"); }
 
 static ncclResult_t destroy(ncclComm_t comm, const char* realname) {
+  if (!comm) return ncclSuccess;
+  if (!is_shim(comm)) { auto f = real_fn<ncclResult_t (*)(ncclComm_t)>(realname); return f ? f(comm) : ncclSuccess; }
   Shim* s = S(comm);
-  if (!s) return ncclSuccess;
   ncclResult_t r = ncclSuccess;
   if (s->real) { auto f = real_fn<ncclResult_t (*)(ncclComm_t)>(realname); if (f) r = f(s->real); }
   if (s->mine) {
     if (debug() && s->rank == 0) fprintf(stderr, "[b200mpi nccl shim] %s: %llu b200mpi kernel launches\n", s->id.c_str(), (unsigned long long)b200mpi_comm_launch_count(s->mine));
     b200mpi_comm_destroy(s->mine);
   }
+  s->magic = 0;
   delete s;
   return r;
 }
@@ -446,7 +490,7 @@ ncclResult_t ncclGroupStart(void) {
   g_group_depth++;
   // Forward only when a real communicator exists (or everything is forwarded); remember it so the
   // matching End is forwarded too and the real library never sees an unbalanced pair.
-  if (forward_all() || g_forwarded.load()) {
+  if (forward_all() || g_forwarded.load() || g_in_real > 0) {
     if (auto f = real_fn<ncclResult_t (*)()>("ncclGroupStart")) { g_group_fwd++; return f(); }
   }
   return ncclSuccess;
@@ -594,8 +638,17 @@ ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, nccl
   return queue_p2p(s, b200mpi_p2p_op_t{nullptr, buf, count * dt_size(dt), peer, 0}, st);
 }
 
-ncclResult_t ncclMemAlloc(void** ptr, size_t size) { return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemAlloc"); }
-ncclResult_t ncclMemFree(void* ptr) { return cudaFree(ptr) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemFree"); }
+// Real NCCL's allocations are VMM handles it later retains / registers: when a real communicator can be involved the
+// allocation must come from the real library (a cudaMalloc pointer makes its registration path fail with "invalid argument").
+static bool real_nccl_in_play() { return forward_all() || g_in_real > 0 || g_forwarded.load() > 0; }
+ncclResult_t ncclMemAlloc(void** ptr, size_t size) {
+  if (real_nccl_in_play()) { if (auto f = REAL(ncclMemAlloc, void**, size_t)) return f(ptr, size); }
+  return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemAlloc");
+}
+ncclResult_t ncclMemFree(void* ptr) {
+  if (real_nccl_in_play()) { if (auto f = REAL(ncclMemFree, void*)) return f(ptr); }
+  return cudaFree(ptr) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemFree");
+}
 ncclResult_t ncclCommRegister(const ncclComm_t c, void* buff, size_t size, void** handle) {
   Shim* s = S(c);
   if (s->real) { auto f = REAL(ncclCommRegister, ncclComm_t, void*, size_t, void**); return f(s->real, buff, size, handle); }
@@ -618,7 +671,15 @@ ncclResult_t ncclCommWindowDeregister(ncclComm_t c, void* win) {
   if (s->real) { auto f = REAL(ncclCommWindowDeregister, ncclComm_t, void*); return f ? f(s->real, win) : ncclSuccess; }
   return ncclSuccess;
 }
-ncclResult_t ncclDevCommCreate(ncclComm_t, const void*, void*) { return err(ncclInvalidUsage, "device-side communicators are not provided by the b200mpi shim"); }
-ncclResult_t ncclDevCommDestroy(ncclComm_t, const void*) { return ncclSuccess; }
+ncclResult_t ncclDevCommCreate(ncclComm_t c, const void* reqs, void* out) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclDevCommCreate, ncclComm_t, const void*, void*); return f ? f(s->real, reqs, out) : err(ncclInvalidUsage, "ncclDevCommCreate missing in real NCCL"); }
+  return err(ncclInvalidUsage, "device-side communicators are not provided by the b200mpi shim");
+}
+ncclResult_t ncclDevCommDestroy(ncclComm_t c, const void* dev) {
+  Shim* s = S(c);
+  if (s->real) { auto f = REAL(ncclDevCommDestroy, ncclComm_t, const void*); return f ? f(s->real, dev) : ncclSuccess; }
+  return ncclSuccess;
+}
 
 }  // extern "C"
