@@ -24,7 +24,7 @@ $(LIBDIR)/libb200mpi_nccl.so: csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) $(RUNT
 
 # tcgen05/TMA GEMM with fused BN statistics: a library of its own so that the experimental kernel cannot affect
 # the validated runtime library
-$(LIBDIR)/libb200mpi_gemm.so: csrc/kernels/gemm_bnstats.cu csrc/include/b200mpi.h
+$(LIBDIR)/libb200mpi_gemm.so: csrc/kernels/gemm_bnstats.cu csrc/kernels/gemm_bnstats_logic.h csrc/include/b200mpi.h
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared csrc/kernels/gemm_bnstats.cu -o $@
 
