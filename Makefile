@@ -118,5 +118,11 @@ tsan:
 	$(call san_build,tsan,-fsanitize=thread)
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
+	# device protocols executed by host threads (same templates / shared logic as the kernels) under ThreadSanitizer:
+	# every shared-memory, TMEM, mailbox and flag access must be ordered by the barriers the kernels use
+	$(SAN_CXX) -std=c++17 -O1 -g -fsanitize=thread -o build/san/tsan/gemm_pipeline_model csrc/tests/gemm_pipeline_model.cc -lpthread
+	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/gemm_pipeline_model
+	$(NVCC) -ccbin $(SAN_CXX) -std=c++17 -O1 -g $(ARCH) -Icsrc/include -Xcudafe --diag_suppress=20011,--diag_suppress=20014 -Xcompiler -fsanitize=thread -x cu csrc/tests/p2p_protocol_test.cu -o build/san/tsan/p2p_protocol_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread -ltsan
+	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/p2p_protocol_test
 
 .PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model
