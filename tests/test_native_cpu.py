@@ -250,3 +250,19 @@ def test_nccl_shim_pass_through_reaches_the_bundled_nccl_on_the_host():
     assert outs["auto"][1] == "True"                      # own id: minted by the shim, tagged
     assert outs["nccl"][1] == "False" and outs["nccl"][3] == "True"   # forwarded: a real NCCL id, bundled libnccl mapped
     assert int(outs["nccl"][2]) >= 22000
+
+
+def test_nccl_shim_exports_every_nccl_symbol_torch_imports():
+    """LD_PRELOAD only works if no ncclX call of libtorch can slip past the shim into the real library with one of our
+    handles: every nccl* symbol libtorch_cuda imports must be defined by libb200mpi_nccl.so."""
+    import torch
+    shim = os.path.join(REPO, "mpi_operator_b200/lib/libb200mpi_nccl.so")
+    lib = os.path.join(os.path.dirname(torch.__file__), "lib", "libtorch_cuda.so")
+    if not (os.path.exists(shim) and os.path.exists(lib)):
+        pytest.skip("libtorch_cuda.so or the shim is not available")
+    need = {ln.split()[-1] for ln in subprocess.run(["nm", "-D", "--undefined-only", lib], capture_output=True, text=True).stdout.splitlines()
+            if ln.split() and ln.split()[-1].startswith("nccl")}
+    have = {ln.split()[-1] for ln in subprocess.run(["nm", "-D", "--defined-only", shim], capture_output=True, text=True).stdout.splitlines()
+            if ln.split() and ln.split()[-1].startswith("nccl")}
+    assert need, "libtorch_cuda.so imports no nccl symbols?"
+    assert need <= have, f"shim is missing {sorted(need - have)}"
