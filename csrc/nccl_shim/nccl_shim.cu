@@ -75,6 +75,12 @@ bool forward_all() {
   return v == 1;
 }
 bool debug() { static int v = getenv("B200MPI_DEBUG") ? 1 : 0; return v; }
+// B200MPI_DEBUG=2: one stderr line per NCCL entry (with tests/mp_launch.py --log-dir: the last call of a failing rank)
+int trace_level() { static int v = getenv("B200MPI_DEBUG") ? atoi(getenv("B200MPI_DEBUG")) : 0; return v; }
+#define TRACE_CALL(fmt, ...)                                                                                   \
+  do {                                                                                                         \
+    if (trace_level() >= 2) fprintf(stderr, "[b200mpi nccl shim %d] %s " fmt "\n", (int)getpid(), __func__, ##__VA_ARGS__); \
+  } while (0)
 
 // libnccl calls some of its own public entry points through the PLT (objdump -R libnccl.so.2: ncclBroadcast,
 // ncclCommGetAsyncError, ncclCommRegister/Deregister, ncclCommWindowDeregister, ncclDevCommDestroy, ncclMemAlloc/Free,
@@ -221,6 +227,7 @@ ncclResult_t init_common(ncclComm_t* out, int nranks, const ncclUniqueId* id, in
                          bool have_config) {
   int dev = 0;
   cudaGetDevice(&dev);
+  TRACE_CALL("rank=%d/%d device=%d id=%s", rank, nranks, dev, id_to_job(id).c_str());
   auto* s = new Shim;
   s->rank = rank; s->world = nranks; s->device = dev; s->id = id_to_job(id);
   if (!forward_all() && nranks <= B200MPI_MAX_RANKS) {
@@ -372,6 +379,7 @@ ncclResult_t ncclCommSplit(ncclComm_t comm, int color, int key, ncclComm_t* newc
 ncclResult_t ncclCommShrink(ncclComm_t, int*, int, ncclComm_t*, const void*, int) { return err(ncclInvalidUsage, "ncclCommShrink is not provided; re-form the communicator (elastic rescale re-spawns ranks)"); }
 
 static ncclResult_t destroy(ncclComm_t comm, const char* realname) {
+  TRACE_CALL("%s", realname);
   if (!comm) return ncclSuccess;
   if (!is_shim(comm)) { auto f = real_fn<ncclResult_t (*)(ncclComm_t)>(realname); return f ? f(comm) : ncclSuccess; }
   Shim* s = S(comm);
@@ -487,6 +495,7 @@ static ncclResult_t queue_p2p(Shim* s, const b200mpi_p2p_op_t& op, cudaStream_t 
 }
 
 ncclResult_t ncclGroupStart(void) {
+  TRACE_CALL("depth=%d", g_group_depth + 1);
   g_group_depth++;
   // Forward only when a real communicator exists (or everything is forwarded); remember it so the
   // matching End is forwarded too and the real library never sees an unbalanced pair.
@@ -515,6 +524,7 @@ ncclResult_t ncclGroupSimulateEnd(void*) { return ncclSuccess; }
 
 ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
+  TRACE_CALL("count=%zu dt=%d op=%d rank=%d/%d %s", count, (int)dt, (int)op, s->rank, s->world, s->real ? "fwd" : "b200mpi");
   g_calls++;
   if (s->real) { auto f = REAL(ncclAllReduce, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, op, s->real, st); }
   b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
@@ -525,6 +535,7 @@ ncclResult_t ncclAllReduce(const void* send, void* recv, size_t count, ncclDataT
 
 ncclResult_t ncclBroadcast(const void* send, void* recv, size_t count, ncclDataType_t dt, int root, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
+  TRACE_CALL("count=%zu dt=%d root=%d rank=%d/%d", count, (int)dt, root, s->rank, s->world);
   g_calls++;
   if (s->real) { auto f = REAL(ncclBroadcast, const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, root, s->real, st); }
   const size_t bytes = count * dt_size(dt);
@@ -535,6 +546,7 @@ ncclResult_t ncclBcast(void* buf, size_t count, ncclDataType_t dt, int root, ncc
 
 ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType_t dt, ncclRedOp_t op, int root, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
+  TRACE_CALL("count=%zu dt=%d op=%d root=%d rank=%d/%d", count, (int)dt, (int)op, root, s->rank, s->world);
   g_calls++;
   if (s->real) { auto f = REAL(ncclReduce, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t); return f(send, recv, count, dt, op, root, s->real, st); }
   b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
@@ -550,6 +562,7 @@ ncclResult_t ncclReduce(const void* send, void* recv, size_t count, ncclDataType
 
 ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclDataType_t dt, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
+  TRACE_CALL("rank=%d/%d", s->rank, s->world);
   g_calls++;
   if (s->real) { auto f = REAL(ncclAllGather, const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t); return f(send, recv, sendcount, dt, s->real, st); }
   const size_t bytes = sendcount * dt_size(dt);
@@ -569,6 +582,7 @@ ncclResult_t ncclAllGather(const void* send, void* recv, size_t sendcount, ncclD
 
 ncclResult_t ncclReduceScatter(const void* send, void* recv, size_t recvcount, ncclDataType_t dt, ncclRedOp_t op, ncclComm_t c, cudaStream_t st) {
   Shim* s = S(c);
+  TRACE_CALL("rank=%d/%d", s->rank, s->world);
   g_calls++;
   if (s->real) { auto f = REAL(ncclReduceScatter, const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); return f(send, recv, recvcount, dt, op, s->real, st); }
   b200mpi_dtype_t bdt; b200mpi_op_t bop; float scale;
