@@ -2,7 +2,7 @@
 # First GPU call of the next round: diagnose the 8-GPU LD_PRELOAD shim failure with per-rank logs.
 # Usage: gpurun --gpus 8 --timeout 600 -- 'tools/gpu_session_next.sh 8'
 N=${1:-8}
-export B200MPI_NO_AUTOBUILD=1 B200MPI_DEBUG=1
+export B200MPI_NO_AUTOBUILD=1 B200MPI_DEBUG=2
 SHIM=$PWD/mpi_operator_b200/lib/libb200mpi_nccl.so
 mkdir -p gpurun_out/shim_n$N
 echo "=== DDP worker under LD_PRELOAD, N=$N (per-rank logs in gpurun_out/shim_n$N) ==="
