@@ -160,7 +160,7 @@ class DataParallelTrainer:
                  weight_decay: float = 0.0, nesterov: bool = False, bucket_bytes: Optional[int] = None,
                  autocast_dtype: Optional[torch.dtype] = torch.bfloat16, channels_last: bool = True,
                  cuda_graph: bool = True, fused_optimizer: bool = True, algo: Optional[str] = None,
-                 comm_backend: str = "b200mpi", bf16_params: Optional[bool] = None):
+                 comm_backend: str = "b200mpi", bf16_params: Optional[bool] = None, async_h2d: Optional[bool] = None):
         self.comm = comm
         self.device = torch.device("cuda", comm.device) if comm.device != "cpu" else torch.device("cpu")
         self._cuda = self.device.type == "cuda"
@@ -193,6 +193,12 @@ class DataParallelTrainer:
         self._launches_per_step = 0
         self._sync = True
         self._carry = False
+        # B200MPI_ASYNC_H2D=1: inputs go host -> staging buffer on a copy stream (overlapping the previous step's compute),
+        # then device -> device into the graph's static input; off by default until it has run on hardware
+        self.async_h2d = os.environ.get("B200MPI_ASYNC_H2D", "0") == "1" if async_h2d is None else bool(async_h2d)
+        self._copy_stream = torch.cuda.Stream(device=self.device) if (self.async_h2d and self._cuda) else None
+        self._stage_x = self._stage_y = None
+        self._pending_batch = None
         self._graph_ops: list = []   # collectives recorded in the CUDA graph: replays launch them without the host
         self._replays = 0
         if hasattr(comm, "add_stat_source"):
@@ -343,12 +349,64 @@ class DataParallelTrainer:
             self._static_y = torch.empty(y.shape, dtype=y.dtype, device=self.device)
             self._graph = None
 
-    def step(self, x, y):
-        """One optimizer step on a batch given as (pinned) host or device tensors."""
-        self._fault.on_step()
+    # ------------------------------------------------- input pipeline --
+    def prefetch(self, x, y) -> None:
+        """Start moving the NEXT batch to the device now (``async_h2d`` mode: on a copy stream, into one of two staging
+        buffers, overlapping whatever the compute stream is still doing); the following ``step()`` without arguments
+        trains on it. A loop that reads the loss every step keeps the copy off the critical path with
+
+            trainer.prefetch(x0, y0)
+            for i in range(n):
+                loss = trainer.step()                 # enqueue step i (inputs already on their way)
+                trainer.prefetch(x[i + 1], y[i + 1])  # H2D of the next batch runs under step i
+                print(float(loss))                    # only now wait for step i
+        """
         self._ensure_static(x, y)
-        self._static_x.copy_(x, non_blocking=True)
-        self._static_y.copy_(y, non_blocking=True)
+        if not (self.async_h2d and self._cuda):
+            self._pending_batch = (x, y)
+            return
+        if self._stage_x is None or self._stage_x[0].shape != x.shape or self._stage_x[0].dtype != x.dtype:
+            # staging buffers keep the HOST layout, so the H2D copy is one plain DMA; the layout change to channels-last
+            # happens in the device-to-device copy into the graph's static input
+            self._stage_x = [torch.empty(x.shape, dtype=x.dtype, device=self.device) for _ in range(2)]
+            self._stage_y = [torch.empty(y.shape, dtype=y.dtype, device=self.device) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [torch.cuda.Event() for _ in range(2)]
+            for ev in self._stage_free:
+                ev.record(torch.cuda.current_stream(self.device))
+            self._stage_idx = 0
+        k = self._stage_idx
+        self._stage_idx ^= 1
+        cs = self._copy_stream
+        cs.wait_event(self._stage_free[k])       # buffer k was last read by the D2D copy two steps ago
+        with torch.cuda.stream(cs):
+            self._stage_x[k].copy_(x, non_blocking=True)
+            self._stage_y[k].copy_(y, non_blocking=True)
+            self._stage_ready[k].record(cs)
+        self._pending_batch = k
+
+    def _consume_batch(self) -> None:
+        """Make the prefetched batch the graph's static input (main stream)."""
+        pb, self._pending_batch = self._pending_batch, None
+        if pb is None:
+            raise RuntimeError("step() without arguments needs a prefetch() first")
+        if isinstance(pb, tuple):                 # synchronous mode: the copy happens here, on the compute stream
+            self._static_x.copy_(pb[0], non_blocking=True)
+            self._static_y.copy_(pb[1], non_blocking=True)
+            return
+        main = torch.cuda.current_stream(self.device)
+        main.wait_event(self._stage_ready[pb])
+        self._static_x.copy_(self._stage_x[pb], non_blocking=True)
+        self._static_y.copy_(self._stage_y[pb], non_blocking=True)
+        self._stage_free[pb].record(main)
+
+    def step(self, x=None, y=None):
+        """One optimizer step on a batch given as (pinned) host or device tensors; without arguments, on the batch handed
+        to ``prefetch()``. Returns the loss as a device scalar (``float(loss)`` is the D2H read)."""
+        self._fault.on_step()
+        if x is not None:
+            self.prefetch(x, y)
+        self._consume_batch()
         if not self.use_graph or not self._cuda or not self._sync or self._carry:
             n0 = self.comm.launch_count
             self._fwd_bwd(self._static_x, self._static_y)

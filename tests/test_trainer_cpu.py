@@ -212,3 +212,23 @@ def test_graph_replay_accounting_folds_recaptures():
                                   {"op": "allreduce", "algo": "oneshot", "calls": 1, "bytes": 4}], 2
     got = {(o["op"], o["algo"]): (o["calls"], o["bytes"]) for o in sources[0]()}
     assert got == {("allreduce_sgd", "nvls"): (51, 5020), ("allreduce", "oneshot"): (2, 8)}
+
+
+def test_prefetch_then_step_without_arguments_matches_step_with_arguments():
+    """Input pipeline API: ``prefetch(x, y); step()`` trains on exactly the batch ``step(x, y)`` would have used (on CPU the
+    copy is synchronous; on a GPU with async_h2d it goes through the copy stream and staging buffers)."""
+    data = batches(3)
+    a = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, channels_last=False, cuda_graph=False, autocast_dtype=None)
+    b = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.1, channels_last=False, cuda_graph=False, autocast_dtype=None,
+                            async_h2d=True)   # no CUDA here: the flag must degrade to the synchronous path
+    b.prefetch(*data[0])
+    for i, (x, y) in enumerate(data):
+        la = float(a.step(x, y))
+        lb = float(b.step())
+        if i + 1 < len(data):
+            b.prefetch(*data[i + 1])
+        assert la == lb
+    with pytest.raises(RuntimeError, match="prefetch"):
+        b.step()
+    for p, q in zip(a.model.parameters(), b.model.parameters()):
+        assert torch.equal(p, q)

@@ -6,9 +6,11 @@ mkdir -p gpurun_out
 echo "=== 1. GPU tier as the driver runs it ==="
 timeout 600 python -m pytest tests -x -q -m gpu --timeout=300 2>&1 | tail -5
 echo "=== 2. bf16 parameter shadow: numerics (xfail marker removed by --runxfail) + bench ==="
-timeout 200 python -m pytest tests/test_trainer_gpu.py -q --runxfail -k bf16_params --timeout=150 2>&1 | tail -5
+timeout 300 python -m pytest tests/test_trainer_gpu.py -q --runxfail -k "bf16_params or async_h2d or counters" --timeout=200 2>&1 | tail -5
 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_default.json
 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_bf16params.json
+B200MPI_ASYNC_H2D=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_asynch2d.json
+B200MPI_ASYNC_H2D=1 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_asynch2d_bf16params.json
 echo "=== 3. tcgen05 GEMM + BN statistics (each case in its own process, bounded waits) ==="
 B200MPI_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_gemm_bnstats_gpu.py -q --timeout=200 2>&1 | tail -15
 echo "=== 4. bench with the tensor-core 1x1 path (only meaningful if step 3 passed) ==="
