@@ -133,6 +133,11 @@ def main() -> int:
     rank, world = info.rank, info.world_size
     dev = info.local_rank % max(1, torch.cuda.device_count())
     torch.cuda.set_device(dev)
+    if os.environ.get("B200MPI_BIND_NUMA") == "1":   # experiment: first-touch the pinned batches on the GPU's NUMA node
+        from mpi_operator_b200.utils.affinity import bind_to_gpu
+        bound = bind_to_gpu(dev)
+        if rank == 0:
+            print(f"[bench] cpu affinity -> {len(bound) if bound else 'unchanged'}", file=sys.stderr)
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234)
     comm = Communicator.create(rank, world, dev, info.job_id)

@@ -103,3 +103,20 @@ def test_horovod_api_on_the_cpu_backend_under_mpirun(np_):
                        capture_output=True, text=True, timeout=180, env=env, cwd="/tmp")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("hvd cpu ok") == np_
+
+
+def test_affinity_helper_is_a_safe_no_op_without_nvml(monkeypatch):
+    from mpi_operator_b200.utils import affinity
+    before = os.sched_getaffinity(0)
+    assert affinity.bind_to_gpu(0) is None or affinity.bind_to_gpu(0) <= before
+    monkeypatch.setenv("B200MPI_NO_AFFINITY", "1")
+    assert affinity.bind_to_gpu(0) is None
+    monkeypatch.delenv("B200MPI_NO_AFFINITY")
+    monkeypatch.setattr(affinity, "gpu_cpu_set", lambda i: {min(before)})     # a GPU-local set inside the allowed set
+    got = affinity.bind_to_gpu(0)
+    try:
+        assert (got == {min(before)} and os.sched_getaffinity(0) == {min(before)}) or len(before) == 1
+        monkeypatch.setattr(affinity, "gpu_cpu_set", lambda i: {10 ** 6})     # disjoint from what the cgroup allows
+        assert affinity.bind_to_gpu(0) is None
+    finally:
+        os.sched_setaffinity(0, before)
