@@ -16,3 +16,11 @@ echo "=== experimental point-to-point (B200MPI_P2P=1), N=$N ==="
 mkdir -p gpurun_out/p2p_n$N
 B200MPI_P2P=1 timeout 150 python tests/mp_launch.py -n $N --timeout 120 --log-dir gpurun_out/p2p_n$N tests/p2p_worker.py
 for f in gpurun_out/p2p_n$N/*.log; do echo "--- $f"; tail -6 $f; done
+echo "=== bench at N=$N: default vs async input pipeline (+ NUMA binding) ==="
+PORT=29611
+for cfg in "" "B200MPI_ASYNC_H2D=1" "B200MPI_ASYNC_H2D=1 B200MPI_BIND_NUMA=1"; do
+  PORT=$((PORT+1))
+  echo "--- cfg: [$cfg]"
+  env $cfg timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
+    bench.py --gpus $N --steps 30 --warmup 5 2>gpurun_out/bench_n${N}_$PORT.err | tail -1 | tee gpurun_out/bench_n${N}_$PORT.json
+done
