@@ -33,6 +33,34 @@ def fused_bn_available(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
 
 _WS_CACHE = {}
 
+# ``num_batches_tracked`` bookkeeping: one 1-element add kernel per BN layer per step (104 launches for ResNet-101). Inside
+# ``defer_counters()`` the fused ops only collect the counters; the caller bumps them all with one multi-tensor add.
+_DEFERRED_COUNTERS = None
+
+
+class defer_counters:
+    """``with defer_counters() as pending: out = model(x)`` then ``torch._foreach_add_(pending, 1)``."""
+
+    def __enter__(self):
+        global _DEFERRED_COUNTERS
+        self._prev = _DEFERRED_COUNTERS
+        _DEFERRED_COUNTERS = []
+        return _DEFERRED_COUNTERS
+
+    def __exit__(self, *exc):
+        global _DEFERRED_COUNTERS
+        _DEFERRED_COUNTERS = self._prev
+        return False
+
+
+def _count_batch(bn: torch.nn.BatchNorm2d) -> None:
+    if bn.num_batches_tracked is None:
+        return
+    if _DEFERRED_COUNTERS is not None:
+        _DEFERRED_COUNTERS.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked.add_(1)
+
 
 def _ws(bn: torch.nn.BatchNorm2d, device) -> torch.Tensor:
     """Scratch for per-CTA partial sums + per-channel coefficients. BN kernels of one stream run
@@ -109,8 +137,7 @@ def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = N
     if fused_bn_available(x, bn) and (residual is None or (residual.dtype == torch.bfloat16 and residual.shape == x.shape)):
         if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
             residual = residual.contiguous(memory_format=torch.channels_last)
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
         return _BNAct.apply(x, residual, bn.weight, bn.bias, bn.running_mean, bn.running_var, _ws(bn, x.device), bn.eps,
                             bn.momentum, relu, getattr(bn, "_b200_grad_ready", None))
     out = bn(x)
@@ -204,8 +231,7 @@ def conv_bn_act(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, x: torch.Tensor
                                       and residual.shape[1] == conv.out_channels and residual.shape[2:] == x.shape[2:]))):
         if residual is not None and not residual.is_contiguous(memory_format=torch.channels_last):
             residual = residual.contiguous(memory_format=torch.channels_last)
-        if bn.num_batches_tracked is not None:
-            bn.num_batches_tracked.add_(1)
+        _count_batch(bn)
         w2d = conv.weight.to(torch.bfloat16).reshape(conv.out_channels, conv.in_channels)
         return _Conv1x1BNAct.apply(x, residual, w2d, bn.weight, bn.bias, bn.running_mean, bn.running_var, _ws(bn, x.device), bn.eps,
                                    bn.momentum, relu, getattr(bn, "_b200_grad_ready", None))

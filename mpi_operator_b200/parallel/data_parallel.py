@@ -199,6 +199,7 @@ class DataParallelTrainer:
         self._copy_stream = torch.cuda.Stream(device=self.device) if (self.async_h2d and self._cuda) else None
         self._stage_x = self._stage_y = None
         self._pending_batch = None
+        self._defer_nbt = os.environ.get("B200MPI_DEFER_NBT", "0") == "1"   # experiment: batch the BN step counters
         self._graph_ops: list = []   # collectives recorded in the CUDA graph: replays launch them without the host
         self._replays = 0
         if hasattr(comm, "add_stat_source"):
@@ -321,12 +322,17 @@ class DataParallelTrainer:
             st.zero_grad()
         for b in st.buckets:
             b.pending = len(b.params)
-        if self.autocast_dtype is not None:
-            with torch.autocast(self.device.type, dtype=self.autocast_dtype):
-                out = self.model(x)
-                loss = self.loss_fn(out, y)
-        else:
-            loss = self.loss_fn(self.model(x), y)
+        import contextlib
+        from ..ops import fused_bn
+        with (fused_bn.defer_counters() if self._defer_nbt else contextlib.nullcontext()) as counters:
+            if self.autocast_dtype is not None:
+                with torch.autocast(self.device.type, dtype=self.autocast_dtype):
+                    out = self.model(x)
+                    loss = self.loss_fn(out, y)
+            else:
+                loss = self.loss_fn(self.model(x), y)
+        if counters:   # one multi-tensor add instead of one tiny kernel per BN layer
+            torch._foreach_add_(counters, 1)
         loss.backward()
         self._loss.copy_(loss.detach())
         if not self._sync:   # local accumulation only (Horovod: backward_passes_per_step > 1)

@@ -16,7 +16,9 @@ B200MPI_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_gemm_bnstats_g
 echo "=== 4. bench with the tensor-core 1x1 path (only meaningful if step 3 passed) ==="
 B200MPI_FUSED_CONV1X1=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1.json
 B200MPI_FUSED_CONV1X1=1 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1_bf16params.json
+echo "=== 4b. everything that passed, together ==="
+B200MPI_ASYNC_H2D=1 B200MPI_BF16_PARAMS=1 B200MPI_DEFER_NBT=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_all_flags.json
 echo "=== 5. launch list of the best configuration ==="
-B200MPI_BF16_PARAMS=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 5000 -c 2400 --csv --log-file gpurun_out/launches_bf16params.csv \
+B200MPI_BF16_PARAMS=1 B200MPI_DEFER_NBT=1 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -s 5000 -c 2400 --csv --log-file gpurun_out/launches_bf16params.csv \
   python bench.py --steps 3 --warmup 3 --no-graph > gpurun_out/ncu_bench.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_bf16params.csv 2>/dev/null | head -30
