@@ -20,21 +20,42 @@ from .store import ADDED, DELETED, MODIFIED, ObjectStore
 
 
 class Indexer:
+    """Thread-safe object cache keyed by namespace/name, with an inverted index over labels: a reconcile lists "the pods
+    of this job" (one label pair) several times and must not scan, sort or copy every object in the cache for it."""
+
     def __init__(self):
         self._lock = threading.RLock()
         self._items: Dict[str, dict] = {}
+        self._by_label: Dict[tuple, set] = {}
+
+    def _unindex(self, key: str, obj: dict) -> None:
+        for pair in (M.meta(obj).get("labels") or {}).items():
+            keys = self._by_label.get(pair)
+            if keys is not None:
+                keys.discard(key)
+                if not keys:
+                    del self._by_label[pair]
 
     # Cached objects are replaced wholesale, never mutated in place, so copies are taken outside the lock.
     def add(self, obj: dict) -> None:
         mine = copy.deepcopy(obj)
+        key = M.key_of(obj)
         with self._lock:
-            self._items[M.key_of(obj)] = mine
+            old = self._items.get(key)
+            if old is not None:
+                self._unindex(key, old)
+            self._items[key] = mine
+            for pair in (M.meta(mine).get("labels") or {}).items():
+                self._by_label.setdefault(pair, set()).add(key)
 
     update = add
 
     def delete(self, obj: dict) -> None:
+        key = M.key_of(obj)
         with self._lock:
-            self._items.pop(M.key_of(obj), None)
+            old = self._items.pop(key, None)
+            if old is not None:
+                self._unindex(key, old)
 
     def get_by_key(self, key: str) -> Optional[dict]:
         with self._lock:
@@ -42,11 +63,18 @@ class Indexer:
         return copy.deepcopy(o) if o is not None else None
 
     def list(self, namespace: str = "", selector: Optional[Dict[str, str]] = None) -> List[dict]:
-        """Sorted by key. Namespace and label selector are applied before anything is copied: a reconcile lists
-        "the pods of this job" several times and must not pay for every object in the cache."""
+        """Sorted by key. Equality selectors start from the smallest matching label bucket; namespace and the full selector
+        are applied before anything is copied."""
         with self._lock:
+            if selector:
+                buckets = [self._by_label.get(pair) for pair in selector.items()]
+                if any(b is None for b in buckets):
+                    return []
+                keys = sorted(min(buckets, key=len))
+            else:
+                keys = sorted(self._items)
             hits = []
-            for key in sorted(self._items):
+            for key in keys:
                 o = self._items[key]
                 if namespace and M.namespace_of(o) != namespace:
                     continue

@@ -210,7 +210,9 @@ class NodeAgent:
             self._sync_jobs()
             self._pods_by_owner = None   # snapshot is only valid inside _sync_jobs
             self._schedule()
+            self._flush_slots()          # launchers started below read the slot map of their job
             self._sync_pods()
+            self._flush_slots()
             metrics.gpu_slots_free.set(self.alloc.free_gpus)
             metrics.ranks_active.set(sum(1 for p in self._procs.values() if p.popen is not None and p.popen.poll() is None))
 
@@ -532,6 +534,16 @@ class NodeAgent:
         return os.path.join(self.state_dir, "jobs", ns, job_name, "slots.json")
 
     def _write_all_slots(self) -> None:
+        """Mark the per-job slot maps stale; they are rewritten once per tick (before pods are started and at the end of the
+        tick) instead of once per pod event — each rewrite lists every pod."""
+        self._slots_dirty = True
+
+    def _flush_slots(self) -> None:
+        if getattr(self, "_slots_dirty", False):
+            self._slots_dirty = False
+            self._write_all_slots_now()
+
+    def _write_all_slots_now(self) -> None:
         """hostname -> GPU list per MPIJob, read by the native mpirun to pin ranks."""
         by_job: Dict[tuple, Dict[str, List[int]]] = {}
         for pod in self.store.list("pods"):

@@ -255,3 +255,29 @@ def test_event_ttl_prunes_old_events():
     assert rec.prune(now=time.time() + 3600) == 2 and s.list("events") == []
     rec.event(job, "Normal", "MPIJobRunning", "running")      # the correlator's stale entry falls back to a fresh event
     assert len(s.list("events")) == 1
+
+
+def test_indexer_label_index_tracks_updates_and_deletes():
+    from mpi_operator_b200.client.informers import Indexer
+    ix = Indexer()
+
+    def pod(name, ns="default", **labels):
+        return {"metadata": {"name": name, "namespace": ns, "labels": dict(labels)}}
+    ix.add(pod("a", job="j1", role="worker"))
+    ix.add(pod("b", job="j1", role="launcher"))
+    ix.add(pod("c", job="j2", role="worker"))
+    ix.add(pod("d", ns="other", job="j1", role="worker"))
+    names = lambda objs: [o["metadata"]["name"] for o in objs]  # noqa: E731
+    assert names(ix.list("default", {"job": "j1"})) == ["a", "b"]
+    assert names(ix.list("", {"job": "j1", "role": "worker"})) == ["a", "d"]          # sorted by namespace/name key
+    assert ix.list("default", {"job": "nope"}) == [] and ix.list("default", {"missing": "x"}) == []
+    assert names(ix.list("default")) == ["a", "b", "c"]
+    ix.update(pod("a", job="j2", role="worker"))                                        # relabelled: leaves j1, joins j2
+    assert names(ix.list("default", {"job": "j1"})) == ["b"] and names(ix.list("default", {"job": "j2"})) == ["a", "c"]
+    ix.delete(pod("c"))
+    assert names(ix.list("default", {"job": "j2"})) == ["a"]
+    ix.delete(pod("a"))
+    assert ix.list("default", {"job": "j2"}) == [] and ("job", "j2") not in ix._by_label
+    got = ix.list("default", {"job": "j1"})[0]
+    got["metadata"]["labels"]["job"] = "mutated"                                        # callers get copies
+    assert names(ix.list("default", {"job": "j1"})) == ["b"]
