@@ -59,6 +59,7 @@ class ObjectStore:
         # the whole store); the journal is folded into a fresh snapshot every kCompactEvery records and at load time.
         self._journal: List[str] = []
         self._journal_records = 0
+        self._wal = None
         if persist_path and (os.path.exists(persist_path) or os.path.exists(persist_path + ".wal")):
             self._load()
 
@@ -272,21 +273,40 @@ class ObjectStore:
                     if compact:
                         self._write_snapshot(snap)
                     elif lines:
-                        with open(self._persist_path + ".wal", "a") as f:
-                            f.write("\n".join(lines) + "\n")
+                        if self._wal is None:   # kept open: one write + flush per batch of records, no open/close
+                            self._wal = open(self._persist_path + ".wal", "a")
+                        self._wal.write("\n".join(lines) + "\n")
+                        self._wal.flush()
                         self._journal_records += len(lines)
-                except OSError:
-                    pass  # state dir removed underneath us (shutdown): persistence is best effort
+                except (OSError, ValueError):
+                    self._wal = None  # state dir removed underneath us (shutdown): persistence is best effort
             finally:
                 self._save_lock.release()
             if not self._journal:
                 return
+
+    def close(self) -> None:
+        """Flush pending journal records and release the journal file."""
+        self._save()
+        with self._save_lock:
+            if self._wal is not None:
+                try:
+                    self._wal.close()
+                except OSError:
+                    pass
+                self._wal = None
 
     def _write_snapshot(self, snap: dict) -> None:
         tmp = f"{self._persist_path}.tmp{os.getpid()}"
         with open(tmp, "w") as f:
             json.dump(snap, f)
         os.replace(tmp, self._persist_path)
+        if self._wal is not None:
+            try:
+                self._wal.close()
+            except OSError:
+                pass
+            self._wal = None
         try:
             os.unlink(self._persist_path + ".wal")   # records up to snap["rv"] are in the snapshot now
         except OSError:

@@ -188,6 +188,7 @@ class Operator:
         self.agent.stop()
         self.informers.stop()
         self.elector.release()
+        self.store.close()
 
     # ------------------------------------------------------------- serving --
     def serve(self, listen: str, block: bool = False):
