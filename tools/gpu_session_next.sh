@@ -24,3 +24,7 @@ for cfg in "" "B200MPI_ASYNC_H2D=1" "B200MPI_ASYNC_H2D=1 B200MPI_BIND_NUMA=1"; d
   env $cfg timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $PORT \
     bench.py --gpus $N --steps 30 --warmup 5 2>gpurun_out/bench_n${N}_$PORT.err | tail -1 | tee gpurun_out/bench_n${N}_$PORT.json
 done
+if [ "$N" = "8" ]; then
+  echo "=== elastic 4 -> 8 -> 4 on GPUs, timed ==="
+  timeout 300 python benchmarks/elastic_demo.py --total-steps 1500 --step-sleep 0.005 --out gpurun_out/elastic_demo_gpu.json 2>&1 | tail -2
+fi
