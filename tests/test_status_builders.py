@@ -177,3 +177,23 @@ def test_sync_launcher_scheduling_directives():
     assert t["metadata"]["labels"] == {"a": "1", "b": "2"} and t["metadata"]["annotations"] == {"k": "v"}
     assert t["spec"]["nodeSelector"] == {"foo": "bar"} and t["spec"]["tolerations"] == [{"key": "gpu"}]
     assert t["spec"]["schedulingGates"] == [{"name": "kueue"}]
+
+
+def test_restart_policy_replica_level_wins_exit_code_degrades_and_template_value_warns():
+    """the replica-level restartPolicy wins; ExitCode -> Never; a restartPolicy in the pod template is
+    overridden with a Warning SetPodTemplateRestartPolicy event (controller.go:1609-1616,1693-1699)."""
+    from mpi_operator_b200.api.defaults import set_defaults_mpijob
+    from mpi_operator_b200.controller.events import FakeRecorder
+    job = set_defaults_mpijob(new_mpijob("foo", workers=1))
+    job.spec.replica("Launcher").restart_policy = "ExitCode"
+    job.spec.replica("Launcher").template["spec"]["restartPolicy"] = "Always"
+    job.spec.replica("Worker").restart_policy = "OnFailure"
+    rec = FakeRecorder()
+    t = B.new_launcher_pod_template(job, recorder=rec)
+    assert t["spec"]["restartPolicy"] == "Never"
+    assert rec.events == ["Warning SetPodTemplateRestartPolicy Restart policy in pod template overridden by restart policy in replica spec"]
+    assert B.new_worker(job, 0)["spec"]["restartPolicy"] == "OnFailure"
+    rec2 = FakeRecorder()
+    job.spec.replica("Launcher").template["spec"].pop("restartPolicy")
+    B.new_launcher_pod_template(job, recorder=rec2)
+    assert rec2.events == []
