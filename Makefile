@@ -37,9 +37,9 @@ $(BINDIR)/mpirun: csrc/spawner/mpirun.cc
 	ln -sf mpirun $(BINDIR)/mpiexec.hydra
 	ln -sf mpirun $(BINDIR)/orterun
 
-$(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
+$(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_internal.h csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
 	@mkdir -p $(LIBDIR) mpi_operator_b200/include
-	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/runtime/rendezvous.cc -lrt -lpthread
+	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/runtime/rendezvous.cc -lrt -lpthread
 	cp csrc/mpi_shim/mpi.h mpi_operator_b200/include/mpi.h
 
 $(BINDIR)/pi: examples/pi/pi.cc $(LIBDIR)/libmpi.so
@@ -76,12 +76,13 @@ sanitize: all
 
 # Host-side runtime under the compiler sanitizers: launcher, shm rendezvous, libmpi shim.
 SAN_CXX  ?= /usr/bin/g++
-SAN_SRCS := csrc/mpi_shim/mpi_shim.cc csrc/runtime/rendezvous.cc
+SAN_SRCS := csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/runtime/rendezvous.cc
 define san_build
 	@mkdir -p build/san/$(1)
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -o build/san/$(1)/mpirun csrc/spawner/mpirun.cc
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/mpi_stress csrc/tests/mpi_stress.cc $(SAN_SRCS) -lrt -lpthread
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/pi examples/pi/pi.cc $(SAN_SRCS) -lrt -lpthread
+	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/mpi_p2p_test csrc/tests/mpi_p2p_test.cc $(SAN_SRCS) -lrt -lpthread
 endef
 
 # launch planning / counters of the runtime, checked on the host (no GPU): includes comm.cc, kernels come from the .so
@@ -89,6 +90,13 @@ test_comm_host: $(LIBDIR)/libb200mpi.so
 	@mkdir -p build/san
 	$(NVCC) -std=c++17 -O1 $(ARCH) -Icsrc/include -x cu csrc/tests/comm_host_test.cu -o build/san/comm_host_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread
 	build/san/comm_host_test
+
+# MPI point-to-point / v-collective semantics of the libmpi shim on 4 ranks
+test_mpi_p2p: native
+	@mkdir -p build/san
+	$(CXX) -std=c++17 -O2 -Wall -Impi_operator_b200/include -o build/san/mpi_p2p_test csrc/tests/mpi_p2p_test.cc -L$(LIBDIR) -lmpi -Wl,-rpath,$(abspath $(LIBDIR))
+	$(BINDIR)/mpirun -n 4 build/san/mpi_p2p_test
+	$(BINDIR)/mpirun -n 1 build/san/mpi_p2p_test
 
 # the point-to-point protocol of p2p.cu run with host threads instead of CTAs (same template, host platform)
 test_p2p_protocol: $(LIBDIR)/libb200mpi.so
@@ -113,6 +121,7 @@ asan:
 	$(call san_build,asan,-fsanitize=address$(comma)undefined -fno-sanitize-recover=undefined)
 	ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 build/san/asan/mpirun -n 4 build/san/asan/mpi_stress 200
 	build/san/asan/mpirun -n 2 --tag-output build/san/asan/pi
+	build/san/asan/mpirun -n 4 build/san/asan/mpi_p2p_test
 
 tsan:
 	$(call san_build,tsan,-fsanitize=thread)
@@ -125,4 +134,4 @@ tsan:
 	$(NVCC) -ccbin $(SAN_CXX) -std=c++17 -O1 -g $(ARCH) -Icsrc/include -Xcudafe --diag_suppress=20011,--diag_suppress=20014 -Xcompiler -fsanitize=thread -x cu csrc/tests/p2p_protocol_test.cu -o build/san/tsan/p2p_protocol_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread -ltsan
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/p2p_protocol_test
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model test_mpi_p2p

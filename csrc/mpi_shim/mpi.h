@@ -17,7 +17,8 @@ extern "C" {
 typedef int MPI_Comm;
 typedef int MPI_Datatype;
 typedef int MPI_Op;
-typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR, count_; } MPI_Status;
+typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR, count_; } MPI_Status;  /* count_: received bytes */
+typedef int MPI_Request;
 
 #define MPI_COMM_WORLD 0
 #define MPI_COMM_SELF 1
@@ -34,6 +35,15 @@ typedef struct { int MPI_SOURCE, MPI_TAG, MPI_ERROR, count_; } MPI_Status;
 #define MPI_MAX_ERROR_STRING 256
 #define MPI_IN_PLACE ((void*)1)
 #define MPI_STATUS_IGNORE ((MPI_Status*)0)
+#define MPI_STATUSES_IGNORE ((MPI_Status*)0)
+#define MPI_REQUEST_NULL (-1)
+#define MPI_PROC_NULL (-2)
+#define MPI_UNDEFINED (-32766)
+#define MPI_TAG_UB 0x3fffffff
+#define MPI_ERR_TRUNCATE 14
+#define MPI_ERR_RANK 6
+#define MPI_ERR_TAG 4
+#define MPI_ERR_REQUEST 19
 #define MPI_ANY_SOURCE (-1)
 #define MPI_ANY_TAG (-1)
 
@@ -80,6 +90,34 @@ int MPI_Scatter(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void*
                 MPI_Datatype recvtype, int root, MPI_Comm comm);
 int MPI_Alltoall(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, int recvcount,
                  MPI_Datatype recvtype, MPI_Comm comm);
+
+
+/* point-to-point: messages travel as datagrams between per-rank abstract UNIX sockets (mpi_p2p.cc); sends are eager
+ * (buffered at the receiver), matching follows the MPI non-overtaking rule per (source, tag, communicator) */
+int MPI_Send(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm);
+int MPI_Ssend(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm);
+int MPI_Recv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Status* status);
+int MPI_Sendrecv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, int dest, int sendtag, void* recvbuf, int recvcount,
+                 MPI_Datatype recvtype, int source, int recvtag, MPI_Comm comm, MPI_Status* status);
+int MPI_Isend(const void* buf, int count, MPI_Datatype datatype, int dest, int tag, MPI_Comm comm, MPI_Request* request);
+int MPI_Irecv(void* buf, int count, MPI_Datatype datatype, int source, int tag, MPI_Comm comm, MPI_Request* request);
+int MPI_Wait(MPI_Request* request, MPI_Status* status);
+int MPI_Waitall(int count, MPI_Request* requests, MPI_Status* statuses);
+int MPI_Test(MPI_Request* request, int* flag, MPI_Status* status);
+int MPI_Probe(int source, int tag, MPI_Comm comm, MPI_Status* status);
+int MPI_Iprobe(int source, int tag, MPI_Comm comm, int* flag, MPI_Status* status);
+int MPI_Get_count(const MPI_Status* status, MPI_Datatype datatype, int* count);
+
+/* vector collectives and scans */
+int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts, const int* displs,
+                   MPI_Datatype recvtype, MPI_Comm comm);
+int MPI_Gatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts, const int* displs,
+                MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Scatterv(const void* sendbuf, const int* sendcounts, const int* displs, MPI_Datatype sendtype, void* recvbuf, int recvcount,
+                 MPI_Datatype recvtype, int root, MPI_Comm comm);
+int MPI_Reduce_scatter_block(const void* sendbuf, void* recvbuf, int recvcount, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm);
+int MPI_Scan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm);
+int MPI_Exscan(const void* sendbuf, void* recvbuf, int count, MPI_Datatype datatype, MPI_Op op, MPI_Comm comm);
 
 #ifdef __cplusplus
 }

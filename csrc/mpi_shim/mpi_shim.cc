@@ -16,9 +16,11 @@
 
 #include "../runtime/rendezvous.h"
 
+#include "mpi_internal.h"
+
 using b200mpi::Rendezvous;
 
-namespace {
+namespace b200mpi_mpi {
 Rendezvous* g_rv = nullptr;
 int g_rank = 0, g_size = 1;
 bool g_init = false, g_final = false;
@@ -103,7 +105,8 @@ int check(MPI_Comm c) {
   if (c != MPI_COMM_WORLD && c != MPI_COMM_SELF) return MPI_ERR_COMM;
   return MPI_SUCCESS;
 }
-}  // namespace
+}  // namespace b200mpi_mpi
+using namespace b200mpi_mpi;
 
 extern "C" {
 
@@ -118,6 +121,8 @@ int MPI_Init(int*, char***) {
     g_rv = new Rendezvous;
     std::string err;
     if (g_rv->attach(id, g_rank, g_size, -1, g_timeout_ms, &err)) { fail("MPI_Init: " + err); return MPI_ERR_OTHER; }
+    if (p2p_init()) return MPI_ERR_OTHER;
+    if (g_rv->barrier(g_timeout_ms, &err)) { fail("MPI_Init: " + err); return MPI_ERR_OTHER; }   // every message socket is bound
   }
   g_init = true;
   return MPI_SUCCESS;
@@ -133,6 +138,7 @@ int MPI_Finalize(void) {
   if (g_rv) {
     std::string err;
     g_rv->barrier(g_timeout_ms, &err);
+    p2p_shutdown();
     g_rv->detach(g_rank == 0);
     delete g_rv;
     g_rv = nullptr;

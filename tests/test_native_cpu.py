@@ -266,3 +266,12 @@ def test_nccl_shim_exports_every_nccl_symbol_torch_imports():
             if ln.split() and ln.split()[-1].startswith("nccl")}
     assert need, "libtorch_cuda.so imports no nccl symbols?"
     assert need <= have, f"shim is missing {sorted(need - have)}"
+
+
+def test_libmpi_point_to_point_and_vector_collectives():
+    """`make test_mpi_p2p`: MPI_Send/Recv/Isend/Irecv/Wait/Test/Probe/Sendrecv, Gatherv/Scatterv/Allgatherv, Scan/Exscan,
+    Reduce_scatter_block of the libmpi shim on 4 ranks and on 1 rank (csrc/tests/mpi_p2p_test.cc): head-to-head 8 MiB sends
+    do not deadlock, an eager send is deliverable before the receiver's first call, same-tag messages do not overtake."""
+    r = subprocess.run(["make", "test_mpi_p2p"], cwd=REPO, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "all checks passed on 4 ranks" in r.stdout and "all checks passed on 1 ranks" in r.stdout
