@@ -28,7 +28,7 @@ $(LIBDIR)/libb200mpi_gemm.so: csrc/kernels/gemm_bnstats.cu csrc/kernels/gemm_bns
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared csrc/kernels/gemm_bnstats.cu -o $@
 
-native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi
+native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi $(BINDIR)/pingpong
 
 $(BINDIR)/mpirun: csrc/spawner/mpirun.cc
 	@mkdir -p $(BINDIR)
@@ -43,6 +43,9 @@ $(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi
 	cp csrc/mpi_shim/mpi.h mpi_operator_b200/include/mpi.h
 
 $(BINDIR)/pi: examples/pi/pi.cc $(LIBDIR)/libmpi.so
+	$(CXX) -std=c++17 -O2 -Impi_operator_b200/include -o $@ $< -L$(LIBDIR) -lmpi -Wl,-rpath,'$$ORIGIN/../lib'
+
+$(BINDIR)/pingpong: examples/mpi-ring/pingpong.cc $(LIBDIR)/libmpi.so
 	$(CXX) -std=c++17 -O2 -Impi_operator_b200/include -o $@ $< -L$(LIBDIR) -lmpi -Wl,-rpath,'$$ORIGIN/../lib'
 
 sass: $(LIBDIR)/libb200mpi.so

@@ -103,6 +103,20 @@ def test_pi_job_hydra_flavours_run_through_image_entrypoint(op, flavour, hostfil
 
 
 @needs_native
+def test_generic_mpi_program_with_point_to_point_runs_as_an_mpijob(op):
+    """examples/mpi-ring/ring.yaml: a token ring + ping-pong (MPI_Send/MPI_Recv) on 4 ranks over the libmpi shim — MPI programs
+    other than the reference's pi example (collectives only) run too."""
+    job = yaml_io.load_file(os.path.join(REPO, "examples/mpi-ring/ring.yaml"))[0]
+    job.metadata["namespace"] = "default"
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", timeout=60, what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    log = op.agent.logs("default", launcher["metadata"]["name"])
+    assert "ring of 4 ranks closed on mpi-ring-worker-0: token = 10 (expected 10)" in log
+    assert "pingpong         8 bytes" in log and "pingpong  16777216 bytes" in log
+
+
+@needs_native
 def test_pi_job_with_custom_cluster_domain(tmp_path):
     """e2e 'with custom cluster-domain' (test/e2e/mpi_job_test.go:532-583): --cluster-domain is appended to every
     hostfile FQDN and the launcher still resolves its workers."""
