@@ -108,6 +108,14 @@ int MPI_Probe(int source, int tag, MPI_Comm comm, MPI_Status* status);
 int MPI_Iprobe(int source, int tag, MPI_Comm comm, int* flag, MPI_Status* status);
 int MPI_Get_count(const MPI_Status* status, MPI_Datatype datatype, int* count);
 
+/* communicator management on one box: a split that keeps everybody together (or MPI_COMM_TYPE_SHARED: all ranks share the
+ * node) is MPI_COMM_WORLD again, a split into singletons is MPI_COMM_SELF; other partitions are not provided */
+#define MPI_COMM_TYPE_SHARED 1
+#define MPI_INFO_NULL 0
+typedef int MPI_Info;
+int MPI_Comm_split(MPI_Comm comm, int color, int key, MPI_Comm* newcomm);
+int MPI_Comm_split_type(MPI_Comm comm, int split_type, int key, MPI_Info info, MPI_Comm* newcomm);
+
 /* vector collectives and scans */
 int MPI_Allgatherv(const void* sendbuf, int sendcount, MPI_Datatype sendtype, void* recvbuf, const int* recvcounts, const int* displs,
                    MPI_Datatype recvtype, MPI_Comm comm);

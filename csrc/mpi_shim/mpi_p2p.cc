@@ -343,6 +343,29 @@ int MPI_Get_count(const MPI_Status* st, MPI_Datatype t, int* count) {
   return MPI_SUCCESS;
 }
 
+int MPI_Comm_split(MPI_Comm c, int color, int key, MPI_Comm* out) {
+  int e = check(c); if (e) return e;
+  if (c == MPI_COMM_SELF || g_size == 1) { *out = color == MPI_UNDEFINED ? MPI_COMM_NULL : c; return MPI_SUCCESS; }
+  struct CK { int color, key; } mine{color, key};
+  std::vector<CK> all(g_size);
+  e = allgather_bytes(&mine, all.data(), sizeof(CK));
+  if (e) return e;
+  if (color == MPI_UNDEFINED) { *out = MPI_COMM_NULL; return MPI_SUCCESS; }
+  int same = 0;
+  bool ordered = true;
+  for (int r = 0; r < g_size; r++) {
+    if (all[r].color == color) same++;
+    if (r > 0 && all[r].key < all[r - 1].key) ordered = false;
+  }
+  if (same == g_size && ordered) { *out = MPI_COMM_WORLD; return MPI_SUCCESS; }   // everybody together, rank order kept
+  if (same == 1) { *out = MPI_COMM_SELF; return MPI_SUCCESS; }                      // a group of one
+  return fail("MPI_Comm_split: only the trivial partitions (all ranks together in rank order, or singletons) are provided");
+}
+int MPI_Comm_split_type(MPI_Comm c, int split_type, int key, MPI_Info, MPI_Comm* out) {
+  // one box: every rank shares the node, so MPI_COMM_TYPE_SHARED groups everybody
+  return MPI_Comm_split(c, split_type == MPI_UNDEFINED ? MPI_UNDEFINED : 0, key, out);
+}
+
 // ---- vector collectives: rooted ones move data point-to-point (reserved tags above MPI_TAG_UB), Allgatherv gathers the padded
 // blocks through the mailbox allgather and unpacks
 static const int kTagGatherv = MPI_TAG_UB + 1, kTagScatterv = MPI_TAG_UB + 2, kTagScan = MPI_TAG_UB + 3;

@@ -149,6 +149,20 @@ int main(int argc, char** argv) {
     for (int i = 0; i < 2; i++) EXPECT(mineout[i] == n * (2.0 * r + i) + 0.5 * n * (n - 1) / 2.0);
   }
 
+  // 8. communicator splits that one box can express
+  {
+    MPI_Comm shared, self, none;
+    EXPECT(MPI_Comm_split_type(MPI_COMM_WORLD, MPI_COMM_TYPE_SHARED, r, MPI_INFO_NULL, &shared) == MPI_SUCCESS);
+    int lr = -1, ls = -1;
+    MPI_Comm_rank(shared, &lr);
+    MPI_Comm_size(shared, &ls);
+    EXPECT(lr == r && ls == n);                                  // "local rank / local size" the way Horovod derives them
+    EXPECT(MPI_Comm_split(MPI_COMM_WORLD, r, 0, &self) == MPI_SUCCESS);
+    MPI_Comm_size(self, &ls);
+    EXPECT(ls == 1);
+    EXPECT(MPI_Comm_split(MPI_COMM_WORLD, MPI_UNDEFINED, 0, &none) == MPI_SUCCESS && none == MPI_COMM_NULL);
+  }
+
   int any = 0;
   MPI_Allreduce(&g_bad, &any, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
   if (r == 0) printf(any ? "mpi_p2p_test: FAILED\n" : "mpi_p2p_test: all checks passed on %d ranks\n", n);
