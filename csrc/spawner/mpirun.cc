@@ -191,7 +191,25 @@ int main(int argc, char** argv) {
     else if (a == "-timeout") { need(1); timeout_s = atoi(argv[++i]); }
     else if (a == "-V" || a == "-version") { printf("mpirun (b200mpi) 0.1.0 — Open MPI/Hydra-compatible single-box launcher\n"); return 0; }
     else if (a == "-h" || a == "-help") {
-      printf("usage: mpirun [-n N] [-x VAR[=v]] [-mca k v] [--hostfile f] [--tag-output] [-bind-to x] [-map-by x] prog [args]\n");
+      printf("usage: mpirun [options] <program> [args]      (aliases: mpiexec, mpiexec.hydra, orterun)\n"
+             "Single-box launcher with the Open MPI and Hydra (MPICH / Intel MPI) command lines; one or two leading dashes.\n\n"
+             "  -n, -np, -c N                 number of ranks (default: total slots of the hostfile, else 1)\n"
+             "  -hostfile, -machinefile, -f F hostfile: 'host slots=N' (Open MPI) or 'host:N' (Hydra); default from\n"
+             "                                OMPI_MCA_orte_default_hostfile, I_MPI_HYDRA_HOST_FILE, HYDRA_HOST_FILE\n"
+             "  -host, -H, -hosts LIST        comma separated hosts (host[:slots])\n"
+             "  -ppn, -perhost, -npernode N   ranks per host\n"
+             "  -x VAR[=value]                export a variable to the ranks (Open MPI)\n"
+             "  -genv, -env VAR value         export a variable to the ranks (Hydra); -genvall / -envall accepted\n"
+             "  -mca / -gmca key value        exported as OMPI_MCA_<key>=<value>\n"
+             "  -wdir, -wd DIR                working directory of the ranks\n"
+             "  -tag-output, -prepend-rank, -l  prefix every output line with [job,rank]<stream>:\n"
+             "  -timeout SECONDS              kill the job after SECONDS (exit code 124)\n"
+             "  -oversubscribe                allow more ranks than slots\n"
+             "  -bind-to, -map-by, -rank-by, -bootstrap, -launcher, -iface ...   accepted and ignored (one box, no ssh)\n"
+             "  -V, -version / -h, -help\n\n"
+             "Ranks get OMPI_COMM_WORLD_*, PMI_*, RANK/WORLD_SIZE/LOCAL_RANK/MASTER_ADDR/MASTER_PORT, HOROVOD_* and B200MPI_* variables;\n"
+             "GPUs come from the operator's slot map (B200MPI_SLOTS_FILE). The first failing rank's exit code is propagated and the\n"
+             "others are terminated (SIGTERM, then SIGKILL). B200MPI_FAULT=kill_rank:R@time:S injects a failure.\n");
       return 0;
     }
     else if (!a.empty() && a[0] == '-') { fprintf(stderr, "mpirun (b200mpi): note: ignoring unknown option %s\n", argv[i]); }
