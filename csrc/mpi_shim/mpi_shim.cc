@@ -190,19 +190,28 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype t, int root, MPI_Comm c) {
   if (g_rv->bcast(buf, es * count, root, g_timeout_ms, &err)) return fail(err);
   return MPI_SUCCESS;
 }
+// Gather one mailbox-sized chunk from every rank, fold it in rank order (deterministic), move on: O(world x 64 KiB) scratch
+// instead of world copies of the whole buffer.
 static int reduce_impl(const void* send, void* recv, int count, MPI_Datatype t, MPI_Op op, int root, bool all) {
   const size_t es = type_size(t);
   if (!es) return MPI_ERR_TYPE;
   const size_t bytes = es * (size_t)count;
-  const void* mine = send == MPI_IN_PLACE ? recv : send;
-  std::vector<unsigned char> gathered(bytes * g_size);
-  int e = allgather_bytes(mine, gathered.data(), bytes);
-  if (e) return e;
-  if (all || g_rank == root) {
-    std::vector<unsigned char> acc(gathered.begin(), gathered.begin() + bytes);  // rank order: deterministic
-    for (int r = 1; r < g_size; r++)
-      if (!reduce_into(acc.data(), gathered.data() + (size_t)r * bytes, count, t, op)) return MPI_ERR_OP;
-    memcpy(recv, acc.data(), bytes);
+  const unsigned char* mine = static_cast<const unsigned char*>(send == MPI_IN_PLACE ? recv : send);
+  if (g_size == 1) { if (send != MPI_IN_PLACE && (all || g_rank == root)) memmove(recv, send, bytes); return MPI_SUCCESS; }
+  const size_t chunk = b200mpi::kRvMailbox / 8 * 8;   // a whole number of elements of every supported type
+  std::vector<unsigned char> tmp(chunk * g_size), acc(chunk);
+  std::string err;
+  const bool keep = all || g_rank == root;
+  for (size_t done = 0; done < bytes || (bytes == 0 && done == 0); done += chunk) {
+    const size_t n = std::min(chunk, bytes - done);
+    if (g_rv->allgather(mine + done, tmp.data(), n, g_timeout_ms, &err)) return fail(err);
+    if (keep && n) {
+      memcpy(acc.data(), tmp.data(), n);
+      for (int r = 1; r < g_size; r++)
+        if (!reduce_into(acc.data(), tmp.data() + (size_t)r * n, n / es, t, op)) return MPI_ERR_OP;
+      memcpy(static_cast<unsigned char*>(recv) + done, acc.data(), n);
+    }
+    if (bytes == 0) break;
   }
   return MPI_SUCCESS;
 }

@@ -19,7 +19,8 @@ int main(int argc, char** argv) {
   std::minstd_rand rng(12345);  // same sequence on every rank: sizes agree without communication
   int bad = 0;
   for (int it = 0; it < iters && !bad; it++) {
-    const int n = 1 + (int)(rng() % 3000);
+    // every eighth round is larger than one 64 KiB rendezvous mailbox so the chunked reduce / bcast paths run too
+    const int n = it % 8 == 7 ? 8192 + (int)(rng() % 20000) : 1 + (int)(rng() % 3000);
     const int root = (int)(rng() % world);
     // allreduce: sum_r (r + i) = world*i + world*(world-1)/2
     std::vector<long long> a(n), b(n);
