@@ -28,7 +28,7 @@ $(LIBDIR)/libb200mpi_gemm.so: csrc/kernels/gemm_bnstats.cu csrc/kernels/gemm_bns
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(NVFLAGS) -shared csrc/kernels/gemm_bnstats.cu -o $@
 
-native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(BINDIR)/pi $(BINDIR)/pingpong
+native: $(BINDIR)/mpirun $(LIBDIR)/libmpi.so $(LIBDIR)/libb200mpi_hvd.so $(BINDIR)/pi $(BINDIR)/pingpong
 
 $(BINDIR)/mpirun: csrc/spawner/mpirun.cc
 	@mkdir -p $(BINDIR)
@@ -41,6 +41,13 @@ $(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi
 	@mkdir -p $(LIBDIR) mpi_operator_b200/include
 	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/runtime/rendezvous.cc -lrt -lpthread
 	cp csrc/mpi_shim/mpi.h mpi_operator_b200/include/mpi.h
+
+# Horovod-core equivalent: negotiation / fusion / response cache / timeline / stall inspector (host only, no CUDA link:
+# the GPU executor calls libb200mpi.so and the process's cudart through function pointers)
+HVD_SRCS := csrc/hvd_core/hvd_core.cc csrc/runtime/rendezvous.cc
+$(LIBDIR)/libb200mpi_hvd.so: $(HVD_SRCS) csrc/hvd_core/hvd_core.h csrc/runtime/rendezvous.h
+	@mkdir -p $(LIBDIR)
+	$(CXX) $(CXXFLAGS) -Wextra -Wno-unused-parameter -shared -o $@ $(HVD_SRCS) -lrt -lpthread -ldl
 
 $(BINDIR)/pi: examples/pi/pi.cc $(LIBDIR)/libmpi.so
 	$(CXX) -std=c++17 -O2 -Impi_operator_b200/include -o $@ $< -L$(LIBDIR) -lmpi -Wl,-rpath,'$$ORIGIN/../lib'
@@ -86,7 +93,16 @@ define san_build
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/mpi_stress csrc/tests/mpi_stress.cc $(SAN_SRCS) -lrt -lpthread
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/pi examples/pi/pi.cc $(SAN_SRCS) -lrt -lpthread
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -Icsrc/mpi_shim -o build/san/$(1)/mpi_p2p_test csrc/tests/mpi_p2p_test.cc $(SAN_SRCS) -lrt -lpthread
+	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -o build/san/$(1)/hvd_core_test csrc/tests/hvd_core_test.cc $(HVD_SRCS) -lrt -lpthread -ldl
 endef
+
+# negotiation / fusion / cache / join semantics of the hvdcore engine on 4 ranks (and 1, 3: odd world sizes)
+test_hvd_core: native
+	@mkdir -p build/san
+	$(CXX) -std=c++17 -O2 -Wall -Icsrc/include -o build/san/hvd_core_test csrc/tests/hvd_core_test.cc $(HVD_SRCS) -lrt -lpthread -ldl
+	$(BINDIR)/mpirun -n 4 build/san/hvd_core_test
+	$(BINDIR)/mpirun -n 3 build/san/hvd_core_test
+	$(BINDIR)/mpirun -n 1 build/san/hvd_core_test
 
 # launch planning / counters of the runtime, checked on the host (no GPU): includes comm.cc, kernels come from the .so
 test_comm_host: $(LIBDIR)/libb200mpi.so
@@ -125,11 +141,13 @@ asan:
 	ASAN_OPTIONS=detect_leaks=1:abort_on_error=0 build/san/asan/mpirun -n 4 build/san/asan/mpi_stress 200
 	build/san/asan/mpirun -n 2 --tag-output build/san/asan/pi
 	build/san/asan/mpirun -n 4 build/san/asan/mpi_p2p_test
+	ASAN_OPTIONS=detect_leaks=1 build/san/asan/mpirun -n 4 build/san/asan/hvd_core_test
 
 tsan:
 	$(call san_build,tsan,-fsanitize=thread)
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/mpi_stress 200
 	build/san/tsan/mpirun -n 2 build/san/tsan/pi
+	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/mpirun -n 4 build/san/tsan/hvd_core_test
 	# device protocols executed by host threads (same templates / shared logic as the kernels) under ThreadSanitizer:
 	# every shared-memory, TMEM, mailbox and flag access must be ordered by the barriers the kernels use
 	$(SAN_CXX) -std=c++17 -O1 -g -fsanitize=thread -o build/san/tsan/gemm_pipeline_model csrc/tests/gemm_pipeline_model.cc -lpthread
@@ -137,4 +155,4 @@ tsan:
 	$(NVCC) -ccbin $(SAN_CXX) -std=c++17 -O1 -g $(ARCH) -Icsrc/include -Xcudafe --diag_suppress=20011,--diag_suppress=20014 -Xcompiler -fsanitize=thread -x cu csrc/tests/p2p_protocol_test.cu -o build/san/tsan/p2p_protocol_test -L$(LIBDIR) -lb200mpi -Xlinker -rpath,$(abspath $(LIBDIR)) -lrt -lpthread -ltsan
 	TSAN_OPTIONS=halt_on_error=1 build/san/tsan/p2p_protocol_test
 
-.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model test_mpi_p2p
+.PHONY: all native sass clean test test_gpu test_e2e generate verify-generate lint sanitize asan tsan test_comm_host test_umma_desc test_p2p_protocol test_gemm_model test_mpi_p2p test_hvd_core

@@ -5,10 +5,14 @@ tensorflow_mnist.py:90 ``hvd.init()``, :123-130 LR x ``hvd.size()``, :133
 ``hvd.DistributedOptimizer(opt, op=hvd.Average)``, :143 broadcast from rank 0,
 :155 GPU pinning by ``hvd.local_rank()``, :159 rank-0-only checkpoints; and
 ``--variable_update=horovod`` in tensorflow-benchmarks.yaml:42).  Horovod's C++
-core (negotiation thread, fusion buffer, NCCL calls) is replaced by:
-gradients living in a symmetric window (no fusion-buffer copies), bucket
-allreduce kernels with the average fused in, launched from autograd hooks on a
-high-priority stream.  Usage is the ``horovod.torch`` one:
+core is replaced twice over.  For the training hot path: gradients living in a
+symmetric window (no fusion-buffer copies), bucket allreduce kernels with the
+average fused in, launched from autograd hooks on a high-priority stream
+(``DistributedOptimizer``).  For everything else Horovod's background thread
+does — named tensors submitted in any order, ``*_async`` handles, fusion of many
+small tensors, response cache, timeline, stall inspector, ``join()`` — the native
+``hvdcore`` engine (csrc/hvd_core, ``hvd/engine.py``).  Usage is the
+``horovod.torch`` one:
 
     import mpi_operator_b200.hvd as hvd      # or: import horovod.torch as hvd
     hvd.init(); torch.cuda.set_device(hvd.local_rank())
@@ -21,10 +25,11 @@ import os
 from typing import Iterable, List, Optional
 
 from ..launch.env import rank_info_from_env
+from .exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
 
 Average, Sum, Adasum, Min, Max = "average", "sum", "adasum", "min", "max"
 
-_state = {"comm": None, "info": None}
+_state = {"comm": None, "info": None, "engine": None}
 
 
 class HorovodNotInitialized(RuntimeError):
@@ -52,13 +57,42 @@ def init(comm=None) -> None:
         # CPU job (the reference's Horovod MNIST example runs on CPU workers): collectives over the libmpi shim
         from .host_backend import HostCommunicator
         _state["comm"] = HostCommunicator()
+        _start_engine(info, None)
         return
     dev = info.local_rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
     _state["comm"] = Communicator.create(info.rank, info.world_size, dev, info.job_id)
+    _start_engine(info, dev)
+
+
+_atexit_registered = False
+
+
+def _start_engine(info, dev) -> None:
+    """Native background engine (hvd/engine.py). Host tensors: on unless B200MPI_HVD_ENGINE=0. Device tensors: only with
+    B200MPI_HVD_ENGINE=1 (the GPU executor has not run on hardware yet); it gets a communicator of its own because
+    collectives on one communicator must be issued in the same order on every rank."""
+    global _atexit_registered
+    want = os.environ.get("B200MPI_HVD_ENGINE", "")
+    if want == "0" or (dev is not None and want != "1"):
+        return
+    from .engine import Engine
+    gcomm = None
+    if dev is not None:
+        from ..runtime.comm import Communicator
+        gcomm = Communicator.create(info.rank, info.world_size, dev, info.job_id + "-hvdgpu")
+    _state["engine"] = Engine(info.job_id, info.rank, info.world_size, gcomm)
+    if not _atexit_registered:   # a script that forgets hvd.shutdown() must not leave its peers negotiating with a ghost
+        import atexit
+        atexit.register(shutdown)
+        _atexit_registered = True
 
 
 def shutdown() -> None:
+    e = _state["engine"]
+    if e is not None:
+        _state["engine"] = None
+        e.shutdown()
     c = _state["comm"]
     if c is not None:
         c.destroy()
@@ -105,6 +139,26 @@ def _op_name(op, average):
     raise ValueError(f"unknown reduction op {op!r}")
 
 
+class _Done:
+    """Handle of an operation that already completed in stream order (direct path)."""
+
+    def __init__(self, result):
+        self.result = result
+
+    def done(self) -> bool:
+        return True
+
+    def wait(self):
+        return self.result
+
+
+def _engine_for(tensor):
+    e = _state["engine"]
+    if e is None or (tensor.is_cuda and not e.has_gpu):
+        return None
+    return e
+
+
 def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
     out = tensor.clone()
     allreduce_(out, average, name, op, prescale_factor, postscale_factor)
@@ -112,32 +166,68 @@ def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, pos
 
 
 def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    return allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor).wait()
+
+
+def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    return allreduce_async_(tensor.clone(), average, name, op, prescale_factor, postscale_factor)
+
+
+def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    """In-place allreduce; returns a handle for ``synchronize`` / ``poll``. With the engine, ranks may submit named
+    tensors in different orders and small tensors submitted close together travel fused."""
     import torch
-    if _op_name(op, average) == "adasum":
+    opn = _op_name(op, average)
+    if opn == "adasum":
         from .adasum import adasum_allreduce_
-        return adasum_allreduce_(_comm(), tensor)
+        return _Done(adasum_allreduce_(_comm(), tensor))
+    e = _engine_for(tensor)
+    if e is not None:
+        t = tensor if tensor.is_contiguous() else tensor.contiguous()
+        if tensor.is_cuda and (t.dtype not in (torch.float32, torch.bfloat16, torch.float16) or opn == "prod"):
+            t = t.float()        # the device kernels reduce floating point; integers round-trip through fp32
+        h = e.allreduce_async(t, t, name, opn, prescale_factor, postscale_factor)
+        h.result = tensor
+        if t is not tensor:
+            h.post = lambda _r, _t=t, _o=tensor: _o.copy_(_t.to(_o.dtype))
+        return h
     t = tensor if tensor.is_contiguous() else tensor.contiguous()
     if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
         f = t.float()
-        _comm().allreduce(f, f, op=_op_name(op, average), scale=prescale_factor * postscale_factor)
+        _comm().allreduce(f, f, op=opn, scale=prescale_factor * postscale_factor)
         tensor.copy_(f.to(tensor.dtype))
-        return tensor
-    _comm().allreduce(t, t, op=_op_name(op, average), scale=prescale_factor * postscale_factor)
+        return _Done(tensor)
+    _comm().allreduce(t, t, op=opn, scale=prescale_factor * postscale_factor)
     if t is not tensor:
         tensor.copy_(t)
-    return tensor
+    return _Done(tensor)
 
 
-def grouped_allreduce(tensors, average=None, name=None, op=None):
-    return [allreduce(t, average, name, op) for t in tensors]
+def grouped_allreduce(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    hs = grouped_allreduce_async(tensors, average, name, op, prescale_factor, postscale_factor)
+    return [h.wait() for h in hs]
+
+
+def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    """All tensors are submitted before any is waited for, so the engine negotiates them in one cycle and fuses them."""
+    return [allreduce_async(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor)
+            for i, t in enumerate(tensors)]
 
 
 def allgather(tensor, name=None):
+    return allgather_async(tensor, name).wait()
+
+
+def allgather_async(tensor, name=None):
+    """Concatenation along the first dimension. Through the engine (host tensors) the first dimensions may differ."""
     import torch
+    e = _engine_for(tensor)
+    if e is not None and not tensor.is_cuda:
+        return e.allgather_async(tensor if tensor.dim() else tensor.reshape(1), name)
     t = tensor.contiguous()
     out = torch.empty((size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     _comm().allgather(t, out)
-    return out
+    return _Done(out)
 
 
 def broadcast(tensor, root_rank, name=None):
@@ -146,11 +236,26 @@ def broadcast(tensor, root_rank, name=None):
 
 
 def broadcast_(tensor, root_rank, name=None):
+    return broadcast_async_(tensor, root_rank, name).wait()
+
+
+def broadcast_async(tensor, root_rank, name=None):
+    return broadcast_async_(tensor.clone(), root_rank, name)
+
+
+def broadcast_async_(tensor, root_rank, name=None):
     t = tensor if tensor.is_contiguous() else tensor.contiguous()
+    e = _engine_for(tensor)
+    if e is not None:
+        h = e.broadcast_async(t, root_rank, name)
+        h.result = tensor
+        if t is not tensor:
+            h.post = lambda _r, _t=t, _o=tensor: _o.copy_(_t)
+        return h
     _comm().broadcast(t, root=root_rank)
     if t is not tensor:
         tensor.copy_(t)
-    return tensor
+    return _Done(tensor)
 
 
 def alltoall(tensor, splits=None, name=None):
@@ -158,6 +263,11 @@ def alltoall(tensor, splits=None, name=None):
     padded to the largest split so the same even kernel moves them, and ``(output, received_splits)`` is returned."""
     import torch
     t = tensor.contiguous()
+    e = _engine_for(tensor)
+    if e is not None and not tensor.is_cuda:   # host tensors: ragged alltoallv in the engine, no padding
+        sp = None if splits is None else [int(v) for v in (splits.tolist() if hasattr(splits, "tolist") else splits)]
+        out, recv = e.alltoall_async(t, sp, name).wait()
+        return out if splits is None else (out, recv)
     if splits is None:
         out = torch.empty_like(t)
         _comm().alltoall(t, out)
@@ -200,49 +310,74 @@ def _dev():
 
 def barrier():
     import torch
-    _comm().barrier()
+    e = _state["engine"]
+    if e is not None:
+        e.barrier()
+    else:
+        _comm().barrier()
     if _on_gpu():
         torch.cuda.synchronize()
 
 
 def join(device=-1) -> int:
+    """Tell the other ranks this rank has run out of data: their allreduces keep completing (this rank contributes zeros)
+    until every rank has joined. Returns the last rank that joined. Without the engine it degrades to a barrier."""
+    e = _state["engine"]
+    if e is not None:
+        return e.join()
     barrier()
     return size() - 1
 
 
 def synchronize(handle=None):
+    """Wait for an ``*_async`` handle and return its output."""
     import torch
+    if hasattr(handle, "wait"):
+        return handle.wait()
     if _on_gpu():
         torch.cuda.current_stream().synchronize()
     return handle
 
 
 def poll(handle=None) -> bool:
-    return True
+    return handle.done() if hasattr(handle, "done") else True
 
 
-# async flavours complete in stream order: the "handle" is the tensor itself
-allreduce_async = allreduce
-allreduce_async_ = allreduce_
-allgather_async = allgather
-broadcast_async = broadcast
-broadcast_async_ = broadcast_
+def start_timeline(file_path: str, mark_cycles: bool = False) -> None:
+    """Horovod Timeline (Chrome trace of every tensor's negotiation / fusion / reduction phases), written by rank 0;
+    also enabled for the whole run by ``HOROVOD_TIMELINE=<path>``."""
+    e = _state["engine"]
+    if e is None:
+        raise RuntimeError("the timeline is written by the background engine (not started; see B200MPI_HVD_ENGINE)")
+    e.start_timeline(file_path)
+
+
+def stop_timeline() -> None:
+    e = _state["engine"]
+    if e is not None:
+        e.stop_timeline()
+
+
+def engine_stats() -> dict:
+    """Counters of the background engine: cycles, negotiated tensors, fused groups, cache hits / misses, stall warnings."""
+    e = _state["engine"]
+    return e.stats() if e is not None else {}
 
 
 def broadcast_parameters(params, root_rank: int = 0) -> None:
-    """K3 (tensorflow_mnist.py:143): state_dict / named_parameters / list of (name, tensor)."""
+    """K3 (tensorflow_mnist.py:143): state_dict / named_parameters / list of (name, tensor). Every tensor is submitted
+    before the first wait, so with the engine the whole model is negotiated in one cycle."""
     import torch
     if isinstance(params, dict):
         items = sorted(params.items())
     else:
         items = list(params)
-    for _, p in items:
-        if isinstance(p, torch.Tensor) and (p.is_cuda or not _on_gpu()):
-            t = p.data if p.is_contiguous() else p.data.contiguous()
-            if t.numel():
-                _comm().broadcast(t, root=root_rank)
-                if t.data_ptr() != p.data_ptr():
-                    p.data.copy_(t)
+    handles = []
+    for key, p in items:
+        if isinstance(p, torch.Tensor) and (p.is_cuda or not _on_gpu()) and p.numel():
+            handles.append(broadcast_async_(p.data, root_rank, name=f"broadcast_parameters.{key}"))
+    for h in handles:
+        h.wait()
 
 
 def broadcast_object(obj, root_rank: int = 0, name=None):

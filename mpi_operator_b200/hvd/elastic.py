@@ -11,9 +11,7 @@ from typing import Callable, Optional
 
 import torch
 
-
-class HostsUpdatedInterrupt(RuntimeError):
-    """Raised inside a training function when the host set changed."""
+from .exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
 
 
 class WorkersAvailableException(RuntimeError):

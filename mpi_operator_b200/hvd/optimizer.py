@@ -121,7 +121,111 @@ class _DistributedOptimizer:
         return self._opt.load_state_dict(sd)
 
 
+class _EngineDistributedOptimizer:
+    """Horovod's own scheme, on the native engine: every parameter's gradient is submitted as a NAMED async allreduce from
+    its autograd hook, the background thread negotiates / fuses / reduces while backward is still running, ``step()``
+    waits for the handles. Unlike the bucket optimizer it tolerates ranks producing gradients in different orders and
+    parameters that receive no gradient on some ranks (they contribute zeros), and it supports ``compression``."""
+
+    def __init__(self, optimizer, named_parameters=None, compression=None, backward_passes_per_step: int = 1, op="average",
+                 gradient_predivide_factor: float = 1.0):
+        from . import Compression, _op_name
+        self._opt = optimizer
+        self._op = _op_name(op, None)
+        self._passes = max(1, int(backward_passes_per_step))
+        self._compression = compression or Compression.none
+        self._predivide = float(gradient_predivide_factor)
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
+        named = list(named_parameters) if named_parameters is not None else []
+        by_id = {id(p): n for n, p in named}
+        if named and len(by_id) != len(named):
+            raise ValueError("named_parameters contains the same parameter twice")
+        self._names = {p: by_id.get(id(p), f"noname.{i}") for i, p in enumerate(params)}
+        if len(set(self._names.values())) != len(params):
+            raise ValueError("parameter names must be unique")
+        self._params = params
+        self._handles = {}
+        self._counts = {p: 0 for p in params}
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def _submit(self, p):
+        from . import allreduce_async_
+        grad = p.grad
+        if self._passes > 1:
+            grad.div_(self._passes)
+        t, ctx = self._compression.compress(grad)
+        pre = post = 1.0
+        if self._op == "avg" and self._predivide != 1.0:
+            pre, post = 1.0 / self._predivide, self._predivide
+        h = allreduce_async_(t, name="DistributedOptimizer.grad." + self._names[p], op=_OPS[self._op], prescale_factor=pre,
+                             postscale_factor=post)
+        self._handles[p] = (h, t, ctx)
+
+    def _hook(self, p):
+        self._counts[p] += 1
+        if self._counts[p] == self._passes:
+            self._submit(p)
+
+    def synchronize(self):
+        import torch
+        for p in self._params:   # no gradient on this rank this step: the other ranks still expect the tensor
+            if p not in self._handles and self._counts[p] == 0:
+                if p.grad is None:
+                    p.grad = torch.zeros_like(p)
+                self._submit(p)
+        for p, (h, t, ctx) in list(self._handles.items()):
+            h.wait()
+            out = self._compression.decompress(t, ctx)
+            if out.data_ptr() != p.grad.data_ptr():
+                p.grad.copy_(out)
+        self._handles.clear()
+        for p in self._params:
+            self._counts[p] = 0
+
+    def step(self, closure=None):
+        from ..utils import fault
+        fault.injector().on_step()
+        if any(0 < c < self._passes for c in self._counts.values()):
+            return None          # still accumulating local backward passes
+        self.synchronize()
+        return self._opt.step(closure)
+
+    def zero_grad(self, set_to_none: bool = False):
+        if self._handles:
+            raise AssertionError("optimizer.zero_grad() was called after loss.backward() but before optimizer.step() or "
+                                 "optimizer.synchronize(): the submitted gradients would be lost")
+        return self._opt.zero_grad(set_to_none=set_to_none)
+
+    def __getattr__(self, name):
+        return getattr(self._opt, name)
+
+    @property
+    def param_groups(self):
+        return self._opt.param_groups
+
+    def state_dict(self):
+        return self._opt.state_dict()
+
+    def load_state_dict(self, sd):
+        return self._opt.load_state_dict(sd)
+
+
+_OPS = {"avg": "average", "sum": "sum", "min": "min", "max": "max", "adasum": "adasum"}
+
+
 def DistributedOptimizer(optimizer, named_parameters=None, compression=None, backward_passes_per_step=1, op="average",  # noqa: N802
                          gradient_predivide_factor=1.0, **kw):
+    """``B200MPI_HVD_OPTIMIZER=engine`` (or ``engine=True``) selects Horovod's per-parameter scheme on the native background
+    engine; the default is the window/bucket optimizer (gradients live in NVLink-visible memory, no fusion copies)."""
+    import os
+    from . import Compression, _op_name, _state
+    use_engine = kw.get("engine")
+    if use_engine is None:
+        use_engine = os.environ.get("B200MPI_HVD_OPTIMIZER", "") == "engine"
+    needs_engine = compression not in (None, Compression.none)
+    if (use_engine or needs_engine) and _state.get("engine") is not None and _op_name(op, None) != "adasum":
+        return _EngineDistributedOptimizer(optimizer, named_parameters, compression, backward_passes_per_step, op,
+                                           gradient_predivide_factor)
     return _DistributedOptimizer(optimizer, named_parameters, compression, backward_passes_per_step, op,
                                  gradient_predivide_factor, kw.get("bucket_bytes"))
