@@ -69,3 +69,14 @@ def test_point_to_point_mailboxes():
     n = min(torch.cuda.device_count(), 8)
     rcs = launch(n, [os.path.join(HERE, "p2p_worker.py")], timeout=240, extra_env={"B200MPI_P2P": "1"})
     assert rcs == [0] * n
+
+
+@pytest.mark.xfail(strict=False, reason="GPU executor of the hvdcore engine (B200MPI_HVD_ENGINE=1): written after the round's GPU budget was spent; the "
+                                        "negotiation / fusion / cache / join logic it shares with the host executor is covered by tests/test_hvd_engine.py")
+def test_horovod_engine_with_cuda_tensors():
+    """Named async allreduces of CUDA tensors, fused on the engine's stream into b200mpi kernels (tests/hvd_engine_gpu_worker.py)."""
+    sys.path.insert(0, HERE)
+    from mp_launch import launch
+    n = min(torch.cuda.device_count(), 8)
+    rcs = launch(n, [os.path.join(HERE, "hvd_engine_gpu_worker.py")], timeout=240, extra_env={"B200MPI_HVD_ENGINE": "1"})
+    assert rcs == [0] * n

@@ -16,6 +16,10 @@ echo "=== experimental point-to-point (B200MPI_P2P=1), N=$N ==="
 mkdir -p gpurun_out/p2p_n$N
 B200MPI_P2P=1 timeout 150 python tests/mp_launch.py -n $N --timeout 120 --log-dir gpurun_out/p2p_n$N tests/p2p_worker.py
 for f in gpurun_out/p2p_n$N/*.log; do echo "--- $f"; tail -6 $f; done
+echo "=== hvdcore engine with CUDA tensors (B200MPI_HVD_ENGINE=1), N=$N ==="
+mkdir -p gpurun_out/hvd_n$N
+B200MPI_HVD_ENGINE=1 timeout 150 python tests/mp_launch.py -n $N --timeout 120 --log-dir gpurun_out/hvd_n$N tests/hvd_engine_gpu_worker.py
+for f in gpurun_out/hvd_n$N/*.log; do echo "--- $f"; tail -6 $f; done
 echo "=== bench at N=$N: default vs async input pipeline (+ NUMA binding) ==="
 PORT=29611
 for cfg in "" "B200MPI_ASYNC_H2D=1" "B200MPI_ASYNC_H2D=1 B200MPI_BIND_NUMA=1"; do
