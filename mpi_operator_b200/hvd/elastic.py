@@ -101,7 +101,9 @@ class TorchState(State):
 
 def run(func: Callable) -> Callable:
     """Decorator: restore + sync state, run; on HostsUpdatedInterrupt exit with the
-    'rescale' code so the launcher re-spawns the new world (daemon-side elasticity)."""
+    'rescale' code so the launcher re-spawns the new world (daemon-side elasticity).
+    A HorovodInternalError (a peer died, the engine was shut down or stalled out) rolls the state back to the last
+    commit and ends this incarnation the same way: the re-spawned world resumes from the committed checkpoint."""
     @functools.wraps(func)
     def wrapper(state, *args, **kwargs):
         state.restore()
@@ -110,5 +112,10 @@ def run(func: Callable) -> Callable:
             return func(state, *args, **kwargs)
         except HostsUpdatedInterrupt:
             state.save()
+            raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
+        except HorovodInternalError as e:
+            import sys
+            print(f"[elastic] collective failed ({e}); rolling back to the last commit and leaving for a re-spawn", file=sys.stderr, flush=True)
+            state.restore()
             raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
     return wrapper

@@ -1,6 +1,6 @@
 """Rank script (run under the native mpirun): the horovod.torch async API on the native hvdcore engine — named tensors in
 rank-dependent order, fusion and response-cache counters, ragged allgather, mismatch errors, join(), timeline, the
-engine-backed DistributedOptimizer with fp16 compression, stall inspector. Modes: default | stall | stall_shutdown."""
+engine-backed DistributedOptimizer with fp16 compression, stall inspector. Modes: default | stall | stall_shutdown | peer_death."""
 import json
 import os
 import sys
@@ -27,6 +27,20 @@ if mode == "stall":
     hvd.shutdown()
     print(f"rank {r}/{n} stall ok", flush=True)
     sys.exit(0)
+
+if mode == "peer_death":
+    # rank 1 vanishes without a shutdown: the other engines notice the dead pid in the rendezvous barrier and fail the
+    # outstanding handles (HorovodInternalError, transport) instead of hanging
+    hvd.barrier()
+    if r == 1:
+        os._exit(0)
+    try:
+        hvd.allreduce(torch.ones(3), name="orphaned")
+        raise SystemExit("allreduce completed without rank 1")
+    except hvd.HorovodInternalError as e:
+        assert e.code == -5 and ("died" in str(e) or "aborted" in str(e)), (e.code, str(e))
+    print(f"rank {r}/{n} peer death detected", flush=True)
+    os._exit(0)
 
 if mode == "stall_shutdown":
     # rank 1 never submits: after HOROVOD_STALL_SHUTDOWN_TIME_SECONDS every engine stops and the waiters get an error

@@ -63,6 +63,16 @@ def test_elastic_state_commit_restore_and_host_update(tmp_path, monkeypatch):
         train(st)
     assert e.value.code == 75
 
+    @elastic.run
+    def broken(state):       # a dead peer / shut-down engine surfaces as HorovodInternalError: roll back, leave for a re-spawn
+        state.step = 12345
+        raise hvd.HorovodInternalError("rank 1 died", -5)
+    st.step = 8
+    st.save()
+    with pytest.raises(SystemExit) as e:
+        broken(st)
+    assert e.value.code == 75 and st.step == 8
+
 
 def test_trace_export_and_roofline_report(tmp_path):
     import json

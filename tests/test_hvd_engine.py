@@ -71,6 +71,12 @@ def test_stall_shutdown_fails_the_waiters_on_every_rank():
     assert r.stdout.count("stall_shutdown ok") == 3
 
 
+def test_a_dead_peer_fails_the_outstanding_handles_instead_of_hanging():
+    r = _run(3, "peer_death", timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("peer death detected") == 2
+
+
 def test_engine_can_be_disabled():
     """B200MPI_HVD_ENGINE=0: the front-end falls back to the direct (call-order) path over the libmpi shim."""
     code = ("import sys; sys.path.insert(0, %r); import torch, horovod.torch as hvd; hvd.init(); "
