@@ -213,6 +213,7 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
       }
     }
+    __syncwarp();   // lanes 1..31 skipped the loop: reconverge before the block-wide barrier below
   } else if (warp == 1) {
     // ======================================================= MMA issuer ====
     if (lane == 0) {
@@ -237,6 +238,7 @@ k_gemm_bnstats(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         acc.advance(2);
       }
     }
+    __syncwarp();
   } else {
     // ========================================================= epilogue ====
     const int et = threadIdx.x - 64;             // 0..127
