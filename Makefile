@@ -36,6 +36,7 @@ $(BINDIR)/mpirun: csrc/spawner/mpirun.cc
 	ln -sf mpirun $(BINDIR)/mpiexec
 	ln -sf mpirun $(BINDIR)/mpiexec.hydra
 	ln -sf mpirun $(BINDIR)/orterun
+	printf '#!/bin/sh\nexec python -m mpi_operator_b200.cmd.horovodrun "$$@"\n' > $(BINDIR)/horovodrun && chmod +x $(BINDIR)/horovodrun
 
 $(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_internal.h csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
 	@mkdir -p $(LIBDIR) mpi_operator_b200/include

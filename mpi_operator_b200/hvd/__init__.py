@@ -431,4 +431,6 @@ class Compression:
 
 
 from .optimizer import DistributedOptimizer  # noqa: E402,F401
+
+from .sync_batch_norm import SyncBatchNorm  # noqa: E402,F401
 from . import elastic  # noqa: E402,F401

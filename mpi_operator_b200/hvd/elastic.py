@@ -119,3 +119,55 @@ def run(func: Callable) -> Callable:
             state.restore()
             raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
     return wrapper
+
+
+class ElasticSampler(torch.utils.data.Sampler):
+    """Horovod's ``hvd.elastic.ElasticSampler``: shards the dataset over the CURRENT world and remembers which indices of
+    the epoch were already consumed, so that after a rescale the remaining samples are re-partitioned over the new world
+    instead of being repeated or dropped. Register it in the ``TorchState`` (``TorchState(model, opt, sampler=sampler)``)
+    and call ``record_batch`` after every step."""
+
+    def __init__(self, dataset, shuffle: bool = True, seed: int = 0):
+        self.dataset, self.shuffle, self.seed = dataset, shuffle, seed
+        self.epoch = 0
+        self.processed_indices = set()
+        self.reset()
+
+    def set_epoch(self, epoch: int) -> None:
+        self.epoch = epoch
+        self.processed_indices = set()
+        self.reset()
+
+    def record_batch(self, batch_idx: int, batch_size: int) -> None:
+        self.processed_indices.update(self.get_indices(batch_idx, batch_size))
+
+    def get_indices(self, batch_idx: int, batch_size: int):
+        start = batch_idx * batch_size
+        return self.indices[start:min(start + batch_size, len(self.indices))]
+
+    def state_dict(self) -> dict:
+        return {"epoch": self.epoch, "processed_indices": sorted(self.processed_indices)}
+
+    def load_state_dict(self, sd: dict) -> None:
+        self.epoch = sd["epoch"]
+        self.processed_indices = set(sd["processed_indices"])
+        self.reset()
+
+    def reset(self) -> None:
+        from . import is_initialized, rank, size
+        self.num_replicas, self.rank = (size(), rank()) if is_initialized() else (1, 0)
+        remaining = [i for i in range(len(self.dataset)) if i not in self.processed_indices]
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)
+            remaining = [remaining[i] for i in torch.randperm(len(remaining), generator=g).tolist()]
+        self.remaining_indices = remaining
+        self.num_samples = (len(remaining) + self.num_replicas - 1) // self.num_replicas
+        total = self.num_samples * self.num_replicas
+        padded = remaining + remaining[:total - len(remaining)] if remaining else []
+        self.indices = padded[self.rank:total:self.num_replicas]
+
+    def __iter__(self):
+        return iter(self.indices)
+
+    def __len__(self):
+        return self.num_samples

@@ -70,6 +70,46 @@ for step in range(3):
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (p - q).abs().max()
 
+# SyncBatchNorm == nn.BatchNorm2d over the concatenated global batch (outputs, input gradients, affine gradients, running stats)
+torch.manual_seed(5)
+full = torch.randn(4 * n, 3, 5, 5, dtype=torch.float64)
+w_out = torch.randn(4 * n, 3, 5, 5, dtype=torch.float64)
+ref_bn = nn.BatchNorm2d(3).double()
+sbn = hvd.SyncBatchNorm(3).double()
+with torch.no_grad():
+    for m_ in (ref_bn, sbn):
+        m_.weight.copy_(torch.tensor([1.5, -0.5, 2.0]))
+        m_.bias.copy_(torch.tensor([0.1, 0.2, -0.3]))
+xf = full.clone().requires_grad_(True)
+ref_out = ref_bn(xf)
+(ref_out * w_out).sum().backward()
+xl = full[4 * r:4 * r + 4].clone().requires_grad_(True)
+yl = sbn(xl)
+(yl * w_out[4 * r:4 * r + 4]).sum().backward()
+assert torch.allclose(yl, ref_out[4 * r:4 * r + 4].detach(), atol=1e-9)
+assert torch.allclose(xl.grad, xf.grad[4 * r:4 * r + 4], atol=1e-9)
+assert torch.allclose(hvd.allreduce(sbn.weight.grad, op=hvd.Sum), ref_bn.weight.grad, atol=1e-9)
+assert torch.allclose(sbn.running_mean, ref_bn.running_mean, atol=1e-9) and torch.allclose(sbn.running_var, ref_bn.running_var, atol=1e-9)
+sbn.eval()
+ref_bn.eval()
+assert torch.allclose(sbn(full[:2]), ref_bn(full[:2]), atol=1e-9)
+
+# ElasticSampler: the ranks partition the epoch; after 2 recorded batches the rest is re-partitioned without repeats
+ds = list(range(10 * n + 3))
+samp = hvd.elastic.ElasticSampler(ds, shuffle=True, seed=3)
+mine = list(samp)
+everyone = hvd.allgather_object(mine)
+assert len(mine) == len(samp) and set(i for part in everyone for i in part) == set(ds)
+samp.record_batch(0, 4)
+samp.record_batch(1, 4)
+done = set(i for part in hvd.allgather_object(sorted(samp.processed_indices)) for i in part)
+sd = samp.state_dict()
+samp2 = hvd.elastic.ElasticSampler(ds, shuffle=True, seed=3)
+samp2.load_state_dict(sd)
+assert samp2.epoch == 0 and not (set(samp2) & samp.processed_indices) and len(done) == 8 * n
+samp.set_epoch(1)
+assert not samp.processed_indices and len(list(samp)) == len(samp)
+
 # Adasum: orthogonal gradients add, parallel gradients average
 e = torch.zeros(n)
 e[r] = 1.0

@@ -1,5 +1,6 @@
 """mpijobctl against a live in-process daemon (the kubectl workflow of the reference README.md:63-170)."""
 import io
+import os
 import json
 import socket
 import time
@@ -100,3 +101,31 @@ def test_run_standalone_and_version(tmp_path, capsys):
     out = capsys.readouterr().out
     assert rc == 0 and "launcher-says-hi" in out and "Succeeded after" in out
     assert mpijobctl.main(["version"]) == 0
+
+
+def test_horovodrun_maps_its_flags_onto_mpirun_and_the_engine(tmp_path, capsys):
+    """`horovodrun` is Horovod's launcher CLI; here it is a front for the native mpirun and the HOROVOD_* knobs of hvdcore."""
+    import subprocess
+    import sys
+    from mpi_operator_b200.cmd import horovodrun
+    a = horovodrun.build_parser().parse_args(["-np", "4", "-H", "localhost:4", "--fusion-threshold-mb", "32", "--cycle-time-ms", "2.5",
+                                              "--cache-capacity", "0", "--timeline-filename", "/tmp/t.json", "--no-stall-check",
+                                              "--start-timeout", "30", "-x", "FOO=bar", "--mpi-args=-tag-output", "python", "train.py", "--lr", "0.1"])
+    argv = horovodrun.mpirun_argv(a)
+    assert argv[0].endswith("bin/mpirun") and argv[1:5] == ["-np", "4", "-H", "localhost:4"]
+    assert argv[-4:] == ["python", "train.py", "--lr", "0.1"] and "-tag-output" in argv
+    exported = {argv[i + 1] for i, v in enumerate(argv) if v == "-x"}
+    assert {"HOROVOD_FUSION_THRESHOLD=33554432", "HOROVOD_CYCLE_TIME=2.5", "HOROVOD_CACHE_CAPACITY=0", "HOROVOD_TIMELINE=/tmp/t.json",
+            "HOROVOD_STALL_CHECK_DISABLE=1", "B200MPI_INIT_TIMEOUT_MS=30000", "FOO=bar"} <= exported
+    assert horovodrun.main(["--check-build"]) == 0 and "[X] PyTorch" in capsys.readouterr().out
+    assert horovodrun.main([]) == 2
+    if not horovodrun.MPIRUN.exists():
+        pytest.skip("native launcher not built (run make)")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import os, torch, horovod.torch as hvd; hvd.init(); "
+            "assert hvd.engine_stats()['cycle_time_ms'] == 3.0 and hvd.engine_stats()['cache_capacity'] == 7; "
+            "print('sum', float(hvd.allreduce(torch.ones(1), op=hvd.Sum))); hvd.shutdown()")
+    r = subprocess.run([sys.executable, "-m", "mpi_operator_b200.cmd.horovodrun", "-np", "2", "--cycle-time-ms", "3", "--cache-capacity", "7",
+                        sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
+                       env=dict(os.environ, PYTHONPATH=repo, B200MPI_HVD_DEVICE="cpu"), cwd=repo)
+    assert r.returncode == 0 and r.stdout.count("sum 2.0") == 2, r.stdout + r.stderr
