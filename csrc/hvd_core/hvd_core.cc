@@ -6,6 +6,9 @@
 #include "hvd_core.h"
 
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -355,6 +358,10 @@ struct Engine {
   uint32_t next_cache_id = 1;
   std::vector<unsigned char> fusion_host;
   std::vector<float> acc32;
+  // host data plane: per rank a {data, result} pair of `box` bytes in a segment of its own (unlinked as soon as every rank has
+  // mapped it); when it cannot be created the 64 KiB mailboxes of the rendezvous segment carry the data instead
+  unsigned char* seg = nullptr;
+  size_t seg_bytes = 0, box = 0;
   uint64_t last_stall_scan = 0;
   bool stall_shutdown_pending = false;
 
@@ -442,35 +449,69 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
   return 0;
 }
 
-// In-place allreduce of `count` elements through the mailboxes: publish a chunk, fold every rank's chunk in rank order
-// (bit-identical result on all ranks), next chunk. 16-bit floats accumulate in fp32.
+inline unsigned char* box_data(Engine* e, int r) { return e->seg ? e->seg + (size_t)r * 2 * e->box : e->rv.header()->slot[r].mailbox; }
+inline unsigned char* box_result(Engine* e, int r) { return e->seg + (size_t)r * 2 * e->box + e->box; }
+inline size_t box_bytes(Engine* e) { return e->seg ? e->box : kRvMailbox; }
+
+// acc = fold over ranks (in rank order) of n elements found at offset `off` of every rank's data box; result to `out`
+void fold_boxes(Engine* e, size_t off, size_t n, int dt, int op, void* out) {
+  const int W = e->world;
+  if (dt == HVD_F16 || dt == HVD_BF16) {
+    if (e->acc32.size() < n) e->acc32.resize(n);
+    float* a = e->acc32.data();
+    const uint16_t* s0 = (const uint16_t*)(box_data(e, 0) + off);
+    if (dt == HVD_F16) for (size_t i = 0; i < n; i++) a[i] = f16_to_f(s0[i]); else for (size_t i = 0; i < n; i++) a[i] = bf16_to_f(s0[i]);
+    for (int r = 1; r < W; r++) {
+      if (dt == HVD_F16) fold16<f16_to_f>(a, box_data(e, r) + off, n, op); else fold16<bf16_to_f>(a, box_data(e, r) + off, n, op);
+    }
+    uint16_t* o = (uint16_t*)out;
+    if (dt == HVD_F16) for (size_t i = 0; i < n; i++) o[i] = f_to_f16(a[i]); else for (size_t i = 0; i < n; i++) o[i] = f_to_bf16(a[i]);
+  } else {
+    memcpy(out, box_data(e, 0) + off, n * esize(dt));
+    for (int r = 1; r < W; r++) fold(out, box_data(e, r) + off, n, dt, op);
+  }
+}
+
+// In-place allreduce of `count` elements. Every chunk: publish it; barrier; with the data segment each rank folds ONE slice
+// of the chunk over all ranks (rank order: bit-identical everywhere) into its result box, barrier, everyone gathers the
+// slices — 1/W of the folding per rank and two barriers per `box` bytes; the next chunk's publish needs no extra barrier
+// because nobody reads data boxes while results are gathered. Without the segment (64 KiB mailboxes) every rank folds the
+// whole chunk itself. 16-bit floats accumulate in fp32.
 int host_allreduce(Engine* e, void* buf, int64_t count, int dt, int op) {
   std::string err;
-  const int W = e->world;
+  const int W = e->world, me = e->rank;
   const size_t es = esize(dt);
-  const size_t per = kRvMailbox / 8 * 8 / es;   // elements per chunk
-  b200mpi::RvHeader* H = e->rv.header();
+  const size_t per = box_bytes(e) / 8 * 8 / es;   // elements per chunk
   unsigned char* p = (unsigned char*)buf;
-  const bool half = dt == HVD_F16 || dt == HVD_BF16;
-  if (half && e->acc32.size() < per) e->acc32.resize(per);
   for (int64_t done = 0; done < count; done += (int64_t)per) {
     const size_t n = (size_t)std::min<int64_t>((int64_t)per, count - done);
-    memcpy(H->slot[e->rank].mailbox, p + (size_t)done * es, n * es);
+    unsigned char* o = p + (size_t)done * es;
+    memcpy(box_data(e, me), o, n * es);
     if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
-    if (half) {
-      float* a = e->acc32.data();
-      const uint16_t* s0 = (const uint16_t*)H->slot[0].mailbox;
-      if (dt == HVD_F16) for (size_t i = 0; i < n; i++) a[i] = f16_to_f(s0[i]); else for (size_t i = 0; i < n; i++) a[i] = bf16_to_f(s0[i]);
-      for (int r = 1; r < W; r++) {
-        if (dt == HVD_F16) fold16<f16_to_f>(a, H->slot[r].mailbox, n, op); else fold16<bf16_to_f>(a, H->slot[r].mailbox, n, op);
+    if (e->seg) {
+      const size_t lo = n * (size_t)me / (size_t)W, hi = n * (size_t)(me + 1) / (size_t)W;
+      if (hi > lo) fold_boxes(e, lo * es, hi - lo, dt, op, box_result(e, me) + lo * es);
+      if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+      for (int r = 0; r < W; r++) {
+        const size_t a = n * (size_t)r / (size_t)W, b = n * (size_t)(r + 1) / (size_t)W;
+        if (b > a) memcpy(o + a * es, box_result(e, r) + a * es, (b - a) * es);
       }
-      uint16_t* o = (uint16_t*)(p + (size_t)done * es);
-      if (dt == HVD_F16) for (size_t i = 0; i < n; i++) o[i] = f_to_f16(a[i]); else for (size_t i = 0; i < n; i++) o[i] = f_to_bf16(a[i]);
     } else {
-      unsigned char* o = p + (size_t)done * es;
-      memcpy(o, H->slot[0].mailbox, n * es);
-      for (int r = 1; r < W; r++) fold(o, H->slot[r].mailbox, n, dt, op);
+      fold_boxes(e, 0, n, dt, op, o);
+      if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
     }
+  }
+  return 0;
+}
+
+int host_bcast(Engine* e, void* buf, size_t bytes, int root) {
+  std::string err;
+  const size_t B = box_bytes(e);
+  for (size_t off = 0; off < bytes; off += B) {
+    const size_t n = std::min(B, bytes - off);
+    if (e->rank == root) memcpy(box_data(e, root), (char*)buf + off, n);
+    if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+    if (e->rank != root) memcpy((char*)buf + off, box_data(e, root), n);
     if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
   }
   return 0;
@@ -479,17 +520,17 @@ int host_allreduce(Engine* e, void* buf, int64_t count, int dt, int op) {
 int host_allgatherv(Engine* e, const void* in, void* out, const std::vector<int64_t>& counts) {
   std::string err;
   const int W = e->world;
-  b200mpi::RvHeader* H = e->rv.header();
+  const int64_t B = (int64_t)box_bytes(e);
   int64_t mx = 0;
   std::vector<int64_t> displ(W, 0);
   for (int r = 0; r < W; r++) { mx = std::max(mx, counts[r]); if (r) displ[r] = displ[r - 1] + counts[r - 1]; }
-  for (int64_t off = 0; off < mx; off += (int64_t)kRvMailbox) {
-    const int64_t mine = std::min<int64_t>((int64_t)kRvMailbox, counts[e->rank] - off);
-    if (mine > 0) memcpy(H->slot[e->rank].mailbox, (const char*)in + off, (size_t)mine);
+  for (int64_t off = 0; off < mx; off += B) {
+    const int64_t mine = std::min<int64_t>(B, counts[e->rank] - off);
+    if (mine > 0) memcpy(box_data(e, e->rank), (const char*)in + off, (size_t)mine);
     if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
     for (int r = 0; r < W; r++) {
-      const int64_t n = std::min<int64_t>((int64_t)kRvMailbox, counts[r] - off);
-      if (n > 0) memcpy((char*)out + displ[r] + off, H->slot[r].mailbox, (size_t)n);
+      const int64_t n = std::min<int64_t>(B, counts[r] - off);
+      if (n > 0) memcpy((char*)out + displ[r] + off, box_data(e, r), (size_t)n);
     }
     if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
   }
@@ -500,7 +541,7 @@ int host_allgatherv(Engine* e, const void* in, void* out, const std::vector<int6
 int host_alltoallv(Engine* e, const void* in, void* out, const std::vector<std::vector<int64_t>>& send) {
   std::string err;
   const int W = e->world, me = e->rank;
-  b200mpi::RvHeader* H = e->rv.header();
+  const int64_t B = (int64_t)box_bytes(e);
   std::vector<int64_t> sd(W, 0), rdp(W, 0);
   for (int r = 1; r < W; r++) { sd[r] = sd[r - 1] + send[me][r - 1]; rdp[r] = rdp[r - 1] + send[r - 1][me]; }
   if (send[me][me] > 0) memcpy((char*)out + rdp[me], (const char*)in + sd[me], (size_t)send[me][me]);
@@ -508,16 +549,49 @@ int host_alltoallv(Engine* e, const void* in, void* out, const std::vector<std::
     const int dst = (me + step) % W, src = (me - step + W) % W;
     int64_t mx = 0;
     for (int s = 0; s < W; s++) mx = std::max(mx, send[s][(s + step) % W]);
-    for (int64_t off = 0; off < mx; off += (int64_t)kRvMailbox) {
-      const int64_t ns = std::min<int64_t>((int64_t)kRvMailbox, send[me][dst] - off);
-      if (ns > 0) memcpy(H->slot[me].mailbox, (const char*)in + sd[dst] + off, (size_t)ns);
+    for (int64_t off = 0; off < mx; off += B) {
+      const int64_t ns = std::min<int64_t>(B, send[me][dst] - off);
+      if (ns > 0) memcpy(box_data(e, me), (const char*)in + sd[dst] + off, (size_t)ns);
       if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
-      const int64_t nr = std::min<int64_t>((int64_t)kRvMailbox, send[src][me] - off);
-      if (nr > 0) memcpy((char*)out + rdp[src] + off, H->slot[src].mailbox, (size_t)nr);
+      const int64_t nr = std::min<int64_t>(B, send[src][me] - off);
+      if (nr > 0) memcpy((char*)out + rdp[src] + off, box_data(e, src), (size_t)nr);
       if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
     }
   }
   return 0;
+}
+
+// Creates the data segment (rank 0), maps it everywhere, unlinks the name. Any failure on any rank -> nobody uses it.
+void open_data_segment(Engine* e) {
+  const size_t box = (size_t)std::max(64.0, env_d("B200MPI_HVD_MAILBOX_KB", 256.0)) * 1024;
+  const size_t bytes = (size_t)e->world * 2 * box;
+  char name[96];
+  snprintf(name, sizeof(name), "/b200mpi-hvd-%016llx", (unsigned long long)e->rv.header()->nonce);
+  std::string err;
+  unsigned char ok = 0;
+  int fd = -1;
+  if (env_d("B200MPI_HVD_MAILBOX_KB", 256.0) > 0) {
+    if (e->rank == 0) {
+      shm_unlink(name);
+      fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+      if (fd >= 0 && (ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0)) { close(fd); fd = -1; shm_unlink(name); }
+    }
+  }
+  std::vector<unsigned char> all(e->world);
+  ok = fd >= 0;
+  if (e->rv.allgather(&ok, all.data(), 1, e->timeout_ms, &err)) return;        // rank 0 created it?
+  if (all[0]) {
+    if (e->rank != 0) fd = shm_open(name, O_RDWR, 0600);
+    void* m = fd >= 0 ? mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+    if (fd >= 0) close(fd);
+    ok = m != MAP_FAILED;
+    e->rv.allgather(&ok, all.data(), 1, e->timeout_ms, &err);                   // everyone mapped it?
+    bool every = true;
+    for (unsigned char v : all) every = every && v;
+    if (e->rank == 0) shm_unlink(name);      // the mappings keep it alive; nothing is left behind if a rank crashes
+    if (every) { e->seg = (unsigned char*)m; e->seg_bytes = bytes; e->box = box; }
+    else if (m != MAP_FAILED) munmap(m, bytes);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ coordinator --
@@ -827,8 +901,8 @@ void run_single(Engine* e, Response& rs) {
     case HVD_BROADCAST: {
       const size_t nb = (size_t)q.count * esize(q.dtype);
       if (q.devkind == 0) {
-        std::string er;
-        if (e->rv.bcast(o ? o->out : nullptr, nb, q.root, e->timeout_ms, &er)) { rc = HVD_ERR_TRANSPORT; err = er; }
+        rc = host_bcast(e, o->out, nb, q.root);
+        if (rc) err = t_err;
       } else if (!e->has_gpu) { rc = HVD_ERR_UNSUPPORTED; err = "device tensor submitted but the engine was started without a GPU executor"; }
       else {
         typedef int (*bc_t)(void*, void*, size_t, int, void*);
@@ -1013,6 +1087,7 @@ void engine_main(Engine* e) {
   }
   if (e->stream && e->fusion_dev) { e->cu.StreamSynchronize(e->stream); e->cu.Free(e->fusion_dev); e->fusion_dev = nullptr; }
   e->tl.close();
+  if (e->seg) { munmap(e->seg, e->seg_bytes); e->seg = nullptr; }
 }
 
 }  // namespace
@@ -1049,6 +1124,7 @@ int hvdcore_init(const char* job_id, int rank, int world, const hvdcore_gpu_t* g
   const int init_timeout = (int)env_d("B200MPI_INIT_TIMEOUT_MS", env_d("B200MPI_TIMEOUT_MS", 60000));
   if (e->rv.attach(name, rank, world, gpu ? gpu->device : -1, init_timeout, &err)) return fail(HVD_ERR_TRANSPORT, err);
   g_generation++;
+  open_data_segment(e.get());
   const char* tlp = getenv("HOROVOD_TIMELINE");
   if (tlp && *tlp && rank == 0) e->tl.open(tlp);
   Engine* raw = e.release();
@@ -1153,13 +1229,13 @@ int hvdcore_stats_json(char* buf, size_t cap) {
     snprintf(tmp, sizeof(tmp),
              "{\"rank\": %d, \"world\": %d, \"cycles\": %llu, \"tensors\": %llu, \"fused_groups\": %llu, \"fused_tensors\": %llu, "
              "\"bytes\": %llu, \"cache_hits\": %llu, \"cache_misses\": %llu, \"negotiation_bytes\": %llu, \"stall_warnings\": %llu, "
-             "\"errors\": %llu, \"cycle_time_ms\": %.3f, \"fusion_threshold\": %lld, \"cache_capacity\": %d, \"gpu\": %s}",
+             "\"errors\": %llu, \"cycle_time_ms\": %.3f, \"fusion_threshold\": %lld, \"cache_capacity\": %d, \"gpu\": %s, \"mailbox_bytes\": %zu}",
              e->rank, e->world, (unsigned long long)e->st.cycles.load(), (unsigned long long)e->st.tensors.load(),
              (unsigned long long)e->st.groups.load(), (unsigned long long)e->st.fused_tensors.load(), (unsigned long long)e->st.bytes.load(),
              (unsigned long long)e->st.cache_hits.load(), (unsigned long long)e->st.cache_misses.load(),
              (unsigned long long)e->st.negotiation_bytes.load(), (unsigned long long)e->st.stall_warnings.load(),
              (unsigned long long)e->st.errors.load(), e->cycle_ms.load(), (long long)e->fusion_threshold.load(), e->cache_capacity,
-             e->has_gpu ? "true" : "false");
+             e->has_gpu ? "true" : "false", e->seg ? e->box : (size_t)kRvMailbox);
   }
   const size_t n = strlen(tmp);
   if (buf && cap) { const size_t k = n < cap - 1 ? n : cap - 1; memcpy(buf, tmp, k); buf[k] = 0; }
