@@ -333,7 +333,10 @@ def synchronize(handle=None):
     """Wait for an ``*_async`` handle and return its output."""
     import torch
     if hasattr(handle, "wait"):
-        return handle.wait()
+        out = handle.wait()
+        if isinstance(handle, _Done) and _on_gpu():   # direct path: the work is queued on the current stream
+            torch.cuda.current_stream().synchronize()
+        return out
     if _on_gpu():
         torch.cuda.current_stream().synchronize()
     return handle
