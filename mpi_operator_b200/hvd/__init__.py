@@ -22,7 +22,7 @@ small tensors, response cache, timeline, stall inspector, ``join()`` — the nat
 from __future__ import annotations
 
 import os
-from typing import Iterable, List, Optional
+
 
 from ..launch.env import rank_info_from_env
 from .exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
