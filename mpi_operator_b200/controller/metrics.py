@@ -20,6 +20,11 @@ allreduce_bytes = Counter("b200mpi_allreduce_bytes", "Bytes reduced by b200mpi a
 collective_calls = Counter("b200mpi_collective_calls", "Collective kernels launched by finished ranks", ["op", "algo"], registry=REGISTRY)
 collective_bytes = Counter("b200mpi_collective_bytes", "Payload bytes moved by collective kernels of finished ranks", ["op", "algo"],
                            registry=REGISTRY)
+hvd_tensors = Counter("b200mpi_hvd_tensors", "Collectives negotiated by the Horovod-core engine of finished ranks", registry=REGISTRY)
+hvd_fused_groups = Counter("b200mpi_hvd_fused_groups", "Fused allreduce groups executed by the engine", registry=REGISTRY)
+hvd_cache_hits = Counter("b200mpi_hvd_response_cache_hits", "Submissions sent as cached ids", registry=REGISTRY)
+hvd_negotiation_bytes = Counter("b200mpi_hvd_negotiation_bytes", "Bytes exchanged by the engine's negotiation", registry=REGISTRY)
+hvd_stall_warnings = Counter("b200mpi_hvd_stall_warnings", "Stall-inspector warnings", registry=REGISTRY)
 ranks_active = Gauge("b200mpi_ranks_active", "Ranks currently running under the node agent", registry=REGISTRY)
 gpu_slots_free = Gauge("b200mpi_gpu_slots_free", "Unallocated GPU slots on this box", registry=REGISTRY)
 reconcile_seconds = Histogram("mpi_operator_reconcile_duration_seconds", "Wall time of one syncHandler call",
@@ -36,6 +41,11 @@ def observe_rank_stats(stats: dict) -> None:
         collective_bytes.labels(op=op, algo=algo).inc(nbytes)
         if op.startswith("allreduce"):
             allreduce_bytes.labels(algo=algo).inc(nbytes)
+    h = stats.get("hvd") or {}     # hvd.engine_stats() of the rank (csrc/hvd_core), if the job used the Horovod front-end
+    for counter, key in ((hvd_tensors, "tensors"), (hvd_fused_groups, "fused_groups"), (hvd_cache_hits, "cache_hits"),
+                         (hvd_negotiation_bytes, "negotiation_bytes"), (hvd_stall_warnings, "stall_warnings")):
+        if int(h.get(key, 0)) > 0:
+            counter.inc(int(h[key]))
 
 
 def render() -> bytes:

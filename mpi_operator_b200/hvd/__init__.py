@@ -88,10 +88,27 @@ def _start_engine(info, dev) -> None:
         _atexit_registered = True
 
 
+def _dump_engine_stats(e) -> None:
+    """Per-rank engine counters for the operator's /metrics (the node agent harvests $B200MPI_STATS_DIR when the pod ends)."""
+    d = os.environ.get("B200MPI_STATS_DIR")
+    if not d:
+        return
+    try:
+        import json
+        os.makedirs(d, exist_ok=True)
+        path = os.path.join(d, f"stats-hvd-rank{e.rank}-{os.getpid()}.json")
+        with open(path + ".tmp", "w") as f:
+            json.dump({"rank": e.rank, "world": e.world, "ops": [], "hvd": e.stats()}, f)
+        os.replace(path + ".tmp", path)
+    except OSError:
+        pass
+
+
 def shutdown() -> None:
     e = _state["engine"]
     if e is not None:
         _state["engine"] = None
+        _dump_engine_stats(e)
         e.shutdown()
     c = _state["comm"]
     if c is not None:

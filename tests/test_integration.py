@@ -179,11 +179,15 @@ def test_horovod_mnist_example_runs_as_a_cpu_job(op):
     c0 = job.spec.replica("Launcher").template["spec"]["containers"][0]
     c0["args"] = list(c0["args"]) + ["--steps", "20", "--batch-size", "32"]      # keep the CPU test short
     c0["env"] = list(c0.get("env", [])) + [{"name": "B200MPI_HVD_DEVICE", "value": "cpu"}]
+    negotiated = metrics.counter_value(metrics.hvd_tensors)
     submit(op, job)
     wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", timeout=120, what="Succeeded")
     launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
     log = op.agent.logs("default", launcher["metadata"]["name"])
     assert "step 0 loss" in log and "final loss (averaged over 2 ranks)" in log
+    # the ranks' Horovod-core engines (broadcast_parameters, the final metric allreduce) report to /metrics through the agent
+    assert metrics.counter_value(metrics.hvd_tensors) >= negotiated + 2 * 9
+    assert "b200mpi_hvd_tensors_total" in metrics.render().decode()
 
 
 @needs_native
