@@ -6,9 +6,6 @@
 #include "hvd_core.h"
 
 #include <dlfcn.h>
-#include <fcntl.h>
-#include <sys/mman.h>
-#include <unistd.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -561,37 +558,13 @@ int host_alltoallv(Engine* e, const void* in, void* out, const std::vector<std::
   return 0;
 }
 
-// Creates the data segment (rank 0), maps it everywhere, unlinks the name. Any failure on any rank -> nobody uses it.
+// B200MPI_HVD_MAILBOX_KB (default 256, 0 = mailboxes only): box size of the engine's data segment (Rendezvous::open_boxes)
 void open_data_segment(Engine* e) {
-  const size_t box = (size_t)std::max(64.0, env_d("B200MPI_HVD_MAILBOX_KB", 256.0)) * 1024;
-  const size_t bytes = (size_t)e->world * 2 * box;
-  char name[96];
-  snprintf(name, sizeof(name), "/b200mpi-hvd-%016llx", (unsigned long long)e->rv.header()->nonce);
-  std::string err;
-  unsigned char ok = 0;
-  int fd = -1;
-  if (env_d("B200MPI_HVD_MAILBOX_KB", 256.0) > 0) {
-    if (e->rank == 0) {
-      shm_unlink(name);
-      fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
-      if (fd >= 0 && (ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0)) { close(fd); fd = -1; shm_unlink(name); }
-    }
-  }
-  std::vector<unsigned char> all(e->world);
-  ok = fd >= 0;
-  if (e->rv.allgather(&ok, all.data(), 1, e->timeout_ms, &err)) return;        // rank 0 created it?
-  if (all[0]) {
-    if (e->rank != 0) fd = shm_open(name, O_RDWR, 0600);
-    void* m = fd >= 0 ? mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
-    if (fd >= 0) close(fd);
-    ok = m != MAP_FAILED;
-    e->rv.allgather(&ok, all.data(), 1, e->timeout_ms, &err);                   // everyone mapped it?
-    bool every = true;
-    for (unsigned char v : all) every = every && v;
-    if (e->rank == 0) shm_unlink(name);      // the mappings keep it alive; nothing is left behind if a rank crashes
-    if (every) { e->seg = (unsigned char*)m; e->seg_bytes = bytes; e->box = box; }
-    else if (m != MAP_FAILED) munmap(m, bytes);
-  }
+  const double kb = env_d("B200MPI_HVD_MAILBOX_KB", 256.0);
+  if (kb <= 0) return;
+  const size_t box = (size_t)std::max(64.0, kb) * 1024;
+  e->seg = e->rv.open_boxes(box, e->timeout_ms, &e->seg_bytes);
+  e->box = e->seg ? box : 0;
 }
 
 // ------------------------------------------------------------------------------------------------ coordinator --
@@ -1087,7 +1060,7 @@ void engine_main(Engine* e) {
   }
   if (e->stream && e->fusion_dev) { e->cu.StreamSynchronize(e->stream); e->cu.Free(e->fusion_dev); e->fusion_dev = nullptr; }
   e->tl.close();
-  if (e->seg) { munmap(e->seg, e->seg_bytes); e->seg = nullptr; }
+  if (e->seg) { Rendezvous::close_boxes(e->seg, e->seg_bytes); e->seg = nullptr; }
 }
 
 }  // namespace

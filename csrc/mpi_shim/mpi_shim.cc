@@ -25,6 +25,13 @@ Rendezvous* g_rv = nullptr;
 int g_rank = 0, g_size = 1;
 bool g_init = false, g_final = false;
 int g_timeout_ms = 60000;
+// bulk-data boxes (Rendezvous::open_boxes): large collectives move `g_box` bytes per rank per step instead of 64 KiB, and a
+// reduction is folded slice-parallel (every rank reduces 1/world of each chunk); nullptr -> the mailboxes carry everything
+unsigned char* g_boxes = nullptr;
+size_t g_boxes_bytes = 0, g_box = 0;
+inline unsigned char* box_data(int r) { return g_boxes ? g_boxes + (size_t)r * 2 * g_box : g_rv->header()->slot[r].mailbox; }
+inline unsigned char* box_result(int r) { return g_boxes + (size_t)r * 2 * g_box + g_box; }
+inline size_t box_bytes() { return g_boxes ? g_box : b200mpi::kRvMailbox; }
 
 int env_first(std::initializer_list<const char*> names, int dflt) {
   for (const char* n : names) {
@@ -85,17 +92,30 @@ bool reduce_into(void* acc, const void* x, size_t n, MPI_Datatype t, MPI_Op op) 
 #undef CASEF
 }
 
-// out[r*bytes .. ] = rank r's `in` (bytes each), any size, chunked through the mailboxes
+// out[r*bytes .. ] = rank r's `in` (bytes each), any size, one box (or mailbox) per rank per step
 int allgather_bytes(const void* in, void* out, size_t bytes) {
   if (g_size == 1) { if (out != in) memmove(out, in, bytes); return MPI_SUCCESS; }
   std::string err;
-  const size_t chunk = b200mpi::kRvMailbox;
-  std::vector<unsigned char> tmp(chunk * g_size);
-  for (size_t done = 0; done < bytes || (bytes == 0 && done == 0); done += chunk) {
+  const size_t chunk = box_bytes();
+  for (size_t done = 0; done < bytes; done += chunk) {
     const size_t n = std::min(chunk, bytes - done);
-    if (g_rv->allgather((const char*)in + done, tmp.data(), n, g_timeout_ms, &err)) return fail(err);
-    for (int r = 0; r < g_size; r++) memcpy((char*)out + (size_t)r * bytes + done, tmp.data() + (size_t)r * n, n);
-    if (bytes == 0) break;
+    memcpy(box_data(g_rank), (const char*)in + done, n);
+    if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+    for (int r = 0; r < g_size; r++) memcpy((char*)out + (size_t)r * bytes + done, box_data(r), n);
+    if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+  }
+  return MPI_SUCCESS;
+}
+
+int bcast_bytes(void* buf, size_t bytes, int root) {
+  std::string err;
+  const size_t chunk = box_bytes();
+  for (size_t done = 0; done < bytes; done += chunk) {
+    const size_t n = std::min(chunk, bytes - done);
+    if (g_rank == root) memcpy(box_data(root), (char*)buf + done, n);
+    if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+    if (g_rank != root) memcpy((char*)buf + done, box_data(root), n);
+    if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
   }
   return MPI_SUCCESS;
 }
@@ -123,6 +143,11 @@ int MPI_Init(int*, char***) {
     if (g_rv->attach(id, g_rank, g_size, -1, g_timeout_ms, &err)) { fail("MPI_Init: " + err); return MPI_ERR_OTHER; }
     if (p2p_init()) return MPI_ERR_OTHER;
     if (g_rv->barrier(g_timeout_ms, &err)) { fail("MPI_Init: " + err); return MPI_ERR_OTHER; }   // every message socket is bound
+    const int kb = env_first({"B200MPI_MPI_MAILBOX_KB"}, 256);
+    if (kb > 0) {
+      g_box = (size_t)std::max(64, kb) * 1024;
+      g_boxes = g_rv->open_boxes(g_box, g_timeout_ms, &g_boxes_bytes);
+    }
   }
   g_init = true;
   return MPI_SUCCESS;
@@ -139,6 +164,8 @@ int MPI_Finalize(void) {
     std::string err;
     g_rv->barrier(g_timeout_ms, &err);
     p2p_shutdown();
+    Rendezvous::close_boxes(g_boxes, g_boxes_bytes);
+    g_boxes = nullptr;
     g_rv->detach(g_rank == 0);
     delete g_rv;
     g_rv = nullptr;
@@ -186,34 +213,52 @@ int MPI_Bcast(void* buf, int count, MPI_Datatype t, int root, MPI_Comm c) {
   if (c == MPI_COMM_SELF || g_size == 1) return MPI_SUCCESS;
   const size_t es = type_size(t);
   if (!es) return MPI_ERR_TYPE;
-  std::string err;
-  if (g_rv->bcast(buf, es * count, root, g_timeout_ms, &err)) return fail(err);
-  return MPI_SUCCESS;
+  return bcast_bytes(buf, es * (size_t)count, root);
 }
-// Gather one mailbox-sized chunk from every rank, fold it in rank order (deterministic), move on: O(world x 64 KiB) scratch
-// instead of world copies of the whole buffer.
+// Chunk by chunk: every rank publishes its chunk; with the boxes each rank folds ONE slice of it over all ranks (rank order:
+// the result is bit-identical everywhere) into its result box and the ranks that keep the result gather the slices; with the
+// mailboxes only, every keeper folds the whole chunk itself. Two barriers per chunk either way.
 static int reduce_impl(const void* send, void* recv, int count, MPI_Datatype t, MPI_Op op, int root, bool all) {
   const size_t es = type_size(t);
   if (!es) return MPI_ERR_TYPE;
   const size_t bytes = es * (size_t)count;
   const unsigned char* mine = static_cast<const unsigned char*>(send == MPI_IN_PLACE ? recv : send);
   if (g_size == 1) { if (send != MPI_IN_PLACE && (all || g_rank == root)) memmove(recv, send, bytes); return MPI_SUCCESS; }
-  const size_t chunk = b200mpi::kRvMailbox / 8 * 8;   // a whole number of elements of every supported type
-  std::vector<unsigned char> tmp(chunk * g_size), acc(chunk);
+  const size_t chunk = box_bytes() / 8 * 8;   // a whole number of elements of every supported type
   std::string err;
   const bool keep = all || g_rank == root;
-  for (size_t done = 0; done < bytes || (bytes == 0 && done == 0); done += chunk) {
-    const size_t n = std::min(chunk, bytes - done);
-    if (g_rv->allgather(mine + done, tmp.data(), n, g_timeout_ms, &err)) return fail(err);
-    if (keep && n) {
-      memcpy(acc.data(), tmp.data(), n);
-      for (int r = 1; r < g_size; r++)
-        if (!reduce_into(acc.data(), tmp.data() + (size_t)r * n, n / es, t, op)) return MPI_ERR_OP;
-      memcpy(static_cast<unsigned char*>(recv) + done, acc.data(), n);
+  const size_t W = (size_t)g_size, me = (size_t)g_rank;
+  int rc = MPI_SUCCESS;
+  for (size_t done = 0; done < bytes; done += chunk) {
+    const size_t n = std::min(chunk, bytes - done), ne = n / es;
+    unsigned char* out = static_cast<unsigned char*>(recv) + done;
+    memcpy(box_data(g_rank), mine + done, n);
+    if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+    if (g_boxes) {
+      const size_t lo = ne * me / W, hi = ne * (me + 1) / W;
+      if (hi > lo) {
+        unsigned char* acc = box_result(g_rank) + lo * es;
+        memcpy(acc, box_data(0) + lo * es, (hi - lo) * es);
+        for (int r = 1; r < g_size; r++)
+          if (!reduce_into(acc, box_data(r) + lo * es, hi - lo, t, op)) rc = MPI_ERR_OP;
+      }
+      if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+      if (keep)
+        for (size_t r = 0; r < W; r++) {
+          const size_t a = ne * r / W, b = ne * (r + 1) / W;
+          if (b > a) memcpy(out + a * es, box_result((int)r) + a * es, (b - a) * es);
+        }
+    } else {
+      if (keep) {
+        std::vector<unsigned char> acc(box_data(0), box_data(0) + n);
+        for (int r = 1; r < g_size; r++)
+          if (!reduce_into(acc.data(), box_data(r), ne, t, op)) rc = MPI_ERR_OP;
+        memcpy(out, acc.data(), n);
+      }
+      if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
     }
-    if (bytes == 0) break;
   }
-  return MPI_SUCCESS;
+  return rc;
 }
 int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) {
   int e = check(c); if (e) return e;
@@ -245,8 +290,7 @@ int MPI_Scatter(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Dataty
   const size_t bytes = type_size(st) * (size_t)sn;
   std::vector<unsigned char> all(bytes * g_size);
   if (g_rank == root) memcpy(all.data(), s, all.size());
-  std::string err;
-  if (g_size > 1 && g_rv->bcast(all.data(), all.size(), root, g_timeout_ms, &err)) return fail(err);
+  if (g_size > 1) { e = bcast_bytes(all.data(), all.size(), root); if (e) return e; }
   memcpy(r, all.data() + (size_t)g_rank * bytes, bytes);
   return MPI_SUCCESS;
 }

@@ -201,6 +201,40 @@ int Rendezvous::bcast(void* buf, size_t bytes, int root, int timeout_ms, std::st
   return 0;
 }
 
+unsigned char* Rendezvous::open_boxes(size_t box, int timeout_ms, size_t* total_bytes) {
+  if (!hdr_ || box == 0) return nullptr;
+  const size_t bytes = (size_t)world_ * 2 * box;
+  char name[96];
+  snprintf(name, sizeof(name), "/b200mpi-boxes-%016llx", (unsigned long long)hdr_->nonce);
+  std::string err;
+  int fd = -1;
+  if (rank_ == 0) {
+    shm_unlink(name);
+    fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+    // fallocate: fail here (and fall back) rather than SIGBUS later when /dev/shm is too small
+    if (fd >= 0 && (ftruncate(fd, (off_t)bytes) != 0 || posix_fallocate(fd, 0, (off_t)bytes) != 0)) { close(fd); fd = -1; shm_unlink(name); }
+  }
+  std::vector<unsigned char> all((size_t)world_);
+  unsigned char ok = fd >= 0;
+  if (allgather(&ok, all.data(), 1, timeout_ms, &err)) { if (fd >= 0) { close(fd); shm_unlink(name); } return nullptr; }
+  if (!all[0]) return nullptr;                       // rank 0 could not create it
+  if (rank_ != 0) fd = shm_open(name, O_RDWR, 0600);
+  void* m = fd >= 0 ? mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+  if (fd >= 0) close(fd);
+  ok = m != MAP_FAILED;
+  const int rc = allgather(&ok, all.data(), 1, timeout_ms, &err);   // has everyone mapped it?
+  if (rank_ == 0) shm_unlink(name);
+  bool every = rc == 0;
+  for (unsigned char v : all) every = every && v;
+  if (!every) { if (m != MAP_FAILED) munmap(m, bytes); return nullptr; }
+  if (total_bytes) *total_bytes = bytes;
+  return static_cast<unsigned char*>(m);
+}
+
+void Rendezvous::close_boxes(unsigned char* base, size_t total_bytes) {
+  if (base) munmap(base, total_bytes);
+}
+
 struct FdMsg { uint32_t src; uint32_t tag; };
 
 int Rendezvous::send_fd(int dst, uint32_t tag, int fd, std::string* err) {

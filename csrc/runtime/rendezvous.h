@@ -56,6 +56,12 @@ class Rendezvous {
   int allgather(const void* in, void* out, size_t bytes, int timeout_ms, std::string* err);
   // bulk broadcast/gather helpers used by the CPU libmpi shim
   int bcast(void* buf, size_t bytes, int root, int timeout_ms, std::string* err);
+  // Bulk-data boxes for host collectives: per rank a {data, result} pair of `box` bytes in a segment of its own, created by
+  // rank 0, mapped by every rank, then unlinked at once (the mappings keep it alive; nothing is left behind after a crash).
+  // Collective call. Returns the base address (rank r's data box = base + r * 2 * box, its result box follows) or nullptr when
+  // any rank could not create / map it (e.g. /dev/shm too small): callers then keep using the 64 KiB mailboxes.
+  unsigned char* open_boxes(size_t box, int timeout_ms, size_t* total_bytes);
+  static void close_boxes(unsigned char* base, size_t total_bytes);
   void heartbeat();
   void set_abort() { if (hdr_) hdr_->abort_flag.store(1); }
   bool aborted() const { return hdr_ && hdr_->abort_flag.load() != 0; }
