@@ -111,6 +111,40 @@ def cmd_get(cli: MPIJobClient, a) -> int:
     return 0
 
 
+def cmd_get_watch(cli: MPIJobClient, a) -> int:
+    """`get <kind> -w`: the table once, then one line per change (resourceVersion moved) — kubectl get -w."""
+    import time
+    rc = cmd_get(cli, a)
+    if rc:
+        return rc
+    res = KIND_ALIASES.get(a.kind.lower())
+    seen = {}
+    deadline = time.time() + a.watch_timeout if a.watch_timeout else None
+
+    def snapshot():
+        items = [cli.get_resource(res, a.namespace, a.name)] if a.name else cli.list_resource(res, None if a.all_namespaces else a.namespace)
+        return {(o["metadata"].get("namespace", ""), o["metadata"]["name"]): o for o in items}
+    try:
+        seen = {k: o["metadata"].get("resourceVersion") for k, o in snapshot().items()}
+        while deadline is None or time.time() < deadline:
+            time.sleep(0.2)
+            try:
+                cur = snapshot()
+            except ApiException:
+                cur = {}
+            for k, o in cur.items():
+                if seen.get(k) != o["metadata"].get("resourceVersion"):
+                    seen[k] = o["metadata"].get("resourceVersion")
+                    state = _job_state(o) if res == "mpijobs" else (o.get("status", {}).get("phase", "") if res == "pods" else "")
+                    print(f"{o['metadata']['name']:36} {state:10} {_age(o['metadata'].get('creationTimestamp')):6}", flush=True)
+            for k in [k for k in seen if k not in cur]:
+                del seen[k]
+                print(f"{k[1]:36} {'Deleted':10}", flush=True)
+    except KeyboardInterrupt:
+        pass
+    return 0
+
+
 def cmd_describe(cli: MPIJobClient, a) -> int:
     try:
         j = cli.get(a.name, a.namespace)
@@ -157,12 +191,37 @@ def cmd_delete(cli: MPIJobClient, a) -> int:
 
 
 def cmd_logs(cli: MPIJobClient, a) -> int:
-    try:
-        print(cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod), end="")
-        return 0
-    except ApiException as e:
-        print(f"error: {e}", file=sys.stderr)
-        return 1
+    """`logs <job>` prints the launcher's log (where mpirun multiplexes every rank's output); `-f` keeps printing what is
+    appended until the job finishes (kubectl logs -f)."""
+    import time
+    printed = 0
+    deadline = time.time() + a.timeout if getattr(a, "timeout", None) else None
+    while True:
+        try:
+            text = cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod)
+        except ApiException as e:
+            if not getattr(a, "follow", False) or printed:
+                print(f"error: {e}", file=sys.stderr)
+                return 1
+            text = ""          # -f before the launcher pod exists: keep waiting
+        if len(text) < printed:   # the container restarted: its log starts over
+            printed = 0
+        sys.stdout.write(text[printed:])
+        sys.stdout.flush()
+        printed = len(text)
+        if not getattr(a, "follow", False):
+            return 0
+        try:
+            done = _job_state(cli.get(a.name, a.namespace)) in ("Succeeded", "Failed")
+        except ApiException:
+            done = True
+        if done:
+            tail = cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod) if printed else ""
+            sys.stdout.write(tail[printed:])
+            return 0
+        if deadline and time.time() > deadline:
+            return 1
+        time.sleep(0.25)
 
 
 def cmd_scale(cli: MPIJobClient, a) -> int:
@@ -243,6 +302,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     p.add_argument("name", nargs="?")
     p.add_argument("-o", "--output", default="")
     p.add_argument("-A", "--all-namespaces", action="store_true")
+    p.add_argument("-w", "--watch", action="store_true", help="after listing, print a line whenever an object changes")
+    p.add_argument("--watch-timeout", type=float, default=None, help="with -w: stop after this many seconds")
     p = sub.add_parser("describe")
     p.add_argument("kind", nargs="?", default="mpijob")
     p.add_argument("name")
@@ -253,6 +314,8 @@ def main(argv: Optional[List[str]] = None) -> int:
     p.add_argument("name")
     p.add_argument("--worker", type=int, default=None)
     p.add_argument("--pod", default=None)
+    p.add_argument("-f", "--follow", action="store_true", help="stream the log until the job finishes")
+    p.add_argument("--timeout", type=float, default=None, help="with -f: give up after this many seconds")
     p = sub.add_parser("scale")
     p.add_argument("name")
     p.add_argument("--replicas", type=int, required=True)
@@ -284,7 +347,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     if a.cmd in ("apply", "create"):
         return cmd_apply(cli, a)
     if a.cmd == "get":
-        return cmd_get(cli, a)
+        return cmd_get_watch(cli, a) if a.watch else cmd_get(cli, a)
     if a.cmd == "describe":
         return cmd_describe(cli, a)
     if a.cmd == "delete":

@@ -129,3 +129,21 @@ def test_horovodrun_maps_its_flags_onto_mpirun_and_the_engine(tmp_path, capsys):
                         sys.executable, "-c", code], capture_output=True, text=True, timeout=120,
                        env=dict(os.environ, PYTHONPATH=repo, B200MPI_HVD_DEVICE="cpu"), cwd=repo)
     assert r.returncode == 0 and r.stdout.count("sum 2.0") == 2, r.stdout + r.stderr
+
+
+def test_logs_follow_and_get_watch(server, tmp_path):
+    """kubectl habits from the reference's README (`kubectl logs -f`, `kubectl get -w`): follow the launcher log until the job
+    finishes; watch prints one line per state change."""
+    f = tmp_path / "job.yaml"
+    f.write_text(JOB.replace("name: cli", "name: follow").replace("echo launcher-says-hi; sleep 0.3",
+                                                                     "for i in 1 2 3; do echo tick-$i; sleep 0.4; done"))
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    watch = subprocess.Popen([sys.executable, "-m", "mpi_operator_b200.cmd.mpijobctl", "--server", server, "get", "mpijobs", "-w",
+                              "--watch-timeout", "6"], stdout=subprocess.PIPE, text=True, cwd=repo)
+    assert ctl(server, "apply", "-f", str(f))[0] == 0
+    rc, out, err = ctl(server, "logs", "follow", "-f", "--timeout", "30")
+    assert rc == 0 and [l for l in out.splitlines() if l.startswith("tick-")] == ["tick-1", "tick-2", "tick-3"], (out, err)
+    wout, _ = watch.communicate(timeout=30)
+    assert watch.returncode == 0 and "NAME" in wout and "Succeeded" in wout and wout.count("follow") >= 2, wout   # several change lines
