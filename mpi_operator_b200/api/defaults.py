@@ -37,6 +37,19 @@ def set_defaults_run_policy(job: MPIJob) -> None:
         job.spec.run_policy.clean_pod_policy = C.CLEAN_POD_POLICY_NONE
 
 
+def normalize_pod_template(spec: ReplicaSpec | None) -> None:
+    """Not in the reference (there the API server's schema rejects it): a container ``command`` / ``args`` given as one
+    string becomes a one-element list. The reference's own SDK example passes ``command="mpirun"``
+    (sdk/python/v2beta1/tensorflow-mnist.py:30,44-47); without an API-server schema in front of us, accept what it means."""
+    if spec is None or not isinstance(spec.template, dict):
+        return
+    for c in ((spec.template.get("spec") or {}).get("containers") or []):
+        if isinstance(c, dict):
+            for key in ("command", "args"):
+                if isinstance(c.get(key), str):
+                    c[key] = [c[key]]
+
+
 def set_defaults_mpijob(job: MPIJob) -> MPIJob:
     """default.go:60-80. Mutates and returns ``job``."""
     set_defaults_run_policy(job)
@@ -51,4 +64,6 @@ def set_defaults_mpijob(job: MPIJob) -> MPIJob:
     specs = job.spec.mpi_replica_specs or {}
     set_defaults_launcher(specs.get(C.REPLICA_TYPE_LAUNCHER))
     set_defaults_worker(specs.get(C.REPLICA_TYPE_WORKER))
+    for rs in specs.values():
+        normalize_pod_template(rs)
     return job

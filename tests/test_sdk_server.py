@@ -1,6 +1,7 @@
 """SDK models / ApiClient (reference: sdk/python/v2beta1/test/*.py stubs + mpijob/api_client.py) and the
 daemon's REST surface, leader election, healthz, metrics (cmd/mpi-operator/app/server.go)."""
 import json
+import os
 import socket
 import time
 import urllib.request
@@ -138,3 +139,57 @@ def test_models_match_the_reference_sdk_when_installed():
         norm = {k: v.replace("IoK8sApimachineryPkgApisMetaV1", "V1") for k, v in types.items()}
         assert ours.openapi_types == norm, name
     assert mpijob.models.MODEL_CLASSES["IoK8sApimachineryPkgApisMetaV1ObjectMeta"] is mpijob.V1ObjectMeta
+
+
+def test_reference_sdk_example_runs_unmodified_through_the_kubernetes_shim(tmp_path):
+    """The reference's own SDK example (sdk/python/v2beta1/tensorflow-mnist.py: kubernetes.client models, the stale
+    `mpijob.V1ReplicaSpec` import, `config.load_kube_config()`, `CustomObjectsApi().create_namespaced_custom_object`) is
+    executed as is against the single-box daemon through the in-tree `kubernetes` compatibility package."""
+    import socket
+    import subprocess
+    import sys
+    ref = "/root/reference/sdk/python/v2beta1/tensorflow-mnist.py"
+    if not os.path.exists(ref):
+        pytest.skip("reference tree not mounted")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    op = Operator(ServerOption(fake_gpus=2, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    op.start()
+    try:
+        repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        # run a byte-identical copy from an empty directory: next to the original lies the reference's own `mpijob` package,
+        # with which the example cannot even be imported (it no longer defines V1ReplicaSpec)
+        script = tmp_path / "tensorflow-mnist.py"
+        script.write_bytes(open(ref, "rb").read())
+        r = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=60, cwd=str(tmp_path),
+                           env=dict(os.environ, PYTHONPATH=repo, MPIJOB_SERVER=f"127.0.0.1:{port}"))
+        assert r.returncode == 0, r.stdout + r.stderr
+        from kubernetes import client, config, watch
+        config.load_kube_config(host=f"127.0.0.1:{port}")
+        api = client.CustomObjectsApi()
+        job = api.get_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist")
+        assert job["spec"]["mpiReplicaSpecs"]["Worker"]["replicas"] == 2 and job["spec"]["slotsPerWorker"] == 1
+        c = job["spec"]["mpiReplicaSpecs"]["Launcher"]["template"]["spec"]["containers"][0]
+        assert c["resources"] == {"limits": {"cpu": "1", "memory": "2Gi"}} and c["args"][:2] == ["-np", "2"]
+        # the example passes command="mpirun" (a string); the launcher pod the controller builds has the list form
+        launchers = [p for p in client.CoreV1Api().list_namespaced_pod("default", label_selector="training.kubeflow.org/job-role=launcher").items]
+        deadline = time.time() + 10
+        while not launchers and time.time() < deadline:
+            time.sleep(0.1)
+            launchers = client.CoreV1Api().list_namespaced_pod("default", label_selector="training.kubeflow.org/job-role=launcher").items
+        assert launchers and launchers[0].spec.containers[0].command == ["mpirun"] and launchers[0].metadata.name.startswith("tensorflow-mnist-launcher")
+        assert [j["metadata"]["name"] for j in api.list_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs")["items"]] == ["tensorflow-mnist"]
+        assert [j["metadata"]["name"] for j in api.list_cluster_custom_object("kubeflow.org", "v2beta1", "mpijobs")["items"]] == ["tensorflow-mnist"]
+        ev = next(iter(watch.Watch().stream(api.list_namespaced_custom_object, "kubeflow.org", "v2beta1", "default", "mpijobs", timeout_seconds=5)))
+        assert ev["type"] == "ADDED" and ev["object"]["metadata"]["name"] == "tensorflow-mnist"
+        api.patch_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist", {"spec": {"runPolicy": {"suspend": True}}})
+        assert api.get_namespaced_custom_object_status("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist")["spec"]["runPolicy"]["suspend"] is True
+        with pytest.raises(client.rest.ApiException):
+            api.get_namespaced_custom_object("example.com", "v1", "default", "widgets", "x")
+        core = client.CoreV1Api()
+        assert isinstance(core.list_namespaced_pod("default").items, list)
+        api.delete_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist")
+        with pytest.raises(client.rest.ApiException):
+            api.get_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist")
+    finally:
+        op.stop()
