@@ -341,7 +341,7 @@ struct Engine {
   std::atomic<double> cycle_ms{1.0}, stall_check_s{60.0}, stall_shutdown_s{0.0};
   std::atomic<int64_t> fusion_threshold{64ll << 20};
   int cache_capacity = 1024;
-  bool stall_check = true;
+  bool stall_check = true, mark_cycles = false;
   int timeout_ms = 600000;
 
   // engine-thread state
@@ -1034,6 +1034,8 @@ void engine_main(Engine* e) {
     if (exchange(e, w.s, flags, &msgs, &all_flags, &fusion)) { fail_everything(e, HVD_ERR_TRANSPORT, "hvdcore: " + t_err); break; }
     std::vector<Response> rsp;
     coordinate(e, msgs, &rsp);
+    if (e->mark_cycles && !rsp.empty() && e->tl.on())   // HOROVOD_TIMELINE_MARK_CYCLES: a tick on row 0 for every cycle with work
+      e->tl.ev(0, 'i', "CYCLE_START", "\"cycle\": " + std::to_string(e->cycle_no) + ", \"responses\": " + std::to_string(rsp.size()));
     // 3. fused execution
     execute(e, rsp, fusion);
     if (!e->gpu_inflight.empty()) gpu_poll(e, false);
@@ -1081,6 +1083,7 @@ int hvdcore_init(const char* job_id, int rank, int world, const hvdcore_gpu_t* g
   e->fusion_threshold = (int64_t)env_d("HOROVOD_FUSION_THRESHOLD", (double)(64ll << 20));
   e->cache_capacity = (int)env_d("HOROVOD_CACHE_CAPACITY", 1024);
   e->stall_check = env_d("HOROVOD_STALL_CHECK_DISABLE", 0) == 0;
+  e->mark_cycles = env_d("HOROVOD_TIMELINE_MARK_CYCLES", 0) != 0;
   e->stall_check_s = env_d("HOROVOD_STALL_CHECK_TIME_SECONDS", 60);
   e->stall_shutdown_s = env_d("HOROVOD_STALL_SHUTDOWN_TIME_SECONDS", 0);
   e->timeout_ms = (int)env_d("B200MPI_HVD_TIMEOUT_MS", 600000);

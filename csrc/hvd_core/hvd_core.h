@@ -12,8 +12,8 @@
  * Single-box redesign: there is no coordinator rank and no MPI. Every cycle each rank publishes its new requests in
  * the job's shared-memory rendezvous segment (csrc/runtime/rendezvous.h), every rank reads all of them and runs the
  * SAME deterministic state machine, so all ranks derive the identical fused response list without a second message.
- * Host tensors are reduced through the segment's mailboxes; device tensors go to the b200mpi kernels on the engine's
- * own stream and communicator.
+ * Host tensors are reduced through a bulk-data segment (Rendezvous::open_boxes; slice-parallel fold), device tensors by the
+ * b200mpi kernels on the engine's own stream and communicator.
  *
  * All functions return 0 or a negative code unless stated; hvdcore_last_error() is thread-local.
  */
@@ -69,7 +69,7 @@ typedef struct {
 /* Attaches to the rendezvous segment "<job_id>-hvd" and starts the background thread. `gpu` may be NULL (host only).
  * Tunables are read from the environment like Horovod's: HOROVOD_CYCLE_TIME (ms, default 1), HOROVOD_FUSION_THRESHOLD
  * (bytes, default 64 MiB), HOROVOD_CACHE_CAPACITY (default 1024, 0 disables), HOROVOD_TIMELINE (path, rank 0 writes),
- * HOROVOD_STALL_CHECK_DISABLE, HOROVOD_STALL_CHECK_TIME_SECONDS (60), HOROVOD_STALL_SHUTDOWN_TIME_SECONDS (0 = never). */
+ * HOROVOD_TIMELINE_MARK_CYCLES, HOROVOD_STALL_CHECK_DISABLE, HOROVOD_STALL_CHECK_TIME_SECONDS (60), HOROVOD_STALL_SHUTDOWN_TIME_SECONDS (0 = never). */
 int hvdcore_init(const char* job_id, int rank, int world, const hvdcore_gpu_t* gpu);
 /* Tells every rank's engine to stop after the current cycle; outstanding handles fail with HVD_ERR_SHUTDOWN. */
 int hvdcore_shutdown(void);
