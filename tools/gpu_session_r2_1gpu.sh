@@ -13,6 +13,10 @@ B200MPI_ASYNC_H2D=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/nul
 B200MPI_ASYNC_H2D=1 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_asynch2d_bf16params.json
 echo "=== 3. tcgen05 GEMM + BN statistics (each case in its own process, bounded waits) ==="
 B200MPI_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_zz_gemm_bnstats_gpu.py -q --timeout=200 2>&1 | tail -15
+echo "=== 3b. GEMM micro-benchmark vs cuBLAS + statistics pass, and one full ncu capture of the kernel (only if step 3 passed) ==="
+B200MPI_EXPERIMENTAL=1 timeout 300 python benchmarks/gemm_bnstats_bench.py --out gpurun_out/gemm_bnstats_bench.json 2>&1 | tail -14
+B200MPI_EXPERIMENTAL=1 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_gemm_bnstats -c 1 -o gpurun_out/prof_gemm_bnstats \
+  python benchmarks/gemm_bnstats_bench.py --iters 1 > gpurun_out/ncu_gemm.log 2>&1
 echo "=== 4. bench with the tensor-core 1x1 path (only meaningful if step 3 passed) ==="
 B200MPI_FUSED_CONV1X1=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1.json
 B200MPI_FUSED_CONV1X1=1 B200MPI_BF16_PARAMS=1 timeout 200 python bench.py --steps 20 --warmup 5 2>/dev/null | tail -1 | tee gpurun_out/bench_conv1x1_bf16params.json
