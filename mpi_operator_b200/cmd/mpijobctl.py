@@ -112,34 +112,22 @@ def cmd_get(cli: MPIJobClient, a) -> int:
 
 
 def cmd_get_watch(cli: MPIJobClient, a) -> int:
-    """`get <kind> -w`: the table once, then one line per change (resourceVersion moved) — kubectl get -w."""
-    import time
+    """`get <kind> -w`: the table once, then one line per event of the server's `?watch=true` stream — kubectl get -w."""
     rc = cmd_get(cli, a)
     if rc:
         return rc
     res = KIND_ALIASES.get(a.kind.lower())
-    seen = {}
-    deadline = time.time() + a.watch_timeout if a.watch_timeout else None
-
-    def snapshot():
-        items = [cli.get_resource(res, a.namespace, a.name)] if a.name else cli.list_resource(res, None if a.all_namespaces else a.namespace)
-        return {(o["metadata"].get("namespace", ""), o["metadata"]["name"]): o for o in items}
+    ns = None if a.all_namespaces else a.namespace
     try:
-        seen = {k: o["metadata"].get("resourceVersion") for k, o in snapshot().items()}
-        while deadline is None or time.time() < deadline:
-            time.sleep(0.2)
-            try:
-                cur = snapshot()
-            except ApiException:
-                cur = {}
-            for k, o in cur.items():
-                if seen.get(k) != o["metadata"].get("resourceVersion"):
-                    seen[k] = o["metadata"].get("resourceVersion")
-                    state = _job_state(o) if res == "mpijobs" else (o.get("status", {}).get("phase", "") if res == "pods" else "")
-                    print(f"{o['metadata']['name']:36} {state:10} {_age(o['metadata'].get('creationTimestamp')):6}", flush=True)
-            for k in [k for k in seen if k not in cur]:
-                del seen[k]
-                print(f"{k[1]:36} {'Deleted':10}", flush=True)
+        listed = [cli.get_resource(res, a.namespace, a.name)] if a.name else cli.list_resource(res, ns)
+        shown = {(o["metadata"].get("namespace", ""), o["metadata"]["name"]): o["metadata"].get("resourceVersion") for o in listed}
+        for ev in cli.watch(res, ns, timeout=a.watch_timeout or 3600.0, name=a.name):
+            o = ev["object"]
+            key = (o["metadata"].get("namespace", ""), o["metadata"]["name"])
+            if ev["type"] == "ADDED" and shown.get(key) == o["metadata"].get("resourceVersion"):
+                continue          # the stream first replays what the table already showed
+            state = "Deleted" if ev["type"] == "DELETED" else (_job_state(o) if res == "mpijobs" else (o.get("status", {}).get("phase", "") if res == "pods" else ""))
+            print(f"{o['metadata']['name']:36} {state:10} {_age(o['metadata'].get('creationTimestamp')):6}", flush=True)
     except KeyboardInterrupt:
         pass
     return 0

@@ -272,11 +272,53 @@ def _make_handler(op: Operator):
                 sel = None
                 if "labelSelector" in q:
                     sel = dict(kv.split("=", 1) for kv in q["labelSelector"][0].split(",") if "=" in kv)
+                if q.get("watch", ["false"])[0].lower() in ("true", "1"):
+                    return self._watch(res, ns, sel, q)
                 items = store.list(res, ns or None, sel)
                 api_version, kind, _ = RESOURCES[res]
                 return self._send(200, {"apiVersion": api_version, "kind": kind + "List", "metadata": {}, "items": items})
             except errors.ApiError as e:
                 return self._send(e.code, e.to_status())
+
+        def _watch(self, res, ns, sel, q):
+            """`?watch=true` (what client-go informers and `kubectl get -w` use): one JSON object per line,
+            {"type": ADDED|MODIFIED|DELETED, "object": ...}, chunked, existing objects first, until `timeoutSeconds` (default
+            300) or the client goes away. Filters: namespace of the path, `labelSelector`, `fieldSelector=metadata.name=<n>`."""
+            import queue
+            events: "queue.Queue" = queue.Queue()
+            name_filter = None
+            for term in (q.get("fieldSelector", [""])[0].split(",") if "fieldSelector" in q else []):
+                k, _, v = term.partition("=")
+                if k.strip() == "metadata.name":
+                    name_filter = v.strip().lstrip("=")
+
+            def wanted(o) -> bool:
+                md = o.get("metadata", {})
+                if ns and md.get("namespace", "") != ns:
+                    return False
+                if name_filter and md.get("name") != name_filter:
+                    return False
+                return not sel or all((md.get("labels") or {}).get(k) == v for k, v in sel.items())
+            cancel = store.watch(res, lambda t, o, old: events.put((t, o)) if wanted(o) else None, replay=True)
+            try:
+                deadline = time.time() + float(q.get("timeoutSeconds", ["300"])[0])
+                self.send_response(200)
+                self.send_header("Content-Type", "application/json")
+                self.send_header("Transfer-Encoding", "chunked")
+                self.end_headers()
+                while time.time() < deadline:
+                    try:
+                        t, o = events.get(timeout=min(1.0, max(0.05, deadline - time.time())))
+                    except queue.Empty:
+                        continue
+                    line = (json.dumps({"type": t, "object": o}) + "\n").encode()
+                    self.wfile.write(b"%x\r\n" % len(line) + line + b"\r\n")
+                    self.wfile.flush()
+                self.wfile.write(b"0\r\n\r\n")
+            except (BrokenPipeError, ConnectionResetError, OSError):
+                self.close_connection = True
+            finally:
+                cancel()
 
         def _admit(self, res, obj):
             """API-server side admission for MPIJobs: CRD schema defaults + structural validation."""

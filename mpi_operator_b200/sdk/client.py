@@ -134,6 +134,38 @@ class MPIJobClient:
         data = self.api.call_api(self._path("pods", namespace, pod, "log"), "GET", response_type="raw")
         return data.decode(errors="replace")
 
+    def watch(self, resource: str = "mpijobs", namespace: Optional[str] = "default", timeout: float = 300.0,
+              label_selector: Optional[str] = None, name: Optional[str] = None):
+        """Generator over the server's `?watch=true` stream: ``{"type": "ADDED" | "MODIFIED" | "DELETED", "object": {...}}``,
+        existing objects first, until ``timeout`` seconds have passed (then the generator ends)."""
+        import http.client
+        import json
+        import urllib.parse
+        u = urllib.parse.urlparse(self.api.configuration.host)
+        q = {"watch": "true", "timeoutSeconds": repr(float(timeout))}
+        if label_selector:
+            q["labelSelector"] = label_selector
+        if name:
+            q["fieldSelector"] = f"metadata.name={name}"
+        conn = http.client.HTTPConnection(u.hostname, u.port or 80, timeout=timeout + 10)
+        try:
+            conn.request("GET", self._path(resource, namespace) + "?" + urllib.parse.urlencode(q))
+            resp = conn.getresponse()
+            if resp.status != 200:
+                raise ApiException(status=resp.status, reason=resp.reason, body=resp.read())
+            buf = b""
+            while True:
+                chunk = resp.read1(65536)
+                if not chunk:
+                    return
+                buf += chunk
+                while b"\n" in buf:
+                    line, buf = buf.split(b"\n", 1)
+                    if line.strip():
+                        yield json.loads(line)
+        finally:
+            conn.close()
+
     # ------------------------------------------------------- generic access --
     def list_resource(self, resource: str, namespace: Optional[str] = "default") -> List[Dict[str, Any]]:
         return self.api.call_api(self._path(resource, namespace), "GET")["items"]

@@ -193,3 +193,41 @@ def test_reference_sdk_example_runs_unmodified_through_the_kubernetes_shim(tmp_p
             api.get_namespaced_custom_object("kubeflow.org", "v2beta1", "default", "mpijobs", "tensorflow-mnist")
     finally:
         op.stop()
+
+
+def test_watch_stream_delivers_added_modified_deleted_in_order(tmp_path):
+    """`GET ...?watch=true` (client-go informers / `kubectl get -w` in the reference): existing objects first,
+    then every change as it happens, filtered by namespace / label selector / metadata.name, until timeoutSeconds."""
+    import threading
+    from mpi_operator_b200.sdk import MPIJobClient
+    from helpers import new_mpijob
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    op = Operator(ServerOption(fake_gpus=2, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    try:
+        cli = MPIJobClient(f"127.0.0.1:{port}")       # controller not started: only what this test writes changes the store
+        cli.create(new_mpijob("old", workers=1))
+        got, done = [], threading.Event()
+
+        def consume():
+            for ev in cli.watch("mpijobs", "default", timeout=3.0):
+                got.append((ev["type"], ev["object"]["metadata"]["name"]))
+            done.set()
+        t = threading.Thread(target=consume)
+        t.start()
+        deadline = time.time() + 5
+        while not got and time.time() < deadline:
+            time.sleep(0.02)
+        cli.create(new_mpijob("new", workers=1))
+        cli.create(new_mpijob("elsewhere", namespace="other", workers=1))          # other namespace: filtered out
+        cli.patch("new", {"metadata": {"labels": {"team": "a"}}})
+        cli.delete("old")
+        assert done.wait(10)
+        t.join()
+        assert got == [("ADDED", "old"), ("ADDED", "new"), ("MODIFIED", "new"), ("DELETED", "old")], got
+        by_name = [(e["type"], e["object"]["metadata"]["name"]) for e in cli.watch("mpijobs", None, timeout=0.5, name="elsewhere")]
+        assert by_name == [("ADDED", "elsewhere")]
+        by_label = [e["object"]["metadata"]["name"] for e in cli.watch("mpijobs", "default", timeout=0.5, label_selector="team=a")]
+        assert by_label == ["new"]
+    finally:
+        op.stop()
