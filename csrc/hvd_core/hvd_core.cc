@@ -38,7 +38,7 @@ int fail(int code, const std::string& msg) { t_err = msg; return code; }
 
 constexpr size_t kInline = 248;          // negotiation bytes that ride in the first (small) exchange of a cycle
 constexpr size_t kMaxBlob = 1024;        // HVD_EXCHANGE payload limit
-constexpr uint32_t kFlagShutdown = 1u, kFlagStallShutdown = 2u;
+constexpr uint32_t kFlagShutdown = 1u, kFlagStallShutdown = 2u, kFlagAutotune = 4u;   // autotune: rank 0's tunables are adopted by all
 const char* const kOpName[] = {"ALLREDUCE", "ALLGATHER", "BROADCAST", "ALLTOALL", "BARRIER", "JOIN", "EXCHANGE"};
 
 size_t esize(int dt) {
@@ -361,6 +361,14 @@ struct Engine {
   size_t seg_bytes = 0, box = 0;
   uint64_t last_stall_scan = 0;
   bool stall_shutdown_pending = false;
+  // HOROVOD_AUTOTUNE (rank 0 decides, see autotune_step): grid search over {cycle time} x {fusion threshold}, scored by
+  // reduced bytes per second over windows of busy cycles
+  bool autotune = false, autotune_done = false;
+  int at_warmup = 3, at_steps = 10, at_idx = -1, at_busy = 0, at_best = -1;
+  uint64_t at_bytes0 = 0, at_t0 = 0, at_samples = 0;
+  double at_best_score = 0;
+  std::vector<std::pair<double, int64_t>> at_grid;
+  FILE* at_log = nullptr;
 
   // gpu
   bool has_gpu = false;
@@ -406,10 +414,11 @@ void finish_local(Engine* e, const std::string& name, int status, const std::str
 int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std::string>* all, uint32_t* all_flags, int64_t* fusion) {
   std::string err;
   const int W = e->world;
-  struct Hdr { uint32_t len, flags; int64_t fusion; };   // fusion threshold: the smallest one wins, so groups agree
+  // fusion threshold: the smallest one wins, so groups agree — unless rank 0 is autotuning, then its threshold and cycle time are adopted
+  struct Hdr { uint32_t len, flags; int64_t fusion; double cycle_ms; };
   unsigned char small[sizeof(Hdr) + kInline];
   memset(small, 0, sizeof(small));
-  Hdr h{(uint32_t)mine.size(), flags, e->fusion_threshold.load()};
+  Hdr h{(uint32_t)mine.size(), flags, e->fusion_threshold.load(), e->cycle_ms.load()};
   *fusion = h.fusion;
   memcpy(small, &h, sizeof(h));
   memcpy(small + sizeof(h), mine.data(), std::min(mine.size(), kInline));
@@ -417,6 +426,8 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
   if (e->rv.allgather(small, got.data(), sizeof(small), e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
   all->assign(W, std::string());
   *all_flags = 0;
+  int64_t tuned_fusion = -1;
+  double tuned_cycle = 0;
   size_t max_len = 0;
   std::vector<size_t> lens(W);
   for (int r = 0; r < W; r++) {
@@ -424,9 +435,14 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
     memcpy(&hr, got.data() + (size_t)r * sizeof(small), sizeof(hr));
     *all_flags |= hr.flags;
     *fusion = std::min(*fusion, hr.fusion);
+    if (r == 0 && (hr.flags & kFlagAutotune)) { tuned_fusion = hr.fusion; tuned_cycle = hr.cycle_ms; }
     lens[r] = hr.len;
     max_len = std::max(max_len, (size_t)hr.len);
     (*all)[r].assign((const char*)got.data() + (size_t)r * sizeof(small) + sizeof(hr), std::min((size_t)hr.len, kInline));
+  }
+  if (tuned_fusion >= 0) {   // every rank runs with the values rank 0 is currently trying (or has settled on)
+    *fusion = tuned_fusion;
+    if (e->rank != 0) { e->fusion_threshold = tuned_fusion; e->cycle_ms = tuned_cycle; }
   }
   size_t off = kInline;
   std::vector<unsigned char> big, mine_chunk;
@@ -979,6 +995,33 @@ void stall_scan(Engine* e, uint32_t* flags) {
   if (kill && e->rank == 0) *flags |= kFlagStallShutdown;   // the decision travels with the next exchange so every rank stops in the same cycle
 }
 
+// ---------------------------------------------------------------------------------------------------- autotune --
+// Rank 0 only. A "step" is a cycle that executed at least one response; a sample is `at_steps` steps under one candidate
+// setting, scored by allreduce bytes per second; the first `at_warmup` samples are discarded. Every candidate of the grid is
+// tried once, then the best one is kept. The other ranks adopt whatever rank 0 announces (kFlagAutotune in the exchange).
+void autotune_step(Engine* e, bool busy) {
+  if (!e->autotune || e->autotune_done || e->rank != 0 || !busy) return;
+  const uint64_t now = now_ns();
+  if (e->at_busy == 0) { e->at_t0 = now; e->at_bytes0 = e->st.bytes.load(); }
+  if (++e->at_busy < e->at_steps) return;
+  const double secs = (double)(now - e->at_t0) / 1e9;
+  const double score = secs > 0 ? (double)(e->st.bytes.load() - e->at_bytes0) / secs : 0;
+  e->at_busy = 0;
+  e->at_samples++;
+  if (e->at_warmup > 0) { e->at_warmup--; return; }
+  if (e->at_idx >= 0) {
+    if (e->at_log) { fprintf(e->at_log, "%.3f,%.3f,%.3f\n", e->at_grid[e->at_idx].first, (double)e->at_grid[e->at_idx].second / 1048576.0, score / 1e6); fflush(e->at_log); }
+    if (score > e->at_best_score) { e->at_best_score = score; e->at_best = e->at_idx; }
+  }
+  if (++e->at_idx >= (int)e->at_grid.size()) {
+    e->autotune_done = true;
+    e->at_idx = e->at_best >= 0 ? e->at_best : 0;
+    if (e->at_log) { fprintf(e->at_log, "# best: cycle %.3f ms, fusion %.3f MiB, %.3f MB/s\n", e->at_grid[e->at_idx].first, (double)e->at_grid[e->at_idx].second / 1048576.0, e->at_best_score / 1e6); fclose(e->at_log); e->at_log = nullptr; }
+  }
+  e->cycle_ms = e->at_grid[e->at_idx].first;
+  e->fusion_threshold = e->at_grid[e->at_idx].second;
+}
+
 // ----------------------------------------------------------------------------------------------------- thread --
 void fail_everything(Engine* e, int code, const std::string& why) {
   std::vector<std::string> names;
@@ -1025,7 +1068,7 @@ void engine_main(Engine* e) {
         e->pending.emplace(q.name, std::move(op));
       }
     }
-    uint32_t flags = carry_flags | (e->shutdown_requested.load() ? kFlagShutdown : 0);
+    uint32_t flags = carry_flags | (e->shutdown_requested.load() ? kFlagShutdown : 0) | (e->autotune && e->rank == 0 ? kFlagAutotune : 0);
     carry_flags = 0;
     // 2. exchange + replicated coordination
     std::vector<std::string> msgs;
@@ -1050,6 +1093,7 @@ void engine_main(Engine* e) {
       break;
     }
     stall_scan(e, &carry_flags);
+    autotune_step(e, !rsp.empty());
     // 4. sleep out the rest of the cycle unless there is work waiting
     const bool busy = !rsp.empty() || !e->gpu_inflight.empty();
     if (!busy) {
@@ -1084,6 +1128,15 @@ int hvdcore_init(const char* job_id, int rank, int world, const hvdcore_gpu_t* g
   e->cache_capacity = (int)env_d("HOROVOD_CACHE_CAPACITY", 1024);
   e->stall_check = env_d("HOROVOD_STALL_CHECK_DISABLE", 0) == 0;
   e->mark_cycles = env_d("HOROVOD_TIMELINE_MARK_CYCLES", 0) != 0;
+  e->autotune = env_d("HOROVOD_AUTOTUNE", 0) != 0;
+  if (e->autotune) {
+    e->at_warmup = (int)env_d("HOROVOD_AUTOTUNE_WARMUP_SAMPLES", 3);
+    e->at_steps = std::max(1, (int)env_d("HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE", 10));
+    for (double c : {0.5, 1.0, 2.5, 5.0})
+      for (int64_t f : {1ll << 20, 4ll << 20, 16ll << 20, 64ll << 20, 128ll << 20}) e->at_grid.emplace_back(c, f);
+    const char* lg = getenv("HOROVOD_AUTOTUNE_LOG");
+    if (lg && *lg && rank == 0) { e->at_log = fopen(lg, "w"); if (e->at_log) fputs("cycle_time_ms,fusion_threshold_mb,score_mb_per_s\n", e->at_log); }
+  }
   e->stall_check_s = env_d("HOROVOD_STALL_CHECK_TIME_SECONDS", 60);
   e->stall_shutdown_s = env_d("HOROVOD_STALL_SHUTDOWN_TIME_SECONDS", 0);
   e->timeout_ms = (int)env_d("B200MPI_HVD_TIMEOUT_MS", 600000);
@@ -1205,13 +1258,14 @@ int hvdcore_stats_json(char* buf, size_t cap) {
     snprintf(tmp, sizeof(tmp),
              "{\"rank\": %d, \"world\": %d, \"cycles\": %llu, \"tensors\": %llu, \"fused_groups\": %llu, \"fused_tensors\": %llu, "
              "\"bytes\": %llu, \"cache_hits\": %llu, \"cache_misses\": %llu, \"negotiation_bytes\": %llu, \"stall_warnings\": %llu, "
-             "\"errors\": %llu, \"cycle_time_ms\": %.3f, \"fusion_threshold\": %lld, \"cache_capacity\": %d, \"gpu\": %s, \"mailbox_bytes\": %zu}",
+             "\"errors\": %llu, \"cycle_time_ms\": %.3f, \"fusion_threshold\": %lld, \"cache_capacity\": %d, \"gpu\": %s, \"mailbox_bytes\": %zu, \"autotune\": %s, \"autotune_samples\": %llu}",
              e->rank, e->world, (unsigned long long)e->st.cycles.load(), (unsigned long long)e->st.tensors.load(),
              (unsigned long long)e->st.groups.load(), (unsigned long long)e->st.fused_tensors.load(), (unsigned long long)e->st.bytes.load(),
              (unsigned long long)e->st.cache_hits.load(), (unsigned long long)e->st.cache_misses.load(),
              (unsigned long long)e->st.negotiation_bytes.load(), (unsigned long long)e->st.stall_warnings.load(),
              (unsigned long long)e->st.errors.load(), e->cycle_ms.load(), (long long)e->fusion_threshold.load(), e->cache_capacity,
-             e->has_gpu ? "true" : "false", e->seg ? e->box : (size_t)kRvMailbox);
+             e->has_gpu ? "true" : "false", e->seg ? e->box : (size_t)kRvMailbox,
+             !e->autotune ? "\"off\"" : (e->autotune_done ? "\"done\"" : "\"searching\""), (unsigned long long)e->at_samples);
   }
   const size_t n = strlen(tmp);
   if (buf && cap) { const size_t k = n < cap - 1 ? n : cap - 1; memcpy(buf, tmp, k); buf[k] = 0; }

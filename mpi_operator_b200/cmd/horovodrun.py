@@ -31,6 +31,10 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no-stall-check", action="store_true")
     p.add_argument("--stall-check-warning-time-seconds", type=float)
     p.add_argument("--stall-check-shutdown-time-seconds", type=float)
+    p.add_argument("--autotune", action="store_true", help="search cycle time x fusion threshold for the best allreduce throughput")
+    p.add_argument("--autotune-log-file")
+    p.add_argument("--autotune-warmup-samples", type=int)
+    p.add_argument("--autotune-steps-per-sample", type=int)
     p.add_argument("--start-timeout", type=int, help="seconds to wait for all ranks to join the rendezvous")
     p.add_argument("--verbose", action="store_true")
     p.add_argument("--mpi", action="store_true", help="accepted: the MPI-style launcher is the only one")
@@ -60,6 +64,14 @@ def engine_env(a) -> dict:
         e["HOROVOD_STALL_CHECK_TIME_SECONDS"] = repr(a.stall_check_warning_time_seconds)
     if a.stall_check_shutdown_time_seconds is not None:
         e["HOROVOD_STALL_SHUTDOWN_TIME_SECONDS"] = repr(a.stall_check_shutdown_time_seconds)
+    if a.autotune:
+        e["HOROVOD_AUTOTUNE"] = "1"
+    if a.autotune_log_file:
+        e["HOROVOD_AUTOTUNE_LOG"] = a.autotune_log_file
+    if a.autotune_warmup_samples is not None:
+        e["HOROVOD_AUTOTUNE_WARMUP_SAMPLES"] = str(a.autotune_warmup_samples)
+    if a.autotune_steps_per_sample is not None:
+        e["HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE"] = str(a.autotune_steps_per_sample)
     if a.start_timeout is not None:
         e["B200MPI_INIT_TIMEOUT_MS"] = str(a.start_timeout * 1000)
     if a.verbose:

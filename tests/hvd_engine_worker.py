@@ -1,6 +1,6 @@
 """Rank script (run under the native mpirun): the horovod.torch async API on the native hvdcore engine — named tensors in
 rank-dependent order, fusion and response-cache counters, ragged allgather, mismatch errors, join(), timeline, the
-engine-backed DistributedOptimizer with fp16 compression, stall inspector. Modes: default | stall | stall_shutdown | peer_death."""
+engine-backed DistributedOptimizer with fp16 compression, stall inspector. Modes: default | stall | stall_shutdown | peer_death | autotune."""
 import json
 import os
 import sys
@@ -26,6 +26,26 @@ if mode == "stall":
     assert hvd.engine_stats()["stall_warnings"] >= 1 or n == 1
     hvd.shutdown()
     print(f"rank {r}/{n} stall ok", flush=True)
+    sys.exit(0)
+
+if mode == "autotune":
+    # HOROVOD_AUTOTUNE=1: rank 0 walks the {cycle time} x {fusion threshold} grid, every rank adopts its current candidate in the
+    # same cycle (so fused groups always agree and results stay exact), and the search ends on the best-scoring setting
+    for it in range(140):
+        hs = [hvd.allreduce_async_(torch.full((2000 + 10 * k,), float(r + k)), name=f"at.{k}", op=hvd.Sum) for k in range(12)]
+        for k, h in enumerate(hs):
+            assert torch.equal(hvd.synchronize(h), torch.full((2000 + 10 * k,), float(n * k + n * (n - 1) / 2))), (it, k)
+    st = hvd.engine_stats()
+    mine = torch.tensor([st["cycle_time_ms"], float(st["fusion_threshold"])], dtype=torch.float64)
+    everyone = hvd.allgather(mine.view(1, 2), name="at.params")
+    assert all(torch.equal(everyone[0], everyone[k]) for k in range(n)), everyone        # every rank ended on rank 0's choice
+    if r == 0:
+        assert st["autotune"] == "done" and st["autotune_samples"] >= 21, st
+        rows = [l for l in open(os.environ["HOROVOD_AUTOTUNE_LOG"]).read().splitlines() if l and l[0].isdigit()]
+        assert len(rows) == 20 and len({tuple(l.split(",")[:2]) for l in rows}) == 20, rows
+        assert st["cycle_time_ms"] in (0.5, 1.0, 2.5, 5.0) and st["fusion_threshold"] in (1 << 20, 4 << 20, 16 << 20, 64 << 20, 128 << 20)
+    hvd.shutdown()
+    print(f"rank {r}/{n} autotune ok", flush=True)
     sys.exit(0)
 
 if mode == "peer_death":

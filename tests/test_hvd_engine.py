@@ -77,6 +77,14 @@ def test_a_dead_peer_fails_the_outstanding_handles_instead_of_hanging():
     assert r.stdout.count("peer death detected") == 2
 
 
+def test_autotune_walks_the_grid_and_every_rank_follows_rank_0(tmp_path):
+    log = tmp_path / "autotune.csv"
+    r = _run(3, "autotune", env={"HOROVOD_AUTOTUNE": "1", "HOROVOD_AUTOTUNE_LOG": str(log), "HOROVOD_AUTOTUNE_WARMUP_SAMPLES": "1",
+                                 "HOROVOD_AUTOTUNE_STEPS_PER_SAMPLE": "3"}, timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    assert r.stdout.count("autotune ok") == 3 and "# best: cycle" in log.read_text()
+
+
 def test_engine_can_be_disabled():
     """B200MPI_HVD_ENGINE=0: the front-end falls back to the direct (call-order) path over the libmpi shim."""
     code = ("import sys; sys.path.insert(0, %r); import torch, horovod.torch as hvd; hvd.init(); "
