@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 
 from ..runtime.comm import Communicator, Window
-from ..utils import fault
+from ..utils import fault, nvtx
 
 
 def _align(n: int, a: int) -> int:
@@ -282,7 +282,7 @@ class DataParallelTrainer:
         ev = torch.cuda.Event()
         ev.record(main)
         self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
+        with torch.cuda.stream(self.comm_stream), nvtx.range(f"b200mpi.bucket@{b.start}"):
             self._reduce_bucket_body(b)
         b.pending = -1  # fired
 
@@ -324,7 +324,7 @@ class DataParallelTrainer:
             b.pending = len(b.params)
         import contextlib
         from ..ops import fused_bn
-        with (fused_bn.defer_counters() if self._defer_nbt else contextlib.nullcontext()) as counters:
+        with (fused_bn.defer_counters() if self._defer_nbt else contextlib.nullcontext()) as counters, nvtx.range("b200mpi.forward"):
             if self.autocast_dtype is not None:
                 with torch.autocast(self.device.type, dtype=self.autocast_dtype):
                     out = self.model(x)
@@ -333,7 +333,8 @@ class DataParallelTrainer:
                 loss = self.loss_fn(self.model(x), y)
         if counters:   # one multi-tensor add instead of one tiny kernel per BN layer
             torch._foreach_add_(counters, 1)
-        loss.backward()
+        with nvtx.range("b200mpi.backward+allreduce_sgd"):   # bucket kernels are launched from the autograd hooks inside
+            loss.backward()
         self._loss.copy_(loss.detach())
         if not self._sync:   # local accumulation only (Horovod: backward_passes_per_step > 1)
             self._carry = True
