@@ -294,14 +294,28 @@ int MPI_Scatter(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Dataty
   memcpy(r, all.data() + (size_t)g_rank * bytes, bytes);
   return MPI_SUCCESS;
 }
+// Pairwise exchange: in step k rank r publishes the block for rank (r + k) % W in its box and reads the block rank (r - k) % W
+// published for it — W - 1 steps of `bytes` per rank instead of gathering every rank's whole send buffer everywhere.
 int MPI_Alltoall(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm c) {
   int e = check(c); if (e) return e;
   const size_t bytes = type_size(st) * (size_t)sn;
-  std::vector<unsigned char> all(bytes * g_size * g_size);
-  e = allgather_bytes(s, all.data(), bytes * g_size);
-  if (e) return e;
-  for (int src = 0; src < g_size; src++)
-    memcpy((char*)r + (size_t)src * bytes, all.data() + ((size_t)src * g_size + g_rank) * bytes, bytes);
+  if (c == MPI_COMM_SELF || g_size == 1) { if (r != s) memmove(r, s, bytes); return MPI_SUCCESS; }
+  std::vector<unsigned char> tmp;
+  const unsigned char* src = static_cast<const unsigned char*>(s);
+  if (s == MPI_IN_PLACE) { tmp.assign((unsigned char*)r, (unsigned char*)r + bytes * g_size); src = tmp.data(); }
+  memcpy((char*)r + (size_t)g_rank * bytes, src + (size_t)g_rank * bytes, bytes);
+  std::string err;
+  const size_t chunk = box_bytes();
+  for (int step = 1; step < g_size; step++) {
+    const int dst = (g_rank + step) % g_size, from = (g_rank - step + g_size) % g_size;
+    for (size_t done = 0; done < bytes; done += chunk) {
+      const size_t n = std::min(chunk, bytes - done);
+      memcpy(box_data(g_rank), src + (size_t)dst * bytes + done, n);
+      if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+      memcpy((char*)r + (size_t)from * bytes + done, box_data(from), n);
+      if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
+    }
+  }
   return MPI_SUCCESS;
 }
 
