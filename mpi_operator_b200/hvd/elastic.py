@@ -28,12 +28,24 @@ def _discover_hosts() -> Optional[str]:
 
 
 class State:
+    """Horovod's ``ObjectState``: named picklable attributes that are saved on ``commit()``, rolled back by ``restore()`` and
+    broadcast from rank 0 by ``sync()``; callbacks registered with ``register_reset_callbacks`` run after every (re)start of the
+    world (``on_reset``), e.g. to rescale the learning rate to the new ``hvd.size()``."""
+
     def __init__(self, **kwargs):
         self._saved = {}
+        self._reset_callbacks = []
         self._hosts = _discover_hosts()
         for k, v in kwargs.items():
             setattr(self, k, v)
         self._keys = list(kwargs)
+
+    def register_reset_callbacks(self, callbacks) -> None:
+        self._reset_callbacks.extend(callbacks)
+
+    def on_reset(self) -> None:
+        for cb in self._reset_callbacks:
+            cb()
 
     def commit(self):
         from ..utils import fault
@@ -58,6 +70,9 @@ class State:
         from . import broadcast_object
         for k in self._keys:
             setattr(self, k, broadcast_object(getattr(self, k), 0))
+
+
+ObjectState = State   # Horovod's name for the generic state
 
 
 class TorchState(State):
@@ -108,6 +123,7 @@ def run(func: Callable) -> Callable:
     def wrapper(state, *args, **kwargs):
         state.restore()
         state.sync()
+        state.on_reset()      # every incarnation is a reset of the world: new size, new rank
         try:
             return func(state, *args, **kwargs)
         except HostsUpdatedInterrupt:

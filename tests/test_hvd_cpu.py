@@ -55,8 +55,13 @@ def test_elastic_state_commit_restore_and_host_update(tmp_path, monkeypatch):
     st.restore()
     assert st.step == 8
 
+    resets = []
+    st.register_reset_callbacks([lambda: resets.append(st.step)])
+    assert elastic.ObjectState is elastic.State
+
     @elastic.run
     def train(state):
+        assert resets == [8]          # on_reset ran after restore + sync, before the training function
         raise elastic.HostsUpdatedInterrupt("rescale")
     monkeypatch.setattr(elastic.State, "sync", lambda self: None)
     with pytest.raises(SystemExit) as e:
