@@ -186,7 +186,7 @@ def cmd_logs(cli: MPIJobClient, a) -> int:
     deadline = time.time() + a.timeout if getattr(a, "timeout", None) else None
     while True:
         try:
-            text = cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod)
+            text = cli.logs(a.name, a.namespace, worker=a.worker, pod=a.pod, tail=None if getattr(a, "follow", False) else getattr(a, "tail", None))
         except ApiException as e:
             if not getattr(a, "follow", False) or printed:
                 print(f"error: {e}", file=sys.stderr)
@@ -303,6 +303,7 @@ def main(argv: Optional[List[str]] = None) -> int:
     p.add_argument("--worker", type=int, default=None)
     p.add_argument("--pod", default=None)
     p.add_argument("-f", "--follow", action="store_true", help="stream the log until the job finishes")
+    p.add_argument("--tail", type=int, default=None, help="only the last N lines")
     p.add_argument("--timeout", type=float, default=None, help="with -f: give up after this many seconds")
     p = sub.add_parser("scale")
     p.add_argument("name")

@@ -266,7 +266,13 @@ def _make_handler(op: Operator):
                     return self._send(404, errors.not_found("path", self.path).to_status())
                 res, ns, name, sub = r
                 if res == "pods" and sub == "log":
-                    return self._send(200, op.agent.logs(ns, name).encode(), "text/plain")
+                    if q.get("follow", ["false"])[0].lower() in ("true", "1"):
+                        return self._follow_log(ns, name, q)
+                    text = op.agent.logs(ns, name)
+                    if "tailLines" in q:       # kubectl logs --tail=N
+                        n_tail = max(0, int(q["tailLines"][0]))
+                        text = "".join(text.splitlines(keepends=True)[-n_tail:]) if n_tail else ""
+                    return self._send(200, text.encode(), "text/plain")
                 if name:
                     return self._send(200, store.get(res, ns, name))
                 sel = None
@@ -319,6 +325,37 @@ def _make_handler(op: Operator):
                 self.close_connection = True
             finally:
                 cancel()
+
+        def _follow_log(self, ns, name, q):
+            """`pods/<name>/log?follow=true` (kubectl logs -f): chunks as the container writes them, until the pod has finished
+            (Succeeded / Failed / deleted) and its log is drained, or `timeoutSeconds` (default 3600)."""
+            deadline = time.time() + float(q.get("timeoutSeconds", ["3600"])[0])
+            sent = 0
+            try:
+                self.send_response(200)
+                self.send_header("Content-Type", "text/plain")
+                self.send_header("Transfer-Encoding", "chunked")
+                self.end_headers()
+                while True:
+                    data = op.agent.logs(ns, name).encode()
+                    if len(data) < sent:          # container restarted: a fresh log
+                        sent = 0
+                    if len(data) > sent:
+                        piece = data[sent:]
+                        self.wfile.write(b"%x\r\n" % len(piece) + piece + b"\r\n")
+                        self.wfile.flush()
+                        sent = len(data)
+                        continue
+                    try:
+                        phase = (store.get("pods", ns, name).get("status") or {}).get("phase", "")
+                    except errors.ApiError:
+                        phase = "Deleted"
+                    if phase in ("Succeeded", "Failed", "Deleted") or time.time() > deadline:
+                        break
+                    time.sleep(0.1)
+                self.wfile.write(b"0\r\n\r\n")
+            except (BrokenPipeError, ConnectionResetError, OSError):
+                self.close_connection = True
 
         def _admit(self, res, obj):
             """API-server side admission for MPIJobs: CRD schema defaults + structural validation."""

@@ -120,7 +120,8 @@ class MPIJobClient:
                 raise TimeoutError(f"timed out waiting for condition {condition} on mpijob/{name}")
             time.sleep(poll)
 
-    def logs(self, name: str, namespace: str = "default", worker: Optional[int] = None, pod: Optional[str] = None) -> str:
+    def logs(self, name: str, namespace: str = "default", worker: Optional[int] = None, pod: Optional[str] = None,
+             tail: Optional[int] = None) -> str:
         if pod is None:
             pods = self.list_resource("pods", namespace)
             role = "worker" if worker is not None else "launcher"
@@ -131,8 +132,30 @@ class MPIJobClient:
             if not cands:
                 raise ApiException(status=404, reason=f"no {role} pod found for mpijob {name}")
             pod = sorted(cands, key=lambda p: p["metadata"].get("creationTimestamp", ""))[-1]["metadata"]["name"]
-        data = self.api.call_api(self._path("pods", namespace, pod, "log"), "GET", response_type="raw")
+        path = self._path("pods", namespace, pod, "log")
+        if tail is not None:
+            path += f"?tailLines={int(tail)}"
+        data = self.api.call_api(path, "GET", response_type="raw")
         return data.decode(errors="replace")
+
+    def follow_pod_log(self, pod: str, namespace: str = "default", timeout: float = 3600.0):
+        """Generator over `pods/<pod>/log?follow=true`: text pieces as the container writes them, until the pod finishes."""
+        import http.client
+        import urllib.parse
+        u = urllib.parse.urlparse(self.api.configuration.host)
+        conn = http.client.HTTPConnection(u.hostname, u.port or 80, timeout=timeout + 10)
+        try:
+            conn.request("GET", self._path("pods", namespace, pod, "log") + f"?follow=true&timeoutSeconds={float(timeout)!r}")
+            resp = conn.getresponse()
+            if resp.status != 200:
+                raise ApiException(status=resp.status, reason=resp.reason, body=resp.read())
+            while True:
+                chunk = resp.read1(65536)
+                if not chunk:
+                    return
+                yield chunk.decode(errors="replace")
+        finally:
+            conn.close()
 
     def watch(self, resource: str = "mpijobs", namespace: Optional[str] = "default", timeout: float = 300.0,
               label_selector: Optional[str] = None, name: Optional[str] = None):

@@ -61,6 +61,7 @@ def test_apply_get_describe_logs_wait_delete(server, tmp_path):
     rc, out, _ = ctl(server, "describe", "cli")
     assert "MPIJobSucceeded" in out and "Conditions:" in out and "Launcher: replicas=1" in out
     assert "launcher-says-hi" in ctl(server, "logs", "cli")[1]
+    assert ctl(server, "logs", "cli", "--tail", "1")[1].count("\n") == 1 and ctl(server, "logs", "cli", "--tail", "0")[1] == ""
     rc, out, _ = ctl(server, "get", "pods")
     assert "cli-launcher-" in out
     rc, out, _ = ctl(server, "get", "events")
@@ -145,5 +146,10 @@ def test_logs_follow_and_get_watch(server, tmp_path):
     assert ctl(server, "apply", "-f", str(f))[0] == 0
     rc, out, err = ctl(server, "logs", "follow", "-f", "--timeout", "30")
     assert rc == 0 and [l for l in out.splitlines() if l.startswith("tick-")] == ["tick-1", "tick-2", "tick-3"], (out, err)
+    # the server-side stream (pods/<name>/log?follow=true) delivers the same text and ends when the pod has finished
+    from mpi_operator_b200.sdk import MPIJobClient
+    cli = MPIJobClient(server)
+    pod = [p["metadata"]["name"] for p in cli.list_resource("pods", "default") if "follow-launcher" in p["metadata"]["name"]][0]
+    assert "".join(cli.follow_pod_log(pod, timeout=10)).count("tick-") == 3
     wout, _ = watch.communicate(timeout=30)
     assert watch.returncode == 0 and "NAME" in wout and "Succeeded" in wout and wout.count("follow") >= 2, wout   # several change lines
