@@ -28,6 +28,7 @@
 #include <map>
 #include <sstream>
 #include <string>
+#include <sys/stat.h>
 #include <vector>
 
 extern char** environ;
@@ -119,17 +120,48 @@ static std::map<std::string, std::vector<int>> read_slots_file(const char* path)
   return out;
 }
 
+// -output-filename DIR (Open MPI): besides the multiplexed console, every rank's streams go to DIR/1/rank.<N>/{stdout,stderr};
+// -timestamp-output: every line is prefixed with the wall-clock time it was forwarded.
+static std::string g_outdir;
+static bool g_timestamp = false;
+static FILE* rank_file(int rank, const char* chan) {
+  static std::map<std::pair<int, std::string>, FILE*> files;
+  auto key = std::make_pair(rank, std::string(chan));
+  auto it = files.find(key);
+  if (it != files.end()) return it->second;
+  std::string dir = g_outdir + "/1";
+  mkdir(g_outdir.c_str(), 0755);
+  mkdir(dir.c_str(), 0755);
+  dir += "/rank." + std::to_string(rank);
+  mkdir(dir.c_str(), 0755);
+  FILE* f = fopen((dir + "/" + chan).c_str(), "w");
+  files[key] = f;
+  return f;
+}
+static void emit_line(FILE* to, bool tag, int rank, const char* chan, const char* data, size_t n, bool add_newline) {
+  if (g_timestamp) {
+    char ts[40];
+    time_t now = time(nullptr);
+    struct tm tmv;
+    localtime_r(&now, &tmv);
+    strftime(ts, sizeof(ts), "%a %b %d %H:%M:%S %Y", &tmv);
+    fprintf(to, "%s<%s>:", ts, chan);
+  }
+  if (tag) fprintf(to, "[1,%d]<%s>:", rank, chan);
+  fwrite(data, 1, n, to);
+  if (add_newline) fputc('\n', to);
+  if (!g_outdir.empty()) {
+    if (FILE* f = rank_file(rank, chan)) { fwrite(data, 1, n, f); if (add_newline) fputc('\n', f); fflush(f); }
+  }
+}
 static void flush_lines(std::string& buf, FILE* to, bool tag, int rank, const char* chan, bool final) {
   size_t pos;
   while ((pos = buf.find('\n')) != std::string::npos) {
-    if (tag) fprintf(to, "[1,%d]<%s>:", rank, chan);
-    fwrite(buf.data(), 1, pos + 1, to);
+    emit_line(to, tag, rank, chan, buf.data(), pos + 1, false);
     buf.erase(0, pos + 1);
   }
   if (final && !buf.empty()) {
-    if (tag) fprintf(to, "[1,%d]<%s>:", rank, chan);
-    fwrite(buf.data(), 1, buf.size(), to);
-    fputc('\n', to);
+    emit_line(to, tag, rank, chan, buf.data(), buf.size(), true);
     buf.clear();
   }
   fflush(to);
@@ -166,8 +198,10 @@ int main(int argc, char** argv) {
       if (a == "-l") tag_output = true;
     }
     else if (a == "-tag-output" || a == "-prepend-rank") tag_output = true;
+    else if (a == "-timestamp-output") g_timestamp = true;
+    else if (a == "-output-filename" || a == "-outfile-pattern") { need(1); g_outdir = argv[++i]; }
     else if (a == "-bind-to" || a == "-map-by" || a == "-rank-by" || a == "-prefix" || a == "-launcher" || a == "-launcher-exec" ||
-             a == "-bootstrap" || a == "-bootstrap-exec" || a == "-iface" || a == "-output-filename" || a == "-report-pid" ||
+             a == "-bootstrap" || a == "-bootstrap-exec" || a == "-iface" || a == "-report-pid" ||
              a == "-cpus-per-proc" || a == "-cpus-per-rank") { need(1); ++i; }
     else if (a == "-mca" || a == "-gmca" || a == "-omca" || a == "-pmixmca" || a == "-prtemca") {
       need(2);
@@ -203,8 +237,12 @@ int main(int argc, char** argv) {
              "  -mca / -gmca key value        exported as OMPI_MCA_<key>=<value>\n"
              "  -wdir, -wd DIR                working directory of the ranks\n"
              "  -tag-output, -prepend-rank, -l  prefix every output line with [job,rank]<stream>:\n"
+             "  -output-filename DIR          also write every rank's output to DIR/1/rank.<N>/{stdout,stderr}\n"
+             "  -timestamp-output             prefix every forwarded line with the time\n"
              "  -timeout SECONDS              kill the job after SECONDS (exit code 124)\n"
              "  -oversubscribe                allow more ranks than slots\n"
+             "  prog1 args : -np N prog2 ...  MPMD: several application contexts, ranks numbered context by context (MPI_APPNUM in\n"
+             "                                OMPI_MCA_orte_app_num / PMI_APPNUM); a context may carry its own -np, -x, -env, -wdir\n"
              "  -bind-to, -map-by, -rank-by, -bootstrap, -launcher, -iface ...   accepted and ignored (one box, no ssh)\n"
              "  -V, -version / -h, -help\n\n"
              "Ranks get OMPI_COMM_WORLD_*, PMI_*, RANK/WORLD_SIZE/LOCAL_RANK/MASTER_ADDR/MASTER_PORT, HOROVOD_* and B200MPI_* variables;\n"
@@ -216,8 +254,54 @@ int main(int argc, char** argv) {
     else break;
   }
   if (i >= argc) die("no program to launch");
-  std::vector<char*> prog(argv + i, argv + argc);
-  prog.push_back(nullptr);
+  // MPMD: `mpirun -np 1 ./master : -np 4 ./worker args` (Open MPI and Hydra): app contexts separated by a lone ':'; every
+  // context after the first may start with its own -n/-np, -x / -env / -genv, -wdir; ranks are numbered context by context.
+  struct App { int np = -1; std::vector<char*> argv; std::vector<std::pair<std::string, std::string>> env; std::string wdir; };
+  std::vector<App> apps(1);
+  apps[0].np = np;
+  {
+    bool opts = false;   // the first context's options were parsed above
+    for (int k = i; k < argc; k++) {
+      std::string a = argv[k];
+      if (a == ":") {
+        if (apps.back().argv.empty()) die("empty application context before ':'");
+        apps.emplace_back();
+        opts = true;
+        continue;
+      }
+      if (opts && a.size() > 1 && a[0] == '-') {
+        if (a.size() > 2 && a[1] == '-') a = a.substr(1);
+        auto need_k = [&](int n) { if (k + n >= argc) die("option " + a + " needs an argument"); };
+        if (a == "-n" || a == "-np" || a == "-c") { need_k(1); apps.back().np = atoi(argv[++k]); }
+        else if (a == "-x") {
+          need_k(1);
+          std::string kv = argv[++k];
+          size_t eq = kv.find('=');
+          if (eq != std::string::npos) apps.back().env.push_back({kv.substr(0, eq), kv.substr(eq + 1)});
+          else if (const char* v = getenv(kv.c_str())) apps.back().env.push_back({kv, v});
+        }
+        else if (a == "-env" || a == "-genv") { need_k(2); apps.back().env.push_back({argv[k + 1], argv[k + 2]}); k += 2; }
+        else if (a == "-wdir" || a == "-wd") { need_k(1); apps.back().wdir = argv[++k]; }
+        else if (a == "-host" || a == "-H" || a == "-hosts" || a == "-bind-to" || a == "-map-by" || a == "-mca") { need_k(a == "-mca" ? 2 : 1); k += a == "-mca" ? 2 : 1; }
+        else fprintf(stderr, "mpirun (b200mpi): note: ignoring unknown option %s in application context %zu\n", argv[k], apps.size() - 1);
+        continue;
+      }
+      opts = false;
+      apps.back().argv.push_back(argv[k]);
+    }
+    if (apps.back().argv.empty()) die("no program after ':'");
+    for (auto& ap : apps) ap.argv.push_back(nullptr);
+    if (apps.size() > 1) {
+      np = 0;
+      for (auto& ap : apps) { if (ap.np <= 0) ap.np = 1; np += ap.np; }   // Open MPI: one process per context unless -np says otherwise
+    }
+  }
+  auto app_of = [&](int rank) -> size_t {
+    if (apps.size() == 1) return 0;
+    int r = rank;
+    for (size_t k = 0; k < apps.size(); k++) { if (r < apps[k].np) return k; r -= apps[k].np; }
+    return apps.size() - 1;
+  };
 
   // ---- hosts -------------------------------------------------------------
   int default_slots = 1;
@@ -363,11 +447,17 @@ int main(int argc, char** argv) {
           set("LD_PRELOAD", pre);
         }
       }
-      execvp(prog[0], prog.data());
+      const size_t appnum = app_of(rk.rank);
+      App& ap = apps[appnum];
+      for (auto& kv : ap.env) set(kv.first.c_str(), kv.second);
+      seti("OMPI_MCA_orte_app_num", (int)appnum); seti("PMI_APPNUM", (int)appnum); seti("B200MPI_APPNUM", (int)appnum);   // MPI_APPNUM
+      if (!ap.wdir.empty() && chdir(ap.wdir.c_str()) != 0) { fprintf(stderr, "mpirun (b200mpi): cannot chdir to %s\n", ap.wdir.c_str()); _exit(127); }
+      char** prog = ap.argv.data();
+      execvp(prog[0], prog);
       if (errno == ENOENT && strchr(prog[0], '/')) {
         // image-relative path (e.g. /home/mpiuser/pi from the reference YAML): fall back to PATH lookup
         const char* base = strrchr(prog[0], '/') + 1;
-        execvp(base, prog.data());
+        execvp(base, prog);
       }
       fprintf(stderr, "mpirun (b200mpi): could not exec %s: %s\n", prog[0], strerror(errno));
       _exit(127);

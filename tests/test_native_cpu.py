@@ -30,6 +30,26 @@ def test_mpirun_rank_env_all_dialects_and_flags():
     assert lines == [f"[1,{i}]<stdout>:{i}/3 {i}/3 {i}/3 {i} {i} bar ob1 ^openib worker 127.0.0.1" for i in range(3)]
 
 
+def test_mpirun_mpmd_output_files_and_timestamps(tmp_path):
+    """MPMD application contexts (`prog1 : -np 2 prog2`, Open MPI / Hydra), per-context -np / -x, MPI_APPNUM in the environment,
+    -output-filename DIR (DIR/1/rank.<N>/{stdout,stderr}) and -timestamp-output."""
+    out = tmp_path / "logs"
+    r = run([MPIRUN, "-np", "1", "--tag-output", "-output-filename", str(out), "sh", "-c",
+             "echo master $OMPI_COMM_WORLD_RANK/$OMPI_COMM_WORLD_SIZE app=$PMI_APPNUM role=[$ROLE]", ":",
+             "-np", "2", "-x", "ROLE=w", "sh", "-c", "echo worker $PMI_RANK/$PMI_SIZE app=$OMPI_MCA_orte_app_num role=[$ROLE]; echo oops >&2"])
+    assert r.returncode == 0, r.stderr
+    assert sorted(r.stdout.strip().splitlines()) == ["[1,0]<stdout>:master 0/3 app=0 role=[]", "[1,1]<stdout>:worker 1/3 app=1 role=[w]",
+                                                     "[1,2]<stdout>:worker 2/3 app=1 role=[w]"]
+    assert (out / "1" / "rank.0" / "stdout").read_text() == "master 0/3 app=0 role=[]\n"
+    assert (out / "1" / "rank.2" / "stdout").read_text() == "worker 2/3 app=1 role=[w]\n"
+    assert (out / "1" / "rank.1" / "stderr").read_text() == "oops\n"
+    r = run([MPIRUN, "-np", "1", "--timestamp-output", "echo", "stamped"])
+    import re
+    assert re.fullmatch(r"\w{3} \w{3} \d{2} \d{2}:\d{2}:\d{2} \d{4}<stdout>:stamped\n", r.stdout), r.stdout
+    r = run([MPIRUN, "-np", "1", "true", ":"])
+    assert r.returncode != 0 and "no program after ':'" in r.stderr
+
+
 def test_mpirun_hostfile_dialects_and_slot_placement(tmp_path):
     hf = tmp_path / "hostfile"
     hf.write_text("job-worker-0.job.ns.svc slots=2\njob-worker-1.job.ns.svc slots=2\n")
