@@ -77,6 +77,11 @@ int MPI_Type_size(MPI_Datatype datatype, int* size);
 int MPI_Error_string(int errorcode, char* string, int* resultlen);
 double MPI_Wtime(void);
 double MPI_Wtick(void);
+/* predefined attributes of MPI_COMM_WORLD: *(int**)attribute_val points at the value; MPI_APPNUM is the MPMD application
+ * context the launcher started this rank in (mpirun prog1 : -np 2 prog2) */
+enum { MPI_TAG_UB_KEY = 1, MPI_APPNUM = 2, MPI_UNIVERSE_SIZE = 3, MPI_WTIME_IS_GLOBAL = 4, MPI_HOST = 5, MPI_IO = 6 };
+int MPI_Comm_get_attr(MPI_Comm comm, int keyval, void* attribute_val, int* flag);
+int MPI_Attr_get(MPI_Comm comm, int keyval, void* attribute_val, int* flag);
 
 int MPI_Barrier(MPI_Comm comm);
 int MPI_Bcast(void* buffer, int count, MPI_Datatype datatype, int root, MPI_Comm comm);

@@ -192,6 +192,27 @@ int MPI_Get_processor_name(char* name, int* len) {
   return MPI_SUCCESS;
 }
 int MPI_Get_version(int* v, int* s) { *v = 3; *s = 1; return MPI_SUCCESS; }
+int MPI_Comm_get_attr(MPI_Comm c, int keyval, void* attribute_val, int* flag) {
+  int e = check(c); if (e) return e;
+  static int tag_ub = MPI_TAG_UB, appnum = 0, universe = 1, wtime_global = 1, host = MPI_PROC_NULL, io = 0;
+  appnum = env_first({"B200MPI_APPNUM", "OMPI_MCA_orte_app_num", "PMI_APPNUM"}, 0);
+  universe = env_first({"OMPI_UNIVERSE_SIZE"}, g_size);
+  io = g_rank;
+  int* v = nullptr;
+  switch (keyval) {
+    case MPI_TAG_UB_KEY: case MPI_TAG_UB: v = &tag_ub; break;   // this header defines MPI_TAG_UB as the bound itself; accept it as the key too
+    case MPI_APPNUM: v = &appnum; break;
+    case MPI_UNIVERSE_SIZE: v = &universe; break;
+    case MPI_WTIME_IS_GLOBAL: v = &wtime_global; break;   // one box, one CLOCK_MONOTONIC
+    case MPI_HOST: v = &host; break;
+    case MPI_IO: v = &io; break;
+    default: break;
+  }
+  *flag = v != nullptr;
+  if (v) *static_cast<int**>(attribute_val) = v;
+  return MPI_SUCCESS;
+}
+int MPI_Attr_get(MPI_Comm c, int keyval, void* attribute_val, int* flag) { return MPI_Comm_get_attr(c, keyval, attribute_val, flag); }
 int MPI_Get_library_version(char* v, int* len) {
   *len = snprintf(v, 256, "b200mpi libmpi shim 0.1.0 (shm rendezvous transport)");
   return MPI_SUCCESS;

@@ -43,6 +43,16 @@ def test_mpirun_mpmd_output_files_and_timestamps(tmp_path):
     assert (out / "1" / "rank.0" / "stdout").read_text() == "master 0/3 app=0 role=[]\n"
     assert (out / "1" / "rank.2" / "stdout").read_text() == "worker 2/3 app=1 role=[w]\n"
     assert (out / "1" / "rank.1" / "stderr").read_text() == "oops\n"
+    src = tmp_path / "appnum.c"
+    src.write_text('#include <mpi.h>\n#include <stdio.h>\nint main(int c, char** v) { MPI_Init(&c, &v); int r, f = 0, *a = 0, *u = 0; '
+                   'MPI_Comm_rank(MPI_COMM_WORLD, &r); MPI_Comm_get_attr(MPI_COMM_WORLD, MPI_APPNUM, &a, &f); '
+                   'MPI_Comm_get_attr(MPI_COMM_WORLD, MPI_UNIVERSE_SIZE, &u, &f); printf("rank %d appnum %d universe %d\\n", r, *a, *u); '
+                   'MPI_Finalize(); return 0; }\n')
+    exe = tmp_path / "appnum"
+    subprocess.run(["gcc", "-I" + os.path.join(REPO, "mpi_operator_b200/include"), "-o", str(exe), str(src), "-L" + os.path.join(REPO, "mpi_operator_b200/lib"),
+                    "-lmpi", "-Wl,-rpath," + os.path.join(REPO, "mpi_operator_b200/lib")], check=True)
+    r = run([MPIRUN, "-np", "1", str(exe), ":", "-np", "2", str(exe)])
+    assert sorted(r.stdout.strip().splitlines()) == ["rank 0 appnum 0 universe 3", "rank 1 appnum 1 universe 3", "rank 2 appnum 1 universe 3"], r.stdout + r.stderr
     r = run([MPIRUN, "-np", "1", "--timestamp-output", "echo", "stamped"])
     import re
     assert re.fullmatch(r"\w{3} \w{3} \d{2} \d{2}:\d{2}:\d{2} \d{4}<stdout>:stamped\n", r.stdout), r.stdout
