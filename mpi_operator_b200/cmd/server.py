@@ -261,6 +261,9 @@ def _make_handler(op: Operator):
                     t = op.agent.topology.to_dict()
                     t["free_gpus"] = op.agent.alloc.free_gpus
                     return self._send(200, t)
+                disc = self._discovery(parts)
+                if disc is not None:
+                    return self._send(200, disc)
                 r = self._resolve(parts)
                 if r is None:
                     return self._send(404, errors.not_found("path", self.path).to_status())
@@ -325,6 +328,41 @@ def _make_handler(op: Operator):
                 self.close_connection = True
             finally:
                 cancel()
+
+        def _discovery(self, parts):
+            """API discovery documents (`/api`, `/apis`, `/api/v1`, `/apis/<group>/<version>`, `/openapi/v2`): what kubectl and
+            client libraries read before they address a resource, so generic Kubernetes tooling can be pointed at the daemon."""
+            verbs = ["create", "delete", "get", "list", "patch", "update", "watch"]
+            groups = {}
+            for (prefix, plural), res in API_GROUPS.items():
+                groups.setdefault(prefix, []).append((plural, res))
+            if parts == ["api"]:
+                return {"kind": "APIVersions", "versions": ["v1"], "serverAddressByClientCIDRs": []}
+            if parts == ["apis"]:
+                out = []
+                for prefix in sorted(groups):
+                    if prefix.startswith("apis/"):
+                        _, g, v = prefix.split("/")
+                        gv = {"groupVersion": f"{g}/{v}", "version": v}
+                        out.append({"name": g, "versions": [gv], "preferredVersion": gv})
+                return {"kind": "APIGroupList", "apiVersion": "v1", "groups": out}
+            if parts == ["openapi", "v2"]:
+                from ..api.openapi import swagger
+                return swagger()
+            key = "/".join(parts)
+            if key in groups:
+                rl = []
+                for plural, res in sorted(groups[key]):
+                    _, kind, namespaced = RESOURCES[res]
+                    short = {"mpijobs": ["mpijob", "mj"], "pods": ["po"], "services": ["svc"], "configmaps": ["cm"], "events": ["ev"]}.get(plural, [])
+                    rl.append({"name": plural, "singularName": kind.lower(), "namespaced": namespaced, "kind": kind, "verbs": verbs, "shortNames": short})
+                    if res in ("mpijobs", "pods", "jobs"):
+                        rl.append({"name": plural + "/status", "singularName": "", "namespaced": namespaced, "kind": kind, "verbs": ["get", "patch", "update"]})
+                    if res == "pods":
+                        rl.append({"name": "pods/log", "singularName": "", "namespaced": True, "kind": "Pod", "verbs": ["get"]})
+                gv = key[len("apis/"):] if key.startswith("apis/") else "v1"
+                return {"kind": "APIResourceList", "apiVersion": "v1", "groupVersion": gv, "resources": rl}
+            return None
 
         def _follow_log(self, ns, name, q):
             """`pods/<name>/log?follow=true` (kubectl logs -f): chunks as the container writes them, until the pod has finished

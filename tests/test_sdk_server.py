@@ -231,3 +231,23 @@ def test_watch_stream_delivers_added_modified_deleted_in_order(tmp_path):
         assert by_label == ["new"]
     finally:
         op.stop()
+
+
+def test_api_discovery_documents(tmp_path):
+    """`/api`, `/apis`, `/api/v1`, `/apis/kubeflow.org/v2beta1`, `/openapi/v2`: what kubectl / client libraries read first."""
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    op = Operator(ServerOption(fake_gpus=0, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    try:
+        def get(path):
+            return json.loads(urllib.request.urlopen(f"http://127.0.0.1:{port}{path}", timeout=5).read())
+        assert get("/api")["versions"] == ["v1"]
+        groups = {g["name"]: g["preferredVersion"]["groupVersion"] for g in get("/apis")["groups"]}
+        assert groups["kubeflow.org"] == "kubeflow.org/v2beta1" and groups["batch"] == "batch/v1" and "scheduling.volcano.sh" in groups
+        core = {r["name"]: r for r in get("/api/v1")["resources"]}
+        assert core["pods"]["kind"] == "Pod" and core["pods"]["namespaced"] and "pods/log" in core and "watch" in core["events"]["verbs"]
+        mj = {r["name"]: r for r in get("/apis/kubeflow.org/v2beta1")["resources"]}
+        assert mj["mpijobs"]["kind"] == "MPIJob" and "mpijob" in mj["mpijobs"]["shortNames"] and "mpijobs/status" in mj
+        assert "v2beta1.MPIJob" in get("/openapi/v2")["definitions"]
+    finally:
+        op.stop()
