@@ -135,3 +135,34 @@ def test_affinity_helper_is_a_safe_no_op_without_nvml(monkeypatch):
         assert affinity.bind_to_gpu(0) is None
     finally:
         os.sched_setaffinity(0, before)
+
+
+def test_horovod_package_layout_and_programmatic_run():
+    """Deep imports scripts use (`horovod.torch.elastic`, `horovod.torch.mpi_ops`, `horovod.common.exceptions`, ...) and
+    `horovod.run(fn, np=N)`: the function runs on N ranks under the native mpirun, results come back in rank order."""
+    import horovod
+    import horovod.torch.elastic as hvde
+    from horovod.common.exceptions import HorovodInternalError, HostsUpdatedInterrupt
+    from horovod.common.util import mpi_built, nccl_built
+    from horovod.torch.compression import Compression
+    from horovod.torch.functions import broadcast_parameters
+    from horovod.torch.mpi_ops import allreduce_async_, poll, synchronize
+    from horovod.torch.optimizer import DistributedOptimizer
+    from horovod.torch.sync_batch_norm import SyncBatchNorm
+    assert HorovodInternalError is hvd.HorovodInternalError and HostsUpdatedInterrupt is hvde.HostsUpdatedInterrupt
+    assert hvde.run is hvd.elastic.run and Compression is hvd.Compression and SyncBatchNorm is hvd.SyncBatchNorm
+    assert callable(allreduce_async_) and callable(poll) and callable(synchronize) and callable(broadcast_parameters)
+    assert DistributedOptimizer is hvd.DistributedOptimizer and mpi_built() and nccl_built()
+    if not os.path.exists(os.path.join(_repo(), "mpi_operator_b200/bin/mpirun")):
+        pytest.skip("native launcher not built (run make)")
+
+    def sum_of_ranks(offset):
+        import torch as t
+        import horovod.torch as h
+        h.init()
+        out = float(h.allreduce(t.tensor([float(h.rank() + offset)]), op=h.Sum))
+        r = h.rank()
+        h.shutdown()
+        return r, out
+    res = horovod.run(sum_of_ranks, args=(10,), np=3, env={"B200MPI_HVD_DEVICE": "cpu"})
+    assert res == [(0, 33.0), (1, 33.0), (2, 33.0)]
