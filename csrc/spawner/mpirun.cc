@@ -27,6 +27,7 @@
 #include <fstream>
 #include <map>
 #include <sstream>
+#include <dirent.h>
 #include <string>
 #include <sys/stat.h>
 #include <vector>
@@ -548,6 +549,19 @@ int main(int argc, char** argv) {
   }
   if (g_signal) return 128 + (int)g_signal;
   if (timeout_s > 0 && killing && first_fail_rank < 0) { fprintf(stderr, "mpirun (b200mpi): job exceeded --timeout %d s\n", timeout_s); return 124; }
+  // Every rank is gone: remove the job's shared-memory segments (runtime, libmpi shim, Horovod-core engine). The ranks unlink
+  // them themselves on a clean shutdown; after a crash, a kill or a script that simply exits they would stay in /dev/shm forever.
+  {
+    std::string key;
+    for (char ch : job_id) key.push_back((isalnum((unsigned char)ch) || ch == '-' || ch == '_' || ch == '.') ? ch : '_');
+    if (DIR* d = opendir("/dev/shm")) {
+      while (dirent* de = readdir(d)) {
+        const std::string n = de->d_name;
+        if (n.rfind("b200mpi-", 0) == 0 && n.find(key) != std::string::npos) unlink(("/dev/shm/" + n).c_str());
+      }
+      closedir(d);
+    }
+  }
   if (first_fail_rank >= 0) {
     int code = WIFEXITED(first_fail_status) ? WEXITSTATUS(first_fail_status) : 128 + WTERMSIG(first_fail_status);
     fprintf(stderr,

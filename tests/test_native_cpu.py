@@ -90,6 +90,19 @@ def test_mpirun_failure_propagation_kills_siblings_and_reports():
     assert r.returncode == 127
 
 
+def test_mpirun_removes_the_jobs_shared_memory_segments(tmp_path):
+    """Ranks that crash, get killed or simply exit without MPI_Finalize leave their rendezvous segments behind; the launcher
+    removes everything that carries its job id once all ranks are gone."""
+    src = tmp_path / "leaky.c"
+    src.write_text('#include <mpi.h>\n#include <unistd.h>\nint main(int c, char** v) { MPI_Init(&c, &v); MPI_Barrier(MPI_COMM_WORLD); _exit(0); }\n')
+    exe = tmp_path / "leaky"
+    subprocess.run(["gcc", "-I" + os.path.join(REPO, "mpi_operator_b200/include"), "-o", str(exe), str(src), "-L" + os.path.join(REPO, "mpi_operator_b200/lib"),
+                    "-lmpi", "-Wl,-rpath," + os.path.join(REPO, "mpi_operator_b200/lib")], check=True)
+    r = run([MPIRUN, "-np", "3", str(exe)], env={"B200MPI_JOB_ID": "leak-check-job"})
+    assert r.returncode == 0, r.stderr
+    assert not [n for n in os.listdir("/dev/shm") if "leak-check-job" in n]
+
+
 def test_mpirun_image_relative_path_falls_back_to_path_lookup():
     r = run([MPIRUN, "-n", "2", "/home/mpiuser/pi", "20000"], env={"PATH": BIN + os.pathsep + os.environ["PATH"], "B200MPI_JOB_ID": f"t-{os.getpid()}"})
     assert r.returncode == 0 and "pi is approximately 3." in r.stdout
