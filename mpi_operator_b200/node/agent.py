@@ -696,6 +696,24 @@ class NodeAgent:
         self.alloc.release(M.key_of(pod))
         self._write_all_slots()
 
+    @staticmethod
+    def _sweep_shm(env) -> None:
+        """The container's processes are gone (exited, or killed together with their mpirun, which then could not clean up):
+        drop the rendezvous / data segments that carry its job id, like kubelet tearing down a pod's emptyDir."""
+        job = (env or {}).get("B200MPI_JOB_ID", "")
+        if not job:
+            return
+        key = "".join(ch if (ch.isalnum() or ch in "-_.") else "_" for ch in job)
+        try:
+            for n in os.listdir("/dev/shm"):
+                if n.startswith("b200mpi-") and key in n:
+                    try:
+                        os.unlink(os.path.join("/dev/shm", n))
+                    except OSError:
+                        pass
+        except OSError:
+            pass
+
     def _harvest_stats(self, pr: _Proc) -> None:
         """Per-rank collective counters (runtime/comm.py: dump_stats) -> b200mpi_collective_*_total. Files are consumed
         so an OnFailure restart of the same container is not counted twice."""
@@ -738,6 +756,7 @@ class NodeAgent:
             return
         pr.popen = None
         self._harvest_stats(pr)
+        self._sweep_shm(getattr(pr, "_env", None))
         if rc == 0:
             self._set_terminal(pod, pr, "Succeeded", 0, "Completed")
             return
@@ -771,6 +790,7 @@ class NodeAgent:
                 pr.popen.wait(timeout=2)
         except (ProcessLookupError, PermissionError, subprocess.TimeoutExpired):
             pass
+        self._sweep_shm(getattr(pr, "_env", None))     # the ranks were killed along with their mpirun: nobody else cleans up
 
     # ----------------------------------------------------- volume refresh --
     def refresh_config_volumes(self) -> None:
