@@ -97,8 +97,12 @@ class CoreV1Api:
     def read_namespaced_pod(self, name, namespace, **kw):
         return _Obj(self._c.get_resource("pods", namespace, name))
 
-    def read_namespaced_pod_log(self, name, namespace, **kw):
-        return self._c.logs("", namespace, pod=name)
+    def read_namespaced_pod_log(self, name, namespace, tail_lines=None, follow=False, _preload_content=True, **kw):
+        """``follow=True, _preload_content=False`` returns an iterator over the log as it grows (until the pod finishes)."""
+        if follow:
+            stream = self._c.follow_pod_log(name, namespace, timeout=float(kw.get("_request_timeout") or 3600.0))
+            return stream if not _preload_content else "".join(stream)
+        return self._c.logs("", namespace, pod=name, tail=tail_lines)
 
     def list_namespaced_event(self, namespace, **kw):
         return _List([_Obj(e) for e in self._c.list_resource("events", namespace)])

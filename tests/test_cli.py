@@ -151,5 +151,11 @@ def test_logs_follow_and_get_watch(server, tmp_path):
     cli = MPIJobClient(server)
     pod = [p["metadata"]["name"] for p in cli.list_resource("pods", "default") if "follow-launcher" in p["metadata"]["name"]][0]
     assert "".join(cli.follow_pod_log(pod, timeout=10)).count("tick-") == 3
+    from kubernetes import client as k8s, config as k8s_config
+    k8s_config.load_kube_config(host=server)
+    core = k8s.CoreV1Api()
+    assert core.read_namespaced_pod_log(pod, "default", tail_lines=1) == "tick-3\n"
+    assert "".join(core.read_namespaced_pod_log(pod, "default", follow=True, _preload_content=False)).count("tick-") == 3
+    assert core.read_namespaced_pod(pod, "default").status.phase == "Succeeded"
     wout, _ = watch.communicate(timeout=30)
     assert watch.returncode == 0 and "NAME" in wout and "Succeeded" in wout and wout.count("follow") >= 2, wout   # several change lines
