@@ -1050,6 +1050,7 @@ void engine_main(Engine* e) {
     }
   }
   uint32_t carry_flags = 0;
+  int idle_cycles = 0;
   for (;;) {
     const auto t_start = std::chrono::steady_clock::now();
     e->cycle_no++;
@@ -1096,9 +1097,13 @@ void engine_main(Engine* e) {
     autotune_step(e, !rsp.empty());
     // 4. sleep out the rest of the cycle unless there is work waiting
     const bool busy = !rsp.empty() || !e->gpu_inflight.empty();
+    // nothing submitted, pending or half-negotiated anywhere for 100 cycles: stretch the cycle five-fold (a local submission
+    // still wakes this thread at once; a peer that is backing off adds at most that stretch to the first tensor after a pause)
+    idle_cycles = (busy || !e->pending.empty() || !e->table.empty()) ? 0 : idle_cycles + 1;
+    const double stretch = idle_cycles > 100 ? 5.0 : 1.0;
     if (!busy) {
       std::unique_lock<std::mutex> lk(e->mu);
-      const auto deadline = t_start + std::chrono::microseconds((int64_t)(e->cycle_ms.load() * 1000.0));
+      const auto deadline = t_start + std::chrono::microseconds((int64_t)(e->cycle_ms.load() * 1000.0 * stretch));
       e->queue_cv.wait_until(lk, deadline, [&] { return !e->queue.empty() || e->shutdown_requested.load(); });
     } else if (!e->gpu_inflight.empty() && rsp.empty()) {
       std::this_thread::sleep_for(std::chrono::microseconds(50));

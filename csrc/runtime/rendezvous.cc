@@ -2,12 +2,14 @@
 
 #include <errno.h>
 #include <fcntl.h>
+#include <linux/futex.h>
 #include <sched.h>
 #include <signal.h>
 #include <string.h>
 #include <sys/mman.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
+#include <sys/syscall.h>
 #include <sys/un.h>
 #include <time.h>
 #include <unistd.h>
@@ -24,6 +26,22 @@ uint64_t now_ns() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (uint64_t)ts.tv_sec * 1000000000ull + ts.tv_nsec;
+}
+
+static inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield");
+#endif
+}
+// futex on a word in the shared segment (no FUTEX_PRIVATE_FLAG: waiters and waker are different processes)
+static void futex_wait(std::atomic<uint32_t>* addr, uint32_t expected, long timeout_ns) {
+  timespec ts{timeout_ns / 1000000000L, timeout_ns % 1000000000L};
+  syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAIT, expected, &ts, nullptr, 0);
+}
+static void futex_wake_all(std::atomic<uint32_t>* addr) {
+  syscall(SYS_futex, reinterpret_cast<uint32_t*>(addr), FUTEX_WAKE, INT32_MAX, nullptr, nullptr, 0);
 }
 
 static void nap(int& spins) {
@@ -154,24 +172,35 @@ int Rendezvous::barrier(int timeout_ms, std::string* err) {
   if (hdr_->bar_count.fetch_add(1, std::memory_order_acq_rel) + 1 == (uint32_t)world_) {
     hdr_->bar_count.store(0, std::memory_order_relaxed);
     hdr_->bar_sense.store(sense, std::memory_order_release);
+    futex_wake_all(&hdr_->bar_sense);
     return 0;
   }
+  // Waiters spin briefly (the common case: everyone arrives within microseconds), then sleep in the kernel on the sense word
+  // (a futex shared between processes) and are woken by the last arriver; every wake-up or 2 ms they re-check abort / timeout /
+  // dead peers. No sched_yield storms when ranks outnumber cores, no busy CPU while a peer is late.
   const uint64_t t0 = now_ns();
+  uint64_t last_check = t0;
   int spins = 0;
   while (hdr_->bar_sense.load(std::memory_order_acquire) != sense) {
     if (hdr_->abort_flag.load(std::memory_order_relaxed)) { *err = "rendezvous: job aborted"; return -ECANCELED; }
-    if ((spins & 0xff) == 0xff) {
-      if ((now_ns() - t0) / 1000000ull > (uint64_t)timeout_ms) { *err = "rendezvous: host barrier timed out"; return -ETIMEDOUT; }
+    if ((++spins & 15) != 0) { cpu_relax(); continue; }
+    const uint64_t now = now_ns();
+    if (now - t0 < 40000ull) continue;          // spin ~40 us: data-phase skew (a 256 KiB copy) fits in it
+    if (now - t0 < 80000ull) { sched_yield(); continue; }
+    if (now - last_check > 100000000ull) {    // every 100 ms
+      last_check = now;
+      if ((now - t0) / 1000000ull > (uint64_t)timeout_ms) { *err = "rendezvous: host barrier timed out"; return -ETIMEDOUT; }
       for (int r = 0; r < world_; r++) {
         if (r != rank_ && kill(hdr_->slot[r].pid, 0) != 0 && errno == ESRCH) {
           *err = "rendezvous: rank " + std::to_string(r) + " (pid " + std::to_string(hdr_->slot[r].pid) + ") died";
           hdr_->abort_flag.store(1);
+          futex_wake_all(&hdr_->bar_sense);
           return -EPIPE;
         }
       }
       heartbeat();
     }
-    nap(spins);
+    futex_wait(&hdr_->bar_sense, sense ^ 1u, 2000000);   // returns at once if the word already changed
   }
   return 0;
 }
