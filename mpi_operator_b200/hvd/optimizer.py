@@ -30,7 +30,8 @@ class _DistributedOptimizer:
         if any(p.dtype != torch.float32 for p in params):
             raise ValueError("DistributedOptimizer expects fp32 parameters (use autocast for low-precision compute)")
         self._params = list(reversed(params))
-        cap = (bucket_bytes or int(os.environ.get("B200MPI_BUCKET_BYTES", 32 << 20))) // 4
+        on_host = getattr(self._comm, "device", None) == "cpu"   # smaller buckets on the host: they are what overlaps with backward
+        cap = (bucket_bytes or int(os.environ.get("B200MPI_BUCKET_BYTES", (4 << 20) if on_host else (32 << 20)))) // 4
         self._buckets: List[dict] = []
         cur = {"start": 0, "numel": 0, "params": []}
         self._slot = {}
@@ -54,6 +55,12 @@ class _DistributedOptimizer:
             p.grad = self._flat[start:start + p.numel()].as_strided(p.size(), p.stride())
         self._gpu = self._comm.device != "cpu"   # CPU jobs (libmpi shim backend): same buckets, synchronous collectives
         self._stream = torch.cuda.Stream(priority=-1) if self._gpu else None
+        # Host tensors: each bucket goes to the background engine as a named async allreduce, so the reduction of bucket k runs
+        # while autograd produces bucket k+1 (measured on the MNIST convnet, 2 ranks: 72-77 ms/step vs 77-83 with the synchronous
+        # libmpi call in the hook; single rank 72.8). B200MPI_HVD_BUCKET_ASYNC=0 keeps the synchronous path.
+        from . import _state
+        self._engine = _state.get("engine") if (not self._gpu and os.environ.get("B200MPI_HVD_BUCKET_ASYNC", "1") != "0") else None
+        self._handles = []
         for b in self._buckets:
             b["pending"] = len(b["params"])
             for p in b["params"]:
@@ -71,6 +78,12 @@ class _DistributedOptimizer:
     def _fire(self, b):
         import contextlib
         scale = 1.0 / self._passes if self._passes > 1 else None
+        if self._engine is not None and self._op != "adasum":
+            from . import allreduce_async_
+            self._handles.append(allreduce_async_(self._flat[b["start"]:b["start"] + b["numel"]], name=f"DistributedOptimizer.bucket.{b['start']}",
+                                                  op=_OPS[self._op], postscale_factor=scale or 1.0))
+            b["pending"] = -1
+            return
         if self._gpu:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
@@ -88,6 +101,9 @@ class _DistributedOptimizer:
         for b in self._buckets:
             if b["pending"] != -1:
                 self._fire(b)
+        for h in self._handles:
+            h.wait()
+        self._handles = []
         if self._gpu:
             torch.cuda.current_stream().wait_stream(self._stream)
 
