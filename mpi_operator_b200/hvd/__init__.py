@@ -209,7 +209,7 @@ def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1
             h.post = lambda _r, _t=t, _o=tensor: _o.copy_(_t.to(_o.dtype))
         return h
     t = tensor if tensor.is_contiguous() else tensor.contiguous()
-    if t.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+    if _on_gpu() and t.dtype not in (torch.float32, torch.bfloat16, torch.float16):   # the host backend reduces every MPI type natively
         f = t.float()
         _comm().allreduce(f, f, op=opn, scale=prescale_factor * postscale_factor)
         tensor.copy_(f.to(tensor.dtype))

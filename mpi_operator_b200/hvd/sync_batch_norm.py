@@ -15,7 +15,8 @@ class _SyncBNFunction(torch.autograd.Function):
         from . import Sum, allreduce
         red = [0] + list(range(2, x.dim()))
         c = x.shape[1]
-        xf = x.float()
+        acc = torch.float64 if x.dtype == torch.float64 else torch.float32   # statistics in fp32 (fp64 stays fp64)
+        xf = x.to(acc)
         if training:
             local = torch.cat([xf.sum(red), (xf * xf).sum(red), torch.full((1,), float(xf.numel() // c), device=x.device)])
             tot = allreduce(local, op=Sum, name=f"{name}.fwd")
@@ -28,13 +29,13 @@ class _SyncBNFunction(torch.autograd.Function):
                     unbiased = var * (count / (count - 1).clamp_min(1))
                     running_var.mul_(1 - momentum).add_(unbiased.to(running_var.dtype), alpha=momentum)
         else:
-            mean, var, count = running_mean.float(), running_var.float(), None
+            mean, var, count = running_mean.to(acc), running_var.to(acc), None
         invstd = torch.rsqrt(var + eps)
         shape = [1, c] + [1] * (x.dim() - 2)
         xhat = (xf - mean.view(shape)) * invstd.view(shape)
         out = xhat
         if weight is not None:
-            out = out * weight.float().view(shape) + bias.float().view(shape)
+            out = out * weight.to(acc).view(shape) + bias.to(acc).view(shape)
         ctx.save_for_backward(xhat, invstd, weight)
         ctx.training, ctx.name, ctx.count = training, name, count
         return out.to(x.dtype)
@@ -46,10 +47,10 @@ class _SyncBNFunction(torch.autograd.Function):
         red = [0] + list(range(2, dy.dim()))
         c = dy.shape[1]
         shape = [1, c] + [1] * (dy.dim() - 2)
-        dyf = dy.float()
+        dyf = dy.to(xhat.dtype)
         dweight = (dyf * xhat).sum(red) if weight is not None else None
         dbias = dyf.sum(red) if weight is not None else None
-        g = dyf * weight.float().view(shape) if weight is not None else dyf
+        g = dyf * weight.to(xhat.dtype).view(shape) if weight is not None else dyf
         if ctx.training:
             local = torch.cat([g.sum(red), (g * xhat).sum(red)])
             tot = allreduce(local, op=Sum, name=f"{ctx.name}.bwd")

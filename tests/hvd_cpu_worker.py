@@ -86,8 +86,8 @@ ref_out = ref_bn(xf)
 xl = full[4 * r:4 * r + 4].clone().requires_grad_(True)
 yl = sbn(xl)
 (yl * w_out[4 * r:4 * r + 4]).sum().backward()
-assert torch.allclose(yl, ref_out[4 * r:4 * r + 4].detach(), atol=1e-9)
-assert torch.allclose(xl.grad, xf.grad[4 * r:4 * r + 4], atol=1e-9)
+assert torch.allclose(yl, ref_out[4 * r:4 * r + 4].detach(), rtol=0, atol=1e-12)
+assert torch.allclose(xl.grad, xf.grad[4 * r:4 * r + 4], rtol=0, atol=1e-12)
 assert torch.allclose(hvd.allreduce(sbn.weight.grad, op=hvd.Sum), ref_bn.weight.grad, atol=1e-9)
 assert torch.allclose(sbn.running_mean, ref_bn.running_mean, atol=1e-9) and torch.allclose(sbn.running_var, ref_bn.running_var, atol=1e-9)
 sbn.eval()

@@ -101,8 +101,8 @@ def _repo():
     return _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("np_", [1, 3])
-def test_horovod_api_on_the_cpu_backend_under_mpirun(np_):
+@pytest.mark.parametrize("np_,engine", [(1, "1"), (3, "1"), (2, "0")])
+def test_horovod_api_on_the_cpu_backend_under_mpirun(np_, engine):
     """The reference's Horovod example is a CPU job (examples/v2beta1/horovod/tensorflow-mnist.yaml: cpu-only workers).
     Without CUDA, hvd.init() builds the libmpi-shim communicator (hvd/host_backend.py); tests/hvd_cpu_worker.py checks
     every collective, DistributedOptimizer against SGD on the averaged gradient, Adasum and the elastic State."""
@@ -113,7 +113,7 @@ def test_horovod_api_on_the_cpu_backend_under_mpirun(np_):
     mpirun = os.path.join(repo, "mpi_operator_b200/bin/mpirun")
     if not os.path.exists(mpirun):
         pytest.skip("native launcher not built (run make)")
-    env = dict(os.environ, B200MPI_HVD_DEVICE="cpu")
+    env = dict(os.environ, B200MPI_HVD_DEVICE="cpu", B200MPI_HVD_ENGINE=engine)   # "0": direct call-order path over the libmpi shim
     r = subprocess.run([mpirun, "-np", str(np_), sys.executable, os.path.join(repo, "tests/hvd_cpu_worker.py")],
                        capture_output=True, text=True, timeout=180, env=env, cwd="/tmp")
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
