@@ -241,10 +241,27 @@ def allgather_async(tensor, name=None):
     e = _engine_for(tensor)
     if e is not None and not tensor.is_cuda:
         return e.allgather_async(tensor if tensor.dim() else tensor.reshape(1), name)
-    t = tensor.contiguous()
-    out = torch.empty((size() * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    _comm().allgather(t, out)
-    return _Done(out)
+    t = tensor.contiguous() if tensor.dim() else tensor.reshape(1)
+    n = size()
+    # direct path: the ranks first tell each other their first dimension (one 8-byte allgather), equal sizes then take the
+    # single-kernel path, ragged ones are padded to the largest and trimmed after the gather (Horovod semantics: concatenation
+    # along dim 0 with per-rank first dimensions)
+    mine = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    rows = torch.empty(n, dtype=torch.int64, device=t.device)
+    _comm().allgather(mine, rows)
+    rows = rows.tolist()
+    if len(set(rows)) == 1:
+        out = torch.empty((n * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        if out.numel():
+            _comm().allgather(t, out)
+        return _Done(out)
+    width = max(rows)
+    padded = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[:t.shape[0]] = t
+    got = torch.empty((n * width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    _comm().allgather(padded, got)
+    got = got.view((n, width) + tuple(t.shape[1:]))
+    return _Done(torch.cat([got[k, :rows[k]] for k in range(n)], dim=0))
 
 
 def broadcast(tensor, root_rank, name=None):

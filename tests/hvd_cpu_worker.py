@@ -30,6 +30,9 @@ assert torch.equal(inplace, n * torch.arange(10.) + n * (n - 1) / 2)
 # allgather / broadcast / alltoall / reducescatter
 g = hvd.allgather(torch.full((2, 3), float(r)))
 assert g.shape == (2 * n, 3) and all(torch.equal(g[2 * k:2 * k + 2], torch.full((2, 3), float(k))) for k in range(n))
+rag = hvd.allgather(torch.full((r + 1, 2), float(r)))                  # ragged first dimension (engine: allgatherv; direct path: pad + trim)
+assert torch.equal(rag, torch.cat([torch.full((k + 1, 2), float(k)) for k in range(n)]))
+assert hvd.allgather(torch.tensor(float(r))).tolist() == [float(k) for k in range(n)]      # 0-dim tensors gather to [n]
 b = hvd.broadcast(torch.full((5,), float(r)), root_rank=n - 1)
 assert torch.equal(b, torch.full((5,), float(n - 1)))
 a2a = hvd.alltoall(torch.arange(n, dtype=torch.float32) + 100 * r)
