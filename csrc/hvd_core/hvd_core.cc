@@ -203,7 +203,6 @@ struct LocalOp {
   int handle = 0;
   int device = -1;
   void* ready_event = nullptr;
-  uint64_t t_enq = 0;
 };
 struct Handle { bool done = false; int status = 0; std::string err; };
 
@@ -360,7 +359,6 @@ struct Engine {
   unsigned char* seg = nullptr;
   size_t seg_bytes = 0, box = 0;
   uint64_t last_stall_scan = 0;
-  bool stall_shutdown_pending = false;
   // HOROVOD_AUTOTUNE (rank 0 decides, see autotune_step): grid search over {cycle time} x {fusion threshold}, scored by
   // reduced bytes per second over windows of busy cycles
   bool autotune = false, autotune_done = false;
@@ -1205,7 +1203,7 @@ int hvdcore_enqueue(hvd_op_t op, const char* name, const void* in, void* out, in
   q.count = count;
   if (extra && n_extra > 0) q.extra.assign(extra, extra + n_extra);
   if (op == HVD_EXCHANGE && count) q.blob.assign((const char*)in, (size_t)count);
-  lo.in = in; lo.out = out; lo.device = device; lo.ready_event = ready_event; lo.t_enq = now_ns();
+  lo.in = in; lo.out = out; lo.device = device; lo.ready_event = ready_event;
   std::lock_guard<std::mutex> lk(e->mu);
   if (e->stopped.load()) return fail(e->stop_code, e->stop_reason.empty() ? "Horovod has been shut down" : e->stop_reason);
   if (name && *name) q.name = name;
