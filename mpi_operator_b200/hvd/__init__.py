@@ -156,6 +156,36 @@ def _op_name(op, average):
     raise ValueError(f"unknown reduction op {op!r}")
 
 
+class ProcessSet:
+    """Horovod >= 0.23 process sets. Only the global set exists here (the reference's Horovod 0.19/0.20 predates the feature):
+    ``process_set=hvd.global_process_set`` is accepted everywhere, ``hvd.add_process_set`` explains itself."""
+
+    process_set_id = 0
+
+    def size(self) -> int: return size()  # noqa: E704
+
+    def rank(self) -> int: return rank()  # noqa: E704
+
+    def included(self) -> bool: return True  # noqa: E704
+
+    @property
+    def ranks(self):
+        return list(range(size()))
+
+
+global_process_set = ProcessSet()
+
+
+def add_process_set(ranks):
+    raise NotImplementedError("process sets other than hvd.global_process_set are not implemented (one NVSwitch box: every "
+                              "collective spans the job's ranks); split the job into several MPIJobs instead")
+
+
+def _check_process_set(ps) -> None:
+    if ps is not None and ps is not global_process_set:
+        raise NotImplementedError("only hvd.global_process_set is supported")
+
+
 class _Done:
     """Handle of an operation that already completed in stream order (direct path)."""
 
@@ -176,13 +206,15 @@ def _engine_for(tensor):
     return e
 
 
-def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    _check_process_set(process_set)
     out = tensor.clone()
     allreduce_(out, average, name, op, prescale_factor, postscale_factor)
     return out
 
 
-def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    _check_process_set(process_set)
     return allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor).wait()
 
 
@@ -231,7 +263,8 @@ def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_
             for i, t in enumerate(tensors)]
 
 
-def allgather(tensor, name=None):
+def allgather(tensor, name=None, process_set=None):
+    _check_process_set(process_set)
     return allgather_async(tensor, name).wait()
 
 
@@ -264,12 +297,14 @@ def allgather_async(tensor, name=None):
     return _Done(torch.cat([got[k, :rows[k]] for k in range(n)], dim=0))
 
 
-def broadcast(tensor, root_rank, name=None):
+def broadcast(tensor, root_rank, name=None, process_set=None):
+    _check_process_set(process_set)
     out = tensor.clone()
     return broadcast_(out, root_rank, name)
 
 
-def broadcast_(tensor, root_rank, name=None):
+def broadcast_(tensor, root_rank, name=None, process_set=None):
+    _check_process_set(process_set)
     return broadcast_async_(tensor, root_rank, name).wait()
 
 

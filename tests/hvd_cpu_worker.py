@@ -46,6 +46,13 @@ got, recv_splits = hvd.alltoall(send, splits=[d + 1 for d in range(n)])
 assert recv_splits.tolist() == [r + 1] * n and got.shape == (n * (r + 1), 2)
 assert torch.equal(got, torch.cat([torch.full((r + 1, 2), float(src)) for src in range(n)]))
 assert hvd.allgather_object({"rank": r, "blob": "x" * (r * 3)}) == [{"rank": k, "blob": "x" * (k * 3)} for k in range(n)]
+assert hvd.global_process_set.size() == n and hvd.global_process_set.ranks == list(range(n)) and hvd.global_process_set.included()
+assert torch.equal(hvd.allreduce(torch.ones(2), op=hvd.Sum, process_set=hvd.global_process_set), torch.full((2,), float(n)))
+try:
+    hvd.add_process_set([0])
+    raise SystemExit("add_process_set should explain that only the global set exists")
+except NotImplementedError:
+    pass
 hvd.barrier()
 
 # DistributedOptimizer == SGD on the rank-averaged gradient, identical parameters on every rank afterwards
