@@ -62,12 +62,24 @@ def add_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--fake-gpus", type=int, default=None, help="pretend the box has N GPUs (tests)")
     p.add_argument("-v", "--v", dest="verbosity", type=int, default=0, help="log verbosity (klog -v)")
     p.add_argument("--alsologtostderr", action="store_true", help="accepted for manifest compatibility")
+    # the rest of klog's flag set (options.go:93-95 registers all of them): accepted, inert — logging goes to stderr
+    p.add_argument("--logtostderr", nargs="?", const="true", default="true", help=argparse.SUPPRESS)
+    p.add_argument("--stderrthreshold", default="", help=argparse.SUPPRESS)
+    p.add_argument("--log_dir", "--log-dir", dest="log_dir", default="", help=argparse.SUPPRESS)
+    p.add_argument("--log_file", "--log-file", dest="log_file", default="", help=argparse.SUPPRESS)
+    p.add_argument("--vmodule", default="", help=argparse.SUPPRESS)
+    p.add_argument("--skip_headers", "--skip-headers", dest="skip_headers", nargs="?", const="true", default="", help=argparse.SUPPRESS)
     p.add_argument("--no-leader-elect", dest="leader_elect", action="store_false")
 
 
 def parse(argv: Optional[List[str]] = None) -> ServerOption:
     p = argparse.ArgumentParser(prog="mpi-operator", description="single-box MPIJob operator daemon")
     add_flags(p)
+    import sys
+    argv = list(sys.argv[1:] if argv is None else argv)
+    # Go's flag package (the reference binary) takes -flag and --flag alike; its manifests use the single dash
+    # (manifests/base/deployment.yaml: `-alsologtostderr`), so do the same here
+    argv = ["-" + a if (a.startswith("-") and not a.startswith("--") and len(a.split("=", 1)[0]) > 2) else a for a in argv]
     ns = p.parse_args(argv)
     opt = ServerOption()
     for k in opt.__dataclass_fields__:

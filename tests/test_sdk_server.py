@@ -233,6 +233,13 @@ def test_watch_stream_delivers_added_modified_deleted_in_order(tmp_path):
         op.stop()
 
 
+def test_go_style_single_dash_flags_and_klog_flags_are_accepted():
+    """The reference's Deployment passes `-alsologtostderr` (Go flag syntax); klog's other flags are registered too."""
+    o = parse(["-alsologtostderr", "-v=4", "-threadiness", "3", "-lock-namespace=kubeflow", "-logtostderr=true", "-stderrthreshold=INFO",
+               "--monitoring-port", "9090", "-v", "2"])
+    assert o.threadiness == 3 and o.lock_namespace == "kubeflow" and o.monitoring_port == 9090
+
+
 def test_api_discovery_documents(tmp_path):
     """`/api`, `/apis`, `/api/v1`, `/apis/kubeflow.org/v2beta1`, `/openapi/v2`: what kubectl / client libraries read first."""
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
