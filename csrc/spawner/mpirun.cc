@@ -557,7 +557,13 @@ int main(int argc, char** argv) {
     if (DIR* d = opendir("/dev/shm")) {
       while (dirent* de = readdir(d)) {
         const std::string n = de->d_name;
-        if (n.rfind("b200mpi-", 0) == 0 && n.find(key) != std::string::npos) unlink(("/dev/shm/" + n).c_str());
+        // names are b200mpi-<id>[-suffix] and b200mpi-mpi-<id>[-suffix]: match the id exactly, not as a substring (pid 123 vs 1234)
+        for (const char* prefix : {"b200mpi-mpi-", "b200mpi-"}) {
+          const size_t pl = strlen(prefix);
+          if (n.compare(0, pl, prefix) != 0) continue;
+          const std::string rest = n.substr(pl);
+          if (rest == key || rest.compare(0, key.size() + 1, key + "-") == 0) { unlink(("/dev/shm/" + n).c_str()); break; }
+        }
       }
       closedir(d);
     }

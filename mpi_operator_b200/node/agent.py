@@ -706,7 +706,9 @@ class NodeAgent:
         key = "".join(ch if (ch.isalnum() or ch in "-_.") else "_" for ch in job)
         try:
             for n in os.listdir("/dev/shm"):
-                if n.startswith("b200mpi-") and key in n:
+                # b200mpi-[mpi-]<job id>.<mpirun pid>[-suffix]: match the id up to a separator, not as a substring
+                rest = n[len("b200mpi-mpi-"):] if n.startswith("b200mpi-mpi-") else (n[len("b200mpi-"):] if n.startswith("b200mpi-") else None)
+                if rest is not None and (rest == key or rest.startswith(key + ".") or rest.startswith(key + "-")):
                     try:
                         os.unlink(os.path.join("/dev/shm", n))
                     except OSError:
