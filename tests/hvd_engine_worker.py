@@ -130,6 +130,12 @@ nc = torch.arange(12, dtype=torch.float32).view(3, 4).t()          # non-contigu
 hvd.allreduce_(nc, op=hvd.Sum, name="noncontig")
 assert torch.equal(nc, n * torch.arange(12, dtype=torch.float32).view(3, 4).t())
 
+# reductions fold in rank order on exactly one rank per slice: the result is bit-identical everywhere (floating-point sums too)
+noisy = torch.randn(100003, generator=torch.Generator().manual_seed(99 + r)) * 10.0 ** float(r)
+red = hvd.allreduce(noisy, op=hvd.Sum, name="bits")
+sig = hvd.allgather(red.view(torch.int32).to(torch.int64).sum().reshape(1, 1), name="bits.sig")
+assert all(int(sig[k]) == int(sig[0]) for k in range(n)), sig
+
 # ragged allgather: rank k contributes k + 1 rows
 g = hvd.allgather(torch.full((r + 1, 2), float(r)), name="ragged")
 assert g.shape == (n * (n + 1) // 2, 2)
