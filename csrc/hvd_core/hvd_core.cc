@@ -37,6 +37,8 @@ thread_local std::string t_err;
 int fail(int code, const std::string& msg) { t_err = msg; return code; }
 
 constexpr size_t kInline = 248;          // negotiation bytes that ride in the first (small) exchange of a cycle
+constexpr size_t kTail = 1024;           // end of every mailbox: two alternating slots for that exchange
+constexpr size_t kBody = kRvMailbox - kTail;   // what long messages / mailbox data phases may use (a multiple of 8)
 constexpr size_t kMaxBlob = 1024;        // HVD_EXCHANGE payload limit
 constexpr uint32_t kFlagShutdown = 1u, kFlagStallShutdown = 2u, kFlagAutotune = 4u;   // autotune: rank 0's tunables are adopted by all
 const char* const kOpName[] = {"ALLREDUCE", "ALLGATHER", "BROADCAST", "ALLTOALL", "BARRIER", "JOIN", "EXCHANGE"};
@@ -420,8 +422,19 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
   *fusion = h.fusion;
   memcpy(small, &h, sizeof(h));
   memcpy(small + sizeof(h), mine.data(), std::min(mine.size(), kInline));
+  // The small exchange costs ONE barrier: it lives in the last kTail bytes of the mailbox, in two slots used alternately. A rank
+  // may write slot p^1 (next cycle) while a slow peer still reads slot p; it cannot get two cycles ahead because the next cycle's
+  // barrier needs that peer. Everything else that goes through the mailbox (long messages, data without the box segment) stays
+  // below the tail (kBody).
   std::vector<unsigned char> got(sizeof(small) * W);
-  if (e->rv.allgather(small, got.data(), sizeof(small), e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+  {
+    static_assert(sizeof(small) <= kTail / 2, "exchange slot too small");
+    b200mpi::RvHeader* H = e->rv.header();
+    const size_t slot = kBody + (size_t)(e->cycle_no & 1u) * (kTail / 2);
+    memcpy(H->slot[e->rank].mailbox + slot, small, sizeof(small));
+    if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+    for (int r = 0; r < W; r++) memcpy(got.data() + (size_t)r * sizeof(small), H->slot[r].mailbox + slot, sizeof(small));
+  }
   all->assign(W, std::string());
   *all_flags = 0;
   int64_t tuned_fusion = -1;
@@ -445,7 +458,7 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
   size_t off = kInline;
   std::vector<unsigned char> big, mine_chunk;
   while (off < max_len) {
-    const size_t chunk = std::min(kRvMailbox, max_len - off);
+    const size_t chunk = std::min(kBody, max_len - off);
     mine_chunk.assign(chunk, 0);
     if (mine.size() > off) memcpy(mine_chunk.data(), mine.data() + off, std::min(chunk, mine.size() - off));
     big.resize(chunk * W);
@@ -462,7 +475,7 @@ int exchange(Engine* e, const std::string& mine, uint32_t flags, std::vector<std
 
 inline unsigned char* box_data(Engine* e, int r) { return e->seg ? e->seg + (size_t)r * 2 * e->box : e->rv.header()->slot[r].mailbox; }
 inline unsigned char* box_result(Engine* e, int r) { return e->seg + (size_t)r * 2 * e->box + e->box; }
-inline size_t box_bytes(Engine* e) { return e->seg ? e->box : kRvMailbox; }
+inline size_t box_bytes(Engine* e) { return e->seg ? e->box : kBody; }
 
 // acc = fold over ranks (in rank order) of n elements found at offset `off` of every rank's data box; result to `out`
 void fold_boxes(Engine* e, size_t off, size_t n, int dt, int op, void* out) {
