@@ -364,7 +364,8 @@ struct Engine {
   // HOROVOD_AUTOTUNE (rank 0 decides, see autotune_step): grid search over {cycle time} x {fusion threshold}, scored by
   // reduced bytes per second over windows of busy cycles
   bool autotune = false, autotune_done = false;
-  int at_warmup = 3, at_steps = 10, at_idx = -1, at_busy = 0, at_best = -1;
+  int at_warmup = 3, at_steps = 10, at_idx = -1, at_busy = 0, at_best = -1, at_tail = 3;   // at_tail: cycles that still announce the final choice
+  bool at_seen = false;                                                                    // (other ranks) rank 0 has been announcing
   uint64_t at_bytes0 = 0, at_t0 = 0, at_samples = 0;
   double at_best_score = 0;
   std::vector<std::pair<double, int64_t>> at_grid;
@@ -1080,13 +1081,19 @@ void engine_main(Engine* e) {
         e->pending.emplace(q.name, std::move(op));
       }
     }
-    uint32_t flags = carry_flags | (e->shutdown_requested.load() ? kFlagShutdown : 0) | (e->autotune && e->rank == 0 ? kFlagAutotune : 0);
+    bool announce = e->autotune && e->rank == 0 && (!e->autotune_done || e->at_tail > 0);
+    if (announce && e->autotune_done) e->at_tail--;
+    uint32_t flags = carry_flags | (e->shutdown_requested.load() ? kFlagShutdown : 0) | (announce ? kFlagAutotune : 0);
     carry_flags = 0;
     // 2. exchange + replicated coordination
     std::vector<std::string> msgs;
     uint32_t all_flags = 0;
     int64_t fusion = 0;
     if (exchange(e, w.s, flags, &msgs, &all_flags, &fusion)) { fail_everything(e, HVD_ERR_TRANSPORT, "hvdcore: " + t_err); break; }
+    if (e->autotune && e->rank != 0) {     // followers: the search is over once rank 0 stops announcing candidates
+      if (all_flags & kFlagAutotune) e->at_seen = true;
+      else if (e->at_seen) e->autotune_done = true;
+    }
     std::vector<Response> rsp;
     coordinate(e, msgs, &rsp);
     if (e->mark_cycles && !rsp.empty() && e->tl.on())   // HOROVOD_TIMELINE_MARK_CYCLES: a tick on row 0 for every cycle with work

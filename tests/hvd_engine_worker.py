@@ -39,8 +39,9 @@ if mode == "autotune":
     mine = torch.tensor([st["cycle_time_ms"], float(st["fusion_threshold"])], dtype=torch.float64)
     everyone = hvd.allgather(mine.view(1, 2), name="at.params")
     assert all(torch.equal(everyone[0], everyone[k]) for k in range(n)), everyone        # every rank ended on rank 0's choice
+    assert st["autotune"] == "done", st                   # followers notice that rank 0 stopped announcing candidates
     if r == 0:
-        assert st["autotune"] == "done" and st["autotune_samples"] >= 21, st
+        assert st["autotune_samples"] >= 21, st
         rows = [l for l in open(os.environ["HOROVOD_AUTOTUNE_LOG"]).read().splitlines() if l and l[0].isdigit()]
         assert len(rows) == 20 and len({tuple(l.split(",")[:2]) for l in rows}) == 20, rows
         assert st["cycle_time_ms"] in (0.5, 1.0, 2.5, 5.0) and st["fusion_threshold"] in (1 << 20, 4 << 20, 16 << 20, 64 << 20, 128 << 20)
