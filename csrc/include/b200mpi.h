@@ -60,6 +60,7 @@ enum {
 enum {
   B200MPI_FLAG_NO_MULTICAST = 1u << 0, /* never create NVLS multicast objects */
   B200MPI_FLAG_FORCE_IPC = 1u << 1,    /* cudaIpc instead of VMM fd export    */
+  B200MPI_FLAG_NO_PIPE = 1u << 2,      /* user-pointer allreduce: never the pipelined kernel (chunked staged two-shot) */
 };
 
 const char* b200mpi_last_error(void);
@@ -206,6 +207,10 @@ int b200mpi_set_tuning(b200mpi_comm_t comm, size_t oneshot_max_bytes, size_t nvl
 int b200mpi_get_tuning(b200mpi_comm_t comm, size_t* oneshot_max_bytes, size_t* nvls_min_bytes,
                        int* max_blocks, int* timeout_ms);
 /* which algorithm would AUTO pick */
+/* Pipelined user-pointer allreduce (k_allreduce_pipe): messages of at least `min_bytes` (SIZE_MAX: keep) run as one
+ * kernel of `lanes` x {copy-in, reduce, copy-out} CTAs with `depth` staging slots of `chunk_bytes` per lane.
+ * Non-positive values keep the current setting. Env: B200MPI_PIPE_{MIN_BYTES,LANES_NVLS,LANES_P2P,DEPTH,CHUNK_BYTES}. */
+int b200mpi_set_pipe(b200mpi_comm_t comm, size_t min_bytes, int lanes_nvls, int lanes_p2p, int depth, size_t chunk_bytes);
 int b200mpi_select_algo(b200mpi_comm_t comm, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op,
                         int symmetric);
 

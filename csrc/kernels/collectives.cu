@@ -167,6 +167,145 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
 }
 
 // ===========================================================================
+// Pipelined staged allreduce for arbitrary user pointers (the path the NCCL-ABI
+// shim and hvd take for tensors that do not live in a symmetric window).
+// The message is cut into chunks; lane l owns chunks l, l+L, l+2L ... and is a
+// chain of THREE CTAs that run concurrently and hand chunks on through flags:
+//   role 0 (copy-in)  user input -> staging slot            -> IN flag to all ranks
+//   role 1 (reduce)   wait IN of all ranks; slice `rank` of the chunk is reduced
+//                     (multimem.ld_reduce, or pull from every peer) and the result
+//                     written to every rank's slot (multimem.st / peer stores)
+//                                                            -> RED flag to all ranks
+//   role 2 (copy-out) wait RED of all ranks; staging slot -> user output
+//                                                            -> local counter (frees the slot)
+// so while chunk k is on NVLink, chunk k+1 is being copied in and chunk k-1 copied
+// out: the local HBM copies that serialised the old staged kernel (three phases, two
+// full barriers, 370 GB/s at 8 GPUs) disappear behind the link time. A slot is
+// reused for chunk k+depth only after the local copy-out of chunk k, which itself
+// waited for every rank's RED flag, i.e. for every peer's last access to the slot.
+// Flags only grow (per-role, per-lane counters persist in the epoch array), so the
+// kernel is CUDA-graph capturable like the others.
+// ===========================================================================
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_allreduce_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  const int L = a.lanes, D = a.depth;
+  const int role = blockIdx.x / L, lane = blockIdx.x - role * L;
+  const size_t Cv = a.per;
+  const size_t nchunks = (a.nvec + Cv - 1) / Cv;
+  const uint32_t n_mine = nchunks > (size_t)lane ? (uint32_t)((nchunks - lane + L - 1) / L) : 0u;
+  uint32_t* const ctr = a.c.epoch + kPipeEpochOff + (size_t)role * kPipeLanes + lane;
+  uint32_t* const out_done = a.c.epoch + kPipeEpochOff + 3 * (size_t)kPipeLanes + lane;
+  const uint32_t base = *ctr;
+  const size_t row_in = kPipeSigOff + (size_t)lane * kMaxRanks;
+  const size_t row_red = kPipeSigOff + ((size_t)kPipeLanes + lane) * kMaxRanks;
+  char* const mine = a.buf.p[rank];
+  const bool do_scale = a.scale != 1.0f;
+
+  for (uint32_t j = 0; j < n_mine; j++) {
+    const size_t v0 = ((size_t)lane + (size_t)j * L) * Cv;           // first vector of the chunk in the message
+    const size_t len = a.nvec - v0 < Cv ? a.nvec - v0 : Cv;          // vectors in this chunk
+    const size_t slot = ((size_t)lane * D + (j % D)) * Cv;           // vector offset of the staging slot
+    const uint32_t tgt = base + j + 1;
+    if (role == 0) {
+      if (j >= (uint32_t)D) local_wait(a.c, out_done, tgt - D);
+      constexpr int U = 8;
+      for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < len) v[u] = user_load(a.in, v0 + i, a.nbytes, a.in_aligned);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < len) *reinterpret_cast<uint4*>(mine + (slot + i) * 16) = v[u];
+        }
+      }
+      flag_signal_all(a.c, row_in, tgt);
+    } else if (role == 1) {
+      flag_wait_all(a.c, row_in, tgt);
+      const size_t per = (len + world - 1) / world;
+      const size_t sb = (size_t)rank * per;
+      const size_t lim = sb < len ? (len - sb < per ? len - sb : per) : 0;
+      if (MODE == MODE_NVLS) {
+        constexpr int U = 4;
+        char* const mc = a.buf.mc + (slot + sb) * 16;
+        for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
+          uint4 v[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+            if (i < lim) v[u] = nvls_ld_reduce<T>(mc + i * 16, a.op);
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+            if (i < lim) multimem_st_v4(mc + i * 16, do_scale ? scale_vec<T>(v[u], a.scale) : v[u]);
+          }
+        }
+      } else {
+        constexpr int U = 2;
+        char* pp[kMaxRanks];
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + (slot + sb) * 16;
+        for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
+          uint4 v[U][kMaxRanks];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+#pragma unroll
+            for (int k = 0; k < kMaxRanks; k++)
+              if (k < world && i < lim) v[u][k] = ld_sys_v4(pp[k] + i * 16);
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+            if (i < lim) {
+              float acc[VecTraits<T>::N];
+#pragma unroll
+              for (int k = 0; k < kMaxRanks; k++)
+                if (k < world) accum<T>(acc, v[u][k], a.op, k == 0);
+              if (do_scale) {
+#pragma unroll
+                for (int q = 0; q < VecTraits<T>::N; q++) acc[q] *= a.scale;
+              }
+              const uint4 o = VecTraits<T>::pack(acc);
+#pragma unroll
+              for (int k = 0; k < kMaxRanks; k++)
+                if (k < world) st_peer_v4(pp[k] + i * 16, o);
+            }
+          }
+        }
+      }
+      flag_signal_all(a.c, row_red, tgt);
+    } else {
+      flag_wait_all(a.c, row_red, tgt);
+      constexpr int U = 8;
+      for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < len) v[u] = ld_sys_v4(mine + (slot + i) * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t i = i0 + (size_t)u * blockDim.x;
+          if (i < len) user_store(a.out, v0 + i, a.nbytes, a.out_aligned, v[u]);
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) st_release_gpu(out_done, tgt);
+    }
+  }
+  if (threadIdx.x == 0) *ctr = base + n_mine;
+}
+
+// ===========================================================================
 // Push one-shot allreduce (latency path). Every rank stores its input straight
 // into a private slot of every peer's staging window, signals, then reduces
 // the `world` slots that landed in its own HBM — one NVLink traversal and one
@@ -523,6 +662,10 @@ cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype,
   }
   if (staged) DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, true>, l, a))
   DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, false>, l, a))
+}
+cudaError_t launch_allreduce_pipe(const Launch& l, const KArgs& a, int dtype, int mode) {
+  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_allreduce_pipe<T, MODE_NVLS>, l, a))
+  DISPATCH_T(dtype, go(k_allreduce_pipe<T, MODE_P2P>, l, a))
 }
 cudaError_t launch_allreduce_oneshot(const Launch& l, const KArgs& a, int dtype) {
   DISPATCH_T(dtype, go(k_allreduce_oneshot<T>, l, a))

@@ -25,6 +25,17 @@ constexpr int kOneshotBlocks = 32;     // fixed staging partition of the push on
 constexpr size_t kSigWords = (size_t)kMaxBlocks * kMaxRanks;
 // epoch array (u32 words): [0,kMaxBlocks) barrier epochs, [kMaxBlocks, 2*kMaxBlocks) one-shot use counts
 constexpr size_t kEpochWords = 2 * (size_t)kMaxBlocks;
+// Pipelined staged allreduce (k_allreduce_pipe): kPipeLanes independent lanes, each a chain of three CTAs
+// (copy-in, reduce, copy-out) that hand chunks to each other through flags.
+//   signal pad  : [kSigWords, kSigWords + 2*kPipeLanes*kMaxRanks)  IN-ready / REDUCED flags, [kind][lane][src rank]
+//   epoch array : [kEpochWords, kEpochWords + 4*kPipeLanes)        chunks done so far per (role, lane), then the
+//                                                                  local copy-out counter the copy-in CTA polls
+constexpr int kPipeLanes = 48;
+constexpr size_t kPipeSigOff = kSigWords;
+constexpr size_t kPipeSigWords = 2 * (size_t)kPipeLanes * kMaxRanks;
+constexpr size_t kSigWordsTotal = kSigWords + kPipeSigWords;
+constexpr size_t kPipeEpochOff = kEpochWords;
+constexpr size_t kEpochWordsTotal = kEpochWords + 4 * (size_t)kPipeLanes;
 
 enum : int { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };
 
@@ -49,6 +60,14 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -79,6 +98,45 @@ __device__ __forceinline__ void rank_barrier(const DevComm& c, uint32_t epoch) {
           *c.err = 1 + peer;
           break;
         }
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// One-directional variants of the barrier for pipelines: `flag_signal_all` publishes `value` in slot [src = me] of
+// every rank's flag row (after the CTA's earlier stores, ordered by the bar.sync), `flag_wait_all` waits until every
+// rank's slot of MY row reached `value`. `row` is the word offset of the row inside the signal pad.
+__device__ __forceinline__ void flag_signal_all(const DevComm& c, size_t row, uint32_t value) {
+  __syncthreads();
+  if (threadIdx.x < (unsigned)c.world) st_release_sys(c.sig[threadIdx.x] + row + c.rank, value);
+}
+__device__ __forceinline__ void flag_wait_all(const DevComm& c, size_t row, uint32_t value) {
+  if (threadIdx.x < (unsigned)c.world) {
+    const int peer = threadIdx.x;
+    const uint32_t* mine = c.sig[c.rank] + row + peer;
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_sys(mine) - value) < 0) {
+      if ((++spins & 0x3ffu) == 0) {
+        unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > c.timeout_ns) { *c.err = 1 + peer; break; }
+      }
+    }
+  }
+  __syncthreads();
+}
+// same-GPU counter written by another CTA of this kernel
+__device__ __forceinline__ void local_wait(const DevComm& c, const uint32_t* p, uint32_t value) {
+  if (threadIdx.x == 0) {
+    unsigned long long t0 = 0;
+    uint32_t spins = 0;
+    while ((int32_t)(ld_acquire_gpu(p) - value) < 0) {
+      if ((++spins & 0x3ffu) == 0) {
+        unsigned long long now = globaltimer_ns();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > c.timeout_ns) { *c.err = 1 + c.rank; break; }
       }
     }
   }

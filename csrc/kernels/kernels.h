@@ -30,6 +30,9 @@ struct KArgs {
   const float* hyper;  // optional device {lr, mu, wd}: lets a captured CUDA graph follow LR schedules
   int nesterov;
   int first_step;
+  // pipelined staged allreduce: lanes x {copy-in, reduce, copy-out} CTAs, `depth` staging slots of `per` vectors per lane
+  int lanes;
+  int depth;
 };
 
 struct Launch {
@@ -73,6 +76,7 @@ enum : int { MODE_P2P = 0, MODE_NVLS = 1 };
 
 // a = args of this rank (ignored in emulated mode where l.emu_args is used)
 cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype, int mode, bool staged);
+cudaError_t launch_allreduce_pipe(const Launch& l, const KArgs& a, int dtype, int mode);
 cudaError_t launch_allreduce_oneshot(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_allreduce_sgd(const Launch& l, const KArgs& a, int dtype, int mode);
 cudaError_t launch_allgather(const Launch& l, const KArgs& a);

@@ -148,6 +148,10 @@ struct b200mpi_comm {
   int max_blocks = 64;
   int nvls_blocks = 16;  // the switch does the adds: 16 CTAs saturate NVLS (sweep: nvls@16 >= nvls@32 > nvls@128)
   int timeout_ms = 30000;
+  // pipelined staged allreduce (user pointers): from pipe_min bytes up; lanes per mode (each lane = 3 CTAs)
+  size_t pipe_min = (size_t)8 << 20;
+  int pipe_lanes_nvls = 16, pipe_lanes_p2p = 40, pipe_depth = 3;
+  size_t pipe_chunk = (size_t)1 << 20;
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
   std::vector<TraceRec> trace;
@@ -420,6 +424,11 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   c->nvls_min = env_size("B200MPI_NVLS_MIN_BYTES", c->nvls_min);
   c->max_blocks = std::min(env_int("B200MPI_MAX_BLOCKS", c->max_blocks), kMaxBlocks);
   c->nvls_blocks = std::min(env_int("B200MPI_NVLS_BLOCKS", c->nvls_blocks), kMaxBlocks);
+  c->pipe_min = env_size("B200MPI_PIPE_MIN_BYTES", c->pipe_min);
+  c->pipe_lanes_nvls = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_NVLS", c->pipe_lanes_nvls), kPipeLanes));
+  c->pipe_lanes_p2p = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_P2P", c->pipe_lanes_p2p), kPipeLanes));
+  c->pipe_depth = std::max(2, std::min(env_int("B200MPI_PIPE_DEPTH", c->pipe_depth), 8));
+  c->pipe_chunk = std::max((size_t)16 << 10, env_size("B200MPI_PIPE_CHUNK_BYTES", c->pipe_chunk));
   if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", (size_t)64 << 20);
   // one-shot region: 2 parities x kOneshotBlocks CTAs x kMaxRanks slots x cap
   c->oneshot_cap_vecs = 2048;  // 32 KiB per slot -> 1 MiB max one-shot payload
@@ -436,11 +445,11 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   const int nlocal = c->local ? c->world : 1;
   for (int i = 0; i < nlocal; i++) {
     const int r = c->local ? i : c->rank;
-    CUDA_TRY(cudaMalloc((void**)&c->epoch[r], kEpochWords * sizeof(uint32_t)));
-    CUDA_TRY(cudaMemset(c->epoch[r], 0, kEpochWords * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc((void**)&c->epoch[r], kEpochWordsTotal * sizeof(uint32_t)));
+    CUDA_TRY(cudaMemset(c->epoch[r], 0, kEpochWordsTotal * sizeof(uint32_t)));
   }
   if (c->local) CUDA_TRY(cudaMalloc((void**)&c->emu_ring, sizeof(KArgs) * kMaxRanks * b200mpi_comm::kEmuRing));
-  int rc = window_alloc(c, kSigWords * sizeof(uint32_t), &c->sig_win);
+  int rc = window_alloc(c, kSigWordsTotal * sizeof(uint32_t), &c->sig_win);
   if (rc) return rc;
   rc = window_alloc(c, c->stage_bytes, &c->stage_win);
   if (rc) return rc;
@@ -545,6 +554,31 @@ static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const vo
     }
     return run(c, stream, blocks, "allreduce", nbytes, algo, args,
                [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, mode, false); });
+  }
+  // staged, large: ONE pipelined kernel (copy-in / reduce / copy-out CTAs chained through flags per lane)
+  if (nbytes >= c->pipe_min && !(c->flags & B200MPI_FLAG_NO_PIPE)) {
+    int L = mode == MODE_NVLS ? c->pipe_lanes_nvls : c->pipe_lanes_p2p;
+    if (c->local) L = std::max(1, std::min(L, emu_max_blocks(c) / 3));
+    const int D = c->pipe_depth;
+    const size_t nvec = (nbytes + 15) / 16;
+    // chunk: at most pipe_chunk, small enough that every lane gets >= 2 chunks, and L*D slots must fit the staging region
+    size_t cv = std::min(c->pipe_chunk / 16, c->twoshot_bytes / 16 / ((size_t)L * D));
+    cv = std::min(cv, std::max((size_t)1024, nvec / ((size_t)L * 2)));
+    cv = std::max((size_t)c->world, cv / c->world * c->world);
+    for (size_t k = 0; k < ranks.size(); k++) {
+      const int r = ranks[k];
+      KArgs& a = args[k];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, r);
+      a.buf = win_region(c, c->stage_win, c->twoshot_off);
+      a.in = in_ptr(c, in, r);
+      a.out = out_ptr(c, out, r);
+      a.nbytes = nbytes; a.nvec = nvec; a.per = cv; a.scale = scale; a.op = op;
+      a.lanes = L; a.depth = D;
+      a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
+    }
+    return run(c, stream, 3 * L, "allreduce_pipe", nbytes, algo, args,
+               [&](const Launch& l, const KArgs& a) { return launch_allreduce_pipe(l, a, dtype, mode); });
   }
   // staged: chunk through the two-shot staging region
   const size_t chunk_max = c->twoshot_bytes / 16 * 16;
@@ -872,6 +906,14 @@ int b200mpi_get_tuning(b200mpi_comm_t c, size_t* oneshot_max, size_t* nvls_min, 
   if (nvls_min) *nvls_min = c->nvls_min;
   if (max_blocks) *max_blocks = c->max_blocks;
   if (timeout_ms) *timeout_ms = c->timeout_ms;
+  return 0;
+}
+int b200mpi_set_pipe(b200mpi_comm_t c, size_t min_bytes, int lanes_nvls, int lanes_p2p, int depth, size_t chunk_bytes) {
+  if (min_bytes != (size_t)-1) c->pipe_min = min_bytes;
+  if (lanes_nvls > 0) c->pipe_lanes_nvls = std::min(lanes_nvls, kPipeLanes);
+  if (lanes_p2p > 0) c->pipe_lanes_p2p = std::min(lanes_p2p, kPipeLanes);
+  if (depth > 0) c->pipe_depth = std::max(2, std::min(depth, 8));
+  if (chunk_bytes > 0) c->pipe_chunk = std::max((size_t)16 << 10, chunk_bytes);
   return 0;
 }
 int b200mpi_select_algo(b200mpi_comm_t c, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op, int symmetric) {

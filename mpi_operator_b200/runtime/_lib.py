@@ -19,7 +19,7 @@ F32, BF16, F16 = 0, 1, 2
 SUM, MAX, MIN = 0, 1, 2
 ALGO_AUTO, ALGO_ONESHOT, ALGO_TWOSHOT, ALGO_NVLS = 0, 1, 2, 3
 ALGO_NAMES = {0: "auto", 1: "oneshot", 2: "twoshot", 3: "nvls"}
-FLAG_NO_MULTICAST, FLAG_FORCE_IPC = 1, 2
+FLAG_NO_MULTICAST, FLAG_FORCE_IPC, FLAG_NO_PIPE = 1, 2, 4
 
 _lib = None
 
@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
     L.b200mpi_set_tuning.argtypes = [vp, sz, sz, i, i]
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
     L.b200mpi_select_algo.argtypes = [vp, sz, i, i, i]
+    L.b200mpi_set_pipe.argtypes = [vp, sz, i, i, i, sz]
     if hasattr(L, "b200mpi_p2p_batch"):  # experimental point-to-point (csrc/kernels/p2p.cu)
         L.b200mpi_p2p_batch.argtypes = [vp, vp, i, vp]
         L.b200mpi_comm_has_p2p.argtypes = [vp]

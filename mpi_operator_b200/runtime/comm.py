@@ -231,6 +231,12 @@ class Communicator:
         check(_lib.lib().b200mpi_set_tuning(self._h, as_sz(oneshot_max_bytes), as_sz(nvls_min_bytes), max_blocks,
                                             timeout_ms))
 
+    def set_pipe(self, min_bytes: int = -1, lanes_nvls: int = 0, lanes_p2p: int = 0, depth: int = 0,
+                 chunk_bytes: int = 0) -> None:
+        """Pipelined user-pointer allreduce (``k_allreduce_pipe``): size threshold, lanes per mode, slots, chunk size."""
+        check(_lib.lib().b200mpi_set_pipe(self._h, C.c_size_t(-1).value if min_bytes < 0 else min_bytes, lanes_nvls,
+                                          lanes_p2p, depth, chunk_bytes))
+
     def get_tuning(self) -> dict:
         a, b, c_, d = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_int()
         _lib.lib().b200mpi_get_tuning(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d))

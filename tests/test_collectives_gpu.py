@@ -49,6 +49,50 @@ def test_allreduce_generic(comm, dtype, algo, n, op):
         assert torch.equal(o, outs[0])
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [5, 4099, (1 << 20) + 13, 3 * (1 << 20) + 7])
+@pytest.mark.parametrize("chunk", [16 << 10, 256 << 10])
+def test_allreduce_pipelined_user_pointers(comm, dtype, n, chunk):
+    """k_allreduce_pipe: lanes of copy-in / reduce / copy-out CTAs chained through flags; many chunks per lane
+    (slot reuse), ragged last chunk, sizes below one chunk, out of place and in place, back to back."""
+    comm.set_pipe(min_bytes=0, chunk_bytes=chunk, depth=2)
+    try:
+        for it in range(3):
+            xs = _rand(comm.world, n, dtype, seed=n + it)
+            want = _ref(xs, "avg")
+            outs = [torch.empty_like(x) for x in xs] if it != 1 else xs
+            comm.allreduce(xs, outs, op="avg", algo="twoshot")
+            torch.cuda.synchronize()
+            comm.check_error()
+            rtol, atol = TOL[dtype]
+            for o in outs:
+                torch.testing.assert_close(o.float(), want.to(dtype).float(), rtol=rtol, atol=atol)
+                assert torch.equal(o, outs[0])
+        assert any(o["op"] == "allreduce_pipe" for o in comm.stats(native_only=True)["ops"])
+    finally:
+        comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20, depth=3)
+
+
+def test_pipelined_and_barrier_kernels_interleave(comm):
+    """The pipeline keeps its own flags and counters: interleaving it with the barrier-based kernels on the same
+    staging window must stay bit-exact (integer-valued data)."""
+    comm.set_pipe(min_bytes=64 << 10, chunk_bytes=32 << 10, depth=2)
+    try:
+        g = torch.Generator().manual_seed(4)
+        sizes = torch.randint(1, 200000, (40,), generator=g).tolist()
+        bufs = [(b * 8).round() for b in _rand(comm.world, 200000, torch.float32, seed=11)]
+        for i, n in enumerate(sizes):
+            xs = [t[:n].clone() for t in bufs]
+            want = torch.stack(xs).sum(0)
+            comm.allreduce(xs, xs, algo="twoshot" if i % 2 else "auto")
+            for x in xs:
+                assert torch.equal(x, want), f"iteration {i} n={n}"
+        torch.cuda.synchronize()
+        comm.check_error()
+    finally:
+        comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20, depth=3)
+
+
 def test_allreduce_inplace_unaligned(comm):
     base = [torch.randn(1000 + 3, device="cuda") for _ in range(comm.world)]
     xs = [b[3:] for b in base]  # 12-byte offset: exercises the byte-wise slow path
