@@ -11,13 +11,17 @@ tensorflow-benchmarks.yaml: --model=resnet101 --batch_size=64
 
 --impl ours       (default) b200mpi: symmetric-window gradients, fused
                   allreduce+SGD sm_100a kernels, whole step in a CUDA graph
---impl nccl       same engine, gradient allreduce via stock NCCL (torch.distributed)
-                  + unfused optimizer: "our launcher + stock NCCL" baseline
---impl torchddp   stock torch DDP + torch.optim.SGD, eager (the identical-script baseline)
+--impl nccl       same engine (fused BN kernels, CUDA graph), gradient allreduce via stock NCCL
+                  (torch.distributed) + unfused optimizer: isolates what the collective runtime buys
+--impl torchddp   STOCK: torchvision's resnet101 + torch DDP + torch.optim.SGD, eager, bf16 autocast;
+                  none of this repo's kernels or engine (the identical-workload baseline on the same box)
 --impl reference  the unmodified reference from baseline/_ref (a Go Kubernetes
                   operator: cannot run here -> prints {"unavailable": ...})
 
-Prints ONE JSON line on rank 0 (contract in the task description).
+Prints ONE JSON line on rank 0 (contract in the task description). After its own measurement `--impl ours` also runs
+the two same-box baselines as child processes (one per rank, own rendezvous port, own timeout; a failing or hanging
+child cannot break the main line) and reports them under "same_box" with the ratios: the reference itself cannot run on
+this box (see reference_arm), so these are the only same-hardware, same-dtype comparators.
 """
 from __future__ import annotations
 
@@ -94,6 +98,46 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def run_same_box_arms(args, rank: int, world: int, job_id: str) -> dict:
+    """Same-box baselines as child processes: every rank starts `bench.py --impl <arm>` for its own GPU with a shifted
+    rendezvous port / job id; rank 0 parses the child's JSON line. Never raises: a failed arm is reported as such."""
+    out = {}
+    base_port = int(os.environ.get("MASTER_PORT", "29500"))
+    for k, arm in enumerate(("nccl", "torchddp")):
+        env = dict(os.environ)
+        env["MASTER_PORT"] = str(base_port + 211 * (k + 1))
+        env["B200MPI_JOB_ID"] = f"{job_id}-arm-{arm}"
+        env.pop("TORCHELASTIC_RUN_ID", None)
+        cmd = [sys.executable, os.path.abspath(__file__), "--impl", arm, "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--model", args.model, "--batch-size", str(args.batch_size), "--dtype", args.dtype,
+               "--no-same-box"]
+        t0 = time.time()
+        try:
+            p = subprocess.Popen(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+            try:
+                so, se = p.communicate(timeout=args.arm_timeout)
+                rc = p.returncode
+            except subprocess.TimeoutExpired:
+                os.killpg(p.pid, 9)   # exactly the process group this rank started
+                so, se = p.communicate()
+                rc = "timeout"
+        except Exception as e:  # pragma: no cover
+            so, se, rc = "", repr(e), "spawn failed"
+        if rank == 0:
+            line = next((ln for ln in reversed(so.splitlines()) if ln.startswith("{")), None)
+            try:
+                d = json.loads(line) if line else None
+            except ValueError:
+                d = None
+            if d and "value" in d:
+                out[arm] = {"value": d["value"], "ms_per_step": d["ms_per_step"], "e2e": d.get("e2e", {}).get("value"),
+                            "impl": d.get("impl"), "wall_s": round(time.time() - t0, 1)}
+            else:
+                out[arm] = {"error": f"rc={rc}", "stderr_tail": se[-300:] if se else ""}
+    return out
+
+
+
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -106,6 +150,10 @@ def main() -> int:
     ap.add_argument("--no-fused", action="store_true")
     ap.add_argument("--algo", default=None)
     ap.add_argument("--bucket-mb", type=float, default=None)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="compute dtype: bf16 autocast (headline) or fp32 (the reference YAML's precision: no --use_fp16)")
+    ap.add_argument("--no-same-box", action="store_true", help="skip the same-box baseline arms after the measurement")
+    ap.add_argument("--arm-timeout", type=int, default=240)
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -142,7 +190,12 @@ def main() -> int:
     torch.manual_seed(1234)
     comm = Communicator.create(rank, world, dev, info.job_id)
     B = args.batch_size
-    model = build_model(args.model)
+    amp_dtype = torch.bfloat16 if args.dtype == "bf16" else None
+    if args.impl == "torchddp":
+        import torchvision   # stock model definition: nothing of this repo on the baseline's compute path
+        model = getattr(torchvision.models, args.model)(weights=None)
+    else:
+        model = build_model(args.model)
     loss_fn = nn.CrossEntropyLoss()
     lr = 0.01 * world  # Horovod convention: LR x size (tensorflow_mnist.py:123-130)
 
@@ -170,7 +223,7 @@ def main() -> int:
             sx.copy_(host_x[i % nb], non_blocking=True)
             sy.copy_(host_y[i % nb], non_blocking=True)
             opt.zero_grad(set_to_none=True)
-            with torch.autocast("cuda", dtype=torch.bfloat16):
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=amp_dtype is not None):
                 loss = loss_fn(m(sx), sy)
             loss.backward()
             opt.step()
@@ -180,13 +233,13 @@ def main() -> int:
     else:
         trainer = DataParallelTrainer(
             model, loss_fn, comm, lr=lr, momentum=0.9, cuda_graph=not args.no_graph,
-            fused_optimizer=not args.no_fused, algo=args.algo,
+            fused_optimizer=not args.no_fused, algo=args.algo, autocast_dtype=amp_dtype,
             bucket_bytes=int(args.bucket_mb * (1 << 20)) if args.bucket_mb else None,
             comm_backend="nccl" if args.impl == "nccl" else "b200mpi")
 
         def step(i):
             return trainer.step(host_x[i % nb], host_y[i % nb])
-        launches_per_step = lambda: trainer.launches_per_step  # noqa: E731
+        launches_per_step = lambda: trainer.launches_per_step  # noqa: E731  (collective + fused BN / GEMM kernels of one step)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
 
@@ -244,16 +297,31 @@ def main() -> int:
     K = args.steps
     value = world * B * K / (ms_dev_max * 1e-3)
     e2e = world * B * K / (ms_e2e_max * 1e-3)
+    same_box = None
+    if args.impl == "ours" and not args.no_same_box and os.environ.get("B200MPI_BENCH_SAME_BOX", "1") != "0":
+        barrier()
+        arms = run_same_box_arms(args, rank, world, info.job_id)
+        barrier()
+        if rank == 0:
+            def ratio(a, key="value", mine=value):
+                return round(mine / arms[a][key], 3) if arms.get(a, {}).get(key) else None
+            same_box = {
+                "nccl_same_engine": arms.get("nccl"), "torchddp_stock": arms.get("torchddp"),
+                "ratio_vs_nccl": ratio("nccl"), "ratio_vs_torchddp": ratio("torchddp"),
+                "e2e_ratio_vs_nccl": ratio("nccl", "e2e", e2e), "e2e_ratio_vs_torchddp": ratio("torchddp", "e2e", e2e),
+                "what": "same box, same dtype, same batch, run right after the main measurement: nccl_same_engine = this "
+                        "repo's trainer (fused BN kernels, CUDA graph) with the gradient allreduce on stock NCCL + unfused "
+                        "SGD; torchddp_stock = torchvision resnet101 + torch DDP + torch.optim.SGD, eager, no repo code"}
     if rank == 0:
         out = {
             "metric": "resnet101_images_per_sec" if args.model == "resnet101" else f"{args.model}_images_per_sec",
             "value": round(value, 2), "unit": "images/sec", "n_gpus": world, "steps": K, "warmup": args.warmup,
             "ms_per_step": round(ms_dev_max / K, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": round(value / (BASELINE_IMG_S_PER_GPU * world), 3),
-            "dtype": "bf16", "data": "synthetic", "impl": args.impl,
+            "dtype": args.dtype, "data": "synthetic", "impl": args.impl,
             "config": {"model": args.model, "global_batch": B * world, "batch_per_gpu": B, "image": "3x224x224",
                        "parallelism": f"dp{world}", "optimizer": "sgd_momentum0.9", "layout": "channels_last",
-                       "params_dtype": "fp32 master, bf16 autocast compute" + (
+                       "params_dtype": ("fp32 master, bf16 autocast compute" if amp_dtype is not None else "fp32") + (
                            " (bf16 weight shadow refreshed by the fused SGD kernel)"
                            if args.impl != "torchddp" and getattr(trainer, "bf16_params", False) else ""),
                        "l2": "256 MiB buffer rewritten between timed steps (inside the timed region); per-step "
@@ -271,6 +339,8 @@ def main() -> int:
             "gpu_launches": int(launches_per_step() * K),
             "gpu_launches_per_step": int(launches_per_step()),
         }
+        if same_box is not None:
+            out["same_box"] = same_box
         print(json.dumps(out), flush=True)
     barrier()
     if use_dist:

@@ -91,7 +91,14 @@ def main():
                 algos["twoshot"] = lambda: comm.allreduce_window(win, 0, n, dtype, op="avg", algo="twoshot")
                 if comm.has_multicast:
                     algos["nvls"] = lambda: comm.allreduce_window(win, 0, n, dtype, op="avg", algo="nvls")
-                algos["twoshot_staged"] = lambda: comm.allreduce(t, t, op="avg", algo="twoshot")
+                def staged(pipe):
+                    def run():  # user pointers: old chunked staged kernel vs the pipelined kernel (auto = NVLS when bound)
+                        comm.set_pipe(min_bytes=0 if pipe else (1 << 62))
+                        comm.allreduce(t, t, op="avg", algo="auto" if size > (1 << 20) else "twoshot")
+                    return run
+                algos["staged"] = staged(False)
+                if size >= (256 << 10):
+                    algos["pipe"] = staged(True)
             if use_nccl:
                 algos["nccl"] = lambda: dist.all_reduce(t, op=dist.ReduceOp.AVG)
             if a.tune_blocks and size >= (16 << 20):

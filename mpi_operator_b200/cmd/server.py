@@ -191,9 +191,12 @@ class Operator:
         self.store.close()
 
     # ------------------------------------------------------------- serving --
-    def serve(self, listen: str, block: bool = False):
+    def serve(self, listen: str, block: bool = False, restricted: bool = False):
+        """``restricted``: GET /metrics and /healthz only (what the reference serves on --monitoring-port, main.go:29-40,
+        and on :8080, server.go:188-204). The object API (create pods = run commands, read Secrets) is served only on
+        ``--listen``, which defaults to loopback."""
         host, _, port = listen.rpartition(":")
-        srv = ThreadingHTTPServer((host or "127.0.0.1", int(port)), _make_handler(self))
+        srv = ThreadingHTTPServer((host or "127.0.0.1", int(port)), _make_handler(self, restricted=restricted))
         srv.daemon_threads = True
         self._http.append(srv)
         t = threading.Thread(target=srv.serve_forever, daemon=True)
@@ -203,11 +206,21 @@ class Operator:
         return srv
 
 
-def _make_handler(op: Operator):
+def _make_handler(op: Operator, restricted: bool = False):
     store = op.store
 
     class H(BaseHTTPRequestHandler):
         protocol_version = "HTTP/1.1"
+
+        def _refuse(self):
+            """Restricted listeners (monitoring / healthz ports): nothing but GET /metrics and GET /healthz."""
+            if not restricted:
+                return False
+            if self.command == "GET" and self._route()[0] in (["metrics"], ["healthz"]):
+                return False
+            self._send(404 if self.command == "GET" else 405, {"kind": "Status", "status": "Failure", "code": 404 if self.command == "GET" else 405,
+                                                                "message": "this port serves GET /metrics and GET /healthz only"})
+            return True
 
         def log_message(self, fmt, *args):  # quiet
             log.debug("http: " + fmt, *args)
@@ -248,6 +261,8 @@ def _make_handler(op: Operator):
             return None
 
         def do_GET(self):  # noqa: N802
+            if self._refuse():
+                return None
             parts, q = self._route()
             try:
                 if parts == ["healthz"]:
@@ -404,6 +419,8 @@ def _make_handler(op: Operator):
                     raise errors.invalid("mpijobs", M.name_of(obj), "spec.mpiReplicaSpecs: Required value")
 
         def do_POST(self):  # noqa: N802
+            if self._refuse():
+                return None
             parts, _ = self._route()
             try:
                 r = self._resolve(parts)
@@ -419,6 +436,8 @@ def _make_handler(op: Operator):
                 return self._send(e.code, e.to_status())
 
         def do_PUT(self):  # noqa: N802
+            if self._refuse():
+                return None
             parts, _ = self._route()
             try:
                 r = self._resolve(parts)
@@ -435,6 +454,8 @@ def _make_handler(op: Operator):
                 return self._send(e.code, e.to_status())
 
         def do_PATCH(self):  # noqa: N802
+            if self._refuse():
+                return None
             parts, _ = self._route()
             try:
                 r = self._resolve(parts)
@@ -446,6 +467,8 @@ def _make_handler(op: Operator):
                 return self._send(e.code, e.to_status())
 
         def do_DELETE(self):  # noqa: N802
+            if self._refuse():
+                return None
             parts, _ = self._route()
             try:
                 r = self._resolve(parts)
@@ -482,11 +505,11 @@ def run(opt: ServerOption) -> int:
     log.info("REST API on http://%s", opt.listen)
     if opt.healthz_port:
         try:
-            op.serve(f"127.0.0.1:{opt.healthz_port}")
+            op.serve(f"127.0.0.1:{opt.healthz_port}", restricted=True)
         except OSError as e:
             log.warning("healthz port %d unavailable: %s", opt.healthz_port, e)
     if opt.monitoring_port:
-        op.serve(f"0.0.0.0:{opt.monitoring_port}")
+        op.serve(f"0.0.0.0:{opt.monitoring_port}", restricted=True)   # Prometheus scrape port: /metrics + /healthz only
     op.start()
     stop.wait()
     op.stop()

@@ -453,12 +453,18 @@ def broadcast_parameters(params, root_rank: int = 0) -> None:
 
 
 def broadcast_object(obj, root_rank: int = 0, name=None):
+    """Pickle on the root, broadcast, unpickle everywhere. The length travels as four 16-bit limbs in a float32 tensor
+    (every limb is exact in fp32, any length up to 2^64 survives; a single float32 is only exact below 2^24 = 16 MiB)."""
     import pickle
     import torch
     payload = pickle.dumps(obj) if rank() == root_rank else b""
-    n = torch.tensor([len(payload)], dtype=torch.float32, device=_dev())
+    ln0 = len(payload)
+    n = torch.tensor([(ln0 >> (16 * k)) & 0xFFFF for k in range(4)], dtype=torch.float32, device=_dev())
     _comm().broadcast(n, root=root_rank)
-    ln = int(n.item())
+    limbs = [int(v) for v in n.tolist()]
+    ln = sum(v << (16 * k) for k, v in enumerate(limbs))
+    if rank() == root_rank and ln != ln0:
+        raise RuntimeError(f"broadcast_object: length {ln0} did not survive the broadcast ({ln})")
     buf = torch.zeros(ln + (-ln) % 2, dtype=torch.uint8, device=_dev())
     if rank() == root_rank:
         buf[:ln] = torch.frombuffer(bytearray(payload), dtype=torch.uint8).to(_dev())
@@ -480,10 +486,56 @@ def allgather_object(obj, name=None) -> list:
 
 
 def broadcast_optimizer_state(optimizer, root_rank: int = 0) -> None:
-    sd = optimizer.state_dict() if rank() == root_rank else None
-    sd = broadcast_object(sd, root_rank)
+    """Rank `root_rank`'s optimizer state everywhere. The structure (param groups, scalar state) travels as one small
+    pickle; state TENSORS (momentum buffers, Adam moments: hundreds of MB for a real model) are broadcast in place as
+    tensors, never pickled."""
+    import torch
+    sd = optimizer.state_dict()
+    tensors_root = []
+
+    def strip(o):   # tensors -> placeholders (shape, dtype), in deterministic traversal order
+        if isinstance(o, torch.Tensor):
+            tensors_root.append(o)
+            return ("__b200mpi_tensor__", len(tensors_root) - 1, tuple(o.shape), str(o.dtype).replace("torch.", ""), o.device.type)
+        if isinstance(o, dict):
+            return {k: strip(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(strip(v) for v in o)
+        return o
+
+    skeleton = strip(sd) if rank() == root_rank else None
+    skeleton = broadcast_object(skeleton, root_rank)
+    received = {}
+
+    def fill(o):
+        if isinstance(o, tuple) and len(o) == 5 and o[0] == "__b200mpi_tensor__":
+            _, idx, shape, dt, devtype = o
+            if rank() == root_rank:
+                t = tensors_root[idx]
+            else:
+                t = torch.empty(shape, dtype=getattr(torch, dt), device=_dev() if devtype == "cuda" else "cpu")
+            received[idx] = t
+            return t
+        if isinstance(o, dict):
+            return {k: fill(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(fill(v) for v in o)
+        return o
+
+    full = fill(skeleton)
+    for idx in sorted(received):
+        t = received[idx]
+        if t.numel() == 0:
+            continue
+        if (t.dtype in (torch.float32, torch.bfloat16, torch.float16) and t.is_contiguous() and t.dim() > 0
+                and t.device.type == _dev()):
+            broadcast_(t, root_rank, name=f"broadcast_optimizer_state.{idx}")
+        else:   # step counters and other small non-float tensors
+            v = broadcast_object(t.cpu() if rank() == root_rank else None, root_rank)
+            if rank() != root_rank:
+                t.copy_(v.to(t.device))
     if rank() != root_rank:
-        optimizer.load_state_dict(sd)
+        optimizer.load_state_dict(full)
 
 
 class Compression:

@@ -59,17 +59,46 @@ class State:
             self._hosts = cur
             raise HostsUpdatedInterrupt("discover_hosts.sh changed")
 
+    @staticmethod
+    def _is_sampler(v) -> bool:
+        return hasattr(v, "state_dict") and hasattr(v, "load_state_dict") and hasattr(v, "processed_indices")
+
     def save(self):
-        self._saved = {k: getattr(self, k) for k in self._keys}
+        """Snapshot by VALUE (Horovod deep-copies too): a later ``restore()`` must roll back to the commit even when the
+        live objects were mutated in place since. Samplers are saved through their ``state_dict()`` (never the dataset)."""
+        import copy
+        self._saved = {}
+        for k in self._keys:
+            v = getattr(self, k)
+            self._saved[k] = ("__sampler__", copy.deepcopy(v.state_dict())) if self._is_sampler(v) else copy.deepcopy(v)
 
     def restore(self):
+        import copy
         for k, v in self._saved.items():
-            setattr(self, k, v)
+            if isinstance(v, tuple) and len(v) == 2 and v[0] == "__sampler__":
+                cur = getattr(self, k, None)
+                if cur is not None and self._is_sampler(cur):
+                    cur.load_state_dict(copy.deepcopy(v[1]))   # the SAME sampler object the DataLoader holds
+                continue
+            setattr(self, k, copy.deepcopy(v))
 
     def sync(self):
-        from . import broadcast_object
+        """Rank 0's values everywhere. Samplers are merged instead: every rank's processed indices are gathered and
+        united (each rank consumed a different shard), loaded into the existing sampler object and re-partitioned over
+        the current world by its ``reset()`` — rank, shard and dataset stay local."""
+        from . import allgather_object, broadcast_object
         for k in self._keys:
-            setattr(self, k, broadcast_object(getattr(self, k), 0))
+            v = getattr(self, k)
+            if self._is_sampler(v):
+                parts = allgather_object({"epoch": v.epoch, "processed": sorted(v.processed_indices)})
+                epoch = max(p["epoch"] for p in parts)
+                done = set()
+                for p in parts:
+                    if p["epoch"] == epoch:
+                        done.update(p["processed"])
+                v.load_state_dict({"epoch": epoch, "processed_indices": sorted(done)})
+                continue
+            setattr(self, k, broadcast_object(v, 0))
 
 
 ObjectState = State   # Horovod's name for the generic state
@@ -88,7 +117,8 @@ class TorchState(State):
         if self.model is not None:
             self._model_sd = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
         if self.optimizer is not None:
-            self._opt_sd = self.optimizer.state_dict()
+            import copy
+            self._opt_sd = copy.deepcopy(self.optimizer.state_dict())   # state_dict() aliases the live momentum tensors
         if self.checkpoint_path and rank() == 0:  # rank-0-only checkpoint
             tmp = self.checkpoint_path + ".tmp"
             torch.save({"model": self._model_sd, "optimizer": self._opt_sd, "extra": self._saved}, tmp)
@@ -103,7 +133,8 @@ class TorchState(State):
         if self.model is not None and self._model_sd is not None:
             self.model.load_state_dict(self._model_sd)
         if self.optimizer is not None and self._opt_sd is not None:
-            self.optimizer.load_state_dict(self._opt_sd)
+            import copy
+            self.optimizer.load_state_dict(copy.deepcopy(self._opt_sd))   # load_state_dict adopts the tensors it is given
 
     def sync(self):
         from . import broadcast_optimizer_state, broadcast_parameters

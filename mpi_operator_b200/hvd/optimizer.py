@@ -24,8 +24,14 @@ class _DistributedOptimizer:
         self._opt = optimizer
         self._comm = _comm()
         self._op = _op_name(op, None)
-        self._passes = backward_passes_per_step
-        self._pass = 0
+        self._passes = max(1, int(backward_passes_per_step))
+        from . import Compression
+        if compression not in (None, Compression.none):
+            raise ValueError("the window/bucket DistributedOptimizer does not compress gradients; pass engine=True (or set "
+                             "B200MPI_HVD_OPTIMIZER=engine) for compression")
+        self._predivide = float(gradient_predivide_factor)
+        if self._predivide != 1.0 and self._op != "avg":
+            raise ValueError("gradient_predivide_factor requires op=Average")
         params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
         if any(p.dtype != torch.float32 for p in params):
             raise ValueError("DistributedOptimizer expects fp32 parameters (use autocast for low-precision compute)")
@@ -61,23 +67,41 @@ class _DistributedOptimizer:
         from . import _state
         self._engine = _state.get("engine") if (not self._gpu and os.environ.get("B200MPI_HVD_BUCKET_ASYNC", "1") != "0") else None
         self._handles = []
+        self._counts = {p: 0 for p in params}   # backward passes seen per parameter since the last step()
         for b in self._buckets:
             b["pending"] = len(b["params"])
             for p in b["params"]:
                 p.register_post_accumulate_grad_hook(self._hook(b))
 
+    def _rehome(self, p):
+        """``p.grad`` must stay a view of the symmetric window (that is what the bucket kernel reduces). Code that drops
+        it (``model.zero_grad()`` defaults to set_to_none=True, ``p.grad = None``) makes autograd allocate a fresh tensor:
+        copy it into the window slot and point ``p.grad`` back at the view instead of silently reducing stale zeros."""
+        _, start = self._slot[p]
+        view = self._flat[start:start + p.numel()].as_strided(p.size(), p.stride())
+        if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+            if self._counts[p] > 1:
+                view.add_(p.grad)     # earlier passes of this accumulation round are already in the window
+            else:
+                view.copy_(p.grad)
+            p.grad = view
+
     def _hook(self, b):
-        def fn(_p):
-            if self._pass + 1 < self._passes:
-                return
-            b["pending"] -= 1
-            if b["pending"] == 0:
-                self._fire(b)
+        def fn(p):
+            # Horovod usage with backward_passes_per_step = N: N x backward() then ONE step(). Count backward passes per
+            # parameter (autograd accumulates into the window view) and reduce the bucket when every parameter of it has
+            # seen its N-th pass.
+            self._counts[p] += 1
+            self._rehome(p)
+            if self._counts[p] == self._passes:
+                b["pending"] -= 1
+                if b["pending"] == 0:
+                    self._fire(b)
         return fn
 
     def _fire(self, b):
         import contextlib
-        scale = 1.0 / self._passes if self._passes > 1 else None
+        scale = 1.0 / self._passes if self._passes > 1 else None   # mean over the local passes, fused into the reduction
         if self._engine is not None and self._op != "adasum":
             from . import allreduce_async_
             self._handles.append(allreduce_async_(self._flat[b["start"]:b["start"] + b["numel"]], name=f"DistributedOptimizer.bucket.{b['start']}",
@@ -98,8 +122,14 @@ class _DistributedOptimizer:
         b["pending"] = -1
 
     def synchronize(self):
+        for p in self._params:      # gradients replaced behind our back since the last hook
+            if p.grad is None:
+                _, start = self._slot[p]
+                p.grad = self._flat[start:start + p.numel()].as_strided(p.size(), p.stride())
+            else:
+                self._rehome(p)
         for b in self._buckets:
-            if b["pending"] != -1:
+            if b["pending"] != -1:  # parameters without a gradient this round, or fewer backward passes than configured
                 self._fire(b)
         for h in self._handles:
             h.wait()
@@ -110,18 +140,21 @@ class _DistributedOptimizer:
     def step(self, closure=None):
         from ..utils import fault
         fault.injector().on_step()
-        self._pass += 1
-        if self._pass < self._passes:
-            return None
-        self._pass = 0
-        self.synchronize()
+        self.synchronize()          # always: step() is the one call per update (Horovod semantics)
         out = self._opt.step(closure)
         for b in self._buckets:
             b["pending"] = len(b["params"])
+        for p in self._counts:
+            self._counts[p] = 0
         return out
 
     def zero_grad(self, set_to_none: bool = False):
-        self._flat.zero_()  # gradients stay views of the symmetric window
+        """Zeroes the window; gradients stay views of it whatever ``set_to_none`` says (they must remain peer-visible)."""
+        self._flat.zero_()
+        for p in self._params:
+            if p.grad is None or p.grad.data_ptr() != self._flat[self._slot[p][1]:].data_ptr():
+                _, start = self._slot[p]
+                p.grad = self._flat[start:start + p.numel()].as_strided(p.size(), p.stride())
 
     def __getattr__(self, name):
         return getattr(self._opt, name)

@@ -32,6 +32,12 @@ def fused_bn_available(x: torch.Tensor, bn: torch.nn.BatchNorm2d) -> bool:
 
 
 _WS_CACHE = {}
+_LAUNCHES = 0   # kernels of this module launched so far (each fused call = 3: stats/reduce, finalize, apply/elemt)
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
 
 # ``num_batches_tracked`` bookkeeping: one 1-element add kernel per BN layer per step (104 launches for ResNet-101). Inside
 # ``defer_counters()`` the fused ops only collect the counters; the caller bumps them all with one multi-tensor add.
@@ -97,6 +103,8 @@ class _BNAct(torch.autograd.Function):
                                        ws.data_ptr(), m, c, eps, momentum, int(relu), stream)
         if rc != 0:
             raise RuntimeError(f"b200mpi_bn_act_fwd failed ({rc})")
+        global _LAUNCHES
+        _LAUNCHES += 3
         ctx.save_for_backward(x, mask, weight, save_mean, save_invstd, ws)
         ctx.relu, ctx.has_res = relu, residual is not None
         ctx.direct, ctx.wb = direct, (weight, bias)
@@ -126,6 +134,8 @@ class _BNAct(torch.autograd.Function):
                                        m, c, int(ctx.relu), stream)
         if rc != 0:
             raise RuntimeError(f"b200mpi_bn_act_bwd failed ({rc})")
+        global _LAUNCHES
+        _LAUNCHES += 3
         if direct:
             ctx.direct(ctx.wb[0])
             ctx.direct(ctx.wb[1])
@@ -186,6 +196,8 @@ class _Conv1x1BNAct(torch.autograd.Function):
                                                 parts, m, cout, eps, momentum, int(relu), stream)
         if rc != 0:
             raise RuntimeError(f"b200mpi_bn_act_fwd_prestats failed ({rc})")
+        global _LAUNCHES
+        _LAUNCHES += 3   # GEMM+stats, finalize, apply
         ctx.save_for_backward(x2d, w2d, yconv, mask, weight, save_mean, save_invstd, ws)
         ctx.relu, ctx.has_res, ctx.shape = relu, residual is not None, (n, cin, cout, h, w)
         ctx.direct, ctx.wb = direct, (weight, bias)
@@ -213,6 +225,8 @@ class _Conv1x1BNAct(torch.autograd.Function):
                                        m, cout, int(ctx.relu), stream)
         if rc != 0:
             raise RuntimeError(f"b200mpi_bn_act_bwd failed ({rc})")
+        global _LAUNCHES
+        _LAUNCHES += 3
         dx = (dy @ w2d).view(n, h, w, cin).permute(0, 3, 1, 2) if ctx.needs_input_grad[0] else None   # dgrad: [M,Cout] x [Cout,Cin]
         dw2d = dy.t() @ x2d if ctx.needs_input_grad[2] else None                                          # wgrad: [Cout,M] x [M,Cin]
         if direct:

@@ -28,6 +28,7 @@ from typing import Callable, List, Optional
 import torch
 import torch.nn as nn
 
+from ..ops import fused_bn
 from ..runtime.comm import Communicator, Window
 from ..utils import fault, nvtx
 
@@ -165,7 +166,9 @@ class DataParallelTrainer:
         self.device = torch.device("cuda", comm.device) if comm.device != "cpu" else torch.device("cpu")
         self._cuda = self.device.type == "cuda"
         if bf16_params is None:
-            bf16_params = os.environ.get("B200MPI_BF16_PARAMS", "0") == "1"
+            # default on: ran on B200 in rounds 1 (driver XPASS) and 2 (profiles/r2: 15.34 -> 15.00 ms/step, 1 GPU)
+            # (CUDA only: the CPU debug path keeps fp32 leaves unless asked)
+            bf16_params = os.environ.get("B200MPI_BF16_PARAMS", "1" if self._cuda else "0") == "1"
         self.bf16_params = bool(bf16_params) and autocast_dtype == torch.bfloat16
         self.loss_fn = loss_fn
         self.autocast_dtype = autocast_dtype
@@ -194,8 +197,9 @@ class DataParallelTrainer:
         self._sync = True
         self._carry = False
         # B200MPI_ASYNC_H2D=1: inputs go host -> staging buffer on a copy stream (overlapping the previous step's compute),
-        # then device -> device into the graph's static input; off by default until it has run on hardware
-        self.async_h2d = os.environ.get("B200MPI_ASYNC_H2D", "0") == "1" if async_h2d is None else bool(async_h2d)
+        # then device -> device into the graph's static input. Default on (profiles/r2: 15.34 -> 15.10 ms/step on 1 GPU;
+        # at 8 GPUs the compute-stream copy was the suspected scaling limiter)
+        self.async_h2d = os.environ.get("B200MPI_ASYNC_H2D", "1") == "1" if async_h2d is None else bool(async_h2d)
         self._copy_stream = torch.cuda.Stream(device=self.device) if (self.async_h2d and self._cuda) else None
         self._stage_x = self._stage_y = None
         self._pending_batch = None
@@ -323,7 +327,6 @@ class DataParallelTrainer:
         for b in st.buckets:
             b.pending = len(b.params)
         import contextlib
-        from ..ops import fused_bn
         with (fused_bn.defer_counters() if self._defer_nbt else contextlib.nullcontext()) as counters, nvtx.range("b200mpi.forward"):
             if self.autocast_dtype is not None:
                 with torch.autocast(self.device.type, dtype=self.autocast_dtype):
@@ -415,9 +418,9 @@ class DataParallelTrainer:
             self.prefetch(x, y)
         self._consume_batch()
         if not self.use_graph or not self._cuda or not self._sync or self._carry:
-            n0 = self.comm.launch_count
+            n0 = self.comm.launch_count + fused_bn.launch_count()
             self._fwd_bwd(self._static_x, self._static_y)
-            self._launches_per_step = self.comm.launch_count - n0
+            self._launches_per_step = self.comm.launch_count + fused_bn.launch_count() - n0
             return self._loss
         if self._graph is None:
             self._capture()
@@ -437,11 +440,11 @@ class DataParallelTrainer:
         if self.comm.world > 1:
             self.comm.host_barrier()
         g = torch.cuda.CUDAGraph()
-        n0 = self.comm.launch_count
+        n0 = self.comm.launch_count + fused_bn.launch_count()
         before = {(o["op"], o["algo"]): o for o in self.comm.stats(native_only=True)["ops"]} if hasattr(self.comm, "stats") else {}
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._fwd_bwd(self._static_x, self._static_y)
-        self._launches_per_step = self.comm.launch_count - n0
+        self._launches_per_step = self.comm.launch_count + fused_bn.launch_count() - n0   # our kernels in one replay
         if hasattr(self.comm, "stats"):
             self._folded_ops = self._replayed_ops()
             self._graph_ops, self._replays = [], 0

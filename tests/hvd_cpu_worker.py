@@ -80,6 +80,51 @@ for step in range(3):
 for p, q in zip(model.parameters(), ref.parameters()):
     assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), (p - q).abs().max()
 
+# backward_passes_per_step=2, Horovod usage: 2 x backward(), ONE step(); also survives model.zero_grad() (set_to_none=True)
+torch.manual_seed(0)
+model2 = nn.Sequential(nn.Linear(6, 8), nn.Tanh(), nn.Linear(8, 3))
+ref2 = nn.Sequential(nn.Linear(6, 8), nn.Tanh(), nn.Linear(8, 3))
+ref2.load_state_dict(model2.state_dict())
+opt2 = hvd.DistributedOptimizer(torch.optim.SGD(model2.parameters(), lr=0.1, momentum=0.9), named_parameters=model2.named_parameters(),
+                                backward_passes_per_step=2, bucket_bytes=128)
+assert type(opt2).__name__ == "_DistributedOptimizer"
+ropt2 = torch.optim.SGD(ref2.parameters(), lr=0.1, momentum=0.9)
+for step in range(3):
+    if step == 1:
+        model2.zero_grad()            # drops .grad (set_to_none=True): the optimizer must re-home the fresh gradients
+    else:
+        opt2.zero_grad()
+    ropt2.zero_grad()
+    for micro in range(2):
+        xs = [torch.randn(4, 6, generator=torch.Generator().manual_seed(5000 + 100 * step + 10 * micro + k)) for k in range(n)]
+        model2(xs[r]).pow(2).mean().backward()
+        (sum(ref2(x).pow(2).mean() for x in xs) / n / 2).backward()      # mean over ranks and over the two local passes
+    opt2.step()
+    ropt2.step()
+for p, q in zip(model2.parameters(), ref2.parameters()):
+    assert torch.allclose(p, q, rtol=1e-5, atol=1e-6), ("passes=2", (p - q).abs().max())
+if os.environ.get("B200MPI_HVD_ENGINE") == "0":   # no engine to fall back to: an unsupported argument must be refused loudly
+    try:
+        hvd.DistributedOptimizer(torch.optim.SGD(nn.Linear(2, 2).parameters(), lr=0.1), compression=hvd.Compression.fp16)
+        raise SystemExit("bucket optimizer accepted a compression it cannot apply")
+    except ValueError:
+        pass
+
+# broadcast_object beyond 16 MiB (a float32 length is only exact below 2^24) and optimizer state as tensors
+big = bytes(range(256)) * ((17 << 20) // 256) + b"tail!"
+got_big = hvd.broadcast_object(big if r == 0 else None, root_rank=0)
+assert len(got_big) == (17 << 20) + 5 and got_big[-5:] == b"tail!" and got_big[:256] == bytes(range(256))
+mom_model = nn.Linear(5, 4)
+hvd.broadcast_parameters(mom_model.state_dict(), root_rank=0)
+mom_opt = torch.optim.SGD(mom_model.parameters(), lr=0.1 * (r + 1), momentum=0.9)
+if r == 0:
+    mom_model(torch.ones(2, 5)).sum().backward()
+    mom_opt.step()
+hvd.broadcast_optimizer_state(mom_opt, root_rank=0)
+assert mom_opt.param_groups[0]["lr"] == 0.1 and len(mom_opt.state_dict()["state"]) == 2
+mb = hvd.allgather(mom_opt.state_dict()["state"][0]["momentum_buffer"].flatten()[None])
+assert all(torch.equal(mb[0], mb[k]) for k in range(n)) and mb[0].abs().sum() > 0
+
 # SyncBatchNorm == nn.BatchNorm2d over the concatenated global batch (outputs, input gradients, affine gradients, running stats)
 torch.manual_seed(5)
 full = torch.randn(4 * n, 3, 5, 5, dtype=torch.float64)
@@ -135,5 +180,32 @@ state.commit()
 state.epoch = 9
 state.restore()
 assert state.epoch == 5
+# commit snapshots by VALUE: in-place changes after the commit are rolled back (objects, model, optimizer momentum)
+em = nn.Linear(3, 2)
+eo = torch.optim.SGD(em.parameters(), lr=0.1, momentum=0.9)
+em(torch.ones(1, 3)).sum().backward()
+eo.step()
+hist = [1, 2]
+samp3 = hvd.elastic.ElasticSampler(list(range(8 * n)), shuffle=False)
+st2 = hvd.elastic.TorchState(model=em, optimizer=eo, hist=hist, sampler=samp3)
+st2.commit()
+w_commit = em.weight.detach().clone()
+m_commit = eo.state_dict()["state"][0]["momentum_buffer"].clone()
+hist.append(3)
+em(torch.ones(1, 3)).sum().backward()
+eo.step()
+samp3.record_batch(0, 2)
+assert not torch.equal(em.weight, w_commit)
+st2.restore()
+assert st2.hist == [1, 2] and torch.equal(em.weight, w_commit)
+assert torch.equal(eo.state_dict()["state"][0]["momentum_buffer"], m_commit)
+assert st2.sampler is samp3 and not samp3.processed_indices          # same object, rolled back through load_state_dict
+# sync() unites the processed indices of all ranks and keeps every rank on its own shard
+samp3.record_batch(0, 2)
+mine_done = set(samp3.processed_indices)
+st2.sync()
+assert st2.sampler is samp3 and samp3.rank == r and samp3.num_replicas == n
+assert mine_done <= samp3.processed_indices and len(samp3.processed_indices) == 2 * n
+assert not (set(samp3.indices) & samp3.processed_indices)
 print(f"rank {r}/{n} hvd cpu ok", flush=True)
 hvd.shutdown()

@@ -4,6 +4,7 @@ import json
 import os
 import socket
 import time
+import urllib.error
 import urllib.request
 
 import pytest
@@ -109,6 +110,35 @@ def test_rest_api_end_to_end_with_sdk_client(tmp_path):
         assert cli.list() == [] and cli.list_resource("jobs") == []  # owner-reference GC
         with pytest.raises(mpijob.exceptions.NotFoundException):
             cli.get("rest")
+    finally:
+        op.stop()
+
+
+def test_monitoring_port_serves_metrics_and_healthz_only(tmp_path):
+    """The reference serves nothing but /metrics on --monitoring-port (cmd/mpi-operator/main.go:29-40). Here that port
+    binds 0.0.0.0, so it must not expose the object API (a POSTed Pod is a command the node agent runs; Secrets hold keys)."""
+    port, mon = _free_port(), _free_port()
+    op = Operator(ServerOption(fake_gpus=0, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    op.serve(f"127.0.0.1:{mon}", restricted=True)
+    op.start()
+    try:
+        base = f"http://127.0.0.1:{mon}"
+        assert "mpi_operator_jobs_created_total" in urllib.request.urlopen(base + "/metrics").read().decode()
+        assert urllib.request.urlopen(base + "/healthz").read() == b"ok"
+        for path in ("/api/v1/secrets", "/api/v1/namespaces/default/pods", "/apis/kubeflow.org/v2beta1/mpijobs", "/version", "/topology"):
+            with pytest.raises(urllib.error.HTTPError) as e:
+                urllib.request.urlopen(base + path)
+            assert e.value.code == 404
+        pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "evil"}, "spec": {"containers": [{"name": "c", "command": ["true"]}]}}
+        for method in ("POST", "PUT", "PATCH", "DELETE"):
+            req = urllib.request.Request(base + "/api/v1/namespaces/default/pods", data=json.dumps(pod).encode(), method=method,
+                                         headers={"Content-Type": "application/json"})
+            with pytest.raises(urllib.error.HTTPError) as e:
+                urllib.request.urlopen(req)
+            assert e.value.code == 405
+        # the full API is still there on the loopback listener
+        assert json.load(urllib.request.urlopen(f"http://127.0.0.1:{port}/api/v1/namespaces/default/pods"))["items"] == []
     finally:
         op.stop()
 

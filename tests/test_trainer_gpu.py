@@ -49,8 +49,6 @@ def test_trainer_matches_torch_sgd(graph):
     comm.destroy()
 
 
-@pytest.mark.xfail(strict=False, reason="bf16 parameter shadow (B200MPI_BF16_PARAMS=1, off by default): host logic is verified on CPU "
-                                        "in test_trainer_cpu.py; the GPU budget of the round ended before this path ran on hardware")
 @pytest.mark.parametrize("graph", [False, True])
 def test_bf16_params_trainer_tracks_the_fp32_master_trainer(graph):
     """Same model, same batches: the bf16-shadow trainer (bf16 leaves, fp32 masters in the window, shadow written by
@@ -78,8 +76,6 @@ def test_bf16_params_trainer_tracks_the_fp32_master_trainer(graph):
     comm.destroy()
 
 
-@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent; the native counters are checked on the host by "
-                                        "`make test_comm_host`, the trainer-side accounting by test_trainer_cpu.py")
 def test_collective_counters_cover_eager_launches_and_graph_replays():
     """Communicator.stats(): host launches counted natively, CUDA-graph replays added by the trainer (what the node
     agent exports as b200mpi_collective_*_total)."""
@@ -102,8 +98,6 @@ def test_collective_counters_cover_eager_launches_and_graph_replays():
     comm.destroy()
 
 
-@pytest.mark.xfail(strict=False, reason="async input pipeline (B200MPI_ASYNC_H2D=1, off by default) was written after the round's GPU budget "
-                                        "was spent; API semantics are covered on CPU in test_trainer_cpu.py")
 @pytest.mark.parametrize("graph", [False, True])
 def test_async_h2d_pipeline_trains_on_the_same_batches(graph):
     """Copy-stream H2D into double-buffered staging + D2D into the graph's static input must feed exactly the batches the
