@@ -125,7 +125,7 @@ def test_allreduce_window(comm, dtype, algo):
 
 
 def test_back_to_back_stress(comm):
-    """10^3 back-to-back small allreduces of random sizes must stay bit-exact
+    """300 back-to-back small allreduces of random sizes must stay bit-exact
     (flag/epoch reuse, one-shot slot double-buffering)."""
     g = torch.Generator().manual_seed(1)
     sizes = torch.randint(1, 5000, (300,), generator=g).tolist()
