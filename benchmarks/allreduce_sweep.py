@@ -91,14 +91,16 @@ def main():
                 algos["twoshot"] = lambda: comm.allreduce_window(win, 0, n, dtype, op="avg", algo="twoshot")
                 if comm.has_multicast:
                     algos["nvls"] = lambda: comm.allreduce_window(win, 0, n, dtype, op="avg", algo="nvls")
-                def staged(pipe):
-                    def run():  # user pointers: old chunked staged kernel vs the pipelined kernel (auto = NVLS when bound)
+                def user(pipe, reg):
+                    def run():  # user pointers: chunked staged kernel / pipelined kernel / cudaIpc-registered zero-copy two-shot
                         comm.set_pipe(min_bytes=0 if pipe else (1 << 62))
+                        comm.set_reg(2 if reg else 0, 0)
                         comm.allreduce(t, t, op="avg", algo="auto" if size > (1 << 20) else "twoshot")
                     return run
-                algos["staged"] = staged(False)
+                algos["staged"] = user(False, False)
                 if size >= (256 << 10):
-                    algos["pipe"] = staged(True)
+                    algos["pipe"] = user(True, False)
+                    algos["reg"] = user(False, True)
             if use_nccl:
                 algos["nccl"] = lambda: dist.all_reduce(t, op=dist.ReduceOp.AVG)
             if a.tune_blocks and size >= (16 << 20):

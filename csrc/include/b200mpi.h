@@ -207,10 +207,29 @@ int b200mpi_set_tuning(b200mpi_comm_t comm, size_t oneshot_max_bytes, size_t nvl
 int b200mpi_get_tuning(b200mpi_comm_t comm, size_t* oneshot_max_bytes, size_t* nvls_min_bytes,
                        int* max_blocks, int* timeout_ms);
 /* which algorithm would AUTO pick */
+/*
+ * Zero-copy collectives on a symmetric window region (no staging, no copy-out). The region starts at `offset`
+ * (16-byte aligned) and is `world` slices of `slice_bytes` (a multiple of 16); slice r belongs to rank r.
+ *   allgather_sym       : every rank's slice r of its OWN copy ends up in slice r of every copy (multimem.st on NVLS)
+ *   reduce_scatter_sym  : slice r of every copy is reduced (x scale) into rank r's `out` (slice-sized device pointer,
+ *                         16-byte aligned) or, with out == NULL, in place into slice r of rank r's own copy
+ *                         (multimem.ld_reduce on NVLS). Emulated mode: `out` is an array of world pointers.
+ *   broadcast_sym       : the root's [offset, offset+bytes) replaces the same region of every copy
+ */
+int b200mpi_allgather_sym(b200mpi_comm_t comm, int win, size_t offset, size_t slice_bytes, void* stream);
+int b200mpi_reduce_scatter_sym(b200mpi_comm_t comm, int win, size_t offset, size_t slice_count, b200mpi_dtype_t dtype,
+                               b200mpi_op_t op, float scale, void* out, void* stream);
+int b200mpi_broadcast_sym(b200mpi_comm_t comm, int win, size_t offset, size_t bytes, int root, void* stream);
+
 /* Pipelined user-pointer allreduce (k_allreduce_pipe): messages of at least `min_bytes` (SIZE_MAX: keep) run as one
  * kernel of `lanes` x {copy-in, reduce, copy-out} CTAs with `depth` staging slots of `chunk_bytes` per lane.
  * Non-positive values keep the current setting. Env: B200MPI_PIPE_{MIN_BYTES,LANES_NVLS,LANES_P2P,DEPTH,CHUNK_BYTES}. */
 int b200mpi_set_pipe(b200mpi_comm_t comm, size_t min_bytes, int lanes_nvls, int lanes_p2p, int depth, size_t chunk_bytes);
+/* Lazy registration of user buffers (cudaIpc) for the user-pointer collectives: mode 0 = never, 1 = where the zero-copy
+ * P2P kernels win (default: world 2, paths without NVLS, allgather), 2 = whenever the buffers can be exported; calls below
+ * `min_bytes` (SIZE_MAX: keep) always take the staged kernels. Env: B200MPI_REG, B200MPI_REG_MIN_BYTES. */
+int b200mpi_set_reg(b200mpi_comm_t comm, int mode, size_t min_bytes);
+int b200mpi_reg_stats(b200mpi_comm_t comm, uint64_t* zero_copy_calls, uint64_t* handles_opened, uint64_t* refused);
 int b200mpi_select_algo(b200mpi_comm_t comm, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op,
                         int symmetric);
 

@@ -110,8 +110,13 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
       }
     } else {
       char* pp[kMaxRanks];
+      char* po[kMaxRanks];   // where the result goes: the same region, or a second one (registered out-of-place user buffers)
 #pragma unroll
-      for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
+      for (int k = 0; k < kMaxRanks; k++) {
+        const int r = wrap(rank + (k < world ? k : 0), world);
+        pp[k] = a.buf.p[r] + base * 16;
+        po[k] = (a.param.p[0] ? a.param.p[r] : a.buf.p[r]) + base * 16;
+      }
       for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
         uint4 v[U][kMaxRanks];
 #pragma unroll
@@ -136,7 +141,7 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
             const uint4 o = VecTraits<T>::pack(acc);
 #pragma unroll
             for (int k = 0; k < kMaxRanks; k++)
-              if (k < world) st_peer_v4(pp[k] + i * 16, o);
+              if (k < world) st_peer_v4(po[k] + i * 16, o);
           }
         }
       }
@@ -167,33 +172,140 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
 }
 
 // ===========================================================================
-// Pipelined staged allreduce for arbitrary user pointers (the path the NCCL-ABI
+// Pipelined staged collectives for arbitrary user pointers (the path the NCCL-ABI
 // shim and hvd take for tensors that do not live in a symmetric window).
-// The message is cut into chunks; lane l owns chunks l, l+L, l+2L ... and is a
-// chain of THREE CTAs that run concurrently and hand chunks on through flags:
-//   role 0 (copy-in)  user input -> staging slot            -> IN flag to all ranks
-//   role 1 (reduce)   wait IN of all ranks; slice `rank` of the chunk is reduced
-//                     (multimem.ld_reduce, or pull from every peer) and the result
-//                     written to every rank's slot (multimem.st / peer stores)
-//                                                            -> RED flag to all ranks
-//   role 2 (copy-out) wait RED of all ranks; staging slot -> user output
-//                                                            -> local counter (frees the slot)
-// so while chunk k is on NVLink, chunk k+1 is being copied in and chunk k-1 copied
-// out: the local HBM copies that serialised the old staged kernel (three phases, two
-// full barriers, 370 GB/s at 8 GPUs) disappear behind the link time. A slot is
-// reused for chunk k+depth only after the local copy-out of chunk k, which itself
-// waited for every rank's RED flag, i.e. for every peer's last access to the slot.
-// Flags only grow (per-role, per-lane counters persist in the epoch array), so the
-// kernel is CUDA-graph capturable like the others.
+// The payload is cut into chunks; lane l owns chunks l, l+L, l+2L ... and is a
+// chain of up to THREE CTAs that run concurrently and hand chunks on through flags:
+//
+//   ALLREDUCE       role 0  user input -> staging slot                          -> IN  (all ranks)
+//                   role 1  wait IN; slice `rank` of the chunk: multimem.ld_reduce (or pull from every peer),
+//                           scale, multimem.st (or peer stores) into every rank's slot -> RED (all ranks)
+//                   role 2  wait RED; staging slot -> user output                -> local counter (frees the slot)
+//   ALLGATHER       role 0  user input chunk -> region `rank` of EVERY rank's slot (multimem.st / peer stores),
+//                           own block of the output written directly            -> IN  (all ranks)
+//                   role 2  wait IN; regions of the other ranks -> user output   -> RED (all ranks: slot may be refilled)
+//   REDUCE_SCATTER  role 0  all `world` blocks of the user input chunk -> own slot -> IN (all ranks)
+//                   role 1  wait IN; region `rank`: ld_reduce / pull, scale -> user output -> RED (all ranks)
+//   BROADCAST       role 0  (root) user buffer chunk -> every rank's slot        -> IN  (all ranks; non-roots signal at once)
+//                   role 2  wait IN; (non-root) slot -> user buffer              -> RED (all ranks)
+//
+// so while chunk k is on NVLink, chunk k+1 is being copied in and chunk k-1 copied out: the local HBM copies that
+// serialised the old staged kernels (three phases, two full barriers: 370 GB/s at 8 GPUs for allreduce) disappear behind
+// the link time. A slot is refilled for chunk k+depth only after every rank that reads or writes it for chunk k has
+// said so (local counter for allreduce, RED flags otherwise). Flags only grow (per-role, per-lane counters persist in
+// the epoch array and advance identically for all three roles), so the kernel is CUDA-graph capturable like the others.
 // ===========================================================================
-template <typename T, int MODE>
+// copy `len` vectors user -> staging (plain stores into local HBM), 8 loads in flight per thread
+__device__ __forceinline__ void pipe_copy_in(char* dst, const char* ubase, size_t uvec0, size_t unbytes, bool ualigned, size_t len) {
+  constexpr int U = 8;
+  for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < len) v[u] = user_load(ubase, uvec0 + i, unbytes, ualigned);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < len) *reinterpret_cast<uint4*>(dst + i * 16) = v[u];
+    }
+  }
+}
+__device__ __forceinline__ void pipe_copy_out(char* ubase, size_t uvec0, size_t unbytes, bool ualigned, const char* src, size_t len) {
+  constexpr int U = 8;
+  for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < len) v[u] = ld_sys_v4(src + i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < len) user_store(ubase, uvec0 + i, unbytes, ualigned, v[u]);
+    }
+  }
+}
+
+// reduce `lim` vectors that every rank holds at byte offset `off` of its staging region; RESULT: `emit(i, vec)`
+// NR = compile-time bound on the world size of the P2P variant: with 2 ranks eight vectors per thread are kept in
+// flight (a peer load is ~3 us away; the link needs ~2 MB outstanding per direction), with up to 8 ranks two.
+template <typename T, int MODE, int NR, typename Emit>
+__device__ __forceinline__ void pipe_reduce(const KArgs& a, size_t off, size_t lim, Emit&& emit) {
+  const int rank = a.c.rank, world = a.c.world;
+  const bool do_scale = a.scale != 1.0f;
+  if (MODE == MODE_NVLS) {
+    constexpr int U = 4;
+    const char* const mc = a.buf.mc + off;
+    for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) v[u] = nvls_ld_reduce<T>(mc + i * 16, a.op);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) emit(i, do_scale ? scale_vec<T>(v[u], a.scale) : v[u]);
+      }
+    }
+  } else {
+    constexpr int U = NR <= 2 ? 8 : 2;
+    const char* pp[NR];
+#pragma unroll
+    for (int k = 0; k < NR; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + off;
+    for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
+      uint4 v[U][NR];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+#pragma unroll
+        for (int k = 0; k < NR; k++)
+          if (k < world && i < lim) v[u][k] = ld_sys_v4(pp[k] + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) {
+          float acc[VecTraits<T>::N];
+#pragma unroll
+          for (int k = 0; k < NR; k++)
+            if (k < world) accum<T>(acc, v[u][k], a.op, k == 0);
+          if (do_scale) {
+#pragma unroll
+            for (int q = 0; q < VecTraits<T>::N; q++) acc[q] *= a.scale;
+          }
+          emit(i, VecTraits<T>::pack(acc));
+        }
+      }
+    }
+  }
+}
+
+// store to the same staging byte offset on every rank (one multimem.st, or `world` peer stores)
+template <int MODE, int NR>
+__device__ __forceinline__ void pipe_store_all(const KArgs& a, size_t off, const uint4& v) {
+  if (MODE == MODE_NVLS) {
+    multimem_st_v4(a.buf.mc + off, v);
+  } else {
+    const int rank = a.c.rank, world = a.c.world;
+#pragma unroll
+    for (int k = 0; k < NR; k++)
+      if (k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + off, v);
+  }
+}
+
+template <typename T, int MODE, int OP, int NR>
 __global__ void __launch_bounds__(kThreads)
-k_allreduce_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
   EMU_ARGS;
   const int rank = a.c.rank, world = a.c.world;
   const int L = a.lanes, D = a.depth;
   const int role = blockIdx.x / L, lane = blockIdx.x - role * L;
-  const size_t Cv = a.per;
+  const size_t Cv = a.per;                                     // vectors per chunk (of the per-rank payload)
   const size_t nchunks = (a.nvec + Cv - 1) / Cv;
   const uint32_t n_mine = nchunks > (size_t)lane ? (uint32_t)((nchunks - lane + L - 1) / L) : 0u;
   uint32_t* const ctr = a.c.epoch + kPipeEpochOff + (size_t)role * kPipeLanes + lane;
@@ -201,106 +313,99 @@ k_allreduce_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu
   const uint32_t base = *ctr;
   const size_t row_in = kPipeSigOff + (size_t)lane * kMaxRanks;
   const size_t row_red = kPipeSigOff + ((size_t)kPipeLanes + lane) * kMaxRanks;
+  const size_t row_done = kPipeSigOff + (2 * (size_t)kPipeLanes + lane) * kMaxRanks;
   char* const mine = a.buf.p[rank];
-  const bool do_scale = a.scale != 1.0f;
+  constexpr bool kWide = OP == PIPE_ALLGATHER || OP == PIPE_REDUCE_SCATTER;   // slot = world regions of Cv vectors
+  const size_t slot_vecs = kWide ? Cv * world : Cv;
+  constexpr bool kUsesRole1 = OP == PIPE_ALLREDUCE || OP == PIPE_REDUCE_SCATTER;
+  constexpr bool kUsesRole2 = OP != PIPE_REDUCE_SCATTER;
+  const bool idle = (role == 1 && !kUsesRole1) || (role == 2 && !kUsesRole2);
+  const int last_role = kUsesRole2 ? 2 : 1;   // the role whose completion means: no rank touches this lane's slots any more
+  // Ops whose FIRST action is a store into the peers' staging (allgather, broadcast) must know that every peer has left its
+  // previous kernel: the barrier-based staged allreduce ends with a local copy-out from staging after its last barrier.
+  // Entering this launch is that proof (stream order), so role 0 trades one ENTRY flag with everyone before it pushes.
+  if ((OP == PIPE_ALLGATHER || OP == PIPE_BROADCAST) && role == 0 && n_mine > 0) {
+    const size_t row_entry = kPipeSigOff + (3 * (size_t)kPipeLanes + lane) * kMaxRanks;
+    flag_signal_all(a.c, row_entry, base + 1);
+    flag_wait_all(a.c, row_entry, base + 1);
+  }
 
-  for (uint32_t j = 0; j < n_mine; j++) {
-    const size_t v0 = ((size_t)lane + (size_t)j * L) * Cv;           // first vector of the chunk in the message
-    const size_t len = a.nvec - v0 < Cv ? a.nvec - v0 : Cv;          // vectors in this chunk
-    const size_t slot = ((size_t)lane * D + (j % D)) * Cv;           // vector offset of the staging slot
+  for (uint32_t j = 0; j < n_mine && !idle; j++) {
+    const size_t v0 = ((size_t)lane + (size_t)j * L) * Cv;            // first vector of the chunk in the payload
+    const size_t len = a.nvec - v0 < Cv ? a.nvec - v0 : Cv;           // vectors in this chunk
+    const size_t slot = ((size_t)lane * D + (j % D)) * slot_vecs;     // vector offset of the staging slot
     const uint32_t tgt = base + j + 1;
     if (role == 0) {
-      if (j >= (uint32_t)D) local_wait(a.c, out_done, tgt - D);
-      constexpr int U = 8;
-      for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
-        uint4 v[U];
+      if (j >= (uint32_t)D) {
+        if (OP == PIPE_ALLREDUCE) local_wait(a.c, out_done, tgt - D);
+        else flag_wait_all(a.c, row_red, tgt - D);
+      }
+      if (OP == PIPE_ALLREDUCE) {
+        pipe_copy_in(mine + slot * 16, a.in, v0, a.nbytes, a.in_aligned, len);
+      } else if (OP == PIPE_REDUCE_SCATTER) {
+        for (int r = 0; r < world; r++)
+          pipe_copy_in(mine + (slot + (size_t)r * Cv) * 16, a.in + (size_t)r * a.ustride, v0, a.nbytes, a.in_aligned, len);
+      } else if (OP == PIPE_ALLGATHER || (OP == PIPE_BROADCAST && rank == a.root)) {
+        // push: user chunk -> the same staging offset on every rank; allgather also writes its own output block directly
+        const size_t dst = (slot + (OP == PIPE_ALLGATHER ? (size_t)rank * Cv : 0)) * 16;
+        constexpr int U = 4;
+        for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+          uint4 v[U];
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const size_t i = i0 + (size_t)u * blockDim.x;
-          if (i < len) v[u] = user_load(a.in, v0 + i, a.nbytes, a.in_aligned);
-        }
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+            if (i < len) v[u] = user_load(a.in, v0 + i, a.nbytes, a.in_aligned);
+          }
 #pragma unroll
-        for (int u = 0; u < U; u++) {
-          const size_t i = i0 + (size_t)u * blockDim.x;
-          if (i < len) *reinterpret_cast<uint4*>(mine + (slot + i) * 16) = v[u];
+          for (int u = 0; u < U; u++) {
+            const size_t i = i0 + (size_t)u * blockDim.x;
+            if (i < len) {
+              pipe_store_all<MODE, NR>(a, dst + i * 16, v[u]);
+              if (OP == PIPE_ALLGATHER) user_store(a.out + (size_t)rank * a.ustride, v0 + i, a.nbytes, a.out_aligned, v[u]);
+            }
+          }
         }
       }
       flag_signal_all(a.c, row_in, tgt);
     } else if (role == 1) {
       flag_wait_all(a.c, row_in, tgt);
-      const size_t per = (len + world - 1) / world;
-      const size_t sb = (size_t)rank * per;
-      const size_t lim = sb < len ? (len - sb < per ? len - sb : per) : 0;
-      if (MODE == MODE_NVLS) {
-        constexpr int U = 4;
-        char* const mc = a.buf.mc + (slot + sb) * 16;
-        for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
-          uint4 v[U];
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const size_t i = i0 + (size_t)u * blockDim.x;
-            if (i < lim) v[u] = nvls_ld_reduce<T>(mc + i * 16, a.op);
-          }
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const size_t i = i0 + (size_t)u * blockDim.x;
-            if (i < lim) multimem_st_v4(mc + i * 16, do_scale ? scale_vec<T>(v[u], a.scale) : v[u]);
-          }
-        }
-      } else {
-        constexpr int U = 2;
-        char* pp[kMaxRanks];
-#pragma unroll
-        for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + (slot + sb) * 16;
-        for (size_t i0 = threadIdx.x; i0 < lim; i0 += (size_t)blockDim.x * U) {
-          uint4 v[U][kMaxRanks];
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const size_t i = i0 + (size_t)u * blockDim.x;
-#pragma unroll
-            for (int k = 0; k < kMaxRanks; k++)
-              if (k < world && i < lim) v[u][k] = ld_sys_v4(pp[k] + i * 16);
-          }
-#pragma unroll
-          for (int u = 0; u < U; u++) {
-            const size_t i = i0 + (size_t)u * blockDim.x;
-            if (i < lim) {
-              float acc[VecTraits<T>::N];
-#pragma unroll
-              for (int k = 0; k < kMaxRanks; k++)
-                if (k < world) accum<T>(acc, v[u][k], a.op, k == 0);
-              if (do_scale) {
-#pragma unroll
-                for (int q = 0; q < VecTraits<T>::N; q++) acc[q] *= a.scale;
-              }
-              const uint4 o = VecTraits<T>::pack(acc);
-#pragma unroll
-              for (int k = 0; k < kMaxRanks; k++)
-                if (k < world) st_peer_v4(pp[k] + i * 16, o);
-            }
-          }
-        }
+      if (OP == PIPE_ALLREDUCE) {
+        const size_t per = (len + world - 1) / world;
+        const size_t sb = (size_t)rank * per;
+        const size_t lim = sb < len ? (len - sb < per ? len - sb : per) : 0;
+        const size_t off = (slot + sb) * 16;
+        pipe_reduce<T, MODE, NR>(a, off, lim, [&](size_t i, const uint4& o) { pipe_store_all<MODE, NR>(a, off + i * 16, o); });
+      } else {   // REDUCE_SCATTER: region `rank` of every rank's slot -> my output
+        const size_t off = (slot + (size_t)rank * Cv) * 16;
+        pipe_reduce<T, MODE, NR>(a, off, len, [&](size_t i, const uint4& o) { user_store(a.out, v0 + i, a.nbytes, a.out_aligned, o); });
       }
       flag_signal_all(a.c, row_red, tgt);
     } else {
-      flag_wait_all(a.c, row_red, tgt);
-      constexpr int U = 8;
-      for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
-        uint4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const size_t i = i0 + (size_t)u * blockDim.x;
-          if (i < len) v[u] = ld_sys_v4(mine + (slot + i) * 16);
+      flag_wait_all(a.c, OP == PIPE_ALLREDUCE ? row_red : row_in, tgt);
+      if (OP == PIPE_ALLREDUCE) {
+        pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
+        __syncthreads();
+        if (threadIdx.x == 0) st_release_gpu(out_done, tgt);
+      } else {
+        if (OP == PIPE_ALLGATHER) {
+          for (int k = 1; k < world; k++) {     // own block was written by role 0
+            const int r = wrap(rank + k, world);
+            pipe_copy_out(a.out + (size_t)r * a.ustride, v0, a.nbytes, a.out_aligned, mine + (slot + (size_t)r * Cv) * 16, len);
+          }
+        } else if (rank != a.root) {
+          pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
         }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const size_t i = i0 + (size_t)u * blockDim.x;
-          if (i < len) user_store(a.out, v0 + i, a.nbytes, a.out_aligned, v[u]);
-        }
+        flag_signal_all(a.c, row_red, tgt);
       }
-      __syncthreads();
-      if (threadIdx.x == 0) st_release_gpu(out_done, tgt);
     }
+  }
+  // Launch-completion handshake: a rank's kernel must not end before EVERY rank has finished with this lane's slots (peers
+  // read and write them), otherwise the next launch on this stream - any kernel that uses the staging window, with any
+  // slot geometry - could overwrite data a slower peer is still consuming. The last role tells all ranks it is done, role 0
+  // (which finished first and would otherwise idle) waits for all of them.
+  if (n_mine > 0) {
+    if (role == last_role) flag_signal_all(a.c, row_done, base + n_mine);
+    if (role == 0) flag_wait_all(a.c, row_done, base + n_mine);
   }
   if (threadIdx.x == 0) *ctr = base + n_mine;
 }
@@ -474,6 +579,151 @@ k_allreduce_sgd(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu)
             if constexpr (N == 8) st_peer_v4(dst, make_uint4(w[0], w[1], w[2], w[3]));
             else *reinterpret_cast<uint2*>(dst) = make_uint2(w[0], w[1]);
           }
+        }
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+// ===========================================================================
+// Zero-copy collectives on a symmetric window region (no staging, no copy-out):
+// the data already lives in peer-visible - and, when bound, multicast - memory.
+// The region is `world` slices of `per` vectors; slice r belongs to rank r.
+//   allgather       rank r's slice r -> slice r of every rank: ONE multimem.st per vector (the switch fans
+//                   out, S/N bytes leave each GPU) or `world` peer stores
+//   reduce_scatter  slice r of every rank -> reduced into rank r's slice r (or a user pointer):
+//                   multimem.ld_reduce (the switch adds) or pulls from every peer
+//   broadcast       the root's region -> every rank's region: multimem.st / peer stores
+// Entry barrier: every rank's input is in place and nobody still reads what is about to be overwritten;
+// exit barrier: everything has landed / everybody has read.
+// ===========================================================================
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_allgather_sym(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  rank_barrier(a.c, ++e);
+  const size_t base = (size_t)rank * a.per;
+  const size_t lim = base < a.nvec ? (a.nvec - base < a.per ? a.nvec - base : a.per) : 0;
+  // a.in: the slice comes from a separate buffer (registered user tensors) and must also land in this rank's own copy
+  const char* src = a.in ? a.in : a.buf.p[rank] + base * 16;
+  const int k0 = a.in ? 0 : 1;
+  constexpr int U = 4;
+  for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+    uint4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i < lim) v[u] = ld_stream_v4(src + i * 16);
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t i = i0 + (size_t)u * blockDim.x;
+      if (i >= lim) continue;
+      if (MODE == MODE_NVLS) {
+        multimem_st_v4(a.buf.mc + (base + i) * 16, v[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k >= k0 && k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + (base + i) * 16, v[u]);
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_reduce_scatter_sym(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  rank_barrier(a.c, ++e);
+  const size_t base = (size_t)rank * a.per;
+  const size_t lim = base < a.nvec ? (a.nvec - base < a.per ? a.nvec - base : a.per) : 0;
+  const bool do_scale = a.scale != 1.0f;
+  char* const dst = a.out ? a.out : a.buf.p[rank] + base * 16;   // user pointer (slice-sized) or in place
+  if (MODE == MODE_NVLS) {
+    constexpr int U = 4;
+    const char* mc = a.buf.mc + base * 16;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) v[u] = nvls_ld_reduce<T>(mc + i * 16, a.op);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < lim) *reinterpret_cast<uint4*>(dst + i * 16) = do_scale ? scale_vec<T>(v[u], a.scale) : v[u];
+      }
+    }
+  } else {
+    constexpr int U = 2;
+    const char* pp[kMaxRanks];
+#pragma unroll
+    for (int k = 0; k < kMaxRanks; k++) pp[k] = a.buf.p[wrap(rank + (k < world ? k : 0), world)] + base * 16;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < lim; i0 += gstride() * U) {
+      uint4 v[U][kMaxRanks];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k < world && i < lim) v[u][k] = ld_sys_v4(pp[k] + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i >= lim) continue;
+        float acc[VecTraits<T>::N];
+#pragma unroll
+        for (int k = 0; k < kMaxRanks; k++)
+          if (k < world) accum<T>(acc, v[u][k], a.op, k == 0);
+        if (do_scale) {
+#pragma unroll
+          for (int q = 0; q < VecTraits<T>::N; q++) acc[q] *= a.scale;
+        }
+        *reinterpret_cast<uint4*>(dst + i * 16) = VecTraits<T>::pack(acc);
+      }
+    }
+  }
+  rank_barrier(a.c, ++e);
+  if (threadIdx.x == 0) a.c.epoch[blockIdx.x] = e;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+k_broadcast_sym(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
+  EMU_ARGS;
+  const int rank = a.c.rank, world = a.c.world;
+  uint32_t e = a.c.epoch[blockIdx.x];
+  rank_barrier(a.c, ++e);
+  if (rank == a.root) {
+    const char* src = a.buf.p[rank];
+    constexpr int U = 4;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x * U + threadIdx.x; i0 < a.nvec; i0 += gstride() * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < a.nvec) v[u] = ld_stream_v4(src + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i >= a.nvec) continue;
+        if (MODE == MODE_NVLS) {
+          multimem_st_v4(a.buf.mc + i * 16, v[u]);
+        } else {
+#pragma unroll
+          for (int k = 1; k < kMaxRanks; k++)
+            if (k < world) st_peer_v4(a.buf.p[wrap(rank + k, world)] + i * 16, v[u]);
         }
       }
     }
@@ -663,9 +913,21 @@ cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype,
   if (staged) DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, true>, l, a))
   DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, false>, l, a))
 }
-cudaError_t launch_allreduce_pipe(const Launch& l, const KArgs& a, int dtype, int mode) {
-  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_allreduce_pipe<T, MODE_NVLS>, l, a))
-  DISPATCH_T(dtype, go(k_allreduce_pipe<T, MODE_P2P>, l, a))
+// kind: PIPE_* ; byte-wise kinds (allgather, broadcast) ignore dtype. P2P variants are specialised for world <= 2.
+template <int OP>
+static cudaError_t launch_pipe_t(const Launch& l, const KArgs& a, int dtype, int mode) {
+  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_pipe<T, MODE_NVLS, OP, kMaxRanks>, l, a))
+  if (a.c.world <= 2) DISPATCH_T(dtype, go(k_pipe<T, MODE_P2P, OP, 2>, l, a))
+  DISPATCH_T(dtype, go(k_pipe<T, MODE_P2P, OP, kMaxRanks>, l, a))
+}
+cudaError_t launch_pipe(const Launch& l, const KArgs& a, int kind, int dtype, int mode) {
+  switch (kind) {
+    case PIPE_ALLREDUCE: return launch_pipe_t<PIPE_ALLREDUCE>(l, a, dtype, mode);
+    case PIPE_REDUCE_SCATTER: return launch_pipe_t<PIPE_REDUCE_SCATTER>(l, a, dtype, mode);
+    case PIPE_ALLGATHER: return launch_pipe_t<PIPE_ALLGATHER>(l, a, DT_F32, mode);
+    case PIPE_BROADCAST: return launch_pipe_t<PIPE_BROADCAST>(l, a, DT_F32, mode);
+    default: return cudaErrorInvalidValue;
+  }
 }
 cudaError_t launch_allreduce_oneshot(const Launch& l, const KArgs& a, int dtype) {
   DISPATCH_T(dtype, go(k_allreduce_oneshot<T>, l, a))
@@ -675,6 +937,16 @@ cudaError_t launch_allreduce_sgd(const Launch& l, const KArgs& a, int dtype, int
   DISPATCH_T(dtype, go(k_allreduce_sgd<T, MODE_P2P>, l, a))
 }
 cudaError_t launch_allgather(const Launch& l, const KArgs& a) { return go(k_allgather, l, a); }
+cudaError_t launch_allgather_sym(const Launch& l, const KArgs& a, int mode) {
+  return mode == MODE_NVLS ? go(k_allgather_sym<MODE_NVLS>, l, a) : go(k_allgather_sym<MODE_P2P>, l, a);
+}
+cudaError_t launch_broadcast_sym(const Launch& l, const KArgs& a, int mode) {
+  return mode == MODE_NVLS ? go(k_broadcast_sym<MODE_NVLS>, l, a) : go(k_broadcast_sym<MODE_P2P>, l, a);
+}
+cudaError_t launch_reduce_scatter_sym(const Launch& l, const KArgs& a, int dtype, int mode) {
+  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_reduce_scatter_sym<T, MODE_NVLS>, l, a))
+  DISPATCH_T(dtype, go(k_reduce_scatter_sym<T, MODE_P2P>, l, a))
+}
 cudaError_t launch_broadcast(const Launch& l, const KArgs& a, int mode) {
   return mode == MODE_NVLS ? go(k_broadcast<MODE_NVLS>, l, a) : go(k_broadcast<MODE_P2P>, l, a);
 }

@@ -27,12 +27,12 @@ constexpr size_t kSigWords = (size_t)kMaxBlocks * kMaxRanks;
 constexpr size_t kEpochWords = 2 * (size_t)kMaxBlocks;
 // Pipelined staged allreduce (k_allreduce_pipe): kPipeLanes independent lanes, each a chain of three CTAs
 // (copy-in, reduce, copy-out) that hand chunks to each other through flags.
-//   signal pad  : [kSigWords, kSigWords + 2*kPipeLanes*kMaxRanks)  IN-ready / REDUCED flags, [kind][lane][src rank]
+//   signal pad  : [kSigWords, kSigWords + 4*kPipeLanes*kMaxRanks)  IN-ready / REDUCED / DONE / ENTRY flags, [kind][lane][src rank]
 //   epoch array : [kEpochWords, kEpochWords + 4*kPipeLanes)        chunks done so far per (role, lane), then the
 //                                                                  local copy-out counter the copy-in CTA polls
 constexpr int kPipeLanes = 48;
 constexpr size_t kPipeSigOff = kSigWords;
-constexpr size_t kPipeSigWords = 2 * (size_t)kPipeLanes * kMaxRanks;
+constexpr size_t kPipeSigWords = 4 * (size_t)kPipeLanes * kMaxRanks;
 constexpr size_t kSigWordsTotal = kSigWords + kPipeSigWords;
 constexpr size_t kPipeEpochOff = kEpochWords;
 constexpr size_t kEpochWordsTotal = kEpochWords + 4 * (size_t)kPipeLanes;

@@ -76,10 +76,14 @@ enum : int { MODE_P2P = 0, MODE_NVLS = 1 };
 
 // a = args of this rank (ignored in emulated mode where l.emu_args is used)
 cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype, int mode, bool staged);
-cudaError_t launch_allreduce_pipe(const Launch& l, const KArgs& a, int dtype, int mode);
+enum : int { PIPE_ALLREDUCE = 0, PIPE_ALLGATHER = 1, PIPE_REDUCE_SCATTER = 2, PIPE_BROADCAST = 3 };
+cudaError_t launch_pipe(const Launch& l, const KArgs& a, int kind, int dtype, int mode);
 cudaError_t launch_allreduce_oneshot(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_allreduce_sgd(const Launch& l, const KArgs& a, int dtype, int mode);
 cudaError_t launch_allgather(const Launch& l, const KArgs& a);
+cudaError_t launch_allgather_sym(const Launch& l, const KArgs& a, int mode);
+cudaError_t launch_broadcast_sym(const Launch& l, const KArgs& a, int mode);
+cudaError_t launch_reduce_scatter_sym(const Launch& l, const KArgs& a, int dtype, int mode);
 cudaError_t launch_broadcast(const Launch& l, const KArgs& a, int mode);
 cudaError_t launch_reduce_scatter(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_reduce(const Launch& l, const KArgs& a, int dtype);

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <map>
 #include <set>
 #include <string>
 #include <vector>
@@ -45,7 +46,7 @@ struct Driver {
   DRV(cuMemImportFromShareableHandle); DRV(cuMemGetAllocationGranularity);
   DRV(cuMulticastCreate); DRV(cuMulticastAddDevice); DRV(cuMulticastBindMem);
   DRV(cuMulticastUnbind); DRV(cuMulticastGetGranularity); DRV(cuDeviceGetAttribute);
-  DRV(cuGetErrorString);
+  DRV(cuGetErrorString); DRV(cuMemGetAddressRange); DRV(cuPointerGetAttribute);
 #undef DRV
 };
 static Driver& driver() {
@@ -69,7 +70,7 @@ static Driver& driver() {
     LOAD(cuMemImportFromShareableHandle); LOAD(cuMemGetAllocationGranularity);
     LOAD(cuMulticastCreate); LOAD(cuMulticastAddDevice); LOAD(cuMulticastBindMem);
     LOAD(cuMulticastUnbind); LOAD(cuMulticastGetGranularity); LOAD(cuDeviceGetAttribute);
-    LOAD(cuGetErrorString);
+    LOAD(cuGetErrorString); LOAD(cuMemGetAddressRange); LOAD(cuPointerGetAttribute);
 #undef LOAD
     d.ok = all;
   });
@@ -150,8 +151,13 @@ struct b200mpi_comm {
   int timeout_ms = 30000;
   // pipelined staged allreduce (user pointers): from pipe_min bytes up; lanes per mode (each lane = 3 CTAs)
   size_t pipe_min = (size_t)8 << 20;
-  int pipe_lanes_nvls = 16, pipe_lanes_p2p = 40, pipe_depth = 3;
+  int pipe_lanes_nvls = 16, pipe_lanes_p2p = 40, pipe_lanes_wide = 32, pipe_depth = 3;
   size_t pipe_chunk = (size_t)1 << 20;
+  // lazy registration of user buffers (cudaIpc): peer mappings by (rank, allocation id); see reg_exchange()
+  size_t reg_min = (size_t)8 << 20;
+  int reg_mode = 1;  // 0 off, 1 where it wins (P2P paths: world 2; byte-wise ops), 2 always
+  std::map<std::pair<int, unsigned long long>, char*> peer_maps;
+  uint64_t reg_hits = 0, reg_opens = 0, reg_refused = 0;
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
   std::vector<TraceRec> trace;
@@ -427,8 +433,11 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   c->pipe_min = env_size("B200MPI_PIPE_MIN_BYTES", c->pipe_min);
   c->pipe_lanes_nvls = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_NVLS", c->pipe_lanes_nvls), kPipeLanes));
   c->pipe_lanes_p2p = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_P2P", c->pipe_lanes_p2p), kPipeLanes));
+  c->pipe_lanes_wide = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_WIDE", c->pipe_lanes_wide), kPipeLanes));
   c->pipe_depth = std::max(2, std::min(env_int("B200MPI_PIPE_DEPTH", c->pipe_depth), 8));
   c->pipe_chunk = std::max((size_t)16 << 10, env_size("B200MPI_PIPE_CHUNK_BYTES", c->pipe_chunk));
+  c->reg_min = env_size("B200MPI_REG_MIN_BYTES", c->reg_min);
+  c->reg_mode = env_int("B200MPI_REG", c->reg_mode);
   if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", (size_t)64 << 20);
   // one-shot region: 2 parities x kOneshotBlocks CTAs x kMaxRanks slots x cap
   c->oneshot_cap_vecs = 2048;  // 32 KiB per slot -> 1 MiB max one-shot payload
@@ -497,6 +506,135 @@ static std::vector<int> my_ranks(b200mpi_comm* c) {
   return v;
 }
 
+// ------------------------------------------------ lazy user-buffer registration ----
+// Arbitrary device pointers (torch's caching-allocator blocks under the NCCL-ABI shim) become peer-addressable through
+// cudaIpc: the allocation that contains the pointer is found with cuMemGetAddressRange, identified by its
+// CU_POINTER_ATTRIBUTE_BUFFER_ID (a freed-and-reused address gets a new id), exported once, and opened once per peer.
+// Whether a call can go zero-copy must be decided IDENTICALLY on every rank, so every eligible call (size >= reg_min:
+// the same test everywhere) trades one 168-byte record per rank through the shm rendezvous (two host barriers, a few
+// microseconds against >= 8 MiB of payload); if any rank cannot export (VMM/expandable segments, cudaMallocAsync pools,
+// unaligned tensors) all ranks take the staged path together. In a CUDA-graph capture the exchange happens once at
+// capture time and the mapped pointers are baked into the graph, like NCCL's graph registration.
+struct LocalSeg { unsigned long long id; CUdeviceptr base; size_t size; cudaIpcMemHandle_t h; bool ok; };
+static std::mutex g_seg_mu;
+static std::map<unsigned long long, LocalSeg> g_segs;   // process-wide: by allocation id
+
+static bool local_seg(const void* p, size_t bytes, LocalSeg* out, size_t* off) {
+  Driver& d = driver();
+  if (!d.cuMemGetAddressRange_ || !d.cuPointerGetAttribute_ || !p) return false;
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  unsigned long long id = 0;
+  if (d.cuMemGetAddressRange_(&base, &size, (CUdeviceptr)p) != CUDA_SUCCESS) return false;
+  if (d.cuPointerGetAttribute_(&id, CU_POINTER_ATTRIBUTE_BUFFER_ID, (CUdeviceptr)p) != CUDA_SUCCESS) return false;
+  if ((CUdeviceptr)p + bytes > base + size) return false;
+  std::lock_guard<std::mutex> l(g_seg_mu);
+  auto it = g_segs.find(id);
+  if (it == g_segs.end()) {
+    LocalSeg sgm;
+    memset(&sgm, 0, sizeof(sgm));
+    sgm.id = id; sgm.base = base; sgm.size = size;
+    sgm.ok = cudaIpcGetMemHandle(&sgm.h, (void*)base) == cudaSuccess;
+    if (!sgm.ok) cudaGetLastError();
+    if (g_segs.size() > 4096) g_segs.clear();   // ids of freed allocations never come back; keep the table bounded
+    it = g_segs.emplace(id, sgm).first;
+  }
+  *out = it->second;
+  *off = (size_t)((CUdeviceptr)p - base);
+  return it->second.ok;
+}
+
+struct RegRec {   // one per rank per eligible call; must stay <= kRvScratch (256) bytes
+  unsigned long long id[2];
+  unsigned long long off[2];
+  cudaIpcMemHandle_t h[2];
+  int ok;
+  int pad;
+};
+static_assert(sizeof(RegRec) <= kRvScratch, "RegRec must fit the rendezvous scratch slot");
+
+// Collective (host). bufs[0] = input, bufs[1] = output (may be equal, may be null when a role has none on this rank —
+// then pass the other one twice). On success wins[k].p[r] = rank r's bufs[k] mapped in this process.
+static bool reg_exchange(b200mpi_comm* c, const void* in, void* out, size_t in_bytes, size_t out_bytes, Win* win_in, Win* win_out) {
+  RegRec mine;
+  memset(&mine, 0, sizeof(mine));
+  LocalSeg sg[2];
+  size_t off[2] = {0, 0};
+  const void* ptr[2] = {in, out};
+  const size_t nb[2] = {in_bytes, out_bytes};
+  mine.ok = 1;
+  for (int k = 0; k < 2; k++) {
+    if (!aligned16(ptr[k]) || !local_seg(ptr[k], nb[k], &sg[k], &off[k])) { mine.ok = 0; break; }
+    mine.id[k] = sg[k].id; mine.off[k] = off[k]; mine.h[k] = sg[k].h;
+  }
+  std::vector<RegRec> all(c->world);
+  std::string err;
+  if (c->rv.allgather(&mine, all.data(), sizeof(RegRec), c->timeout_ms, &err)) return false;
+  for (auto& r : all) if (!r.ok) { c->reg_refused++; return false; }
+  Win* wins[2] = {win_in, win_out};
+  bool ok = true;
+  for (int k = 0; k < 2 && ok; k++) {
+    memset(wins[k], 0, sizeof(Win));
+    for (int r = 0; r < c->world && ok; r++) {
+      if (r == c->rank) { wins[k]->p[r] = (char*)const_cast<void*>(ptr[k]); continue; }
+      auto key = std::make_pair(r, all[r].id[k]);
+      auto it = c->peer_maps.find(key);
+      if (it == c->peer_maps.end()) {
+        void* q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].h[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        it = c->peer_maps.emplace(key, (char*)q).first;
+        c->reg_opens++;
+      }
+      wins[k]->p[r] = it->second + all[r].off[k];
+    }
+  }
+  // a failed open on one rank must send everybody to the staged path: second (tiny) agreement round
+  int good = ok ? 1 : 0;
+  std::vector<int> goods(c->world);
+  if (c->rv.allgather(&good, goods.data(), sizeof(int), c->timeout_ms, &err)) return false;
+  for (int g : goods) if (!g) { c->reg_refused++; return false; }
+  c->reg_hits++;
+  return true;
+}
+static bool reg_wanted(b200mpi_comm* c, size_t bytes, bool p2p_path) {
+  if (c->local || c->world < 2 || c->reg_mode == 0 || bytes < c->reg_min) return false;
+  return c->reg_mode >= 2 || p2p_path;
+}
+
+// Pipelined staged collectives (k_pipe): `nbytes` = per-rank payload; `wide` ops keep `world` regions per staging slot.
+static bool pipe_wanted(b200mpi_comm* c, size_t full_bytes) {
+  return full_bytes >= c->pipe_min && !(c->flags & B200MPI_FLAG_NO_PIPE) && c->world > 1;
+}
+template <typename Fill>
+static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dtype, size_t nbytes, bool wide,
+                   cudaStream_t stream, int algo, Fill&& fill) {
+  if (mode == MODE_NVLS && !(c->multicast && c->wins[c->stage_win].mc)) mode = MODE_P2P;
+  int L = wide ? c->pipe_lanes_wide : (mode == MODE_NVLS ? c->pipe_lanes_nvls : c->pipe_lanes_p2p);
+  if (c->local) L = std::max(1, std::min(L, emu_max_blocks(c) / 3));
+  const int D = c->pipe_depth;
+  const size_t nvec = (nbytes + 15) / 16;
+  const size_t regions = wide ? (size_t)c->world : 1;
+  // chunk: a slot (regions x chunk) of at most pipe_chunk bytes, L*D slots must fit the staging region, and every lane
+  // should get >= 2 chunks when the message allows it
+  size_t cv = std::min(c->pipe_chunk / 16, c->twoshot_bytes / 16 / ((size_t)L * D)) / regions;
+  cv = std::min(cv, std::max((size_t)1024 / regions, nvec / ((size_t)L * 2)));
+  cv = std::max((size_t)c->world, cv / c->world * c->world);
+  if ((size_t)L * D * cv * regions * 16 > c->twoshot_bytes) return fail(B200MPI_ERR_INVALID, std::string(name) + ": staging window too small");
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  for (size_t k = 0; k < ranks.size(); k++) {
+    KArgs& a = args[k];
+    memset(&a, 0, sizeof(a));
+    a.c = dev_comm(c, ranks[k]);
+    a.buf = win_region(c, c->stage_win, c->twoshot_off);
+    a.nbytes = nbytes; a.nvec = nvec; a.per = cv; a.scale = 1.0f;
+    a.lanes = L; a.depth = D;
+    fill(a, ranks[k]);
+  }
+  return run(c, stream, 3 * L, name, nbytes, algo, args,
+             [&](const Launch& l, const KArgs& a) { return launch_pipe(l, a, kind, dtype, mode); });
+}
+
 static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const void* in, void* out, size_t count,
                         int dtype, int op, float scale, int algo, cudaStream_t stream) {
   if (count == 0) return 0;
@@ -555,31 +693,31 @@ static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const vo
     return run(c, stream, blocks, "allreduce", nbytes, algo, args,
                [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, mode, false); });
   }
-  // staged, large: ONE pipelined kernel (copy-in / reduce / copy-out CTAs chained through flags per lane)
-  if (nbytes >= c->pipe_min && !(c->flags & B200MPI_FLAG_NO_PIPE)) {
-    int L = mode == MODE_NVLS ? c->pipe_lanes_nvls : c->pipe_lanes_p2p;
-    if (c->local) L = std::max(1, std::min(L, emu_max_blocks(c) / 3));
-    const int D = c->pipe_depth;
-    const size_t nvec = (nbytes + 15) / 16;
-    // chunk: at most pipe_chunk, small enough that every lane gets >= 2 chunks, and L*D slots must fit the staging region
-    size_t cv = std::min(c->pipe_chunk / 16, c->twoshot_bytes / 16 / ((size_t)L * D));
-    cv = std::min(cv, std::max((size_t)1024, nvec / ((size_t)L * 2)));
-    cv = std::max((size_t)c->world, cv / c->world * c->world);
-    for (size_t k = 0; k < ranks.size(); k++) {
-      const int r = ranks[k];
-      KArgs& a = args[k];
+  // large, P2P path: register the user buffers (cudaIpc) and run the zero-copy two-shot straight on them
+  if (nbytes % 16 == 0 && reg_wanted(c, nbytes, mode == MODE_P2P)) {
+    Win win_in, win_out;
+    if (reg_exchange(c, in, out, nbytes, nbytes, &win_in, &win_out)) {
+      const size_t nvec = nbytes / 16;
+      const size_t per = (nvec + c->world - 1) / c->world;
+      const int blocks = blocks_for(c, per, 2, c->max_blocks);
+      KArgs& a = args[0];
       memset(&a, 0, sizeof(a));
-      a.c = dev_comm(c, r);
-      a.buf = win_region(c, c->stage_win, c->twoshot_off);
+      a.c = dev_comm(c, c->rank);
+      a.buf = win_in;
+      if (in != out) a.param = win_out;
+      a.nbytes = nbytes; a.nvec = nvec; a.per = per; a.scale = scale; a.op = op;
+      return run(c, stream, blocks, "allreduce_reg", nbytes, B200MPI_ALGO_TWOSHOT, args,
+                 [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, MODE_P2P, false); });
+    }
+  }
+  // staged, large: ONE pipelined kernel (copy-in / reduce / copy-out CTAs chained through flags per lane)
+  if (pipe_wanted(c, nbytes))
+    return pipe_op(c, "allreduce_pipe", PIPE_ALLREDUCE, mode, dtype, nbytes, false, stream, algo, [&](KArgs& a, int r) {
       a.in = in_ptr(c, in, r);
       a.out = out_ptr(c, out, r);
-      a.nbytes = nbytes; a.nvec = nvec; a.per = cv; a.scale = scale; a.op = op;
-      a.lanes = L; a.depth = D;
+      a.scale = scale; a.op = op;
       a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
-    }
-    return run(c, stream, 3 * L, "allreduce_pipe", nbytes, algo, args,
-               [&](const Launch& l, const KArgs& a) { return launch_allreduce_pipe(l, a, dtype, mode); });
-  }
+    });
   // staged: chunk through the two-shot staging region
   const size_t chunk_max = c->twoshot_bytes / 16 * 16;
   for (size_t done = 0; done < nbytes; done += chunk_max) {
@@ -629,6 +767,31 @@ static int staged_op(b200mpi_comm* c, const char* name, size_t nbytes, int slots
     if (rc) return rc;
   }
   return 0;
+}
+
+// ---- zero-copy collectives on a symmetric window region (k_*_sym) ------------------------------------------------
+static int sym_check(b200mpi_comm* c, int win, size_t off, size_t nbytes, const char* what) {
+  if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return fail(B200MPI_ERR_INVALID, std::string(what) + ": bad window");
+  if (off % 16 || nbytes % 16 || off + nbytes > c->wins[win].bytes)
+    return fail(B200MPI_ERR_INVALID, std::string(what) + ": region must be 16-byte aligned/sized and inside the window");
+  return 0;
+}
+template <typename Fill, typename L>
+static int sym_op(b200mpi_comm* c, const char* name, int win, size_t off, size_t nbytes, size_t per_vecs, int mode, int per_thread,
+                  cudaStream_t stream, Fill&& fill, L&& launcher) {
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  const size_t nvec = nbytes / 16;
+  const int blocks = blocks_for(c, per_vecs, per_thread, mode == MODE_NVLS ? c->nvls_blocks * 2 : c->max_blocks);
+  for (size_t k = 0; k < ranks.size(); k++) {
+    KArgs& a = args[k];
+    memset(&a, 0, sizeof(a));
+    a.c = dev_comm(c, ranks[k]);
+    a.buf = win_region(c, win, off);
+    a.nbytes = nbytes; a.nvec = nvec; a.per = per_vecs; a.scale = 1.0f;
+    fill(a, ranks[k]);
+  }
+  return run(c, stream, blocks, name, nbytes, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT, args, launcher);
 }
 
 }  // namespace b200mpi
@@ -706,6 +869,8 @@ int b200mpi_comm_destroy(b200mpi_comm_t c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (!c->local && c->rv.header()) { std::string err; c->rv.barrier(2000, &err); }
+  for (auto& kv : c->peer_maps) cudaIpcCloseMemHandle(kv.second);
+  c->peer_maps.clear();
   for (auto& W : c->wins) window_release(c, W);
   for (int r = 0; r < kMaxRanks; r++) if (c->epoch[r]) cudaFree(c->epoch[r]);
   if (c->emu_ring) cudaFree(c->emu_ring);
@@ -815,6 +980,26 @@ int b200mpi_set_hyper_ptr(b200mpi_comm_t c, const float* p) { c->hyper = p; retu
 int b200mpi_broadcast_bytes(b200mpi_comm_t c, void* buf, size_t bytes, int root, void* stream) {
   if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "broadcast: bad root");
   const int mode = c->multicast ? MODE_NVLS : MODE_P2P;
+  if (bytes % 16 == 0 && reg_wanted(c, bytes, mode == MODE_P2P || c->world == 2)) {   // zero-copy: root stores into the peers' buffers
+    Win w, w2;
+    if (reg_exchange(c, buf, buf, bytes, bytes, &w, &w2)) {
+      std::vector<KArgs> args(1);
+      KArgs& a = args[0];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, c->rank);
+      a.buf = w;
+      a.nbytes = bytes; a.nvec = bytes / 16; a.per = bytes / 16; a.scale = 1.0f; a.root = root;
+      return run(c, (cudaStream_t)stream, blocks_for(c, bytes / 16, 4, c->max_blocks), "broadcast_reg", bytes, B200MPI_ALGO_TWOSHOT, args,
+                 [&](const Launch& l, const KArgs& a) { return launch_broadcast_sym(l, a, MODE_P2P); });
+    }
+  }
+  if (pipe_wanted(c, bytes))
+    return pipe_op(c, "broadcast_pipe", PIPE_BROADCAST, mode, DT_F32, bytes, false, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
+                   [&](KArgs& a, int r) {
+                     a.root = root;
+                     a.in = out_ptr(c, buf, r); a.out = out_ptr(c, buf, r);
+                     a.in_aligned = a.out_aligned = aligned16(a.in);
+                   });
   return staged_op(c, "broadcast", bytes, 1, (cudaStream_t)stream,
                    [&](KArgs& a, int r, size_t done, size_t) {
                      a.root = root;
@@ -829,6 +1014,30 @@ int b200mpi_broadcast(b200mpi_comm_t c, void* buf, size_t count, b200mpi_dtype_t
 
 int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream) {
   const size_t total = count * esize(dtype);
+  if (total % 16 == 0 && reg_wanted(c, total * c->world, true)) {   // zero-copy: every rank stores its block into every output
+    Win win_in, win_out;
+    if (reg_exchange(c, in, out, total, total * c->world, &win_in, &win_out)) {
+      std::vector<KArgs> args(1);
+      KArgs& a = args[0];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, c->rank);
+      a.buf = win_out;
+      a.in = (const char*)in;
+      a.nbytes = total * c->world; a.nvec = total / 16 * c->world; a.per = total / 16; a.scale = 1.0f;
+      return run(c, (cudaStream_t)stream, blocks_for(c, total / 16, 4, c->max_blocks), "allgather_reg", total, B200MPI_ALGO_TWOSHOT, args,
+                 [&](const Launch& l, const KArgs& a) { return launch_allgather_sym(l, a, MODE_P2P); });
+    }
+  }
+  if (pipe_wanted(c, total * c->world)) {
+    const int mode = c->multicast ? MODE_NVLS : MODE_P2P;
+    return pipe_op(c, "allgather_pipe", PIPE_ALLGATHER, mode, DT_F32, total, true, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
+                   [&](KArgs& a, int r) {
+                     a.in = in_ptr(c, in, r); a.out = out_ptr(c, out, r);
+                     a.in_aligned = aligned16(a.in);
+                     a.out_aligned = aligned16(a.out) && (total % 16 == 0);
+                     a.ustride = total;
+                   });
+  }
   // chunks of the per-rank payload land at out + r*total + done
   return staged_op(c, "allgather", total, c->world, (cudaStream_t)stream,
                    [&](KArgs& a, int r, size_t done, size_t nb) {
@@ -847,6 +1056,31 @@ int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count,
 int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype,
                            b200mpi_op_t op, float scale, void* stream) {
   const size_t total = count * esize(dtype);
+  if (dtype < 0 || dtype > 2 || op < 0 || op > 2) return fail(B200MPI_ERR_INVALID, "reduce_scatter: bad dtype/op");
+  const bool rs_nvls = c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32);
+  if (total % 16 == 0 && reg_wanted(c, total * c->world, !rs_nvls)) {   // zero-copy: pull the owned block from every input
+    Win win_in, win_out;
+    if (reg_exchange(c, in, out, total * c->world, total, &win_in, &win_out)) {
+      std::vector<KArgs> args(1);
+      KArgs& a = args[0];
+      memset(&a, 0, sizeof(a));
+      a.c = dev_comm(c, c->rank);
+      a.buf = win_in;
+      a.out = (char*)out;
+      a.nbytes = total * c->world; a.nvec = total / 16 * c->world; a.per = total / 16; a.scale = scale; a.op = op;
+      return run(c, (cudaStream_t)stream, blocks_for(c, total / 16, 2, c->max_blocks), "reduce_scatter_reg", total, B200MPI_ALGO_TWOSHOT, args,
+                 [&](const Launch& l, const KArgs& a) { return launch_reduce_scatter_sym(l, a, dtype, MODE_P2P); });
+    }
+  }
+  if (pipe_wanted(c, total * c->world)) {
+    const int mode = rs_nvls ? MODE_NVLS : MODE_P2P;
+    return pipe_op(c, "reduce_scatter_pipe", PIPE_REDUCE_SCATTER, mode, dtype, total, true, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
+                   [&](KArgs& a, int r) {
+                     a.in = in_ptr(c, in, r); a.out = out_ptr(c, out, r);
+                     a.in_aligned = aligned16(a.in) && (total % 16 == 0); a.out_aligned = aligned16(a.out);
+                     a.op = op; a.scale = scale; a.ustride = total;
+                   });
+  }
   return staged_op(c, "reduce_scatter", total, c->world, (cudaStream_t)stream,
                    [&](KArgs& a, int r, size_t done, size_t) {
                      a.in = in_ptr(c, in, r) + done; a.out = out_ptr(c, out, r) + done;
@@ -867,6 +1101,40 @@ int b200mpi_reduce(b200mpi_comm_t c, const void* in, void* out, size_t count, b2
                      a.op = op; a.scale = scale; a.root = root;
                    },
                    [&](const Launch& l, const KArgs& a) { return launch_reduce(l, a, dtype); });
+}
+
+int b200mpi_allgather_sym(b200mpi_comm_t c, int win, size_t offset, size_t slice_bytes, void* stream) {
+  if (slice_bytes == 0) return 0;
+  int rc = sym_check(c, win, offset, slice_bytes * c->world, "allgather_sym");
+  if (rc) return rc;
+  const int mode = (c->multicast && c->wins[win].mc) ? MODE_NVLS : MODE_P2P;
+  return sym_op(c, "allgather_sym", win, offset, slice_bytes * c->world, slice_bytes / 16, mode, 4, (cudaStream_t)stream,
+                [&](KArgs&, int) {}, [&](const Launch& l, const KArgs& a) { return launch_allgather_sym(l, a, mode); });
+}
+
+int b200mpi_reduce_scatter_sym(b200mpi_comm_t c, int win, size_t offset, size_t slice_count, b200mpi_dtype_t dtype,
+                               b200mpi_op_t op, float scale, void* out, void* stream) {
+  if (slice_count == 0) return 0;
+  if (dtype < 0 || dtype > 2 || op < 0 || op > 2) return fail(B200MPI_ERR_INVALID, "reduce_scatter_sym: bad dtype/op");
+  const size_t slice_bytes = slice_count * esize(dtype);
+  int rc = sym_check(c, win, offset, slice_bytes * c->world, "reduce_scatter_sym");
+  if (rc) return rc;
+  if (!c->local && out && !aligned16(out)) return fail(B200MPI_ERR_INVALID, "reduce_scatter_sym: output must be 16-byte aligned");
+  const int mode = (c->multicast && c->wins[win].mc && (op == B200MPI_SUM || dtype != B200MPI_F32)) ? MODE_NVLS : MODE_P2P;
+  return sym_op(c, "reduce_scatter_sym", win, offset, slice_bytes * c->world, slice_bytes / 16, mode, mode == MODE_NVLS ? 4 : 2,
+                (cudaStream_t)stream,
+                [&](KArgs& a, int r) { a.op = op; a.scale = scale; a.out = out ? out_ptr(c, out, r) : nullptr; },
+                [&](const Launch& l, const KArgs& a) { return launch_reduce_scatter_sym(l, a, dtype, mode); });
+}
+
+int b200mpi_broadcast_sym(b200mpi_comm_t c, int win, size_t offset, size_t bytes, int root, void* stream) {
+  if (bytes == 0) return 0;
+  if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "broadcast_sym: bad root");
+  int rc = sym_check(c, win, offset, bytes, "broadcast_sym");
+  if (rc) return rc;
+  const int mode = (c->multicast && c->wins[win].mc) ? MODE_NVLS : MODE_P2P;
+  return sym_op(c, "broadcast_sym", win, offset, bytes, bytes / 16, mode, 4, (cudaStream_t)stream,
+                [&](KArgs& a, int) { a.root = root; }, [&](const Launch& l, const KArgs& a) { return launch_broadcast_sym(l, a, mode); });
 }
 
 int b200mpi_alltoall(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream) {
@@ -912,8 +1180,20 @@ int b200mpi_set_pipe(b200mpi_comm_t c, size_t min_bytes, int lanes_nvls, int lan
   if (min_bytes != (size_t)-1) c->pipe_min = min_bytes;
   if (lanes_nvls > 0) c->pipe_lanes_nvls = std::min(lanes_nvls, kPipeLanes);
   if (lanes_p2p > 0) c->pipe_lanes_p2p = std::min(lanes_p2p, kPipeLanes);
+  if (lanes_nvls > 0 && lanes_p2p > 0) c->pipe_lanes_wide = std::min(std::max(lanes_nvls, lanes_p2p), kPipeLanes);
   if (depth > 0) c->pipe_depth = std::max(2, std::min(depth, 8));
   if (chunk_bytes > 0) c->pipe_chunk = std::max((size_t)16 << 10, chunk_bytes);
+  return 0;
+}
+int b200mpi_set_reg(b200mpi_comm_t c, int mode, size_t min_bytes) {
+  if (mode >= 0) c->reg_mode = mode;
+  if (min_bytes != (size_t)-1) c->reg_min = min_bytes;
+  return 0;
+}
+int b200mpi_reg_stats(b200mpi_comm_t c, uint64_t* zero_copy_calls, uint64_t* handles_opened, uint64_t* refused) {
+  if (zero_copy_calls) *zero_copy_calls = c->reg_hits;
+  if (handles_opened) *handles_opened = c->reg_opens;
+  if (refused) *refused = c->reg_refused;
   return 0;
 }
 int b200mpi_select_algo(b200mpi_comm_t c, size_t bytes, b200mpi_dtype_t dtype, b200mpi_op_t op, int symmetric) {

@@ -123,7 +123,10 @@ class FlatModelState:
     def broadcast_parameters(self, root: int = 0) -> None:
         """K3: rank-0 state to everyone (tensorflow_mnist.py:143)."""
         if self.comm.world > 1:
-            self.comm.broadcast(self.flat_param, root=root)
+            if hasattr(self.comm, "broadcast_window"):   # zero-copy: the parameters already live in a symmetric window
+                self.comm.broadcast_window(self.param_win, 0, self.total * 4, root=root)
+            else:
+                self.comm.broadcast(self.flat_param, root=root)
         self.refresh_lowp()
 
     def refresh_lowp(self) -> None:

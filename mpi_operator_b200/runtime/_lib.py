@@ -92,6 +92,11 @@ def lib() -> C.CDLL:
     L.b200mpi_get_tuning.argtypes = [vp, C.POINTER(sz), C.POINTER(sz), C.POINTER(i), C.POINTER(i)]
     L.b200mpi_select_algo.argtypes = [vp, sz, i, i, i]
     L.b200mpi_set_pipe.argtypes = [vp, sz, i, i, i, sz]
+    L.b200mpi_set_reg.argtypes = [vp, i, sz]
+    L.b200mpi_reg_stats.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.b200mpi_allgather_sym.argtypes = [vp, i, sz, sz, vp]
+    L.b200mpi_reduce_scatter_sym.argtypes = [vp, i, sz, sz, i, i, f, vp, vp]
+    L.b200mpi_broadcast_sym.argtypes = [vp, i, sz, sz, i, vp]
     if hasattr(L, "b200mpi_p2p_batch"):  # experimental point-to-point (csrc/kernels/p2p.cu)
         L.b200mpi_p2p_batch.argtypes = [vp, vp, i, vp]
         L.b200mpi_comm_has_p2p.argtypes = [vp]

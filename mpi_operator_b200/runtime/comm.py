@@ -237,6 +237,15 @@ class Communicator:
         check(_lib.lib().b200mpi_set_pipe(self._h, C.c_size_t(-1).value if min_bytes < 0 else min_bytes, lanes_nvls,
                                           lanes_p2p, depth, chunk_bytes))
 
+    def set_reg(self, mode: int = -1, min_bytes: int = -1) -> None:
+        """Lazy cudaIpc registration of user buffers: 0 never, 1 where the zero-copy P2P kernels win, 2 whenever possible."""
+        check(_lib.lib().b200mpi_set_reg(self._h, mode, C.c_size_t(-1).value if min_bytes < 0 else min_bytes))
+
+    def reg_stats(self) -> dict:
+        a, b, c_ = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _lib.lib().b200mpi_reg_stats(self._h, C.byref(a), C.byref(b), C.byref(c_))
+        return {"zero_copy_calls": a.value, "handles_opened": b.value, "refused": c_.value}
+
     def get_tuning(self) -> dict:
         a, b, c_, d = C.c_size_t(), C.c_size_t(), C.c_int(), C.c_int()
         _lib.lib().b200mpi_get_tuning(self._h, C.byref(a), C.byref(b), C.byref(c_), C.byref(d))
@@ -283,6 +292,24 @@ class Communicator:
         check(_lib.lib().b200mpi_allreduce_sym(self._h, win.id, offset, count, dtype_code(dtype), _OPS[op],
                                                self._scale(op, self.world, scale), resolve_algo(algo),
                                                _stream_ptr(stream)), "allreduce_sym")
+
+    def allgather_window(self, win: Window, offset: int, slice_bytes: int, stream=None) -> None:
+        """Zero-copy allgather: the region is ``world`` slices of ``slice_bytes``; rank r's slice r (of its own copy) is
+        delivered into slice r of every copy (one ``multimem.st`` per vector on NVLS)."""
+        check(_lib.lib().b200mpi_allgather_sym(self._h, win.id, offset, slice_bytes, _stream_ptr(stream)), "allgather_sym")
+
+    def reduce_scatter_window(self, win: Window, offset: int, slice_count: int, dtype, op: str = "sum",
+                              scale: Optional[float] = None, out=None, stream=None) -> None:
+        """Zero-copy reduce-scatter: slice r of every copy is reduced into rank r's ``out`` (slice-sized tensor) or, with
+        ``out=None``, in place into slice r of rank r's own copy (``multimem.ld_reduce`` on NVLS)."""
+        pout = self._ptrs(out)[0] if out is not None else None
+        check(_lib.lib().b200mpi_reduce_scatter_sym(self._h, win.id, offset, slice_count, dtype_code(dtype), _OPS[op],
+                                                    self._scale(op, self.world, scale), pout, _stream_ptr(stream)),
+              "reduce_scatter_sym")
+
+    def broadcast_window(self, win: Window, offset: int, nbytes: int, root: int = 0, stream=None) -> None:
+        """Zero-copy broadcast of a window region from ``root``'s copy into every copy."""
+        check(_lib.lib().b200mpi_broadcast_sym(self._h, win.id, offset, nbytes, root, _stream_ptr(stream)), "broadcast_sym")
 
     def allreduce(self, tensor, out=None, op: str = "sum", scale: Optional[float] = None, algo=None, stream=None):
         """Allreduce on arbitrary contiguous CUDA tensors (in place when ``out`` is None)."""

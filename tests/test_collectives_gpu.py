@@ -73,6 +73,41 @@ def test_allreduce_pipelined_user_pointers(comm, dtype, n, chunk):
         comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20, depth=3)
 
 
+@pytest.mark.parametrize("n", [3, 1000, 70001, (1 << 19) + 5])
+@pytest.mark.parametrize("chunk", [16 << 10, 128 << 10])
+def test_pipelined_allgather_reduce_scatter_broadcast(comm, n, chunk):
+    """The other ops of k_pipe on user pointers: allgather (push + copy-out), reduce_scatter (copy-in + reduce), broadcast
+    (root pushes); several chunks per lane, ragged tails, odd sizes (byte-wise slow path), back to back with each other."""
+    comm.set_pipe(min_bytes=0, chunk_bytes=chunk, depth=2)
+    W = comm.world
+    try:
+        for it in range(2):
+            xs = _rand(W, n, torch.bfloat16, seed=n + it)
+            outs = [torch.empty(W * n, device="cuda", dtype=torch.bfloat16) for _ in range(W)]
+            comm.allgather(xs, outs)
+            want = torch.cat(xs)
+            ins = _rand(W, W * n, torch.float32, seed=2 * n + it)
+            rs = [torch.empty(n, device="cuda", dtype=torch.float32) for _ in range(W)]
+            comm.reduce_scatter(ins, rs, op="sum")
+            root = (it + 1) % W
+            bs = _rand(W, n, torch.float32, seed=3 * n + it)
+            bwant = bs[root].clone()
+            comm.broadcast(bs, root=root)
+            torch.cuda.synchronize()
+            comm.check_error()
+            for o in outs:
+                assert torch.equal(o, want)
+            rwant = _ref(ins, "sum")
+            for r, o in enumerate(rs):
+                torch.testing.assert_close(o, rwant[r * n:(r + 1) * n], rtol=1e-5, atol=1e-5 * W)
+            for b in bs:
+                assert torch.equal(b, bwant)
+        names = {o["op"] for o in comm.stats(native_only=True)["ops"]}
+        assert {"allgather_pipe", "reduce_scatter_pipe", "broadcast_pipe"} <= names
+    finally:
+        comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20, depth=3)
+
+
 def test_pipelined_and_barrier_kernels_interleave(comm):
     """The pipeline keeps its own flags and counters: interleaving it with the barrier-based kernels on the same
     staging window must stay bit-exact (integer-valued data)."""
@@ -85,6 +120,12 @@ def test_pipelined_and_barrier_kernels_interleave(comm):
             xs = [t[:n].clone() for t in bufs]
             want = torch.stack(xs).sum(0)
             comm.allreduce(xs, xs, algo="twoshot" if i % 2 else "auto")
+            if i % 5 == 0:   # a push op (first action: stores into the peers' staging) right behind an allreduce
+                g_in = [t[:n].clone() for t in bufs]
+                g_out = [torch.empty(comm.world * n, device="cuda") for _ in range(comm.world)]
+                comm.allgather(g_in, g_out)
+                for o in g_out:
+                    assert torch.equal(o, torch.cat(g_in)), f"allgather at iteration {i} n={n}"
             for x in xs:
                 assert torch.equal(x, want), f"iteration {i} n={n}"
         torch.cuda.synchronize()
@@ -121,6 +162,52 @@ def test_allreduce_window(comm, dtype, algo):
     for v in views:
         torch.testing.assert_close(v.float(), want.to(dtype).float(), rtol=rtol, atol=atol)
         assert torch.equal(v, views[0])
+    win.free()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_window_allgather_reduce_scatter_broadcast(comm, dtype):
+    """Zero-copy forms on a symmetric window (k_allgather_sym / k_reduce_scatter_sym / k_broadcast_sym)."""
+    W = comm.world
+    esz = torch.empty((), dtype=dtype).element_size()
+    per = 4096 + 8                       # elements per slice (16-byte multiple in both dtypes)
+    off = 256
+    win = comm.alloc_window(off + W * per * esz)
+    views = [win.tensor(dtype, rank=r, offset=off, numel=W * per) for r in range(W)]
+    # allgather: rank r owns slice r of its own copy; everything else is poison
+    xs = _rand(W, per, dtype, seed=21)
+    for r, v in enumerate(views):
+        v.fill_(-7.0)
+        v[r * per:(r + 1) * per].copy_(xs[r])
+    comm.allgather_window(win, off, per * esz)
+    torch.cuda.synchronize()
+    comm.check_error()
+    for v in views:
+        assert torch.equal(v, torch.cat(xs))
+    # reduce_scatter, out of place then in place
+    ins = _rand(W, W * per, dtype, seed=22)
+    for v, x in zip(views, ins):
+        v.copy_(x)
+    want = _ref(ins, "avg")
+    outs = [torch.empty(per, device="cuda", dtype=dtype) for _ in range(W)]
+    comm.reduce_scatter_window(win, off, per, dtype, op="avg", out=outs)
+    torch.cuda.synchronize()
+    rtol, atol = TOL[dtype]
+    for r, o in enumerate(outs):
+        torch.testing.assert_close(o.float(), want[r * per:(r + 1) * per].to(dtype).float(), rtol=rtol, atol=atol)
+    comm.reduce_scatter_window(win, off, per, dtype, op="avg")
+    torch.cuda.synchronize()
+    for r, v in enumerate(views):
+        torch.testing.assert_close(v[r * per:(r + 1) * per].float(), want[r * per:(r + 1) * per].to(dtype).float(), rtol=rtol, atol=atol)
+    # broadcast from the last rank
+    root = W - 1
+    for r, v in enumerate(views):
+        v.fill_(float(r))
+    comm.broadcast_window(win, off, W * per * esz, root=root)
+    torch.cuda.synchronize()
+    comm.check_error()
+    for v in views:
+        assert torch.equal(v, torch.full_like(v, float(root)))
     win.free()
 
 
