@@ -225,6 +225,9 @@ int b200mpi_broadcast_sym(b200mpi_comm_t comm, int win, size_t offset, size_t by
  * kernel of `lanes` x {copy-in, reduce, copy-out} CTAs with `depth` staging slots of `chunk_bytes` per lane.
  * Non-positive values keep the current setting. Env: B200MPI_PIPE_{MIN_BYTES,LANES_NVLS,LANES_P2P,DEPTH,CHUNK_BYTES}. */
 int b200mpi_set_pipe(b200mpi_comm_t comm, size_t min_bytes, int lanes_nvls, int lanes_p2p, int depth, size_t chunk_bytes);
+/* Debug timeline of the last pipelined launch (B200MPI_PIPE_DEBUG=1 when the communicator was created):
+ * out[3 roles][48 lanes][32 chunks][3] = {wait begin, work begin, end} as %globaltimer ns. Returns u64 words written. */
+size_t b200mpi_pipe_timeline(b200mpi_comm_t comm, unsigned long long* out, size_t cap);
 /* Lazy registration of user buffers (cudaIpc) for the user-pointer collectives: mode 0 = never, 1 = where the zero-copy
  * P2P kernels win (default: world 2, paths without NVLS, allgather), 2 = whenever the buffers can be exported; calls below
  * `min_bytes` (SIZE_MAX: keep) always take the staged kernels. Env: B200MPI_REG, B200MPI_REG_MIN_BYTES. */

@@ -82,32 +82,41 @@ __device__ __forceinline__ void block_reduce_to_partial(float (&s1)[8], float (&
   }
 }
 
-// Merge `parts` partial rows: CTA handles 32 outputs, its 8 warps split the rows, lanes = outputs.
-// Returns (for threads with warp==0) the total for output blockIdx.x*32 + lane.
+// Merge `parts` partial rows. The finalize kernels are pure latency (a few KB of L2-resident data, 339 launches per
+// ResNet-101 step: 9.2 us each = 3.1 ms in round 1's launch table), so the merge is laid out for the shortest dependent
+// chain instead of for coalescing: a CTA owns 8 outputs (32 contiguous bytes per row) and its 256 threads are 32 row
+// slots x 8 outputs, each slot walking rows slot, slot+32, ... with 4 loads in flight -> ceil(parts/128) rounds of L2
+// latency (3 for the maximum of 296 rows; the 8-warps-x-32-outputs layout needed 10).
+// Returns (for threads 0..7) the total for output blockIdx.x*8 + threadIdx.x.
+constexpr int kMergeOut = 8;
 __device__ __forceinline__ float merge_partials(const float* __restrict__ partials, int parts, int nout, int* out_index) {
-  __shared__ float sm[8][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int o = blockIdx.x * 32 + lane;
+  __shared__ float sm[8][kMergeOut + 1];
+  const int oi = threadIdx.x & (kMergeOut - 1), slot = threadIdx.x >> 3;   // 32 slots
+  const int o = blockIdx.x * kMergeOut + oi;
   float acc = 0.f;
   if (o < nout) {
     const float* p = partials + o;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;  // 4 independent loads in flight per lane
-    int b = warp;
-    for (; b + 24 < parts; b += 32) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int b = slot;
+    for (; b + 96 < parts; b += 128) {
       a0 += __ldcg(p + (size_t)b * nout);
-      a1 += __ldcg(p + (size_t)(b + 8) * nout);
-      a2 += __ldcg(p + (size_t)(b + 16) * nout);
-      a3 += __ldcg(p + (size_t)(b + 24) * nout);
+      a1 += __ldcg(p + (size_t)(b + 32) * nout);
+      a2 += __ldcg(p + (size_t)(b + 64) * nout);
+      a3 += __ldcg(p + (size_t)(b + 96) * nout);
     }
-    for (; b < parts; b += 8) a0 += __ldcg(p + (size_t)b * nout);
+    for (; b < parts; b += 32) a0 += __ldcg(p + (size_t)b * nout);
     acc = (a0 + a1) + (a2 + a3);
   }
-  sm[warp][lane] = acc;
+  // the 4 slots of a warp that share an output: lanes oi, oi+8, oi+16, oi+24
+  acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < kMergeOut) sm[warp][lane] = acc;
   __syncthreads();
   float tot = 0.f;
-  if (warp == 0) {
+  if (threadIdx.x < kMergeOut) {
 #pragma unroll
-    for (int w = 0; w < 8; w++) tot += sm[w][lane];
+    for (int w = 0; w < 8; w++) tot += sm[w][threadIdx.x];
   }
   *out_index = o;
   return tot;
@@ -159,7 +168,7 @@ k_bn_fwd_finalize(const __nv_bfloat16* __restrict__ x_row0, const float* __restr
   const float tot = merge_partials(partials, parts, 2 * C, &o);
   if ((threadIdx.x >> 5) != 0) return;
   const float other = __shfl_xor_sync(0xffffffffu, tot, 1);  // lanes 2j / 2j+1 hold S1 / S2 of one channel
-  if (o >= 2 * C || (o & 1)) return;
+  if (threadIdx.x >= kMergeOut || o >= 2 * C || (o & 1)) return;
   const int cgi = o >> 4, j = (o & 15) >> 1, c = cgi * 8 + j;
   const float S1 = tot, S2 = other;
   const float inv_m = 1.0f / (float)M;
@@ -284,7 +293,7 @@ k_bn_bwd_finalize(const float* __restrict__ partials, int parts, float* __restri
   const float tot = merge_partials(partials, parts, 2 * C, &o);
   if ((threadIdx.x >> 5) != 0) return;
   const float other = __shfl_xor_sync(0xffffffffu, tot, 1);
-  if (o >= 2 * C || (o & 1)) return;
+  if (threadIdx.x >= kMergeOut || o >= 2 * C || (o & 1)) return;
   const int cgi = o >> 4, j = (o & 15) >> 1, c = cgi * 8 + j;
   const float inv_m = 1.0f / (float)M;
   const float invstd = save_invstd[c];
@@ -391,7 +400,7 @@ int b200mpi_bn_act_fwd(const void* x, const void* residual, void* y, void* mask,
   long long rows;
   plan(M, C, kMaxParts, 2LL * C, &grid, &rows, reduce_chunk());
   k_bn_fwd_stats<<<grid, kThreadsBN, 0, s>>>((const uint4*)x, partials, M, C, rows);
-  k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>((const __nv_bfloat16*)x, partials, grid, coef, M, C, weight, bias,
+  k_bn_fwd_finalize<<<(2 * C + kMergeOut - 1) / kMergeOut, kThreadsBN, 0, s>>>((const __nv_bfloat16*)x, partials, grid, coef, M, C, weight, bias,
                                                             running_mean, running_var, save_mean, save_invstd, eps, momentum);
   plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, elem_chunk());
   if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
@@ -413,7 +422,7 @@ int b200mpi_bn_act_fwd_prestats(const void* x, const void* residual, void* y, vo
   float* coef = workspace;
   int grid;
   long long rows;
-  k_bn_fwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>(nullptr, partials, parts, coef, M, C, weight, bias, running_mean,
+  k_bn_fwd_finalize<<<(2 * C + kMergeOut - 1) / kMergeOut, kThreadsBN, 0, s>>>(nullptr, partials, parts, coef, M, C, weight, bias, running_mean,
                                                             running_var, save_mean, save_invstd, eps, momentum);
   plan(M, C, 1184, (residual ? 6LL : 4LL) * C, &grid, &rows, elem_chunk());
   if (relu && residual) k_bn_fwd_apply<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)x, (const uint4*)residual, (uint4*)y, (uint8_t*)mask, coef, M, C, rows);
@@ -435,7 +444,7 @@ int b200mpi_bn_act_bwd(const void* dz, const void* x, const void* mask, void* dx
   plan(M, C, kMaxParts, 4LL * C, &grid, &rows, reduce_chunk());
   if (relu) k_bn_bwd_reduce<true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, partials, M, C, rows, save_mean);
   else k_bn_bwd_reduce<false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, nullptr, partials, M, C, rows, save_mean);
-  k_bn_bwd_finalize<<<(2 * C + 31) / 32, kThreadsBN, 0, s>>>(partials, grid, coef, M, C, weight, save_mean, save_invstd, dweight, dbias);
+  k_bn_bwd_finalize<<<(2 * C + kMergeOut - 1) / kMergeOut, kThreadsBN, 0, s>>>(partials, grid, coef, M, C, weight, save_mean, save_invstd, dweight, dbias);
   plan(M, C, 1184, (dres ? 8LL : 6LL) * C, &grid, &rows, elem_chunk());
   if (relu && dres) k_bn_bwd_elemt<true, true><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, (uint4*)dres, coef, M, C, rows);
   else if (relu) k_bn_bwd_elemt<true, false><<<grid, kThreadsBN, 0, s>>>((const uint4*)dz, (const uint4*)x, (const uint8_t*)mask, (uint4*)dx, nullptr, coef, M, C, rows);

@@ -195,38 +195,108 @@ k_allreduce_twoshot(const __grid_constant__ KArgs a0, const KArgs* __restrict__ 
 // said so (local counter for allreduce, RED flags otherwise). Flags only grow (per-role, per-lane counters persist in
 // the epoch array and advance identically for all three roles), so the kernel is CUDA-graph capturable like the others.
 // ===========================================================================
-// copy `len` vectors user -> staging (plain stores into local HBM), 8 loads in flight per thread
-__device__ __forceinline__ void pipe_copy_in(char* dst, const char* ubase, size_t uvec0, size_t unbytes, bool ualigned, size_t len) {
-  constexpr int U = 8;
-  for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
-    uint4 v[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * blockDim.x;
-      if (i < len) v[u] = user_load(ubase, uvec0 + i, unbytes, ualigned);
+// ---- TMA bulk copies for the pipeline's local staging copies ------------------------------------------------------
+// One elected thread moves a chunk global -> shared -> global with cp.async.bulk (SASS UBLKCP): a ring of kBulkNB
+// buffers, up to kBulkNB/2 loads and kBulkNB/2 stores in flight (96 KB each way per CTA) with no registers and no
+// warps tied up - a 512-thread CTA doing 16-byte loads/stores topped out at ~26 GB/s (timeline: 40 us per MiB), which
+// made the copy stages as slow as the NVLS stage they are supposed to hide behind.
+constexpr int kBulkNB = 8;
+constexpr uint32_t kBulkBytes = 24 * 1024;
+constexpr size_t kPipeSmemBytes = (size_t)kBulkNB * kBulkBytes + 128;   // + mbarriers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// called by ONE thread. `pc` = pieces moved so far by this CTA (selects buffer and mbarrier phase); dst/src 16-byte aligned,
+// bytes a multiple of 16. On return every store has been ISSUED; bulk_copy_drain() waits for them to land.
+__device__ __forceinline__ void bulk_copy(char* dst, const char* src, size_t bytes, uint32_t ring, uint32_t bars, uint32_t& pc) {
+  constexpr int LA = kBulkNB / 2;
+  const size_t P = (bytes + kBulkBytes - 1) / kBulkBytes;
+  for (size_t p = 0; p < P + LA; p++) {
+    if (p >= (size_t)LA) {
+      const size_t q = p - LA;
+      const uint32_t g = pc + (uint32_t)q, sidx = g % kBulkNB;
+      const uint32_t n = (uint32_t)(bytes - q * kBulkBytes < kBulkBytes ? bytes - q * kBulkBytes : kBulkBytes);
+      bulk_mbar_wait(bars + sidx * 8, (g / kBulkNB) & 1u);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + q * kBulkBytes), "r"(ring + sidx * kBulkBytes), "r"(n) : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * blockDim.x;
-      if (i < len) *reinterpret_cast<uint4*>(dst + i * 16) = v[u];
+    if (p < P) {
+      const uint32_t g = pc + (uint32_t)p, sidx = g % kBulkNB;
+      const uint32_t n = (uint32_t)(bytes - p * kBulkBytes < kBulkBytes ? bytes - p * kBulkBytes : kBulkBytes);
+      // the store that last read this buffer is at least kBulkNB - LA groups back
+      asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kBulkNB - LA) : "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bars + sidx * 8), "r"(n) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + sidx * kBulkBytes),
+                   "l"(src + p * kBulkBytes), "r"(n), "r"(bars + sidx * 8)
+                   : "memory");
     }
   }
+  pc += (uint32_t)P;
+}
+__device__ __forceinline__ void bulk_copy_drain() {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");   // async-proxy writes before the generic-proxy flag that publishes them
+}
+
+// copy `len` vectors user -> staging (plain stores into local HBM), 8 loads in flight per thread.
+// The aligned, full-vector case is a separate loop on purpose: user_load()'s byte-wise tail takes the address of its
+// result, which parks the vector in local memory and makes every load wait for the previous one (measured with the
+// in-kernel timeline: 74 us per MiB per CTA = 14 GB/s, the bottleneck of the whole pipeline).
+__device__ __forceinline__ void pipe_copy_in(char* dst, const char* ubase, size_t uvec0, size_t unbytes, bool ualigned, size_t len) {
+  constexpr int U = 4;   // 32 KB in flight per CTA; 8 made the NVLS variants spill (128-register budget of 512-thread CTAs)
+  if (ualigned && (uvec0 + len) * 16 <= unbytes) {
+    const char* src = ubase + uvec0 * 16;
+    for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < len) v[u] = ld_stream_v4(src + i * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < len) *reinterpret_cast<uint4*>(dst + i * 16) = v[u];
+      }
+    }
+    return;
+  }
+  for (size_t i = threadIdx.x; i < len; i += blockDim.x)
+    *reinterpret_cast<uint4*>(dst + i * 16) = user_load(ubase, uvec0 + i, unbytes, ualigned);
 }
 __device__ __forceinline__ void pipe_copy_out(char* ubase, size_t uvec0, size_t unbytes, bool ualigned, const char* src, size_t len) {
-  constexpr int U = 8;
-  for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
-    uint4 v[U];
+  constexpr int U = 4;
+  if (ualigned && (uvec0 + len) * 16 <= unbytes) {
+    char* dst = ubase + uvec0 * 16;
+    for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
+      uint4 v[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * blockDim.x;
-      if (i < len) v[u] = ld_sys_v4(src + i * 16);
-    }
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < len) v[u] = ld_sys_v4(src + i * 16);
+      }
 #pragma unroll
-    for (int u = 0; u < U; u++) {
-      const size_t i = i0 + (size_t)u * blockDim.x;
-      if (i < len) user_store(ubase, uvec0 + i, unbytes, ualigned, v[u]);
+      for (int u = 0; u < U; u++) {
+        const size_t i = i0 + (size_t)u * blockDim.x;
+        if (i < len) *reinterpret_cast<uint4*>(dst + i * 16) = v[u];
+      }
     }
+    return;
   }
+  for (size_t i = threadIdx.x; i < len; i += blockDim.x)
+    user_store(ubase, uvec0 + i, unbytes, ualigned, ld_sys_v4(src + i * 16));
 }
 
 // reduce `lim` vectors that every rank holds at byte offset `off` of its staging region; RESULT: `emit(i, vec)`
@@ -320,6 +390,16 @@ k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
   constexpr bool kUsesRole1 = OP == PIPE_ALLREDUCE || OP == PIPE_REDUCE_SCATTER;
   constexpr bool kUsesRole2 = OP != PIPE_REDUCE_SCATTER;
   const bool idle = (role == 1 && !kUsesRole1) || (role == 2 && !kUsesRole2);
+  // TMA ring of the copy roles (dynamic shared memory: kBulkNB buffers + their mbarriers)
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  const uint32_t ring = smem_u32(pipe_smem), bars = ring + kBulkNB * kBulkBytes;
+  uint32_t pieces = 0;
+  if (role != 1 && threadIdx.x == 0) {
+    for (int b = 0; b < kBulkNB; b++) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bars + b * 8), "r"(1) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
   const int last_role = kUsesRole2 ? 2 : 1;   // the role whose completion means: no rank touches this lane's slots any more
   // Ops whose FIRST action is a store into the peers' staging (allgather, broadcast) must know that every peer has left its
   // previous kernel: the barrier-based staged allreduce ends with a local copy-out from staging after its last barrier.
@@ -330,7 +410,11 @@ k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
     flag_wait_all(a.c, row_entry, base + 1);
   }
 
+  // optional timeline (B200MPI_PIPE_DEBUG): per (role, lane, chunk) the time the CTA started waiting, started working, finished
+  unsigned long long* const dbg = a.dbg ? a.dbg + (((size_t)role * kPipeLanes + lane) * kPipeDbgChunks) * 3 : nullptr;
+#define PIPE_STAMP(k) do { if (dbg && j < (uint32_t)kPipeDbgChunks && threadIdx.x == 0) dbg[j * 3 + (k)] = globaltimer_ns(); } while (0)
   for (uint32_t j = 0; j < n_mine && !idle; j++) {
+    PIPE_STAMP(0);
     const size_t v0 = ((size_t)lane + (size_t)j * L) * Cv;            // first vector of the chunk in the payload
     const size_t len = a.nvec - v0 < Cv ? a.nvec - v0 : Cv;           // vectors in this chunk
     const size_t slot = ((size_t)lane * D + (j % D)) * slot_vecs;     // vector offset of the staging slot
@@ -340,35 +424,65 @@ k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
         if (OP == PIPE_ALLREDUCE) local_wait(a.c, out_done, tgt - D);
         else flag_wait_all(a.c, row_red, tgt - D);
       }
+      PIPE_STAMP(1);
+      const bool bulk = a.in_aligned && (v0 + len) * 16 <= a.nbytes;   // whole chunk 16-byte aligned and inside the payload
       if (OP == PIPE_ALLREDUCE) {
-        pipe_copy_in(mine + slot * 16, a.in, v0, a.nbytes, a.in_aligned, len);
+        if (bulk) {
+          if (threadIdx.x == 0) { bulk_copy(mine + slot * 16, a.in + v0 * 16, len * 16, ring, bars, pieces); bulk_copy_drain(); }
+        } else {
+          pipe_copy_in(mine + slot * 16, a.in, v0, a.nbytes, a.in_aligned, len);
+        }
       } else if (OP == PIPE_REDUCE_SCATTER) {
-        for (int r = 0; r < world; r++)
-          pipe_copy_in(mine + (slot + (size_t)r * Cv) * 16, a.in + (size_t)r * a.ustride, v0, a.nbytes, a.in_aligned, len);
+        if (bulk) {
+          if (threadIdx.x == 0) {
+            for (int r = 0; r < world; r++)
+              bulk_copy(mine + (slot + (size_t)r * Cv) * 16, a.in + (size_t)r * a.ustride + v0 * 16, len * 16, ring, bars, pieces);
+            bulk_copy_drain();
+          }
+        } else {
+          for (int r = 0; r < world; r++)
+            pipe_copy_in(mine + (slot + (size_t)r * Cv) * 16, a.in + (size_t)r * a.ustride, v0, a.nbytes, a.in_aligned, len);
+        }
       } else if (OP == PIPE_ALLGATHER || (OP == PIPE_BROADCAST && rank == a.root)) {
         // push: user chunk -> the same staging offset on every rank; allgather also writes its own output block directly
         const size_t dst = (slot + (OP == PIPE_ALLGATHER ? (size_t)rank * Cv : 0)) * 16;
         constexpr int U = 4;
+        const bool fast_in = a.in_aligned && (v0 + len) * 16 <= a.nbytes;
+        const bool fast_out = a.out_aligned && (v0 + len) * 16 <= a.nbytes;
+        const char* src = a.in + v0 * 16;
+        char* own = OP == PIPE_ALLGATHER ? a.out + (size_t)rank * a.ustride + v0 * 16 : nullptr;
         for (size_t i0 = threadIdx.x; i0 < len; i0 += (size_t)blockDim.x * U) {
           uint4 v[U];
+          if (fast_in) {
 #pragma unroll
-          for (int u = 0; u < U; u++) {
-            const size_t i = i0 + (size_t)u * blockDim.x;
-            if (i < len) v[u] = user_load(a.in, v0 + i, a.nbytes, a.in_aligned);
+            for (int u = 0; u < U; u++) {
+              const size_t i = i0 + (size_t)u * blockDim.x;
+              if (i < len) v[u] = ld_stream_v4(src + i * 16);
+            }
+          } else {
+            for (int u = 0; u < U; u++) {
+              const size_t i = i0 + (size_t)u * blockDim.x;
+              if (i < len) v[u] = user_load(a.in, v0 + i, a.nbytes, a.in_aligned);
+            }
           }
 #pragma unroll
           for (int u = 0; u < U; u++) {
             const size_t i = i0 + (size_t)u * blockDim.x;
             if (i < len) {
               pipe_store_all<MODE, NR>(a, dst + i * 16, v[u]);
-              if (OP == PIPE_ALLGATHER) user_store(a.out + (size_t)rank * a.ustride, v0 + i, a.nbytes, a.out_aligned, v[u]);
+              if (OP == PIPE_ALLGATHER) {
+                if (fast_out) *reinterpret_cast<uint4*>(own + i * 16) = v[u];
+                else user_store(a.out + (size_t)rank * a.ustride, v0 + i, a.nbytes, a.out_aligned, v[u]);
+              }
             }
           }
         }
       }
       flag_signal_all(a.c, row_in, tgt);
+      PIPE_STAMP(2);
     } else if (role == 1) {
       flag_wait_all(a.c, row_in, tgt);
+      PIPE_STAMP(1);
       if (OP == PIPE_ALLREDUCE) {
         const size_t per = (len + world - 1) / world;
         const size_t sb = (size_t)rank * per;
@@ -377,28 +491,58 @@ k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
         pipe_reduce<T, MODE, NR>(a, off, lim, [&](size_t i, const uint4& o) { pipe_store_all<MODE, NR>(a, off + i * 16, o); });
       } else {   // REDUCE_SCATTER: region `rank` of every rank's slot -> my output
         const size_t off = (slot + (size_t)rank * Cv) * 16;
-        pipe_reduce<T, MODE, NR>(a, off, len, [&](size_t i, const uint4& o) { user_store(a.out, v0 + i, a.nbytes, a.out_aligned, o); });
+        if (a.out_aligned && (v0 + len) * 16 <= a.nbytes) {
+          char* const dst = a.out + v0 * 16;
+          pipe_reduce<T, MODE, NR>(a, off, len, [&](size_t i, const uint4& o) { *reinterpret_cast<uint4*>(dst + i * 16) = o; });
+        } else {
+          pipe_reduce<T, MODE, NR>(a, off, len, [&](size_t i, const uint4& o) { user_store(a.out, v0 + i, a.nbytes, a.out_aligned, o); });
+        }
       }
       flag_signal_all(a.c, row_red, tgt);
+      PIPE_STAMP(2);
     } else {
       flag_wait_all(a.c, OP == PIPE_ALLREDUCE ? row_red : row_in, tgt);
+      PIPE_STAMP(1);
+      const bool bulk = a.out_aligned && (v0 + len) * 16 <= a.nbytes;
+      // the slot was filled by remote (generic-proxy) stores observed through the flag acquire: order them before TMA reads
+      if (bulk && threadIdx.x == 0) asm volatile("fence.proxy.async;" ::: "memory");
       if (OP == PIPE_ALLREDUCE) {
-        pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
+        if (bulk) {
+          if (threadIdx.x == 0) { bulk_copy(a.out + v0 * 16, mine + slot * 16, len * 16, ring, bars, pieces); bulk_copy_drain(); }
+        } else {
+          pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
+        }
         __syncthreads();
         if (threadIdx.x == 0) st_release_gpu(out_done, tgt);
       } else {
         if (OP == PIPE_ALLGATHER) {
-          for (int k = 1; k < world; k++) {     // own block was written by role 0
-            const int r = wrap(rank + k, world);
-            pipe_copy_out(a.out + (size_t)r * a.ustride, v0, a.nbytes, a.out_aligned, mine + (slot + (size_t)r * Cv) * 16, len);
+          if (bulk) {
+            if (threadIdx.x == 0) {
+              for (int k = 1; k < world; k++) {     // own block was written by role 0
+                const int r = wrap(rank + k, world);
+                bulk_copy(a.out + (size_t)r * a.ustride + v0 * 16, mine + (slot + (size_t)r * Cv) * 16, len * 16, ring, bars, pieces);
+              }
+              bulk_copy_drain();
+            }
+          } else {
+            for (int k = 1; k < world; k++) {
+              const int r = wrap(rank + k, world);
+              pipe_copy_out(a.out + (size_t)r * a.ustride, v0, a.nbytes, a.out_aligned, mine + (slot + (size_t)r * Cv) * 16, len);
+            }
           }
         } else if (rank != a.root) {
-          pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
+          if (bulk) {
+            if (threadIdx.x == 0) { bulk_copy(a.out + v0 * 16, mine + slot * 16, len * 16, ring, bars, pieces); bulk_copy_drain(); }
+          } else {
+            pipe_copy_out(a.out, v0, a.nbytes, a.out_aligned, mine + slot * 16, len);
+          }
         }
         flag_signal_all(a.c, row_red, tgt);
       }
+      PIPE_STAMP(2);
     }
   }
+#undef PIPE_STAMP
   // Launch-completion handshake: a rank's kernel must not end before EVERY rank has finished with this lane's slots (peers
   // read and write them), otherwise the next launch on this stream - any kernel that uses the staging window, with any
   // slot geometry - could overwrite data a slower peer is still consuming. The last role tells all ranks it is done, role 0
@@ -913,12 +1057,29 @@ cudaError_t launch_allreduce_twoshot(const Launch& l, const KArgs& a, int dtype,
   if (staged) DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, true>, l, a))
   DISPATCH_T(dtype, go(k_allreduce_twoshot<T, MODE_P2P, false>, l, a))
 }
+// launch with the TMA ring as dynamic shared memory (> 48 KB: opt in once per instantiation)
+template <typename K>
+static cudaError_t go_pipe(K kernel, const Launch& l, const KArgs& a) {
+  // K is the same function-pointer type for every instantiation: remember the kernels already opted in by address
+  static const void* done[64];
+  static int ndone = 0;
+  bool seen = false;
+  for (int i = 0; i < ndone; i++) seen = seen || done[i] == (const void*)kernel;
+  if (!seen) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemBytes);
+    if (e != cudaSuccess) return e;
+    if (ndone < 64) done[ndone++] = (const void*)kernel;
+  }
+  dim3 grid(l.blocks, l.emu_world > 0 ? l.emu_world : 1, 1);
+  kernel<<<grid, kThreads, kPipeSmemBytes, l.stream>>>(a, l.emu_world > 0 ? l.emu_args : nullptr);
+  return cudaGetLastError();
+}
 // kind: PIPE_* ; byte-wise kinds (allgather, broadcast) ignore dtype. P2P variants are specialised for world <= 2.
 template <int OP>
 static cudaError_t launch_pipe_t(const Launch& l, const KArgs& a, int dtype, int mode) {
-  if (mode == MODE_NVLS) DISPATCH_T(dtype, go(k_pipe<T, MODE_NVLS, OP, kMaxRanks>, l, a))
-  if (a.c.world <= 2) DISPATCH_T(dtype, go(k_pipe<T, MODE_P2P, OP, 2>, l, a))
-  DISPATCH_T(dtype, go(k_pipe<T, MODE_P2P, OP, kMaxRanks>, l, a))
+  if (mode == MODE_NVLS) DISPATCH_T(dtype, go_pipe(k_pipe<T, MODE_NVLS, OP, kMaxRanks>, l, a))
+  if (a.c.world <= 2) DISPATCH_T(dtype, go_pipe(k_pipe<T, MODE_P2P, OP, 2>, l, a))
+  DISPATCH_T(dtype, go_pipe(k_pipe<T, MODE_P2P, OP, kMaxRanks>, l, a))
 }
 cudaError_t launch_pipe(const Launch& l, const KArgs& a, int kind, int dtype, int mode) {
   switch (kind) {

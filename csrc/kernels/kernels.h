@@ -33,7 +33,9 @@ struct KArgs {
   // pipelined staged allreduce: lanes x {copy-in, reduce, copy-out} CTAs, `depth` staging slots of `per` vectors per lane
   int lanes;
   int depth;
+  unsigned long long* dbg;   // optional timeline: [role 3][lane kPipeLanes][chunk kPipeDbgChunks][3] globaltimer ns
 };
+constexpr int kPipeDbgChunks = 32;
 
 struct Launch {
   cudaStream_t stream;

@@ -151,13 +151,15 @@ struct b200mpi_comm {
   int timeout_ms = 30000;
   // pipelined staged allreduce (user pointers): from pipe_min bytes up; lanes per mode (each lane = 3 CTAs)
   size_t pipe_min = (size_t)8 << 20;
-  int pipe_lanes_nvls = 16, pipe_lanes_p2p = 40, pipe_lanes_wide = 32, pipe_depth = 3;
+  int pipe_lanes_nvls = 32, pipe_lanes_p2p = 40, pipe_lanes_wide = 32, pipe_depth = 3;
+  int pipe_p2p = 0;
   size_t pipe_chunk = (size_t)1 << 20;
   // lazy registration of user buffers (cudaIpc): peer mappings by (rank, allocation id); see reg_exchange()
   size_t reg_min = (size_t)8 << 20;
   int reg_mode = 1;  // 0 off, 1 where it wins (P2P paths: world 2; byte-wise ops), 2 always
   std::map<std::pair<int, unsigned long long>, char*> peer_maps;
   uint64_t reg_hits = 0, reg_opens = 0, reg_refused = 0;
+  unsigned long long* pipe_dbg = nullptr;   // B200MPI_PIPE_DEBUG=1: device timeline buffer of the last k_pipe launch
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
   std::vector<TraceRec> trace;
@@ -435,10 +437,17 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   c->pipe_lanes_p2p = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_P2P", c->pipe_lanes_p2p), kPipeLanes));
   c->pipe_lanes_wide = std::max(1, std::min(env_int("B200MPI_PIPE_LANES_WIDE", c->pipe_lanes_wide), kPipeLanes));
   c->pipe_depth = std::max(2, std::min(env_int("B200MPI_PIPE_DEPTH", c->pipe_depth), 8));
+  c->pipe_p2p = env_int("B200MPI_PIPE_P2P", c->pipe_p2p);
   c->pipe_chunk = std::max((size_t)16 << 10, env_size("B200MPI_PIPE_CHUNK_BYTES", c->pipe_chunk));
+  if (env_int("B200MPI_PIPE_DEBUG", 0) && !c->local) {
+    const size_t n = (size_t)3 * kPipeLanes * kPipeDbgChunks * 3;
+    CUDA_TRY(cudaMalloc((void**)&c->pipe_dbg, n * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemset(c->pipe_dbg, 0, n * sizeof(unsigned long long)));
+  }
   c->reg_min = env_size("B200MPI_REG_MIN_BYTES", c->reg_min);
   c->reg_mode = env_int("B200MPI_REG", c->reg_mode);
-  if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", (size_t)64 << 20);
+  // 16 MiB one-shot region + 144 MiB for the pipelined kernels (48 lanes x 3 slots x 1 MiB)
+  if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", c->local ? (size_t)64 << 20 : (size_t)160 << 20);
   // one-shot region: 2 parities x kOneshotBlocks CTAs x kMaxRanks slots x cap
   c->oneshot_cap_vecs = 2048;  // 32 KiB per slot -> 1 MiB max one-shot payload
   c->oneshot_region = (size_t)2 * kOneshotBlocks * kMaxRanks * c->oneshot_cap_vecs * 16;
@@ -605,6 +614,9 @@ static bool reg_wanted(b200mpi_comm* c, size_t bytes, bool p2p_path) {
 static bool pipe_wanted(b200mpi_comm* c, size_t full_bytes) {
   return full_bytes >= c->pipe_min && !(c->flags & B200MPI_FLAG_NO_PIPE) && c->world > 1;
 }
+// without NVLS the pipelined kernel has to win against the zero-copy registered path (which it does not) and against the
+// barrier-based staged kernel (unmeasured since the copy fix): opt-in until the sweep says otherwise
+static bool pipe_p2p_ok(b200mpi_comm* c) { return c->pipe_p2p || c->local; }
 template <typename Fill>
 static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dtype, size_t nbytes, bool wide,
                    cudaStream_t stream, int algo, Fill&& fill) {
@@ -629,6 +641,7 @@ static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dt
     a.buf = win_region(c, c->stage_win, c->twoshot_off);
     a.nbytes = nbytes; a.nvec = nvec; a.per = cv; a.scale = 1.0f;
     a.lanes = L; a.depth = D;
+    a.dbg = c->pipe_dbg;
     fill(a, ranks[k]);
   }
   return run(c, stream, 3 * L, name, nbytes, algo, args,
@@ -711,7 +724,7 @@ static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const vo
     }
   }
   // staged, large: ONE pipelined kernel (copy-in / reduce / copy-out CTAs chained through flags per lane)
-  if (pipe_wanted(c, nbytes))
+  if (pipe_wanted(c, nbytes) && (mode == MODE_NVLS || pipe_p2p_ok(c)))
     return pipe_op(c, "allreduce_pipe", PIPE_ALLREDUCE, mode, dtype, nbytes, false, stream, algo, [&](KArgs& a, int r) {
       a.in = in_ptr(c, in, r);
       a.out = out_ptr(c, out, r);
@@ -875,6 +888,7 @@ int b200mpi_comm_destroy(b200mpi_comm_t c) {
   for (int r = 0; r < kMaxRanks; r++) if (c->epoch[r]) cudaFree(c->epoch[r]);
   if (c->emu_ring) cudaFree(c->emu_ring);
   if (c->p2p_cnt) cudaFree(c->p2p_cnt);
+  if (c->pipe_dbg) cudaFree(c->pipe_dbg);
   if (c->err_host) cudaFreeHost(c->err_host);
   c->rv.detach(c->rank == 0);
   delete c;
@@ -993,7 +1007,7 @@ int b200mpi_broadcast_bytes(b200mpi_comm_t c, void* buf, size_t bytes, int root,
                  [&](const Launch& l, const KArgs& a) { return launch_broadcast_sym(l, a, MODE_P2P); });
     }
   }
-  if (pipe_wanted(c, bytes))
+  if (pipe_wanted(c, bytes) && (mode == MODE_NVLS || pipe_p2p_ok(c)))
     return pipe_op(c, "broadcast_pipe", PIPE_BROADCAST, mode, DT_F32, bytes, false, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
                    [&](KArgs& a, int r) {
                      a.root = root;
@@ -1028,7 +1042,7 @@ int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count,
                  [&](const Launch& l, const KArgs& a) { return launch_allgather_sym(l, a, MODE_P2P); });
     }
   }
-  if (pipe_wanted(c, total * c->world)) {
+  if (pipe_wanted(c, total * c->world) && (c->multicast || pipe_p2p_ok(c))) {
     const int mode = c->multicast ? MODE_NVLS : MODE_P2P;
     return pipe_op(c, "allgather_pipe", PIPE_ALLGATHER, mode, DT_F32, total, true, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
                    [&](KArgs& a, int r) {
@@ -1072,7 +1086,7 @@ int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t c
                  [&](const Launch& l, const KArgs& a) { return launch_reduce_scatter_sym(l, a, dtype, MODE_P2P); });
     }
   }
-  if (pipe_wanted(c, total * c->world)) {
+  if (pipe_wanted(c, total * c->world) && (rs_nvls || pipe_p2p_ok(c))) {
     const int mode = rs_nvls ? MODE_NVLS : MODE_P2P;
     return pipe_op(c, "reduce_scatter_pipe", PIPE_REDUCE_SCATTER, mode, dtype, total, true, (cudaStream_t)stream, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT,
                    [&](KArgs& a, int r) {
@@ -1179,11 +1193,21 @@ int b200mpi_get_tuning(b200mpi_comm_t c, size_t* oneshot_max, size_t* nvls_min, 
 int b200mpi_set_pipe(b200mpi_comm_t c, size_t min_bytes, int lanes_nvls, int lanes_p2p, int depth, size_t chunk_bytes) {
   if (min_bytes != (size_t)-1) c->pipe_min = min_bytes;
   if (lanes_nvls > 0) c->pipe_lanes_nvls = std::min(lanes_nvls, kPipeLanes);
-  if (lanes_p2p > 0) c->pipe_lanes_p2p = std::min(lanes_p2p, kPipeLanes);
+  if (lanes_p2p > 0) { c->pipe_lanes_p2p = std::min(lanes_p2p, kPipeLanes); c->pipe_p2p = 1; }
   if (lanes_nvls > 0 && lanes_p2p > 0) c->pipe_lanes_wide = std::min(std::max(lanes_nvls, lanes_p2p), kPipeLanes);
   if (depth > 0) c->pipe_depth = std::max(2, std::min(depth, 8));
   if (chunk_bytes > 0) c->pipe_chunk = std::max((size_t)16 << 10, chunk_bytes);
   return 0;
+}
+// Timeline of the last pipelined launch (needs B200MPI_PIPE_DEBUG=1 at creation): out[role][lane][chunk][3] in ns
+// relative to the earliest stamp; returns the number of u64 written (0 when disabled).
+size_t b200mpi_pipe_timeline(b200mpi_comm_t c, unsigned long long* out, size_t cap) {
+  const size_t n = (size_t)3 * kPipeLanes * kPipeDbgChunks * 3;
+  if (!c->pipe_dbg || cap < n) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out, c->pipe_dbg, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaMemset(c->pipe_dbg, 0, n * sizeof(unsigned long long));
+  return n;
 }
 int b200mpi_set_reg(b200mpi_comm_t c, int mode, size_t min_bytes) {
   if (mode >= 0) c->reg_mode = mode;

@@ -9,13 +9,10 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")))
-
 import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from mpi_operator_b200.models import build_model
 
 
 def main():
@@ -30,7 +27,8 @@ def main():
     torch.cuda.set_device(dev)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     torch.backends.cudnn.benchmark = True
-    model = build_model(a.model).cuda().to(memory_format=torch.channels_last)
+    import torchvision   # stock model definition: this script is what a user of torch DDP already has
+    model = getattr(torchvision.models, a.model)(weights=None).cuda().to(memory_format=torch.channels_last)
     ddp = nn.parallel.DistributedDataParallel(model, device_ids=[dev], gradient_as_bucket_view=True)
     opt = torch.optim.SGD(ddp.parameters(), lr=0.01 * world, momentum=0.9)
     x = torch.randn(a.batch_size, 3, 224, 224, device="cuda").contiguous(memory_format=torch.channels_last)

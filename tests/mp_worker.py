@@ -113,6 +113,124 @@ def main():
     comm.barrier()
     torch.cuda.synchronize()
     comm.check_error()
+
+    # ---- user-pointer paths on REAL peers: pipelined kernels (NVLS where bound), cudaIpc-registered zero-copy kernels ----
+    def check(name, ok):
+        nonlocal fails
+        if not ok:
+            print(f"[rank {R}] {name} FAILED", flush=True)
+            fails += 1
+
+    for label, pipe_min, reg_mode in (("pipe", 0, 0), ("reg", 1 << 62, 2), ("auto", 8 << 20, 1)):
+        comm.set_pipe(min_bytes=pipe_min, chunk_bytes=256 << 10)
+        comm.set_reg(reg_mode, 0 if reg_mode == 2 else (8 << 20))
+        for it, n in enumerate((1 << 20, 3 * (1 << 20) + 8, 12 * (1 << 20))):
+            for dtype in (torch.float32, torch.bfloat16):
+                xs = [gen(40 + it, n, dtype, r) for r in range(W)]
+                want = torch.stack([x.float() for x in xs]).mean(0)
+                out = torch.empty_like(xs[R])
+                comm.allreduce(xs[R], out, op="avg")                       # out of place
+                inp = xs[R].clone()
+                comm.allreduce(inp, inp, op="avg")                         # in place
+                torch.cuda.synchronize()
+                comm.check_error()
+                tol = 1e-5 if dtype == torch.float32 else 3e-2
+                for o in (out, inp):
+                    check(f"{label} allreduce {dtype} n={n}", (o.float() - want).abs().max().item() <= tol * max(1.0, want.abs().max().item()))
+            x = gen(50 + it, n, torch.float32, R)
+            ag = torch.empty(W * n, device="cuda")
+            comm.allgather(x, ag)
+            full = gen(60 + it, W * n, torch.float32, R)
+            rs = torch.empty(n, device="cuda")
+            comm.reduce_scatter(full, rs)
+            b = gen(70 + it, n, torch.float32, R)
+            comm.broadcast(b, root=it % W)
+            torch.cuda.synchronize()
+            comm.check_error()
+            check(f"{label} allgather n={n}", torch.equal(ag, torch.cat([gen(50 + it, n, torch.float32, r) for r in range(W)])))
+            rs_want = torch.stack([gen(60 + it, W * n, torch.float32, r) for r in range(W)]).sum(0)[R * n:(R + 1) * n]
+            check(f"{label} reduce_scatter n={n}", torch.allclose(rs, rs_want, atol=1e-4 * W))
+            check(f"{label} broadcast n={n}", torch.equal(b, gen(70 + it, n, torch.float32, it % W)))
+    if R == 0:
+        print(f"[mp_worker] stats={[(o['op'], o['algo'], o['calls']) for o in comm.stats(native_only=True)['ops']]} reg={comm.reg_stats()}", flush=True)
+    comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20)
+    comm.set_reg(1, 8 << 20)
+
+    # ---- zero-copy window forms on real peers ----
+    per = 1 << 18
+    w2 = comm.alloc_window(W * per * 4)
+    v = w2.tensor(torch.float32, numel=W * per)
+    v.fill_(-1.0)
+    v[R * per:(R + 1) * per].copy_(gen(80, per, torch.float32, R))
+    torch.cuda.synchronize()
+    comm.allgather_window(w2, 0, per * 4)
+    torch.cuda.synchronize()
+    check("allgather_window", torch.equal(v, torch.cat([gen(80, per, torch.float32, r) for r in range(W)])))
+    v.copy_(gen(81, W * per, torch.float32, R))
+    torch.cuda.synchronize()
+    comm.reduce_scatter_window(w2, 0, per, torch.float32, op="sum")
+    torch.cuda.synchronize()
+    rs_want = torch.stack([gen(81, W * per, torch.float32, r) for r in range(W)]).sum(0)[R * per:(R + 1) * per]
+    check("reduce_scatter_window", torch.allclose(v[R * per:(R + 1) * per], rs_want, atol=1e-4 * W))
+    v.fill_(float(R))
+    torch.cuda.synchronize()
+    comm.broadcast_window(w2, 0, W * per * 4, root=W - 1)
+    torch.cuda.synchronize()
+    comm.check_error()
+    check("broadcast_window", torch.equal(v, torch.full_like(v, float(W - 1))))
+
+    # ---- stress: STRESS_ITERS back-to-back allreduces of random sizes 4 B .. 8 MiB on integer-valued data
+    # (fp32 sums are exact in any order, so every result must be bit-exact), random algorithm per call incl. NVLS, the
+    # pipelined kernel and the fused allreduce+SGD kernel, check_error() every 100 calls ----
+    iters = int(os.environ.get("B200MPI_STRESS_ITERS", "10000"))
+    g = torch.Generator().manual_seed(1234)          # same sequence on every rank
+    big = 2 * 1024 * 1024                              # elements (8 MiB fp32)
+    base = [(gen(90, big, torch.float32, r) * 4).round() for r in range(W)]
+    total = torch.stack(base).sum(0)
+    swin = comm.alloc_window(big * 4)
+    sv = swin.tensor(torch.float32, numel=big)
+    pwin2 = comm.alloc_window(big * 4)
+    spv = pwin2.tensor(torch.float32, numel=big)
+    smom = torch.zeros(comm.slice_elems(big, torch.float32), device="cuda")
+    kinds = ["oneshot", "twoshot", "auto", "pipe", "window"] + (["nvls"] if comm.has_multicast else []) + ["sgd"]
+    bad = 0
+    for i in range(iters):
+        # log-uniform size, in elements; window / sgd kinds need 16-byte multiples
+        n = int(2 ** (torch.rand((), generator=g).item() * 21)) if i % 50 else big
+        n = max(1, min(big, n))
+        kind = kinds[int(torch.randint(0, len(kinds), (), generator=g))]
+        if kind == "oneshot" and n * 4 > (1 << 20):
+            kind = "twoshot"
+        if kind in ("window", "nvls", "sgd"):
+            n = max(8, n // 8 * 8)
+            sv[:n].copy_(base[R][:n])
+            if kind == "sgd":     # p = 0 - lr * (scale * sum) with lr = scale = 1, no momentum: parameters = -sum, exact
+                spv[:n].zero_()
+                comm.allreduce_sgd_window(swin, 0, pwin2, 0, smom, n, torch.float32, lr=1.0, momentum_coef=0.0, first_step=True,
+                                          scale=1.0)
+                ok = torch.equal(spv[:n], -total[:n])
+            else:
+                comm.allreduce_window(swin, 0, n, torch.float32, op="sum", algo="nvls" if kind == "nvls" else "auto")
+                ok = torch.equal(sv[:n], total[:n])
+        else:
+            x = base[R][:n].clone()
+            if kind == "pipe":
+                comm.set_pipe(min_bytes=0, chunk_bytes=64 << 10)
+                comm.allreduce(x, x, algo="twoshot")
+                comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20)
+            else:
+                comm.allreduce(x, x, algo=kind)
+            ok = torch.equal(x, total[:n])
+        if not ok:
+            bad += 1
+            if bad <= 3:
+                print(f"[rank {R}] stress iteration {i}: kind={kind} n={n} mismatch", flush=True)
+        if i % 100 == 99:
+            torch.cuda.synchronize()
+            comm.check_error()
+    torch.cuda.synchronize()
+    comm.check_error()
+    check(f"stress ({iters} iterations, {bad} mismatches)", bad == 0)
     comm.host_barrier()
     print(f"[rank {R}] mp_worker done, failures={fails}", flush=True)
     comm.destroy()
