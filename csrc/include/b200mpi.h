@@ -118,6 +118,19 @@ void* b200mpi_window_mc_ptr(b200mpi_comm_t comm, int win);
 size_t b200mpi_window_size(b200mpi_comm_t comm, int win);
 
 /*
+ * Exportable device allocations and windows built around them (what the NCCL-ABI shim's ncclMemAlloc /
+ * ncclCommRegister map to): b200mpi_mem_alloc returns VMM memory of the current device that can be exported and bound
+ * to a multicast object; b200mpi_window_adopt (COLLECTIVE: every rank passes its own allocation of the same size, in the
+ * same order) maps the peers' allocations and binds them to an NVLS multicast object, after which the buffer is a
+ * symmetric window: b200mpi_allreduce_sym & co. run zero-copy on it. b200mpi_mem_lookup: 1 if `p` lies in such an
+ * allocation (base / size returned).
+ */
+int b200mpi_mem_alloc(size_t bytes, void** ptr);
+int b200mpi_mem_free(void* ptr);
+int b200mpi_mem_lookup(const void* p, void** base, size_t* size);
+int b200mpi_window_adopt(b200mpi_comm_t comm, void* base, int* win);
+
+/*
  * In-place allreduce on a symmetric window region [offset, offset+count*esz).
  * out = scale * reduce_over_ranks(in). `scale` is fused into the reduction
  * (1/world for Horovod's Average; reference call site: examples/v2beta1/

@@ -55,12 +55,13 @@ struct Shim {
   int rank = 0, world = 1, device = 0;
   std::string id;
   int splits = 0;
+  std::map<void*, int> registered;   // base of an ncclMemAlloc allocation -> adopted b200mpi window
 };
 
 std::mutex g_mu;
 std::map<int, float> g_premul;  // dynamic ncclRedOp_t -> scalar
 int g_next_op = 16;
-std::atomic<uint64_t> g_calls{0}, g_forwarded{0};
+std::atomic<uint64_t> g_calls{0}, g_forwarded{0}, g_registered{0};
 thread_local std::string g_last_error;
 thread_local int g_group_depth = 0;
 thread_local int g_group_fwd = 0;
@@ -288,6 +289,7 @@ extern "C" {
 // exported for tests / stats
 uint64_t b200mpi_shim_calls(void) { return g_calls.load(); }
 uint64_t b200mpi_shim_forwarded(void) { return g_forwarded.load(); }
+uint64_t b200mpi_shim_registered(void) { return g_registered.load(); }   // ncclMemAlloc buffers adopted as NVLS windows
 
 ncclResult_t ncclGetVersion(int* v) {
   if (forward_all() || g_in_real > 0 || g_forwarded.load()) {
@@ -655,24 +657,50 @@ ncclResult_t ncclRecv(void* buf, size_t count, ncclDataType_t dt, int peer, nccl
 // Real NCCL's allocations are VMM handles it later retains / registers: when a real communicator can be involved the
 // allocation must come from the real library (a cudaMalloc pointer makes its registration path fail with "invalid argument").
 static bool real_nccl_in_play() { return forward_all() || g_in_real > 0 || g_forwarded.load() > 0; }
+// ncclMemAlloc hands out exportable VMM memory (b200mpi_mem_alloc); ncclCommRegister on such a buffer is COLLECTIVE here
+// (every rank registers its allocation of the same size, in the same order - what torch's MemPool registration and NCCL's
+// own symmetric registration require as well): the runtime maps the peers' allocations and binds them to an NVLS multicast
+// object, and from then on collectives on tensors inside it (>= B200MPI_REG_MIN_BYTES, agreed per call through the shm
+// rendezvous) run zero-copy on the window: multimem.ld_reduce / multimem.st straight on the user's memory.
+// Buffers that did not come from ncclMemAlloc need no registration: cudaIpc registration is lazy (see reg_exchange).
 ncclResult_t ncclMemAlloc(void** ptr, size_t size) {
   if (real_nccl_in_play()) { if (auto f = REAL(ncclMemAlloc, void**, size_t)) return f(ptr, size); }
+  if (!ptr) return err(ncclInvalidArgument, "ncclMemAlloc: null pointer");
+  if (b200mpi_mem_alloc(size, ptr) == 0) return ncclSuccess;
   return cudaMalloc(ptr, size) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemAlloc");
 }
 ncclResult_t ncclMemFree(void* ptr) {
   if (real_nccl_in_play()) { if (auto f = REAL(ncclMemFree, void*)) return f(ptr); }
+  if (!ptr) return ncclSuccess;
+  void* base = nullptr;
+  if (b200mpi_mem_lookup(ptr, &base, nullptr) && base == ptr) return from_rc(b200mpi_mem_free(ptr), "ncclMemFree");
   return cudaFree(ptr) == cudaSuccess ? ncclSuccess : err(ncclUnhandledCudaError, "ncclMemFree");
 }
 ncclResult_t ncclCommRegister(const ncclComm_t c, void* buff, size_t size, void** handle) {
   Shim* s = S(c);
   if (s->real) { auto f = REAL(ncclCommRegister, ncclComm_t, void*, size_t, void**); return f(s->real, buff, size, handle); }
-  if (handle) *handle = nullptr;  // unregistered buffers go through the staging window inside the kernel
+  if (handle) *handle = nullptr;
+  void* base = nullptr;
+  if (!s->mine || !b200mpi_mem_lookup(buff, &base, nullptr)) return ncclSuccess;   // lazily registered on first large use
+  auto it = s->registered.find(base);
+  int win = -1;
+  if (it == s->registered.end()) {
+    if (b200mpi_window_adopt(s->mine, base, &win) != 0) {
+      if (debug()) fprintf(stderr, "[b200mpi nccl shim] ncclCommRegister: %s (buffer stays usable through the staged paths)\n", b200mpi_last_error());
+      return ncclSuccess;
+    }
+    s->registered[base] = win;
+    g_registered++;
+  } else {
+    win = it->second;
+  }
+  if (handle) *handle = reinterpret_cast<void*>((intptr_t)(win + 1));
   return ncclSuccess;
 }
 ncclResult_t ncclCommDeregister(const ncclComm_t c, void* handle) {
   Shim* s = S(c);
   if (s->real) { auto f = REAL(ncclCommDeregister, ncclComm_t, void*); return f(s->real, handle); }
-  return ncclSuccess;
+  return ncclSuccess;   // windows are released with the communicator (freeing one is a collective, deregistration is not)
 }
 ncclResult_t ncclCommWindowRegister(ncclComm_t c, void* buff, size_t size, void** win, int flags) {
   Shim* s = S(c);

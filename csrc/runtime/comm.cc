@@ -113,6 +113,7 @@ struct Window {
   CUmemGenericAllocationHandle h[kMaxRanks] = {};     // vmm handles (own + imported)
   char* mc = nullptr;
   CUmemGenericAllocationHandle mch = 0;
+  bool adopted = false;   // own copy belongs to b200mpi_mem_alloc (ncclMemAlloc): never unmapped / released with the window
 };
 
 struct TraceRec { const char* op; size_t bytes; int algo; int blocks; uint64_t t_ns; };
@@ -159,6 +160,7 @@ struct b200mpi_comm {
   int reg_mode = 1;  // 0 off, 1 where it wins (P2P paths: world 2; byte-wise ops), 2 always
   std::map<std::pair<int, unsigned long long>, char*> peer_maps;
   uint64_t reg_hits = 0, reg_opens = 0, reg_refused = 0;
+  int n_adopted = 0;   // windows built around b200mpi_mem_alloc allocations (collective count: same on every rank)
   unsigned long long* pipe_dbg = nullptr;   // B200MPI_PIPE_DEBUG=1: device timeline buffer of the last k_pipe launch
   std::atomic<uint64_t> launches{0};
   bool trace_on = false;
@@ -271,7 +273,9 @@ static int window_alloc_ipc(b200mpi_comm* c, Window& W, size_t bytes) {
   return 0;
 }
 
-static int window_alloc_vmm(b200mpi_comm* c, Window& W, size_t bytes, bool want_mc) {
+// `own`: an existing exportable VMM allocation of this rank to build the window around (b200mpi_window_adopt), or nullptr
+struct OwnAlloc { CUmemGenericAllocationHandle h; char* ptr; size_t mapped; };
+static int window_alloc_vmm(b200mpi_comm* c, Window& W, size_t bytes, bool want_mc, const OwnAlloc* own = nullptr) {
   Driver& d = driver();
   std::string err;
   CUmemAllocationProp prop;
@@ -294,11 +298,17 @@ static int window_alloc_vmm(b200mpi_comm* c, Window& W, size_t bytes, bool want_
   W.bytes = bytes;
   W.mapped = round_up(bytes, gran);
   W.vmm = true;
+  if (own) {
+    if (own->mapped % gran) want_mc = false;   // not a multiple of the multicast granularity: peer mappings only
+    W.mapped = own->mapped;
+    W.adopted = true;
+  }
   mprop.size = W.mapped;
   const uint32_t tag = c->next_tag;
   c->next_tag += 2;
 
-  CU_TRY(d.cuMemCreate_(&W.h[c->rank], W.mapped, &prop, 0));
+  if (own) W.h[c->rank] = own->h;
+  else CU_TRY(d.cuMemCreate_(&W.h[c->rank], W.mapped, &prop, 0));
   int myfd = -1;
   CU_TRY(d.cuMemExportToShareableHandle_(&myfd, W.h[c->rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0));
   for (int r = 0; r < c->world; r++)
@@ -319,16 +329,25 @@ static int window_alloc_vmm(b200mpi_comm* c, Window& W, size_t bytes, bool want_
   acc.location.id = c->device;
   acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
   for (int r = 0; r < c->world; r++) {
+    if (own && r == c->rank) { W.ptr[r] = own->ptr; continue; }   // already mapped by b200mpi_mem_alloc
     CUdeviceptr va = 0;
     CU_TRY(d.cuMemAddressReserve_(&va, W.mapped, gran, 0, 0));
     CU_TRY(d.cuMemMap_(va, W.mapped, 0, W.h[r], 0));
     CU_TRY(d.cuMemSetAccess_(va, W.mapped, &acc, 1));
     W.ptr[r] = reinterpret_cast<char*>(va);
   }
-  CUDA_TRY(cudaMemset(W.ptr[c->rank], 0, W.mapped));
+  if (!own) CUDA_TRY(cudaMemset(W.ptr[c->rank], 0, W.mapped));
   CUDA_TRY(cudaDeviceSynchronize());
 
   // NVLS: rank 0 creates the multicast object, everyone adds its device and binds its memory.
+  if (own) {   // adopted allocations: every rank must bring the same size, and all must still want multicast
+    struct { size_t mapped; int mc; } me{W.mapped, want_mc ? 1 : 0}, all[kMaxRanks];
+    if (c->rv.allgather(&me, all, sizeof(me), c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err);
+    for (int r = 0; r < c->world; r++) {
+      if (all[r].mapped != W.mapped) return fail(B200MPI_ERR_INVALID, "window_adopt: ranks registered allocations of different sizes");
+      if (!all[r].mc) want_mc = false;
+    }
+  }
   int mc_ok = want_mc ? 1 : 0;
   if (want_mc) {
     int mcfd = -1;
@@ -406,6 +425,7 @@ static void window_release(b200mpi_comm* c, Window& W) {
     }
     if (W.mch) d.cuMemRelease_(W.mch);
     for (int r = 0; r < c->world; r++) {
+      if (W.adopted && r == c->rank) continue;   // belongs to b200mpi_mem_alloc / b200mpi_mem_free
       if (W.ptr[r]) { d.cuMemUnmap_((CUdeviceptr)W.ptr[r], W.mapped); d.cuMemAddressFree_((CUdeviceptr)W.ptr[r], W.mapped); }
       if (W.h[r]) d.cuMemRelease_(W.h[r]);
     }
@@ -557,29 +577,55 @@ struct RegRec {   // one per rank per eligible call; must stay <= kRvScratch (25
   unsigned long long id[2];
   unsigned long long off[2];
   cudaIpcMemHandle_t h[2];
-  int ok;
-  int pad;
+  int ok;          // both buffers exportable through cudaIpc
+  int win;         // adopted (ncclCommRegister'ed) window that contains BOTH buffers, or -1
+  unsigned long long woff[2];   // their offsets inside it
 };
 static_assert(sizeof(RegRec) <= kRvScratch, "RegRec must fit the rendezvous scratch slot");
 
-// Collective (host). bufs[0] = input, bufs[1] = output (may be equal, may be null when a role has none on this rank —
-// then pass the other one twice). On success wins[k].p[r] = rank r's bufs[k] mapped in this process.
-static bool reg_exchange(b200mpi_comm* c, const void* in, void* out, size_t in_bytes, size_t out_bytes, Win* win_in, Win* win_out) {
+static int adopted_window_of(b200mpi_comm* c, const void* p, size_t bytes, size_t* off) {
+  for (size_t i = 0; i < c->wins.size(); i++) {
+    const Window& W = c->wins[i];
+    if (!W.live || !W.adopted) continue;
+    const char* b = W.ptr[c->rank];
+    if ((const char*)p >= b && (const char*)p + bytes <= b + W.mapped) { *off = (size_t)((const char*)p - b); return (int)i; }
+  }
+  return -1;
+}
+
+// Collective (host). On REG_IPC wins[k].p[r] = rank r's buffer k mapped in this process; on REG_SYM both buffers of
+// every rank sit at the same offsets of the same adopted window (*sym_win, sym_off[2]).
+enum { REG_NONE = 0, REG_IPC = 1, REG_SYM = 2 };
+static int reg_exchange(b200mpi_comm* c, const void* in, void* out, size_t in_bytes, size_t out_bytes, bool want_ipc, Win* win_in,
+                        Win* win_out, int* sym_win = nullptr, size_t* sym_off = nullptr) {
   RegRec mine;
   memset(&mine, 0, sizeof(mine));
   LocalSeg sg[2];
   size_t off[2] = {0, 0};
   const void* ptr[2] = {in, out};
   const size_t nb[2] = {in_bytes, out_bytes};
-  mine.ok = 1;
-  for (int k = 0; k < 2; k++) {
+  mine.win = -1;
+  if (c->n_adopted > 0 && sym_win) {
+    size_t o0 = 0, o1 = 0;
+    const int w0 = adopted_window_of(c, in, in_bytes, &o0), w1 = adopted_window_of(c, out, out_bytes, &o1);
+    if (w0 >= 0 && w0 == w1 && o0 % 16 == 0 && o1 % 16 == 0) { mine.win = w0; mine.woff[0] = o0; mine.woff[1] = o1; }
+  }
+  mine.ok = want_ipc ? 1 : 0;
+  for (int k = 0; k < 2 && mine.ok; k++) {
     if (!aligned16(ptr[k]) || !local_seg(ptr[k], nb[k], &sg[k], &off[k])) { mine.ok = 0; break; }
     mine.id[k] = sg[k].id; mine.off[k] = off[k]; mine.h[k] = sg[k].h;
   }
   std::vector<RegRec> all(c->world);
   std::string err;
-  if (c->rv.allgather(&mine, all.data(), sizeof(RegRec), c->timeout_ms, &err)) return false;
-  for (auto& r : all) if (!r.ok) { c->reg_refused++; return false; }
+  if (c->rv.allgather(&mine, all.data(), sizeof(RegRec), c->timeout_ms, &err)) return REG_NONE;
+  bool sym = mine.win >= 0;
+  for (auto& r : all) sym = sym && r.win == mine.win && r.woff[0] == mine.woff[0] && r.woff[1] == mine.woff[1];
+  if (sym) {
+    *sym_win = mine.win; sym_off[0] = mine.woff[0]; sym_off[1] = mine.woff[1];
+    c->reg_hits++;
+    return REG_SYM;
+  }
+  for (auto& r : all) if (!r.ok) { c->reg_refused += want_ipc ? 1 : 0; return REG_NONE; }
   Win* wins[2] = {win_in, win_out};
   bool ok = true;
   for (int k = 0; k < 2 && ok; k++) {
@@ -600,10 +646,10 @@ static bool reg_exchange(b200mpi_comm* c, const void* in, void* out, size_t in_b
   // a failed open on one rank must send everybody to the staged path: second (tiny) agreement round
   int good = ok ? 1 : 0;
   std::vector<int> goods(c->world);
-  if (c->rv.allgather(&good, goods.data(), sizeof(int), c->timeout_ms, &err)) return false;
-  for (int g : goods) if (!g) { c->reg_refused++; return false; }
+  if (c->rv.allgather(&good, goods.data(), sizeof(int), c->timeout_ms, &err)) return REG_NONE;
+  for (int g : goods) if (!g) { c->reg_refused++; return REG_NONE; }
   c->reg_hits++;
-  return true;
+  return REG_IPC;
 }
 static bool reg_wanted(b200mpi_comm* c, size_t bytes, bool p2p_path) {
   if (c->local || c->world < 2 || c->reg_mode == 0 || bytes < c->reg_min) return false;
@@ -707,9 +753,15 @@ static int do_allreduce(b200mpi_comm* c, bool sym, int win, size_t off, const vo
                [&](const Launch& l, const KArgs& a) { return launch_allreduce_twoshot(l, a, dtype, mode, false); });
   }
   // large, P2P path: register the user buffers (cudaIpc) and run the zero-copy two-shot straight on them
-  if (nbytes % 16 == 0 && reg_wanted(c, nbytes, mode == MODE_P2P)) {
+  const bool ipc_ok = reg_wanted(c, nbytes, mode == MODE_P2P);
+  if (nbytes % 16 == 0 && !c->local && nbytes >= c->reg_min && (ipc_ok || c->n_adopted > 0)) {
     Win win_in, win_out;
-    if (reg_exchange(c, in, out, nbytes, nbytes, &win_in, &win_out)) {
+    int sw = -1;
+    size_t so[2] = {0, 0};
+    const int kind = reg_exchange(c, in, out, nbytes, nbytes, ipc_ok, &win_in, &win_out, &sw, so);
+    if (kind == REG_SYM && so[0] == so[1])   // registered (ncclMemAlloc + ncclCommRegister) and in place: zero-copy NVLS on the window
+      return do_allreduce(c, true, sw, so[0], nullptr, nullptr, count, dtype, op, scale, B200MPI_ALGO_AUTO, stream);
+    if (kind == REG_IPC) {
       const size_t nvec = nbytes / 16;
       const size_t per = (nvec + c->world - 1) / c->world;
       const int blocks = blocks_for(c, per, 2, c->max_blocks);
@@ -805,6 +857,66 @@ static int sym_op(b200mpi_comm* c, const char* name, int win, size_t off, size_t
     fill(a, ranks[k]);
   }
   return run(c, stream, blocks, name, nbytes, mode == MODE_NVLS ? B200MPI_ALGO_NVLS : B200MPI_ALGO_TWOSHOT, args, launcher);
+}
+
+// ---- exportable allocations (the shim's ncclMemAlloc) and windows built around them (ncclCommRegister) ----------------
+struct MemAlloc { CUmemGenericAllocationHandle h; size_t mapped; int device; };
+static std::mutex g_mem_mu;
+static std::map<char*, MemAlloc> g_mem;   // by base pointer
+
+static int mem_alloc(size_t bytes, void** out) {
+  Driver& d = driver();
+  if (!d.ok) return fail(B200MPI_ERR_UNSUPPORTED, "mem_alloc: CUDA VMM driver entry points unavailable");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUmemAllocationProp prop;
+  memset(&prop, 0, sizeof(prop));
+  prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+  prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  prop.location.id = dev;
+  prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  size_t gran = 0;
+  CU_TRY(d.cuMemGetAllocationGranularity_(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED));
+  CUmulticastObjectProp mprop;   // round to the multicast granularity of a full box so the allocation can be bound later
+  memset(&mprop, 0, sizeof(mprop));
+  mprop.numDevices = 2;
+  mprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+  mprop.size = round_up(bytes, gran);
+  size_t mg = 0;
+  if (d.cuMulticastGetGranularity_(&mg, &mprop, CU_MULTICAST_GRANULARITY_MINIMUM) == CUDA_SUCCESS && mg > gran) gran = mg;
+  MemAlloc m;
+  m.mapped = round_up(bytes ? bytes : 1, gran);
+  m.device = dev;
+  CU_TRY(d.cuMemCreate_(&m.h, m.mapped, &prop, 0));
+  CUdeviceptr va = 0;
+  CUresult r = d.cuMemAddressReserve_(&va, m.mapped, gran, 0, 0);
+  if (r == CUDA_SUCCESS) r = d.cuMemMap_(va, m.mapped, 0, m.h, 0);
+  CUmemAccessDesc acc;
+  acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+  acc.location.id = dev;
+  acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+  if (r == CUDA_SUCCESS) r = d.cuMemSetAccess_(va, m.mapped, &acc, 1);
+  if (r != CUDA_SUCCESS) { d.cuMemRelease_(m.h); return fail(B200MPI_ERR_CUDA, "mem_alloc: " + cu_err(r)); }
+  std::lock_guard<std::mutex> l(g_mem_mu);
+  g_mem[(char*)va] = m;
+  *out = (void*)va;
+  return 0;
+}
+static int mem_free(void* p) {
+  MemAlloc m;
+  {
+    std::lock_guard<std::mutex> l(g_mem_mu);
+    auto it = g_mem.find((char*)p);
+    if (it == g_mem.end()) return fail(B200MPI_ERR_INVALID, "mem_free: not a b200mpi_mem_alloc pointer");
+    m = it->second;
+    g_mem.erase(it);
+  }
+  Driver& d = driver();
+  cudaDeviceSynchronize();
+  d.cuMemUnmap_((CUdeviceptr)p, m.mapped);
+  d.cuMemAddressFree_((CUdeviceptr)p, m.mapped);
+  d.cuMemRelease_(m.h);
+  return 0;
 }
 
 }  // namespace b200mpi
@@ -923,6 +1035,7 @@ int b200mpi_window_free(b200mpi_comm_t c, int win) {
   if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return fail(B200MPI_ERR_INVALID, "window_free: bad window");
   cudaDeviceSynchronize();
   if (!c->local) { std::string err; if (c->rv.barrier(c->timeout_ms, &err)) return fail(B200MPI_ERR_SYS, err); }
+  if (c->wins[win].adopted && c->n_adopted > 0) c->n_adopted--;
   window_release(c, c->wins[win]);
   return 0;
 }
@@ -939,6 +1052,41 @@ void* b200mpi_window_mc_ptr(b200mpi_comm_t c, int win) {
 size_t b200mpi_window_size(b200mpi_comm_t c, int win) {
   if (win < 0 || win >= (int)c->wins.size() || !c->wins[win].live) return 0;
   return c->wins[win].bytes;
+}
+
+int b200mpi_mem_alloc(size_t bytes, void** ptr) { return mem_alloc(bytes, ptr); }
+int b200mpi_mem_free(void* ptr) { return mem_free(ptr); }
+int b200mpi_mem_lookup(const void* p, void** base, size_t* size) {
+  std::lock_guard<std::mutex> l(g_mem_mu);
+  auto it = g_mem.upper_bound((char*)const_cast<void*>(p));
+  if (it == g_mem.begin()) return 0;
+  --it;
+  if ((const char*)p >= it->first + it->second.mapped) return 0;
+  if (base) *base = it->first;
+  if (size) *size = it->second.mapped;
+  return 1;
+}
+int b200mpi_window_adopt(b200mpi_comm_t c, void* base, int* win) {
+  if (c->local || !c->vmm) return fail(B200MPI_ERR_UNSUPPORTED, "window_adopt: needs a multi-process communicator with VMM fd export");
+  MemAlloc m;
+  {
+    std::lock_guard<std::mutex> l(g_mem_mu);
+    auto it = g_mem.find((char*)base);
+    if (it == g_mem.end()) return fail(B200MPI_ERR_INVALID, "window_adopt: not the base of a b200mpi_mem_alloc allocation");
+    m = it->second;
+  }
+  if (m.device != c->device) return fail(B200MPI_ERR_INVALID, "window_adopt: allocation lives on another device");
+  int id = -1;
+  for (size_t i = 0; i < c->wins.size(); i++) if (!c->wins[i].live) { id = (int)i; break; }
+  if (id < 0) { c->wins.emplace_back(); id = (int)c->wins.size() - 1; }
+  Window W;
+  OwnAlloc own{m.h, (char*)base, m.mapped};
+  int rc = window_alloc_vmm(c, W, m.mapped, c->multicast, &own);
+  if (rc) return rc;
+  c->wins[id] = W;
+  c->n_adopted++;
+  *win = id;
+  return 0;
 }
 
 int b200mpi_allreduce_sym(b200mpi_comm_t c, int win, size_t offset, size_t count, b200mpi_dtype_t dtype,
@@ -994,9 +1142,14 @@ int b200mpi_set_hyper_ptr(b200mpi_comm_t c, const float* p) { c->hyper = p; retu
 int b200mpi_broadcast_bytes(b200mpi_comm_t c, void* buf, size_t bytes, int root, void* stream) {
   if (root < 0 || root >= c->world) return fail(B200MPI_ERR_INVALID, "broadcast: bad root");
   const int mode = c->multicast ? MODE_NVLS : MODE_P2P;
-  if (bytes % 16 == 0 && reg_wanted(c, bytes, mode == MODE_P2P || c->world == 2)) {   // zero-copy: root stores into the peers' buffers
+  const bool bc_ipc = reg_wanted(c, bytes, mode == MODE_P2P || c->world == 2);
+  if (bytes % 16 == 0 && !c->local && bytes >= c->reg_min && (bc_ipc || c->n_adopted > 0)) {   // zero-copy: root stores into the peers' buffers
     Win w, w2;
-    if (reg_exchange(c, buf, buf, bytes, bytes, &w, &w2)) {
+    int sw = -1;
+    size_t so[2] = {0, 0};
+    const int kind = reg_exchange(c, buf, buf, bytes, bytes, bc_ipc, &w, &w2, &sw, so);
+    if (kind == REG_SYM) return b200mpi_broadcast_sym(c, sw, so[0], bytes, root, stream);
+    if (kind == REG_IPC) {
       std::vector<KArgs> args(1);
       KArgs& a = args[0];
       memset(&a, 0, sizeof(a));
@@ -1030,7 +1183,7 @@ int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count,
   const size_t total = count * esize(dtype);
   if (total % 16 == 0 && reg_wanted(c, total * c->world, true)) {   // zero-copy: every rank stores its block into every output
     Win win_in, win_out;
-    if (reg_exchange(c, in, out, total, total * c->world, &win_in, &win_out)) {
+    if (reg_exchange(c, in, out, total, total * c->world, true, &win_in, &win_out) == REG_IPC) {
       std::vector<KArgs> args(1);
       KArgs& a = args[0];
       memset(&a, 0, sizeof(a));
@@ -1074,7 +1227,7 @@ int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t c
   const bool rs_nvls = c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32);
   if (total % 16 == 0 && reg_wanted(c, total * c->world, !rs_nvls)) {   // zero-copy: pull the owned block from every input
     Win win_in, win_out;
-    if (reg_exchange(c, in, out, total * c->world, total, &win_in, &win_out)) {
+    if (reg_exchange(c, in, out, total * c->world, total, true, &win_in, &win_out) == REG_IPC) {
       std::vector<KArgs> args(1);
       KArgs& a = args[0];
       memset(&a, 0, sizeof(a));

@@ -596,9 +596,11 @@ class NodeAgent:
         # torch.distributed scripts then resolve ncclAllReduce & co. to b200mpi kernels. B200MPI_ALGO=nccl
         # (or B200MPI_INJECT=0) is the baseline mode: same launcher, stock NCCL.
         shim = os.path.join(PKG_DIR, "lib", "libb200mpi_nccl.so")
-        # Opt-in for now (pod env B200MPI_INJECT=1): validated with torch DDP on 2 GPUs (22 collectives on b200mpi
-        # kernels, 0 forwarded); the 8-GPU DDP job still fails and is being debugged.
-        if (os.path.exists(shim) and env.get("B200MPI_ALGO", "") != "nccl" and env.get("B200MPI_INJECT", "0") == "1"
+        # On by default (round 2: unmodified torch DDP under the shim passes at 2, 4 and 8 GPUs, tests/test_multigpu.py);
+        # B200MPI_INJECT=0 or B200MPI_ALGO=nccl in the launcher env is the baseline mode (same launcher, stock NCCL).
+        # A box without GPUs has nothing to inject into (CPU MPIJobs such as examples/pi): there the default is off.
+        default_inject = "1" if self.topology.gpu_count > 0 else "0"
+        if (os.path.exists(shim) and env.get("B200MPI_ALGO", "") != "nccl" and env.get("B200MPI_INJECT", default_inject) != "0"
                 and "B200MPI_INJECT_LIB" not in env):
             env["B200MPI_INJECT_LIB"] = shim
         gpus = (M.meta(pod).get("annotations") or {}).get(GPU_ANNOTATION, "")

@@ -72,11 +72,20 @@ class FlatModelState:
         off = 0
         cur = Bucket(0, 0, 0)
         cap = max(bucket_bytes // 4, 1)
+        # The LAST bucket (the earliest layers) is the one whose allreduce+SGD cannot hide behind backward: keep it small
+        # (B200MPI_TAIL_BUCKET_BYTES, default 4 MiB) so the exposed tail of the step is one short kernel.
+        tail_cap = max(int(os.environ.get("B200MPI_TAIL_BUCKET_BYTES", 4 << 20)) // 4, 1)
+        pad = 64 if bf16_params else 4
+        remaining = sum(_align(p.numel(), pad) for p in order)
+        tail_started = False
         for p in order:
             # keep every tensor 16-byte aligned; with a bf16 shadow, 64 elements so the bf16 views handed to
             # cuDNN start on 128-byte boundaries as well
-            n = _align(p.numel(), 64 if bf16_params else 4)
-            if cur.params and cur.numel + n > cap:
+            n = _align(p.numel(), pad)
+            start_tail = bool((not tail_started) and len(cur.params) > 0 and remaining <= tail_cap and remaining < cap)
+            tail_started = tail_started or start_tail
+            remaining -= n
+            if cur.params and (cur.numel + n > cap or start_tail):
                 cur.numel = _align(cur.numel, 8)
                 off = cur.start + cur.numel
                 self.buckets.append(cur)

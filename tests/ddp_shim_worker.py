@@ -67,16 +67,40 @@ def main():
         ropt.step()
     for p, q in zip(model.parameters(), ref.parameters()):
         fails += int(not torch.allclose(p, q, rtol=1e-4, atol=1e-5))
+    # registered buffers: ncclMemAlloc (torch MemPool over the backend's allocator) + ncclCommRegister (register_mem_pool).
+    # Under the shim the pool's segment becomes an NVLS-bound symmetric window and large in-place collectives run zero-copy.
+    reg_note = "skipped"
+    try:
+        backend = dist.group.WORLD._get_backend(torch.device("cuda", dev))
+        pool = torch.cuda.MemPool(backend.mem_allocator)
+        with torch.cuda.use_mem_pool(pool):
+            big = torch.empty(6 * 1024 * 1024, device="cuda")           # 24 MiB: above B200MPI_REG_MIN_BYTES
+        backend.register_mem_pool(pool)
+        for it in range(2):
+            big.fill_(float(rank + 1 + it))
+            dist.all_reduce(big)
+            want = sum(float(r + 1 + it) for r in range(world))
+            fails += int(not torch.equal(big, torch.full_like(big, want)))
+        small = big[:1000]
+        small.fill_(1.0)
+        dist.all_reduce(small)                                            # small tensors in the pool: ordinary paths
+        fails += int(not torch.equal(small, torch.full_like(small, float(world))))
+        dist.broadcast(big, src=world - 1)
+        torch.cuda.synchronize()
+        reg_note = "ok"
+    except (AttributeError, RuntimeError, TypeError) as e:   # torch build without MemPool / mem_allocator
+        reg_note = f"unavailable ({type(e).__name__}: {str(e)[:80]})"
     torch.cuda.synchronize()
     injected = "b200mpi" in os.environ.get("LD_PRELOAD", "")
     calls = fwd = -1
     if injected:
         lib = ctypes.CDLL(os.environ["LD_PRELOAD"].split(":")[0])
-        lib.b200mpi_shim_calls.restype = lib.b200mpi_shim_forwarded.restype = ctypes.c_uint64
+        lib.b200mpi_shim_calls.restype = lib.b200mpi_shim_forwarded.restype = lib.b200mpi_shim_registered.restype = ctypes.c_uint64
         calls, fwd = lib.b200mpi_shim_calls(), lib.b200mpi_shim_forwarded()
+        reg_note += f", windows adopted={lib.b200mpi_shim_registered()}"
         if os.environ.get("B200MPI_ALGO") != "nccl":
             fails += int(calls == 0 or fwd != 0)  # our kernels ran, nothing fell through to real NCCL
-    print(f"[rank {rank}] ddp_shim_worker failures={fails} shim_calls={calls} forwarded={fwd}", flush=True)
+    print(f"[rank {rank}] ddp_shim_worker failures={fails} shim_calls={calls} forwarded={fwd} registered-buffers: {reg_note}", flush=True)
     dist.destroy_process_group()
     sys.exit(1 if fails else 0)
 

@@ -409,6 +409,15 @@ def test_collective_runtime_is_ld_injected_into_ranks(op):
     wait_for(lambda: conds(get(op, base)).get("Succeeded") == "True", what="Succeeded")
     launcher = [p for p in op.store.list("pods", "default") if "noinject-launcher" in p["metadata"]["name"]][0]
     assert "preload=[]" in op.agent.logs("default", launcher["metadata"]["name"])
+    # default: on when the box has GPUs (this fixture has fake ones), off with B200MPI_INJECT=0
+    for name, env, want in (("dflt", [], f"preload=[{shim}]"), ("optout", [{"name": "B200MPI_INJECT", "value": "0"}], "preload=[]")):
+        j = new_mpijob(name, workers=1, launcher_cmd=("mpirun",), launcher_args=("-np", "1", "sh", "-c", "echo preload=[$LD_PRELOAD]"),
+                       worker_cmd=("/usr/sbin/sshd",))
+        j.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = env
+        submit(op, j)
+        wait_for(lambda: conds(get(op, j)).get("Succeeded") == "True", what="Succeeded")
+        launcher = [p for p in op.store.list("pods", "default") if f"{name}-launcher" in p["metadata"]["name"]][0]
+        assert want in op.agent.logs("default", launcher["metadata"]["name"])
 
 
 def test_daemon_restart_reaps_lost_processes_and_recovers(tmp_path):
