@@ -36,7 +36,7 @@ def main():
     ap.add_argument("--data_name", default="imagenet")
     ap.add_argument("--device", default="gpu")
     ap.add_argument("--num_gpus", type=int, default=1)
-    ap.add_argument("--b200_engine", default="fused", choices=["fused", "hvd", "nccl"],
+    ap.add_argument("--b200_engine", default=os.environ.get("B200MPI_ENGINE", "fused"), choices=["fused", "hvd", "nccl"],
                     help="fused: symmetric-window grads + fused allreduce+SGD kernel in a CUDA graph; "
                          "hvd: hvd.DistributedOptimizer API path; nccl: stock NCCL baseline")
     ap.add_argument("--b200_compute_dtype", default="bf16", choices=["bf16", "fp32"])

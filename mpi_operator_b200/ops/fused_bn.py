@@ -158,10 +158,11 @@ def bn_act(bn: torch.nn.BatchNorm2d, x: torch.Tensor, residual: torch.Tensor = N
 
 # --------------------------------------------------------------------------------------------------------------
 # 1x1 convolution + BatchNorm(+residual)+ReLU with the BN statistics taken in the GEMM epilogue
-# (csrc/kernels/gemm_bnstats.cu: TMA + tcgen05 + TMEM). EXPERIMENTAL, opt-in with B200MPI_FUSED_CONV1X1=1: the GEMM
-# kernel has not run on hardware yet. Forward = 3 launches (GEMM+stats, finalize, apply) instead of conv + 3;
-# backward = the fused BN backward kernels + two library GEMMs (dgrad, wgrad).
-_CONV1X1 = os.environ.get("B200MPI_FUSED_CONV1X1", "0") == "1"
+# (csrc/kernels/gemm_bnstats.cu: TMA + tcgen05 + TMEM). On by default since round 2 (numerics: tests/test_zz_gemm_bnstats_gpu.py
+# on a B200; ResNet-101 step 14.15 -> 13.75 ms, profiles/r2); B200MPI_FUSED_CONV1X1=0 keeps cuDNN for the 1x1 convolutions.
+# Forward = 3 launches (GEMM+stats, finalize, apply) instead of conv + 3; backward = the fused BN backward kernels + two
+# library GEMMs (dgrad, wgrad).
+_CONV1X1 = os.environ.get("B200MPI_FUSED_CONV1X1", "1") == "1"
 
 
 def _conv1x1_eligible(conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, x: torch.Tensor) -> bool:
