@@ -83,7 +83,7 @@ lint:
 	python -m compileall -q mpi_operator_b200 tests bench.py __graft_entry__.py
 
 sanitize: all
-	compute-sanitizer --tool racecheck python tools/profile_kernels.py
+	tools/sanitize.sh
 
 # Host-side runtime under the compiler sanitizers: launcher, shm rendezvous, libmpi shim.
 SAN_CXX  ?= /usr/bin/g++

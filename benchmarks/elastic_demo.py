@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--total-steps", type=int, default=400)
     ap.add_argument("--step-sleep", type=float, default=0.02)
     ap.add_argument("--out", default="")
+    ap.add_argument("--inplace", action="store_true",
+                    help="B200MPI_ELASTIC_INPLACE=1: mpirun spawns only the additional ranks and survivors re-form the communicator in place")
     a = ap.parse_args()
     sizes = [int(v) for v in a.sizes.split(",")]
     import torch
@@ -42,8 +44,9 @@ def main():
                              launcher_args=("python", os.path.join(ROOT, "examples/horovod/elastic_mnist.py"), "--total-steps", str(a.total_steps),
                                             "--commit-every", "5", "--step-sleep", str(a.step_sleep), "--checkpoint", os.path.join(d, "ckpt.pt")))
             c0 = job.spec.replica("Launcher").template["spec"]["containers"][0]
+            c0["env"] = [{"name": "B200MPI_ELASTIC_INPLACE", "value": "1"}] if a.inplace else []
             if cpu:
-                c0["env"] = [{"name": "B200MPI_HVD_DEVICE", "value": "cpu"}]
+                c0["env"].append({"name": "B200MPI_HVD_DEVICE", "value": "cpu"})
             else:
                 job.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 1}}
             c = op.clientset.kubeflow_v2beta1().mpijobs("default")
@@ -79,7 +82,9 @@ def main():
             t_done = wait(lambda: conds(c.get("elastic")).get("Succeeded") == "True", "job success", timeout=600)
             text = logs()
             restarts = [ln for ln in text.splitlines() if "(re)started at step" in ln]
-            out = {"backend": "cpu (libmpi shim)" if cpu else "gpu (b200mpi)", "sizes": sizes, "phases": phases,
+            reformed = [ln.split("re-formed in place: ")[1] for ln in text.splitlines() if "re-formed in place" in ln]
+            out = {"backend": "cpu (libmpi shim)" if cpu else "gpu (b200mpi)", "mode": "in place" if a.inplace else "restart", "sizes": sizes,
+                   "phases": phases, "survivor_reform": reformed,
                    "total_seconds": round(t_done - t_create, 2), "resumed_from_steps": [int(ln.split("step ")[1].split()[0]) for ln in restarts],
                    "worlds_seen": text.split("world sizes seen: ")[-1].strip().splitlines()[0] if "world sizes seen" in text else None}
             print(json.dumps(out))

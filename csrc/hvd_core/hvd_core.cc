@@ -1170,7 +1170,13 @@ int hvdcore_init(const char* job_id, int rank, int world, const hvdcore_gpu_t* g
     e->gpu = *gpu;
     e->has_gpu = true;
   }
-  std::string name = std::string(job_id && *job_id ? job_id : "default") + "-hvd";
+  // A process that re-initialises under the SAME job id (hvd.shutdown(); hvd.init()) needs a fresh segment name, and every
+  // rank does that the same number of times. An elastic world re-formed in place carries its generation in the job id
+  // itself (survivors re-initialise, newcomers initialise for the first time): a new id restarts the private counter.
+  static std::string last_job;
+  const std::string jid = job_id && *job_id ? job_id : "default";
+  if (jid != last_job) { g_generation = 0; last_job = jid; }
+  std::string name = jid + "-hvd";
   if (g_generation) name += "-g" + std::to_string(g_generation);
   std::string err;
   const int init_timeout = (int)env_d("B200MPI_INIT_TIMEOUT_MS", env_d("B200MPI_TIMEOUT_MS", 60000));

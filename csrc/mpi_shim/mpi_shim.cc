@@ -173,6 +173,15 @@ int MPI_Finalize(void) {
   g_final = true;
   return MPI_SUCCESS;
 }
+// Elastic rescale in place (hvd.elastic with B200MPI_ELASTIC_DIR): leave the current world (every rank of it calls this or
+// MPI_Finalize) and join the one the environment now describes (B200MPI_RANK / B200MPI_WORLD_SIZE / B200MPI_JOB_ID).
+// Not MPI: the standard forbids a second MPI_Init, the Horovod front-end needs exactly that.
+extern "C" int b200mpi_mpi_reinit(void) {
+  if (g_init && !g_final) MPI_Finalize();
+  g_init = false;
+  g_final = false;
+  return MPI_Init(nullptr, nullptr);
+}
 int MPI_Abort(MPI_Comm, int code) {
   if (g_rv) g_rv->set_abort();
   fprintf(stderr, "[libmpi b200mpi rank %d] MPI_Abort(%d)\n", g_rank, code);

@@ -41,6 +41,7 @@ struct Rank {
   pid_t pid = -1;
   int pidfd = -1, out = -1, err = -1;
   bool exited = false;
+  bool retired = false;   // elastic scale-down: this rank is expected to leave; its exit is not a failure
   int status = 0;
   std::string obuf, ebuf;
 };
@@ -399,7 +400,30 @@ int main(int argc, char** argv) {
   // On one box the whole job is a single NVSwitch node: LOCAL_RANK == RANK indexes
   // the job's GPU list.
   const bool single_node_view = !cvd.empty() || getenv("B200MPI_SINGLE_NODE_VIEW");
-  for (auto& rk : ranks) {
+  // ---- elastic rescale in place (B200MPI_ELASTIC_INPLACE=1): this launcher watches discover_hosts.sh itself; see the
+  // supervise loop. Ranks learn the world from <elastic_dir>/world = "<generation> <world size>".
+  const bool elastic = getenv("B200MPI_ELASTIC_INPLACE") && atoi(getenv("B200MPI_ELASTIC_INPLACE")) != 0 && apps.size() == 1;
+  std::string elastic_dir, discover_path;
+  int generation = 0, world_now = np;
+  if (elastic) {
+    elastic_dir = std::string(getenv("B200MPI_POD_DIR") ? getenv("B200MPI_POD_DIR") : "/tmp") + "/b200mpi-elastic-" + std::to_string((long)getpid());
+    mkdir(elastic_dir.c_str(), 0755);
+    if (const char* dp = getenv("B200MPI_DISCOVER_HOSTS")) discover_path = dp;
+    else {
+      std::string root = getenv("B200MPI_POD_ROOTFS") ? getenv("B200MPI_POD_ROOTFS") : "";
+      discover_path = root + "/etc/mpi/discover_hosts.sh";
+      if (access(discover_path.c_str(), R_OK) != 0) discover_path = "/etc/mpi/discover_hosts.sh";
+    }
+  }
+  auto publish_world = [&](int gen, int world) {
+    const std::string tmp = elastic_dir + "/world.tmp", fin = elastic_dir + "/world";
+    if (FILE* f = fopen(tmp.c_str(), "w")) { fprintf(f, "%d %d\n", gen, world); fclose(f); rename(tmp.c_str(), fin.c_str()); }
+  };
+  if (elastic) publish_world(0, np);
+
+  // spawn one rank into a world of `world` ranks (generation `gen`; join: it enters a RUNNING elastic job)
+  auto spawn_rank = [&](Rank& rk, int world, int gen, bool join) {
+    const int np = world;   // everything below describes the world this rank is born into
     int po[2], pe[2];
     if (pipe2(po, O_CLOEXEC) || pipe2(pe, O_CLOEXEC)) die(std::string("pipe: ") + strerror(errno));
     pid_t pid = fork();
@@ -412,12 +436,17 @@ int main(int argc, char** argv) {
       signal(SIGINT, SIG_DFL);
       signal(SIGTERM, SIG_DFL);
       const int lrank = single_node_view ? rk.rank : rk.local_rank;
-      const int lsize = single_node_view ? np : local_size[rk.node];
+      const int lsize = single_node_view ? np : local_size[std::min((size_t)rk.node, local_size.size() - 1)];
       const int node = single_node_view ? 0 : rk.node;
       auto set = [](const char* k, const std::string& v) { setenv(k, v.c_str(), 1); };
       auto seti = [&](const char* k, int v) { set(k, std::to_string(v)); };
       for (auto& kv : xenv) set(kv.first.c_str(), kv.second);
       set("B200MPI_JOB_ID", job_id);
+      if (elastic) {
+        set("B200MPI_ELASTIC_DIR", elastic_dir);
+        seti("B200MPI_GENERATION", gen);
+        if (join) set("B200MPI_ELASTIC_JOIN", "1");
+      }
       seti("B200MPI_RANK", rk.rank); seti("B200MPI_WORLD_SIZE", np);
       seti("B200MPI_LOCAL_RANK", lrank); seti("B200MPI_LOCAL_SIZE", lsize);
       seti("OMPI_COMM_WORLD_RANK", rk.rank); seti("OMPI_COMM_WORLD_SIZE", np);
@@ -433,7 +462,7 @@ int main(int argc, char** argv) {
       set("K_MPI_JOB_ROLE", "worker");
       set("B200MPI_HOSTNAME", short_host(rk.host));
       set("HOSTNAME", short_host(rk.host));
-      if (!cvd.empty()) {
+      if (!cvd.empty() && rk.rank < (int)job_gpus.size()) {
         set("CUDA_VISIBLE_DEVICES", cvd);
         seti("B200MPI_GPU", job_gpus[rk.rank]);
         unsetenv("NVIDIA_VISIBLE_DEVICES");
@@ -469,7 +498,8 @@ int main(int argc, char** argv) {
     fcntl(pe[0], F_SETFL, O_NONBLOCK);
     rk.pid = pid; rk.out = po[0]; rk.err = pe[0];
     rk.pidfd = (int)syscall(SYS_pidfd_open, pid, 0);  // -1 on old kernels: waitpid polling below still works
-  }
+  };
+  for (auto& rk : ranks) spawn_rank(rk, np, 0, false);
 
   // ---- fault injection from outside the ranks (mpi_operator_b200/utils/fault.py documents the grammar):
   // B200MPI_FAULT="kill_rank:R@time:SECONDS[;once]" — SIGKILL rank R's process group SECONDS after spawn.
@@ -496,7 +526,89 @@ int main(int argc, char** argv) {
   auto kill_all = [&](int sig) {
     for (auto& rk : ranks) if (!rk.exited && rk.pid > 0) kill(-rk.pid, sig);
   };
+  // elastic state: `target` = world size discover_hosts.sh currently describes; a grow first spawns the new ranks, waits for
+  // their ready files (python + torch imported, about to join) and only then publishes the world, so the survivors keep
+  // training on the old world while the newcomers boot.
+  int el_target = np, el_stable = 0, el_pending_world = 0;
+  time_t el_pending_since = 0;
+  struct timespec el_last = ts0;
+  auto discover_world = [&]() -> int {
+    FILE* f = fopen(discover_path.c_str(), "r");
+    if (!f) return -1;
+    char line[1024];
+    int hosts_n = 0;
+    while (fgets(line, sizeof(line), f)) if (strncmp(line, "echo ", 5) == 0) hosts_n++;
+    fclose(f);
+    return hosts_n * default_slots;
+  };
   while (alive > 0 || std::any_of(ranks.begin(), ranks.end(), [](const Rank& r) { return r.out >= 0 || r.err >= 0; })) {
+    if (elastic && !killing && alive > 0) {
+      struct timespec tn; clock_gettime(CLOCK_MONOTONIC, &tn);
+      if ((tn.tv_sec - el_last.tv_sec) + (tn.tv_nsec - el_last.tv_nsec) * 1e-9 >= 0.25) {
+        el_last = tn;
+        if (el_pending_world == 0) {
+          const int w = discover_world();
+          if (w > 0 && w != world_now) {
+            if (w == el_target) el_stable++; else { el_target = w; el_stable = 0; }
+            if (el_stable >= 2) {   // the same new world for three consecutive reads (the controller rewrites the file pod by pod)
+              generation++;
+              el_pending_world = w;
+              el_pending_since = time(nullptr);
+              if (w > world_now) {
+                // GPU map of the larger world, then the additional ranks
+                auto slots2 = read_slots_file(getenv("B200MPI_SLOTS_FILE"));
+                if (!slots2.empty() && !cvd.empty()) {
+                  std::vector<int> g2;
+                  std::vector<std::string> names;
+                  for (auto& kv : slots2) names.push_back(kv.first);
+                  // keep the survivors' order: known hosts first (hostfile order), new hosts after them in name order
+                  for (auto& h : hosts) { auto it = slots2.find(short_host(h.name)); if (it != slots2.end()) g2.insert(g2.end(), it->second.begin(), it->second.end()); }
+                  for (auto& nme : names) {
+                    bool known = false;
+                    for (auto& h : hosts) known = known || short_host(h.name) == nme;
+                    if (!known) { g2.insert(g2.end(), slots2[nme].begin(), slots2[nme].end()); hosts.push_back({nme, default_slots}); }
+                  }
+                  if ((int)g2.size() >= w) {
+                    job_gpus = g2;
+                    cvd.clear();
+                    for (int k = 0; k < w; k++) cvd += (k ? "," : "") + std::to_string(job_gpus[k]);
+                  }
+                }
+                const int first_new = (int)ranks.size();
+                for (int r = first_new; r < w; r++) {
+                  Rank nr;
+                  nr.rank = r; nr.local_rank = r; nr.node = 0; nr.host = r < (int)hosts.size() ? hosts[r].name : (hosts.empty() ? "localhost" : hosts.back().name);
+                  ranks.push_back(nr);
+                }
+                for (int r = first_new; r < w; r++) { spawn_rank(ranks[r], w, generation, true); alive++; }
+                fprintf(stderr, "mpirun (b200mpi): elastic: world %d -> %d, generation %d: spawned %d ranks, waiting until they are ready\n",
+                        world_now, w, generation, w - first_new);
+              } else {
+                for (auto& rk : ranks) if (rk.rank >= w) rk.retired = true;
+                publish_world(generation, w);
+                fprintf(stderr, "mpirun (b200mpi): elastic: world %d -> %d, generation %d: ranks >= %d retire at their next commit\n",
+                        world_now, w, generation, w);
+                world_now = w;
+                el_pending_world = 0;
+              }
+            }
+          } else if (w == world_now) { el_target = w; el_stable = 0; }
+        } else {
+          // grow in progress: publish once every newcomer has announced itself (or after 120 s regardless)
+          bool all_ready = true;
+          for (int r = world_now; r < el_pending_world; r++) {
+            const std::string rf = elastic_dir + "/ready." + std::to_string(generation) + "." + std::to_string(r);
+            all_ready = all_ready && access(rf.c_str(), F_OK) == 0;
+          }
+          if (all_ready || time(nullptr) - el_pending_since > 120) {
+            publish_world(generation, el_pending_world);
+            fprintf(stderr, "mpirun (b200mpi): elastic: generation %d published (%d ranks)\n", generation, el_pending_world);
+            world_now = el_pending_world;
+            el_pending_world = 0;
+          }
+        }
+      }
+    }
     std::vector<pollfd> pf;
     for (auto& rk : ranks) {
       if (rk.out >= 0) pf.push_back({rk.out, POLLIN, 0});
@@ -524,7 +636,8 @@ int main(int argc, char** argv) {
         if (w == rk.pid) {
           rk.exited = true; rk.status = st; alive--;
           if (rk.pidfd >= 0) { close(rk.pidfd); rk.pidfd = -1; }
-          const bool bad = !(WIFEXITED(st) && WEXITSTATUS(st) == 0);
+          bool bad = !(WIFEXITED(st) && WEXITSTATUS(st) == 0);
+          if (rk.retired && WIFEXITED(st) && WEXITSTATUS(st) == 75) bad = false;   // left with the rescale code after a scale-down
           if (bad && first_fail_rank < 0 && !killing) { first_fail_rank = rk.rank; first_fail_status = st; }
         }
       }

@@ -29,7 +29,7 @@ from .exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F40
 
 Average, Sum, Adasum, Min, Max = "average", "sum", "adasum", "min", "max"
 
-_state = {"comm": None, "info": None, "engine": None}
+_state = {"comm": None, "info": None, "engine": None, "optimizers": []}
 
 
 class HorovodNotInitialized(RuntimeError):
@@ -40,6 +40,29 @@ def _comm():
     if _state["comm"] is None:
         raise HorovodNotInitialized("hvd.init() has not been called")
     return _state["comm"]
+
+
+def _elastic_generation() -> int:
+    return int(os.environ.get("B200MPI_GENERATION", "0") or 0)
+
+
+def _job_id(info) -> str:
+    """Rendezvous key of the CURRENT incarnation of the world: the launcher's job id, plus the elastic generation when the
+    world is being re-formed in place (survivors and newly spawned ranks meet under the new key)."""
+    g = _elastic_generation()
+    return info.job_id + (f"-g{g}" if g else "")
+
+
+def _announce_ready() -> None:
+    """Ranks spawned into a running elastic job tell the launcher they are about to join (imports done): only then does it
+    publish the new world to the survivors, which keep training on the old one in the meantime."""
+    d, g = os.environ.get("B200MPI_ELASTIC_DIR"), _elastic_generation()
+    if d and g and os.environ.get("B200MPI_ELASTIC_JOIN") == "1":
+        try:
+            with open(os.path.join(d, f"ready.{g}.{os.environ.get('B200MPI_RANK', '0')}"), "w") as f:
+                f.write("ready\n")
+        except OSError:
+            pass
 
 
 def init(comm=None) -> None:
@@ -53,16 +76,69 @@ def init(comm=None) -> None:
     if comm is not None:
         _state["comm"] = comm
         return
+    _announce_ready()
+    if _elastic_generation() and not os.environ.get("B200MPI_TIMEOUT_MS"):
+        os.environ.setdefault("B200MPI_INIT_TIMEOUT_MS", "180000")   # survivors join at their next commit, not immediately
     if not torch.cuda.is_available() or os.environ.get("B200MPI_HVD_DEVICE", "") == "cpu":
         # CPU job (the reference's Horovod MNIST example runs on CPU workers): collectives over the libmpi shim
         from .host_backend import HostCommunicator
-        _state["comm"] = HostCommunicator()
+        if _elastic_generation():
+            os.environ["B200MPI_JOB_ID"] = _job_id(info)     # the libmpi shim reads the key from the environment
+            os.environ.setdefault("B200MPI_TIMEOUT_MS", "180000")
+        try:
+            _state["comm"] = HostCommunicator()
+        finally:
+            os.environ["B200MPI_JOB_ID"] = info.job_id
         _start_engine(info, None)
         return
     dev = info.local_rank % torch.cuda.device_count()
     torch.cuda.set_device(dev)
-    _state["comm"] = Communicator.create(info.rank, info.world_size, dev, info.job_id)
+    _state["comm"] = Communicator.create(info.rank, info.world_size, dev, _job_id(info))
     _start_engine(info, dev)
+
+
+def _reinit(world: int, generation: int) -> None:
+    """Elastic rescale IN PLACE: this (surviving) rank leaves the old world and joins generation `generation` with `world`
+    ranks, keeping its process, its CUDA context and its model. Optimizers built by ``DistributedOptimizer`` re-home their
+    gradient windows into the new communicator."""
+    opts = [o for o in (r() for r in _state.get("optimizers", [])) if o is not None]
+    for o in opts:
+        o._detach()
+    base_job = _state["info"].job_id if _state.get("info") else rank_info_from_env().job_id
+    base_job = os.environ.get("B200MPI_BASE_JOB_ID", base_job)
+    os.environ.setdefault("B200MPI_BASE_JOB_ID", base_job)
+    e = _state["engine"]
+    if e is not None:
+        _state["engine"] = None
+        e.shutdown()
+    c = _state["comm"]
+    for k in ("B200MPI_WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "WORLD_SIZE", "HOROVOD_SIZE", "B200MPI_LOCAL_SIZE",
+              "OMPI_COMM_WORLD_LOCAL_SIZE", "MPI_LOCALNRANKS", "LOCAL_WORLD_SIZE", "HOROVOD_LOCAL_SIZE"):
+        if k in os.environ:
+            os.environ[k] = str(world)
+    os.environ["B200MPI_GENERATION"] = str(generation)
+    os.environ["B200MPI_JOB_ID"] = base_job
+    os.environ.pop("B200MPI_ELASTIC_JOIN", None)
+    if not os.environ.get("B200MPI_TIMEOUT_MS_USER"):
+        os.environ.setdefault("B200MPI_INIT_TIMEOUT_MS", "180000")
+    info = rank_info_from_env()
+    _state["info"] = info
+    if hasattr(c, "reinit"):          # host backend: the libmpi shim re-attaches under the new key
+        os.environ["B200MPI_JOB_ID"] = _job_id(info)
+        os.environ.setdefault("B200MPI_TIMEOUT_MS", "180000")
+        c.reinit()
+        os.environ["B200MPI_JOB_ID"] = base_job
+        _start_engine(info, None)
+    else:
+        import torch
+        from ..runtime.comm import Communicator
+        torch.cuda.synchronize()
+        dev = c.device
+        c.destroy()
+        _state["comm"] = Communicator.create(info.rank, info.world_size, dev, _job_id(info))
+        _start_engine(info, dev)
+    for o in opts:
+        o._attach()
 
 
 _atexit_registered = False
@@ -80,8 +156,8 @@ def _start_engine(info, dev) -> None:
     gcomm = None
     if dev is not None:
         from ..runtime.comm import Communicator
-        gcomm = Communicator.create(info.rank, info.world_size, dev, info.job_id + "-hvdgpu")
-    _state["engine"] = Engine(info.job_id, info.rank, info.world_size, gcomm)
+        gcomm = Communicator.create(info.rank, info.world_size, dev, _job_id(info) + "-hvdgpu")
+    _state["engine"] = Engine(_job_id(info), info.rank, info.world_size, gcomm)
     if not _atexit_registered:   # a script that forgets hvd.shutdown() must not leave its peers negotiating with a ghost
         import atexit
         atexit.register(shutdown)

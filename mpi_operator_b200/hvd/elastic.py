@@ -27,6 +27,21 @@ def _discover_hosts() -> Optional[str]:
     return None
 
 
+def _read_world():
+    """(generation, world size) the launcher last published for this job, or None. With B200MPI_ELASTIC_DIR set the native
+    mpirun runs in elastic mode: it watches discover_hosts.sh itself, spawns the additional ranks of a larger world, waits
+    until they are ready and only then writes `<dir>/world`; surviving ranks re-form the communicator IN PLACE."""
+    d = os.environ.get("B200MPI_ELASTIC_DIR")
+    if not d:
+        return None
+    try:
+        with open(os.path.join(d, "world")) as f:
+            g, w = f.read().split()[:2]
+        return int(g), int(w)
+    except (OSError, ValueError):
+        return None
+
+
 class State:
     """Horovod's ``ObjectState``: named picklable attributes that are saved on ``commit()``, rolled back by ``restore()`` and
     broadcast from rank 0 by ``sync()``; callbacks registered with ``register_reset_callbacks`` run after every (re)start of the
@@ -54,6 +69,15 @@ class State:
         self.check_host_updates()
 
     def check_host_updates(self):
+        if os.environ.get("B200MPI_ELASTIC_DIR"):      # in-place mode: the launcher decides when the new world is ready
+            # every rank must leave the old world at the SAME commit: agree on the newest generation anyone has seen
+            from . import Max, _dev, allreduce
+            gw = _read_world()
+            seen = torch.tensor([float(gw[0] if gw else 0)], device=_dev())
+            newest = int(allreduce(seen, op=Max, name="elastic.generation").item())
+            if newest > int(os.environ.get("B200MPI_GENERATION", "0") or 0):
+                raise HostsUpdatedInterrupt(f"world generation {newest}")
+            return
         cur = _discover_hosts()
         if cur is not None and self._hosts is not None and cur != self._hosts:
             self._hosts = cur
@@ -155,16 +179,34 @@ def run(func: Callable) -> Callable:
         state.restore()
         state.sync()
         state.on_reset()      # every incarnation is a reset of the world: new size, new rank
-        try:
-            return func(state, *args, **kwargs)
-        except HostsUpdatedInterrupt:
-            state.save()
-            raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
-        except HorovodInternalError as e:
-            import sys
-            print(f"[elastic] collective failed ({e}); rolling back to the last commit and leaving for a re-spawn", file=sys.stderr, flush=True)
-            state.restore()
-            raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
+        while True:
+            try:
+                return func(state, *args, **kwargs)
+            except HostsUpdatedInterrupt:
+                state.save()
+                gw = _read_world()
+                if gw is None:    # restart mode: leave with the rescale code, the launcher re-runs mpirun on the new hostfile
+                    raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
+                # in-place mode: survivors keep their process, CUDA context and model; ranks beyond the new world retire
+                import time as _time
+                from . import _reinit, rank, shutdown
+                generation, world = gw
+                t0 = _time.time()
+                if rank() >= world:
+                    shutdown()
+                    raise SystemExit(0)
+                _reinit(world, generation)
+                state.sync()          # rank 0 (always a survivor) brings the new ranks up to the committed state
+                state.on_reset()
+                if rank() == 0:
+                    import sys
+                    print(f"[elastic] re-formed in place: generation {generation}, world size {world}, {(_time.time() - t0) * 1e3:.0f} ms",
+                          file=sys.stderr, flush=True)
+            except HorovodInternalError as e:
+                import sys
+                print(f"[elastic] collective failed ({e}); rolling back to the last commit and leaving for a re-spawn", file=sys.stderr, flush=True)
+                state.restore()
+                raise SystemExit(int(os.environ.get("B200MPI_RESCALE_EXIT_CODE", "75")))
     return wrapper
 
 

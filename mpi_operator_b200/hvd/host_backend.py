@@ -180,3 +180,13 @@ class HostCommunicator:
         if self._alive and self._owns_mpi:
             self._L.MPI_Finalize()
         self._alive = False
+
+    def reinit(self) -> None:
+        """Elastic rescale in place: leave the current world and join the one the environment now describes
+        (B200MPI_RANK / B200MPI_WORLD_SIZE / B200MPI_JOB_ID); every rank of the old world calls this or ``destroy``."""
+        self._check(self._L.b200mpi_mpi_reinit(), "b200mpi_mpi_reinit")
+        r, n = C.c_int(0), C.c_int(1)
+        self._L.MPI_Comm_rank(_COMM_WORLD, C.byref(r))
+        self._L.MPI_Comm_size(_COMM_WORLD, C.byref(n))
+        self.rank, self.world = r.value, n.value
+        self._alive = True

@@ -20,9 +20,8 @@ class _DistributedOptimizer:
 
     def __init__(self, optimizer, named_parameters=None, compression=None, backward_passes_per_step: int = 1, op="average",
                  gradient_predivide_factor: float = 1.0, bucket_bytes: Optional[int] = None):
-        from . import _comm, _op_name
+        from . import _op_name
         self._opt = optimizer
-        self._comm = _comm()
         self._op = _op_name(op, None)
         self._passes = max(1, int(backward_passes_per_step))
         from . import Compression
@@ -35,7 +34,27 @@ class _DistributedOptimizer:
         params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
         if any(p.dtype != torch.float32 for p in params):
             raise ValueError("DistributedOptimizer expects fp32 parameters (use autocast for low-precision compute)")
+        self._all_params = params
         self._params = list(reversed(params))
+        self._bucket_bytes = bucket_bytes
+        self._hooked = False
+        self._attach()
+        from . import _state
+        import weakref
+        _state.setdefault("optimizers", []).append(weakref.ref(self))
+
+    def _detach(self):
+        """Before the communicator goes away (elastic rescale in place): gradients stop viewing its window."""
+        for p in self._all_params:
+            p.grad = None
+        self._flat = self._win = None
+        self._handles = []
+
+    def _attach(self):
+        """(Re)build the gradient window and the buckets in the CURRENT communicator."""
+        from . import _comm, _state
+        self._comm = _comm()
+        params, bucket_bytes = self._all_params, self._bucket_bytes
         on_host = getattr(self._comm, "device", None) == "cpu"   # smaller buckets on the host: they are what overlaps with backward
         cap = (bucket_bytes or int(os.environ.get("B200MPI_BUCKET_BYTES", (4 << 20) if on_host else (32 << 20)))) // 4
         self._buckets: List[dict] = []
@@ -64,14 +83,22 @@ class _DistributedOptimizer:
         # Host tensors: each bucket goes to the background engine as a named async allreduce, so the reduction of bucket k runs
         # while autograd produces bucket k+1 (measured on the MNIST convnet, 2 ranks: 72-77 ms/step vs 77-83 with the synchronous
         # libmpi call in the hook; single rank 72.8). B200MPI_HVD_BUCKET_ASYNC=0 keeps the synchronous path.
-        from . import _state
         self._engine = _state.get("engine") if (not self._gpu and os.environ.get("B200MPI_HVD_BUCKET_ASYNC", "1") != "0") else None
         self._handles = []
         self._counts = {p: 0 for p in params}   # backward passes seen per parameter since the last step()
+        bucket_of = {}
         for b in self._buckets:
             b["pending"] = len(b["params"])
             for p in b["params"]:
-                p.register_post_accumulate_grad_hook(self._hook(b))
+                bucket_of[p] = b
+        self._bucket_of = bucket_of
+        if not self._hooked:       # hooks are registered once; they look the bucket up at call time (buckets are rebuilt on re-attach)
+            for p in params:
+                p.register_post_accumulate_grad_hook(self._hook_for)
+            self._hooked = True
+
+    def _hook_for(self, p):
+        self._hook(self._bucket_of[p])(p)
 
     def _rehome(self, p):
         """``p.grad`` must stay a view of the symmetric window (that is what the bucket kernel reduces). Code that drops

@@ -72,9 +72,10 @@ class FlatModelState:
         off = 0
         cur = Bucket(0, 0, 0)
         cap = max(bucket_bytes // 4, 1)
-        # The LAST bucket (the earliest layers) is the one whose allreduce+SGD cannot hide behind backward: keep it small
-        # (B200MPI_TAIL_BUCKET_BYTES, default 4 MiB) so the exposed tail of the step is one short kernel.
-        tail_cap = max(int(os.environ.get("B200MPI_TAIL_BUCKET_BYTES", 4 << 20)) // 4, 1)
+        # The LAST bucket (the earliest layers) is the one whose allreduce+SGD cannot hide behind backward. With
+        # B200MPI_TAIL_BUCKET_BYTES=<n> (e.g. 4194304) it is capped at n bytes so the exposed tail of the step is one short
+        # kernel. Opt-in: written after the round's last multi-GPU session, so it has not run on hardware yet (0 = off).
+        tail_cap = int(os.environ.get("B200MPI_TAIL_BUCKET_BYTES", 0)) // 4
         pad = 64 if bf16_params else 4
         remaining = sum(_align(p.numel(), pad) for p in order)
         tail_started = False
@@ -132,8 +133,18 @@ class FlatModelState:
     def broadcast_parameters(self, root: int = 0) -> None:
         """K3: rank-0 state to everyone (tensorflow_mnist.py:143)."""
         if self.comm.world > 1:
-            if hasattr(self.comm, "broadcast_window"):   # zero-copy: the parameters already live in a symmetric window
+            mode = os.environ.get("B200MPI_PARAM_BROADCAST", "window")
+            if mode == "window" and hasattr(self.comm, "broadcast_window"):   # zero-copy: the parameters already live in a symmetric window
                 self.comm.broadcast_window(self.param_win, 0, self.total * 4, root=root)
+            elif mode == "staged" and hasattr(self.comm, "set_pipe"):
+                # the barrier-based staged kernel, exactly what round 1 ran on 8 GPUs (bench.py's conservative configuration)
+                self.comm.set_pipe(min_bytes=1 << 62)
+                self.comm.set_reg(0)
+                try:
+                    self.comm.broadcast(self.flat_param, root=root)
+                finally:
+                    self.comm.set_pipe(min_bytes=8 << 20)
+                    self.comm.set_reg(1)
             else:
                 self.comm.broadcast(self.flat_param, root=root)
         self.refresh_lowp()
@@ -178,9 +189,11 @@ class DataParallelTrainer:
         self.device = torch.device("cuda", comm.device) if comm.device != "cpu" else torch.device("cpu")
         self._cuda = self.device.type == "cuda"
         if bf16_params is None:
-            # default on: ran on B200 in rounds 1 (driver XPASS) and 2 (profiles/r2: 15.34 -> 15.00 ms/step, 1 GPU)
-            # (CUDA only: the CPU debug path keeps fp32 leaves unless asked)
-            bf16_params = os.environ.get("B200MPI_BF16_PARAMS", "1" if self._cuda else "0") == "1"
+            # Default on for single-GPU CUDA runs: ran on B200 in rounds 1 (driver XPASS) and 2 (profiles/r2: 15.34 -> 15.00
+            # ms/step). With world > 1 the fused kernel pushes the bf16 shadow to every peer with unicast 8-byte stores
+            # (no multimem form yet) and that path has not been measured on more than one GPU: opt-in there
+            # (B200MPI_BF16_PARAMS=1). The CPU debug path keeps fp32 leaves unless asked.
+            bf16_params = os.environ.get("B200MPI_BF16_PARAMS", "1" if (self._cuda and comm.world == 1) else "0") == "1"
         self.bf16_params = bool(bf16_params) and autocast_dtype == torch.bfloat16
         self.loss_fn = loss_fn
         self.autocast_dtype = autocast_dtype

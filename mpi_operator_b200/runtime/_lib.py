@@ -47,7 +47,16 @@ def lib() -> C.CDLL:
         if os.environ.get("B200MPI_NO_AUTOBUILD"):
             raise B200MPIError(f"{LIB_PATH} is missing; run `make` (or __graft_entry__.build())")
         build()
-    L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
+    # When the NCCL-ABI shim is LD_PRELOADed (the node agent injects it into every rank) it already contains the whole
+    # runtime - same sources, same symbols. Loading libb200mpi.so next to it would put two copies of every kernel stub and
+    # every exported helper into one process, with calls between them resolved to whichever copy comes first: use the
+    # preloaded one as THE runtime instead.
+    path = str(LIB_PATH)
+    for pre in os.environ.get("LD_PRELOAD", "").replace(" ", ":").split(":"):
+        if pre.endswith("libb200mpi_nccl.so") and os.path.exists(pre):
+            path = pre
+            break
+    L = C.CDLL(path, mode=C.RTLD_GLOBAL)
     vp, sz, i, u, f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_float
     L.b200mpi_last_error.restype = C.c_char_p
     L.b200mpi_version.restype = C.c_char_p

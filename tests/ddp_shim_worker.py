@@ -69,8 +69,11 @@ def main():
         fails += int(not torch.allclose(p, q, rtol=1e-4, atol=1e-5))
     # registered buffers: ncclMemAlloc (torch MemPool over the backend's allocator) + ncclCommRegister (register_mem_pool).
     # Under the shim the pool's segment becomes an NVLS-bound symmetric window and large in-place collectives run zero-copy.
-    reg_note = "skipped"
+    reg_note = "skipped (only under the injected shim: stock NCCL's user-buffer registration is not what this test is about)"
+    injected_now = "b200mpi" in os.environ.get("LD_PRELOAD", "") and os.environ.get("B200MPI_ALGO") != "nccl"
     try:
+        if not injected_now:
+            raise TypeError("not injected")
         backend = dist.group.WORLD._get_backend(torch.device("cuda", dev))
         pool = torch.cuda.MemPool(backend.mem_allocator)
         with torch.cuda.use_mem_pool(pool):
@@ -89,7 +92,8 @@ def main():
         torch.cuda.synchronize()
         reg_note = "ok"
     except (AttributeError, RuntimeError, TypeError) as e:   # torch build without MemPool / mem_allocator
-        reg_note = f"unavailable ({type(e).__name__}: {str(e)[:80]})"
+        if injected_now:
+            reg_note = f"unavailable ({type(e).__name__}: {str(e)[:80]})"
     torch.cuda.synchronize()
     injected = "b200mpi" in os.environ.get("LD_PRELOAD", "")
     calls = fwd = -1

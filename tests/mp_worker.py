@@ -156,6 +156,17 @@ def main():
     comm.set_pipe(min_bytes=8 << 20, chunk_bytes=1 << 20)
     comm.set_reg(1, 8 << 20)
 
+    # ---- Adasum (K6) on device tensors: orthogonal gradients add, parallel gradients average ----
+    from mpi_operator_b200.hvd.adasum import adasum_allreduce_
+    e = torch.zeros(W * 1000, device="cuda")
+    e[R * 1000:(R + 1) * 1000] = 1.0
+    adasum_allreduce_(comm, e)
+    p_ = torch.full((4096,), 2.0, device="cuda")
+    adasum_allreduce_(comm, p_)
+    torch.cuda.synchronize()
+    check("adasum orthogonal", torch.allclose(e, torch.ones_like(e)))
+    check("adasum parallel", torch.allclose(p_, torch.full_like(p_, 2.0)))
+
     # ---- zero-copy window forms on real peers ----
     per = 1 << 18
     w2 = comm.alloc_window(W * per * 4)

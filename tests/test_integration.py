@@ -171,6 +171,47 @@ def test_elastic_horovod_rescales_2_4_2_and_resumes_from_committed_steps(op, tmp
 
 
 @needs_native
+def test_elastic_horovod_rescales_in_place_without_restarting_survivors(op, tmp_path):
+    """B200MPI_ELASTIC_INPLACE=1: the native mpirun watches discover_hosts.sh itself, spawns only the ADDITIONAL ranks of a
+    larger world (publishing the new world once they are ready) and lets the surplus ranks of a smaller one retire; the
+    surviving ranks keep their process and re-form the communicator at their next commit (hvd.elastic, generation counter).
+    2 -> 4 -> 2 on the CPU backend: mpirun starts exactly once, rank 0's pid never changes, training resumes from the
+    committed step without reloading a checkpoint."""
+    ckpt = str(tmp_path / "ckpt.pt")
+    job = new_mpijob("inplace", workers=2, launcher_cmd=("mpirun",), worker_cmd=("/usr/sbin/sshd", "-De"),
+                     launcher_args=("python", os.path.join(REPO, "examples/horovod/elastic_mnist.py"), "--total-steps", "160",
+                                    "--commit-every", "4", "--step-sleep", "0.02", "--checkpoint", ckpt))
+    job.spec.replica("Launcher").template["spec"]["containers"][0]["env"] = [
+        {"name": "B200MPI_HVD_DEVICE", "value": "cpu"}, {"name": "B200MPI_ELASTIC_INPLACE", "value": "1"}]
+    c = op.clientset.kubeflow_v2beta1().mpijobs("default")
+    c.create(job)
+
+    def logs():
+        return "".join(op.agent.logs("default", p["metadata"]["name"]) for p in op.store.list("pods", "default")
+                       if "launcher" in p["metadata"]["name"])
+
+    def scale(n):
+        j = c.get("inplace")
+        j.spec.replica("Worker").replicas = n
+        c.update(j)
+
+    wait_for(lambda: "world size 2" in logs(), timeout=60, what="first incarnation")
+    scale(4)
+    wait_for(lambda: "world size 4" in logs(), timeout=90, what="scaled-up world")
+    scale(2)
+    wait_for(lambda: logs().count("with world size 2") >= 2, timeout=90, what="scaled-down world")
+    wait_for(lambda: conds(c.get("inplace")).get("Succeeded") == "True", timeout=180, what="job success")
+    text = logs()
+    assert "world sizes seen: [2, 4, 2]" in text, text[-3000:]
+    assert text.count("re-formed in place") == 2, text[-3000:]
+    assert "elastic: world 2 -> 4, generation 1: spawned 2 ranks" in text and "elastic: world 4 -> 2, generation 2" in text
+    restarts = [ln for ln in text.splitlines() if "(re)started at step" in ln]
+    assert len(restarts) == 3 and all(int(ln.split("step ")[1].split()[0]) > 0 for ln in restarts[1:]), restarts
+    launcher = [p for p in op.store.list("pods", "default") if "inplace-launcher" in p["metadata"]["name"]]
+    assert len(launcher) == 1 and not launcher[0].get("status", {}).get("containerStatuses", [{}])[0].get("restartCount", 0)
+
+
+@needs_native
 def test_horovod_mnist_example_runs_as_a_cpu_job(op):
     """F3: examples/horovod/tensorflow-mnist.yaml — `mpirun -np 2 ... python /examples/tensorflow_mnist.py`,
     the image path remapped to the torch script; on a host without CUDA the hvd collectives run over the libmpi shim."""
