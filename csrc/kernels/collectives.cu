@@ -446,7 +446,9 @@ k_pipe(const __grid_constant__ KArgs a0, const KArgs* __restrict__ emu) {
       } else if (OP == PIPE_ALLGATHER || (OP == PIPE_BROADCAST && rank == a.root)) {
         // push: user chunk -> the same staging offset on every rank; allgather also writes its own output block directly
         const size_t dst = (slot + (OP == PIPE_ALLGATHER ? (size_t)rank * Cv : 0)) * 16;
-        constexpr int U = 4;
+        // the root of a broadcast is the only rank that pushes: twice the loads in flight per CTA (8-GPU sweep of round 2:
+        // 388 GB/s with 4, against NCCL's 656)
+        constexpr int U = OP == PIPE_BROADCAST ? 8 : 4;
         const bool fast_in = a.in_aligned && (v0 + len) * 16 <= a.nbytes;
         const bool fast_out = a.out_aligned && (v0 + len) * 16 <= a.nbytes;
         const char* src = a.in + v0 * 16;

@@ -668,6 +668,7 @@ static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dt
                    cudaStream_t stream, int algo, Fill&& fill) {
   if (mode == MODE_NVLS && !(c->multicast && c->wins[c->stage_win].mc)) mode = MODE_P2P;
   int L = wide ? c->pipe_lanes_wide : (mode == MODE_NVLS ? c->pipe_lanes_nvls : c->pipe_lanes_p2p);
+  if (kind == PIPE_BROADCAST && mode == MODE_NVLS) L = kPipeLanes;   // one pushing rank: give it every lane
   if (c->local) L = std::max(1, std::min(L, emu_max_blocks(c) / 3));
   const int D = c->pipe_depth;
   const size_t nvec = (nbytes + 15) / 16;
@@ -1225,7 +1226,10 @@ int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t c
   const size_t total = count * esize(dtype);
   if (dtype < 0 || dtype > 2 || op < 0 || op > 2) return fail(B200MPI_ERR_INVALID, "reduce_scatter: bad dtype/op");
   const bool rs_nvls = c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32);
-  if (total % 16 == 0 && reg_wanted(c, total * c->world, !rs_nvls)) {   // zero-copy: pull the owned block from every input
+  // zero-copy: pull the owned block from every input. Preferred over the NVLS pipeline at every world size: the P2P pull
+  // runs at the link's read rate (allreduce_reg: 630 GB/s at 4 and 8 GPUs) with no staging copy of the N x larger input,
+  // the pipelined kernel reached 564 GB/s at 8 GPUs against NCCL's 632 (profiles/r2/roofline_shim_vs_nccl_n8.md)
+  if (total % 16 == 0 && reg_wanted(c, total * c->world, true)) {
     Win win_in, win_out;
     if (reg_exchange(c, in, out, total * c->world, total, true, &win_in, &win_out) == REG_IPC) {
       std::vector<KArgs> args(1);
