@@ -14,9 +14,12 @@ RUNTIME_HDRS := csrc/include/b200mpi.h csrc/kernels/device.cuh csrc/kernels/kern
 
 all: $(LIBDIR)/libb200mpi.so $(LIBDIR)/libb200mpi_nccl.so $(LIBDIR)/libb200mpi_gemm.so native
 
+# -Bsymbolic: the NCCL-ABI shim contains the same sources and is LD_PRELOADed into every rank by the node agent; without it
+# the runtime's internal calls would bind to the preloaded copy while its entry points (looked up by handle) stay local,
+# i.e. one call would run through two copies of the file-static state.
 $(LIBDIR)/libb200mpi.so: $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) $(NVFLAGS) -shared -x cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread
+	$(NVCC) $(NVFLAGS) -shared -x cu $(RUNTIME_SRCS) -o $@ -lrt -lpthread -Xlinker -Bsymbolic
 
 $(LIBDIR)/libb200mpi_nccl.so: csrc/nccl_shim/nccl_shim.cu $(RUNTIME_SRCS) $(RUNTIME_HDRS)
 	@mkdir -p $(LIBDIR)

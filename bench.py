@@ -177,6 +177,7 @@ def supervise(args) -> int:
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     base_port = os.environ.get("MASTER_PORT", "29500")
     workdir = f"/tmp/b200mpi_bench_{base_port}_{os.getppid()}"   # every rank has the same parent: unique per launch, shared by the ranks
+    t_start = time.time()
     result, used, notes = None, None, []
     for k, (name, extra) in enumerate(ATTEMPTS):
         rc, d, err = _run_child(args, "ours", _clean_child_env(17 * (k + 1), f"ours-{name}", extra), args.attempt_timeout)
@@ -196,9 +197,20 @@ def supervise(args) -> int:
         arms = {}
         for k, arm in enumerate(("nccl", "torchddp")):
             t0 = time.time()
-            rc, d, err = _run_child(args, arm, _clean_child_env(211 * (k + 1), f"arm-{arm}", {}), args.arm_timeout)
+            # the whole invocation stays inside --budget seconds (the driver gives one N of the scaling run ~870 s): an arm
+            # starts only if every rank still has room for it, and is cut short rather than overrunning
+            left = args.budget - (t0 - t_start)
+            room = left >= 90
             if world > 1:
-                _agree(workdir, f"arm{k}", rank, world, rc == 0, args.arm_timeout + 60)   # keep the ranks in step
+                room = _agree(workdir, f"room{k}", rank, world, room, 60)
+            if not room:
+                if rank == 0:
+                    arms[arm] = {"skipped": f"time budget ({args.budget} s) nearly used by the main measurement"}
+                continue
+            limit = int(max(60, min(args.arm_timeout, left - 30)))
+            rc, d, err = _run_child(args, arm, _clean_child_env(211 * (k + 1), f"arm-{arm}", {}), limit)
+            if world > 1:
+                _agree(workdir, f"arm{k}", rank, world, rc == 0, limit + 60)   # keep the ranks in step
             if rank == 0:
                 if d and "value" in d:
                     arms[arm] = {"value": d["value"], "ms_per_step": d["ms_per_step"], "e2e": d.get("e2e", {}).get("value"),
@@ -248,8 +260,10 @@ def main() -> int:
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
                     help="compute dtype: bf16 autocast (headline) or fp32 (the reference YAML's precision: no --use_fp16)")
     ap.add_argument("--no-same-box", action="store_true", help="skip the same-box baseline arms after the measurement")
-    ap.add_argument("--arm-timeout", type=int, default=240)
-    ap.add_argument("--attempt-timeout", type=int, default=360, help="limit for one configuration of the main measurement")
+    ap.add_argument("--arm-timeout", type=int, default=180)
+    ap.add_argument("--attempt-timeout", type=int, default=240, help="limit for one configuration of the main measurement")
+    ap.add_argument("--budget", type=int, default=int(os.environ.get("B200MPI_BENCH_BUDGET_S", 780)),
+                    help="seconds the whole invocation may take; the same-box arms are skipped or shortened to stay inside it")
     ap.add_argument("--child", action="store_true", help="(internal) run the measurement in this process")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -34,7 +34,8 @@ def main():
     ap.add_argument("--use_fp16", default="False")
     ap.add_argument("--data_format", default="NCHW")
     ap.add_argument("--data_name", default="imagenet")
-    ap.add_argument("--device", default="gpu")
+    ap.add_argument("--device", default="gpu", choices=["gpu", "cpu"], help="cpu: host tensors through the Horovod-API engine (no CUDA needed)")
+    ap.add_argument("--image_size", type=int, default=224)
     ap.add_argument("--num_gpus", type=int, default=1)
     ap.add_argument("--b200_engine", default=os.environ.get("B200MPI_ENGINE", "fused"), choices=["fused", "hvd", "nccl"],
                     help="fused: symmetric-window grads + fused allreduce+SGD kernel in a CUDA graph; "
@@ -52,16 +53,24 @@ def main():
 
     hvd.init()
     rank, size = hvd.rank(), hvd.size()
+    on_gpu = args.device == "gpu"
+    if on_gpu and not torch.cuda.is_available():
+        raise SystemExit("tf_cnn_benchmarks (b200): --device=gpu but no CUDA device is visible (use --device=cpu for a host run)")
+    if not on_gpu:
+        args.b200_engine, args.b200_compute_dtype = "hvd", "fp32"
+    S = args.image_size
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
     mu = args.momentum if args.optimizer == "momentum" or args.momentum else 0.0
     lr = args.init_learning_rate * size  # Horovod convention (tensorflow_mnist.py:123-130)
     B = args.batch_size
-    model = build_model(args.model)
+    model = build_model(args.model, **({"image_size": S} if args.model == "trivial" else {}))
     loss_fn = nn.CrossEntropyLoss()
-    dtype = torch.bfloat16 if (args.b200_compute_dtype == "bf16" or str(args.use_fp16).lower() == "true") else None
-    x = torch.randn(B, 3, 224, 224).pin_memory()
-    y = torch.randint(0, 1000, (B,)).pin_memory()
+    dtype = torch.bfloat16 if on_gpu and (args.b200_compute_dtype == "bf16" or str(args.use_fp16).lower() == "true") else None
+    x = torch.randn(B, 3, S, S)
+    y = torch.randint(0, 1000, (B,))
+    if on_gpu:
+        x, y = x.pin_memory(), y.pin_memory()
 
     if rank == 0:
         print("TensorFlow:  n/a (PyTorch %s + b200mpi runtime)" % torch.__version__)
@@ -73,11 +82,11 @@ def main():
         print(f"             {B} per device")
         print(f"Num batches: {args.num_batches}")
         print("Num epochs:  %.2f" % (args.num_batches * B * size / 1281167.0))
-        print(f"Devices:     {['horovod/gpu:%d' % i for i in range(size)]}")
+        print(f"Devices:     {['horovod/%s:%d' % (args.device, i) for i in range(size)]}")
         print(f"Data format: {args.data_format}")
         print(f"Optimizer:   {args.optimizer}")
         print(f"Variables:   {args.variable_update}")
-        print(f"Engine:      {args.b200_engine} (NVLS multicast: {hvd._comm().has_multicast})")
+        print(f"Engine:      {args.b200_engine} (NVLS multicast: {getattr(hvd._comm(), 'has_multicast', False)})")
         print("==========")
         print("Generating model")
         sys.stdout.flush()
@@ -92,26 +101,31 @@ def main():
         def step():
             return trainer.step(x, y)
     else:
-        model = model.cuda().to(memory_format=torch.channels_last)
+        dev = "cuda" if on_gpu else "cpu"
+        model = model.to(dev).to(memory_format=torch.channels_last)
         opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=mu, weight_decay=args.weight_decay)
         opt = hvd.DistributedOptimizer(opt, named_parameters=model.named_parameters(), op=hvd.Average)
         hvd.broadcast_parameters(model.state_dict(), root_rank=0)
-        sx = torch.empty(B, 3, 224, 224, device="cuda").contiguous(memory_format=torch.channels_last)
-        sy = torch.empty(B, dtype=torch.long, device="cuda")
+        sx = torch.empty(B, 3, S, S, device=dev).contiguous(memory_format=torch.channels_last)
+        sy = torch.empty(B, dtype=torch.long, device=dev)
 
         def step():
             sx.copy_(x, non_blocking=True)
             sy.copy_(y, non_blocking=True)
             opt.zero_grad()
-            with torch.autocast("cuda", dtype=dtype, enabled=dtype is not None):
+            with torch.autocast(dev, dtype=dtype, enabled=dtype is not None):
                 loss = loss_fn(model(sx), sy)
             loss.backward()
             opt.step()
             return loss.detach()
 
+    def device_sync():
+        if on_gpu:
+            torch.cuda.synchronize()
+
     for _ in range(args.num_warmup_batches):
         loss = step()
-    torch.cuda.synchronize()
+    device_sync()
     hvd.barrier()
     if rank == 0:
         print("Running warm up")
@@ -139,7 +153,7 @@ def main():
             elif rank == 0:
                 print(f"{i}\timages/sec: n/a (first step)\t{lv:.3f}")
             t0 = time.perf_counter()
-    torch.cuda.synchronize()
+    device_sync()
     hvd.barrier()
     total = args.num_batches * B * size / (time.perf_counter() - t_all)
     if rank == 0:

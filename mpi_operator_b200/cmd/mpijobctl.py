@@ -22,7 +22,7 @@ import json
 import os
 import sys
 import time
-from typing import List, Optional
+from typing import Dict, List, Optional
 
 import yaml
 
@@ -261,15 +261,35 @@ def cmd_run(a) -> int:
                 c.create(job)
                 t0 = time.time()
                 state = "Pending"
+                printed: Dict[str, int] = {}  # launcher pod -> bytes of its log already written
+
+                def drain() -> None:
+                    # The launcher pod is deleted when its Job hits the backoff limit (batch/v1 semantics with
+                    # restartPolicy OnFailure), so the log is copied out while the pod still exists.
+                    for p in op.store.list("pods", job.namespace):
+                        md = p["metadata"]
+                        if md.get("labels", {}).get(C.JOB_ROLE_LABEL) != "launcher" or md.get("labels", {}).get(C.JOB_NAME_LABEL, job.name) != job.name:
+                            continue
+                        text = op.agent.logs(job.namespace, md["name"])
+                        done = printed.get(md["name"], 0)
+                        if len(text) < done:  # container restarted in place: the log file started over
+                            done = 0
+                        if len(text) > done:
+                            sys.stdout.write(text[done:])
+                            sys.stdout.flush()
+                        printed[md["name"]] = len(text)
+
+                last_drain = 0.0
                 while time.time() - t0 < a.timeout:
                     j = c.get(job.name).to_dict()
                     state = _job_state(j)
+                    if time.time() - last_drain > 0.5:
+                        drain()
+                        last_drain = time.time()
                     if state in ("Succeeded", "Failed"):
                         break
                     time.sleep(0.05)
-                for p in op.store.list("pods", job.namespace):
-                    if p["metadata"].get("labels", {}).get(C.JOB_ROLE_LABEL) == "launcher":
-                        sys.stdout.write(op.agent.logs(job.namespace, p["metadata"]["name"]))
+                drain()
                 print(f"mpijob.kubeflow.org/{job.name}: {state} after {time.time() - t0:.2f}s")
                 rc = rc or (0 if state == "Succeeded" else 1)
     finally:

@@ -5,10 +5,12 @@ tensorflow_mnist.py:38-73).  Model compute stays in PyTorch/cuDNN; the
 hand-written sm_100a surface is the collective + optimizer path."""
 from .resnet import resnet18, resnet50, resnet101, resnet152, ResNet  # noqa: F401
 from .mnist import MnistConvNet  # noqa: F401
+from .classic import trivial, lenet, alexnet, vgg11, vgg16, vgg19  # noqa: F401
 
 MODEL_REGISTRY = {
     "resnet18": resnet18, "resnet50": resnet50, "resnet101": resnet101, "resnet152": resnet152,
     "mnist": MnistConvNet,
+    "trivial": trivial, "lenet": lenet, "alexnet": alexnet, "vgg11": vgg11, "vgg16": vgg16, "vgg19": vgg19,
 }
 
 

@@ -61,3 +61,13 @@ def test_failing_baseline_arm_is_reported_not_fatal():
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
     assert "error" in d["same_box"]["nccl_same_engine"] and d["same_box"]["ratio_vs_nccl"] is None
     assert d["same_box"]["ratio_vs_torchddp"] == 2.0
+
+
+def test_arms_are_skipped_when_the_time_budget_is_spent():
+    env = dict(os.environ, B200MPI_BENCH_SELFTEST="ok", B200MPI_BENCH_BUDGET_S="30", MASTER_PORT="29824")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        env.pop(k, None)
+    r = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "3", "--warmup", "3"], capture_output=True, text=True, timeout=120, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    assert d["value"] == 4000.0 and "skipped" in d["same_box"]["nccl_same_engine"] and d["same_box"]["ratio_vs_nccl"] is None

@@ -232,6 +232,57 @@ def test_horovod_mnist_example_runs_as_a_cpu_job(op):
 
 
 @needs_native
+def test_headline_tensorflow_benchmarks_yaml_runs_on_the_host_with_device_cpu(op):
+    """The reference's headline job (examples/v2beta1/tensorflow-benchmarks/tensorflow-benchmarks.yaml:17-42), same YAML and
+    mpirun line, with the flags a user would edit: a small model and --device=cpu. Covers image lookup, script path, the
+    Open MPI flags of that command line, hvd.init under the operator and the sample-output format (README.md:180-212)."""
+    job = yaml_io.load_file(os.path.join(REPO, "examples/tensorflow-benchmarks/tensorflow-benchmarks.yaml"))[0]
+    job.metadata["namespace"] = "default"
+    c0 = job.spec.replica("Launcher").template["spec"]["containers"][0]
+    cmd = [t for t in c0["command"] if not t.startswith("--model=") and not t.startswith("--batch_size=")]
+    c0["command"] = cmd + ["--model=trivial", "--batch_size=8", "--device=cpu", "--image_size=32", "--num_batches=20", "--num_warmup_batches=2"]
+    submit(op, job)
+    wait_for(lambda: conds(get(op, job)).get("Succeeded") == "True", timeout=120, what="Succeeded")
+    launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["labels"][C.JOB_ROLE_LABEL] == "launcher"][0]
+    log = op.agent.logs("default", launcher["metadata"]["name"])
+    assert "Model:       trivial" in log and "Batch size:  16 global" in log and "Variables:   horovod" in log
+    assert "20\timages/sec:" in log and "total images/sec:" in log
+
+
+@needs_native
+def test_mpijobctl_run_keeps_the_launcher_log_of_a_job_that_failed(tmp_path):
+    """A launcher that hits the backoff limit is deleted with its Job (batch/v1 semantics); `mpijobctl run` copies the log
+    out while the pod exists, so the reason for the failure is still on the terminal."""
+    import subprocess
+    import sys
+    y = tmp_path / "fail.yaml"
+    y.write_text("""apiVersion: kubeflow.org/v2beta1
+kind: MPIJob
+metadata: {name: doomed}
+spec:
+  runPolicy: {backoffLimit: 0}
+  mpiReplicaSpecs:
+    Launcher:
+      replicas: 1
+      restartPolicy: Never
+      template:
+        spec:
+          containers:
+          - {name: l, image: mpioperator/mpi-pi, command: [sh, -c, "echo the-reason-it-failed; exit 3"]}
+    Worker:
+      replicas: 1
+      template:
+        spec:
+          containers:
+          - {name: w, image: mpioperator/mpi-pi}
+""")
+    r = subprocess.run([sys.executable, "-m", "mpi_operator_b200.cmd.mpijobctl", "run", "-f", str(y), "--fake-gpus", "2", "--timeout", "60"],
+                       cwd=REPO, capture_output=True, text=True, timeout=120, env=dict(os.environ, B200MPI_STATE_DIR=str(tmp_path / "state")))
+    assert r.returncode == 1, r.stdout + r.stderr
+    assert "the-reason-it-failed" in r.stdout and "doomed: Failed" in r.stdout
+
+
+@needs_native
 def test_malformed_command_backoff_limit_failed(op):
     job = new_mpijob("bad", workers=1, launcher_cmd=("mpirun",), launcher_args=("-n", "1", "sh", "-c", "echo boom >&2; exit 7"),
                      worker_cmd=("/usr/sbin/sshd", "-De"), backoff_limit=1)
