@@ -39,6 +39,19 @@ def test_one_line_with_same_box_ratios_and_clean_child_env(world):
     assert sb["nccl_same_engine"]["impl"] == "nccl" and sb["torchddp_stock"]["impl"] == "torchddp"
 
 
+def test_faster_multi_gpu_candidate_is_the_one_reported():
+    """world > 1: the default configuration and the one with the bf16 shadow + small tail bucket are both measured in full;
+    the line carries the faster one and lists both."""
+    r = _launch(2, "full_faster", 29825)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["config"]["bench_configuration"] == "full" and d["value"] == pytest.approx(8400.0)
+    assert set(d["config"]["candidates"]) == {"default", "full"}
+    assert d["same_box"]["ratio_vs_nccl"] == pytest.approx(8400 / 7800, abs=1e-3)
+
+
 def test_failing_default_configuration_falls_back_on_every_rank():
     r = _launch(2, "fail_default", 29821)
     assert r.returncode == 0, r.stderr[-2000:]
