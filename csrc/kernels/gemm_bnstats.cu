@@ -19,9 +19,9 @@
 // Persistent: CTA c owns column block c % num_n and walks m-blocks with stride grid/num_n, so every epilogue thread keeps one
 // column's running sums in registers for the whole kernel and writes a single partial row at the end (no atomics).
 //
-// Status: compiled for sm_100a and checked with ptxas/cuobjdump here; NOT yet run on hardware (the round's GPU budget was
-// spent before it was written), therefore not wired into the default model path. tests/test_zz_gemm_bnstats_gpu.py is the
-// numerics test against torch (opt-in: B200MPI_EXPERIMENTAL=1). Every wait is bounded and traps instead of hanging.
+// Status: first executed on a B200 in round 2 - numerics 10 / 10 against fp32 references (tests/test_zz_gemm_bnstats_gpu.py),
+// ncu capture + 12-shape micro-benchmark in profiles/ncu_gemm_bnstats.md, ResNet-101 step 14.15 -> 13.75 ms; on by default
+// for eligible 1x1 convolutions (B200MPI_FUSED_CONV1X1=0 restores cuDNN). Every wait is bounded and traps instead of hanging.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
