@@ -373,6 +373,8 @@ struct Engine {
 
   // gpu
   bool has_gpu = false;
+  unsigned char* ada_seg = nullptr;   // Adasum scratch: world slots of ada_slot bytes in a shared segment of its own
+  size_t ada_slot = 0, ada_total = 0;
   hvdcore_gpu_t gpu{};
   Cuda cu;
   void* stream = nullptr;
@@ -526,6 +528,92 @@ int host_allreduce(Engine* e, void* buf, int64_t count, int dt, int op) {
       if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
     }
   }
+  return 0;
+}
+
+// ---- Adasum (Horovod's op=hvd.Adasum; the --use-adasum flag of the reference's MNIST example, tensorflow_mnist.py:31-32,133) ----
+// adasum(a, b) = (1 - a.b / (2 |a|^2)) a + (1 - a.b / (2 |b|^2)) b, folded as a binary tree over the ranks: orthogonal gradients
+// add, parallel gradients average. Horovod does vector-halving / distance-doubling over MPI; on one box every rank's vector
+// goes into a slot of a shared scratch segment and ALL ranks work on every pair of a tree level, each on its own 1/W slice:
+// partial dot products (double) are exchanged through the rendezvous allgather and summed in rank order - identical
+// coefficients everywhere - then each rank combines its slice in place. O(n) work per rank, one allgather per level,
+// the result (slot 0) is bit-identical on all ranks.
+template <typename T> struct AdaPair { T* a; const T* b; };
+
+template <typename T>
+int adasum_levels(Engine* e, size_t n) {
+  std::string err;
+  const int W = e->world, me = e->rank;
+  const size_t lo = n * (size_t)me / (size_t)W, hi = n * (size_t)(me + 1) / (size_t)W;
+  std::vector<int> active((size_t)W);
+  for (int r = 0; r < W; r++) active[(size_t)r] = r;
+  constexpr size_t kBatch = 32;   // pairs per allgather round (768 bytes of the rendezvous mailbox)
+  std::vector<double> all((size_t)W * 3 * kBatch);
+  while (active.size() > 1) {
+    const size_t np = active.size() / 2;
+    for (size_t p0 = 0; p0 < np; p0 += kBatch) {
+      const size_t nb = std::min(kBatch, np - p0);
+      double mine[3 * kBatch];
+      for (size_t k = 0; k < nb; k++) {
+        const T* a = (const T*)(e->ada_seg + (size_t)active[2 * (p0 + k)] * e->ada_slot);
+        const T* b = (const T*)(e->ada_seg + (size_t)active[2 * (p0 + k) + 1] * e->ada_slot);
+        double dot = 0, na = 0, nbn = 0;
+        for (size_t i = lo; i < hi; i++) { const double x = (double)a[i], y = (double)b[i]; dot += x * y; na += x * x; nbn += y * y; }
+        mine[3 * k] = dot; mine[3 * k + 1] = na; mine[3 * k + 2] = nbn;
+      }
+      if (e->rv.allgather(mine, all.data(), nb * 3 * sizeof(double), e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+      for (size_t k = 0; k < nb; k++) {
+        double dot = 0, na = 0, nbn = 0;
+        for (int r = 0; r < W; r++) { const double* q = all.data() + ((size_t)r * nb + k) * 3; dot += q[0]; na += q[1]; nbn += q[2]; }
+        const double ca = na > 0 ? 1.0 - dot / (2.0 * na) : 1.0, cb = nbn > 0 ? 1.0 - dot / (2.0 * nbn) : 1.0;
+        T* a = (T*)(e->ada_seg + (size_t)active[2 * (p0 + k)] * e->ada_slot);
+        const T* b = (const T*)(e->ada_seg + (size_t)active[2 * (p0 + k) + 1] * e->ada_slot);
+        for (size_t i = lo; i < hi; i++) a[i] = (T)(ca * (double)a[i] + cb * (double)b[i]);
+      }
+    }
+    std::vector<int> next;   // (no barrier between levels: a rank only ever touches its own slice of every slot)
+    for (size_t k = 0; k < np; k++) next.push_back(active[2 * k]);
+    if (active.size() % 2) next.push_back(active.back());
+    active.swap(next);
+  }
+  if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);   // every slice of the root slot is final
+  return 0;
+}
+
+// In-place Adasum of `count` elements of dtype f32 / f64 / f16 / bf16 (16-bit floats are combined in fp32). `in` may be null
+// (a joined rank contributes zeros, which Adasum treats as neutral).
+int host_adasum(Engine* e, const void* in, void* out, int64_t count, int dt) {
+  if (dt != HVD_F32 && dt != HVD_F64 && dt != HVD_F16 && dt != HVD_BF16) return fail(HVD_ERR_UNSUPPORTED, "Adasum needs a floating-point tensor");
+  if (count == 0) return 0;
+  std::string err;
+  const size_t n = (size_t)count, ws = dt == HVD_F64 ? 8 : 4;
+  const size_t need = (n * ws + 63) / 64 * 64;
+  if (e->ada_slot < need) {   // collective decision: every rank sees the same count
+    if (e->ada_seg) { Rendezvous::close_boxes(e->ada_seg, e->ada_total); e->ada_seg = nullptr; e->ada_slot = 0; }
+    const size_t box = std::max(need, (size_t)1 << 20) / 2;
+    e->ada_seg = e->rv.open_boxes(box, e->timeout_ms, &e->ada_total);
+    if (!e->ada_seg) return fail(HVD_ERR_TRANSPORT, "Adasum: could not create the shared scratch segment (" + std::to_string((size_t)e->world * 2 * box) + " bytes in /dev/shm)");
+    e->ada_slot = 2 * box;
+  }
+  unsigned char* mine = e->ada_seg + (size_t)e->rank * e->ada_slot;
+  if (!in) memset(mine, 0, n * ws);
+  else if (dt == HVD_F32 || dt == HVD_F64) memcpy(mine, in, n * ws);
+  else {
+    float* f = (float*)mine; const uint16_t* h = (const uint16_t*)in;
+    if (dt == HVD_F16) for (size_t i = 0; i < n; i++) f[i] = f16_to_f(h[i]); else for (size_t i = 0; i < n; i++) f[i] = bf16_to_f(h[i]);
+  }
+  if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);
+  const int rc = dt == HVD_F64 ? adasum_levels<double>(e, n) : adasum_levels<float>(e, n);
+  if (rc) return rc;
+  if (out) {
+    const unsigned char* res = e->ada_seg;   // slot 0 holds the root of the tree
+    if (dt == HVD_F32 || dt == HVD_F64) memcpy(out, res, n * ws);
+    else {
+      const float* f = (const float*)res; uint16_t* h = (uint16_t*)out;
+      if (dt == HVD_F16) for (size_t i = 0; i < n; i++) h[i] = f_to_f16(f[i]); else for (size_t i = 0; i < n; i++) h[i] = f_to_bf16(f[i]);
+    }
+  }
+  if (e->rv.barrier(e->timeout_ms, &err)) return fail(HVD_ERR_TRANSPORT, err);     // everyone has read slot 0 before it is reused
   return 0;
 }
 
@@ -788,7 +876,16 @@ void run_allreduce_group(Engine* e, std::vector<Response*>& grp) {
   if (q0.devkind == 0) {
     // ---- host path ----
     int rc = 0;
-    if (grp.size() == 1 && ops[0]) {
+    if (q0.redop == HVD_ADASUM) {   // never fused (execute()): the coefficients are per tensor
+      LocalOp* o = ops[0];
+      std::vector<unsigned char> tmp;
+      const void* src = o ? o->in : nullptr;
+      if (o && q0.pre != 1.0) { tmp.assign((const unsigned char*)o->in, (const unsigned char*)o->in + (size_t)total * es); scale_buf(tmp.data(), (size_t)total, q0.dtype, q0.pre); src = tmp.data(); }
+      if (tl) e->tl.ev(grp[0]->tl_pid, 'B', "SHM_ADASUM");
+      rc = host_adasum(e, src, o ? o->out : nullptr, total, q0.dtype);
+      if (tl) e->tl.ev(grp[0]->tl_pid, 'E', "");
+      if (!rc && o) scale_buf(o->out, (size_t)total, q0.dtype, q0.post);
+    } else if (grp.size() == 1 && ops[0]) {
       LocalOp* o = ops[0];
       if (o->out != o->in) memcpy(o->out, o->in, (size_t)total * es);
       scale_buf(o->out, (size_t)total, q0.dtype, q0.pre);
@@ -831,6 +928,7 @@ void run_allreduce_group(Engine* e, std::vector<Response*>& grp) {
   std::string err;
   int rc = 0;
   if (!e->has_gpu) { rc = HVD_ERR_UNSUPPORTED; err = "device tensor submitted but the engine was started without a GPU executor"; }
+  else if (q0.redop == HVD_ADASUM) { rc = HVD_ERR_UNSUPPORTED; err = "Adasum of device tensors goes through the communicator directly (hvd/adasum.py)"; }
   else if (dt < 0 || op < 0) { rc = HVD_ERR_UNSUPPORTED; err = "device allreduce supports float32/bfloat16/float16 with sum/min/max (convert first)"; }
   std::vector<int> handles, pids;
   if (!rc) {
@@ -958,7 +1056,7 @@ void execute(Engine* e, std::vector<Response>& rsp, int64_t threshold) {
     // greedy fusion with look-ahead: same dtype / op / scales / device kind, total size under the threshold
     std::vector<Response*> grp{&r};
     int64_t bytes = r.req.count * (int64_t)esize(r.req.dtype);
-    for (size_t j = i + 1; j < rsp.size() && bytes < threshold; j++) {
+    for (size_t j = i + 1; j < rsp.size() && bytes < threshold && r.req.redop != HVD_ADASUM; j++) {
       if (used[j] || !rsp[j].error.empty() || rsp[j].req.op != HVD_ALLREDUCE) continue;
       const Request& a = r.req; const Request& b = rsp[j].req;
       if (a.dtype != b.dtype || a.redop != b.redop || a.devkind != b.devkind || memcmp(&a.pre, &b.pre, 8) || memcmp(&a.post, &b.post, 8)) continue;
@@ -1130,6 +1228,7 @@ void engine_main(Engine* e) {
   if (e->stream && e->fusion_dev) { e->cu.StreamSynchronize(e->stream); e->cu.Free(e->fusion_dev); e->fusion_dev = nullptr; }
   e->tl.close();
   if (e->seg) { Rendezvous::close_boxes(e->seg, e->seg_bytes); e->seg = nullptr; }
+  if (e->ada_seg) { Rendezvous::close_boxes(e->ada_seg, e->ada_total); e->ada_seg = nullptr; e->ada_slot = 0; }
 }
 
 }  // namespace
@@ -1219,7 +1318,7 @@ int hvdcore_enqueue(hvd_op_t op, const char* name, const void* in, void* out, in
   if (op == HVD_EXCHANGE && (dtype != HVD_U8 || count > (int64_t)kMaxBlob || device >= 0)) return fail(HVD_ERR_INVALID, "hvdcore: exchange takes <= 1024 host bytes");
   if (op == HVD_ALLGATHER && n_extra != e->world) return fail(HVD_ERR_INVALID, "hvdcore: allgather needs one byte count per rank");
   if (op == HVD_ALLTOALL && n_extra != 2 * e->world) return fail(HVD_ERR_INVALID, "hvdcore: alltoall needs send and receive byte counts per rank");
-  if ((op == HVD_ALLREDUCE) && (redop < HVD_SUM || redop > HVD_PROD)) return fail(HVD_ERR_INVALID, "hvdcore: unknown reduction");
+  if ((op == HVD_ALLREDUCE) && (redop < HVD_SUM || redop > HVD_ADASUM)) return fail(HVD_ERR_INVALID, "hvdcore: unknown reduction");
   LocalOp lo;
   Request& q = lo.req;
   q.op = (uint8_t)op; q.dtype = (uint8_t)dtype; q.redop = (uint8_t)redop; q.devkind = device >= 0 ? 1 : 0;

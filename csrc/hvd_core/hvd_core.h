@@ -42,7 +42,7 @@ typedef enum {
   HVD_BOOL = 9,
 } hvd_dtype_t;
 
-typedef enum { HVD_SUM = 0, HVD_MIN = 1, HVD_MAX = 2, HVD_PROD = 3 } hvd_redop_t;
+typedef enum { HVD_SUM = 0, HVD_MIN = 1, HVD_MAX = 2, HVD_PROD = 3, HVD_ADASUM = 4 /* host float tensors; never fused */ } hvd_redop_t;
 
 enum {
   HVD_OK = 0,

@@ -203,6 +203,67 @@ int main() {
     CHECK(hvdcore_wait(h) == 0 && v[0] == 2.f * W, "allreduce after join: %f", v[0]);
   }
 
+  // ---- 6b. Adasum (HVD_ADASUM): orthogonal vectors add, parallel vectors average, zero is neutral; vs a double tree ---------
+  {
+    const int n = 1000 + 7;
+    std::vector<float> e(W * 3, 0.f);
+    e[R * 3] = 1.f; e[R * 3 + 1] = 2.f;                       // pairwise orthogonal across ranks
+    int h = ar("adasum.orth", e.data(), e.data(), (int64_t)e.size(), HVD_F32, HVD_ADASUM);
+    CHECK(hvdcore_wait(h) == 0, "adasum orth: %s", hvdcore_last_error());
+    for (int r = 0; r < W; r++) CHECK(e[r * 3] == 1.f && e[r * 3 + 1] == 2.f && e[r * 3 + 2] == 0.f, "orthogonal vectors must add (slot %d: %f %f)", r, e[r * 3], e[r * 3 + 1]);
+    std::vector<double> p(n);
+    for (int i = 0; i < n; i++) p[i] = (double)(R + 1) * (0.25 + i % 13);     // parallel across ranks: rank r holds (r+1) * base
+    h = ar("adasum.par", p.data(), p.data(), n, HVD_F64, HVD_ADASUM);
+    CHECK(hvdcore_wait(h) == 0, "adasum parallel: %s", hvdcore_last_error());
+    // tree of averages: level by level (a + b) / 2 over coefficients r + 1
+    std::vector<double> c(W);
+    for (int r = 0; r < W; r++) c[r] = r + 1;
+    while (c.size() > 1) {
+      std::vector<double> nx;
+      for (size_t i = 0; i + 1 < c.size(); i += 2) nx.push_back((c[i] + c[i + 1]) / 2);
+      if (c.size() % 2) nx.push_back(c.back());
+      c.swap(nx);
+    }
+    for (int i = 0; i < n; i += 97) CHECK(fabs(p[i] - c[0] * (0.25 + i % 13)) < 1e-9 * (1 + fabs(p[i])), "parallel vectors must average: %g vs %g", p[i], c[0] * (0.25 + i % 13));
+    // random vectors, several in flight at once with other traffic (never fused with each other), bf16 in / out
+    std::vector<std::vector<float>> all(W, std::vector<float>(n));
+    for (int r = 0; r < W; r++) { std::mt19937 g(4242 + r); std::normal_distribution<float> d; for (auto& x : all[r]) x = d(g); }
+    std::vector<float> mine = all[R], other(64, 1.f);
+    std::vector<uint16_t> half(n);
+    for (int i = 0; i < n; i++) half[i] = to_bf16(all[R][i]);
+    const int h1 = ar("adasum.rand", mine.data(), mine.data(), n, HVD_F32, HVD_ADASUM, 2.0, 0.5);
+    const int h2 = ar("adasum.side", other.data(), other.data(), 64, HVD_F32);
+    const int h3 = ar("adasum.bf16", half.data(), half.data(), n, HVD_BF16, HVD_ADASUM);
+    CHECK(hvdcore_wait(h1) == 0 && hvdcore_wait(h2) == 0 && hvdcore_wait(h3) == 0, "adasum batch: %s", hvdcore_last_error());
+    CHECK(other[0] == (float)W, "side allreduce %f", other[0]);
+    auto tree = [&](std::vector<std::vector<double>> v) {
+      while (v.size() > 1) {
+        std::vector<std::vector<double>> nx;
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+          double d = 0, na = 0, nb = 0;
+          for (int k = 0; k < n; k++) { d += v[i][k] * v[i + 1][k]; na += v[i][k] * v[i][k]; nb += v[i + 1][k] * v[i + 1][k]; }
+          const double ca = na > 0 ? 1 - d / (2 * na) : 1, cb = nb > 0 ? 1 - d / (2 * nb) : 1;
+          std::vector<double> o(n);
+          for (int k = 0; k < n; k++) o[k] = ca * v[i][k] + cb * v[i + 1][k];
+          nx.push_back(o);
+        }
+        if (v.size() % 2) nx.push_back(v.back());
+        v.swap(nx);
+      }
+      return v[0];
+    };
+    std::vector<std::vector<double>> d32(W, std::vector<double>(n)), d16(W, std::vector<double>(n));
+    for (int r = 0; r < W; r++) for (int k = 0; k < n; k++) { d32[r][k] = 2.0 * all[r][k]; d16[r][k] = from_bf16(to_bf16(all[r][k])); }
+    const std::vector<double> w32 = tree(d32), w16 = tree(d16);
+    double e32 = 0, e16 = 0;
+    for (int k = 0; k < n; k++) { e32 = std::max(e32, fabs(mine[k] - 0.5 * w32[k])); e16 = std::max(e16, fabs(from_bf16(half[k]) - w16[k])); }
+    CHECK(e32 < 1e-4, "adasum f32 vs double tree: max err %g", e32);
+    CHECK(e16 < 5e-2, "adasum bf16 vs double tree: max err %g", e16);
+    int64_t bad_i[4] = {1, 2, 3, 4};
+    h = hvdcore_enqueue(HVD_ALLREDUCE, "adasum.int", bad_i, bad_i, 4, HVD_I64, HVD_ADASUM, 0, 1, 1, -1, nullptr, nullptr, 0);
+    CHECK(hvdcore_wait(h) == HVD_ERR_UNSUPPORTED, "integer Adasum must be refused on every rank");
+  }
+
   // ---- 7. agreement on the verdict, shutdown ---------------------------------------------------------------------------
   int32_t bad = g_bad, any = 0;
   int h = ar("verdict", &bad, &any, 1, HVD_I32, HVD_MAX);

@@ -304,8 +304,23 @@ def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1
     import torch
     opn = _op_name(op, average)
     if opn == "adasum":
-        from .adasum import adasum_allreduce_
-        return _Done(adasum_allreduce_(_comm(), tensor))
+        e = _engine_for(tensor)
+        if e is not None and not tensor.is_cuda and tensor.is_floating_point() and tensor.dtype in (torch.float32, torch.float64, torch.float16, torch.bfloat16):
+            # native: every rank's vector in a shared scratch segment, all ranks work on their 1/W slice of every pair of a
+            # tree level (csrc/hvd_core/hvd_core.cc: host_adasum); negotiated by name like any other engine collective
+            t = tensor if tensor.is_contiguous() else tensor.contiguous()
+            h = e.allreduce_async(t, t, name, "adasum", prescale_factor, postscale_factor)
+            h.result = tensor
+            if t is not tensor:
+                h.post = lambda _r, _t=t, _o=tensor: _o.copy_(_t)
+            return h
+        from .adasum import adasum_allreduce_   # device tensors: one allgather kernel + a local fp32 tree
+        if prescale_factor != 1.0:
+            tensor.mul_(prescale_factor)
+        adasum_allreduce_(_comm(), tensor)
+        if postscale_factor != 1.0:
+            tensor.mul_(postscale_factor)
+        return _Done(tensor)
     e = _engine_for(tensor)
     if e is not None:
         t = tensor if tensor.is_contiguous() else tensor.contiguous()

@@ -13,8 +13,12 @@ from typing import List
 import torch
 
 
+def _work(t: torch.Tensor) -> torch.Tensor:
+    return t if t.dtype == torch.float64 else t.float()     # 16-bit floats are combined in fp32, doubles stay doubles
+
+
 def adasum_pair(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    a32, b32 = a.float(), b.float()
+    a32, b32 = _work(a), _work(b)
     dot = torch.dot(a32.flatten(), b32.flatten())
     na, nb = a32.pow(2).sum(), b32.pow(2).sum()
     ca = torch.where(na > 0, 1.0 - dot / (2.0 * na.clamp_min(1e-30)), torch.ones_like(dot))
@@ -24,7 +28,7 @@ def adasum_pair(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 def adasum_tree(tensors: List[torch.Tensor]) -> torch.Tensor:
     """Pairwise (recursive-halving order) fold; N need not be a power of two."""
-    level = [t.float() for t in tensors]
+    level = [_work(t) for t in tensors]
     while len(level) > 1:
         nxt = [adasum_pair(level[i], level[i + 1]) for i in range(0, len(level) - 1, 2)]
         if len(level) % 2:
@@ -35,7 +39,7 @@ def adasum_tree(tensors: List[torch.Tensor]) -> torch.Tensor:
 
 def adasum_allreduce_(comm, tensor: torch.Tensor, stream=None) -> torch.Tensor:
     flat = tensor.contiguous().view(-1)
-    work = flat if flat.dtype in (torch.float32, torch.bfloat16, torch.float16) else flat.float()
+    work = flat if flat.dtype in (torch.float32, torch.bfloat16, torch.float16, torch.float64) else flat.float()   # the allgather kernel is byte-wise
     gathered = torch.empty(comm.world * work.numel(), dtype=work.dtype, device=work.device)
     comm.allgather(work, gathered, stream=stream)
     out = adasum_tree(list(gathered.view(comm.world, -1).unbind(0)))

@@ -27,7 +27,7 @@ LIB_PATH = Path(__file__).resolve().parent.parent / "lib" / "libb200mpi_hvd.so"
 ALLREDUCE, ALLGATHER, BROADCAST, ALLTOALL, BARRIER, JOIN, EXCHANGE = range(7)
 _DTYPES = {torch.uint8: 0, torch.int8: 1, torch.int16: 2, torch.int32: 3, torch.int64: 4, torch.float16: 5, torch.bfloat16: 6,
            torch.float32: 7, torch.float64: 8, torch.bool: 9}
-_REDOPS = {"sum": 0, "avg": 0, "min": 1, "max": 2, "prod": 3}
+_REDOPS = {"sum": 0, "avg": 0, "min": 1, "max": 2, "prod": 3, "adasum": 4}   # adasum: host float tensors (hvd_core.cc host_adasum)
 ERR_SHUTDOWN, ERR_MISMATCH, ERR_TRANSPORT, ERR_DUPLICATE, ERR_STALL = -3, -4, -5, -6, -8
 
 

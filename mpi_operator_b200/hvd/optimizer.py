@@ -287,6 +287,84 @@ class _EngineDistributedOptimizer:
         return self._opt.load_state_dict(sd)
 
 
+class _DistributedAdasumOptimizer:
+    """``DistributedOptimizer(..., op=hvd.Adasum)``: Horovod applies Adasum to the MODEL DELTAS, not to the gradients -
+    every rank takes its own optimizer step from the common starting point, the per-tensor deltas are combined with Adasum
+    (orthogonal updates add up, parallel ones average), and the combined delta is applied to the starting point, so any
+    wrapped optimizer (Adam's per-coordinate scaling included) keeps its meaning and the learning rate is NOT multiplied by
+    the world size (reference example: examples/v2beta1/horovod/tensorflow_mnist.py:126-133). Host tensors go through
+    the native engine (named async Adasum per parameter, csrc/hvd_core/hvd_core.cc: host_adasum); device tensors through
+    one allgather kernel + a local fp32 tree (hvd/adasum.py)."""
+
+    def __init__(self, optimizer, named_parameters=None, compression=None, backward_passes_per_step: int = 1,
+                 gradient_predivide_factor: float = 1.0):
+        from . import Compression
+        if compression not in (None, Compression.none):
+            raise ValueError("op=hvd.Adasum does not combine with gradient compression")
+        if float(gradient_predivide_factor) != 1.0:
+            raise ValueError("gradient_predivide_factor requires op=Average")
+        self._opt = optimizer
+        self._passes = max(1, int(backward_passes_per_step))
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.requires_grad]
+        named = list(named_parameters) if named_parameters is not None else []
+        by_id = {id(p): n for n, p in named}
+        self._names = {p: by_id.get(id(p), f"noname.{i}") for i, p in enumerate(params)}
+        if len(set(self._names.values())) != len(params):
+            raise ValueError("parameter names must be unique")
+        self._params = params
+        self._counts = {p: 0 for p in params}
+        self._step_no = 0
+        for p in params:
+            p.register_post_accumulate_grad_hook(self._hook)
+
+    def _hook(self, p):
+        self._counts[p] += 1
+
+    def synchronize(self):   # API compatibility: the collective work happens inside step()
+        return None
+
+    def step(self, closure=None):
+        from . import allreduce_async_, Adasum
+        from ..utils import fault
+        fault.injector().on_step()
+        if any(0 < c < self._passes for c in self._counts.values()):
+            return None          # still accumulating local backward passes
+        if self._passes > 1:
+            for p in self._params:
+                if p.grad is not None:
+                    p.grad.div_(self._passes)
+        start = [p.detach().clone() for p in self._params]
+        loss = self._opt.step(closure)                 # local step from the common starting point
+        handles = []
+        for p, s0 in zip(self._params, start):
+            delta = p.detach() - s0                    # zero where this rank had no gradient: neutral for Adasum
+            handles.append((allreduce_async_(delta, name=f"DistributedOptimizer.adasum.{self._names[p]}", op=Adasum), delta))
+        with torch.no_grad():
+            for (h, delta), p, s0 in zip(handles, self._params, start):
+                h.wait()
+                p.copy_(s0 + delta)
+        for p in self._params:
+            self._counts[p] = 0
+        self._step_no += 1
+        return loss
+
+    def zero_grad(self, set_to_none: bool = False):
+        return self._opt.zero_grad(set_to_none=set_to_none)
+
+    def __getattr__(self, name):
+        return getattr(self._opt, name)
+
+    @property
+    def param_groups(self):
+        return self._opt.param_groups
+
+    def state_dict(self):
+        return self._opt.state_dict()
+
+    def load_state_dict(self, sd):
+        return self._opt.load_state_dict(sd)
+
+
 _OPS = {"avg": "average", "sum": "sum", "min": "min", "max": "max", "adasum": "adasum"}
 
 
@@ -300,6 +378,9 @@ def DistributedOptimizer(optimizer, named_parameters=None, compression=None, bac
     if use_engine is None:
         use_engine = os.environ.get("B200MPI_HVD_OPTIMIZER", "") == "engine"
     needs_engine = compression not in (None, Compression.none)
+    if _op_name(op, None) == "adasum":
+        return _DistributedAdasumOptimizer(optimizer, named_parameters, compression, backward_passes_per_step,
+                                           gradient_predivide_factor)
     if (use_engine or needs_engine) and _state.get("engine") is not None and _op_name(op, None) != "adasum":
         return _EngineDistributedOptimizer(optimizer, named_parameters, compression, backward_passes_per_step, op,
                                            gradient_predivide_factor)

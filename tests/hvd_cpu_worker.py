@@ -170,6 +170,54 @@ e = torch.zeros(n)
 e[r] = 1.0
 assert torch.allclose(hvd.allreduce(e, op=hvd.Adasum), torch.ones(n))
 assert torch.allclose(hvd.allreduce(torch.ones(4), op=hvd.Adasum), torch.ones(4))
+# against the pairwise tree folded locally over the gathered vectors (with the engine: the native slice-parallel
+# implementation, hvd_core.cc host_adasum; without: one allgather + the same tree), several dtypes and an odd length
+from mpi_operator_b200.hvd.adasum import adasum_tree
+
+
+def tree64(vs):   # the same pairwise tree in float64
+    vs = [v.double() for v in vs]
+    while len(vs) > 1:
+        nxt = []
+        for i in range(0, len(vs) - 1, 2):
+            a, b = vs[i], vs[i + 1]
+            d, na, nb = torch.dot(a, b), torch.dot(a, a), torch.dot(b, b)
+            nxt.append((1 - d / (2 * na) if na > 0 else 1.0) * a + (1 - d / (2 * nb) if nb > 0 else 1.0) * b)
+        if len(vs) % 2:
+            nxt.append(vs[-1])
+        vs = nxt
+    return vs[0]
+
+
+for dt, tol in ((torch.float32, 1e-5), (torch.float64, 1e-12), (torch.bfloat16, 2e-2)):
+    gen = torch.Generator().manual_seed(100 + r)
+    v = torch.randn(1237, generator=gen, dtype=torch.float32).to(dt)
+    want = tree64(list(hvd.allgather(v.unsqueeze(0)).unbind(0)))
+    got = hvd.allreduce(v, op=hvd.Adasum, name=f"adasum.{dt}")
+    assert got.dtype == dt and torch.allclose(got.double(), want.double(), rtol=tol, atol=tol), (dt, (got.double() - want.double()).abs().max())
+    same = hvd.allgather(got.unsqueeze(0))
+    assert all(torch.equal(same[0], same[k]) for k in range(n))          # bit-identical on every rank
+assert torch.allclose(hvd.allreduce(torch.full((3,), 2.0), op=hvd.Adasum, prescale_factor=0.5, postscale_factor=4.0), torch.full((3,), 4.0))
+# DistributedOptimizer(op=Adasum) works on the model DELTAS of a local optimizer step (Horovod's semantics), so the wrapped
+# optimizer keeps its meaning: start + adasum(rank deltas) per tensor
+torch.manual_seed(7)
+am = nn.Linear(6, 3)
+hvd.broadcast_parameters(am.state_dict(), root_rank=0)
+start = [p.detach().clone() for p in am.parameters()]
+aopt = hvd.DistributedOptimizer(torch.optim.Adam(am.parameters(), lr=0.05), named_parameters=am.named_parameters(), op=hvd.Adasum)
+xg = torch.randn(4, 6, generator=torch.Generator().manual_seed(50 + r))
+aopt.zero_grad()
+am(xg).pow(2).sum().backward()
+ref_m = nn.Linear(6, 3)
+ref_m.load_state_dict({k: v.clone() for k, v in zip(am.state_dict(), start)})
+ropt = torch.optim.Adam(ref_m.parameters(), lr=0.05)
+ref_m(xg).pow(2).sum().backward()
+ropt.step()
+aopt.step()
+for p, s0, q in zip(am.parameters(), start, ref_m.parameters()):
+    deltas = hvd.allgather((q.detach() - s0).reshape(1, -1))
+    want = s0 + adasum_tree(list(deltas.unbind(0))).view_as(s0)
+    assert torch.allclose(p.detach(), want, rtol=1e-5, atol=1e-6), (p.detach() - want).abs().max()
 
 # elastic state: commit / restore / sync
 state = hvd.elastic.TorchState(model=model, optimizer=None, epoch=r, batch=7)

@@ -166,3 +166,22 @@ def test_horovod_package_layout_and_programmatic_run():
         return r, out
     res = horovod.run(sum_of_ranks, args=(10,), np=3, env={"B200MPI_HVD_DEVICE": "cpu"})
     assert res == [(0, 33.0), (1, 33.0), (2, 33.0)]
+
+
+def test_mnist_example_with_the_use_adasum_flag():
+    """The reference example's optional ``--use-adasum`` (tensorflow_mnist.py:31-32,126-133): DistributedOptimizer(op=Adasum)
+    combines the ranks' model deltas; on host tensors through the native engine (hvd_core.cc host_adasum)."""
+    import os
+    import re
+    import subprocess
+    import sys
+    repo = _repo()
+    mpirun = os.path.join(repo, "mpi_operator_b200/bin/mpirun")
+    if not os.path.exists(mpirun):
+        pytest.skip("native launcher not built (run make)")
+    env = dict(os.environ, B200MPI_HVD_DEVICE="cpu")
+    r = subprocess.run([mpirun, "-np", "2", sys.executable, os.path.join(repo, "examples/horovod/torch_mnist.py"), "--use-adasum",
+                        "--steps", "60"], capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    losses = [float(x) for x in re.findall(r"loss = ([0-9.]+)", r.stdout)]
+    assert len(losses) >= 3 and losses[-1] < 0.25 * losses[0], losses
