@@ -370,8 +370,10 @@ static int launch(const void* X, const void* W, void* Y, float* partials, int* p
 
 extern "C" {
 
+// M >= 128: every shape that ran on hardware had at least one full row tile (ragged tails - M = 196, 1000 - are covered); smaller
+// problems (a 2x2 feature map at batch 4) are latency-bound anyway and stay with the library.
 int b200mpi_gemm_bnstats_supported(long long M, int N, int K) {
-  return (M >= 1 && M < (1LL << 31) - 128 && N >= 64 && N % 64 == 0 && K >= 64 && K % 64 == 0 &&
+  return (M >= 128 && M < (1LL << 31) - 128 && N >= 64 && N % 64 == 0 && K >= 64 && K % 64 == 0 &&
           N / (N % 128 == 0 ? 128 : 64) <= 148) ? 1 : 0;
 }
 

@@ -196,8 +196,8 @@ def test_tcgen05_gemm_library_builds_loads_and_validates_shapes():
     from mpi_operator_b200.ops import gemm_bnstats as g
     if not g.LIB_PATH.exists():
         pytest.skip("native libraries not built (run make)")
-    assert g.supported(200704, 256, 64) and g.supported(1, 64, 64) and g.supported(50176, 2048, 512)
-    assert not g.supported(128, 96, 64) and not g.supported(128, 64, 32) and not g.supported(0, 64, 64)
+    assert g.supported(200704, 256, 64) and g.supported(128, 64, 64) and g.supported(50176, 2048, 512)
+    assert not g.supported(128, 96, 64) and not g.supported(128, 64, 32) and not g.supported(0, 64, 64) and not g.supported(127, 64, 64)
     assert not g.supported(128, 148 * 128 + 128, 64)
     assert g.lib().b200mpi_gemm_bnstats_partial_floats(256) == 148 * 2 * 256
     sass = subprocess.run(["/usr/local/cuda/bin/cuobjdump", "-sass", str(g.LIB_PATH)], capture_output=True, text=True)
