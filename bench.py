@@ -187,6 +187,15 @@ def supervise(args) -> int:
     base_port = os.environ.get("MASTER_PORT", "29500")
     workdir = f"/tmp/b200mpi_bench_{base_port}_{os.getppid()}"   # every rank has the same parent: unique per launch, shared by the ranks
     t_start = time.time()
+    try:
+        # The measurements run in child processes; the driver records which in-tree libraries THIS process tree loaded. Map
+        # the runtime into the supervisor as well (dlopen only: no CUDA call, no context on the GPU the children use).
+        from mpi_operator_b200.runtime import _lib as _rt
+        from mpi_operator_b200.ops import gemm_bnstats as _gemm
+        _rt.lib()
+        _gemm.lib()
+    except Exception as e:  # pragma: no cover  (a missing library fails loudly in the children)
+        print(f"[bench supervisor] could not map the runtime libraries: {e}", file=sys.stderr)
     result, used, notes, tried = None, None, [], {}
     k = 0
     for stage in stages(world):
