@@ -41,9 +41,9 @@ $(BINDIR)/mpirun: csrc/spawner/mpirun.cc
 	ln -sf mpirun $(BINDIR)/orterun
 	printf '#!/bin/sh\nexec python -m mpi_operator_b200.cmd.horovodrun "$$@"\n' > $(BINDIR)/horovodrun && chmod +x $(BINDIR)/horovodrun
 
-$(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_internal.h csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
+$(LIBDIR)/libmpi.so: csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_comm.cc csrc/mpi_shim/mpi_internal.h csrc/mpi_shim/mpi.h csrc/runtime/rendezvous.cc csrc/runtime/rendezvous.h
 	@mkdir -p $(LIBDIR) mpi_operator_b200/include
-	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/runtime/rendezvous.cc -lrt -lpthread
+	$(CXX) $(CXXFLAGS) -shared -o $@ csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_comm.cc csrc/runtime/rendezvous.cc -lrt -lpthread
 	cp csrc/mpi_shim/mpi.h mpi_operator_b200/include/mpi.h
 
 # Horovod-core equivalent: negotiation / fusion / response cache / timeline / stall inspector (host only, no CUDA link:
@@ -90,7 +90,7 @@ sanitize: all
 
 # Host-side runtime under the compiler sanitizers: launcher, shm rendezvous, libmpi shim.
 SAN_CXX  ?= /usr/bin/g++
-SAN_SRCS := csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/runtime/rendezvous.cc
+SAN_SRCS := csrc/mpi_shim/mpi_shim.cc csrc/mpi_shim/mpi_p2p.cc csrc/mpi_shim/mpi_comm.cc csrc/runtime/rendezvous.cc
 define san_build
 	@mkdir -p build/san/$(1)
 	$(SAN_CXX) -std=c++17 -O1 -g -fno-omit-frame-pointer $(2) -Icsrc/include -o build/san/$(1)/mpirun csrc/spawner/mpirun.cc
@@ -119,6 +119,8 @@ test_mpi_p2p: native
 	@mkdir -p build/san
 	$(CXX) -std=c++17 -O2 -Wall -Impi_operator_b200/include -o build/san/mpi_p2p_test csrc/tests/mpi_p2p_test.cc -L$(LIBDIR) -lmpi -Wl,-rpath,$(abspath $(LIBDIR))
 	$(BINDIR)/mpirun -n 4 build/san/mpi_p2p_test
+	$(BINDIR)/mpirun -n 5 build/san/mpi_p2p_test
+	$(BINDIR)/mpirun -n 2 build/san/mpi_p2p_test
 	$(BINDIR)/mpirun -n 1 build/san/mpi_p2p_test
 
 # the point-to-point protocol of p2p.cu run with host threads instead of CTAs (same template, host platform)

@@ -54,7 +54,8 @@ struct Request {
   bool active = false, is_recv = false, done = false;
   void* buf = nullptr;
   size_t cap = 0;
-  int src = 0, tag = 0, comm = 0;
+  int src = 0, tag = 0, comm = 0;   // src: WORLD rank (or MPI_ANY_SOURCE), comm: context id
+  MPI_Comm handle = MPI_COMM_WORLD;
   MPI_Status st{};
   int rc = MPI_SUCCESS;
 };
@@ -120,7 +121,7 @@ int drain() {
       m->src = h.src; m->tag = h.tag; m->comm = h.comm; m->id = h.msg_id; m->total = h.total;
       m->data.resize(h.total);
     }
-    if (h.offset + h.bytes <= m->total) {
+    if (h.bytes && h.offset + h.bytes <= m->total) {   // zero-byte messages (barrier tokens) carry no payload
       memcpy(m->data.data() + h.offset, pkt.data() + sizeof(Header), h.bytes);
       m->have += h.bytes;
     }
@@ -141,6 +142,9 @@ bool timed_out(const timespec& t0) {
   return (t.tv_sec - t0.tv_sec) * 1000ll + (t.tv_nsec - t0.tv_nsec) / 1000000ll > g_timeout_ms;
 }
 
+}  // namespace
+
+namespace b200mpi_mpi {
 int send_bytes(const void* buf, size_t bytes, int dest, int tag, int comm) {
   if (dest == MPI_PROC_NULL) return MPI_SUCCESS;
   if (dest < 0 || dest >= g_size) return MPI_ERR_RANK;
@@ -184,7 +188,10 @@ int send_bytes(const void* buf, size_t bytes, int dest, int tag, int comm) {
   return MPI_SUCCESS;
 }
 
-// First message in arrival order that matches (source, tag, comm); nullptr if none has started arriving.
+}  // namespace b200mpi_mpi
+
+namespace {
+// First message in arrival order that matches (source, tag, context); nullptr if none has started arriving.
 Message* find_match(int src, int tag, int comm) {
   for (auto& m : g_inbox)
     if (m.comm == comm && (src == MPI_ANY_SOURCE || m.src == src) &&
@@ -197,6 +204,9 @@ void erase_message(Message* m) {
     if (&*it == m) { g_inbox.erase(it); return; }
 }
 
+}  // namespace
+
+namespace b200mpi_mpi {
 // Blocks until a matching message is complete; copies it out. `probe_only` leaves it queued.
 int recv_bytes(void* buf, size_t cap, int src, int tag, int comm, MPI_Status* st, bool probe_only, bool blocking, int* flag) {
   if (flag) *flag = 0;
@@ -231,6 +241,24 @@ int recv_bytes(void* buf, size_t cap, int src, int tag, int comm, MPI_Status* st
   }
 }
 
+}  // namespace b200mpi_mpi
+
+namespace {
+// status->MPI_SOURCE arrives as a world rank: report the rank in the communicator the call was made on
+void to_comm_rank(MPI_Comm c, MPI_Status* st) {
+  if (!st || st->MPI_SOURCE < 0) return;
+  Comm* C = comm_of(c);
+  if (!C || C->world_like) return;
+  for (int i = 0; i < C->size(); i++)
+    if (C->ranks[i] == st->MPI_SOURCE) { st->MPI_SOURCE = i; return; }
+}
+// comm rank -> world rank (wildcards and MPI_PROC_NULL pass through); -3: out of range
+int to_world(Comm* C, int r) {
+  if (r == MPI_ANY_SOURCE || r == MPI_PROC_NULL) return r;
+  if (r < 0 || r >= C->size()) return -3;
+  return C->ranks[r];
+}
+
 int new_request() {
   for (size_t i = 0; i < g_reqs.size(); i++)
     if (!g_reqs[i].active) { g_reqs[i] = Request{}; g_reqs[i].active = true; return (int)i; }
@@ -250,6 +278,7 @@ int complete_request(int id, bool blocking, int* flag, MPI_Status* st) {
     if (r.rc != MPI_SUCCESS || got) r.done = true;
   }
   if (!r.done) { if (flag) *flag = 0; return MPI_SUCCESS; }
+  if (r.is_recv) to_comm_rank(r.handle, &r.st);
   if (st) *st = r.st;
   const int rc = r.rc;
   r.active = false;
@@ -275,15 +304,26 @@ int MPI_Send(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_
   int e = check(c); if (e) return e;
   const size_t es = type_size(t);
   if (!es || count < 0) return MPI_ERR_TYPE;
-  return send_bytes(buf, es * (size_t)count, c == MPI_COMM_SELF && dest == 0 ? g_rank : dest, tag, c);
+  Comm* C = comm_of(c);
+  const int w = to_world(C, dest);
+  if (w == -3) return MPI_ERR_RANK;
+  return send_bytes(buf, es * (size_t)count, w, tag, C->ctx);
 }
 int MPI_Ssend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c) { return MPI_Send(buf, count, t, dest, tag, c); }
+int MPI_Bsend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c) { return MPI_Send(buf, count, t, dest, tag, c); }   // every send is buffered at the receiver
+int MPI_Rsend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c) { return MPI_Send(buf, count, t, dest, tag, c); }
 
 int MPI_Recv(void* buf, int count, MPI_Datatype t, int source, int tag, MPI_Comm c, MPI_Status* st) {
   int e = check(c); if (e) return e;
   const size_t es = type_size(t);
   if (!es || count < 0) return MPI_ERR_TYPE;
-  return recv_bytes(buf, es * (size_t)count, c == MPI_COMM_SELF && source == 0 ? g_rank : source, tag, c, st, false, true, nullptr);
+  Comm* C = comm_of(c);
+  const int w = to_world(C, source);
+  if (w == -3) return MPI_ERR_RANK;
+  MPI_Status local;
+  e = recv_bytes(buf, es * (size_t)count, w, tag, C->ctx, st ? st : &local, false, true, nullptr);
+  to_comm_rank(c, st);
+  return e;
 }
 
 int MPI_Sendrecv(const void* sb, int sc, MPI_Datatype stype, int dest, int stag, void* rb, int rc_, MPI_Datatype rtype, int source, int rtag,
@@ -292,21 +332,30 @@ int MPI_Sendrecv(const void* sb, int sc, MPI_Datatype stype, int dest, int stag,
   if (e) return e;
   return MPI_Recv(rb, rc_, rtype, source, rtag, c, st);
 }
+int MPI_Sendrecv_replace(void* buf, int count, MPI_Datatype t, int dest, int stag, int source, int rtag, MPI_Comm c, MPI_Status* st) {
+  int e = MPI_Send(buf, count, t, dest, stag, c);   // the outgoing copy has left the buffer when the eager send returns
+  if (e) return e;
+  return MPI_Recv(buf, count, t, source, rtag, c, st);
+}
 
 int MPI_Isend(const void* buf, int count, MPI_Datatype t, int dest, int tag, MPI_Comm c, MPI_Request* req) {
+  const int rc = MPI_Send(buf, count, t, dest, tag, c);  // eager send completes here; the request only carries the result
   const int id = new_request();
-  g_reqs[id].rc = MPI_Send(buf, count, t, dest, tag, c);  // eager send completes here; the request only carries the result
+  g_reqs[id].rc = rc;
   g_reqs[id].done = true;
   *req = id;
-  return g_reqs[id].rc;
+  return rc;
 }
 int MPI_Irecv(void* buf, int count, MPI_Datatype t, int source, int tag, MPI_Comm c, MPI_Request* req) {
   int e = check(c); if (e) return e;
   const size_t es = type_size(t);
   if (!es || count < 0) return MPI_ERR_TYPE;
+  Comm* C = comm_of(c);
+  const int w = to_world(C, source);
+  if (w == -3) return MPI_ERR_RANK;
   const int id = new_request();
   Request& r = g_reqs[id];
-  r.is_recv = true; r.buf = buf; r.cap = es * (size_t)count; r.src = source; r.tag = tag; r.comm = c;
+  r.is_recv = true; r.buf = buf; r.cap = es * (size_t)count; r.src = w; r.tag = tag; r.comm = C->ctx; r.handle = c;
   *req = id;
   return MPI_SUCCESS;
 }
@@ -328,13 +377,88 @@ int MPI_Test(MPI_Request* req, int* flag, MPI_Status* st) {
   if (*flag) *req = MPI_REQUEST_NULL;
   return rc;
 }
+int MPI_Testall(int n, MPI_Request* reqs, int* flag, MPI_Status* sts) {
+  // all-or-nothing: peek first (a request that is not ready stays untouched), complete only when every one is ready
+  *flag = 1;
+  for (int i = 0; i < n && *flag; i++) {
+    const int id = reqs[i];
+    if (id == MPI_REQUEST_NULL) continue;
+    if (id < 0 || id >= (int)g_reqs.size() || !g_reqs[id].active) return MPI_ERR_REQUEST;
+    Request& r = g_reqs[id];
+    if (r.done) continue;
+    int got = 0;
+    r.rc = recv_bytes(r.buf, r.cap, r.src, r.tag, r.comm, &r.st, false, false, &got);
+    if (r.rc != MPI_SUCCESS || got) r.done = true; else *flag = 0;
+  }
+  if (!*flag) return MPI_SUCCESS;
+  return MPI_Waitall(n, reqs, sts);
+}
+int MPI_Testany(int n, MPI_Request* reqs, int* index, int* flag, MPI_Status* st) {
+  *index = MPI_UNDEFINED;
+  *flag = 1;
+  bool any_active = false;
+  for (int i = 0; i < n; i++) {
+    if (reqs[i] == MPI_REQUEST_NULL) continue;
+    any_active = true;
+    int f = 0;
+    const int rc = MPI_Test(&reqs[i], &f, st);
+    if (f) { *index = i; return rc; }
+  }
+  if (any_active) *flag = 0;
+  return MPI_SUCCESS;
+}
+int MPI_Waitany(int n, MPI_Request* reqs, int* index, MPI_Status* st) {
+  for (;;) {
+    int flag = 0;
+    const int rc = MPI_Testany(n, reqs, index, &flag, st);
+    if (rc || flag) return rc;
+    if (g_rv && g_rv->aborted()) return fail("job aborted while waiting");
+    wait_readable(20);
+  }
+}
+int MPI_Waitsome(int n, MPI_Request* reqs, int* outcount, int* indices, MPI_Status* sts) {
+  *outcount = 0;
+  bool any_active = false;
+  for (int i = 0; i < n; i++) any_active = any_active || reqs[i] != MPI_REQUEST_NULL;
+  if (!any_active) { *outcount = MPI_UNDEFINED; return MPI_SUCCESS; }
+  int out = MPI_SUCCESS;
+  while (*outcount == 0) {
+    for (int i = 0; i < n; i++) {
+      if (reqs[i] == MPI_REQUEST_NULL) continue;
+      int f = 0;
+      const int rc = MPI_Test(&reqs[i], &f, sts ? &sts[*outcount] : nullptr);
+      if (f) { indices[(*outcount)++] = i; if (rc && !out) out = rc; }
+    }
+    if (*outcount == 0) {
+      if (g_rv && g_rv->aborted()) return fail("job aborted while waiting");
+      wait_readable(20);
+    }
+  }
+  return out;
+}
+int MPI_Request_free(MPI_Request* req) {
+  if (*req != MPI_REQUEST_NULL && *req >= 0 && *req < (int)g_reqs.size()) g_reqs[*req].active = false;
+  *req = MPI_REQUEST_NULL;
+  return MPI_SUCCESS;
+}
+int MPI_Cancel(MPI_Request*) { return MPI_SUCCESS; }   // eager sends have completed; a posted receive simply stays unmatched
 int MPI_Probe(int source, int tag, MPI_Comm c, MPI_Status* st) {
   int e = check(c); if (e) return e;
-  return recv_bytes(nullptr, 0, source, tag, c, st, true, true, nullptr);
+  Comm* C = comm_of(c);
+  const int w = to_world(C, source);
+  if (w == -3) return MPI_ERR_RANK;
+  e = recv_bytes(nullptr, 0, w, tag, C->ctx, st, true, true, nullptr);
+  to_comm_rank(c, st);
+  return e;
 }
 int MPI_Iprobe(int source, int tag, MPI_Comm c, int* flag, MPI_Status* st) {
   int e = check(c); if (e) return e;
-  return recv_bytes(nullptr, 0, source, tag, c, st, true, false, flag);
+  Comm* C = comm_of(c);
+  const int w = to_world(C, source);
+  if (w == -3) return MPI_ERR_RANK;
+  e = recv_bytes(nullptr, 0, w, tag, C->ctx, st, true, false, flag);
+  if (*flag) to_comm_rank(c, st);
+  return e;
 }
 int MPI_Get_count(const MPI_Status* st, MPI_Datatype t, int* count) {
   const size_t es = type_size(t);
@@ -342,116 +466,5 @@ int MPI_Get_count(const MPI_Status* st, MPI_Datatype t, int* count) {
   *count = st->count_ % (int)es ? MPI_UNDEFINED : st->count_ / (int)es;
   return MPI_SUCCESS;
 }
-
-int MPI_Comm_split(MPI_Comm c, int color, int key, MPI_Comm* out) {
-  int e = check(c); if (e) return e;
-  if (c == MPI_COMM_SELF || g_size == 1) { *out = color == MPI_UNDEFINED ? MPI_COMM_NULL : c; return MPI_SUCCESS; }
-  struct CK { int color, key; } mine{color, key};
-  std::vector<CK> all(g_size);
-  e = allgather_bytes(&mine, all.data(), sizeof(CK));
-  if (e) return e;
-  if (color == MPI_UNDEFINED) { *out = MPI_COMM_NULL; return MPI_SUCCESS; }
-  int same = 0;
-  bool ordered = true;
-  for (int r = 0; r < g_size; r++) {
-    if (all[r].color == color) same++;
-    if (r > 0 && all[r].key < all[r - 1].key) ordered = false;
-  }
-  if (same == g_size && ordered) { *out = MPI_COMM_WORLD; return MPI_SUCCESS; }   // everybody together, rank order kept
-  if (same == 1) { *out = MPI_COMM_SELF; return MPI_SUCCESS; }                      // a group of one
-  return fail("MPI_Comm_split: only the trivial partitions (all ranks together in rank order, or singletons) are provided");
-}
-int MPI_Comm_split_type(MPI_Comm c, int split_type, int key, MPI_Info, MPI_Comm* out) {
-  // one box: every rank shares the node, so MPI_COMM_TYPE_SHARED groups everybody
-  return MPI_Comm_split(c, split_type == MPI_UNDEFINED ? MPI_UNDEFINED : 0, key, out);
-}
-
-// ---- vector collectives: rooted ones move data point-to-point (reserved tags above MPI_TAG_UB), Allgatherv gathers the padded
-// blocks through the mailbox allgather and unpacks
-static const int kTagGatherv = MPI_TAG_UB + 1, kTagScatterv = MPI_TAG_UB + 2, kTagScan = MPI_TAG_UB + 3;
-
-int MPI_Allgatherv(const void* sb, int sc, MPI_Datatype st, void* rb, const int* counts, const int* displs, MPI_Datatype rt, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  const size_t es = type_size(rt);
-  if (!es || type_size(st) != es) return MPI_ERR_TYPE;
-  if (c == MPI_COMM_SELF || g_size == 1) { if (sb != MPI_IN_PLACE) memmove((char*)rb + (size_t)displs[0] * es, sb, (size_t)sc * es); return MPI_SUCCESS; }
-  size_t width = 0;
-  for (int r = 0; r < g_size; r++) width = std::max(width, (size_t)counts[r] * es);
-  std::vector<unsigned char> mine(width ? width : 1, 0), all((width ? width : 1) * g_size);
-  const void* src = sb == MPI_IN_PLACE ? (const char*)rb + (size_t)displs[g_rank] * es : sb;
-  memcpy(mine.data(), src, (size_t)counts[g_rank] * es);
-  e = allgather_bytes(mine.data(), all.data(), mine.size());
-  if (e) return e;
-  for (int r = 0; r < g_size; r++) memcpy((char*)rb + (size_t)displs[r] * es, all.data() + (size_t)r * mine.size(), (size_t)counts[r] * es);
-  return MPI_SUCCESS;
-}
-
-int MPI_Gatherv(const void* sb, int sc, MPI_Datatype st, void* rb, const int* counts, const int* displs, MPI_Datatype rt, int root, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  const size_t es = type_size(st);
-  if (!es) return MPI_ERR_TYPE;
-  if (g_rank != root) return send_bytes(sb, (size_t)sc * es, root, kTagGatherv, c);
-  const size_t rs = type_size(rt);
-  for (int r = 0; r < g_size; r++) {
-    char* dst = (char*)rb + (size_t)displs[r] * rs;
-    if (r == root) { if (sb != MPI_IN_PLACE) memmove(dst, sb, (size_t)sc * es); continue; }
-    e = recv_bytes(dst, (size_t)counts[r] * rs, r, kTagGatherv, c, nullptr, false, true, nullptr);
-    if (e) return e;
-  }
-  return MPI_SUCCESS;
-}
-
-int MPI_Scatterv(const void* sb, const int* counts, const int* displs, MPI_Datatype st, void* rb, int rc_, MPI_Datatype rt, int root, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  const size_t rs = type_size(rt);
-  if (!rs) return MPI_ERR_TYPE;
-  if (g_rank != root) return recv_bytes(rb, (size_t)rc_ * rs, root, kTagScatterv, c, nullptr, false, true, nullptr);
-  const size_t es = type_size(st);
-  for (int r = 0; r < g_size; r++) {
-    const char* src = (const char*)sb + (size_t)displs[r] * es;
-    if (r == root) { if (rb != MPI_IN_PLACE) memmove(rb, src, (size_t)counts[r] * es); continue; }
-    e = send_bytes(src, (size_t)counts[r] * es, r, kTagScatterv, c);
-    if (e) return e;
-  }
-  return MPI_SUCCESS;
-}
-
-int MPI_Reduce_scatter_block(const void* sb, void* rb, int rc_, MPI_Datatype t, MPI_Op op, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  const size_t es = type_size(t);
-  if (!es) return MPI_ERR_TYPE;
-  const int n = c == MPI_COMM_SELF ? 1 : g_size;
-  std::vector<unsigned char> full((size_t)rc_ * es * n);
-  e = MPI_Allreduce(sb == MPI_IN_PLACE ? rb : sb, full.data(), rc_ * n, t, op, c);
-  if (e) return e;
-  memcpy(rb, full.data() + (size_t)(c == MPI_COMM_SELF ? 0 : g_rank) * rc_ * es, (size_t)rc_ * es);
-  return MPI_SUCCESS;
-}
-
-// inclusive / exclusive prefix reduction along the rank order: a chain of point-to-point messages
-static int scan_impl(const void* sb, void* rb, int count, MPI_Datatype t, MPI_Op op, MPI_Comm c, bool exclusive) {
-  int e = check(c); if (e) return e;
-  const size_t es = type_size(t);
-  if (!es) return MPI_ERR_TYPE;
-  const size_t bytes = es * (size_t)count;
-  std::vector<unsigned char> mine((const unsigned char*)(sb == MPI_IN_PLACE ? rb : sb), (const unsigned char*)(sb == MPI_IN_PLACE ? rb : sb) + bytes);
-  if (c == MPI_COMM_SELF || g_size == 1) { if (!exclusive && sb != MPI_IN_PLACE) memmove(rb, sb, bytes); return MPI_SUCCESS; }
-  std::vector<unsigned char> prefix(bytes);   // reduction over ranks 0 .. rank-1
-  if (g_rank > 0) {
-    e = recv_bytes(prefix.data(), bytes, g_rank - 1, kTagScan, c, nullptr, false, true, nullptr);
-    if (e) return e;
-  }
-  std::vector<unsigned char> incl = g_rank > 0 ? prefix : mine;
-  if (g_rank > 0 && !reduce_into(incl.data(), mine.data(), count, t, op)) return MPI_ERR_OP;   // prefix (op) mine, rank order preserved
-  if (g_rank + 1 < g_size) {
-    e = send_bytes(incl.data(), bytes, g_rank + 1, kTagScan, c);
-    if (e) return e;
-  }
-  if (!exclusive) memcpy(rb, incl.data(), bytes);
-  else if (g_rank > 0) memcpy(rb, prefix.data(), bytes);   // rank 0's result of MPI_Exscan is undefined
-  return MPI_SUCCESS;
-}
-int MPI_Scan(const void* sb, void* rb, int count, MPI_Datatype t, MPI_Op op, MPI_Comm c) { return scan_impl(sb, rb, count, t, op, c, false); }
-int MPI_Exscan(const void* sb, void* rb, int count, MPI_Datatype t, MPI_Op op, MPI_Comm c) { return scan_impl(sb, rb, count, t, op, c, true); }
 
 }  // extern "C"

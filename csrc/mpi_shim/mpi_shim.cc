@@ -53,7 +53,7 @@ size_t type_size(MPI_Datatype t) {
     case MPI_INT: case MPI_UNSIGNED: case MPI_FLOAT: case MPI_INT32_T: case MPI_UINT32_T: return 4;
     case MPI_LONG: case MPI_UNSIGNED_LONG: case MPI_LONG_LONG: case MPI_UNSIGNED_LONG_LONG: case MPI_DOUBLE:
     case MPI_INT64_T: case MPI_UINT64_T: return 8;
-    default: return 0;
+    default: return derived_type_size(t);
   }
 }
 
@@ -122,7 +122,7 @@ int bcast_bytes(void* buf, size_t bytes, int root) {
 
 int check(MPI_Comm c) {
   if (!g_init || g_final) return fail("MPI call outside MPI_Init/MPI_Finalize");
-  if (c != MPI_COMM_WORLD && c != MPI_COMM_SELF) return MPI_ERR_COMM;
+  if (!comm_of(c)) return MPI_ERR_COMM;
   return MPI_SUCCESS;
 }
 }  // namespace b200mpi_mpi
@@ -149,6 +149,7 @@ int MPI_Init(int*, char***) {
       g_boxes = g_rv->open_boxes(g_box, g_timeout_ms, &g_boxes_bytes);
     }
   }
+  comms_reset(true);
   g_init = true;
   return MPI_SUCCESS;
 }
@@ -170,6 +171,7 @@ int MPI_Finalize(void) {
     delete g_rv;
     g_rv = nullptr;
   }
+  comms_reset(false);
   g_final = true;
   return MPI_SUCCESS;
 }
@@ -187,10 +189,6 @@ int MPI_Abort(MPI_Comm, int code) {
   fprintf(stderr, "[libmpi b200mpi rank %d] MPI_Abort(%d)\n", g_rank, code);
   _exit(code ? code : 1);
 }
-int MPI_Comm_rank(MPI_Comm c, int* r) { int e = check(c); if (e) return e; *r = c == MPI_COMM_SELF ? 0 : g_rank; return MPI_SUCCESS; }
-int MPI_Comm_size(MPI_Comm c, int* s) { int e = check(c); if (e) return e; *s = c == MPI_COMM_SELF ? 1 : g_size; return MPI_SUCCESS; }
-int MPI_Comm_dup(MPI_Comm c, MPI_Comm* n) { *n = c; return MPI_SUCCESS; }
-int MPI_Comm_free(MPI_Comm* c) { *c = MPI_COMM_NULL; return MPI_SUCCESS; }
 int MPI_Get_processor_name(char* name, int* len) {
   const char* h = getenv("B200MPI_HOSTNAME");
   char buf[MPI_MAX_PROCESSOR_NAME];
@@ -231,18 +229,25 @@ int MPI_Error_string(int code, char* s, int* len) { *len = snprintf(s, MPI_MAX_E
 double MPI_Wtime(void) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
 double MPI_Wtick(void) { return 1e-9; }
 
+// Every collective: singleton communicators are local copies, world-like ones (all ranks in world order) take the
+// shared-memory paths below, any other communicator the point-to-point based algorithms of mpi_comm.cc.
 int MPI_Barrier(MPI_Comm c) {
   int e = check(c); if (e) return e;
-  if (c == MPI_COMM_SELF || g_size == 1) return MPI_SUCCESS;
+  Comm* C = comm_of(c);
+  if (C->size() == 1) return MPI_SUCCESS;
+  if (!C->world_like) return gen_barrier(C);
   std::string err;
   if (g_rv->barrier(g_timeout_ms, &err)) return fail(err);
   return MPI_SUCCESS;
 }
 int MPI_Bcast(void* buf, int count, MPI_Datatype t, int root, MPI_Comm c) {
   int e = check(c); if (e) return e;
-  if (c == MPI_COMM_SELF || g_size == 1) return MPI_SUCCESS;
+  Comm* C = comm_of(c);
   const size_t es = type_size(t);
   if (!es) return MPI_ERR_TYPE;
+  if (root < 0 || root >= C->size()) return MPI_ERR_ROOT;
+  if (C->size() == 1) return MPI_SUCCESS;
+  if (!C->world_like) return gen_bcast(C, buf, es * (size_t)count, root);
   return bcast_bytes(buf, es * (size_t)count, root);
 }
 // Chunk by chunk: every rank publishes its chunk; with the boxes each rank folds ONE slice of it over all ranks (rank order:
@@ -290,49 +295,72 @@ static int reduce_impl(const void* send, void* recv, int count, MPI_Datatype t, 
   }
   return rc;
 }
-int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) {
+static int reduce_any(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c, bool all) {
   int e = check(c); if (e) return e;
-  return reduce_impl(s, r, n, t, op, c == MPI_COMM_SELF ? g_rank : root, false);
-}
-int MPI_Allreduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  return reduce_impl(s, r, n, t, op, 0, true);
-}
-int MPI_Allgather(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm c) {
-  int e = check(c); if (e) return e;
-  const size_t bytes = type_size(st) * (size_t)sn;
-  if (s == MPI_IN_PLACE) {
-    std::vector<unsigned char> mine((unsigned char*)r + g_rank * bytes, (unsigned char*)r + (g_rank + 1) * bytes);
-    return allgather_bytes(mine.data(), r, bytes);
+  Comm* C = comm_of(c);
+  if (!all && (root < 0 || root >= C->size())) return MPI_ERR_ROOT;
+  if (C->size() == 1) {
+    const size_t es = type_size(t);
+    if (!es) return MPI_ERR_TYPE;
+    if (s != MPI_IN_PLACE) memmove(r, s, es * (size_t)n);
+    return MPI_SUCCESS;
   }
-  return allgather_bytes(s, r, bytes);
+  if (!C->world_like) return gen_reduce(C, s, r, (size_t)n, t, op, root, all);
+  MPI_Datatype base; size_t cnt;
+  if (!flatten_type(t, (size_t)n, &base, &cnt)) return MPI_ERR_TYPE;
+  return reduce_impl(s, r, (int)cnt, base, op, root, all);
 }
-int MPI_Gather(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, int root, MPI_Comm c) {
+int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) { return reduce_any(s, r, n, t, op, root, c, false); }
+int MPI_Allreduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, MPI_Comm c) { return reduce_any(s, r, n, t, op, 0, c, true); }
+int MPI_Allgather(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, MPI_Comm c) {
   int e = check(c); if (e) return e;
-  const size_t bytes = type_size(st) * (size_t)sn;
-  std::vector<unsigned char> all(bytes * g_size);
-  e = allgather_bytes(s, all.data(), bytes);
-  if (!e && g_rank == root) memcpy(r, all.data(), all.size());
+  Comm* C = comm_of(c);
+  const size_t bytes = s == MPI_IN_PLACE ? type_size(rt) * (size_t)rn : type_size(st) * (size_t)sn;
+  if (s == MPI_IN_PLACE) {
+    std::vector<unsigned char> mine((unsigned char*)r + (size_t)C->my * bytes, (unsigned char*)r + (size_t)(C->my + 1) * bytes);
+    if (C->size() == 1) return MPI_SUCCESS;
+    return C->world_like ? allgather_bytes(mine.data(), r, bytes) : gen_allgather(C, mine.data(), r, bytes);
+  }
+  if (C->size() == 1) { memmove(r, s, bytes); return MPI_SUCCESS; }
+  return C->world_like ? allgather_bytes(s, r, bytes) : gen_allgather(C, s, r, bytes);
+}
+int MPI_Gather(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm c) {
+  int e = check(c); if (e) return e;
+  Comm* C = comm_of(c);
+  if (root < 0 || root >= C->size()) return MPI_ERR_ROOT;
+  const bool in_place = s == MPI_IN_PLACE;   // only meaningful at the root: its block is already in place
+  const size_t bytes = in_place ? type_size(rt) * (size_t)rn : type_size(st) * (size_t)sn;
+  if (C->size() == 1) { if (!in_place) memmove(r, s, bytes); return MPI_SUCCESS; }
+  std::vector<unsigned char> all(bytes * (size_t)C->size());
+  const void* mine = in_place ? (const char*)r + (size_t)C->my * bytes : s;
+  e = C->world_like ? allgather_bytes(mine, all.data(), bytes) : gen_allgather(C, mine, all.data(), bytes);
+  if (!e && C->my == root) memcpy(r, all.data(), all.size());
   return e;
 }
-int MPI_Scatter(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, int root, MPI_Comm c) {
+int MPI_Scatter(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, int root, MPI_Comm c) {
   int e = check(c); if (e) return e;
-  const size_t bytes = type_size(st) * (size_t)sn;
-  std::vector<unsigned char> all(bytes * g_size);
-  if (g_rank == root) memcpy(all.data(), s, all.size());
-  if (g_size > 1) { e = bcast_bytes(all.data(), all.size(), root); if (e) return e; }
-  memcpy(r, all.data() + (size_t)g_rank * bytes, bytes);
+  Comm* C = comm_of(c);
+  if (root < 0 || root >= C->size()) return MPI_ERR_ROOT;
+  const size_t bytes = C->my == root ? type_size(st) * (size_t)sn : type_size(rt) * (size_t)rn;
+  if (C->size() == 1) { if (r != MPI_IN_PLACE) memmove(r, s, bytes); return MPI_SUCCESS; }
+  std::vector<unsigned char> all(bytes * (size_t)C->size());
+  if (C->my == root) memcpy(all.data(), s, all.size());
+  e = C->world_like ? bcast_bytes(all.data(), all.size(), root) : gen_bcast(C, all.data(), all.size(), root);
+  if (e) return e;
+  if (r != MPI_IN_PLACE) memcpy(r, all.data() + (size_t)C->my * bytes, bytes);
   return MPI_SUCCESS;
 }
 // Pairwise exchange: in step k rank r publishes the block for rank (r + k) % W in its box and reads the block rank (r - k) % W
 // published for it — W - 1 steps of `bytes` per rank instead of gathering every rank's whole send buffer everywhere.
-int MPI_Alltoall(const void* s, int sn, MPI_Datatype st, void* r, int, MPI_Datatype, MPI_Comm c) {
+int MPI_Alltoall(const void* s, int sn, MPI_Datatype st, void* r, int rn, MPI_Datatype rt, MPI_Comm c) {
   int e = check(c); if (e) return e;
-  const size_t bytes = type_size(st) * (size_t)sn;
-  if (c == MPI_COMM_SELF || g_size == 1) { if (r != s) memmove(r, s, bytes); return MPI_SUCCESS; }
+  Comm* C = comm_of(c);
+  const size_t bytes = s == MPI_IN_PLACE ? type_size(rt) * (size_t)rn : type_size(st) * (size_t)sn;
+  if (C->size() == 1) { if (s != MPI_IN_PLACE && r != s) memmove(r, s, bytes); return MPI_SUCCESS; }
   std::vector<unsigned char> tmp;
   const unsigned char* src = static_cast<const unsigned char*>(s);
-  if (s == MPI_IN_PLACE) { tmp.assign((unsigned char*)r, (unsigned char*)r + bytes * g_size); src = tmp.data(); }
+  if (s == MPI_IN_PLACE) { tmp.assign((unsigned char*)r, (unsigned char*)r + bytes * (size_t)C->size()); src = tmp.data(); }
+  if (!C->world_like) return gen_alltoall(C, src, r, bytes);
   memcpy((char*)r + (size_t)g_rank * bytes, src + (size_t)g_rank * bytes, bytes);
   std::string err;
   const size_t chunk = box_bytes();

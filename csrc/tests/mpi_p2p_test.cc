@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 static int g_bad = 0, g_rank = 0;
@@ -161,6 +162,176 @@ int main(int argc, char** argv) {
     MPI_Comm_size(self, &ls);
     EXPECT(ls == 1);
     EXPECT(MPI_Comm_split(MPI_COMM_WORLD, MPI_UNDEFINED, 0, &none) == MPI_SUCCESS && none == MPI_COMM_NULL);
+  }
+
+  // 9. real sub-communicators: parity split with reversed order, every collective inside it, traffic stays inside its context
+  {
+    MPI_Comm half;
+    EXPECT(MPI_Comm_split(MPI_COMM_WORLD, r % 2, -r, &half) == MPI_SUCCESS && half != MPI_COMM_NULL);
+    int hr = -1, hs = -1;
+    MPI_Comm_rank(half, &hr);
+    MPI_Comm_size(half, &hs);
+    const int members = (n + 1 - (r % 2)) / 2;                 // ranks of my parity
+    std::vector<int> mine_world;                                // world ranks of my communicator, in ITS order (descending: key = -r)
+    for (int k = n - 1; k >= 0; k--) if (k % 2 == r % 2) mine_world.push_back(k);
+    EXPECT(hs == members && hr >= 0 && hr < hs && mine_world[hr] == r);
+    int sum = 0, want = 0;
+    for (int k : mine_world) want += k + 1;
+    int v = r + 1;
+    EXPECT(MPI_Allreduce(&v, &sum, 1, MPI_INT, MPI_SUM, half) == MPI_SUCCESS && sum == want);
+    double d[3] = {r * 1.5, 2.0, -r * 1.0}, dmax[3] = {0, 0, 0};
+    EXPECT(MPI_Reduce(d, dmax, 3, MPI_DOUBLE, MPI_MAX, hs - 1, half) == MPI_SUCCESS);
+    if (hr == hs - 1) EXPECT(dmax[0] == mine_world[0] * 1.5 && dmax[1] == 2.0 && dmax[2] == -mine_world[hs - 1] * 1.0);
+    int token = hr == 0 ? 4242 + r : -1;
+    EXPECT(MPI_Bcast(&token, 1, MPI_INT, 0, half) == MPI_SUCCESS && token == 4242 + mine_world[0]);
+    std::vector<int> gathered(hs, -1);
+    EXPECT(MPI_Allgather(&r, 1, MPI_INT, gathered.data(), 1, MPI_INT, half) == MPI_SUCCESS && gathered == mine_world);
+    std::vector<int> a2a_in(hs), a2a_out(hs, -1);
+    for (int k = 0; k < hs; k++) a2a_in[k] = 1000 * r + k;
+    EXPECT(MPI_Alltoall(a2a_in.data(), 1, MPI_INT, a2a_out.data(), 1, MPI_INT, half) == MPI_SUCCESS);
+    for (int k = 0; k < hs; k++) EXPECT(a2a_out[k] == 1000 * mine_world[k] + hr);
+    EXPECT(MPI_Barrier(half) == MPI_SUCCESS);
+    std::vector<int> root_all(hs, -1);
+    MPI_Gather(&v, 1, MPI_INT, root_all.data(), 1, MPI_INT, 0, half);
+    if (hr == 0) for (int k = 0; k < hs; k++) EXPECT(root_all[k] == mine_world[k] + 1);
+    int piece = -1;
+    std::vector<int> pieces(hs);
+    for (int k = 0; k < hs; k++) pieces[k] = 7 * k + r;
+    MPI_Scatter(pieces.data(), 1, MPI_INT, &piece, 1, MPI_INT, hs - 1, half);
+    EXPECT(piece == 7 * hr + mine_world[hs - 1]);
+    int inc = 0;
+    MPI_Scan(&v, &inc, 1, MPI_INT, MPI_SUM, half);
+    int pref = 0;
+    for (int k = 0; k <= hr; k++) pref += mine_world[k] + 1;
+    EXPECT(inc == pref);
+    std::vector<int> contrib(hs, r), got1(1, -1);
+    MPI_Reduce_scatter_block(contrib.data(), got1.data(), 1, MPI_INT, MPI_SUM, half);
+    int wsum = 0;
+    for (int k : mine_world) wsum += k;
+    EXPECT(got1[0] == wsum);
+    // ragged exchange inside the sub-communicator: rank i sends i + 1 copies of its world rank to everybody
+    std::vector<int> sc(hs, hr + 1), sd(hs, 0), rc2(hs), rd(hs);
+    int tot = 0;
+    for (int k = 0; k < hs; k++) { rc2[k] = k + 1; rd[k] = tot; tot += k + 1; }
+    std::vector<int> sbuf(hr + 1, r), rbuf(tot, -1);
+    EXPECT(MPI_Alltoallv(sbuf.data(), sc.data(), sd.data(), MPI_INT, rbuf.data(), rc2.data(), rd.data(), MPI_INT, half) == MPI_SUCCESS);
+    for (int k = 0; k < hs; k++) for (int i = 0; i <= k; i++) EXPECT(rbuf[rd[k] + i] == mine_world[k]);
+    // point-to-point inside the communicator: comm ranks address it, status reports comm ranks, the same (source, tag) on
+    // MPI_COMM_WORLD is a different message
+    if (hs > 1) {
+      const int nxt = (hr + 1) % hs, prv = (hr + hs - 1) % hs;
+      int out_h = 500 + r, out_w = 900 + r, in_h = -1, in_w = -1;
+      MPI_Send(&out_w, 1, MPI_INT, mine_world[nxt], 77, MPI_COMM_WORLD);   // same peer, same tag, other communicator - sent FIRST
+      MPI_Send(&out_h, 1, MPI_INT, nxt, 77, half);
+      MPI_Status st;
+      EXPECT(MPI_Recv(&in_h, 1, MPI_INT, MPI_ANY_SOURCE, 77, half, &st) == MPI_SUCCESS && in_h == 500 + mine_world[prv] && st.MPI_SOURCE == prv);
+      EXPECT(MPI_Recv(&in_w, 1, MPI_INT, mine_world[prv], 77, MPI_COMM_WORLD, &st) == MPI_SUCCESS && in_w == 900 + mine_world[prv] && st.MPI_SOURCE == mine_world[prv]);
+    }
+    // nested split, dup, compare, free
+    MPI_Comm solo, twin;
+    EXPECT(MPI_Comm_split(half, hr, 0, &solo) == MPI_SUCCESS);
+    int ss = 0;
+    MPI_Comm_size(solo, &ss);
+    EXPECT(ss == 1);
+    int alone = 5, alone_out = 0;
+    EXPECT(MPI_Allreduce(&alone, &alone_out, 1, MPI_INT, MPI_SUM, solo) == MPI_SUCCESS && alone_out == 5);   // a singleton reduces to itself
+    EXPECT(MPI_Allreduce(&alone, &alone_out, 1, MPI_INT, MPI_SUM, MPI_COMM_SELF) == MPI_SUCCESS && alone_out == 5);
+    EXPECT(MPI_Comm_dup(half, &twin) == MPI_SUCCESS && twin != half);
+    int cmp = -1;
+    MPI_Comm_compare(half, twin, &cmp);
+    EXPECT(cmp == MPI_CONGRUENT);
+    MPI_Comm_compare(half, half, &cmp);
+    EXPECT(cmp == MPI_IDENT);
+    MPI_Comm_compare(half, MPI_COMM_WORLD, &cmp);
+    EXPECT(cmp == (n == 1 ? MPI_CONGRUENT : MPI_UNEQUAL));
+    int s2 = 0;
+    EXPECT(MPI_Allreduce(&v, &s2, 1, MPI_INT, MPI_SUM, twin) == MPI_SUCCESS && s2 == want);
+    MPI_Comm wdup;
+    EXPECT(MPI_Comm_dup(MPI_COMM_WORLD, &wdup) == MPI_SUCCESS);
+    long long big_sum = 0, mine_ll = r + 1;
+    EXPECT(MPI_Allreduce(&mine_ll, &big_sum, 1, MPI_LONG_LONG, MPI_SUM, wdup) == MPI_SUCCESS && big_sum == (long long)n * (n + 1) / 2);
+    MPI_Comm_free(&solo); MPI_Comm_free(&twin); MPI_Comm_free(&wdup); MPI_Comm_free(&half);
+    EXPECT(half == MPI_COMM_NULL && MPI_Barrier(half) == MPI_ERR_COMM);
+  }
+
+  // 10. groups -> MPI_Comm_create; contiguous derived types; nonblocking collectives and the request family
+  {
+    MPI_Group world_g, ends_g;
+    MPI_Comm_group(MPI_COMM_WORLD, &world_g);
+    int gs = 0, gr = -1;
+    MPI_Group_size(world_g, &gs);
+    MPI_Group_rank(world_g, &gr);
+    EXPECT(gs == n && gr == r);
+    const int pick[2] = {n - 1, 0};
+    MPI_Group_incl(world_g, n > 1 ? 2 : 1, pick, &ends_g);
+    MPI_Comm ends;
+    EXPECT(MPI_Comm_create(MPI_COMM_WORLD, ends_g, &ends) == MPI_SUCCESS);
+    if (r == 0 || r == n - 1) {
+      int er = -1, es = 0;
+      MPI_Comm_rank(ends, &er);
+      MPI_Comm_size(ends, &es);
+      EXPECT(es == (n > 1 ? 2 : 1) && er == (r == n - 1 ? 0 : 1 % es));
+      int x = r, mx = -1;
+      EXPECT(MPI_Allreduce(&x, &mx, 1, MPI_INT, MPI_MAX, ends) == MPI_SUCCESS && mx == n - 1);
+      MPI_Comm_free(&ends);
+    } else {
+      EXPECT(ends == MPI_COMM_NULL);
+    }
+    int tr[2] = {0, n - 1}, tb[2] = {-9, -9};
+    MPI_Group_translate_ranks(world_g, 2, tr, ends_g, tb);
+    EXPECT(tb[0] == (n > 1 ? 1 : 0) && tb[1] == 0);
+    MPI_Group_free(&world_g); MPI_Group_free(&ends_g);
+
+    MPI_Datatype triple;
+    EXPECT(MPI_Type_contiguous(3, MPI_DOUBLE, &triple) == MPI_SUCCESS && MPI_Type_commit(&triple) == MPI_SUCCESS);
+    int tsz = 0;
+    MPI_Type_size(triple, &tsz);
+    EXPECT(tsz == 24);
+    double pts[6] = {1.0 * r, 2.0, 3.0, 4.0, 5.0, 6.0 + r}, tot[6] = {0, 0, 0, 0, 0, 0};
+    EXPECT(MPI_Allreduce(pts, tot, 2, triple, MPI_SUM, MPI_COMM_WORLD) == MPI_SUCCESS);
+    EXPECT(tot[0] == n * (n - 1) / 2.0 && tot[1] == 2.0 * n && tot[5] == 6.0 * n + n * (n - 1) / 2.0);
+    double moved[3] = {-1, -1, -1};
+    MPI_Sendrecv(pts, 1, triple, (r + 1) % n, 90, moved, 1, triple, (r + n - 1) % n, 90, MPI_COMM_WORLD, MPI_STATUS_IGNORE);
+    EXPECT(moved[0] == 1.0 * ((r + n - 1) % n) && moved[2] == 3.0);
+    MPI_Type_free(&triple);
+
+    MPI_Request rq[3];
+    int bsum = 0, one = 1, bval = r == 0 ? 31337 : 0;
+    EXPECT(MPI_Iallreduce(&one, &bsum, 1, MPI_INT, MPI_SUM, MPI_COMM_WORLD, &rq[0]) == MPI_SUCCESS);
+    EXPECT(MPI_Ibcast(&bval, 1, MPI_INT, 0, MPI_COMM_WORLD, &rq[1]) == MPI_SUCCESS);
+    EXPECT(MPI_Ibarrier(MPI_COMM_WORLD, &rq[2]) == MPI_SUCCESS);
+    int all_done = 0;
+    EXPECT(MPI_Testall(3, rq, &all_done, MPI_STATUSES_IGNORE) == MPI_SUCCESS && all_done == 1 && bsum == n && bval == 31337);
+    // Waitany / Waitsome / Testany over receives that complete in a known order
+    int in3[3] = {-1, -1, -1};
+    MPI_Request rr[3];
+    for (int k = 0; k < 3; k++) MPI_Irecv(&in3[k], 1, MPI_INT, r, 200 + k, MPI_COMM_WORLD, &rr[k]);
+    int idx = -1, flag = -1;
+    EXPECT(MPI_Testany(3, rr, &idx, &flag, MPI_STATUS_IGNORE) == MPI_SUCCESS && flag == 0);   // nothing sent yet
+    int payload = 61;
+    MPI_Send(&payload, 1, MPI_INT, r, 201, MPI_COMM_WORLD);
+    EXPECT(MPI_Waitany(3, rr, &idx, MPI_STATUS_IGNORE) == MPI_SUCCESS && idx == 1 && in3[1] == 61 && rr[1] == MPI_REQUEST_NULL);
+    payload = 62;
+    MPI_Send(&payload, 1, MPI_INT, r, 200, MPI_COMM_WORLD);
+    payload = 63;
+    MPI_Send(&payload, 1, MPI_INT, r, 202, MPI_COMM_WORLD);
+    int outc = 0, which[3] = {-1, -1, -1}, seen = 0;
+    while (seen < 2) { EXPECT(MPI_Waitsome(3, rr, &outc, which, MPI_STATUSES_IGNORE) == MPI_SUCCESS && outc >= 1); seen += outc; }
+    EXPECT(in3[0] == 62 && in3[2] == 63);
+    EXPECT(MPI_Waitsome(3, rr, &outc, which, MPI_STATUSES_IGNORE) == MPI_SUCCESS && outc == MPI_UNDEFINED);   // every request is null now
+    int vec[4] = {r, r, r, r}, part1 = -1;
+    std::vector<int> cnts(n, 0);
+    cnts[r] = 0;
+    for (int k = 0; k < n; k++) cnts[k] = k == 0 ? 1 : 0;    // everything reduced lands on rank 0
+    int onev = r + 1;
+    MPI_Reduce_scatter(&onev, &part1, cnts.data(), MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+    if (r == 0) EXPECT(part1 == n * (n + 1) / 2);
+    (void)vec;
+    MPI_Comm_set_errhandler(MPI_COMM_WORLD, MPI_ERRORS_RETURN);
+    char nm[MPI_MAX_OBJECT_NAME];
+    int nl = 0;
+    MPI_Comm_get_name(MPI_COMM_WORLD, nm, &nl);
+    EXPECT(std::string(nm) == "MPI_COMM_WORLD");
   }
 
   int any = 0;
