@@ -300,6 +300,8 @@ def cmd_run(a) -> int:
 def main(argv: Optional[List[str]] = None) -> int:
     ap = argparse.ArgumentParser(prog="mpijobctl")
     ap.add_argument("--server", default=os.environ.get("MPIJOB_SERVER", "127.0.0.1:8087"))
+    ap.add_argument("--token-file", default=os.environ.get("MPIJOB_TOKEN_FILE", ""),
+                    help="bearer token of a daemon started with --auth-token-file (also: $MPIJOB_TOKEN)")
     ap.add_argument("-n", "--namespace", default="default")
     sub = ap.add_subparsers(dest="cmd", required=True)
     for name in ("apply", "create"):
@@ -352,6 +354,8 @@ def main(argv: Optional[List[str]] = None) -> int:
         from .. import version
         print(json.dumps(version.info()))
         return 0
+    if a.token_file:
+        os.environ["MPIJOB_TOKEN_FILE"] = a.token_file   # picked up by the SDK's Configuration
     cli = MPIJobClient(a.server)
     if a.cmd in ("apply", "create"):
         return cmd_apply(cli, a)

@@ -37,6 +37,7 @@ class ServerOption:
     fake_gpus: Optional[int] = None
     verbosity: int = 0
     leader_elect: bool = True
+    auth_token_file: str = ""   # non-empty: the object API wants `Authorization: Bearer <token>` (created 0600 if missing)
 
 
 def add_flags(p: argparse.ArgumentParser) -> None:
@@ -70,6 +71,10 @@ def add_flags(p: argparse.ArgumentParser) -> None:
     p.add_argument("--vmodule", default="", help=argparse.SUPPRESS)
     p.add_argument("--skip_headers", "--skip-headers", dest="skip_headers", nargs="?", const="true", default="", help=argparse.SUPPRESS)
     p.add_argument("--no-leader-elect", dest="leader_elect", action="store_false")
+    p.add_argument("--auth-token-file", default=os.environ.get("MPIJOB_TOKEN_FILE", ""),
+                   help="require `Authorization: Bearer <token>` on the object API; the file is created (mode 0600, random token) "
+                        "if it does not exist. The reference relies on the cluster's RBAC (manifests/base/cluster-role.yaml); on one "
+                        "box this is what keeps other local users from creating pods (= running commands as the daemon's user)")
 
 
 def parse(argv: Optional[List[str]] = None) -> ServerOption:

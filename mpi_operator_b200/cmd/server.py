@@ -139,6 +139,7 @@ class Operator:
         self.opt = opt or ServerOption()
         self.state_dir = self.opt.state_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), f"b200mpi-operator-{os.getpid()}")
         os.makedirs(self.state_dir, exist_ok=True)
+        self.auth_token = _load_or_create_token(self.opt.auth_token_file) if self.opt.auth_token_file else ""
         if self.opt.fake_gpus is not None:
             os.environ["B200MPI_FAKE_GPUS"] = str(self.opt.fake_gpus)
         self.store = store or ObjectStore(os.path.join(self.state_dir, "store.json") if self.opt.state_dir else None)
@@ -206,6 +207,23 @@ class Operator:
         return srv
 
 
+def _load_or_create_token(path: str) -> str:
+    """--auth-token-file: read the bearer token, or create the file (0600) with a random one on first start."""
+    import secrets
+    try:
+        with open(path) as f:
+            tok = f.read().strip()
+        if tok:
+            return tok
+    except FileNotFoundError:
+        pass
+    tok = secrets.token_urlsafe(32)
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o600)
+    with os.fdopen(fd, "w") as f:
+        f.write(tok + "\n")
+    return tok
+
+
 def _make_handler(op: Operator, restricted: bool = False):
     store = op.store
 
@@ -213,9 +231,23 @@ def _make_handler(op: Operator, restricted: bool = False):
         protocol_version = "HTTP/1.1"
 
         def _refuse(self):
-            """Restricted listeners (monitoring / healthz ports): nothing but GET /metrics and GET /healthz."""
+            """Restricted listeners (monitoring / healthz ports): nothing but GET /metrics and GET /healthz. The object API
+            with --auth-token-file: everything but GET /healthz and /version needs the bearer token (401 otherwise)."""
             if not restricted:
-                return False
+                token = getattr(op, "auth_token", "")
+                if not token or (self.command == "GET" and self._route()[0] in (["healthz"], ["version"])):
+                    return False
+                import hmac
+                got = self.headers.get("Authorization", "")
+                if got.startswith("Bearer ") and hmac.compare_digest(got[7:].strip().encode(), token.encode()):
+                    return False
+                n = int(self.headers.get("Content-Length", 0) or 0)
+                if n:
+                    self.rfile.read(n)   # keep the connection in step (HTTP/1.1 keep-alive)
+                self._send(401, {"kind": "Status", "apiVersion": "v1", "status": "Failure", "reason": "Unauthorized", "code": 401,
+                                 "message": "Unauthorized: this daemon was started with --auth-token-file; send "
+                                            "'Authorization: Bearer <token>' (clients read MPIJOB_TOKEN or MPIJOB_TOKEN_FILE)"})
+                return True
             if self.command == "GET" and self._route()[0] in (["metrics"], ["healthz"]):
                 return False
             self._send(404 if self.command == "GET" else 405, {"kind": "Status", "status": "Failure", "code": 404 if self.command == "GET" else 405,

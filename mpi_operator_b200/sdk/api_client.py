@@ -120,6 +120,7 @@ class ApiClient:
         for k, v in (path_params or {}).items():
             resource_path = resource_path.replace("{%s}" % k, str(v))
         headers = dict(self.default_headers)
+        headers.update(self.configuration.auth_headers() if hasattr(self.configuration, "auth_headers") else {})
         headers.update(header_params or {})
         url = (_host or self.configuration.host) + resource_path
         resp = self.rest_client.request(method, url, query_params=query_params, headers=headers,

@@ -145,7 +145,8 @@ class MPIJobClient:
         u = urllib.parse.urlparse(self.api.configuration.host)
         conn = http.client.HTTPConnection(u.hostname, u.port or 80, timeout=timeout + 10)
         try:
-            conn.request("GET", self._path("pods", namespace, pod, "log") + f"?follow=true&timeoutSeconds={float(timeout)!r}")
+            conn.request("GET", self._path("pods", namespace, pod, "log") + f"?follow=true&timeoutSeconds={float(timeout)!r}",
+                         headers=self.api.configuration.auth_headers())
             resp = conn.getresponse()
             if resp.status != 200:
                 raise ApiException(status=resp.status, reason=resp.reason, body=resp.read())
@@ -172,7 +173,7 @@ class MPIJobClient:
             q["fieldSelector"] = f"metadata.name={name}"
         conn = http.client.HTTPConnection(u.hostname, u.port or 80, timeout=timeout + 10)
         try:
-            conn.request("GET", self._path(resource, namespace) + "?" + urllib.parse.urlencode(q))
+            conn.request("GET", self._path(resource, namespace) + "?" + urllib.parse.urlencode(q), headers=self.api.configuration.auth_headers())
             resp = conn.getresponse()
             if resp.status != 200:
                 raise ApiException(status=resp.status, reason=resp.reason, body=resp.read())

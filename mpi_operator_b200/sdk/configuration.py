@@ -8,6 +8,19 @@ import os
 import sys
 
 
+def default_token() -> str:
+    """Bearer token for a daemon started with --auth-token-file: $MPIJOB_TOKEN, else the content of $MPIJOB_TOKEN_FILE."""
+    tok = os.environ.get("MPIJOB_TOKEN", "")
+    path = os.environ.get("MPIJOB_TOKEN_FILE", "")
+    if not tok and path:
+        try:
+            with open(path) as f:
+                tok = f.read().strip()
+        except OSError:
+            tok = ""
+    return tok
+
+
 class Configuration:
     _default = None
 
@@ -17,6 +30,10 @@ class Configuration:
         self.temp_folder_path = None
         self.api_key = dict(api_key or {})
         self.api_key_prefix = dict(api_key_prefix or {})
+        if "authorization" not in self.api_key:   # daemon started with --auth-token-file: MPIJOB_TOKEN or MPIJOB_TOKEN_FILE
+            tok = default_token()
+            if tok:
+                self.api_key["authorization"], self.api_key_prefix["authorization"] = tok, "Bearer"
         self.refresh_api_key_hook = None
         self.username, self.password = username, password
         self.discard_unknown_keys = discard_unknown_keys
@@ -91,7 +108,12 @@ class Configuration:
         return "Basic " + base64.b64encode(f"{self.username or ''}:{self.password or ''}".encode()).decode()
 
     def auth_settings(self):
-        return {}
+        tok = self.get_api_key_with_prefix("authorization")
+        return {"BearerToken": {"type": "api_key", "in": "header", "key": "authorization", "value": tok}} if tok else {}
+
+    def auth_headers(self) -> dict:
+        tok = self.get_api_key_with_prefix("authorization")
+        return {"Authorization": tok} if tok else {}
 
     def to_debug_report(self):
         return ("Python SDK Debug Report:\n"

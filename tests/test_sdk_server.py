@@ -143,6 +143,53 @@ def test_monitoring_port_serves_metrics_and_healthz_only(tmp_path):
         op.stop()
 
 
+def test_auth_token_file_protects_the_object_api(tmp_path, monkeypatch):
+    """--auth-token-file: the reference leans on the cluster's RBAC (manifests/base/cluster-role.yaml); on a shared box the
+    loopback API would otherwise let any local user create pods (= run commands as the daemon's user) and read Secrets."""
+    import stat
+    port, mon = _free_port(), _free_port()
+    tok_file = tmp_path / "token"
+    op = Operator(ServerOption(fake_gpus=0, leader_elect=False, state_dir=str(tmp_path / "state"), auth_token_file=str(tok_file)))
+    op.serve(f"127.0.0.1:{port}")
+    op.serve(f"127.0.0.1:{mon}", restricted=True)
+    op.start()
+    try:
+        token = tok_file.read_text().strip()
+        assert len(token) >= 32 and stat.S_IMODE(os.stat(tok_file).st_mode) == 0o600
+        base = f"http://127.0.0.1:{port}"
+        assert urllib.request.urlopen(base + "/healthz").read() == b"ok"            # liveness stays open
+        assert "mpi_operator_jobs_created_total" in urllib.request.urlopen(f"http://127.0.0.1:{mon}/metrics").read().decode()
+        pod = {"apiVersion": "v1", "kind": "Pod", "metadata": {"name": "evil"}, "spec": {"containers": [{"name": "c", "command": ["true"]}]}}
+        for method, path, body in (("GET", "/api/v1/secrets", None), ("GET", "/apis/kubeflow.org/v2beta1/namespaces/default/mpijobs", None),
+                                   ("GET", "/metrics", None), ("POST", "/api/v1/namespaces/default/pods", pod),
+                                   ("DELETE", "/api/v1/namespaces/default/pods/evil", None)):
+            for hdr in ({}, {"Authorization": "Bearer wrong"}, {"Authorization": token}):
+                req = urllib.request.Request(base + path, data=json.dumps(body).encode() if body else None, method=method,
+                                             headers={"Content-Type": "application/json", **hdr})
+                with pytest.raises(urllib.error.HTTPError) as e:
+                    urllib.request.urlopen(req)
+                assert e.value.code == 401 and json.load(e.value)["reason"] == "Unauthorized"
+        assert op.store.list("pods", "default") == []
+        monkeypatch.delenv("MPIJOB_TOKEN", raising=False)
+        monkeypatch.delenv("MPIJOB_TOKEN_FILE", raising=False)
+        from mpi_operator_b200.sdk.exceptions import UnauthorizedException
+        with pytest.raises(UnauthorizedException):
+            mpijob.MPIJobClient(f"127.0.0.1:{port}").list()
+        monkeypatch.setenv("MPIJOB_TOKEN_FILE", str(tok_file))                       # what mpijobctl and the SDK read
+        cli = mpijob.MPIJobClient(f"127.0.0.1:{port}")
+        assert cli.list() == []
+        events = list(cli.watch("mpijobs", "default", timeout=0.3))
+        assert events == []
+        monkeypatch.delenv("MPIJOB_TOKEN_FILE")
+        monkeypatch.setenv("MPIJOB_TOKEN", token)
+        assert mpijob.MPIJobClient(f"127.0.0.1:{port}").list() == []
+        # a second daemon on the same file adopts the token instead of replacing it
+        from mpi_operator_b200.cmd.server import _load_or_create_token
+        assert _load_or_create_token(str(tok_file)) == token
+    finally:
+        op.stop()
+
+
 def test_models_match_the_reference_sdk_when_installed():
     """Parity against the UNMODIFIED reference SDK installed at baseline/_ref (pip --target of
     /root/reference/sdk/python/v2beta1): same openapi_types and attribute_map for all 9 MPIJob models."""
