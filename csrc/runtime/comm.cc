@@ -155,9 +155,15 @@ struct b200mpi_comm {
   int pipe_lanes_nvls = 32, pipe_lanes_p2p = 40, pipe_lanes_wide = 32, pipe_depth = 3;
   int pipe_p2p = 0;
   size_t pipe_chunk = (size_t)1 << 20;
-  // user-pointer allreduce with NVLS available: below this size the registered zero-copy two-shot is faster than the
-  // staging pipeline (8 GPUs: 60.8 vs 83.6 us at 16 MiB, 386 vs 386 at 128 MiB, 747 vs 696 at 256 MiB)
-  size_t pipe_pref_min = (size_t)192 << 20;
+  // user-pointer allreduce with NVLS available: below this size the registered zero-copy two-shot is preferred to the staging
+  // pipeline. As a kernel it is faster up to 128 MiB (8 GPUs: 60.8 vs 83.6 us at 16 MiB, 386 vs 386 at 128 MiB, 747 vs 696 at
+  // 256 MiB), but every call on the registered path pays a host agreement round (two rendezvous allgathers, reg_exchange) that
+  // graph-replay timings do not show and that the eager callers of this path (torch DDP buckets under the shim) would pay per
+  // bucket. The end-to-end DDP measurement of round 2 (28.9 k img/s, 8 GPUs) ran on the pipeline: 0 = keep that.
+  size_t pipe_pref_min = 0;
+  // reduce-scatter: the registered pull (630 GB/s-class kernel at 4 and 8 GPUs) instead of the NVLS pipeline (564 GB/s at 8 GPUs,
+  // NCCL 632) once the message is large enough for the host agreement round (~50 us) to disappear next to the kernel time
+  size_t rs_reg_min = (size_t)64 << 20;
   // lazy registration of user buffers (cudaIpc): peer mappings by (rank, allocation id); see reg_exchange()
   size_t reg_min = (size_t)8 << 20;
   int reg_mode = 1;  // 0 off, 1 where it wins (P2P paths: world 2; byte-wise ops), 2 always
@@ -469,6 +475,7 @@ static int comm_finish_init(b200mpi_comm* c, size_t staging_bytes) {
   }
   c->reg_min = env_size("B200MPI_REG_MIN_BYTES", c->reg_min);
   c->pipe_pref_min = env_size("B200MPI_PIPE_PREF_MIN_BYTES", c->pipe_pref_min);
+  c->rs_reg_min = env_size("B200MPI_RS_REG_MIN_BYTES", c->rs_reg_min);
   c->reg_mode = env_int("B200MPI_REG", c->reg_mode);
   // 16 MiB one-shot region + 144 MiB for the pipelined kernels (48 lanes x 3 slots x 1 MiB)
   if (staging_bytes == 0) staging_bytes = env_size("B200MPI_STAGING_BYTES", c->local ? (size_t)64 << 20 : (size_t)160 << 20);
@@ -1230,10 +1237,11 @@ int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t c
   const size_t total = count * esize(dtype);
   if (dtype < 0 || dtype > 2 || op < 0 || op > 2) return fail(B200MPI_ERR_INVALID, "reduce_scatter: bad dtype/op");
   const bool rs_nvls = c->multicast && (op == B200MPI_SUM || dtype != B200MPI_F32);
-  // zero-copy: pull the owned block from every input. Preferred over the NVLS pipeline at every world size: the P2P pull
-  // runs at the link's read rate (allreduce_reg: 630 GB/s at 4 and 8 GPUs) with no staging copy of the N x larger input,
-  // the pipelined kernel reached 564 GB/s at 8 GPUs against NCCL's 632 (profiles/r2/roofline_shim_vs_nccl_n8.md)
-  if (total % 16 == 0 && reg_wanted(c, total * c->world, true)) {
+  // zero-copy: pull the owned block from every input. Without NVLS always; with NVLS from rs_reg_min bytes of input up: the P2P
+  // pull runs at the link's read rate (allreduce_reg: 630 GB/s at 4 and 8 GPUs) with no staging copy of the N x larger input,
+  // the pipelined kernel reached 564 GB/s at 8 GPUs against NCCL's 632 (profiles/r2/roofline_shim_vs_nccl_n8.md); below that
+  // size the per-call host agreement of the registered path would cost more than the kernel gains
+  if (total % 16 == 0 && reg_wanted(c, total * c->world, !rs_nvls || total * c->world >= c->rs_reg_min)) {
     Win win_in, win_out;
     if (reg_exchange(c, in, out, total * c->world, total, true, &win_in, &win_out) == REG_IPC) {
       std::vector<KArgs> args(1);
