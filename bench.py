@@ -170,7 +170,7 @@ def _agree(workdir: str, tag: str, rank: int, world: int, ok: bool, wait_s: floa
 # candidate failed or hung on some rank. Every child verifies its own result (finite loss, parameters bit-identical on
 # all ranks, bf16 shadow == bf16(master)) and exits non-zero otherwise, so a wrong answer cannot be reported as a number.
 CONSERVATIVE = {"B200MPI_BF16_PARAMS": "0", "B200MPI_FUSED_CONV1X1": "0", "B200MPI_TAIL_BUCKET_BYTES": "0",
-                "B200MPI_ASYNC_H2D": "0", "B200MPI_PARAM_BROADCAST": "staged"}
+                "B200MPI_ASYNC_H2D": "0", "B200MPI_PARAM_BROADCAST": "staged", "B200MPI_DEFER_NBT": "0"}
 FULL = {"B200MPI_BF16_PARAMS": "1", "B200MPI_TAIL_BUCKET_BYTES": str(4 << 20)}
 
 

@@ -229,7 +229,9 @@ class DataParallelTrainer:
         self._copy_stream = torch.cuda.Stream(device=self.device) if (self.async_h2d and self._cuda) else None
         self._stage_x = self._stage_y = None
         self._pending_batch = None
-        self._defer_nbt = os.environ.get("B200MPI_DEFER_NBT", "0") == "1"   # experiment: batch the BN step counters
+        # the 104 `num_batches_tracked += 1` kernels of a ResNet-101 step become one multi-tensor add (ran on a B200 in round 2
+        # together with the other flags: profiles/r2/bench_all_flags.json); B200MPI_DEFER_NBT=0 restores one add per BN layer
+        self._defer_nbt = os.environ.get("B200MPI_DEFER_NBT", "1" if self._cuda else "0") == "1"
         self._graph_ops: list = []   # collectives recorded in the CUDA graph: replays launch them without the host
         self._replays = 0
         if hasattr(comm, "add_stat_source"):
