@@ -126,6 +126,8 @@ static std::map<std::string, std::vector<int>> read_slots_file(const char* path)
 // -timestamp-output: every line is prefixed with the wall-clock time it was forwarded.
 static std::string g_outdir;
 static bool g_timestamp = false;
+static bool g_merge_stderr = false;   // -merge-stderr-to-stdout
+static int g_stdin_rank = 0;          // -stdin RANK|all|none: which rank keeps the launcher's stdin (-1 none, -2 all)
 static FILE* rank_file(int rank, const char* chan) {
   static std::map<std::pair<int, std::string>, FILE*> files;
   auto key = std::make_pair(rank, std::string(chan));
@@ -199,6 +201,19 @@ int main(int argc, char** argv) {
       if (a == "-oversubscribe") oversubscribe = true;
       if (a == "-l") tag_output = true;
     }
+    else if (a == "-use-hwthread-cpus" || a == "-verbose" || a == "-v" || a == "-d" || a == "-debug-devel" || a == "-debug-daemons" ||
+             a == "-leave-session-attached" || a == "-continuous" || a == "-no-daemonize" || a == "-do-not-launch" || a == "-novm" ||
+             a == "-bynode" || a == "-byslot" || a == "-bycore" || a == "-bysocket" || a == "-nolocal" || a == "-tag-output-full") {}
+    else if (a == "-pernode") ppn = 1;
+    else if (a == "-merge-stderr-to-stdout") g_merge_stderr = true;
+    else if (a == "-stdin") {
+      need(1);
+      const std::string v = argv[++i];
+      g_stdin_rank = v == "none" ? -1 : v == "all" ? -2 : atoi(v.c_str());
+    }
+    else if (a == "-output-directory") { need(1); g_outdir = argv[++i]; }
+    else if (a == "-tune" || a == "-am" || a == "-report-uri" || a == "-xterm" || a == "-max-restarts" || a == "-max-vm-size" ||
+             a == "-slot-list" || a == "-cpu-set" || a == "-rankfile" || a == "-rf" || a == "-ompi-server" || a == "-path") { need(1); ++i; }
     else if (a == "-tag-output" || a == "-prepend-rank") tag_output = true;
     else if (a == "-timestamp-output") g_timestamp = true;
     else if (a == "-output-filename" || a == "-outfile-pattern") { need(1); g_outdir = argv[++i]; }
@@ -239,7 +254,10 @@ int main(int argc, char** argv) {
              "  -mca / -gmca key value        exported as OMPI_MCA_<key>=<value>\n"
              "  -wdir, -wd DIR                working directory of the ranks\n"
              "  -tag-output, -prepend-rank, -l  prefix every output line with [job,rank]<stream>:\n"
-             "  -output-filename DIR          also write every rank's output to DIR/1/rank.<N>/{stdout,stderr}\n"
+             "  -output-filename, -output-directory DIR   also write every rank's output to DIR/1/rank.<N>/{stdout,stderr}\n"
+             "  -merge-stderr-to-stdout       a rank's stderr travels with its stdout\n"
+             "  -stdin RANK|all|none          which rank reads the launcher's stdin (default 0; the others get /dev/null)\n"
+             "  -pernode                      one rank per host\n"
              "  -timestamp-output             prefix every forwarded line with the time\n"
              "  -timeout SECONDS              kill the job after SECONDS (exit code 124)\n"
              "  -oversubscribe                allow more ranks than slots\n"
@@ -431,7 +449,11 @@ int main(int argc, char** argv) {
     if (pid == 0) {
       setpgid(0, 0);
       dup2(po[1], 1);
-      dup2(pe[1], 2);
+      dup2(g_merge_stderr ? po[1] : pe[1], 2);
+      if (g_stdin_rank != -2 && g_stdin_rank != rk.rank) {   // Open MPI: only rank 0 (or -stdin RANK) reads the launcher's stdin
+        const int nul = open("/dev/null", O_RDONLY);
+        if (nul >= 0) { dup2(nul, 0); if (nul > 2) close(nul); }
+      }
       signal(SIGPIPE, SIG_DFL);
       signal(SIGINT, SIG_DFL);
       signal(SIGTERM, SIG_DFL);

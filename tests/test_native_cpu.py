@@ -60,6 +60,26 @@ def test_mpirun_mpmd_output_files_and_timestamps(tmp_path):
     assert r.returncode != 0 and "no program after ':'" in r.stderr
 
 
+def test_mpirun_stdin_routing_merged_stderr_and_output_directory(tmp_path):
+    """Open MPI's stdio rules: only rank 0 (or `-stdin RANK`) reads the launcher's stdin, the other ranks see /dev/null;
+    `-merge-stderr-to-stdout`; `-output-directory` (the newer spelling of -output-filename); `-pernode`; options that only make
+    sense with daemons are accepted silently."""
+    reader = "read x; echo r$OMPI_COMM_WORLD_RANK=[$x]"
+    r = subprocess.run([MPIRUN, "-np", "2", "sh", "-c", reader], input="hello\n", capture_output=True, text=True, timeout=60)
+    assert sorted(r.stdout.split()) == ["r0=[hello]", "r1=[]"], r.stdout + r.stderr
+    r = subprocess.run([MPIRUN, "-np", "2", "--stdin", "1", "sh", "-c", reader], input="hello\n", capture_output=True, text=True, timeout=60)
+    assert sorted(r.stdout.split()) == ["r0=[]", "r1=[hello]"], r.stdout + r.stderr
+    r = subprocess.run([MPIRUN, "-np", "2", "--stdin", "none", "sh", "-c", reader], input="hello\n", capture_output=True, text=True, timeout=60)
+    assert sorted(r.stdout.split()) == ["r0=[]", "r1=[]"]
+    out = tmp_path / "o"
+    r = run([MPIRUN, "-np", "2", "--merge-stderr-to-stdout", "--tag-output", "--output-directory", str(out), "--use-hwthread-cpus", "--verbose",
+             "--report-uri", "-", "sh", "-c", "echo to-err >&2"])
+    assert r.returncode == 0 and r.stderr == "" and sorted(r.stdout.splitlines()) == ["[1,0]<stdout>:to-err", "[1,1]<stdout>:to-err"], r.stdout + r.stderr
+    assert (out / "1" / "rank.1" / "stdout").read_text() == "to-err\n"
+    r = run([MPIRUN, "--pernode", "-H", "a,b,c", "sh", "-c", "echo $OMPI_COMM_WORLD_SIZE"])
+    assert r.stdout.split() == ["3", "3", "3"], r.stdout + r.stderr
+
+
 def test_mpirun_hostfile_dialects_and_slot_placement(tmp_path):
     hf = tmp_path / "hostfile"
     hf.write_text("job-worker-0.job.ns.svc slots=2\njob-worker-1.job.ns.svc slots=2\n")
