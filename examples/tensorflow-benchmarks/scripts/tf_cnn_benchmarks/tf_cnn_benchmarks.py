@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--device", default="gpu", choices=["gpu", "cpu"], help="cpu: host tensors through the Horovod-API engine (no CUDA needed)")
     ap.add_argument("--image_size", type=int, default=224)
     ap.add_argument("--num_gpus", type=int, default=1)
+    ap.add_argument("--train_dir", default="", help="checkpoint directory (tf_cnn_benchmarks flag): restored from at start if it holds a "
+                                                    "checkpoint, written by rank 0 at the end")
     ap.add_argument("--b200_engine", default=os.environ.get("B200MPI_ENGINE", "fused"), choices=["fused", "hvd", "nccl"],
                     help="fused: symmetric-window grads + fused allreduce+SGD kernel in a CUDA graph; "
                          "hvd: hvd.DistributedOptimizer API path; nccl: stock NCCL baseline")
@@ -119,6 +121,34 @@ def main():
             opt.step()
             return loss.detach()
 
+    # --train_dir: resume / checkpoint (rank-0-only writer, the reference examples' convention: tensorflow_mnist.py:159)
+    ckpt = os.path.join(args.train_dir, "model.ckpt.pt") if args.train_dir else ""
+    if ckpt and os.path.exists(ckpt):
+        sd = torch.load(ckpt, map_location="cpu", weights_only=False)
+        if args.b200_engine in ("fused", "nccl"):
+            trainer.load_state_dict(sd["trainer"])
+        else:
+            model.load_state_dict(sd["model"])
+            opt.load_state_dict(sd["optimizer"])
+        if rank == 0:
+            print(f"Restored checkpoint from {ckpt} (written after {sd.get('batches', '?')} batches on {sd.get('world', '?')} ranks)")
+            sys.stdout.flush()
+
+    def save_checkpoint(batches_done):
+        if not ckpt:
+            return
+        if args.b200_engine in ("fused", "nccl"):
+            payload = {"trainer": trainer.state_dict()}          # collective: momentum shards are gathered
+        else:
+            payload = {"model": model.state_dict(), "optimizer": opt.state_dict()}
+        if rank == 0:
+            os.makedirs(args.train_dir, exist_ok=True)
+            payload.update(batches=batches_done, world=size)
+            torch.save(payload, ckpt + ".tmp")
+            os.replace(ckpt + ".tmp", ckpt)
+            print(f"Saved checkpoint to {ckpt}")
+            sys.stdout.flush()
+
     def device_sync():
         if on_gpu:
             torch.cuda.synchronize()
@@ -161,6 +191,7 @@ def main():
         print(f"total images/sec: {total:.2f}")
         print("----------------------------------------------------------------")
         sys.stdout.flush()
+    save_checkpoint(args.num_warmup_batches + args.num_batches)
     hvd.shutdown()
 
 

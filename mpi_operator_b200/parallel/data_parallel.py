@@ -486,6 +486,85 @@ class DataParallelTrainer:
         if self.comm.world > 1:
             self.comm.host_barrier()
 
+    # ------------------------------------------------- checkpoint / resume --
+    def state_dict(self) -> dict:
+        """World-size independent checkpoint of the training state (the reference's examples checkpoint on
+        rank 0 only, tensorflow_mnist.py:159): fp32 MASTER parameters, module buffers (BN running statistics), the optimizer's
+        momentum and the hyper-parameters, all keyed by parameter / buffer NAME and moved to the host. COLLECTIVE when
+        world > 1: the fused optimizer keeps only 1/world of every bucket's momentum on each rank, so the shards are
+        all-gathered first (one byte-wise allgather kernel per bucket); every rank gets the full dictionary, write it from rank 0.
+        Loading re-shards for whatever world the new trainer runs in (elastic rescale, different GPU count)."""
+        st = self.state
+        names = {p: n for n, p in self.model.named_parameters()}
+        if self._cuda:
+            torch.cuda.synchronize(self.device)
+        mom_flat = torch.zeros(st.total, dtype=torch.float32, device=st.flat_param.device)
+        if self.fused:
+            W = self.comm.world
+            for b in st.buckets:
+                per = b.momentum.numel()
+                full = b.momentum
+                if W > 1:
+                    full = torch.empty(W * per, dtype=torch.float32, device=b.momentum.device)
+                    self.comm.allgather(b.momentum, full)
+                mom_flat[b.start:b.start + b.numel] = full[:b.numel]
+            if self._cuda:
+                torch.cuda.synchronize(self.device)
+        elif hasattr(self, "_flat_mom"):
+            mom_flat.copy_(self._flat_mom)
+        masters, momentum = {}, {}
+        for p in st.params:
+            start, n = st.param_slot[p][1], p.numel()
+            masters[names[p]] = st.flat_param[start:start + n].as_strided(p.size(), p.stride()).detach().cpu().contiguous()
+            momentum[names[p]] = mom_flat[start:start + n].as_strided(p.size(), p.stride()).detach().cpu().contiguous()
+        return {"format": "b200mpi.DataParallelTrainer/1", "model": masters, "momentum": momentum,
+                "buffers": {n: b.detach().cpu().clone() for n, b in self.model.named_buffers()},
+                "hyper": {"lr": float(self.hyper[0]), "momentum": float(self.hyper[1]), "weight_decay": float(self.hyper[2]),
+                          "nesterov": bool(self.nesterov)},
+                "world_size_at_save": int(self.comm.world)}
+
+    def load_state_dict(self, sd: dict, load_hyper: bool = True) -> None:
+        """Restore ``state_dict()`` output in a trainer built on the same model class (any world size, with or without the bf16
+        shadow / fused optimizer). Not collective: every rank loads the same dictionary and keeps its own momentum shard."""
+        if sd.get("format") != "b200mpi.DataParallelTrainer/1":
+            raise ValueError("not a DataParallelTrainer checkpoint")
+        st = self.state
+        names = {p: n for n, p in self.model.named_parameters()}
+        missing = [n for n in names.values() if n not in sd["model"]]
+        if missing:
+            raise KeyError(f"checkpoint lacks parameters {missing[:5]}{' ...' if len(missing) > 5 else ''}")
+        dev = st.flat_param.device
+        mom_flat = torch.zeros(st.total, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p in st.params:
+                start, n, name = st.param_slot[p][1], p.numel(), names[p]
+                src = sd["model"][name]
+                if tuple(src.shape) != tuple(p.shape):
+                    raise ValueError(f"shape of {name}: checkpoint {tuple(src.shape)} vs model {tuple(p.shape)}")
+                st.flat_param[start:start + n].as_strided(p.size(), p.stride()).copy_(src.to(dev, torch.float32))
+                if name in sd.get("momentum", {}):
+                    mom_flat[start:start + n].as_strided(p.size(), p.stride()).copy_(sd["momentum"][name].to(dev, torch.float32))
+            st.refresh_lowp()
+            bufs = dict(self.model.named_buffers())
+            for n, b in sd.get("buffers", {}).items():
+                if n in bufs:
+                    bufs[n].copy_(b.to(bufs[n].device, bufs[n].dtype))
+            if self.fused:
+                r = self.comm.rank
+                for b in st.buckets:
+                    per = b.momentum.numel()
+                    lo, hi = min(r * per, b.numel), min((r + 1) * per, b.numel)
+                    b.momentum.zero_()
+                    b.momentum[:hi - lo] = mom_flat[b.start + lo:b.start + hi]
+            else:
+                self._flat_mom = mom_flat
+        if load_hyper and "hyper" in sd:
+            h = sd["hyper"]
+            self._lr, self._mu, self._wd = h["lr"], h["momentum"], h["weight_decay"]
+            self.hyper.copy_(torch.tensor([self._lr, self._mu, self._wd], dtype=torch.float32))
+        if self._cuda:
+            torch.cuda.synchronize(self.device)
+
     def no_sync(self):
         """Context manager: steps inside accumulate gradients locally (no collective, no update, run eagerly);
         the first step after it reduces the accumulated sum and applies one update."""

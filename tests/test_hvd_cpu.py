@@ -185,3 +185,24 @@ def test_mnist_example_with_the_use_adasum_flag():
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     losses = [float(x) for x in re.findall(r"loss = ([0-9.]+)", r.stdout)]
     assert len(losses) >= 3 and losses[-1] < 0.25 * losses[0], losses
+
+
+def test_tf_cnn_benchmarks_train_dir_checkpoints_and_resumes(tmp_path):
+    """tf_cnn_benchmarks' --train_dir: rank 0 writes a checkpoint at the end, the next run restores it on every rank
+    (rank-0-only writer as in the reference's tensorflow_mnist.py:159)."""
+    import os
+    import subprocess
+    import sys
+    repo = _repo()
+    mpirun = os.path.join(repo, "mpi_operator_b200/bin/mpirun")
+    if not os.path.exists(mpirun):
+        pytest.skip("native launcher not built (run make)")
+    script = os.path.join(repo, "examples/tensorflow-benchmarks/scripts/tf_cnn_benchmarks/tf_cnn_benchmarks.py")
+    cmd = [mpirun, "-np", "2", sys.executable, script, "--device=cpu", "--model=trivial", "--batch_size=4", "--num_batches=3",
+           "--num_warmup_batches=1", "--image_size=32", "--train_dir", str(tmp_path / "ckpt")]
+    env = dict(os.environ, B200MPI_HVD_DEVICE="cpu")
+    first = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
+    assert first.returncode == 0 and "Saved checkpoint" in first.stdout and "Restored" not in first.stdout, first.stdout[-1500:] + first.stderr[-2000:]
+    second = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
+    assert second.returncode == 0 and "Restored checkpoint" in second.stdout and "written after 4 batches on 2 ranks" in second.stdout, \
+        second.stdout[-1500:] + second.stderr[-2000:]

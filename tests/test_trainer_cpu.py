@@ -232,3 +232,80 @@ def test_prefetch_then_step_without_arguments_matches_step_with_arguments():
         b.step()
     for p, q in zip(a.model.parameters(), b.model.parameters()):
         assert torch.equal(p, q)
+
+
+@pytest.mark.parametrize("fused,bf16", [(True, False), (True, True), (False, False)])
+def test_checkpoint_resume_continues_bit_for_bit(fused, bf16):
+    """state_dict() / load_state_dict(): masters, momentum (re-sharded), BN buffers and hyper-parameters; a resumed trainer takes
+    exactly the steps the original would have taken."""
+    data = batches(6, seed=4)
+    kw = dict(lr=0.05, momentum=0.9, weight_decay=1e-4, autocast_dtype=torch.bfloat16 if bf16 else None, cuda_graph=False,
+              bucket_bytes=2048, fused_optimizer=fused, bf16_params=bf16)
+    a = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), **kw)
+    for x, y in data[:3]:
+        a.step(x, y)
+    import io
+    blob = io.BytesIO()
+    torch.save(a.state_dict(), blob)                       # what a rank-0 checkpoint file holds
+    for x, y in data[3:]:
+        a.step(x, y)
+    sd = torch.load(io.BytesIO(blob.getvalue()), weights_only=False)
+    assert sd["format"].startswith("b200mpi.DataParallelTrainer") and set(sd["model"]) == set(sd["momentum"])
+    assert all(t.dtype == torch.float32 and t.device.type == "cpu" for t in sd["model"].values())   # fp32 masters even with bf16 leaves
+    torch.manual_seed(99)                                  # a differently initialised model: everything must come from the checkpoint
+    fresh = small_cnn()
+    with torch.no_grad():
+        for p in fresh.parameters():
+            p.add_(1.0)
+    b = DataParallelTrainer(fresh, nn.CrossEntropyLoss(), FakeComm(), **dict(kw, lr=0.5, momentum=0.0))
+    b.load_state_dict(sd)
+    assert float(b.hyper[0]) == pytest.approx(0.05) and float(b.hyper[1]) == pytest.approx(0.9)
+    for x, y in data[3:]:
+        b.step(x, y)
+    for (n, p), (_, q) in zip(a.state.master_state().items(), b.state.master_state().items()):
+        assert torch.equal(p, q), n
+    for (n, u), (_, v) in zip(a.model.named_buffers(), b.model.named_buffers()):
+        assert torch.equal(u, v), n
+    # a checkpoint written by the fused optimizer loads into the unfused one and vice versa (same momentum semantics)
+    c = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), **dict(kw, fused_optimizer=not fused))
+    c.load_state_dict(sd)
+    for x, y in data[3:]:
+        c.step(x, y)
+    for p, q in zip(a.state.master_state().values(), c.state.master_state().values()):
+        torch.testing.assert_close(p, q, rtol=1e-5, atol=1e-6)
+    with pytest.raises(ValueError):
+        b.load_state_dict({"format": "something else"})
+
+
+def test_momentum_shards_are_rebuilt_for_another_world_size():
+    """The fused optimizer keeps 1/world of each bucket's momentum per rank: loading a world-1 checkpoint into rank r of a
+    world-4 trainer must give it exactly slice r of every bucket."""
+    class Comm4(FakeComm):
+        world = 4
+
+        def __init__(self, rank):
+            super().__init__()
+            self.rank = rank
+
+        def slice_elems(self, count, dtype):
+            nvec = (count + 3) // 4
+            return (nvec + self.world - 1) // self.world * 4
+
+    src = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.05, momentum=0.9, autocast_dtype=None,
+                              cuda_graph=False, bucket_bytes=2048)
+    for x, y in batches(2, seed=5):
+        src.step(x, y)
+    sd = src.state_dict()
+    full = torch.cat([b.momentum[:b.numel] for b in src.state.buckets])
+    assert float(full.abs().sum()) > 0
+    pieces = {}
+    for r in range(4):
+        t = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), Comm4(r), lr=0.05, momentum=0.9, autocast_dtype=None,
+                                cuda_graph=False, bucket_bytes=2048)
+        t.load_state_dict(sd)
+        pieces[r] = [b.momentum.clone() for b in t.state.buckets]
+        assert len(t.state.buckets) == len(src.state.buckets)
+    for k, b in enumerate(src.state.buckets):
+        per = pieces[0][k].numel()
+        rebuilt = torch.cat([pieces[r][k] for r in range(4)])[:b.numel]
+        assert per * 4 >= b.numel and torch.equal(rebuilt, b.momentum[:b.numel])
