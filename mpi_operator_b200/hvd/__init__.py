@@ -27,7 +27,7 @@ import os
 from ..launch.env import rank_info_from_env
 from .exceptions import HorovodInternalError, HostsUpdatedInterrupt  # noqa: F401
 
-Average, Sum, Adasum, Min, Max = "average", "sum", "adasum", "min", "max"
+Average, Sum, Adasum, Min, Max, Product = "average", "sum", "adasum", "min", "max", "product"
 
 _state = {"comm": None, "info": None, "engine": None, "optimizers": []}
 
@@ -229,6 +229,8 @@ def _op_name(op, average):
         return "max"
     if op == Adasum:
         return "adasum"
+    if op == Product:
+        return "prod"
     raise ValueError(f"unknown reduction op {op!r}")
 
 
@@ -321,6 +323,13 @@ def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1
         if postscale_factor != 1.0:
             tensor.mul_(postscale_factor)
         return _Done(tensor)
+    if opn == "prod" and tensor.is_cuda:
+        # the device kernels reduce with sum / min / max; a product is one allgather kernel + a local reduction
+        t = tensor.contiguous()
+        g = torch.empty((size(),) + tuple(t.shape), dtype=t.dtype, device=t.device)
+        _comm().allgather(t if prescale_factor == 1.0 else t * prescale_factor, g)
+        tensor.copy_(g.prod(0) if postscale_factor == 1.0 else g.prod(0) * postscale_factor)
+        return _Done(tensor)
     e = _engine_for(tensor)
     if e is not None:
         t = tensor if tensor.is_contiguous() else tensor.contiguous()
@@ -352,6 +361,26 @@ def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_
     """All tensors are submitted before any is waited for, so the engine negotiates them in one cycle and fuses them."""
     return [allreduce_async(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor)
             for i, t in enumerate(tensors)]
+
+
+def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    hs = grouped_allreduce_async_(tensors, average, name, op, prescale_factor, postscale_factor)
+    return [h.wait() for h in hs]
+
+
+def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+    """In-place form of ``grouped_allreduce_async``."""
+    return [allreduce_async_(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor)
+            for i, t in enumerate(tensors)]
+
+
+def grouped_allgather(tensors, name=None, process_set=None):
+    _check_process_set(process_set)
+    return [h.wait() for h in grouped_allgather_async(tensors, name)]
+
+
+def grouped_allgather_async(tensors, name=None):
+    return [allgather_async(t, f"{name}.{i}" if name else None) for i, t in enumerate(tensors)]
 
 
 def allgather(tensor, name=None, process_set=None):
@@ -458,6 +487,34 @@ def reducescatter(tensor, op=None, name=None):
     out = torch.empty((t.shape[0] // size(),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     _comm().reduce_scatter(t, out, op=_op_name(op, None))
     return out
+
+
+def alltoall_async(tensor, splits=None, name=None):
+    """The exchange is issued in stream / call order and has completed (host) or been enqueued (device) when this returns."""
+    return _Done(alltoall(tensor, splits, name))
+
+
+def reducescatter_async(tensor, op=None, name=None):
+    return _Done(reducescatter(tensor, op, name))
+
+
+def grouped_reducescatter(tensors, op=None, name=None):
+    return [reducescatter(t, op, f"{name}.{i}" if name else None) for i, t in enumerate(tensors)]
+
+
+def grouped_reducescatter_async(tensors, op=None, name=None):
+    return [reducescatter_async(t, op, f"{name}.{i}" if name else None) for i, t in enumerate(tensors)]
+
+
+def is_homogeneous() -> bool:
+    """Every node runs the same number of ranks: trivially true on one box."""
+    return True
+
+
+def remove_process_set(process_set) -> bool:
+    if process_set is global_process_set:
+        raise ValueError("the global process set cannot be removed")
+    return False   # no other process set can exist (add_process_set explains why)
 
 
 def _on_gpu() -> bool:

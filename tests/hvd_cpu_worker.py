@@ -23,6 +23,17 @@ assert torch.equal(hvd.allreduce(h, op=hvd.Sum), torch.full((7,), n * (n + 1) / 
 i64 = torch.tensor([r, 2 * r], dtype=torch.int64)
 assert torch.equal(hvd.allreduce(i64, op=hvd.Sum), torch.tensor([n * (n - 1) // 2, n * (n - 1)]))
 assert torch.allclose(hvd.allreduce(t, op=hvd.Sum, prescale_factor=0.5), 0.5 * (n * torch.arange(10.) + n * (n - 1) / 2))
+import math
+assert torch.allclose(hvd.allreduce(torch.full((3,), float(r + 1)), op=hvd.Product), torch.full((3,), float(math.factorial(n))))
+ga, gb = torch.full((2,), float(r)), torch.full((5,), 2.0 * r)
+hvd.grouped_allreduce_([ga, gb], op=hvd.Sum, name="grp.inplace")
+assert torch.equal(ga, torch.full((2,), n * (n - 1) / 2)) and torch.equal(gb, torch.full((5,), float(n * (n - 1))))
+gg = hvd.grouped_allgather([torch.full((1, 2), float(r)), torch.full((2,), float(-r))], name="grp.gather")
+assert gg[0].shape == (n, 2) and gg[1].shape == (2 * n,) and float(gg[0][n - 1, 0]) == n - 1 and float(gg[1][-1]) == -(n - 1)
+assert torch.equal(hvd.alltoall_async(torch.arange(n, dtype=torch.float32) + 100 * r).wait(), torch.tensor([100. * k + r for k in range(n)]))
+grs = hvd.grouped_reducescatter([torch.ones(2 * n), torch.arange(n, dtype=torch.float32)], op=hvd.Sum)
+assert torch.equal(grs[0], torch.full((2,), float(n))) and torch.equal(grs[1], torch.tensor([float(n * r)]))
+assert hvd.is_homogeneous() and hvd.remove_process_set(object()) is False
 inplace = t.clone()
 hvd.allreduce_(inplace, op=hvd.Sum)
 assert torch.equal(inplace, n * torch.arange(10.) + n * (n - 1) / 2)
