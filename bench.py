@@ -227,6 +227,9 @@ def supervise(args) -> int:
             print(json.dumps({"metric": "resnet101_images_per_sec", "value": None, "n_gpus": world, "impl": "ours",
                               "error": "every configuration failed", "attempts": notes}), flush=True)
         return 1
+    if rank == 0:   # breadcrumb on stderr (the ONE stdout line comes after the baselines): survives a cut-off run in the driver's log tail
+        print(f"[bench supervisor] main measurement ({used}): {json.dumps({k_: result.get(k_) for k_ in ('value', 'ms_per_step', 'n_gpus')})}; "
+              f"candidates {json.dumps(tried)}; {time.time() - t_start:.0f} s so far", file=sys.stderr, flush=True)
     same_box = None
     if not args.no_same_box and os.environ.get("B200MPI_BENCH_SAME_BOX", "1") != "0":
         arms = {}
