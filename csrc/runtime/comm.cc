@@ -674,13 +674,13 @@ static bool pipe_wanted(b200mpi_comm* c, size_t full_bytes) {
 // without NVLS the pipelined kernel has to win against the zero-copy registered path (which it does not) and against the
 // barrier-based staged kernel (unmeasured since the copy fix): opt-in until the sweep says otherwise
 static bool pipe_p2p_ok(b200mpi_comm* c) { return c->pipe_p2p || c->local; }
-template <typename Fill>
-static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dtype, size_t nbytes, bool wide,
-                   cudaStream_t stream, int algo, Fill&& fill) {
-  if (mode == MODE_NVLS && !(c->multicast && c->wins[c->stage_win].mc)) mode = MODE_P2P;
+// Geometry of one pipelined launch (pure arithmetic, checked exhaustively on the host by csrc/tests/comm_host_test.cu):
+// L lanes of three CTAs, D staging slots per lane, chunks of `cv` vectors (x `regions` for the wide ops).
+struct PipePlan { int lanes; int depth; size_t chunk_vecs; size_t regions; bool fits; };
+static PipePlan pipe_plan(const b200mpi_comm* c, int kind, int mode, size_t nbytes, bool wide) {
   int L = wide ? c->pipe_lanes_wide : (mode == MODE_NVLS ? c->pipe_lanes_nvls : c->pipe_lanes_p2p);
   if (kind == PIPE_BROADCAST && mode == MODE_NVLS) L = kPipeLanes;   // one pushing rank: give it every lane
-  if (c->local) L = std::max(1, std::min(L, emu_max_blocks(c) / 3));
+  if (c->local) L = std::max(1, std::min(L, emu_max_blocks(const_cast<b200mpi_comm*>(c)) / 3));
   const int D = c->pipe_depth;
   const size_t nvec = (nbytes + 15) / 16;
   const size_t regions = wide ? (size_t)c->world : 1;
@@ -689,7 +689,17 @@ static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dt
   size_t cv = std::min(c->pipe_chunk / 16, c->twoshot_bytes / 16 / ((size_t)L * D)) / regions;
   cv = std::min(cv, std::max((size_t)1024 / regions, nvec / ((size_t)L * 2)));
   cv = std::max((size_t)c->world, cv / c->world * c->world);
-  if ((size_t)L * D * cv * regions * 16 > c->twoshot_bytes) return fail(B200MPI_ERR_INVALID, std::string(name) + ": staging window too small");
+  return PipePlan{L, D, cv, regions, (size_t)L * D * cv * regions * 16 <= c->twoshot_bytes};
+}
+
+template <typename Fill>
+static int pipe_op(b200mpi_comm* c, const char* name, int kind, int mode, int dtype, size_t nbytes, bool wide,
+                   cudaStream_t stream, int algo, Fill&& fill) {
+  if (mode == MODE_NVLS && !(c->multicast && c->wins[c->stage_win].mc)) mode = MODE_P2P;
+  const PipePlan plan = pipe_plan(c, kind, mode, nbytes, wide);
+  if (!plan.fits) return fail(B200MPI_ERR_INVALID, std::string(name) + ": staging window too small");
+  const int L = plan.lanes, D = plan.depth;
+  const size_t nvec = (nbytes + 15) / 16, cv = plan.chunk_vecs;
   const auto ranks = my_ranks(c);
   std::vector<KArgs> args(c->local ? c->world : 1);
   for (size_t k = 0; k < ranks.size(); k++) {

@@ -90,6 +90,44 @@ int main() {
     EXPECT(b200mpi_comm_has_p2p(nc) == 0 && b200mpi_p2p_batch(nc, ops, 1, nullptr) == B200MPI_ERR_UNSUPPORTED);
   }
 
+  // ---- pipelined launches (k_pipe): every (world, op, mode, size) plan fits the staging region, the grid fits the GPU with
+  //      one CTA per SM, chunks are whole multiples of the world (the reduce phase splits a chunk into per-rank slices),
+  //      a broadcast with NVLS takes every lane, and the defaults of a real communicator (160 MiB staging) hold 48 x 3 x 1 MiB
+  {
+    b200mpi_comm* pc = new b200mpi_comm;
+    pc->twoshot_bytes = (size_t)144 << 20;      // 160 MiB staging minus the 16 MiB one-shot region (comm_finish_init)
+    size_t checked = 0;
+    for (int world : {2, 3, 4, 8}) {
+      pc->world = world;
+      for (int kind : {PIPE_ALLREDUCE, PIPE_ALLGATHER, PIPE_REDUCE_SCATTER, PIPE_BROADCAST}) {
+        const bool wide = kind == PIPE_ALLGATHER || kind == PIPE_REDUCE_SCATTER;
+        for (int mode : {MODE_P2P, MODE_NVLS}) {
+          for (size_t bytes = 1; bytes <= ((size_t)4 << 30); bytes = bytes * 3 + 5) {
+            const PipePlan p = pipe_plan(pc, kind, mode, bytes, wide);
+            EXPECT(p.fits);
+            EXPECT(p.lanes >= 1 && p.lanes <= kPipeLanes && 3 * p.lanes <= 148);          // co-resident: one CTA per SM
+            EXPECT(p.depth >= 2 && p.chunk_vecs >= (size_t)world && p.chunk_vecs % world == 0);
+            EXPECT(p.chunk_vecs * p.regions * 16 <= pc->pipe_chunk + 16 * (size_t)world * p.regions);   // a slot is ~ pipe_chunk at most
+            EXPECT((size_t)p.lanes * p.depth * p.chunk_vecs * p.regions * 16 <= pc->twoshot_bytes);
+            if (kind == PIPE_BROADCAST && mode == MODE_NVLS) EXPECT(p.lanes == kPipeLanes);
+            checked++;
+          }
+        }
+      }
+    }
+    EXPECT(checked > 500);
+    pc->world = 8;
+    const PipePlan big = pipe_plan(pc, PIPE_BROADCAST, MODE_NVLS, (size_t)1 << 30, false);
+    EXPECT(big.lanes == 48 && big.depth == 3 && big.chunk_vecs == ((size_t)1 << 20) / 16);   // 48 x 3 x 1 MiB = exactly the region
+    pc->twoshot_bytes = (size_t)8 << 20;        // a small user-chosen staging region shrinks the chunks instead of failing
+    const PipePlan small = pipe_plan(pc, PIPE_ALLREDUCE, MODE_NVLS, (size_t)1 << 30, false);
+    EXPECT(small.fits && small.chunk_vecs * 16 * small.lanes * small.depth <= pc->twoshot_bytes);
+    pc->local = true;                           // emulated communicators: the whole grid must fit one GPU next to `world` copies
+    pc->twoshot_bytes = (size_t)48 << 20;
+    const PipePlan emu = pipe_plan(pc, PIPE_BROADCAST, MODE_P2P, (size_t)1 << 24, false);
+    EXPECT(emu.fits && 3 * emu.lanes * pc->world <= 148);
+  }
+
   printf(g_failed ? "comm_host_test: %d check(s) FAILED\n" : "comm_host_test: all checks passed\n", g_failed);
   return g_failed ? 1 : 0;
 }
