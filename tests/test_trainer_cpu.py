@@ -309,3 +309,127 @@ def test_momentum_shards_are_rebuilt_for_another_world_size():
         per = pieces[0][k].numel()
         rebuilt = torch.cat([pieces[r][k] for r in range(4)])[:b.numel]
         assert per * 4 >= b.numel and torch.equal(rebuilt, b.momentum[:b.numel])
+
+
+# ---- several ranks as threads: the trainer's host logic with world > 1 (shard sizes, offsets, parameter broadcast, bf16 shadow
+#      pushed to every rank, small tail bucket) against torch SGD on the GLOBAL batch ----------------------------------------
+import threading
+
+
+class ThreadWorld:
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.windows = {}          # window id -> {rank: FakeWindow}
+        self.lock = threading.Lock()
+
+
+class ThreadComm(FakeComm):
+    """What the runtime's kernels do, with threads for ranks: the owner of slice r averages the ranks' gradients for that
+    slice, updates its fp32 parameters (momentum sharded 1/world) and writes the updated slice - and its bf16 shadow - into
+    EVERY rank's window (k_allreduce_sgd, csrc/kernels/collectives.cu)."""
+
+    def __init__(self, tw, rank):
+        super().__init__()
+        self.tw, self.rank, self.world = tw, rank, tw.world
+
+    def alloc_window(self, nbytes):
+        w = super().alloc_window(nbytes)
+        with self.tw.lock:
+            self.tw.windows.setdefault(w.id, {})[self.rank] = w
+        return w
+
+    def slice_elems(self, count, dtype):
+        nvec = (count + 3) // 4
+        return (nvec + self.world - 1) // self.world * 4
+
+    def host_barrier(self):
+        self.tw.barrier.wait(timeout=60)
+
+    def broadcast(self, tensor, root=0, stream=None):       # the trainer broadcasts its flat parameter window
+        self.tw.barrier.wait(timeout=60)
+        if self.rank != root:
+            src = self.tw.windows[0][root].tensor(torch.float32)
+            tensor.copy_(src[:tensor.numel()])
+        self.tw.barrier.wait(timeout=60)
+
+    def allreduce_sgd_window(self, grad_win, grad_off, param_win, param_off, momentum, count, grad_dtype, lr,
+                             momentum_coef=0.0, weight_decay=0.0, nesterov=False, first_step=False, scale=None,
+                             lowp_win=None, lowp_off=0, algo=None, stream=None):
+        self.launch_count += 1
+        if self.hyper is not None:
+            lr, momentum_coef, weight_decay = (float(v) for v in self.hyper)
+        W, r = self.world, self.rank
+        per = self.slice_elems(count, torch.float32)
+        lo, hi = min(r * per, count), min((r + 1) * per, count)
+        self.tw.barrier.wait(timeout=60)                     # every rank's gradients for this bucket are in place
+        if hi > lo:
+            g = sum(self.tw.windows[grad_win.id][k].tensor(torch.float32, offset=grad_off, numel=count)[lo:hi] for k in range(W))
+            g = g * (scale if scale is not None else 1.0 / W)
+            p = param_win.tensor(torch.float32, offset=param_off, numel=count)[lo:hi].clone()
+            g = g + weight_decay * p
+            m = momentum[:hi - lo]
+            m.copy_(g if first_step else momentum_coef * m + g)
+            p = p - lr * (g + momentum_coef * m if nesterov else m)
+            for k in range(W):                                # the all-gather half: updated parameters to every rank
+                self.tw.windows[param_win.id][k].tensor(torch.float32, offset=param_off, numel=count)[lo:hi] = p
+                if lowp_win is not None:
+                    self.tw.windows[lowp_win.id][k].tensor(torch.bfloat16, offset=lowp_off, numel=count)[lo:hi] = p.to(torch.bfloat16)
+        self.tw.barrier.wait(timeout=60)                     # every slice has landed everywhere
+
+
+def plain_cnn():   # no BatchNorm: per-rank batch statistics would make the 2-rank run differ from the global-batch reference
+    torch.manual_seed(0)
+    return nn.Sequential(nn.Conv2d(3, 8, 3, padding=1), nn.ReLU(), nn.Conv2d(8, 16, 3, padding=1), nn.ReLU(),
+                         nn.AdaptiveAvgPool2d(1), nn.Flatten(), nn.Linear(16, 10))
+
+
+@pytest.mark.parametrize("world,full", [(2, False), (2, True), (4, True)])
+def test_multi_rank_trainer_matches_sgd_on_the_global_batch(world, full, monkeypatch):
+    """`full` = bench.py's second multi-GPU candidate: bf16 weight shadow + a small tail bucket."""
+    if full:
+        monkeypatch.setenv("B200MPI_TAIL_BUCKET_BYTES", "1536")
+    g = torch.Generator().manual_seed(11)
+    data = [(torch.randn(4 * world, 3, 8, 8, generator=g), torch.randint(0, 10, (4 * world,), generator=g)) for _ in range(4)]
+    ref = plain_cnn()
+    base = copy.deepcopy(ref)
+    want = reference_steps(ref, data, 0.05, 0.9, 1e-4, autocast=full)
+    tw = ThreadWorld(world)
+    out, errs = {}, []
+
+    def run(r):
+        try:
+            torch.manual_seed(100 + r)
+            model = copy.deepcopy(base)
+            if r != 0:                                        # only rank 0's parameters may survive the initial broadcast
+                with torch.no_grad():
+                    for p in model.parameters():
+                        p.add_(0.5)
+            tr = DataParallelTrainer(model, nn.CrossEntropyLoss(), ThreadComm(tw, r), lr=0.05, momentum=0.9, weight_decay=1e-4,
+                                     bucket_bytes=2048, autocast_dtype=torch.bfloat16 if full else None, channels_last=False,
+                                     cuda_graph=False, bf16_params=full)
+            losses = [float(tr.step(x[4 * r:4 * r + 4], y[4 * r:4 * r + 4])) for x, y in data]
+            out[r] = (losses, [m.clone() for m in tr.state.master_state().values()], tr,
+                      None if tr.state.flat_lowp is None else tr.state.flat_lowp.clone())
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+            tw.barrier.abort()
+
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(120) for t in ts]
+    assert not errs and len(out) == world, errs
+    tol = dict(rtol=3e-3, atol=3e-4) if full else dict(rtol=1e-5, atol=1e-6)
+    mean_loss = [sum(out[r][0][i] for r in range(world)) / world for i in range(len(data))]
+    assert mean_loss == pytest.approx(want, rel=3e-3 if full else 1e-5)
+    for r in range(world):
+        for m, q in zip(out[r][1], ref.parameters()):
+            torch.testing.assert_close(m, q.detach(), **tol)
+        for m, m0 in zip(out[r][1], out[0][1]):
+            assert torch.equal(m, m0)                         # bit-identical parameters on every rank
+        tr = out[r][2]
+        if full:
+            assert len(tr.state.buckets) >= 3 and tr.state.buckets[-1].numel * 4 <= 1536
+            assert torch.equal(out[r][3], tr.state.flat_param.to(torch.bfloat16))   # the check bench.py applies after a run
+        for b in tr.state.buckets:
+            assert b.momentum.numel() == tr.comm.slice_elems(b.numel, torch.float32)
