@@ -224,6 +224,51 @@ def cmd_suspend(cli: MPIJobClient, a, value: bool) -> int:
     return 0
 
 
+def cmd_patch(cli: MPIJobClient, a) -> int:
+    """`kubectl patch mpijob NAME --type merge -p '{"spec": {"runPolicy": {"suspend": true}}}'` (how Kueue-style controllers and
+    scripts flip fields of a running job); only merge patches exist here."""
+    if a.kind.lower() not in ("mpijob", "mpijobs", "mpijob.kubeflow.org"):
+        print("error: only mpijobs can be patched through the CLI", file=sys.stderr)
+        return 2
+    if a.type not in ("merge", "strategic"):
+        print(f"error: patch type {a.type!r} is not supported (merge only)", file=sys.stderr)
+        return 2
+    try:
+        body = yaml.safe_load(a.patch) if a.patch is not None else yaml.safe_load(open(a.patch_file).read())
+    except Exception as e:  # noqa: BLE001
+        print(f"error: cannot parse the patch: {e}", file=sys.stderr)
+        return 2
+    if not isinstance(body, dict):
+        print("error: the patch must be a JSON / YAML object", file=sys.stderr)
+        return 2
+    cli.patch(a.name, body, a.namespace)
+    print(f"mpijob.kubeflow.org/{a.name} patched")
+    return 0
+
+
+def cmd_meta(cli: MPIJobClient, a, field: str) -> int:
+    """`kubectl label / annotate mpijob NAME key=value ... key-` (a trailing dash removes the key)."""
+    changes = {}
+    for kv in a.pairs:
+        if kv.endswith("-") and "=" not in kv:
+            changes[kv[:-1]] = None
+        elif "=" in kv:
+            k, v = kv.split("=", 1)
+            changes[k] = v
+        else:
+            print(f"error: expected key=value or key-, got {kv!r}", file=sys.stderr)
+            return 2
+    if not a.overwrite:
+        cur = (cli.get(a.name, a.namespace).get("metadata", {}).get(field) or {})
+        clash = [k for k, v in changes.items() if v is not None and k in cur and cur[k] != v]
+        if clash:
+            print(f"error: {field[:-1]} {clash[0]!r} already has a value ({cur[clash[0]]}), and --overwrite is false", file=sys.stderr)
+            return 1
+    cli.patch(a.name, {"metadata": {field: changes}}, a.namespace)
+    print(f"mpijob.kubeflow.org/{a.name} {'labeled' if field == 'labels' else 'annotated'}")
+    return 0
+
+
 def cmd_wait(cli: MPIJobClient, a) -> int:
     try:
         j = cli.wait_for_condition(a.name, a.condition, a.namespace, timeout=a.timeout)
@@ -333,6 +378,19 @@ def main(argv: Optional[List[str]] = None) -> int:
     for name in ("suspend", "resume"):
         p = sub.add_parser(name)
         p.add_argument("name")
+    p = sub.add_parser("patch")
+    p.add_argument("kind")
+    p.add_argument("name")
+    p.add_argument("--type", default="merge")
+    g = p.add_mutually_exclusive_group(required=True)
+    g.add_argument("-p", "--patch", default=None)
+    g.add_argument("--patch-file", default=None)
+    for name in ("label", "annotate"):
+        p = sub.add_parser(name)
+        p.add_argument("kind")
+        p.add_argument("name")
+        p.add_argument("pairs", nargs="+", help="key=value ... (key- removes)")
+        p.add_argument("--overwrite", action="store_true")
     p = sub.add_parser("wait")
     p.add_argument("name")
     p.add_argument("--for", dest="condition", default="Succeeded")
@@ -373,6 +431,10 @@ def main(argv: Optional[List[str]] = None) -> int:
         return cmd_suspend(cli, a, True)
     if a.cmd == "resume":
         return cmd_suspend(cli, a, False)
+    if a.cmd == "patch":
+        return cmd_patch(cli, a)
+    if a.cmd in ("label", "annotate"):
+        return cmd_meta(cli, a, "labels" if a.cmd == "label" else "annotations")
     if a.cmd == "wait":
         return cmd_wait(cli, a)
     if a.cmd == "topology":

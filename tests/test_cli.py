@@ -159,3 +159,30 @@ def test_logs_follow_and_get_watch(server, tmp_path):
     assert core.read_namespaced_pod(pod, "default").status.phase == "Succeeded"
     wout, _ = watch.communicate(timeout=30)
     assert watch.returncode == 0 and "NAME" in wout and "Succeeded" in wout and wout.count("follow") >= 2, wout   # several change lines
+
+
+def test_patch_label_annotate(server, tmp_path):
+    """`kubectl patch --type merge -p ...`, `kubectl label`, `kubectl annotate` (key=value, key- removes, --overwrite)."""
+    f = tmp_path / "job.yaml"
+    f.write_text(JOB.replace("sleep 0.3", "sleep 30"))
+    assert ctl(server, "apply", "-f", str(f))[0] == 0
+    rc, out, err = ctl(server, "patch", "mpijob", "cli", "--type", "merge", "-p", '{"spec": {"runPolicy": {"suspend": true}}}')
+    assert rc == 0 and "patched" in out, err
+    rc, out, _ = ctl(server, "get", "mpijob", "cli", "-o", "json")
+    assert json.loads(out)["spec"]["runPolicy"]["suspend"] is True
+    pf = tmp_path / "p.yaml"
+    pf.write_text("spec:\n  runPolicy:\n    suspend: false\n")
+    assert ctl(server, "patch", "mpijob", "cli", "--patch-file", str(pf))[0] == 0
+    assert json.loads(ctl(server, "get", "mpijob", "cli", "-o", "json")[1])["spec"]["runPolicy"]["suspend"] is False
+    assert ctl(server, "patch", "mpijob", "cli", "--type", "json", "-p", "[]")[0] == 2
+    assert ctl(server, "patch", "mpijob", "cli", "-p", "[1, 2]")[0] == 2
+    assert ctl(server, "label", "mpijob", "cli", "team=vision", "tier=batch")[0] == 0
+    assert ctl(server, "annotate", "mpijob", "cli", "note=first")[0] == 0
+    meta = json.loads(ctl(server, "get", "mpijob", "cli", "-o", "json")[1])["metadata"]
+    assert meta["labels"]["team"] == "vision" and meta["labels"]["tier"] == "batch" and meta["annotations"]["note"] == "first"
+    rc, _, err = ctl(server, "label", "mpijob", "cli", "team=speech")
+    assert rc == 1 and "--overwrite" in err
+    assert ctl(server, "label", "mpijob", "cli", "team=speech", "tier-", "--overwrite")[0] == 0
+    meta = json.loads(ctl(server, "get", "mpijob", "cli", "-o", "json")[1])["metadata"]
+    assert meta["labels"]["team"] == "speech" and "tier" not in meta["labels"]
+    assert ctl(server, "delete", "mpijob", "cli")[0] == 0
