@@ -315,14 +315,12 @@ def cmd_run(a) -> int:
                         md = p["metadata"]
                         if md.get("labels", {}).get(C.JOB_ROLE_LABEL) != "launcher" or md.get("labels", {}).get(C.JOB_NAME_LABEL, job.name) != job.name:
                             continue
-                        text = op.agent.logs(job.namespace, md["name"])
-                        done = printed.get(md["name"], 0)
-                        if len(text) < done:  # container restarted in place: the log file started over
-                            done = 0
-                        if len(text) > done:
-                            sys.stdout.write(text[done:])
+                        while True:   # only the new bytes (a restarted / rotated log starts over at 0)
+                            piece, printed[md["name"]] = op.agent.log_slice(job.namespace, md["name"], printed.get(md["name"], 0))
+                            if not piece:
+                                break
+                            sys.stdout.write(piece.decode(errors="replace"))
                             sys.stdout.flush()
-                        printed[md["name"]] = len(text)
 
                 last_drain = 0.0
                 while time.time() - t0 < a.timeout:

@@ -422,14 +422,10 @@ def _make_handler(op: Operator, restricted: bool = False):
                 self.send_header("Transfer-Encoding", "chunked")
                 self.end_headers()
                 while True:
-                    data = op.agent.logs(ns, name).encode()
-                    if len(data) < sent:          # container restarted: a fresh log
-                        sent = 0
-                    if len(data) > sent:
-                        piece = data[sent:]
+                    piece, sent = op.agent.log_slice(ns, name, sent)   # only what is new (restart / rotation: starts over)
+                    if piece:
                         self.wfile.write(b"%x\r\n" % len(piece) + piece + b"\r\n")
                         self.wfile.flush()
-                        sent = len(data)
                         continue
                     try:
                         phase = (store.get("pods", ns, name).get("status") or {}).get("phase", "")

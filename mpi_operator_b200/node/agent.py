@@ -190,6 +190,9 @@ class NodeAgent:
             self._wake.clear()
             try:
                 self.sync_once()
+                if time.monotonic() - getattr(self, "_last_rotate", 0.0) > 10.0:
+                    self._last_rotate = time.monotonic()
+                    self.rotate_logs()
             except Exception:  # noqa: BLE001
                 log.exception("node agent sync failed")
 
@@ -815,3 +818,44 @@ class NodeAgent:
                 return f.read()
         except OSError:
             return ""
+
+    def log_slice(self, namespace: str, pod_name: str, offset: int) -> "tuple[bytes, int]":
+        """Bytes of the pod's log from ``offset`` on and the offset to ask with next time (what `logs -f` polls with: the cost
+        of a poll is the new data, not the whole file). A log that became SHORTER than the offset was restarted or rotated:
+        reading starts over at 0."""
+        path = os.path.join(self.state_dir, "pods", namespace, pod_name, "logs", "0.log")
+        try:
+            size = os.path.getsize(path)
+            if size < offset:
+                offset = 0
+            if size == offset:
+                return b"", offset
+            with open(path, "rb") as f:
+                f.seek(offset)
+                data = f.read(4 << 20)          # bounded pieces: a follower of a huge log streams it in 4 MiB steps
+            return data, offset + len(data)
+        except OSError:
+            return b"", 0
+
+    def rotate_logs(self) -> int:
+        """kubelet-style container log rotation (containerLogMaxSize; here B200MPI_POD_LOG_MAX_BYTES, default 256 MiB, 0 = off):
+        a running pod's log that outgrew the limit is copied to `0.log.1` (replacing the previous generation) and truncated in
+        place - the container holds it open in append mode, so it keeps writing at the new end. Returns the number of rotations."""
+        limit = int(os.environ.get("B200MPI_POD_LOG_MAX_BYTES", 256 << 20))
+        if limit <= 0:
+            return 0
+        n = 0
+        with self._lock:
+            paths = [pr.log_path for pr in self._procs.values() if pr.log_path and pr.popen is not None and pr.popen.poll() is None]
+        for path in paths:
+            try:
+                if os.path.getsize(path) <= limit:
+                    continue
+                import shutil
+                shutil.copyfile(path, path + ".1")
+                with open(path, "r+b") as f:
+                    f.truncate(0)
+                n += 1
+            except OSError:
+                continue
+        return n
