@@ -394,6 +394,11 @@ def main(argv: Optional[List[str]] = None) -> int:
     p.add_argument("--for", dest="condition", default="Succeeded")
     p.add_argument("--timeout", type=float, default=300)
     sub.add_parser("topology")
+    for name in ("cordon", "uncordon"):
+        p = sub.add_parser(name, help="take a GPU out of / back into scheduling (running jobs keep it)")
+        p.add_argument("gpu", type=int, nargs="+")
+        if name == "cordon":
+            p.add_argument("--reason", default="")
     sub.add_parser("version")
     p = sub.add_parser("run")
     p.add_argument("-f", "--filename", action="append", required=True)
@@ -437,6 +442,23 @@ def main(argv: Optional[List[str]] = None) -> int:
         return cmd_wait(cli, a)
     if a.cmd == "topology":
         print(json.dumps(cli.raw_get("/topology"), indent=2))
+        return 0
+    if a.cmd in ("cordon", "uncordon"):
+        body = {a.cmd: a.gpu}
+        if getattr(a, "reason", ""):
+            body["reason"] = a.reason
+        try:
+            t = cli.api.call_api("/topology", "PATCH", body=body)
+        except ApiException as e:
+            try:
+                msg = json.loads(e.body).get("message", str(e))
+            except Exception:  # noqa: BLE001
+                msg = str(e)
+            print(f"error: {msg}", file=sys.stderr)
+            return 1
+        for g in a.gpu:
+            print(f"gpu/{g} {'cordoned' if a.cmd == 'cordon' else 'uncordoned'}")
+        print(f"free GPUs: {t['free_gpus']}; cordoned: {t['cordoned'] or 'none'}")
         return 0
     return 2
 

@@ -152,6 +152,9 @@ class Operator:
             queue_burst=self.opt.controller_burst, namespace=self.opt.namespace)
         self.agent = NodeAgent(self.store, discover_topology(), os.path.join(self.state_dir, "node"))
         self.elector = LeaderElector(self.store, self.state_dir, self.opt.lock_namespace)
+        from ..controller.events import EventRecorder
+        from ..node.health import GpuHealthMonitor
+        self.gpu_health = GpuHealthMonitor(self.agent, recorder=EventRecorder(self.store, "node-agent"))
         self._http: list = []
         self._started = False
 
@@ -177,12 +180,15 @@ class Operator:
     def _run_leading(self) -> None:
         self.controller.run(self.opt.threadiness)
         self.agent.start()
+        if self.agent.topology.source not in ("fake", "none"):   # real GPUs: NVML health probe -> cordon (node/health.py)
+            self.gpu_health.start()
 
     def _stopped_leading(self) -> None:
         log.critical("leader election lost")
         os._exit(1)
 
     def stop(self) -> None:
+        self.gpu_health.stop()
         for s in self._http:
             s.shutdown()
         self.controller.stop()
@@ -305,9 +311,7 @@ def _make_handler(op: Operator, restricted: bool = False):
                 if parts == ["version"]:
                     return self._send(200, version.info())
                 if parts == ["topology"]:
-                    t = op.agent.topology.to_dict()
-                    t["free_gpus"] = op.agent.alloc.free_gpus
-                    return self._send(200, t)
+                    return self._send(200, self._topology())
                 disc = self._discovery(parts)
                 if disc is not None:
                     return self._send(200, disc)
@@ -481,10 +485,29 @@ def _make_handler(op: Operator, restricted: bool = False):
             except errors.ApiError as e:
                 return self._send(e.code, e.to_status())
 
+        def _topology(self):
+            t = op.agent.topology.to_dict()
+            t["free_gpus"] = op.agent.alloc.free_gpus
+            t["cordoned"] = {str(g): why for g, why in sorted(op.agent.alloc.cordoned.items())}
+            return t
+
         def do_PATCH(self):  # noqa: N802
             if self._refuse():
                 return None
             parts, _ = self._route()
+            if parts == ["topology"]:
+                # `kubectl cordon / uncordon` for GPUs: {"cordon": [3], "uncordon": [5], "reason": "..."}
+                try:
+                    body = self._body()
+                    for g in body.get("cordon", []) or []:
+                        op.agent.alloc.cordon(int(g), str(body.get("reason") or "cordoned by the operator"))
+                    for g in body.get("uncordon", []) or []:
+                        op.agent.alloc.uncordon(int(g))
+                except (ValueError, TypeError) as e:
+                    return self._send(422, {"kind": "Status", "status": "Failure", "reason": "Invalid", "code": 422, "message": str(e)})
+                metrics.gpu_slots_free.set(op.agent.alloc.free_gpus)
+                op.agent.wake()
+                return self._send(200, self._topology())
             try:
                 r = self._resolve(parts)
                 if r is None or not r[2]:

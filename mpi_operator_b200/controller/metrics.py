@@ -27,6 +27,8 @@ hvd_negotiation_bytes = Counter("b200mpi_hvd_negotiation_bytes", "Bytes exchange
 hvd_stall_warnings = Counter("b200mpi_hvd_stall_warnings", "Stall-inspector warnings", registry=REGISTRY)
 ranks_active = Gauge("b200mpi_ranks_active", "Ranks currently running under the node agent", registry=REGISTRY)
 gpu_slots_free = Gauge("b200mpi_gpu_slots_free", "Unallocated GPU slots on this box", registry=REGISTRY)
+gpu_healthy = Gauge("b200mpi_gpu_healthy", "1 when the GPU passed its last health probe (node/health.py), 0 when it is cordoned by it", ["gpu"],
+                    registry=REGISTRY)
 reconcile_seconds = Histogram("mpi_operator_reconcile_duration_seconds", "Wall time of one syncHandler call",
                               buckets=(0.001, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5), registry=REGISTRY)
 

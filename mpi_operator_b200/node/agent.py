@@ -166,6 +166,10 @@ class NodeAgent:
             for key in list(self._procs):
                 self._kill(key, grace=0.5)
 
+    def wake(self) -> None:
+        """Run a sync round now (capacity changed: a GPU was cordoned / uncordoned)."""
+        self._wake.set()
+
     def _on_event(self, etype, obj, old) -> None:
         # Never take the agent lock here: watch handlers run under the store's dispatch lock,
         # while the sync loop calls into the store holding the agent lock (lock-order inversion).

@@ -32,11 +32,37 @@ class GangAllocator:
         self._lock = threading.RLock()
         self._free: List[int] = [g.index for g in topology.gpus]
         self._held: Dict[str, List[int]] = {}
+        self._cordoned: Dict[int, str] = {}   # GPU index -> reason (`kubectl cordon` for a GPU; set by hand or by node/health.py)
 
     @property
     def free_gpus(self) -> int:
         with self._lock:
             return len(self._free)
+
+    # ---- cordon: a GPU that must not receive new ranks (operator decision or failed health probe). Reservations that already
+    #      hold it keep it until they end; it does not return to the free pool while cordoned.
+    def cordon(self, gpu: int, reason: str = "cordoned") -> bool:
+        with self._lock:
+            if gpu not in {g.index for g in self.topology.gpus}:
+                raise ValueError(f"no GPU {gpu} on this box")
+            changed = self._cordoned.get(gpu) != reason
+            self._cordoned[gpu] = reason
+            self._free = [g for g in self._free if g != gpu]
+            return changed
+
+    def uncordon(self, gpu: int) -> bool:
+        with self._lock:
+            if gpu not in self._cordoned:
+                return False
+            del self._cordoned[gpu]
+            if not any(gpu in held for held in self._held.values()):
+                self._free = sorted(set(self._free) | {gpu})
+            return True
+
+    @property
+    def cordoned(self) -> Dict[int, str]:
+        with self._lock:
+            return dict(self._cordoned)
 
     def held(self, key: str) -> Optional[List[int]]:
         with self._lock:
@@ -97,4 +123,4 @@ class GangAllocator:
         with self._lock:
             got = self._held.pop(key, None)
             if got:
-                self._free = sorted(set(self._free) | set(got))
+                self._free = sorted(set(self._free) | {g for g in got if g not in self._cordoned})

@@ -186,3 +186,14 @@ def test_patch_label_annotate(server, tmp_path):
     meta = json.loads(ctl(server, "get", "mpijob", "cli", "-o", "json")[1])["metadata"]
     assert meta["labels"]["team"] == "speech" and "tier" not in meta["labels"]
     assert ctl(server, "delete", "mpijob", "cli")[0] == 0
+
+
+def test_cordon_and_uncordon_gpus(server):
+    rc, out, err = ctl(server, "cordon", "1", "3", "--reason", "swap the baseboard")
+    assert rc == 0 and "gpu/1 cordoned" in out and "free GPUs: 2" in out, err
+    topo = json.loads(ctl(server, "topology")[1])
+    assert topo["cordoned"] == {"1": "swap the baseboard", "3": "swap the baseboard"} and topo["free_gpus"] == 2
+    rc, out, _ = ctl(server, "uncordon", "1")
+    assert rc == 0 and "free GPUs: 3" in out
+    rc, _, err = ctl(server, "cordon", "9")
+    assert rc == 1 and "no GPU 9" in err

@@ -569,3 +569,51 @@ def test_pod_logs_are_followed_incrementally_and_rotated(op, monkeypatch):
     tail = op.agent.logs("default", launcher) if any(p["metadata"]["name"] == launcher for p in op.store.list("pods", "default")) else ""
     old = open(log_path + ".1").read() if os.path.exists(log_path + ".1") else ""
     assert "line-0-" in old and ("line-399-" in tail or tail == "")              # the container kept writing after the truncation
+
+
+def test_gpu_cordon_health_monitor_and_scheduling(op):
+    """`mpijobctl cordon <gpu>` / the NVML health monitor (node/health.py): a cordoned GPU receives no new ranks, a job that
+    does not fit the remaining GPUs waits, reservations that already hold the GPU keep it, the monitor lifts only its own
+    cordons, every change is an Event and a metric."""
+    from mpi_operator_b200.controller import metrics
+    from mpi_operator_b200.node.health import GpuHealthMonitor
+    alloc = op.agent.alloc
+    assert alloc.free_gpus == 8
+    holder = new_mpijob("holder", workers=2, launcher_cmd=("sleep", "30"), worker_cmd=("/usr/sbin/sshd", "-De"))
+    holder.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+    op.clientset.kubeflow_v2beta1().mpijobs("default").create(holder)
+    wait_for(lambda: alloc.free_gpus == 6, 15)
+    held = sorted(g for k in ("default/holder-worker-0", "default/holder-worker-1") for g in (alloc.held(k) or []))
+    assert held == [0, 1]
+    verdict = {g: None for g in range(8)}
+    verdict[1] = "uncorrected ECC errors since the last reset"      # a GPU in use
+    verdict[5] = "not reachable through NVML (NVMLError_GpuIsLost)"  # an idle GPU
+    mon = GpuHealthMonitor(op.agent, probe=lambda: dict(verdict), interval=0, recorder=op.gpu_health.recorder)
+    mon.check_once()
+    assert alloc.cordoned == {1: "health: " + verdict[1], 5: "health: " + verdict[5]} and alloc.free_gpus == 5
+    assert alloc.held("default/holder-worker-1") == [1]              # the running reservation keeps its GPU
+    alloc.cordon(7, "maintenance")                                   # a manual cordon
+    assert alloc.free_gpus == 4
+    text = metrics.render().decode() if isinstance(metrics.render(), bytes) else metrics.render()
+    assert 'b200mpi_gpu_healthy{gpu="5"} 0.0' in text and 'b200mpi_gpu_healthy{gpu="2"} 1.0' in text
+    evs = [e for e in op.store.list("events") if e.get("reason") == "GPUUnhealthy"]
+    assert len(evs) == 2 and any("GPU 5" in e["message"] for e in evs)
+    big = new_mpijob("big", workers=5, launcher_cmd=("true",), worker_cmd=("/usr/sbin/sshd", "-De"))
+    big.spec.replica("Worker").template["spec"]["containers"][0]["resources"] = {"limits": {"nvidia.com/gpu": 1}}
+    op.clientset.kubeflow_v2beta1().mpijobs("default").create(big)   # needs 5, only 4 usable GPUs are free
+    time.sleep(1.0)
+    running_big = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("big-worker") and (p.get("status") or {}).get("phase") == "Running"]
+    assert len(running_big) < 5
+    verdict[5] = None
+    mon.check_once()                                                 # GPU 5 recovered: the monitor lifts ITS cordon, not the manual one
+    assert 5 not in alloc.cordoned and alloc.cordoned[7] == "maintenance" and 1 in alloc.cordoned
+    wait_for(lambda: get(op, big).status and any(c.type == "Succeeded" and c.status == "True" for c in get(op, big).status.conditions or []), 30)
+    assert 7 not in {g for k in list(alloc._held) for g in alloc._held[k]}   # nothing was placed on the manually cordoned GPU
+    op.clientset.kubeflow_v2beta1().mpijobs("default").delete("holder")
+    op.clientset.kubeflow_v2beta1().mpijobs("default").delete("big")   # cleanPodPolicy None: its workers still hold their GPUs
+    wait_for(lambda: alloc.held("default/holder-worker-1") is None and not alloc._held, 15)
+    assert 1 not in alloc._free                                      # released while cordoned: stays out of the pool
+    verdict[1] = None
+    mon.check_once()
+    assert 1 in alloc._free and alloc.uncordon(7) and alloc.free_gpus == 8
+    assert any(e.get("reason") == "GPUHealthy" for e in op.store.list("events"))
