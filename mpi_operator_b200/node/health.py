@@ -8,7 +8,7 @@ through the collective watchdog / exit codes -, lifts only the cordons it set it
 (``mpijobctl cordon <gpu>`` / ``PATCH /topology``) are never lifted by the monitor.
 
 The default probe asks NVML (nvidia-ml-py): a device that cannot be queried (fell off the bus, ``NVML_ERROR_GPU_IS_LOST``),
-pending page retirements, a pending / failed row remap, and - only with ``B200MPI_GPU_HEALTH_ECC=1`` - uncorrected volatile ECC errors. Every query is optional: what a
+a FAILED row remap, and - only with ``B200MPI_GPU_HEALTH_STRICT=1`` - pending remaps / page retirements and uncorrected volatile ECC errors. Every query is optional: what a
 driver or GPU generation does not support is skipped.
 """
 from __future__ import annotations
@@ -44,16 +44,18 @@ def nvml_probe() -> Dict[int, Optional[str]]:
             except Exception as e:  # noqa: BLE001
                 out[i] = f"not reachable through NVML ({type(e).__name__}: {e})"
                 continue
-            # A non-zero volatile uncorrected-ECC counter alone does not take a GPU out of service (on Hopper / Blackwell the error
-            # has already been contained: the faulting process was killed and the row is queued for remapping, which the third
-            # check sees); B200MPI_GPU_HEALTH_ECC=1 makes it a reason of its own.
-            ecc_strict = os.environ.get("B200MPI_GPU_HEALTH_ECC", "0") == "1"
+            # Default reasons are the unambiguous ones: the GPU cannot be reached, or a row remap FAILED (the board needs service).
+            # A pending row remap / page retirement or a non-zero volatile uncorrected-ECC counter means the error was contained
+            # (the faulting process was killed) and the GPU stays usable until its next reset: these only count with
+            # B200MPI_GPU_HEALTH_STRICT=1, so a box does not lose capacity over a condition NVIDIA documents as "reset when convenient".
+            strict = os.environ.get("B200MPI_GPU_HEALTH_STRICT", "0") == "1"
             checks = (
-                ("uncorrected ECC errors since the last reset",
-                 lambda: ecc_strict and pynvml.nvmlDeviceGetTotalEccErrors(h, pynvml.NVML_MEMORY_ERROR_TYPE_UNCORRECTED, pynvml.NVML_VOLATILE_ECC) > 0),
+                ("row remapping failed", lambda: bool(pynvml.nvmlDeviceGetRemappedRows(h)[3])),
+                ("row remapping pending (GPU reset needed)", lambda: strict and bool(pynvml.nvmlDeviceGetRemappedRows(h)[2])),
                 ("page retirement pending (reboot / GPU reset needed)",
-                 lambda: pynvml.nvmlDeviceGetRetiredPagesPendingStatus(h) == pynvml.NVML_FEATURE_ENABLED),
-                ("row remapping pending or failed", lambda: any(pynvml.nvmlDeviceGetRemappedRows(h)[2:4])),
+                 lambda: strict and pynvml.nvmlDeviceGetRetiredPagesPendingStatus(h) == pynvml.NVML_FEATURE_ENABLED),
+                ("uncorrected ECC errors since the last reset",
+                 lambda: strict and pynvml.nvmlDeviceGetTotalEccErrors(h, pynvml.NVML_MEMORY_ERROR_TYPE_UNCORRECTED, pynvml.NVML_VOLATILE_ECC) > 0),
             )
             for what, bad in checks:
                 try:

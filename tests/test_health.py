@@ -38,13 +38,15 @@ def fake_nvml(state):
 
 
 def test_nvml_probe_flags_lost_ecc_retirement_and_remap(monkeypatch):
-    state = [{}, {"ecc": 3}, {"lost": True}, {"retire_pending": True}, {"remap_failed": True}, {"no_retire_api": True}]
+    state = [{}, {"ecc": 3}, {"lost": True}, {"retire_pending": True}, {"remap_failed": True}, {"no_retire_api": True}, {"remap_pending": True}]
     monkeypatch.setitem(sys.modules, "pynvml", fake_nvml(state))
-    assert nvml_probe()[1] is None                             # a contained ECC error alone does not cordon a GPU ...
-    monkeypatch.setenv("B200MPI_GPU_HEALTH_ECC", "1")          # ... unless asked to
+    v = nvml_probe()
+    # default: only the unambiguous conditions take a GPU out of service
+    assert [i for i, why in v.items() if why] == [2, 4] and "not reachable" in v[2] and "remapping failed" in v[4]
+    monkeypatch.setenv("B200MPI_GPU_HEALTH_STRICT", "1")       # contained errors count as well
     v = nvml_probe()
     assert v[0] is None and v[5] is None                       # an unsupported query is skipped, not a failure
-    assert "ECC" in v[1] and "not reachable" in v[2] and "retirement" in v[3] and "remap" in v[4]
+    assert "ECC" in v[1] and "retirement" in v[3] and "pending" in v[6]
     monkeypatch.setitem(sys.modules, "pynvml", None)           # no NVML at all (CPU box): nothing to say
     assert nvml_probe() == {}
 
