@@ -433,3 +433,20 @@ def test_multi_rank_trainer_matches_sgd_on_the_global_batch(world, full, monkeyp
             assert torch.equal(out[r][3], tr.state.flat_param.to(torch.bfloat16))   # the check bench.py applies after a run
         for b in tr.state.buckets:
             assert b.momentum.numel() == tr.comm.slice_elems(b.numel, torch.float32)
+
+
+def test_model_zoo_names_of_tf_cnn_benchmarks_build_and_train_one_step():
+    """--model names of tf_cnn_benchmarks beyond the in-tree families resolve to torchvision definitions (same trainer, unfused
+    BN); the *_v1.5 names are the in-tree ResNets; unknown names say what exists."""
+    from mpi_operator_b200.models import build_model, model_names
+    assert {"resnet101", "inception3", "googlenet", "mobilenet", "vgg16", "alexnet", "trivial"} <= set(model_names())
+    assert type(build_model("resnet50_v1.5")).__name__ == "ResNet" and type(build_model("resnet50_v1.5")) is type(build_model("resnet50"))
+    for name in ("mobilenet", "googlenet"):
+        tr = DataParallelTrainer(build_model(name), nn.CrossEntropyLoss(), FakeComm(), lr=0.01, momentum=0.9, autocast_dtype=None,
+                                 channels_last=False, cuda_graph=False)
+        x, y = torch.randn(2, 3, 64, 64), torch.randint(0, 1000, (2,))
+        l0 = float(tr.step(x, y))
+        assert l0 == l0 and tr.launches_per_step == len(tr.state.buckets)
+    with pytest.raises(KeyError) as e:
+        build_model("not-a-model")
+    assert "resnet101" in str(e.value)
