@@ -74,9 +74,11 @@ class FlatModelState:
         cap = max(bucket_bytes // 4, 1)
         # The LAST bucket (the earliest layers) is the one whose allreduce+SGD cannot hide behind backward. With
         # B200MPI_TAIL_BUCKET_BYTES=<n> (e.g. 4194304) it is capped at n bytes so the exposed tail of the step is one short
-        # kernel. Opt-in (0 = off): it was on during round 2's 8-GPU session, whose bench record was lost; bench.py measures it
-        # as its second multi-GPU candidate.
-        tail_cap = int(os.environ.get("B200MPI_TAIL_BUCKET_BYTES", 0)) // 4
+        # kernel. With world > 1 opt-in (0 = off): it was on during round 2's 8-GPU session, whose bench record was lost; bench.py
+        # measures it as its second multi-GPU candidate.
+        # Single-GPU default: 4 MiB (there the last bucket's kernel is exposed in full - it can only start when backward has
+        # finished - and nothing else changes: same kernel, one more launch).
+        tail_cap = int(os.environ.get("B200MPI_TAIL_BUCKET_BYTES", (4 << 20) if (comm.world == 1 and comm.device != "cpu") else 0)) // 4
         pad = 64 if bf16_params else 4
         remaining = sum(_align(p.numel(), pad) for p in order)
         tail_started = False
