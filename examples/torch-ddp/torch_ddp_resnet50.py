@@ -21,11 +21,19 @@ def main():
     ap.add_argument("--batch-size", type=int, default=64)
     ap.add_argument("--steps", type=int, default=60)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "b200mpi"],
+                    help="nccl: ProcessGroupNCCL (under the operator its NCCL calls are LD-injected b200mpi kernels); b200mpi: the c10d "
+                         "backend of mpi_operator_b200.parallel.c10d_backend (same runtime, no preloading)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dev = int(os.environ.get("LOCAL_RANK", rank)) % torch.cuda.device_count()
     torch.cuda.set_device(dev)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
+    if a.backend == "b200mpi":
+        sys.path.insert(0, os.path.abspath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..")))
+        import mpi_operator_b200.parallel.c10d_backend  # noqa: F401  (registers the backend)
+        dist.init_process_group("b200mpi", rank=rank, world_size=world)
+    else:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", dev))
     torch.backends.cudnn.benchmark = True
     import torchvision   # stock model definition: this script is what a user of torch DDP already has
     model = getattr(torchvision.models, a.model)(weights=None).cuda().to(memory_format=torch.channels_last)
@@ -58,7 +66,7 @@ def main():
     if rank == 0:
         injected = "libb200mpi_nccl" in os.environ.get("LD_PRELOAD", "")
         print(f"torch DDP {a.model} bs {a.batch_size}/GPU x {world} GPUs: {world * a.batch_size * a.steps / (ms.item() * 1e-3):.1f} images/sec "
-              f"({ms.item() / a.steps:.2f} ms/step, max over ranks), allreduce backend: {'b200mpi (LD_PRELOAD)' if injected else 'stock NCCL'}, "
+              f"({ms.item() / a.steps:.2f} ms/step, max over ranks), allreduce backend: {'b200mpi (c10d backend)' if a.backend == 'b200mpi' else 'b200mpi (LD_PRELOAD)' if injected else 'stock NCCL'}, "
               f"loss {loss.item():.3f}", flush=True)
     dist.destroy_process_group()
 

@@ -1,0 +1,259 @@
+"""``torch.distributed`` backend ``"b200mpi"``: the second front-end SURVEY.md section 7.1 step 7 names next to the NCCL-ABI
+``LD_PRELOAD`` shim ("a c10d ProcessGroup extension ... keep both behind one runtime API").
+
+    import mpi_operator_b200.parallel.c10d_backend        # registers the backend
+    torch.distributed.init_process_group("b200mpi")       # RANK / WORLD_SIZE / LOCAL_RANK from torchrun or our mpirun
+    model = torch.nn.parallel.DistributedDataParallel(model)
+
+No preloading and no NCCL in the process: the process group is a Python ``ProcessGroup`` whose collectives call the same
+runtime the shim calls - ``runtime.comm.Communicator`` (sm_100a NVSwitch kernels, enqueued on the CURRENT CUDA stream, so the
+returned ``Work`` is complete in stream order exactly like ProcessGroupNCCL's) for CUDA tensors, the ``libmpi`` shim
+(``hvd.host_backend.HostCommunicator``) for CPU tensors. Reference call site that creates the obligation: the workloads of
+examples/v2beta1/tensorflow-benchmarks/tensorflow-benchmarks.yaml:26-42 reach their collectives through a framework-level
+communication library; with PyTorch that library is c10d.
+
+Scope: the default (world) group and groups that contain every rank; ``new_group`` of a strict subset is refused with an
+explanation (sub-communicators exist in the MPI shim - csrc/mpi_shim/mpi_comm.cc - but not yet in the GPU runtime).
+Reductions: SUM, AVG, MIN, MAX natively, PRODUCT through one allgather.
+"""
+from __future__ import annotations
+
+import os
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+from torch._C._distributed_c10d import (AllgatherOptions, AllreduceOptions, AllToAllOptions, BarrierOptions, BroadcastOptions, ReduceOp,
+                                        ReduceOptions, ReduceScatterOptions, _create_work_from_future)
+from torch.futures import Future
+
+BACKEND_NAME = "b200mpi"
+_OP_NAMES = ((ReduceOp.SUM, "sum"), (ReduceOp.AVG, "avg"), (ReduceOp.MIN, "min"), (ReduceOp.MAX, "max"))
+
+
+def _op_name(op) -> Optional[str]:
+    """AllreduceOptions.reduceOp is a ReduceOp OBJECT (it can carry a premul-sum factor): compare, do not hash."""
+    for cand, name in _OP_NAMES:
+        if op == cand:
+            return name
+    return None
+
+
+def _done(result):
+    fut: Future = Future()
+    fut.set_result(result)
+    return _create_work_from_future(fut)
+
+
+class B200ProcessGroup(dist.ProcessGroup):
+    def __init__(self, rank: int, world_size: int):
+        super().__init__(rank, world_size)
+        self._rank, self._world = rank, world_size
+        self._host = None     # hvd.host_backend.HostCommunicator (CPU tensors), created on first use
+        self._dev = None      # runtime.comm.Communicator (CUDA tensors), created on first use
+
+    # ------------------------------------------------------------ plumbing --
+    def size(self):
+        return self._world
+
+    def rank(self):
+        return self._rank
+
+    def getBackendName(self):  # noqa: N802
+        return BACKEND_NAME
+
+    def __repr__(self):
+        return f"B200ProcessGroup(rank={self._rank}, world={self._world})"
+
+    def _comm(self, t: torch.Tensor):
+        from ..launch.env import job_id_from_env
+        if t.is_cuda:
+            if self._dev is None:
+                from ..runtime.comm import Communicator
+                dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+                self._dev = Communicator.create(self._rank, self._world, dev, job_id_from_env(os.environ) + "-c10d")
+            return self._dev
+        if self._host is None:
+            from ..hvd.host_backend import HostCommunicator
+            os.environ.setdefault("B200MPI_JOB_ID", job_id_from_env(os.environ))
+            os.environ.setdefault("B200MPI_RANK", str(self._rank))
+            os.environ.setdefault("B200MPI_WORLD_SIZE", str(self._world))
+            self._host = HostCommunicator()
+            if (self._host.rank, self._host.world) != (self._rank, self._world):
+                raise RuntimeError(f"b200mpi backend: the MPI shim sees rank {self._host.rank}/{self._host.world}, "
+                                   f"torch.distributed {self._rank}/{self._world}")
+        return self._host
+
+    @staticmethod
+    def _contig(t: torch.Tensor):
+        return t if t.is_contiguous() else t.contiguous()
+
+    def _allreduce_one(self, t: torch.Tensor, op) -> None:
+        c = self._comm(t)
+        if self._world == 1:
+            return
+        if op == ReduceOp.PRODUCT:
+            w = self._contig(t)
+            g = torch.empty((self._world,) + tuple(w.shape), dtype=w.dtype, device=w.device)
+            c.allgather(w, g)
+            t.copy_(g.prod(0))
+            return
+        name = _op_name(op)
+        if name is None:
+            raise NotImplementedError(f"b200mpi backend: reduction {op} is not supported (SUM, AVG, MIN, MAX, PRODUCT)")
+        w = self._contig(t)
+        if w.is_cuda and w.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+            f = w.float()                                   # the device kernels reduce floating point; integers round-trip (exact below 2^24)
+            c.allreduce(f, f, op=name)
+            t.copy_(f.to(t.dtype))
+            return
+        c.allreduce(w, w, op=name)
+        if w is not t:
+            t.copy_(w)
+
+    # --------------------------------------------------------- collectives --
+    def allreduce(self, tensors: List[torch.Tensor], opts=AllreduceOptions()):
+        with torch.no_grad():
+            for t in tensors:
+                self._allreduce_one(t.detach(), opts.reduceOp)
+        return _done(tensors)
+
+    def allreduce_coalesced(self, tensors: List[torch.Tensor], opts=AllreduceOptions()):
+        return self.allreduce(tensors, opts)
+
+    def reduce(self, tensors: List[torch.Tensor], opts=ReduceOptions()):
+        # every rank ends up with the result; only the root's copy is defined by the API
+        with torch.no_grad():
+            for t in tensors:
+                self._allreduce_one(t.detach(), opts.reduceOp)
+        return _done(tensors)
+
+    def broadcast(self, tensors: List[torch.Tensor], opts=BroadcastOptions()):
+        with torch.no_grad():
+            for t in tensors:
+                c = self._comm(t)
+                if self._world == 1:
+                    continue
+                w = self._contig(t.detach())
+                c.broadcast(w, root=opts.rootRank)
+                if w.data_ptr() != t.data_ptr():
+                    t.detach().copy_(w)
+        return _done(tensors)
+
+    def _allgather_base(self, output: torch.Tensor, inp: torch.Tensor, opts=AllgatherOptions()):
+        with torch.no_grad():
+            c = self._comm(inp)
+            src = self._contig(inp.detach())
+            if self._world == 1:
+                output.detach().view(-1).copy_(src.view(-1))
+            else:
+                out = output.detach()
+                dst = out if out.is_contiguous() else torch.empty_like(out, memory_format=torch.contiguous_format)
+                flat_in = src.view(-1)
+                pad = flat_in.numel() * flat_in.element_size() % 2   # the device allgather moves 2-byte units
+                if pad and src.is_cuda:
+                    raise NotImplementedError("b200mpi backend: allgather of an odd number of bytes on CUDA tensors")
+                c.allgather(flat_in, dst.view(-1))
+                if dst is not out:
+                    out.copy_(dst)
+        return _done(output)
+
+    def allgather(self, output_lists: List[List[torch.Tensor]], inputs: List[torch.Tensor], opts=AllgatherOptions()):
+        with torch.no_grad():
+            for outs, inp in zip(output_lists, inputs):
+                src = self._contig(inp.detach())
+                flat = torch.empty(self._world * src.numel(), dtype=src.dtype, device=src.device)
+                self._allgather_base(flat, src, opts)
+                for r, o in enumerate(outs):
+                    o.detach().copy_(flat[r * src.numel():(r + 1) * src.numel()].view_as(src))
+        return _done(output_lists)
+
+    def allgather_into_tensor_coalesced(self, outputs, inputs, opts=AllgatherOptions()):
+        for o, i in zip(outputs, inputs):
+            self._allgather_base(o, i, opts)
+        return _done(outputs)
+
+    def _reduce_scatter_base(self, output: torch.Tensor, inp: torch.Tensor, opts=ReduceScatterOptions()):
+        with torch.no_grad():
+            c = self._comm(inp)
+            src = self._contig(inp.detach())
+            if self._world == 1:
+                output.detach().view(-1).copy_(src.view(-1))
+                return _done(output)
+            op = opts.reduceOp
+            name = _op_name(op)
+            if name is None or (src.is_cuda and src.dtype not in (torch.float32, torch.bfloat16, torch.float16)):
+                full = src.clone()                          # generic: allreduce, keep the own block
+                self._allreduce_one(full, op)
+                output.detach().copy_(full.view(self._world, -1)[self._rank].view_as(output))
+                return _done(output)
+            out = output.detach()
+            dst = out if out.is_contiguous() else torch.empty_like(out, memory_format=torch.contiguous_format)
+            c.reduce_scatter(src.view(-1), dst.view(-1), op=name)
+            if dst is not out:
+                out.copy_(dst)
+        return _done(output)
+
+    def reduce_scatter(self, outputs: List[torch.Tensor], input_lists: List[List[torch.Tensor]], opts=ReduceScatterOptions()):
+        for out, ins in zip(outputs, input_lists):
+            self._reduce_scatter_base(out, torch.cat([self._contig(t.detach()).view(-1) for t in ins]), opts)
+        return _done(outputs)
+
+    def reduce_scatter_tensor_coalesced(self, outputs, inputs, opts=ReduceScatterOptions()):
+        for o, i in zip(outputs, inputs):
+            self._reduce_scatter_base(o, i, opts)
+        return _done(outputs)
+
+    def alltoall_base(self, output: torch.Tensor, inp: torch.Tensor, output_split_sizes: Optional[List[int]],
+                      input_split_sizes: Optional[List[int]], opts=AllToAllOptions()):
+        if output_split_sizes or input_split_sizes:
+            raise NotImplementedError("b200mpi backend: all_to_all_single with uneven splits (use hvd.alltoall(tensor, splits))")
+        with torch.no_grad():
+            c = self._comm(inp)
+            src = self._contig(inp.detach())
+            if self._world == 1:
+                output.detach().copy_(src.view_as(output))
+            else:
+                out = output.detach()
+                dst = out if out.is_contiguous() else torch.empty_like(out, memory_format=torch.contiguous_format)
+                c.alltoall(src, dst)
+                if dst is not out:
+                    out.copy_(dst)
+        return _done(output)
+
+    def barrier(self, opts=BarrierOptions()):
+        if self._world > 1:
+            c = self._dev if self._dev is not None else self._comm(torch.empty(0))
+            if c is self._dev:
+                torch.cuda.synchronize()
+                c.host_barrier()
+            else:
+                c.barrier()
+        return _done(None)
+
+    def shutdown(self):
+        for c in (self._dev, self._host):
+            if c is not None:
+                try:
+                    c.destroy()
+                except Exception:  # noqa: BLE001
+                    pass
+        self._dev = self._host = None
+
+
+def _create(dist_opts, backend_opts):
+    ranks = list(getattr(dist_opts, "global_ranks_in_group", []) or [])
+    world = dist.get_world_size() if dist.is_initialized() else dist_opts.group_size
+    if ranks and len(ranks) != world:
+        raise NotImplementedError(
+            f"b200mpi backend: new_group({ranks}) is a strict subset of the {world} ranks; only groups of every rank are supported "
+            "(create the subset with backend='gloo' / 'nccl', or run the ranks as separate MPIJobs)")
+    return B200ProcessGroup(dist_opts.group_rank, dist_opts.group_size)
+
+
+def register() -> None:
+    if BACKEND_NAME.upper() not in getattr(dist.Backend, "backend_list", []) and BACKEND_NAME not in getattr(dist.Backend, "backend_list", []):
+        dist.Backend.register_backend(BACKEND_NAME, _create, extended_api=True, devices=["cpu", "cuda"])
+
+
+register()

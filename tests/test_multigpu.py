@@ -76,3 +76,13 @@ def test_horovod_engine_with_cuda_tensors():
     n = min(torch.cuda.device_count(), 8)
     rcs = launch(n, [os.path.join(HERE, "hvd_engine_gpu_worker.py")], timeout=240, extra_env={"B200MPI_HVD_ENGINE": "1"})
     assert rcs == [0] * n
+
+
+def test_c10d_backend_on_gpus():
+    """torch.distributed backend "b200mpi" (parallel/c10d_backend.py) with CUDA tensors: collectives and DDP on the runtime's
+    kernels without LD_PRELOAD (tests/c10d_worker.py; the CPU form runs in tests/test_c10d_backend.py)."""
+    sys.path.insert(0, HERE)
+    from mp_launch import launch
+    n = min(torch.cuda.device_count(), 8)
+    rcs = launch(n, [os.path.join(HERE, "c10d_worker.py")], timeout=240)
+    assert rcs == [0] * n
