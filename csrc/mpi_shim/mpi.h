@@ -155,6 +155,7 @@ int MPI_Errhandler_free(MPI_Errhandler* errhandler);
 int MPI_Error_class(int errorcode, int* errorclass);
 int MPI_Comm_group(MPI_Comm comm, MPI_Group* group);
 int MPI_Comm_create(MPI_Comm comm, MPI_Group group, MPI_Comm* newcomm);
+int MPI_Comm_create_group(MPI_Comm comm, MPI_Group group, int tag, MPI_Comm* newcomm);   /* collective over the group's members only */
 int MPI_Group_size(MPI_Group group, int* size);
 int MPI_Group_rank(MPI_Group group, int* rank);
 int MPI_Group_incl(MPI_Group group, int n, const int* ranks, MPI_Group* newgroup);

@@ -303,6 +303,37 @@ int MPI_Comm_create(MPI_Comm c, MPI_Group g, MPI_Comm* out) {
   return MPI_SUCCESS;
 }
 
+// MPI-3: collective over the MEMBERS of `g` only (MPI_Comm_create involves every rank of `c`). The context id is agreed through
+// the group's first member: everybody sends its next free id (point-to-point on the parent's context, reserved tag + `tag`), the
+// leader answers with the maximum. What torch.distributed's new_group needs: only members call into the backend.
+int MPI_Comm_create_group(MPI_Comm c, MPI_Group g, int tag, MPI_Comm* out) {
+  int e = check(c); if (e) return e;
+  auto* v = group_of(g); if (!v) return MPI_ERR_GROUP;
+  const std::vector<int> ranks = *v;
+  Comm* P = comm_of(c);
+  int me = -1;
+  for (int i = 0; i < (int)ranks.size(); i++) if (ranks[(size_t)i] == g_rank) me = i;
+  if (me < 0) { *out = MPI_COMM_NULL; return MPI_SUCCESS; }
+  const int t = MPI_TAG_UB + 100 + (tag & 0xffff);
+  int mine = g_next_ctx, top = mine;
+  if (ranks.size() > 1) {
+    if (me != 0) {
+      e = send_bytes(&mine, sizeof(int), ranks[0], t, P->ctx); if (e) return e;
+      e = recv_bytes(&top, sizeof(int), ranks[0], t, P->ctx, nullptr, false, true, nullptr); if (e) return e;
+    } else {
+      for (size_t k = 1; k < ranks.size(); k++) {
+        int theirs = 0;
+        e = recv_bytes(&theirs, sizeof(int), ranks[k], t, P->ctx, nullptr, false, true, nullptr); if (e) return e;
+        top = std::max(top, theirs);
+      }
+      for (size_t k = 1; k < ranks.size(); k++) { e = send_bytes(&top, sizeof(int), ranks[k], t, P->ctx); if (e) return e; }
+    }
+  }
+  g_next_ctx = top + 1;
+  *out = new_comm(ranks, top);
+  return MPI_SUCCESS;
+}
+
 // -------------------------------------------------------------------------------------------- derived datatypes --
 int MPI_Type_contiguous(int count, MPI_Datatype old, MPI_Datatype* out) {
   MPI_Datatype base; size_t n;

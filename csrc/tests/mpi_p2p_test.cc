@@ -280,6 +280,28 @@ int main(int argc, char** argv) {
     int tr[2] = {0, n - 1}, tb[2] = {-9, -9};
     MPI_Group_translate_ranks(world_g, 2, tr, ends_g, tb);
     EXPECT(tb[0] == (n > 1 ? 1 : 0) && tb[1] == 0);
+    // MPI_Comm_create_group: only the members call (the others do something else meanwhile)
+    if (n >= 3) {
+      MPI_Group odd_g;
+      std::vector<int> odd;
+      for (int k = 1; k < n; k += 2) odd.push_back(k);
+      MPI_Group_incl(world_g, (int)odd.size(), odd.data(), &odd_g);
+      if (r % 2 == 1) {
+        MPI_Comm oddc;
+        EXPECT(MPI_Comm_create_group(MPI_COMM_WORLD, odd_g, 7, &oddc) == MPI_SUCCESS && oddc != MPI_COMM_NULL);
+        int osz = 0, orank = -1, s = 0, one = r;
+        MPI_Comm_size(oddc, &osz);
+        MPI_Comm_rank(oddc, &orank);
+        EXPECT(osz == (int)odd.size() && odd[orank] == r);
+        EXPECT(MPI_Allreduce(&one, &s, 1, MPI_INT, MPI_SUM, oddc) == MPI_SUCCESS);
+        int want = 0;
+        for (int k : odd) want += k;
+        EXPECT(s == want);
+        MPI_Comm_free(&oddc);
+      }
+      MPI_Group_free(&odd_g);
+      MPI_Barrier(MPI_COMM_WORLD);
+    }
     MPI_Group_free(&world_g); MPI_Group_free(&ends_g);
 
     MPI_Datatype triple;

@@ -49,7 +49,16 @@ class HostCommunicator:
     is_local = False
     has_multicast = False
 
-    def __init__(self):
+    def __init__(self, _parent: "Optional[HostCommunicator]" = None, _handle: int = _COMM_WORLD):
+        if _parent is not None:      # a sub-communicator (sub()): shares the library and MPI_Init of its parent
+            self._L, self._comm_h, self._owns_mpi = _parent._L, _handle, False
+            r, n = C.c_int(0), C.c_int(1)
+            self._L.MPI_Comm_rank(self._comm_h, C.byref(r))
+            self._L.MPI_Comm_size(self._comm_h, C.byref(n))
+            self.rank, self.world = r.value, n.value
+            self.launch_count, self._windows, self._alive = 0, 0, True
+            return
+        self._comm_h = _COMM_WORLD
         if not LIB_PATH.exists():
             raise RuntimeError(f"{LIB_PATH} is missing; run `make` (or __graft_entry__.build())")
         L = C.CDLL(str(LIB_PATH), mode=C.RTLD_GLOBAL)
@@ -98,7 +107,7 @@ class HostCommunicator:
         res = o if (work is t and o.dtype == t.dtype) else torch.empty_like(work)
         src = _IN_PLACE if res.data_ptr() == work.data_ptr() else C.c_void_p(work.data_ptr())
         if work.numel():
-            self._check(self._L.MPI_Allreduce(src, res.data_ptr(), work.numel(), _MPI_TYPES[work.dtype], _MPI_OPS[op], _COMM_WORLD),
+            self._check(self._L.MPI_Allreduce(src, res.data_ptr(), work.numel(), _MPI_TYPES[work.dtype], _MPI_OPS[op], self._comm_h),
                         "MPI_Allreduce")
         factor = (1.0 / self.world if op == "avg" else 1.0) * (1.0 if scale is None else float(scale))
         if factor != 1.0:
@@ -118,7 +127,7 @@ class HostCommunicator:
         t = self._host(tensor, "broadcast")
         self.launch_count += 1
         if t.numel():
-            self._check(self._L.MPI_Bcast(t.data_ptr(), t.numel() * t.element_size(), _BYTE, root, _COMM_WORLD), "MPI_Bcast")
+            self._check(self._L.MPI_Bcast(t.data_ptr(), t.numel() * t.element_size(), _BYTE, root, self._comm_h), "MPI_Bcast")
         return tensor
 
     def allgather(self, tensor, out, stream=None):
@@ -128,7 +137,7 @@ class HostCommunicator:
             raise ValueError("allgather: output must hold world x input")
         self.launch_count += 1
         if nbytes:
-            self._check(self._L.MPI_Allgather(t.data_ptr(), nbytes, _BYTE, o.data_ptr(), nbytes, _BYTE, _COMM_WORLD), "MPI_Allgather")
+            self._check(self._L.MPI_Allgather(t.data_ptr(), nbytes, _BYTE, o.data_ptr(), nbytes, _BYTE, self._comm_h), "MPI_Allgather")
         return out
 
     def alltoall(self, tensor, out, stream=None):
@@ -139,7 +148,7 @@ class HostCommunicator:
         self.launch_count += 1
         if nbytes:
             per = nbytes // self.world
-            self._check(self._L.MPI_Alltoall(t.data_ptr(), per, _BYTE, o.data_ptr(), per, _BYTE, _COMM_WORLD), "MPI_Alltoall")
+            self._check(self._L.MPI_Alltoall(t.data_ptr(), per, _BYTE, o.data_ptr(), per, _BYTE, self._comm_h), "MPI_Alltoall")
         return out
 
     def reduce_scatter(self, tensor, out, op: str = "sum", scale: Optional[float] = None, stream=None):
@@ -152,9 +161,22 @@ class HostCommunicator:
 
     def barrier(self, stream=None) -> None:
         self.launch_count += 1
-        self._check(self._L.MPI_Barrier(_COMM_WORLD), "MPI_Barrier")
+        self._check(self._L.MPI_Barrier(self._comm_h), "MPI_Barrier")
 
     host_barrier = barrier
+
+    def sub(self, ranks, tag: int = 0) -> "Optional[HostCommunicator]":
+        """Sub-communicator of the given WORLD ranks (in that order); collective over those ranks only
+        (MPI_Comm_create_group, csrc/mpi_shim/mpi_comm.cc). None on a rank that is not a member."""
+        L, i = self._L, C.c_int
+        wg, sg, nc = i(0), i(0), i(-1)
+        arr = (i * len(ranks))(*[int(r) for r in ranks])
+        self._check(L.MPI_Comm_group(_COMM_WORLD, C.byref(wg)), "MPI_Comm_group")
+        self._check(L.MPI_Group_incl(wg, len(ranks), arr, C.byref(sg)), "MPI_Group_incl")
+        self._check(L.MPI_Comm_create_group(_COMM_WORLD, sg, int(tag) & 0xffff, C.byref(nc)), "MPI_Comm_create_group")
+        L.MPI_Group_free(C.byref(wg))
+        L.MPI_Group_free(C.byref(sg))
+        return None if nc.value < 0 else HostCommunicator(_parent=self, _handle=nc.value)
 
     # ---------------------------------------------------------------- misc --
     def alloc_window(self, nbytes: int) -> HostWindow:

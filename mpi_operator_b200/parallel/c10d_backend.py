@@ -12,8 +12,9 @@ returned ``Work`` is complete in stream order exactly like ProcessGroupNCCL's) f
 examples/v2beta1/tensorflow-benchmarks/tensorflow-benchmarks.yaml:26-42 reach their collectives through a framework-level
 communication library; with PyTorch that library is c10d.
 
-Scope: the default (world) group and groups that contain every rank; ``new_group`` of a strict subset is refused with an
-explanation (sub-communicators exist in the MPI shim - csrc/mpi_shim/mpi_comm.cc - but not yet in the GPU runtime).
+``new_group(ranks)`` works as well: a sub-group gets communicators of its own on first use - on the host an MPI
+sub-communicator made by its members only (``MPI_Comm_create_group``, csrc/mpi_shim/mpi_comm.cc), on the device a separate
+runtime communicator whose rendezvous name is derived from the member list.
 Reductions: SUM, AVG, MIN, MAX natively, PRODUCT through one allgather.
 """
 from __future__ import annotations
@@ -45,10 +46,34 @@ def _done(result):
     return _create_work_from_future(fut)
 
 
+_world_host = None   # the process-wide MPI_COMM_WORLD communicator of the libmpi shim (MPI_Init happens once per process)
+
+
+def _host_world(rank: int, world: int):
+    global _world_host
+    if _world_host is None:
+        from ..hvd.host_backend import HostCommunicator
+        from ..launch.env import job_id_from_env
+        os.environ.setdefault("B200MPI_JOB_ID", job_id_from_env(os.environ))
+        os.environ.setdefault("B200MPI_RANK", str(rank))
+        os.environ.setdefault("B200MPI_WORLD_SIZE", str(world))
+        _world_host = HostCommunicator()
+        if (_world_host.rank, _world_host.world) != (rank, world):
+            raise RuntimeError(f"b200mpi backend: the MPI shim sees rank {_world_host.rank}/{_world_host.world}, "
+                               f"torch.distributed {rank}/{world}")
+    return _world_host
+
+
 class B200ProcessGroup(dist.ProcessGroup):
-    def __init__(self, rank: int, world_size: int):
+    def __init__(self, rank: int, world_size: int, global_ranks: Optional[List[int]] = None, global_rank: Optional[int] = None,
+                 global_world: Optional[int] = None):
         super().__init__(rank, world_size)
         self._rank, self._world = rank, world_size
+        self._granks = list(global_ranks) if global_ranks else None          # None: the group is the whole world, in order
+        self._grank = rank if global_rank is None else global_rank
+        self._gworld = world_size if global_world is None else global_world
+        if self._granks == list(range(self._gworld)):
+            self._granks = None
         self._host = None     # hvd.host_backend.HostCommunicator (CPU tensors), created on first use
         self._dev = None      # runtime.comm.Communicator (CUDA tensors), created on first use
 
@@ -67,21 +92,20 @@ class B200ProcessGroup(dist.ProcessGroup):
 
     def _comm(self, t: torch.Tensor):
         from ..launch.env import job_id_from_env
+        import zlib
+        digest = 0 if self._granks is None else zlib.crc32(",".join(map(str, self._granks)).encode())
         if t.is_cuda:
             if self._dev is None:
                 from ..runtime.comm import Communicator
                 dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
-                self._dev = Communicator.create(self._rank, self._world, dev, job_id_from_env(os.environ) + "-c10d")
+                name = job_id_from_env(os.environ) + ("-c10d" if self._granks is None else f"-c10d-{digest:08x}")
+                self._dev = Communicator.create(self._rank, self._world, dev, name)
             return self._dev
         if self._host is None:
-            from ..hvd.host_backend import HostCommunicator
-            os.environ.setdefault("B200MPI_JOB_ID", job_id_from_env(os.environ))
-            os.environ.setdefault("B200MPI_RANK", str(self._rank))
-            os.environ.setdefault("B200MPI_WORLD_SIZE", str(self._world))
-            self._host = HostCommunicator()
-            if (self._host.rank, self._host.world) != (self._rank, self._world):
-                raise RuntimeError(f"b200mpi backend: the MPI shim sees rank {self._host.rank}/{self._host.world}, "
-                                   f"torch.distributed {self._rank}/{self._world}")
+            world = _host_world(self._grank, self._gworld)
+            self._host = world if self._granks is None else world.sub(self._granks, tag=digest)
+            if self._host is None or (self._host.rank, self._host.world) != (self._rank, self._world):
+                raise RuntimeError("b200mpi backend: sub-communicator does not match the torch.distributed group")
         return self._host
 
     @staticmethod
@@ -232,7 +256,7 @@ class B200ProcessGroup(dist.ProcessGroup):
         return _done(None)
 
     def shutdown(self):
-        for c in (self._dev, self._host):
+        for c in (self._dev, self._host if self._host is not _world_host else None):   # MPI itself ends with the process
             if c is not None:
                 try:
                     c.destroy()
@@ -243,12 +267,9 @@ class B200ProcessGroup(dist.ProcessGroup):
 
 def _create(dist_opts, backend_opts):
     ranks = list(getattr(dist_opts, "global_ranks_in_group", []) or [])
-    world = dist.get_world_size() if dist.is_initialized() else dist_opts.group_size
-    if ranks and len(ranks) != world:
-        raise NotImplementedError(
-            f"b200mpi backend: new_group({ranks}) is a strict subset of the {world} ranks; only groups of every rank are supported "
-            "(create the subset with backend='gloo' / 'nccl', or run the ranks as separate MPIJobs)")
-    return B200ProcessGroup(dist_opts.group_rank, dist_opts.group_size)
+    gworld = dist.get_world_size() if dist.is_initialized() else dist_opts.group_size
+    grank = ranks[dist_opts.group_rank] if ranks else dist_opts.group_rank
+    return B200ProcessGroup(dist_opts.group_rank, dist_opts.group_size, ranks or None, grank, gworld)
 
 
 def register() -> None:

@@ -85,14 +85,22 @@ def main():
         ropt.step()
     for p, q in zip(model.parameters(), ref.parameters()):
         fails += int(not torch.allclose(p, q, rtol=1e-4, atol=1e-5))
-    if world > 2:                                                        # a strict subset is refused on its members
-        try:
-            dist.new_group([0, 1])
-            fails += int(rank in (0, 1))                                 # (non-members never reach the backend)
-        except NotImplementedError:
-            fails += int(rank not in (0, 1))
-        except RuntimeError as e:                                        # torch wraps creator exceptions on some versions
-            fails += int("strict subset" not in str(e))
+    if world > 2:                                                        # sub-groups get communicators of their own
+        low, high = dist.new_group([0, 1]), dist.new_group(list(range(1, world))[::-1])   # overlapping groups
+        z = torch.full((5,), float(rank + 1))
+        if rank in (0, 1):
+            dist.all_reduce(z, group=low)
+            fails += int(not torch.equal(z, torch.full((5,), 3.0)))
+        z = torch.full((5,), float(rank + 1))
+        if rank >= 1:
+            dist.all_reduce(z, group=high)
+            fails += int(not torch.equal(z, torch.full((5,), float(sum(range(2, world + 1))))))
+            got = [torch.empty(2) for _ in range(world - 1)]
+            dist.all_gather(got, torch.full((2,), float(rank)), group=high)
+            fails += int([int(t[0]) for t in got] != list(range(1, world)))           # torch orders a group by global rank
+            bb = torch.full((3,), float(rank))
+            dist.broadcast(bb, src=world - 1, group=high)
+            fails += int(not torch.equal(bb, torch.full((3,), float(world - 1))))
     same = dist.new_group(list(range(world)))                            # a group of every rank works
     y = torch.ones(3)
     dist.all_reduce(y, group=same)
