@@ -186,6 +186,10 @@ def shutdown() -> None:
         _state["engine"] = None
         _dump_engine_stats(e)
         e.shutdown()
+    for pid, ps in list(_process_sets.items()):
+        if pid:
+            remove_process_set(ps)
+    _next_process_set_id[0] = 1
     c = _state["comm"]
     if c is not None:
         c.destroy()
@@ -235,33 +239,125 @@ def _op_name(op, average):
 
 
 class ProcessSet:
-    """Horovod >= 0.23 process sets. Only the global set exists here (the reference's Horovod 0.19/0.20 predates the feature):
-    ``process_set=hvd.global_process_set`` is accepted everywhere, ``hvd.add_process_set`` explains itself."""
+    """Horovod >= 0.23 process sets (beyond the reference's Horovod 0.19 / 0.20, kept because newer Horovod scripts use them):
+    a subset of the job's ranks with a communicator of its own. ``hvd.global_process_set`` is every rank; others are made
+    with ``hvd.add_process_set([ranks])`` - on the host an MPI sub-communicator formed by its members
+    (``MPI_Comm_create_group``, csrc/mpi_shim/mpi_comm.cc), on GPUs a separate runtime communicator. Collectives that take
+    ``process_set=`` run on that communicator through the direct (call-order) path; ``root_rank`` stays a GLOBAL rank."""
 
-    process_set_id = 0
-
-    def size(self) -> int: return size()  # noqa: E704
-
-    def rank(self) -> int: return rank()  # noqa: E704
-
-    def included(self) -> bool: return True  # noqa: E704
+    def __init__(self, ranks=None):
+        self._ranks = None if ranks is None else sorted(int(r) for r in set(ranks))
+        self.process_set_id = 0 if ranks is None else None
+        self._c = None
 
     @property
     def ranks(self):
-        return list(range(size()))
+        return list(range(_comm_world().world)) if self._ranks is None else list(self._ranks)
+
+    def size(self) -> int:
+        return len(self.ranks)
+
+    def included(self) -> bool:
+        return self._ranks is None or _comm_world().rank in self._ranks
+
+    def rank(self) -> int:
+        """This process's rank inside the set (-1 when it is not a member)."""
+        me = _comm_world().rank
+        return me if self._ranks is None else (self._ranks.index(me) if me in self._ranks else -1)
+
+    def __repr__(self):
+        return f"ProcessSet(id={self.process_set_id}, ranks={self.ranks if _state['comm'] is not None else self._ranks})"
 
 
 global_process_set = ProcessSet()
+_process_sets = {0: global_process_set}
+_next_process_set_id = [1]
 
 
-def add_process_set(ranks):
-    raise NotImplementedError("process sets other than hvd.global_process_set are not implemented (one NVSwitch box: every "
-                              "collective spans the job's ranks); split the job into several MPIJobs instead")
+def _comm_world():
+    return _state.get("world_comm") or _comm()
 
 
-def _check_process_set(ps) -> None:
+def add_process_set(process_set) -> ProcessSet:
+    """Register a process set (a ``ProcessSet`` or a list of ranks). Every rank of the job calls this, in the same order (the ids
+    must agree); the members build the set's communicator."""
+    ps = process_set if isinstance(process_set, ProcessSet) else ProcessSet(process_set)
+    if ps._ranks is None:
+        return global_process_set
+    world = _comm_world()
+    if not ps._ranks or ps._ranks[0] < 0 or ps._ranks[-1] >= world.world:
+        raise ValueError(f"process set ranks {ps._ranks} are outside the job's 0..{world.world - 1}")
+    for other in _process_sets.values():
+        if other._ranks == ps._ranks:
+            raise ValueError(f"a process set with ranks {ps._ranks} already exists (id {other.process_set_id})")
+    ps.process_set_id = _next_process_set_id[0]
+    _next_process_set_id[0] += 1
+    if ps.included():
+        if getattr(world, "device", None) == "cpu":
+            ps._c = world.sub(ps._ranks, tag=1000 + ps.process_set_id)
+        else:
+            from ..runtime.comm import Communicator
+            ps._c = Communicator.create(ps._ranks.index(world.rank), len(ps._ranks), world.device,
+                                        f"{_state['info'].job_id}-ps{ps.process_set_id}")
+    _process_sets[ps.process_set_id] = ps
+    return ps
+
+
+def remove_process_set(process_set) -> bool:
+    if process_set is global_process_set:
+        raise ValueError("the global process set cannot be removed")
+    pid = getattr(process_set, "process_set_id", None)
+    if pid is None or _process_sets.get(pid) is not process_set:
+        return False
+    del _process_sets[pid]
+    if process_set._c is not None:
+        try:
+            process_set._c.destroy()
+        except Exception:  # noqa: BLE001
+            pass
+        process_set._c = None
+    process_set.process_set_id = None
+    return True
+
+
+class _in_process_set:
+    """``with _in_process_set(ps):`` - the collectives below run on the set's communicator: the module-level communicator is
+    swapped for the duration of the call (and the engine switched off: process-set collectives take the call-order path), so
+    ``size()`` / ``rank()`` inside the implementation mean the set's. Not re-entrant across threads, like Horovod's Python API."""
+
+    def __init__(self, ps):
+        self.ps = None if (ps is None or ps is global_process_set) else ps
+
+    def __enter__(self):
+        ps = self.ps
+        if ps is None:
+            return self
+        if ps.process_set_id is None or _process_sets.get(ps.process_set_id) is not ps:
+            raise ValueError("this process set is not registered: call hvd.add_process_set(process_set) on every rank first")
+        if not ps.included():
+            raise ValueError(f"rank {_comm_world().rank} is not part of process set {ps.process_set_id} (ranks {ps.ranks})")
+        self.saved = (_state["comm"], _state["engine"], _state.get("world_comm"))
+        _state["world_comm"] = self.saved[2] or self.saved[0]
+        _state["comm"], _state["engine"] = ps._c, None
+        return self
+
+    def __exit__(self, *exc):
+        if self.ps is not None:
+            _state["comm"], _state["engine"], _state["world_comm"] = self.saved
+        return False
+
+    def root(self, root_rank: int) -> int:
+        """Horovod's root_rank is a global rank; the communicator wants the rank inside the set."""
+        if self.ps is None:
+            return root_rank
+        if root_rank not in self.ps._ranks:
+            raise ValueError(f"root_rank {root_rank} is not part of process set {self.ps.process_set_id} (ranks {self.ps.ranks})")
+        return self.ps._ranks.index(root_rank)
+
+
+def _check_process_set(ps) -> None:   # kept for callers that only accept the global set
     if ps is not None and ps is not global_process_set:
-        raise NotImplementedError("only hvd.global_process_set is supported")
+        raise NotImplementedError("this operation only supports hvd.global_process_set")
 
 
 class _Done:
@@ -285,22 +381,27 @@ def _engine_for(tensor):
 
 
 def allreduce(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
-    _check_process_set(process_set)
     out = tensor.clone()
-    allreduce_(out, average, name, op, prescale_factor, postscale_factor)
+    allreduce_(out, average, name, op, prescale_factor, postscale_factor, process_set)
     return out
 
 
 def allreduce_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
-    _check_process_set(process_set)
-    return allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor).wait()
+    return allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor, process_set).wait()
 
 
-def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
-    return allreduce_async_(tensor.clone(), average, name, op, prescale_factor, postscale_factor)
+def allreduce_async(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    return allreduce_async_(tensor.clone(), average, name, op, prescale_factor, postscale_factor, process_set)
 
 
-def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    if process_set is not None and process_set is not global_process_set:
+        with _in_process_set(process_set):
+            return allreduce_async_(tensor, average, name, op, prescale_factor, postscale_factor)
+    return _allreduce_async_impl(tensor, average, name, op, prescale_factor, postscale_factor)
+
+
+def _allreduce_async_impl(tensor, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
     """In-place allreduce; returns a handle for ``synchronize`` / ``poll``. With the engine, ranks may submit named
     tensors in different orders and small tensors submitted close together travel fused."""
     import torch
@@ -352,31 +453,31 @@ def allreduce_async_(tensor, average=None, name=None, op=None, prescale_factor=1
     return _Done(tensor)
 
 
-def grouped_allreduce(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
-    hs = grouped_allreduce_async(tensors, average, name, op, prescale_factor, postscale_factor)
+def grouped_allreduce(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    hs = grouped_allreduce_async(tensors, average, name, op, prescale_factor, postscale_factor, process_set)
     return [h.wait() for h in hs]
 
 
-def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+def grouped_allreduce_async(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
     """All tensors are submitted before any is waited for, so the engine negotiates them in one cycle and fuses them."""
-    return [allreduce_async(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor)
+    return [allreduce_async(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor, process_set)
             for i, t in enumerate(tensors)]
 
 
-def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
-    hs = grouped_allreduce_async_(tensors, average, name, op, prescale_factor, postscale_factor)
+def grouped_allreduce_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
+    hs = grouped_allreduce_async_(tensors, average, name, op, prescale_factor, postscale_factor, process_set)
     return [h.wait() for h in hs]
 
 
-def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0):
+def grouped_allreduce_async_(tensors, average=None, name=None, op=None, prescale_factor=1.0, postscale_factor=1.0, process_set=None):
     """In-place form of ``grouped_allreduce_async``."""
-    return [allreduce_async_(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor)
+    return [allreduce_async_(t, average, f"{name}.{i}" if name else None, op, prescale_factor, postscale_factor, process_set)
             for i, t in enumerate(tensors)]
 
 
 def grouped_allgather(tensors, name=None, process_set=None):
-    _check_process_set(process_set)
-    return [h.wait() for h in grouped_allgather_async(tensors, name)]
+    with _in_process_set(process_set):
+        return [h.wait() for h in grouped_allgather_async(tensors, name)]
 
 
 def grouped_allgather_async(tensors, name=None):
@@ -384,8 +485,8 @@ def grouped_allgather_async(tensors, name=None):
 
 
 def allgather(tensor, name=None, process_set=None):
-    _check_process_set(process_set)
-    return allgather_async(tensor, name).wait()
+    with _in_process_set(process_set):
+        return allgather_async(tensor, name).wait()
 
 
 def allgather_async(tensor, name=None):
@@ -418,14 +519,13 @@ def allgather_async(tensor, name=None):
 
 
 def broadcast(tensor, root_rank, name=None, process_set=None):
-    _check_process_set(process_set)
     out = tensor.clone()
-    return broadcast_(out, root_rank, name)
+    return broadcast_(out, root_rank, name, process_set)
 
 
 def broadcast_(tensor, root_rank, name=None, process_set=None):
-    _check_process_set(process_set)
-    return broadcast_async_(tensor, root_rank, name).wait()
+    with _in_process_set(process_set) as ctx:
+        return broadcast_async_(tensor, ctx.root(root_rank), name).wait()
 
 
 def broadcast_async(tensor, root_rank, name=None):
@@ -447,7 +547,14 @@ def broadcast_async_(tensor, root_rank, name=None):
     return _Done(tensor)
 
 
-def alltoall(tensor, splits=None, name=None):
+def alltoall(tensor, splits=None, name=None, process_set=None):
+    if process_set is not None and process_set is not global_process_set:
+        with _in_process_set(process_set):
+            return alltoall(tensor, splits, name)
+    return _alltoall_impl(tensor, splits, name)
+
+
+def _alltoall_impl(tensor, splits=None, name=None):
     """Even alltoall in one kernel; with ``splits`` (rows of dim 0 sent to each rank, horovod semantics) the rows are
     padded to the largest split so the same even kernel moves them, and ``(output, received_splits)`` is returned."""
     import torch
@@ -481,8 +588,11 @@ def alltoall(tensor, splits=None, name=None):
     return out, torch.tensor(recv, dtype=torch.int32)
 
 
-def reducescatter(tensor, op=None, name=None):
+def reducescatter(tensor, op=None, name=None, process_set=None):
     import torch
+    if process_set is not None and process_set is not global_process_set:
+        with _in_process_set(process_set):
+            return reducescatter(tensor, op, name)
     t = tensor.contiguous()
     out = torch.empty((t.shape[0] // size(),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     _comm().reduce_scatter(t, out, op=_op_name(op, None))
@@ -511,12 +621,6 @@ def is_homogeneous() -> bool:
     return True
 
 
-def remove_process_set(process_set) -> bool:
-    if process_set is global_process_set:
-        raise ValueError("the global process set cannot be removed")
-    return False   # no other process set can exist (add_process_set explains why)
-
-
 def _on_gpu() -> bool:
     return _comm().device != "cpu"
 
@@ -525,8 +629,11 @@ def _dev():
     return "cuda" if _on_gpu() else "cpu"
 
 
-def barrier():
+def barrier(process_set=None):
     import torch
+    if process_set is not None and process_set is not global_process_set:
+        with _in_process_set(process_set):
+            return barrier()
     e = _state["engine"]
     if e is not None:
         e.barrier()

@@ -34,6 +34,45 @@ assert torch.equal(hvd.alltoall_async(torch.arange(n, dtype=torch.float32) + 100
 grs = hvd.grouped_reducescatter([torch.ones(2 * n), torch.arange(n, dtype=torch.float32)], op=hvd.Sum)
 assert torch.equal(grs[0], torch.full((2,), float(n))) and torch.equal(grs[1], torch.tensor([float(n * r)]))
 assert hvd.is_homogeneous() and hvd.remove_process_set(object()) is False
+# process sets (Horovod >= 0.23): sub-communicators formed by their members; root_rank stays a global rank
+assert hvd.global_process_set.size() == n and hvd.global_process_set.rank() == r and hvd.global_process_set.included()
+assert torch.equal(hvd.allreduce(torch.ones(2), op=hvd.Sum, process_set=hvd.global_process_set), torch.full((2,), float(n)))
+if n >= 4:
+    ends = hvd.add_process_set([n - 1, 0])
+    evens = hvd.add_process_set(hvd.ProcessSet(range(0, n, 2)))
+    assert (ends.process_set_id, evens.process_set_id) == (1, 2) and ends.ranks == [0, n - 1] and evens.size() == (n + 1) // 2
+    assert ends.included() == (r in (0, n - 1)) and ends.rank() == ({0: 0, n - 1: 1}.get(r, -1))
+    if ends.included():
+        v = hvd.allreduce(torch.full((3,), float(r + 1)), op=hvd.Sum, process_set=ends)
+        assert torch.equal(v, torch.full((3,), float(n + 1))), v
+        assert torch.allclose(hvd.allreduce(torch.full((3,), float(r)), process_set=ends), torch.full((3,), (n - 1) / 2))   # Average over the SET
+        bb = hvd.broadcast(torch.full((4,), float(r)), root_rank=n - 1, process_set=ends)                                      # global root rank
+        assert torch.equal(bb, torch.full((4,), float(n - 1)))
+        gg2 = hvd.allgather(torch.full((1 + ends.rank(), 2), float(r)), process_set=ends)
+        assert gg2.shape == (3, 2) and float(gg2[0, 0]) == 0.0 and float(gg2[2, 1]) == n - 1
+        hvd.barrier(process_set=ends)
+        ga2 = [torch.full((2,), float(r)), torch.ones(3)]
+        hvd.grouped_allreduce_(ga2, op=hvd.Sum, process_set=ends)
+        assert torch.equal(ga2[0], torch.full((2,), float(n - 1))) and torch.equal(ga2[1], torch.full((3,), 2.0))
+    else:
+        try:
+            hvd.allreduce(torch.ones(1), process_set=ends)
+            raise AssertionError("a non-member must not be able to use the set")
+        except ValueError:
+            pass
+    if evens.included():
+        s_ev = hvd.allreduce(torch.tensor([float(r)]), op=hvd.Sum, process_set=evens)
+        assert float(s_ev) == float(sum(range(0, n, 2)))
+        rs_ev = hvd.reducescatter(torch.ones(2 * evens.size()), op=hvd.Sum, process_set=evens)
+        assert torch.equal(rs_ev, torch.full((2,), float(evens.size())))
+    try:
+        hvd.add_process_set([0, n - 1])
+        raise AssertionError("duplicate process set")
+    except ValueError:
+        pass
+    assert torch.equal(hvd.allreduce(torch.ones(2), op=hvd.Sum), torch.full((2,), float(n)))     # the global communicator is back in place
+    assert hvd.size() == n and hvd.rank() == r
+    assert hvd.remove_process_set(ends) and not hvd.remove_process_set(ends) and ends.process_set_id is None
 inplace = t.clone()
 hvd.allreduce_(inplace, op=hvd.Sum)
 assert torch.equal(inplace, n * torch.arange(10.) + n * (n - 1) / 2)
@@ -60,9 +99,9 @@ assert hvd.allgather_object({"rank": r, "blob": "x" * (r * 3)}) == [{"rank": k, 
 assert hvd.global_process_set.size() == n and hvd.global_process_set.ranks == list(range(n)) and hvd.global_process_set.included()
 assert torch.equal(hvd.allreduce(torch.ones(2), op=hvd.Sum, process_set=hvd.global_process_set), torch.full((2,), float(n)))
 try:
-    hvd.add_process_set([0])
-    raise SystemExit("add_process_set should explain that only the global set exists")
-except NotImplementedError:
+    hvd.add_process_set([0, n + 5])
+    raise SystemExit("add_process_set must refuse ranks outside the job")
+except ValueError:
     pass
 hvd.barrier()
 

@@ -101,7 +101,7 @@ def _repo():
     return _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("np_,engine", [(1, "1"), (3, "1"), (2, "0")])
+@pytest.mark.parametrize("np_,engine", [(1, "1"), (4, "1"), (3, "0")])
 def test_horovod_api_on_the_cpu_backend_under_mpirun(np_, engine):
     """The reference's Horovod example is a CPU job (examples/v2beta1/horovod/tensorflow-mnist.yaml: cpu-only workers).
     Without CUDA, hvd.init() builds the libmpi-shim communicator (hvd/host_backend.py); tests/hvd_cpu_worker.py checks
