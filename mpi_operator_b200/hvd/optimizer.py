@@ -373,7 +373,10 @@ def DistributedOptimizer(optimizer, named_parameters=None, compression=None, bac
     """``B200MPI_HVD_OPTIMIZER=engine`` (or ``engine=True``) selects Horovod's per-parameter scheme on the native background
     engine; the default is the window/bucket optimizer (gradients live in NVLink-visible memory, no fusion copies)."""
     import os
-    from . import Compression, _op_name, _state
+    from . import Compression, _op_name, _state, global_process_set
+    if kw.get("process_set") not in (None, global_process_set):
+        raise NotImplementedError("DistributedOptimizer works on the global process set; reduce over a subset with "
+                                  "hvd.allreduce(..., process_set=ps) in your own step")
     use_engine = kw.get("engine")
     if use_engine is None:
         use_engine = os.environ.get("B200MPI_HVD_OPTIMIZER", "") == "engine"
