@@ -104,6 +104,13 @@ class CoreV1Api:
             return stream if not _preload_content else "".join(stream)
         return self._c.logs("", namespace, pod=name, tail=tail_lines)
 
+    def list_node(self, **kw):
+        """The single box as a one-element NodeList (capacity / allocatable nvidia.com/gpu, cordoned GPUs as taints)."""
+        return _List([_Obj(n) for n in self._c.list_resource("nodes", None)])
+
+    def read_node(self, name, **kw):
+        return _Obj(self._c.get_resource("nodes", None, name))
+
     def list_namespaced_event(self, namespace, **kw):
         return _List([_Obj(e) for e in self._c.list_resource("events", namespace)])
 

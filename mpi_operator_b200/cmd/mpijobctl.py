@@ -33,7 +33,8 @@ KIND_ALIASES = {"mpijob": "mpijobs", "mpijobs": "mpijobs", "mj": "mpijobs", "pod
                 "job": "jobs", "jobs": "jobs", "svc": "services", "service": "services", "services": "services",
                 "cm": "configmaps", "configmap": "configmaps", "configmaps": "configmaps", "secret": "secrets",
                 "secrets": "secrets", "event": "events", "events": "events", "ev": "events", "podgroup": "podgroups",
-                "podgroups": "podgroups", "pg": "podgroups", "lease": "leases", "leases": "leases"}
+                "podgroups": "podgroups", "pg": "podgroups", "lease": "leases", "leases": "leases", "node": "nodes", "nodes": "nodes",
+                "no": "nodes"}
 
 
 def _age(ts: Optional[str]) -> str:
@@ -99,6 +100,15 @@ def cmd_get(cli: MPIJobClient, a) -> int:
             cs = (p.get("status", {}).get("containerStatuses") or [{}])[0]
             gp = (p["metadata"].get("annotations") or {}).get("b200mpi.kubeflow.org/gpus", "")
             print(f"{p['metadata']['name']:36} {p.get('status', {}).get('phase', 'Pending'):10} {str(cs.get('restartCount', 0)):8} {gp or '-':10} {_age(p['metadata'].get('creationTimestamp')):6}")
+    elif res == "nodes":
+        print(f"{'NAME':24} {'STATUS':26} {'GPUS':6} {'ALLOCATABLE':12} {'FREE':6} CORDONED")
+        for nd in items:
+            st = "Ready" + (",SchedulingDisabled" if nd.get("spec", {}).get("unschedulable") else "")
+            ann = nd["metadata"].get("annotations", {})
+            cord = json.loads(ann.get("b200mpi.kubeflow.org/cordoned-gpus", "{}"))
+            print(f"{nd['metadata']['name']:24} {st:26} {nd['status']['capacity'].get('nvidia.com/gpu', '0'):6} "
+                  f"{nd['status']['allocatable'].get('nvidia.com/gpu', '0'):12} {ann.get('b200mpi.kubeflow.org/free-gpus', '?'):6} "
+                  f"{','.join(sorted(cord, key=int)) or '-'}")
     elif res == "events":
         print(f"{'LAST SEEN':10} {'TYPE':8} {'REASON':28} {'OBJECT':28} MESSAGE")
         for e in sorted(items, key=lambda e: e.get("lastTimestamp", "")):

@@ -312,6 +312,13 @@ def _make_handler(op: Operator, restricted: bool = False):
                     return self._send(200, version.info())
                 if parts == ["topology"]:
                     return self._send(200, self._topology())
+                if parts[:3] == ["api", "v1", "nodes"] and len(parts) <= 4:
+                    node = self._node()
+                    if len(parts) == 4:
+                        if parts[3] != node["metadata"]["name"]:
+                            return self._send(404, errors.not_found("nodes", parts[3]).to_status())
+                        return self._send(200, node)
+                    return self._send(200, {"apiVersion": "v1", "kind": "NodeList", "metadata": {}, "items": [node]})
                 disc = self._discovery(parts)
                 if disc is not None:
                     return self._send(200, disc)
@@ -484,6 +491,30 @@ def _make_handler(op: Operator, restricted: bool = False):
                 return self._send(200, out)
             except errors.ApiError as e:
                 return self._send(e.code, e.to_status())
+
+        def _node(self):
+            """The box as a v1.Node (`kubectl get nodes` / `describe node`): capacity = discovered GPUs, allocatable = those not
+            cordoned, the NVML facts as labels, cordons as taints. Read-only and synthesised on every request."""
+            import socket
+            topo, alloc = op.agent.topology, op.agent.alloc
+            cordoned = alloc.cordoned
+            n = topo.gpu_count
+            name = socket.gethostname()
+            gpu0 = topo.gpus[0] if topo.gpus else None
+            labels = {"kubernetes.io/hostname": name, "b200mpi.kubeflow.org/topology-source": topo.source}
+            if gpu0 is not None:
+                labels["nvidia.com/gpu.product"] = (gpu0.name or "").replace(" ", "-")
+                labels["nvidia.com/gpu.count"] = str(n)
+                labels["nvidia.com/gpu.memory"] = str(gpu0.memory_bytes >> 20)
+            return {"apiVersion": "v1", "kind": "Node",
+                    "metadata": {"name": name, "uid": "node", "labels": labels,
+                                 "annotations": {"b200mpi.kubeflow.org/cordoned-gpus": json.dumps({str(g): w for g, w in sorted(cordoned.items())}),
+                                                 "b200mpi.kubeflow.org/free-gpus": str(alloc.free_gpus)}},
+                    "spec": {"unschedulable": n > 0 and len(cordoned) == n,
+                             "taints": [{"key": f"b200mpi.kubeflow.org/gpu-{g}", "value": why, "effect": "NoSchedule"} for g, why in sorted(cordoned.items())]},
+                    "status": {"capacity": {"nvidia.com/gpu": str(n)}, "allocatable": {"nvidia.com/gpu": str(n - len(cordoned))},
+                               "conditions": [{"type": "Ready", "status": "True", "reason": "NodeAgentRunning"}],
+                               "nodeInfo": {"kubeletVersion": version.info().get("gitVersion", "") if isinstance(version.info(), dict) else ""}}}
 
         def _topology(self):
             t = op.agent.topology.to_dict()

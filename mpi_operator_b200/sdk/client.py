@@ -192,9 +192,13 @@ class MPIJobClient:
 
     # ------------------------------------------------------- generic access --
     def list_resource(self, resource: str, namespace: Optional[str] = "default") -> List[Dict[str, Any]]:
+        if resource == "nodes":   # cluster-scoped, synthesised by the daemon (the box as a v1.Node)
+            return self.api.call_api("/api/v1/nodes", "GET")["items"]
         return self.api.call_api(self._path(resource, namespace), "GET")["items"]
 
     def get_resource(self, resource: str, namespace: str, name: str) -> Dict[str, Any]:
+        if resource == "nodes":
+            return self.api.call_api(f"/api/v1/nodes/{name}", "GET")
         return self.api.call_api(self._path(resource, namespace, name), "GET")
 
     def delete_resource(self, resource: str, namespace: str, name: str):

@@ -197,3 +197,24 @@ def test_cordon_and_uncordon_gpus(server):
     assert rc == 0 and "free GPUs: 3" in out
     rc, _, err = ctl(server, "cordon", "9")
     assert rc == 1 and "no GPU 9" in err
+
+
+def test_get_nodes_shows_the_box_with_capacity_and_cordons(server):
+    """`kubectl get nodes` / `CoreV1Api.list_node()`: the box as a v1.Node - GPU capacity, allocatable minus cordoned GPUs, taints."""
+    assert ctl(server, "cordon", "2", "--reason", "fan")[0] == 0
+    rc, out, err = ctl(server, "get", "nodes")
+    assert rc == 0 and "ALLOCATABLE" in out and " 4 " in out and " 3 " in out and out.strip().endswith("2"), out + err
+    node = json.loads(ctl(server, "get", "nodes", "-o", "json")[1])["items"][0]
+    assert node["status"]["capacity"]["nvidia.com/gpu"] == "4" and node["status"]["allocatable"]["nvidia.com/gpu"] == "3"
+    assert node["spec"]["taints"] == [{"key": "b200mpi.kubeflow.org/gpu-2", "value": "fan", "effect": "NoSchedule"}]
+    assert node["metadata"]["labels"]["nvidia.com/gpu.count"] == "4" and node["spec"]["unschedulable"] is False
+    rc, out, _ = ctl(server, "get", "node", node["metadata"]["name"], "-o", "yaml")
+    assert rc == 0 and "kind: Node" in out
+    os.environ["MPIJOB_SERVER"] = server
+    try:
+        import kubernetes
+        kubernetes.config.load_kube_config()
+        nodes = kubernetes.client.CoreV1Api().list_node().items
+        assert len(nodes) == 1 and nodes[0].status.allocatable["nvidia.com/gpu"] == "3"
+    finally:
+        os.environ.pop("MPIJOB_SERVER", None)
