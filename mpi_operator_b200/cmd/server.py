@@ -418,6 +418,8 @@ def _make_handler(op: Operator, restricted: bool = False):
                         rl.append({"name": plural + "/status", "singularName": "", "namespaced": namespaced, "kind": kind, "verbs": ["get", "patch", "update"]})
                     if res == "pods":
                         rl.append({"name": "pods/log", "singularName": "", "namespaced": True, "kind": "Pod", "verbs": ["get"]})
+                        rl.append({"name": "nodes", "singularName": "node", "namespaced": False, "kind": "Node", "verbs": ["get", "list"],
+                                   "shortNames": ["no"]})
                 gv = key[len("apis/"):] if key.startswith("apis/") else "v1"
                 return {"kind": "APIResourceList", "apiVersion": "v1", "groupVersion": gv, "resources": rl}
             return None
