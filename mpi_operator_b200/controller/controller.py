@@ -559,6 +559,7 @@ class MPIJobController:
                     job.status.completion_time = launcher.get("status", {}).get("completionTime")
                 S.update_mpijob_conditions(job, C.JOB_SUCCEEDED, C.CONDITION_TRUE, S.MPIJOB_SUCCEEDED_REASON, msg, self._now())
                 metrics.mpi_jobs_successful.inc()
+                metrics.observe_job_duration(job, "Succeeded")
             elif is_job_failed(launcher):
                 self.update_mpijob_failed_status(job, launcher, launcher_pods)
             else:
@@ -615,6 +616,7 @@ class MPIJobController:
             job.status.completion_time = self._now()
         S.update_mpijob_conditions(job, C.JOB_FAILED, C.CONDITION_TRUE, reason, msg, self._now())
         metrics.mpi_jobs_failed.inc()
+        metrics.observe_job_duration(job, "Failed")
 
     def do_update_job_status(self, job: MPIJob) -> None:
         """controller.go:1301-1304."""

@@ -29,6 +29,8 @@ ranks_active = Gauge("b200mpi_ranks_active", "Ranks currently running under the 
 gpu_slots_free = Gauge("b200mpi_gpu_slots_free", "Unallocated GPU slots on this box", registry=REGISTRY)
 gpu_healthy = Gauge("b200mpi_gpu_healthy", "1 when the GPU passed its last health probe (node/health.py), 0 when it is cordoned by it", ["gpu"],
                     registry=REGISTRY)
+job_duration_seconds = Histogram("mpi_operator_job_duration_seconds", "startTime -> completionTime of finished MPIJobs", ["result"],
+                                 buckets=(1, 5, 15, 30, 60, 120, 300, 600, 1800, 3600, 4 * 3600, 24 * 3600), registry=REGISTRY)
 reconcile_seconds = Histogram("mpi_operator_reconcile_duration_seconds", "Wall time of one syncHandler call",
                               buckets=(0.001, 0.005, 0.01, 0.05, 0.1, 0.5, 1, 5), registry=REGISTRY)
 
@@ -56,3 +58,14 @@ def render() -> bytes:
 
 def counter_value(counter) -> float:
     return counter._value.get()  # test helper
+
+
+def observe_job_duration(job, result: str) -> None:
+    """``result``: Succeeded | Failed. Uses the status' own timestamps (RFC 3339); silently skips jobs without a start time."""
+    try:
+        from ..api.meta import parse_rfc3339
+        st, ct = job.status.start_time, job.status.completion_time
+        if st and ct:
+            job_duration_seconds.labels(result=result).observe(max(0.0, parse_rfc3339(ct) - parse_rfc3339(st)))
+    except Exception:  # noqa: BLE001
+        pass

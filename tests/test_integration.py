@@ -482,6 +482,23 @@ def test_metrics_text_has_reference_names(op):
         assert name in text
 
 
+def test_job_duration_histogram_counts_finished_jobs(op):
+    """Beyond the reference's five metrics: startTime -> completionTime of finished jobs, by result."""
+    def count(result):
+        for ln in metrics.render().decode().splitlines():
+            if ln.startswith('mpi_operator_job_duration_seconds_count{result="%s"}' % result):
+                return float(ln.split()[-1])
+        return 0.0
+    ok0, bad0 = count("Succeeded"), count("Failed")
+    good = new_mpijob("dur-ok", workers=1, launcher_cmd=("true",), worker_cmd=("/usr/sbin/sshd", "-De"))
+    bad = new_mpijob("dur-bad", workers=1, launcher_cmd=("false",), worker_cmd=("/usr/sbin/sshd", "-De"))
+    bad.spec.run_policy.backoff_limit = 0
+    submit(op, good)
+    submit(op, bad)
+    wait_for(lambda: conds(get(op, good)).get("Succeeded") == "True" and conds(get(op, bad)).get("Failed") == "True", what="both finished")
+    assert count("Succeeded") == ok0 + 1 and count("Failed") == bad0 + 1
+
+
 @needs_native
 def test_collective_runtime_is_ld_injected_into_ranks(op):
     shim = os.path.join(REPO, "mpi_operator_b200/lib/libb200mpi_nccl.so")
