@@ -63,10 +63,17 @@ enum { MPI_IDENT = 0, MPI_CONGRUENT = 1, MPI_SIMILAR = 2, MPI_UNEQUAL = 3 };
 enum {
   MPI_CHAR = 1, MPI_SIGNED_CHAR, MPI_UNSIGNED_CHAR, MPI_BYTE, MPI_SHORT, MPI_UNSIGNED_SHORT, MPI_INT, MPI_UNSIGNED,
   MPI_LONG, MPI_UNSIGNED_LONG, MPI_LONG_LONG, MPI_UNSIGNED_LONG_LONG, MPI_FLOAT, MPI_DOUBLE, MPI_INT32_T, MPI_INT64_T,
-  MPI_UINT32_T, MPI_UINT64_T, MPI_C_BOOL
+  MPI_UINT32_T, MPI_UINT64_T, MPI_C_BOOL,
+  /* value + index pairs for MPI_MAXLOC / MPI_MINLOC: the C structs { float v; int i; } ... (extent = sizeof the struct) */
+  MPI_FLOAT_INT, MPI_DOUBLE_INT, MPI_LONG_INT, MPI_2INT
 };
 #define MPI_LONG_LONG_INT MPI_LONG_LONG
-enum { MPI_SUM = 1, MPI_MAX, MPI_MIN, MPI_PROD, MPI_LAND, MPI_LOR, MPI_BAND, MPI_BOR };
+enum { MPI_SUM = 1, MPI_MAX, MPI_MIN, MPI_PROD, MPI_LAND, MPI_LOR, MPI_BAND, MPI_BOR, MPI_MAXLOC, MPI_MINLOC };
+#define MPI_OP_NULL 0
+/* user-defined reductions: inoutvec[i] = invec[i] (op) inoutvec[i]; applied in rank order, so non-commutative functions work */
+typedef void(MPI_User_function)(void* invec, void* inoutvec, int* len, MPI_Datatype* datatype);
+int MPI_Op_create(MPI_User_function* function, int commute, MPI_Op* op);
+int MPI_Op_free(MPI_Op* op);
 
 #define MPI_THREAD_SINGLE 0
 #define MPI_THREAD_FUNNELED 1

@@ -470,6 +470,7 @@ static int scan_impl(const void* sb, void* rb, int count, MPI_Datatype t, MPI_Op
   Comm* C = comm_of(c);
   MPI_Datatype base; size_t n;
   if (!flatten_type(t, (size_t)count, &base, &n)) return MPI_ERR_TYPE;
+  if (!op_supported(base, op)) return MPI_ERR_OP;
   const size_t bytes = n * type_size(base);
   const int W = C->size(), m = C->my;
   const unsigned char* in = (const unsigned char*)(sb == MPI_IN_PLACE ? rb : sb);

@@ -37,6 +37,7 @@ bool flatten_type(MPI_Datatype t, size_t count, MPI_Datatype* base, size_t* n); 
 int fail(const std::string& what);
 size_t type_size(MPI_Datatype t);   // bytes of one element, derived (contiguous) types included; 0 = unknown
 bool reduce_into(void* acc, const void* x, size_t n, MPI_Datatype t, MPI_Op op);
+bool op_supported(MPI_Datatype base_type, MPI_Op op);   // checked by every rank before a reduction moves data
 int allgather_bytes(const void* in, void* out, size_t bytes);   // over MPI_COMM_WORLD, shared-memory path
 int check(MPI_Comm c);
 int p2p_init();        // mpi_p2p.cc: binds this rank's message socket (MPI_Init)

@@ -53,6 +53,8 @@ size_t type_size(MPI_Datatype t) {
     case MPI_INT: case MPI_UNSIGNED: case MPI_FLOAT: case MPI_INT32_T: case MPI_UINT32_T: return 4;
     case MPI_LONG: case MPI_UNSIGNED_LONG: case MPI_LONG_LONG: case MPI_UNSIGNED_LONG_LONG: case MPI_DOUBLE:
     case MPI_INT64_T: case MPI_UINT64_T: return 8;
+    case MPI_FLOAT_INT: case MPI_2INT: return 8;
+    case MPI_DOUBLE_INT: case MPI_LONG_INT: return 16;    // the C struct's size (stride of an array of pairs)
     default: return derived_type_size(t);
   }
 }
@@ -76,7 +78,60 @@ void combine_bits(T* acc, const T* x, size_t n, MPI_Op op) {
   for (size_t i = 0; i < n; i++) acc[i] = op == MPI_BAND ? (T)(acc[i] & x[i]) : (T)(acc[i] | x[i]);
 }
 
+// MPI_MAXLOC / MPI_MINLOC on {value, index} pairs: the extreme value wins, equal values keep the lower index
+template <typename V>
+void combine_loc(void* acc_, const void* x_, size_t n, bool want_max) {
+  struct P { V v; int i; };
+  P* a = static_cast<P*>(acc_);
+  const P* x = static_cast<const P*>(x_);
+  for (size_t k = 0; k < n; k++) {
+    const bool better = want_max ? x[k].v > a[k].v : x[k].v < a[k].v;
+    if (better || (x[k].v == a[k].v && x[k].i < a[k].i)) a[k] = x[k];
+  }
+}
+
+std::vector<MPI_User_function*> g_user_ops;   // MPI_Op handle - kFirstUserOp
+constexpr int kFirstUserOp = 100;
+constexpr int kFirstDerivedType = 1000;       // mpi_comm.cc: handles of MPI_Type_contiguous types (reduced through their base type)
+
+// Is (type, op) something reduce_into can do? Checked by every rank BEFORE a reduction starts to move data, so an invalid
+// combination fails on all ranks alike (not only on those whose slice happens to be non-empty).
+bool op_supported(MPI_Datatype t, MPI_Op op) {
+  if (op >= kFirstUserOp) return (size_t)(op - kFirstUserOp) < g_user_ops.size() && g_user_ops[(size_t)(op - kFirstUserOp)] != nullptr;
+  const bool pair = t == MPI_FLOAT_INT || t == MPI_DOUBLE_INT || t == MPI_LONG_INT || t == MPI_2INT;
+  if (op == MPI_MAXLOC || op == MPI_MINLOC) return pair;
+  if (pair || op < MPI_SUM || op > MPI_BOR || !type_size(t) || t >= kFirstDerivedType) return false;
+  if ((op == MPI_BAND || op == MPI_BOR) && (t == MPI_FLOAT || t == MPI_DOUBLE)) return false;
+  return true;
+}
+
 bool reduce_into(void* acc, const void* x, size_t n, MPI_Datatype t, MPI_Op op) {
+  if (op >= kFirstUserOp) {
+    const size_t k = (size_t)(op - kFirstUserOp);
+    if (k >= g_user_ops.size() || !g_user_ops[k]) return false;
+    // acc holds the lower ranks, x the next rank: result = acc (op) x = fn(in = acc, inout = copy of x)
+    const size_t bytes = n * type_size(t);
+    std::vector<unsigned char> tmp((const unsigned char*)x, (const unsigned char*)x + bytes);
+    for (size_t done = 0; done < n;) {   // `len` is an int
+      const size_t part = std::min(n - done, (size_t)1 << 30);
+      int len = (int)part;
+      MPI_Datatype dt = t;
+      g_user_ops[k]((unsigned char*)acc + done * type_size(t), tmp.data() + done * type_size(t), &len, &dt);
+      done += part;
+    }
+    memcpy(acc, tmp.data(), bytes);
+    return true;
+  }
+  if (op == MPI_MAXLOC || op == MPI_MINLOC) {
+    const bool mx = op == MPI_MAXLOC;
+    switch (t) {
+      case MPI_FLOAT_INT: combine_loc<float>(acc, x, n, mx); return true;
+      case MPI_DOUBLE_INT: combine_loc<double>(acc, x, n, mx); return true;
+      case MPI_LONG_INT: combine_loc<long>(acc, x, n, mx); return true;
+      case MPI_2INT: combine_loc<int>(acc, x, n, mx); return true;
+      default: return false;
+    }
+  }
 #define CASE(MT, CT) case MT: if (op == MPI_BAND || op == MPI_BOR) combine_bits((CT*)acc, (const CT*)x, n, op); else combine((CT*)acc, (const CT*)x, n, op); return true;
 #define CASEF(MT, CT) case MT: if (op == MPI_BAND || op == MPI_BOR) return false; combine((CT*)acc, (const CT*)x, n, op); return true;
   switch (t) {
@@ -224,6 +279,20 @@ int MPI_Get_library_version(char* v, int* len) {
   *len = snprintf(v, 256, "b200mpi libmpi shim 0.1.0 (shm rendezvous transport)");
   return MPI_SUCCESS;
 }
+int MPI_Op_create(MPI_User_function* fn, int, MPI_Op* op) {
+  if (!fn) return MPI_ERR_ARG;
+  for (size_t k = 0; k < g_user_ops.size(); k++)
+    if (!g_user_ops[k]) { g_user_ops[k] = fn; *op = kFirstUserOp + (int)k; return MPI_SUCCESS; }
+  g_user_ops.push_back(fn);
+  *op = kFirstUserOp + (int)g_user_ops.size() - 1;
+  return MPI_SUCCESS;
+}
+int MPI_Op_free(MPI_Op* op) {
+  const int k = *op - kFirstUserOp;
+  if (k >= 0 && k < (int)g_user_ops.size()) g_user_ops[(size_t)k] = nullptr;
+  *op = MPI_OP_NULL;
+  return MPI_SUCCESS;
+}
 int MPI_Type_size(MPI_Datatype t, int* s) { *s = (int)type_size(t); return *s ? MPI_SUCCESS : MPI_ERR_TYPE; }
 int MPI_Error_string(int code, char* s, int* len) { *len = snprintf(s, MPI_MAX_ERROR_STRING, "MPI error %d", code); return MPI_SUCCESS; }
 double MPI_Wtime(void) { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + ts.tv_nsec * 1e-9; }
@@ -302,12 +371,15 @@ static int reduce_any(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, 
   if (C->size() == 1) {
     const size_t es = type_size(t);
     if (!es) return MPI_ERR_TYPE;
+    MPI_Datatype b1; size_t c1;
+    if (flatten_type(t, (size_t)n, &b1, &c1) && !op_supported(b1, op)) return MPI_ERR_OP;
     if (s != MPI_IN_PLACE) memmove(r, s, es * (size_t)n);
     return MPI_SUCCESS;
   }
-  if (!C->world_like) return gen_reduce(C, s, r, (size_t)n, t, op, root, all);
   MPI_Datatype base; size_t cnt;
   if (!flatten_type(t, (size_t)n, &base, &cnt)) return MPI_ERR_TYPE;
+  if (!op_supported(base, op)) return MPI_ERR_OP;
+  if (!C->world_like) return gen_reduce(C, s, r, (size_t)n, t, op, root, all);
   return reduce_impl(s, r, (int)cnt, base, op, root, all);
 }
 int MPI_Reduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op op, int root, MPI_Comm c) { return reduce_any(s, r, n, t, op, root, c, false); }

@@ -356,6 +356,48 @@ int main(int argc, char** argv) {
     EXPECT(std::string(nm) == "MPI_COMM_WORLD");
   }
 
+  // 11. MPI_MAXLOC / MPI_MINLOC on value-index pairs, user-defined (non-commutative) reductions in rank order
+  {
+    struct DI { double v; int i; } mine_di[2] = {{(double)((r * 7) % 5), r}, {-1.0 * r, r}}, best[2];
+    EXPECT(MPI_Allreduce(mine_di, best, 2, MPI_DOUBLE_INT, MPI_MAXLOC, MPI_COMM_WORLD) == MPI_SUCCESS);
+    double top = -1; int who = -1;
+    for (int k = 0; k < n; k++) if ((k * 7) % 5 > top) { top = (k * 7) % 5; who = k; }       // ties keep the lower rank
+    EXPECT(best[0].v == top && best[0].i == who && best[1].v == 0.0 && best[1].i == 0);
+    struct II { int v; int i; } mi = {100 - r, r}, lo;
+    EXPECT(MPI_Reduce(&mi, &lo, 1, MPI_2INT, MPI_MINLOC, 0, MPI_COMM_WORLD) == MPI_SUCCESS);
+    if (r == 0) EXPECT(lo.v == 100 - (n - 1) && lo.i == n - 1);
+    int sz = 0;
+    MPI_Type_size(MPI_DOUBLE_INT, &sz);
+    EXPECT(sz == (int)sizeof(DI));
+    MPI_Op horner;
+    EXPECT(MPI_Op_create([](void* in, void* inout, int* len, MPI_Datatype*) {
+      long long* a = (long long*)in; long long* b = (long long*)inout;
+      for (int k = 0; k < *len; k++) b[k] = a[k] * 3 + b[k];                                    // NOT commutative: order matters
+    }, 0, &horner) == MPI_SUCCESS);
+    std::vector<long long> x(1000), y(1000, -1);
+    for (int k = 0; k < 1000; k++) x[k] = r + 1 + k;
+    EXPECT(MPI_Allreduce(x.data(), y.data(), 1000, MPI_LONG_LONG, horner, MPI_COMM_WORLD) == MPI_SUCCESS);
+    for (int k = 0; k < 1000; k += 111) {
+      long long want = 1 + k;
+      for (int q = 1; q < n; q++) want = want * 3 + (q + 1 + k);
+      EXPECT(y[k] == want);
+    }
+    MPI_Comm odd_even;
+    MPI_Comm_split(MPI_COMM_WORLD, r % 2, r, &odd_even);
+    long long one = r + 1, folded = -1, want = -1;
+    EXPECT(MPI_Allreduce(&one, &folded, 1, MPI_LONG_LONG, horner, odd_even) == MPI_SUCCESS);    // point-to-point based path
+    for (int q = r % 2; q < n; q += 2) want = want < 0 ? q + 1 : want * 3 + (q + 1);
+    EXPECT(folded == want);
+    long long pre = -1;
+    EXPECT(MPI_Scan(&one, &pre, 1, MPI_LONG_LONG, horner, MPI_COMM_WORLD) == MPI_SUCCESS);
+    want = 1;
+    for (int q = 1; q <= r; q++) want = want * 3 + (q + 1);
+    EXPECT(pre == want);
+    MPI_Comm_free(&odd_even);
+    MPI_Op_free(&horner);
+    EXPECT(horner == MPI_OP_NULL && MPI_Allreduce(&one, &folded, 1, MPI_LONG_LONG, 100, MPI_COMM_WORLD) != MPI_SUCCESS);
+  }
+
   int any = 0;
   MPI_Allreduce(&g_bad, &any, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
   if (r == 0) printf(any ? "mpi_p2p_test: FAILED\n" : "mpi_p2p_test: all checks passed on %d ranks\n", n);
