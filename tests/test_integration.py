@@ -561,16 +561,17 @@ def test_daemon_restart_reaps_lost_processes_and_recovers(tmp_path):
         o2.stop()
 
 
-def test_pod_logs_are_followed_incrementally_and_rotated(op, monkeypatch):
+def test_pod_logs_are_followed_incrementally_and_rotated(op, monkeypatch, tmp_path):
     """`logs -f` polls with an offset (log_slice) instead of re-reading the file; a running pod's log that outgrows
     B200MPI_POD_LOG_MAX_BYTES is copied to 0.log.1 and truncated in place (kubelet's containerLogMaxSize), the container keeps
     writing and a follower starts over at the new beginning."""
+    stop = tmp_path / "stop"
     job = new_mpijob("chatty", workers=1, launcher_cmd=("sh", "-c"), worker_cmd=("/usr/sbin/sshd", "-De"),
-                     launcher_args=("i=0; while [ $i -lt 400 ]; do echo line-$i-xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx; i=$((i+1)); sleep 0.005; done",))
+                     launcher_args=(f"i=0; while [ ! -f {stop} ]; do echo line-$i-xxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxxx; i=$((i+1)); sleep 0.005; done; echo last-line",))
     op.clientset.kubeflow_v2beta1().mpijobs("default").create(job)
     wait_for(lambda: any("launcher" in p["metadata"]["name"] for p in op.store.list("pods", "default")), 10)
     launcher = next(p for p in op.store.list("pods", "default") if "launcher" in p["metadata"]["name"])["metadata"]["name"]
-    wait_for(lambda: len(op.agent.logs("default", launcher)) > 2000, 10)
+    wait_for(lambda: len(op.agent.logs("default", launcher)) > 2000, 20)
     first, off = op.agent.log_slice("default", launcher, 0)
     assert first.startswith(b"line-0-") and off == len(first)
     again, off2 = op.agent.log_slice("default", launcher, off)
@@ -578,14 +579,14 @@ def test_pod_logs_are_followed_incrementally_and_rotated(op, monkeypatch):
     monkeypatch.setenv("B200MPI_POD_LOG_MAX_BYTES", "1500")
     assert op.agent.rotate_logs() == 1
     log_path = os.path.join(op.agent.state_dir, "pods", "default", launcher, "logs", "0.log")
-    assert os.path.getsize(log_path + ".1") > 1500 and os.path.getsize(log_path) < 1500
+    assert os.path.getsize(log_path + ".1") > 1500
     rotated, off3 = op.agent.log_slice("default", launcher, off2)                # offset beyond the new size: starts over
-    assert off3 <= os.path.getsize(log_path) + 4096 and (rotated == b"" or rotated.startswith(b"line-"))
+    assert rotated == b"" or rotated.startswith(b"line-")
     monkeypatch.setenv("B200MPI_POD_LOG_MAX_BYTES", "0")
-    wait_for(lambda: get(op, job).status and any(c.type == "Succeeded" and c.status == "True" for c in get(op, job).status.conditions or []), 30)
-    tail = op.agent.logs("default", launcher) if any(p["metadata"]["name"] == launcher for p in op.store.list("pods", "default")) else ""
-    old = open(log_path + ".1").read() if os.path.exists(log_path + ".1") else ""
-    assert "line-0-" in old and ("line-399-" in tail or tail == "")              # the container kept writing after the truncation
+    wait_for(lambda: os.path.getsize(log_path) > 200, 20)                        # the container kept writing after the truncation
+    stop.write_text("x")
+    wait_for(lambda: "last-line" in open(log_path).read(), 20)
+    assert "line-0-" in open(log_path + ".1").read() and "line-0-" not in open(log_path).read()
 
 
 def test_gpu_cordon_health_monitor_and_scheduling(op):
