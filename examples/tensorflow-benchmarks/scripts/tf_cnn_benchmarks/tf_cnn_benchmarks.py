@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--device", default="gpu", choices=["gpu", "cpu"], help="cpu: host tensors through the Horovod-API engine (no CUDA needed)")
     ap.add_argument("--image_size", type=int, default=224)
     ap.add_argument("--num_gpus", type=int, default=1)
+    ap.add_argument("--eval", default="False", help="tf_cnn_benchmarks flag: evaluate (forward only) instead of training; restores --train_dir")
     ap.add_argument("--train_dir", default="", help="checkpoint directory (tf_cnn_benchmarks flag): restored from at start if it holds a "
                                                     "checkpoint, written by rank 0 at the end")
     ap.add_argument("--b200_engine", default=os.environ.get("B200MPI_ENGINE", "fused"), choices=["fused", "hvd", "nccl"],
@@ -58,8 +59,9 @@ def main():
     on_gpu = args.device == "gpu"
     if on_gpu and not torch.cuda.is_available():
         raise SystemExit("tf_cnn_benchmarks (b200): --device=gpu but no CUDA device is visible (use --device=cpu for a host run)")
-    if not on_gpu:
-        args.b200_engine, args.b200_compute_dtype = "hvd", "fp32"
+    evaluating = str(args.eval).lower() == "true"
+    if not on_gpu:   # host run: the Horovod-API engine, except for --eval, which needs the trainer (then with the unfused optimizer)
+        args.b200_engine, args.b200_compute_dtype = ("fused" if evaluating else "hvd"), "fp32"
     S = args.image_size
     torch.backends.cudnn.benchmark = True
     torch.manual_seed(1234 + rank)
@@ -98,7 +100,8 @@ def main():
             import torch.distributed as dist
             dist.init_process_group("nccl", rank=rank, world_size=size, device_id=torch.device("cuda", torch.cuda.current_device()))
         trainer = DataParallelTrainer(model, loss_fn, hvd._comm(), lr=lr, momentum=mu, weight_decay=args.weight_decay,
-                                      autocast_dtype=dtype, comm_backend="nccl" if args.b200_engine == "nccl" else "b200mpi")
+                                      autocast_dtype=dtype, comm_backend="nccl" if args.b200_engine == "nccl" else "b200mpi",
+                                      fused_optimizer=on_gpu, cuda_graph=on_gpu)
 
         def step():
             return trainer.step(x, y)
@@ -125,8 +128,18 @@ def main():
     ckpt = os.path.join(args.train_dir, "model.ckpt.pt") if args.train_dir else ""
     if ckpt and os.path.exists(ckpt):
         sd = torch.load(ckpt, map_location="cpu", weights_only=False)
+        # either engine reads what the other wrote: a trainer checkpoint carries masters / momentum / buffers by name, the
+        # Horovod-API engine's a plain module state_dict + the optimizer's
         if args.b200_engine in ("fused", "nccl"):
-            trainer.load_state_dict(sd["trainer"])
+            if "trainer" in sd:
+                trainer.load_state_dict(sd["trainer"])
+            else:
+                names = {n for n, _ in model.named_parameters()}
+                trainer.load_state_dict({"format": "b200mpi.DataParallelTrainer/1", "momentum": {},
+                                         "model": {k: v for k, v in sd["model"].items() if k in names},
+                                         "buffers": {k: v for k, v in sd["model"].items() if k not in names}}, load_hyper=False)
+        elif "trainer" in sd:
+            model.load_state_dict({**sd["trainer"]["model"], **sd["trainer"]["buffers"]})
         else:
             model.load_state_dict(sd["model"])
             opt.load_state_dict(sd["optimizer"])
@@ -152,6 +165,27 @@ def main():
     def device_sync():
         if on_gpu:
             torch.cuda.synchronize()
+
+    if evaluating:
+        # forward-only pass over num_batches synthetic batches: tf_cnn_benchmarks' "Accuracy @ 1 = ... Accuracy @ 5 = ... [N examples]"
+        if args.b200_engine not in ("fused", "nccl"):
+            raise SystemExit("tf_cnn_benchmarks (b200): --eval needs the trainer engines (fused | nccl)")
+        tot = {"top1": 0.0, "top5": 0.0, "n": 0}
+        t_ev = time.perf_counter()
+        for _ in range(args.num_batches):
+            r = trainer.evaluate(x, y)
+            tot["top1"] += r.get("top1", 0.0)
+            tot["top5"] += r.get("top5", 0.0)
+            tot["n"] += r["examples"]
+        device_sync()
+        if rank == 0:
+            print(f"Accuracy @ 1 = {tot['top1'] / args.num_batches:.4f} Accuracy @ 5 = {tot['top5'] / args.num_batches:.4f} [{tot['n']} examples]")
+            print("----------------------------------------------------------------")
+            print(f"total images/sec: {tot['n'] / (time.perf_counter() - t_ev):.2f}")
+            print("----------------------------------------------------------------")
+            sys.stdout.flush()
+        hvd.shutdown()
+        return
 
     for _ in range(args.num_warmup_batches):
         loss = step()

@@ -488,6 +488,40 @@ class DataParallelTrainer:
         if self.comm.world > 1:
             self.comm.host_barrier()
 
+    # ---------------------------------------------------------- evaluation --
+    @torch.no_grad()
+    def evaluate(self, x, y, topk=(1, 5)):
+        """Forward only, in eval mode (BatchNorm uses its running statistics), under the trainer's autocast setting; no gradient,
+        no collective on the training path, the captured CUDA graph is left alone. Returns ``{"loss": ..., "top1": ..., "top5": ...,
+        "examples": n}`` averaged over the ranks (tf_cnn_benchmarks' ``--eval``: "Accuracy @ 1 / @ 5")."""
+        was_training = self.model.training
+        self.model.eval()
+        try:
+            x = x.to(self.device, non_blocking=True)
+            y = y.to(self.device, non_blocking=True)
+            if self.channels_last and x.dim() == 4:
+                x = x.contiguous(memory_format=torch.channels_last)
+            if self.autocast_dtype is not None:
+                with torch.autocast(self.device.type, dtype=self.autocast_dtype):
+                    out = self.model(x)
+                    loss = self.loss_fn(out, y)
+            else:
+                out = self.model(x)
+                loss = self.loss_fn(out, y)
+            ks = [k for k in topk if k <= out.shape[1]]
+            top = out.float().topk(max(ks), dim=1).indices if ks else None
+            stats = [loss.float().reshape(())] + [(top[:, :k] == y[:, None]).any(1).float().mean() for k in ks]
+            vec = torch.stack(stats).contiguous()
+            if self.comm.world > 1:
+                self.comm.allreduce(vec, op="avg")
+            vals = vec.tolist()
+            res = {"loss": vals[0], "examples": int(y.shape[0]) * self.comm.world}
+            for k, v in zip(ks, vals[1:]):
+                res[f"top{k}"] = v
+            return res
+        finally:
+            self.model.train(was_training)
+
     # ------------------------------------------------- checkpoint / resume --
     def state_dict(self) -> dict:
         """World-size independent checkpoint of the training state (the reference's examples checkpoint on

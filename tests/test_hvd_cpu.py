@@ -206,3 +206,9 @@ def test_tf_cnn_benchmarks_train_dir_checkpoints_and_resumes(tmp_path):
     second = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
     assert second.returncode == 0 and "Restored checkpoint" in second.stdout and "written after 4 batches on 2 ranks" in second.stdout, \
         second.stdout[-1500:] + second.stderr[-2000:]
+    # --eval=True: forward only through DataParallelTrainer.evaluate, restoring the checkpoint the OTHER engine wrote
+    third = subprocess.run(cmd + ["--eval=True"], capture_output=True, text=True, timeout=240, env=env, cwd="/tmp")
+    assert third.returncode == 0 and "Restored checkpoint" in third.stdout and "Saved checkpoint" not in third.stdout, third.stdout[-1500:] + third.stderr[-2000:]
+    import re
+    m = re.search(r"Accuracy @ 1 = ([0-9.]+) Accuracy @ 5 = ([0-9.]+) \[(\d+) examples\]", third.stdout)
+    assert m and 0.0 <= float(m.group(1)) <= float(m.group(2)) <= 1.0 and int(m.group(3)) == 3 * 4 * 2

@@ -450,3 +450,25 @@ def test_model_zoo_names_of_tf_cnn_benchmarks_build_and_train_one_step():
     with pytest.raises(KeyError) as e:
         build_model("not-a-model")
     assert "resnet101" in str(e.value)
+
+
+def test_evaluate_is_forward_only_and_uses_running_statistics():
+    tr = DataParallelTrainer(small_cnn(), nn.CrossEntropyLoss(), FakeComm(), lr=0.05, momentum=0.9, autocast_dtype=None,
+                             channels_last=False, cuda_graph=False, bucket_bytes=2048)
+    data = batches(3, seed=9)
+    for x, y in data:
+        tr.step(x, y)
+    before = [m.clone() for m in tr.state.master_state().values()]
+    bufs = [b.clone() for b in tr.model.buffers()]
+    launches = tr.comm.launch_count
+    x, y = data[0]
+    r1 = tr.evaluate(x, y)
+    r2 = tr.evaluate(x, y)
+    assert r1 == r2 and set(r1) == {"loss", "top1", "top5", "examples"} and r1["examples"] == 4 and 0.0 <= r1["top1"] <= r1["top5"] <= 1.0
+    assert tr.model.training and tr.comm.launch_count == launches                      # back in training mode, no collective
+    assert all(torch.equal(a, b) for a, b in zip(before, tr.state.master_state().values()))
+    assert all(torch.equal(a, b) for a, b in zip(bufs, tr.model.buffers()))             # running statistics untouched
+    ref = copy.deepcopy(tr.model).eval()
+    with torch.no_grad():
+        want = float(nn.CrossEntropyLoss()(ref(x), y))
+    assert r1["loss"] == pytest.approx(want, rel=1e-6)
