@@ -24,6 +24,25 @@ def parse_rfc3339(s: str) -> float:
     return _dt.datetime.strptime(s, "%Y-%m-%dT%H:%M:%SZ").replace(tzinfo=_dt.timezone.utc).timestamp()
 
 
+import re as _re
+
+_DNS1123_SUBDOMAIN = _re.compile(r"^[a-z0-9]([-a-z0-9]*[a-z0-9])?(\.[a-z0-9]([-a-z0-9]*[a-z0-9])?)*$")
+
+
+def name_problem(name: str, what: str = "metadata.name") -> Optional[str]:
+    """The apiserver's generic object-name rule (apimachinery validation.IsDNS1123Subdomain): lower-case alphanumerics, '-' and
+    '.', alphanumeric at both ends of every label, at most 253 characters. Here it is also what keeps object names - which become
+    directory names under the node agent's state dir - from containing '/' or '..'. None when the name is fine."""
+    if not isinstance(name, str) or not name:
+        return f"{what}: Required value"
+    if len(name) > 253:
+        return f"{what}: Invalid value: must be no more than 253 characters"
+    if not _DNS1123_SUBDOMAIN.match(name):
+        return (f"{what}: Invalid value: \"{name}\": a lowercase RFC 1123 subdomain must consist of lower case alphanumeric "
+                "characters, '-' or '.', and must start and end with an alphanumeric character")
+    return None
+
+
 def new_uid() -> str:
     return str(uuid.uuid4())
 

@@ -114,6 +114,9 @@ class ObjectStore:
             ns = md.get("namespace", "") if namespaced else ""
             if namespaced and not ns:
                 ns = md["namespace"] = "default"
+            problem = M.name_problem(md["name"]) or (M.name_problem(ns, "metadata.namespace") if namespaced else None)
+            if problem:
+                raise errors.invalid(resource, str(md["name"]), problem)
             key = self._key(ns, md["name"])
             if key in self._objs[resource]:
                 raise errors.already_exists(resource, md["name"])

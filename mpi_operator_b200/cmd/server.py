@@ -295,6 +295,8 @@ def _make_handler(op: Operator, restricted: bool = False):
                     continue
                 name = rest[1] if len(rest) > 1 else ""
                 sub = rest[2] if len(rest) > 2 else ""
+                if (name and M.name_problem(name)) or (ns and M.name_problem(ns)):
+                    return None       # not an object name (and never a path component of the state dir): 404
                 return res, ns, name, sub
             return None
 

@@ -281,3 +281,20 @@ def test_indexer_label_index_tracks_updates_and_deletes():
     got = ix.list("default", {"job": "j1"})[0]
     got["metadata"]["labels"]["job"] = "mutated"                                        # callers get copies
     assert names(ix.list("default", {"job": "j1"})) == ["b"]
+
+
+def test_object_names_follow_the_apiserver_rule_and_cannot_escape_directories():
+    """metadata.name / namespace: DNS-1123 subdomain (apimachinery IsDNS1123Subdomain). Pod names become directory names under the
+    node agent's state dir, so '/', '..' and friends must never get into the store."""
+    from mpi_operator_b200.api import meta as M
+    s = ObjectStore()
+    for bad in ("../../etc", "a/b", "..", "Upper", "under_score", "-lead", "trail-", "a..b", "", "x" * 254):
+        assert M.name_problem(bad) is not None, bad
+        with pytest.raises(ApiError) as e:
+            s.create("pods", {"metadata": {"name": bad, "namespace": "default"}, "spec": {}})
+        assert e.value.code == 422
+    with pytest.raises(ApiError):
+        s.create("pods", {"metadata": {"name": "ok", "namespace": "../up"}, "spec": {}})
+    for good in ("a", "1-llama", "foo-worker-0", "job.17ab3", "a.b.c", "x" * 253):
+        assert M.name_problem(good) is None, good
+        s.create("pods", {"metadata": {"name": good, "namespace": "default"}, "spec": {}})

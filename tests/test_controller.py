@@ -306,10 +306,13 @@ def test_owner_hop_pod_to_job_to_mpijob_enqueues():
     f = Fixture()
     job = f.create_job(new_mpijob("foo", workers=1))
     f.sync(job)
-    while len(f.ctrl.queue):
-        f.ctrl.queue.get(0.01)
-    f.launcher_pod(job, "Running")  # informer -> handle_object -> Job -> MPIJob
     import time
+    time.sleep(0.2)                  # let the informer deliver the events of the objects sync() created
+    while len(f.ctrl.queue):         # drain AND mark done: a key that is still "processing" would not be handed out again
+        k, _ = f.ctrl.queue.get(0.01)
+        if k is not None:
+            f.ctrl.queue.done(k)
+    f.launcher_pod(job, "Running")  # informer -> handle_object -> Job -> MPIJob
     deadline = time.time() + 2
     key = None
     while time.time() < deadline and key is None:

@@ -139,6 +139,18 @@ def test_monitoring_port_serves_metrics_and_healthz_only(tmp_path):
             assert e.value.code == 405
         # the full API is still there on the loopback listener
         assert json.load(urllib.request.urlopen(f"http://127.0.0.1:{port}/api/v1/namespaces/default/pods"))["items"] == []
+        # names in URLs are object names, never path components of the state dir
+        for path in ("/api/v1/namespaces/default/pods/..%2F..%2Fx/log", "/api/v1/namespaces/../pods/x/log", "/api/v1/namespaces/default/pods/../log",
+                     "/api/v1/namespaces/default/pods/UPPER"):
+            with pytest.raises(urllib.error.HTTPError) as e:
+                urllib.request.urlopen(f"http://127.0.0.1:{port}" + path)
+            assert e.value.code == 404, path
+        evil = dict(pod, metadata={"name": "../../evil"})
+        req = urllib.request.Request(f"http://127.0.0.1:{port}/api/v1/namespaces/default/pods", data=json.dumps(evil).encode(), method="POST",
+                                     headers={"Content-Type": "application/json"})
+        with pytest.raises(urllib.error.HTTPError) as e:
+            urllib.request.urlopen(req)
+        assert e.value.code == 422
     finally:
         op.stop()
 
