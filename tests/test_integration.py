@@ -380,10 +380,13 @@ def test_gpu_slots_gang_and_release(gang_op):
     pg = op.store.get("volcano-podgroups", "default", "a")
     assert pg["spec"]["minMember"] == 3 and pg["spec"]["minResources"] == {"nvidia.com/gpu": "4"}
     submit(op, b)
-    time.sleep(0.3)
-    bw = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-")]
+
+    def b_pods():
+        return [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-")]
+    wait_for(lambda: any(c.get("reason") == "Unschedulable" for p in b_pods() for c in (p.get("status") or {}).get("conditions", [])),
+             timeout=10, what="B's gang reported Unschedulable")
+    bw = b_pods()
     assert bw and all(p["status"]["phase"] == "Pending" for p in bw)  # whole gang pending, nothing partially started
-    assert any(c.get("reason") == "Unschedulable" for p in bw for c in p["status"].get("conditions", []))
     wait_for(lambda: conds(get(op, b)).get("Succeeded") == "True", timeout=30, what="B runs after A released its GPUs")
     launcher = [p for p in op.store.list("pods", "default") if p["metadata"]["name"].startswith("b-launcher")][0]
     assert '"b-worker-0": [' in op.agent.logs("default", launcher["metadata"]["name"])
@@ -404,7 +407,7 @@ def test_pending_gangs_are_admitted_in_priority_order(gang_op):
         if prio:
             j.spec.run_policy.scheduling_policy = SchedulingPolicy(priority_class=prio)
         return j
-    a = gang("a", "sleep 1.0")
+    a = gang("a", "sleep 2.0")     # holds every GPU long enough for BOTH waiting gangs to be registered, also on a loaded host
     submit(op, a)
     wait_for(lambda: conds(get(op, a)).get("Running") == "True", what="A running")
     low, high = gang("lo", "date +%s.%N", "low"), gang("hi", "date +%s.%N; sleep 0.3", "high")
