@@ -110,9 +110,12 @@ if timeline:
         ev = json.load(open(timeline))
         phases = {e.get("name") for e in ev}
         assert {"NEGOTIATE_ALLREDUCE", "ALLREDUCE", "MEMCPY_IN_FUSION_BUFFER", "SHM_ALLREDUCE", "MEMCPY_OUT_FUSION_BUFFER"} <= phases, phases
-        procs = {e["args"]["name"] for e in ev if e.get("name") == "process_name"}
-        assert "layer3.weight" in procs and len(procs) == 30, (len(procs), sorted(procs))
-        for pid in {e["pid"] for e in ev}:          # every B has its E
+        rows = {e["pid"]: e["args"]["name"] for e in ev if e.get("name") == "process_name"}
+        # ranks that are already past this point may have submitted their next tensors (grp.*) before rank 0 stopped the
+        # timeline: only the 30 layer rows of the loop above are complete by construction
+        layers = {pid for pid, name in rows.items() if name.startswith("layer")}
+        assert "layer3.weight" in rows.values() and len(layers) == 30, (len(layers), sorted(rows.values()))
+        for pid in layers:                          # every B has its E
             depth = 0
             for e in (x for x in ev if x["pid"] == pid):
                 depth += {"B": 1, "E": -1}.get(e["ph"], 0)
