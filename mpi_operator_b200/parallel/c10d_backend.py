@@ -58,10 +58,22 @@ def _host_world(rank: int, world: int):
         os.environ.setdefault("B200MPI_RANK", str(rank))
         os.environ.setdefault("B200MPI_WORLD_SIZE", str(world))
         _world_host = HostCommunicator()
+        import atexit
+        atexit.register(_finalize_host)   # MPI_Finalize: rank 0 unlinks the job's rendezvous segment (no launcher of ours may be around to do it)
         if (_world_host.rank, _world_host.world) != (rank, world):
             raise RuntimeError(f"b200mpi backend: the MPI shim sees rank {_world_host.rank}/{_world_host.world}, "
                                f"torch.distributed {rank}/{world}")
     return _world_host
+
+
+def _finalize_host() -> None:
+    global _world_host
+    c, _world_host = _world_host, None
+    if c is not None:
+        try:
+            c.destroy()
+        except Exception:  # noqa: BLE001
+            pass
 
 
 class B200ProcessGroup(dist.ProcessGroup):
