@@ -66,6 +66,18 @@ def _host_world(rank: int, world: int):
     return _world_host
 
 
+_dev_comms: list = []
+
+
+def _finalize_dev() -> None:
+    while _dev_comms:
+        c = _dev_comms.pop()
+        try:
+            c.destroy()
+        except Exception:  # noqa: BLE001
+            pass
+
+
 def _finalize_host() -> None:
     global _world_host
     c, _world_host = _world_host, None
@@ -112,6 +124,10 @@ class B200ProcessGroup(dist.ProcessGroup):
                 dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
                 name = job_id_from_env(os.environ) + ("-c10d" if self._granks is None else f"-c10d-{digest:08x}")
                 self._dev = Communicator.create(self._rank, self._world, dev, name)
+                _dev_comms.append(self._dev)
+                if len(_dev_comms) == 1:
+                    import atexit
+                    atexit.register(_finalize_dev)    # rank 0 unlinks the rendezvous segments
             return self._dev
         if self._host is None:
             world = _host_world(self._grank, self._gworld)
@@ -268,6 +284,8 @@ class B200ProcessGroup(dist.ProcessGroup):
         return _done(None)
 
     def shutdown(self):
+        if self._dev in _dev_comms:
+            _dev_comms.remove(self._dev)
         for c in (self._dev, self._host if self._host is not _world_host else None):   # MPI itself ends with the process
             if c is not None:
                 try:
