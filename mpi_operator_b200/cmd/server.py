@@ -137,6 +137,7 @@ class Operator:
 
     def __init__(self, opt: Optional[ServerOption] = None, store: Optional[ObjectStore] = None, clock=None):
         self.opt = opt or ServerOption()
+        self._ephemeral_state = not self.opt.state_dir      # no --state-dir: a throw-away directory, removed again by stop()
         self.state_dir = self.opt.state_dir or os.path.join(os.environ.get("TMPDIR", "/tmp"), f"b200mpi-operator-{os.getpid()}")
         os.makedirs(self.state_dir, exist_ok=True)
         self.auth_token = _load_or_create_token(self.opt.auth_token_file) if self.opt.auth_token_file else ""
@@ -196,6 +197,9 @@ class Operator:
         self.informers.stop()
         self.elector.release()
         self.store.close()
+        if self._ephemeral_state and os.environ.get("B200MPI_KEEP_STATE") != "1":
+            import shutil
+            shutil.rmtree(self.state_dir, ignore_errors=True)
 
     # ------------------------------------------------------------- serving --
     def serve(self, listen: str, block: bool = False, restricted: bool = False):
