@@ -68,6 +68,8 @@ class HostCommunicator:
         L.MPI_Allgather.argtypes = [vp, i, i, vp, i, i, i]
         L.MPI_Alltoall.argtypes = [vp, i, i, vp, i, i, i]
         L.MPI_Barrier.argtypes = [i]
+        L.MPI_Send.argtypes = [vp, i, i, i, i, i]
+        L.MPI_Recv.argtypes = [vp, i, i, i, i, i, vp]
         self._L = L
         flag = i(0)
         L.MPI_Initialized(C.byref(flag))
@@ -162,6 +164,26 @@ class HostCommunicator:
     def barrier(self, stream=None) -> None:
         self.launch_count += 1
         self._check(self._L.MPI_Barrier(self._comm_h), "MPI_Barrier")
+
+    # ------------------------------------------------------ point-to-point --
+    _P2P_PIECE = 1 << 30   # MPI counts are C ints: larger messages travel as 1 GiB pieces (same order on both sides)
+
+    def send(self, tensor, peer: int, tag: int = 0, stream=None) -> None:
+        """Blocking standard-mode send of the tensor's bytes (MPI_Send, csrc/mpi_shim/mpi_p2p.cc: eager, buffered at the receiver)."""
+        t = self._host(tensor, "send")
+        nbytes, base = t.numel() * t.element_size(), t.data_ptr()
+        self.launch_count += 1
+        for off in range(0, max(nbytes, 1), self._P2P_PIECE):
+            n = min(self._P2P_PIECE, nbytes - off)
+            self._check(self._L.MPI_Send(base + off if n else None, n, _BYTE, int(peer), int(tag), self._comm_h), "MPI_Send")
+
+    def recv(self, tensor, peer: int, tag: int = 0, stream=None) -> None:
+        t = self._host(tensor, "recv")
+        nbytes, base = t.numel() * t.element_size(), t.data_ptr()
+        self.launch_count += 1
+        for off in range(0, max(nbytes, 1), self._P2P_PIECE):
+            n = min(self._P2P_PIECE, nbytes - off)
+            self._check(self._L.MPI_Recv(base + off if n else None, n, _BYTE, int(peer), int(tag), self._comm_h, None), "MPI_Recv")
 
     host_barrier = barrier
 

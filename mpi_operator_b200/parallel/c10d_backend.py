@@ -15,7 +15,9 @@ communication library; with PyTorch that library is c10d.
 ``new_group(ranks)`` works as well: a sub-group gets communicators of its own on first use - on the host an MPI
 sub-communicator made by its members only (``MPI_Comm_create_group``, csrc/mpi_shim/mpi_comm.cc), on the device a separate
 runtime communicator whose rendezvous name is derived from the member list.
-Reductions: SUM, AVG, MIN, MAX natively, PRODUCT through one allgather.
+Reductions: SUM, AVG, MIN, MAX natively, PRODUCT through one allgather. Rooted operations (``gather``, ``scatter``, ``reduce``) ride
+the unrooted kernels; ``send`` / ``recv`` / ``batch_isend_irecv`` and the uneven list form of ``all_to_all`` use the libmpi shim's
+tagged mailboxes (CUDA tensors: the runtime's point-to-point kernel when the communicator has it, staged through the host otherwise).
 """
 from __future__ import annotations
 
@@ -24,8 +26,8 @@ from typing import List, Optional
 
 import torch
 import torch.distributed as dist
-from torch._C._distributed_c10d import (AllgatherOptions, AllreduceOptions, AllToAllOptions, BarrierOptions, BroadcastOptions, ReduceOp,
-                                        ReduceOptions, ReduceScatterOptions, _create_work_from_future)
+from torch._C._distributed_c10d import (AllgatherOptions, AllreduceOptions, AllToAllOptions, BarrierOptions, BroadcastOptions, GatherOptions,
+                                        ReduceOp, ReduceOptions, ReduceScatterOptions, ScatterOptions, _create_work_from_future)
 from torch.futures import Future
 
 BACKEND_NAME = "b200mpi"
@@ -44,6 +46,12 @@ def _done(result):
     fut: Future = Future()
     fut.set_result(result)
     return _create_work_from_future(fut)
+
+
+def _bcast_opts(root: int):
+    o = BroadcastOptions()
+    o.rootRank = root
+    return o
 
 
 _world_host = None   # the process-wide MPI_COMM_WORLD communicator of the libmpi shim (MPI_Init happens once per process)
@@ -272,6 +280,89 @@ class B200ProcessGroup(dist.ProcessGroup):
                 if dst is not out:
                     out.copy_(dst)
         return _done(output)
+
+    def alltoall(self, output_tensors: List[torch.Tensor], input_tensors: List[torch.Tensor], opts=AllToAllOptions()):
+        """List form (``dist.all_to_all``): one tensor per peer. Equal sizes ride the all-to-all kernel; uneven lists exchange
+        pairwise (rank r sends to r+k and receives from r-k in round k: every pair meets once, nobody waits in a cycle)."""
+        with torch.no_grad():
+            n = {t.numel() * t.element_size() for t in list(input_tensors) + list(output_tensors)}
+            if len(n) == 1 and len({t.dtype for t in input_tensors}) == 1:
+                src = torch.cat([self._contig(t.detach()).view(-1) for t in input_tensors])
+                dst = torch.empty_like(src)
+                self.alltoall_base(dst, src, None, None, opts)
+                per = src.numel() // self._world
+                for r, o in enumerate(output_tensors):
+                    o.detach().copy_(dst[r * per:(r + 1) * per].view_as(o))
+            else:
+                output_tensors[self._rank].detach().copy_(input_tensors[self._rank].detach())
+                for k in range(1, self._world):
+                    to, frm = (self._rank + k) % self._world, (self._rank - k) % self._world
+                    self._p2p(input_tensors[to], to, 0, True)       # eager send: buffered at the receiver, returns at once
+                    self._p2p(output_tensors[frm], frm, 0, False)
+        return _done(output_tensors)
+
+    def gather(self, output_lists: List[List[torch.Tensor]], input_tensors: List[torch.Tensor], opts=GatherOptions()):
+        # one allgather; only the root copies the blocks out (every rank passes a tensor of the same shape, the API's contract)
+        with torch.no_grad():
+            for k, inp in enumerate(input_tensors):
+                src = self._contig(inp.detach())
+                flat = torch.empty(self._world * src.numel(), dtype=src.dtype, device=src.device)
+                self._allgather_base(flat, src)
+                if self._rank == opts.rootRank:
+                    for r, o in enumerate(output_lists[k]):
+                        o.detach().copy_(flat[r * src.numel():(r + 1) * src.numel()].view_as(o))
+        return _done(output_lists)
+
+    def scatter(self, output_tensors: List[torch.Tensor], input_lists: List[List[torch.Tensor]], opts=ScatterOptions()):
+        # the root's list travels as one broadcast; every rank keeps its own block
+        with torch.no_grad():
+            for k, out in enumerate(output_tensors):
+                o = out.detach()
+                flat = torch.empty(self._world * o.numel(), dtype=o.dtype, device=o.device)
+                if self._rank == opts.rootRank:
+                    flat.copy_(torch.cat([self._contig(t.detach()).view(-1) for t in input_lists[k]]))
+                self.broadcast([flat], _bcast_opts(opts.rootRank))
+                o.copy_(flat[self._rank * o.numel():(self._rank + 1) * o.numel()].view_as(o))
+        return _done(output_tensors)
+
+    def _p2p(self, t: torch.Tensor, peer: int, tag: int, is_send: bool) -> None:
+        """CUDA tensors use the runtime's point-to-point kernel when the communicator was created with it (B200MPI_P2P=1);
+        otherwise - and for CPU tensors - the bytes travel through the libmpi shim's mailboxes (tag matching, eager sends)."""
+        td = t.detach()
+        if td.is_cuda:
+            c = self._comm(td)
+            if getattr(c, "has_p2p", False) and td.is_contiguous():
+                (c.send if is_send else c.recv)(td, peer)
+                return
+            host = self._comm(torch.empty(0))
+            if is_send:
+                host.send(td.contiguous().cpu(), peer, tag)
+            else:
+                tmp = torch.empty(td.shape, dtype=td.dtype, device="cpu")
+                host.recv(tmp, peer, tag)
+                td.copy_(tmp)
+            return
+        host = self._comm(td)
+        if is_send:
+            host.send(self._contig(td), peer, tag)
+        elif td.is_contiguous():
+            host.recv(td, peer, tag)
+        else:
+            tmp = torch.empty(td.shape, dtype=td.dtype)
+            host.recv(tmp, peer, tag)
+            td.copy_(tmp)
+
+    def send(self, tensors: List[torch.Tensor], dst_rank: int, tag: int = 0):
+        with torch.no_grad():
+            for t in tensors:
+                self._p2p(t, dst_rank, tag, True)
+        return _done(None)
+
+    def recv(self, tensors: List[torch.Tensor], src_rank: int, tag: int = 0):
+        with torch.no_grad():
+            for t in tensors:
+                self._p2p(t, src_rank, tag, False)
+        return _done(None)
 
     def barrier(self, opts=BarrierOptions()):
         if self._world > 1:

@@ -61,6 +61,36 @@ def main():
     objs = [None] * world
     dist.all_gather_object(objs, {"rank": rank})
     fails += int([o["rank"] for o in objs] != list(range(world)))
+    # rooted and point-to-point operations
+    mine = torch.arange(4, dtype=torch.float32) + 10 * rank
+    got = [torch.empty(4) for _ in range(world)] if rank == world - 1 else None
+    dist.gather(mine, got, dst=world - 1)
+    if rank == world - 1:
+        fails += int([t.tolist() for t in got] != [[10.0 * r + k for k in range(4)] for r in range(world)])
+    part = torch.empty(3, dtype=torch.int64)
+    dist.scatter(part, [torch.full((3,), 7 * r, dtype=torch.int64) for r in range(world)] if rank == 0 else None, src=0)
+    fails += int(part.tolist() != [7 * rank] * 3)
+    outs = [torch.empty(2) for _ in range(world)]
+    dist.all_to_all(outs, [torch.full((2,), float(100 * rank + r)) for r in range(world)])
+    fails += int([t.tolist() for t in outs] != [[float(100 * r + rank)] * 2 for r in range(world)])
+    if world > 1:
+        outs = [torch.empty(r + 1) for r in range(world)]                # uneven: rank r sends (rank + 1) elements to everyone
+        dist.all_to_all(outs, [torch.full((rank + 1,), float(rank)) for _ in range(world)])
+        fails += int([t.tolist() for t in outs] != [[float(r)] * (r + 1) for r in range(world)])
+        nxt, prv = (rank + 1) % world, (rank - 1) % world
+        tok = torch.full((1000,), float(rank))
+        inc = torch.empty(1000)
+        if rank % 2 == 0:
+            dist.send(tok, nxt, tag=3)
+            dist.recv(inc, prv, tag=3)
+        else:
+            dist.recv(inc, prv, tag=3)
+            dist.send(tok, nxt, tag=3)
+        fails += int(not torch.equal(inc, torch.full((1000,), float(prv))))
+        reqs = dist.batch_isend_irecv([dist.P2POp(dist.isend, tok, nxt), dist.P2POp(dist.irecv, inc.zero_(), prv)])
+        for q in reqs:
+            q.wait()
+        fails += int(not torch.equal(inc, torch.full((1000,), float(prv))))
     dist.barrier()
     # DDP training: identical to a single-process run on the concatenated batch
     torch.manual_seed(0)
