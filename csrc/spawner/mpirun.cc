@@ -14,6 +14,7 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <poll.h>
+#include <sched.h>
 #include <signal.h>
 #include <string.h>
 #include <sys/syscall.h>
@@ -57,6 +58,117 @@ static void die(const std::string& m, int code = 1) {
 static std::string short_host(const std::string& fqdn) {
   size_t d = fqdn.find('.');
   return d == std::string::npos ? fqdn : fqdn.substr(0, d);
+}
+
+
+// ---- processor binding (Open MPI's --bind-to none|numa|socket|core|hwthread, --cpus-per-proc, --cpu-set, --report-bindings).
+// The default is none (every reference command line says `-bind-to none`). What "numa" means on this box: the rank runs on the
+// CPUs of the NUMA node its GPU hangs off (sysfs: /sys/bus/pci/devices/<bus id>/numa_node), so its pinned staging buffers are
+// first-touched in memory local to the GPU's PCIe root and the H2D copy does not cross the socket interconnect; without GPUs the
+// ranks are spread over the NUMA nodes in blocks. All paths can be re-rooted with B200MPI_SYSFS_ROOT (tests).
+enum BindPolicy { BIND_NONE = 0, BIND_NUMA, BIND_CORE };
+static std::string sysroot() { const char* r = getenv("B200MPI_SYSFS_ROOT"); return r ? r : ""; }
+static std::string read_first_line(const std::string& path) {
+  std::ifstream f(path);
+  std::string line;
+  if (f) std::getline(f, line);
+  return line;
+}
+static std::vector<int> parse_cpulist(const std::string& text) {   // "0-3,8,10-11"
+  std::vector<int> out;
+  std::istringstream is(text);
+  std::string tok;
+  while (std::getline(is, tok, ',')) {
+    if (tok.empty()) continue;
+    int a = 0, b = 0;
+    const int n = sscanf(tok.c_str(), "%d-%d", &a, &b);
+    if (n == 1) b = a;
+    if (n >= 1 && a >= 0 && b >= a && b < CPU_SETSIZE) for (int c = a; c <= b; c++) out.push_back(c);
+  }
+  return out;
+}
+static std::string format_cpulist(const std::vector<int>& cpus) {
+  std::string out;
+  for (size_t k = 0; k < cpus.size();) {
+    size_t e = k;
+    while (e + 1 < cpus.size() && cpus[e + 1] == cpus[e] + 1) e++;
+    out += (out.empty() ? "" : ",") + std::to_string(cpus[k]) + (e > k ? "-" + std::to_string(cpus[e]) : "");
+    k = e + 1;
+  }
+  return out;
+}
+static std::vector<int> allowed_cpus(const std::string& cpu_set) {
+  cpu_set_t m;
+  CPU_ZERO(&m);
+  std::vector<int> out;
+  if (sched_getaffinity(0, sizeof(m), &m) == 0) for (int c = 0; c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &m)) out.push_back(c);
+  if (!cpu_set.empty()) {
+    const std::vector<int> want = parse_cpulist(cpu_set);
+    std::vector<int> both;
+    for (int c : out) if (std::find(want.begin(), want.end(), c) != want.end()) both.push_back(c);
+    out = both;
+  }
+  return out;
+}
+// NUMA nodes with their CPUs (restricted to `allowed`); nodes without allowed CPUs are dropped
+static std::vector<std::pair<int, std::vector<int>>> numa_nodes(const std::vector<int>& allowed) {
+  std::vector<std::pair<int, std::vector<int>>> nodes;
+  const std::string dir = sysroot() + "/sys/devices/system/node";
+  if (DIR* d = opendir(dir.c_str())) {
+    while (dirent* e = readdir(d)) {
+      int id = -1;
+      if (sscanf(e->d_name, "node%d", &id) != 1 || id < 0) continue;
+      std::vector<int> cpus;
+      for (int c : parse_cpulist(read_first_line(dir + "/" + e->d_name + "/cpulist")))
+        if (std::find(allowed.begin(), allowed.end(), c) != allowed.end()) cpus.push_back(c);
+      if (!cpus.empty()) nodes.push_back({id, cpus});
+    }
+    closedir(d);
+  }
+  std::sort(nodes.begin(), nodes.end());
+  if (nodes.empty() && !allowed.empty()) nodes.push_back({0, allowed});
+  return nodes;
+}
+// NUMA node of GPU `index` (nvidia-smi / PCI bus order): the index-th entry of /proc/driver/nvidia/gpus sorted by bus id
+static int gpu_numa_node(int index) {
+  std::vector<std::string> bus;
+  const std::string dir = sysroot() + "/proc/driver/nvidia/gpus";
+  if (DIR* d = opendir(dir.c_str())) {
+    while (dirent* e = readdir(d)) if (e->d_name[0] != '.') bus.push_back(e->d_name);
+    closedir(d);
+  }
+  std::sort(bus.begin(), bus.end());
+  if (index < 0 || index >= (int)bus.size()) return -1;
+  std::string id = bus[index];
+  std::transform(id.begin(), id.end(), id.begin(), ::tolower);
+  const std::string v = read_first_line(sysroot() + "/sys/bus/pci/devices/" + id + "/numa_node");
+  return v.empty() ? -1 : atoi(v.c_str());
+}
+// CPUs of local rank `lrank` of `lsize` under `policy` (gpus[r] = GPU index of local rank r, or absent); empty = leave it unbound
+static std::vector<int> binding_for(BindPolicy policy, int lrank, int lsize, const std::vector<int>& gpus, int cpus_per_proc,
+                                    const std::string& cpu_set, int* numa_out) {
+  *numa_out = -1;
+  if (policy == BIND_NONE) return {};
+  const auto nodes = numa_nodes(allowed_cpus(cpu_set));
+  if (nodes.empty()) return {};
+  auto node_of = [&](int r) -> size_t {
+    const int gnode = r < (int)gpus.size() && gpus[r] >= 0 ? gpu_numa_node(gpus[r]) : -1;
+    for (size_t k = 0; k < nodes.size() && gnode >= 0; k++) if (nodes[k].first == gnode) return k;
+    return std::min((size_t)r * nodes.size() / (size_t)std::max(1, lsize), nodes.size() - 1);   // blocks of consecutive ranks per node
+  };
+  const size_t pick = node_of(lrank);
+  *numa_out = nodes[pick].first;
+  const std::vector<int>& cpus = nodes[pick].second;
+  if (policy == BIND_NUMA) return cpus;
+  // core: `cpus_per_proc` consecutive CPUs of the node; the ranks that share a node take consecutive chunks, wrapping when the
+  // node is oversubscribed
+  int before = 0;
+  for (int r = 0; r < lrank; r++) if (node_of(r) == pick) before++;
+  const int per = std::max(1, cpus_per_proc), chunks = std::max(1, (int)cpus.size() / per);
+  const int chunk = before % chunks;
+  std::vector<int> out;
+  for (int k = 0; k < per && chunk * per + k < (int)cpus.size(); k++) out.push_back(cpus[chunk * per + k]);
+  return out;
 }
 
 static std::vector<Host> read_hostfile(const std::string& path, int default_slots) {
@@ -184,8 +296,20 @@ static bool drain(int& fd, std::string& buf) {
 }
 
 int main(int argc, char** argv) {
-  int np = -1, ppn = -1, timeout_s = 0;
-  bool tag_output = false, oversubscribe = false;
+  int np = -1, ppn = -1, timeout_s = 0, cpus_per_proc = 1;
+  bool tag_output = false, oversubscribe = false, report_bindings = false, bind_explicit = false;
+  BindPolicy bind_policy = BIND_NONE;
+  bool pe_given = false;     // -map-by ...:PE=n implies core binding unless a -bind-to says otherwise (Open MPI)
+  std::string cpu_set;
+  auto set_bind = [&](std::string v) {
+    const size_t colon = v.find(':');           // "core:overload-allowed"
+    if (colon != std::string::npos) v = v.substr(0, colon);
+    if (v == "none" || v == "board") bind_policy = BIND_NONE;
+    else if (v == "numa" || v == "socket" || v == "package" || v == "l3cache" || v == "l2cache" || v == "l1cache") bind_policy = BIND_NUMA;
+    else if (v == "core" || v == "hwthread") bind_policy = BIND_CORE;
+    else die("unknown -bind-to policy " + v + " (none, numa, socket, core, hwthread)");
+  };
+  if (const char* b = getenv("B200MPI_BIND_TO")) if (*b) { set_bind(b); bind_explicit = true; }
   std::string hostfile, hostlist, wdir;
   std::vector<std::pair<std::string, std::string>> xenv;  // -x / -genv / -env
   std::vector<std::string> passthrough_unset;
@@ -199,6 +323,7 @@ int main(int argc, char** argv) {
              a == "-display-map" || a == "-display-allocation" || a == "-report-bindings" || a == "-keep-fqdn-hostnames" ||
              a == "-enable-recovery" || a == "-disable-recovery" || a == "-l") {
       if (a == "-oversubscribe") oversubscribe = true;
+      if (a == "-report-bindings") report_bindings = true;
       if (a == "-l") tag_output = true;
     }
     else if (a == "-use-hwthread-cpus" || a == "-verbose" || a == "-v" || a == "-d" || a == "-debug-devel" || a == "-debug-daemons" ||
@@ -213,13 +338,24 @@ int main(int argc, char** argv) {
     }
     else if (a == "-output-directory") { need(1); g_outdir = argv[++i]; }
     else if (a == "-tune" || a == "-am" || a == "-report-uri" || a == "-xterm" || a == "-max-restarts" || a == "-max-vm-size" ||
-             a == "-slot-list" || a == "-cpu-set" || a == "-rankfile" || a == "-rf" || a == "-ompi-server" || a == "-path") { need(1); ++i; }
+             a == "-slot-list" || a == "-rankfile" || a == "-rf" || a == "-ompi-server" || a == "-path") { need(1); ++i; }
     else if (a == "-tag-output" || a == "-prepend-rank") tag_output = true;
     else if (a == "-timestamp-output") g_timestamp = true;
     else if (a == "-output-filename" || a == "-outfile-pattern") { need(1); g_outdir = argv[++i]; }
-    else if (a == "-bind-to" || a == "-map-by" || a == "-rank-by" || a == "-prefix" || a == "-launcher" || a == "-launcher-exec" ||
-             a == "-bootstrap" || a == "-bootstrap-exec" || a == "-iface" || a == "-report-pid" ||
-             a == "-cpus-per-proc" || a == "-cpus-per-rank") { need(1); ++i; }
+    else if (a == "-bind-to") { need(1); set_bind(argv[++i]); bind_explicit = true; }
+    else if (a == "-bind-to-core") { bind_policy = BIND_CORE; bind_explicit = true; }
+    else if (a == "-bind-to-socket") { bind_policy = BIND_NUMA; bind_explicit = true; }
+    else if (a == "-bind-to-none") { bind_policy = BIND_NONE; bind_explicit = true; }
+    else if (a == "-cpus-per-proc" || a == "-cpus-per-rank") { need(1); cpus_per_proc = std::max(1, atoi(argv[++i])); }
+    else if (a == "-cpu-set") { need(1); cpu_set = argv[++i]; }
+    else if (a == "-map-by") {
+      need(1);
+      const std::string v = argv[++i];          // "slot", "numa:PE=4", "ppr:1:node" ... only the PE= modifier matters on one box
+      const size_t pe = v.find("PE=");
+      if (pe != std::string::npos) { cpus_per_proc = std::max(1, atoi(v.c_str() + pe + 3)); pe_given = true; }
+    }
+    else if (a == "-rank-by" || a == "-prefix" || a == "-launcher" || a == "-launcher-exec" ||
+             a == "-bootstrap" || a == "-bootstrap-exec" || a == "-iface" || a == "-report-pid") { need(1); ++i; }
     else if (a == "-mca" || a == "-gmca" || a == "-omca" || a == "-pmixmca" || a == "-prtemca") {
       need(2);
       std::string k = argv[i + 1], v = argv[i + 2];
@@ -263,7 +399,9 @@ int main(int argc, char** argv) {
              "  -oversubscribe                allow more ranks than slots\n"
              "  prog1 args : -np N prog2 ...  MPMD: several application contexts, ranks numbered context by context (MPI_APPNUM in\n"
              "                                OMPI_MCA_orte_app_num / PMI_APPNUM); a context may carry its own -np, -x, -env, -wdir\n"
-             "  -bind-to, -map-by, -rank-by, -bootstrap, -launcher, -iface ...   accepted and ignored (one box, no ssh)\n"
+             "  -bind-to none|numa|socket|core   processor binding (default none); numa = the CPUs next to the rank's GPU; with\n"
+             "                   -cpus-per-proc N / -map-by X:PE=N, -cpu-set LIST, -report-bindings (B200MPI_BIND_TO overrides the default)\n"
+             "  -map-by, -rank-by, -bootstrap, -launcher, -iface ...   accepted and ignored (one box, no ssh)\n"
              "  -V, -version / -h, -help\n\n"
              "Ranks get OMPI_COMM_WORLD_*, PMI_*, RANK/WORLD_SIZE/LOCAL_RANK/MASTER_ADDR/MASTER_PORT, HOROVOD_* and B200MPI_* variables;\n"
              "GPUs come from the operator's slot map (B200MPI_SLOTS_FILE). The first failing rank's exit code is propagated and the\n"
@@ -354,6 +492,7 @@ int main(int argc, char** argv) {
   int total_slots = 0;
   for (auto& h : hosts) total_slots += h.slots;
   if (np <= 0) np = total_slots;
+  if (pe_given && !bind_explicit) bind_policy = BIND_CORE;
   if (np > total_slots && !oversubscribe && getenv("B200MPI_STRICT_SLOTS"))
     die("not enough slots: requested " + std::to_string(np) + ", hostfile provides " + std::to_string(total_slots));
 
@@ -401,6 +540,22 @@ int main(int argc, char** argv) {
   if ((int)job_gpus.size() >= np) {
     for (int k = 0; k < np; k++) cvd += (k ? "," : "") + std::to_string(job_gpus[k]);
   }
+
+  // GPU of every rank as far as binding is concerned: the node agent's reservation, else the launcher's own CUDA_VISIBLE_DEVICES
+  // (numeric entries), else rank r -> GPU r (the LOCAL_RANK convention of every workload here)
+  auto binding_gpus = [&]() {
+    if (!cvd.empty()) return job_gpus;
+    std::vector<int> g;
+    const char* env = getenv("CUDA_VISIBLE_DEVICES");
+    if (env && *env) {
+      std::istringstream is(env);
+      std::string tok;
+      while (std::getline(is, tok, ',')) g.push_back(!tok.empty() && isdigit((unsigned char)tok[0]) ? atoi(tok.c_str()) : -1);
+    } else {
+      for (int r = 0; r < np; r++) g.push_back(r);
+    }
+    return g;
+  };
 
   // ---- rendezvous identity -------------------------------------------------------
   std::string job_id = getenv("B200MPI_JOB_ID") ? getenv("B200MPI_JOB_ID") : "mpirun";
@@ -499,6 +654,16 @@ int main(int argc, char** argv) {
           set("LD_PRELOAD", pre);
         }
       }
+      if (bind_policy != BIND_NONE) {
+        int numa = -1;
+        const std::vector<int> cpus = binding_for(bind_policy, rk.rank, np, binding_gpus(), cpus_per_proc, cpu_set, &numa);
+        if (!cpus.empty()) {
+          cpu_set_t m;
+          CPU_ZERO(&m);
+          for (int c : cpus) CPU_SET(c, &m);
+          if (sched_setaffinity(0, sizeof(m), &m) == 0) { set("B200MPI_BOUND_CPUS", format_cpulist(cpus)); seti("B200MPI_BOUND_NUMA", numa); }
+        }
+      }
       const size_t appnum = app_of(rk.rank);
       App& ap = apps[appnum];
       for (auto& kv : ap.env) set(kv.first.c_str(), kv.second);
@@ -515,6 +680,14 @@ int main(int argc, char** argv) {
       _exit(127);
     }
     setpgid(pid, pid);
+    if (report_bindings) {
+      int numa = -1;
+      const std::vector<int> cpus = binding_for(bind_policy, rk.rank, np, binding_gpus(), cpus_per_proc, cpu_set, &numa);
+      if (cpus.empty()) fprintf(stderr, "[%s:%d] MCW rank %d is not bound (or bound to all available processors)\n", short_host(rk.host).c_str(), (int)pid, rk.rank);
+      else fprintf(stderr, "[%s:%d] MCW rank %d bound to NUMA node %d: cpus %s%s\n", short_host(rk.host).c_str(), (int)pid, rk.rank, numa,
+                   format_cpulist(cpus).c_str(), (!cvd.empty() && rk.rank < (int)job_gpus.size()) ? (" (GPU " + std::to_string(job_gpus[rk.rank]) + ")").c_str() : "");
+      fflush(stderr);
+    }
     close(po[1]); close(pe[1]);
     fcntl(po[0], F_SETFL, O_NONBLOCK);
     fcntl(pe[0], F_SETFL, O_NONBLOCK);

@@ -115,6 +115,8 @@ class Communicator:
     # ------------------------------------------------------------ creation --
     @classmethod
     def create(cls, rank: int, world: int, device: int, job_id: str, staging_bytes: int = 0, flags: int = 0):
+        from . import affinity
+        affinity.maybe_bind(device)      # B200MPI_BIND_TO=numa: run next to the GPU before the staging buffers are first touched
         h = C.c_void_p()
         check(_lib.lib().b200mpi_comm_init(C.byref(h), rank, world, device, job_id.encode(), staging_bytes, flags),
               "comm_init")

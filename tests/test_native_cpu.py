@@ -103,6 +103,62 @@ def test_mpirun_gpu_pinning_from_slots_file(tmp_path):
     assert sorted(r.stdout.strip().splitlines()) == ["0 0 3,5 3", "1 1 3,5 5"]
 
 
+def _fake_sysfs(root, cpus_per_node, gpu_nodes):
+    """Two-socket style topology under `root` (B200MPI_SYSFS_ROOT): NUMA nodes with CPU lists, GPUs with their bus ids / numa_node."""
+    for n, cpus in enumerate(cpus_per_node):
+        d = root / "sys/devices/system/node" / f"node{n}"
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(cpus + "\n")
+    for k, node in enumerate(gpu_nodes):
+        bus = f"0000:{0x1b + 0x20 * k:02X}:00.0"
+        (root / "proc/driver/nvidia/gpus" / bus).mkdir(parents=True)
+        d = root / "sys/bus/pci/devices" / bus.lower()
+        d.mkdir(parents=True)
+        (d / "numa_node").write_text(f"{node}\n")
+
+
+@pytest.mark.skipif(len(os.sched_getaffinity(0)) < 4, reason="needs 4 schedulable CPUs")
+def test_mpirun_processor_binding_follows_the_gpus_numa_node(tmp_path):
+    """--bind-to none|numa|core, PE=, --cpu-set, --report-bindings (Open MPI's options; the reference's command lines pass
+    `-bind-to none`, tensorflow-benchmarks.yaml:23-24, which stays the default): numa = the CPUs next to the rank's GPU."""
+    cpus = sorted(os.sched_getaffinity(0))[:4]
+    lo, hi = f"{cpus[0]},{cpus[1]}", f"{cpus[2]},{cpus[3]}"
+    _fake_sysfs(tmp_path, [lo, hi], [0, 0, 1, 1])
+    show = "echo $RANK $(grep Cpus_allowed_list /proc/self/status | cut -f2) $B200MPI_BOUND_NUMA"
+    allc = open("/proc/self/status").read().split("Cpus_allowed_list:")[1].split()[0]
+    env = {"B200MPI_SYSFS_ROOT": str(tmp_path), "CUDA_VISIBLE_DEVICES": ""}
+
+    def ranks(*flags, np="4", extra=None):
+        r = run([MPIRUN, "-np", np, "--oversubscribe", *flags, "sh", "-c", show], env={**env, **(extra or {})})
+        return [ln.split()[1:] for ln in sorted(r.stdout.strip().splitlines())], r.stderr
+
+    def fmt(*c):   # the kernel's list format for the chosen CPUs
+        c = sorted(c)
+        return f"{c[0]}-{c[-1]}" if len(c) > 1 and c[-1] - c[0] == len(c) - 1 else ",".join(map(str, c))
+    got, err = ranks("-bind-to", "none", "--report-bindings")
+    assert got == [[allc]] * 4 and err.count("is not bound") == 4
+    got, err = ranks("--bind-to", "numa", "--report-bindings")
+    assert got == [[fmt(*cpus[:2]), "0"]] * 2 + [[fmt(*cpus[2:]), "1"]] * 2
+    assert err.count("bound to NUMA node 0") == 2 and err.count("bound to NUMA node 1") == 2
+    got, _ = ranks("--bind-to", "core")
+    assert [g[0] for g in got] == [str(c) for c in cpus]                        # one core each, next to the own GPU
+    got, _ = ranks("--map-by", "numa:PE=2", np="2", extra={"CUDA_VISIBLE_DEVICES": "2,0"})   # PE= implies core binding; GPU order from the environment
+    assert got == [[fmt(*cpus[2:]), "1"], [fmt(*cpus[:2]), "0"]]
+    got, _ = ranks("--map-by", "numa:PE=2", "--bind-to", "none", np="2")          # an explicit policy wins over PE=
+    assert got == [[allc]] * 2
+    got, _ = ranks("--bind-to", "socket", "--cpu-set", f"{cpus[1]},{cpus[3]}")
+    assert got == [[str(cpus[1]), "0"]] * 2 + [[str(cpus[3]), "1"]] * 2
+    got, _ = ranks(np="2", extra={"B200MPI_BIND_TO": "numa"})                     # operator-wide default through the environment
+    assert got == [[fmt(*cpus[:2]), "0"]] * 2
+    # no GPU information at all: ranks are spread over the NUMA nodes in blocks
+    bare = tmp_path / "bare"
+    _fake_sysfs(bare, [lo, hi], [])
+    r = run([MPIRUN, "-np", "4", "--oversubscribe", "--bind-to", "numa", "sh", "-c", show], env={**env, "B200MPI_SYSFS_ROOT": str(bare)})
+    assert [ln.split()[2] for ln in sorted(r.stdout.strip().splitlines())] == ["0", "0", "1", "1"]
+    r = subprocess.run([MPIRUN, "-np", "1", "--bind-to", "sideways", "true"], capture_output=True, text=True)
+    assert r.returncode != 0 and "unknown -bind-to policy" in r.stderr
+
+
 def test_mpirun_failure_propagation_kills_siblings_and_reports():
     r = run([MPIRUN, "-np", "3", "sh", "-c", "if [ $RANK = 1 ]; then echo dying >&2; exit 7; fi; sleep 30"], timeout=20)
     assert r.returncode == 7 and "dying" in r.stderr and "exited with non-zero status" in r.stderr

@@ -7,6 +7,7 @@ buckets, hook bookkeeping, the bf16 parameter shadow, ``no_sync`` accumulation â
 ``torch.optim.SGD`` without a device. GPU numerics of the kernels themselves: test_collectives_gpu.py,
 test_trainer_gpu.py."""
 import copy
+import os
 
 import pytest
 import torch
@@ -472,3 +473,42 @@ def test_evaluate_is_forward_only_and_uses_running_statistics():
     with torch.no_grad():
         want = float(nn.CrossEntropyLoss()(ref(x), y))
     assert r1["loss"] == pytest.approx(want, rel=1e-6)
+
+
+@pytest.mark.skipif(len(os.sched_getaffinity(0)) < 4, reason="needs 4 schedulable CPUs")
+def test_affinity_next_to_the_gpu_is_opt_in_and_reads_sysfs(tmp_path, monkeypatch):
+    """runtime/affinity.py: B200MPI_BIND_TO=numa binds a torchrun-started rank to the CPUs of its GPU's NUMA node (same placement
+    csrc/spawner/mpirun.cc gives with --bind-to numa); the default leaves the process alone."""
+    from mpi_operator_b200.runtime import affinity
+    before = os.sched_getaffinity(0)
+    cpus = sorted(before)[:4]
+    for n, part in enumerate((cpus[:2], cpus[2:])):
+        d = tmp_path / f"sys/devices/system/node/node{n}"
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(affinity.format_cpulist(part) + "\n")
+    for k, node in enumerate((0, 1, -1)):
+        bus = f"0000:{0x1b + 0x20 * k:02X}:00.0"
+        (tmp_path / "proc/driver/nvidia/gpus" / bus).mkdir(parents=True)
+        d = tmp_path / "sys/bus/pci/devices" / bus.lower()
+        d.mkdir(parents=True)
+        (d / "numa_node").write_text(f"{node}\n")
+    monkeypatch.setenv("B200MPI_SYSFS_ROOT", str(tmp_path))
+    monkeypatch.delenv("B200MPI_BOUND_CPUS", raising=False)
+    monkeypatch.delenv("B200MPI_BIND_TO", raising=False)
+    assert affinity.parse_cpulist("0-2,5,7-8") == [0, 1, 2, 5, 7, 8] and affinity.format_cpulist([8, 0, 1, 2, 5, 7]) == "0-2,5,7-8"
+    try:
+        assert affinity.maybe_bind(1) is None and os.sched_getaffinity(0) == before            # not asked: nothing happens
+        monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "1,0")
+        assert affinity.gpu_numa_node(0) == 1 and affinity.gpu_numa_node(1) == 0               # CUDA ordinals follow CUDA_VISIBLE_DEVICES
+        monkeypatch.setenv("CUDA_VISIBLE_DEVICES", "")
+        assert affinity.gpu_numa_node(2) is None and affinity.bind_near_gpu(2) is None         # the platform does not say: unbound
+        assert affinity.gpu_numa_node(7) is None                                               # no such GPU
+        monkeypatch.setenv("B200MPI_BIND_TO", "numa")
+        info = affinity.maybe_bind(1)
+        assert info == {"numa": 1, "cpus": affinity.format_cpulist(cpus[2:])} and os.sched_getaffinity(0) == set(cpus[2:])
+        assert os.environ["B200MPI_BOUND_NUMA"] == "1"
+        assert affinity.maybe_bind(0) is None and os.sched_getaffinity(0) == set(cpus[2:])     # bound once (by us or by mpirun): kept
+    finally:
+        os.sched_setaffinity(0, before)
+        os.environ.pop("B200MPI_BOUND_CPUS", None)
+        os.environ.pop("B200MPI_BOUND_NUMA", None)
