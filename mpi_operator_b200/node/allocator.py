@@ -68,10 +68,39 @@ class GangAllocator:
         with self._lock:
             return list(self._held[key]) if key in self._held else None
 
-    def _take(self, n: int) -> Optional[List[int]]:
+    def _select(self, n: int) -> Optional[List[int]]:
+        """Which free GPUs a reservation of ``n`` gets. Every pair is an NVSwitch peer, so the fabric does not care; the host side
+        does: GPUs 0-3 / 4-7 of an HGX board hang off different sockets. A reservation that fits on one socket is placed on the
+        socket with the FEWEST free GPUs that still holds it (best fit: a later 4-GPU job still finds a whole socket, and the
+        ranks' pinned staging buffers stay local with ``mpirun --bind-to numa``); one that does not fit takes the fullest sockets
+        first. Without NUMA information this is "the first n free GPUs"."""
         if n > len(self._free):
             return None
-        got, self._free = self._free[:n], self._free[n:]
+        node_of = {g.index: g.numa_node for g in self.topology.gpus}
+        by_node: Dict[object, List[int]] = {}
+        for g in self._free:
+            by_node.setdefault(node_of.get(g), []).append(g)
+        order = lambda k: (k is None, k if k is not None else 0)   # noqa: E731  (None sorts last)
+        fits = [k for k, v in by_node.items() if len(v) >= n]
+        if fits:
+            node = min(fits, key=lambda k: (len(by_node[k]), order(k)))
+            return by_node[node][:n]
+        chosen: List[int] = []
+        for k in sorted(by_node, key=lambda k: (-len(by_node[k]), order(k))):
+            chosen.extend(by_node[k][:n - len(chosen)])
+            if len(chosen) == n:
+                break
+        return sorted(chosen)
+
+    def _take(self, n: int, pool: Optional[List[int]] = None) -> Optional[List[int]]:
+        """Removes ``n`` GPUs from the free list: the first ``n`` of ``pool`` (a gang's pre-selected set) or ``_select(n)``."""
+        got = pool[:n] if pool is not None else self._select(n)
+        if got is None or len(got) < n:
+            return None
+        if pool is not None:
+            del pool[:n]
+        taken = set(got)
+        self._free = [g for g in self._free if g not in taken]
         return got
 
     def allocate(self, req: SlotRequest) -> Optional[List[int]]:
@@ -107,8 +136,9 @@ class GangAllocator:
             if need > len(self._free):
                 return None
             out = {}
+            pool = self._select(need)          # one placement decision for the whole gang, dealt out in pod order
             for r in sorted(pending, key=lambda r: r.key):
-                self._held[r.key] = self._take(r.gpus)
+                self._held[r.key] = self._take(r.gpus, pool)
             for r in reqs:
                 out[r.key] = list(self._held[r.key])
             return out

@@ -21,6 +21,8 @@ class GPU:
     name: str = ""
     memory_bytes: int = 0
     nvlink_peers: List[int] = field(default_factory=list)
+    pci_bus_id: str = ""
+    numa_node: Optional[int] = None     # the socket whose PCIe root the GPU hangs off (sysfs); None = the platform does not say
 
 
 @dataclass
@@ -47,6 +49,21 @@ class Topology:
                 "gpus": [g.__dict__ for g in self.gpus]}
 
 
+def _numa_of_bus(bus_id: str) -> Optional[int]:
+    """NVML / torch give "00000000:1B:00.0" or "0000:1b:00.0"; sysfs wants the 4-digit-domain lower-case form."""
+    if not bus_id:
+        return None
+    parts = bus_id.lower().split(":")
+    if len(parts) == 3:
+        parts[0] = parts[0][-4:].rjust(4, "0")
+    root = os.environ.get("B200MPI_SYSFS_ROOT", "")
+    try:
+        node = int(open(f"{root}/sys/bus/pci/devices/{':'.join(parts)}/numa_node").read().strip())
+    except (OSError, ValueError):
+        return None
+    return node if node >= 0 else None
+
+
 def _from_nvml() -> Optional[Topology]:
     try:
         import pynvml  # nvidia-ml-py
@@ -71,7 +88,13 @@ def _from_nvml() -> Optional[Topology]:
                         peers.append(j)
                 except Exception:
                     pass
-            gpus.append(GPU(i, uuid if isinstance(uuid, str) else uuid.decode(), name if isinstance(name, str) else name.decode(), int(mem), peers))
+            try:
+                bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+                bus = bus if isinstance(bus, str) else bus.decode()
+            except Exception:
+                bus = ""
+            gpus.append(GPU(i, uuid if isinstance(uuid, str) else uuid.decode(), name if isinstance(name, str) else name.decode(), int(mem), peers,
+                            bus, _numa_of_bus(bus)))
         return Topology(gpus, "nvml")
     except Exception:
         return None
@@ -92,7 +115,11 @@ def _from_torch() -> Optional[Topology]:
         for i in range(n):
             p = torch.cuda.get_device_properties(i)
             peers = [j for j in range(n) if j != i and torch.cuda.can_device_access_peer(i, j)]
-            gpus.append(GPU(i, str(getattr(p, "uuid", "")), p.name, int(p.total_memory), peers))
+            try:
+                bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+            except AttributeError:
+                bus = ""
+            gpus.append(GPU(i, str(getattr(p, "uuid", "")), p.name, int(p.total_memory), peers, bus, _numa_of_bus(bus)))
         return Topology(gpus, "torch")
     except Exception:
         return None
@@ -102,7 +129,9 @@ def discover_topology() -> Topology:
     fake = os.environ.get("B200MPI_FAKE_GPUS")
     if fake is not None:
         n = int(fake)
-        return Topology([GPU(i, f"GPU-fake-{i}", "FakeB200", 180 << 30, [j for j in range(n) if j != i]) for i in range(n)], "fake")
+        nodes = int(os.environ.get("B200MPI_FAKE_NUMA_NODES", 0))     # e.g. 2: GPUs 0..n/2-1 on socket 0, the rest on socket 1 (HGX layout)
+        return Topology([GPU(i, f"GPU-fake-{i}", "FakeB200", 180 << 30, [j for j in range(n) if j != i], f"0000:{0x1b + 0x10 * i:02x}:00.0",
+                             (i * nodes // n) if nodes > 0 else None) for i in range(n)], "fake")
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     topo = _from_nvml() or _from_torch() or Topology([], "none")
     if vis not in (None, "") and topo.source == "nvml":

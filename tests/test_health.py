@@ -65,3 +65,36 @@ def test_allocator_cordon_rules():
     assert a.uncordon(2) and a.free_gpus == 3
     with pytest.raises(ValueError):
         a.cordon(9)
+
+
+def test_allocator_places_reservations_by_socket(monkeypatch):
+    """Placement is NUMA-aware (node/allocator.py::_select): best fit on one socket, whole sockets first when a gang spans both,
+    plain first-n without NUMA information. The reference leaves placement to kube-scheduler / Volcano."""
+    from mpi_operator_b200.node.allocator import GangAllocator, SlotRequest
+    from mpi_operator_b200.node.topology import discover_topology
+    monkeypatch.setenv("B200MPI_FAKE_GPUS", "8")
+    monkeypatch.setenv("B200MPI_FAKE_NUMA_NODES", "2")
+    topo = discover_topology()
+    assert [g.numa_node for g in topo.gpus] == [0, 0, 0, 0, 1, 1, 1, 1] and topo.to_dict()["gpus"][5]["numa_node"] == 1
+    a = GangAllocator(topo)
+    assert a.allocate(SlotRequest("d/a", 2)) == [0, 1]                    # both sockets fit: the lower one
+    assert a.allocate(SlotRequest("d/b", 2)) == [2, 3]                    # best fit: fills socket 0 instead of opening socket 1
+    gang = [SlotRequest(f"d/g-{k}", 1, group="g") for k in range(4)]
+    assert a.allocate_gang(gang, 4) == {f"d/g-{k}": [4 + k] for k in range(4)}   # a 4-GPU gang still finds a whole socket
+    a.release("d/a")
+    a.release("d/g-0")
+    a.release("d/g-1")                                                     # free: 0,1 (socket 0) and 4,5 (socket 1)
+    assert a.allocate(SlotRequest("d/c", 1)) == [0]
+    assert a.allocate(SlotRequest("d/d", 2)) == [4, 5]                    # does not split across sockets while one socket holds it
+    assert a.allocate(SlotRequest("d/e", 2)) is None and a.free_gpus == 1
+    for k in ("d/b", "d/c", "d/d", "d/g-2", "d/g-3"):
+        a.release(k)
+    assert a.free_gpus == 8
+    a.cordon(1, "test")
+    six = [SlotRequest(f"d/s-{k}", 1, group="s") for k in range(6)]
+    got = a.allocate_gang(six, 6)                                          # spans both: the fuller socket whole, the rest from the other
+    assert sorted(g for v in got.values() for g in v) == [0, 2, 4, 5, 6, 7]
+    # no NUMA information: the first n free GPUs, as before
+    monkeypatch.delenv("B200MPI_FAKE_NUMA_NODES")
+    b = GangAllocator(discover_topology())
+    assert b.allocate(SlotRequest("d/x", 3)) == [0, 1, 2] and b.allocate(SlotRequest("d/y", 3)) == [3, 4, 5]
