@@ -21,6 +21,9 @@ if [ "$N" -ge 2 ]; then
     timeout 870 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) bench.py \
       --gpus $n --steps 20 --warmup 5 2>$O/bench_n$n.err | tail -1 | tee $O/bench_n$n.json | cut -c1-900
   done
+  stamp "3b. bench.py $N GPUs with every rank bound next to its GPU (B200MPI_BIND_TO=numa; off by default until this says it pays)"
+  B200MPI_BIND_TO=numa B200MPI_BENCH_SAME_BOX=0 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29644 bench.py \
+    --gpus $N --steps 20 --warmup 5 2>$O/bench_n${N}_numa.err | tail -1 | tee $O/bench_n${N}_numa.json | cut -c1-400
   stamp "4. step timeline at $N GPUs (exposed comm / copy time per step)"
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29655 benchmarks/step_timeline.py \
     --out $O/step_timeline_n$N.md 2>&1 | tail -3
