@@ -30,6 +30,10 @@ def invalid(resource: str, name: str, why: str) -> ApiError:
     return ApiError("Invalid", f'{resource} "{name}" is invalid: {why}', 422)
 
 
+def bad_request(why: str) -> ApiError:
+    return ApiError("BadRequest", why, 400)
+
+
 def forbidden(why: str) -> ApiError:
     return ApiError("Forbidden", why, 403)
 

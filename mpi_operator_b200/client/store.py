@@ -99,9 +99,22 @@ class ObjectStore:
                     h(etype, obj, old)
         self._save()
 
+    @staticmethod
+    def _check_structure(resource: str, obj: dict) -> None:
+        """The CRD's structural schema, applied on every write of the main resource like kube-apiserver does (types and enums
+        only: api/schema.py); a mistyped field never reaches the controller."""
+        from ..api.schema import core_structural_errors, structural_errors
+        errs = structural_errors(obj) if resource == "mpijobs" else core_structural_errors(resource, obj)
+        if errs:
+            shown = errs[0] if len(errs) == 1 else "[" + ", ".join(errs[:8]) + (", ..." if len(errs) > 8 else "") + "]"
+            md = obj.get("metadata")
+            name = md.get("name") if isinstance(md, dict) else ""
+            raise errors.invalid("MPIJob.kubeflow.org" if resource == "mpijobs" else resource, str(name or ""), shown)
+
     # ---------------------------------------------------------------- CRUD --
     def create(self, resource: str, obj: dict) -> dict:
         self._check(resource)
+        self._check_structure(resource, obj)
         with self._lock:
             api_version, kind, namespaced = RESOURCES[resource]
             obj = copy.deepcopy(obj)
@@ -155,6 +168,8 @@ class ObjectStore:
 
     def _update(self, resource: str, obj: dict, status_only: bool) -> dict:
         self._check(resource)
+        if not status_only:
+            self._check_structure(resource, obj)
         with self._lock:
             md = M.meta(obj)
             ns = md.get("namespace", "") if RESOURCES[resource][2] else ""

@@ -234,6 +234,9 @@ def _load_or_create_token(path: str) -> str:
     return tok
 
 
+MAX_BODY_BYTES = 16 << 20     # larger than any object the apiserver would take (etcd's limit is 1.5 MiB; generous for ConfigMaps)
+
+
 def _make_handler(op: Operator, restricted: bool = False):
     store = op.store
 
@@ -276,8 +279,21 @@ def _make_handler(op: Operator, restricted: bool = False):
             self.wfile.write(data)
 
         def _body(self):
-            n = int(self.headers.get("Content-Length", 0) or 0)
-            return json.loads(self.rfile.read(n) or b"{}") if n else {}
+            try:
+                n = int(self.headers.get("Content-Length", 0) or 0)
+            except ValueError:
+                raise errors.bad_request("Content-Length is not a number")
+            if n > MAX_BODY_BYTES:
+                self.close_connection = True      # the unread body would be parsed as the next request
+                raise errors.ApiError("RequestEntityTooLarge", f"request body of {n} bytes exceeds the limit of {MAX_BODY_BYTES}", 413)
+            raw = self.rfile.read(n) if n > 0 else b""
+            try:
+                obj = json.loads(raw) if raw.strip() else {}
+            except (ValueError, RecursionError) as e:     # RecursionError: absurdly nested input
+                raise errors.bad_request(f"the request body is not valid JSON: {e}")
+            if not isinstance(obj, dict):
+                raise errors.bad_request(f"the request body must be a JSON object, got {type(obj).__name__}")
+            return obj
 
         def _route(self):
             u = urllib.parse.urlparse(self.path)
@@ -460,10 +476,30 @@ def _make_handler(op: Operator, restricted: bool = False):
         def _admit(self, res, obj):
             """API-server side admission for MPIJobs: CRD schema defaults + structural validation."""
             if res == "mpijobs":
+                from ..api.schema import structural_errors
+                # the reference's own SDK example passes `command="mpirun"` (sdk/python/v2beta1/tensorflow-mnist.py:32,48): a bare
+                # string where core/v1 wants a list. Accepted the way a shell user means it - one word - instead of refused.
+                specs = (obj.get("spec") or {}).get("mpiReplicaSpecs") if isinstance(obj.get("spec"), dict) else None
+                for rs in (specs.values() if isinstance(specs, dict) else ()):
+                    pod = ((rs.get("template") or {}).get("spec") if isinstance(rs, dict) and isinstance(rs.get("template"), dict) else None)
+                    for c in (pod.get("containers") if isinstance(pod, dict) and isinstance(pod.get("containers"), list) else ()):
+                        for k in ("command", "args"):
+                            if isinstance(c, dict) and isinstance(c.get(k), str):
+                                c[k] = [c[k]]
+                errs = structural_errors(obj)
+                if errs:
+                    md = obj.get("metadata")
+                    raise errors.invalid("MPIJob.kubeflow.org", str(md.get("name") or "") if isinstance(md, dict) else "",
+                                         errs[0] if len(errs) == 1 else "[" + ", ".join(errs[:8]) + "]")
                 if obj.get("kind", C.KIND) != C.KIND or obj.get("apiVersion", C.API_VERSION) != C.API_VERSION:
                     raise errors.invalid("mpijobs", M.name_of(obj), f"expected {C.API_VERSION}/{C.KIND}")
                 if not (obj.get("spec") or {}).get("mpiReplicaSpecs"):
                     raise errors.invalid("mpijobs", M.name_of(obj), "spec.mpiReplicaSpecs: Required value")
+            elif res == "pods":
+                from ..api.schema import core_structural_errors
+                errs = core_structural_errors(res, obj, required=True)
+                if errs:
+                    raise errors.invalid("pods", M.name_of(obj), errs[0] if len(errs) == 1 else "[" + ", ".join(errs[:8]) + "]")
 
         def do_POST(self):  # noqa: N802
             if self._refuse():
@@ -572,6 +608,28 @@ def _make_handler(op: Operator, restricted: bool = False):
             except errors.ApiError as e:
                 return self._send(e.code, e.to_status())
 
+    def guarded(fn):
+        """No request may end in a dropped connection: API errors become their Status, a body that does not have the shape of
+        the object it claims to be (a string where a map belongs ...) is a 400 like the apiserver's decoder gives, anything
+        else a 500 with the exception's text; the traceback goes to the log."""
+        def wrapper(self):
+            try:
+                return fn(self)
+            except errors.ApiError as e:
+                return self._send(e.code, e.to_status())
+            except (BrokenPipeError, ConnectionResetError):
+                self.close_connection = True
+            except (AttributeError, TypeError, KeyError, IndexError, ValueError) as e:
+                log.debug("http: malformed request %s %s", self.command, self.path, exc_info=True)
+                return self._send(400, errors.bad_request(f"the request could not be decoded: {type(e).__name__}: {e}").to_status())
+            except Exception as e:  # noqa: BLE001
+                log.exception("http: %s %s failed", self.command, self.path)
+                return self._send(500, errors.ApiError("InternalError", f"{type(e).__name__}: {e}", 500).to_status())
+        wrapper.__name__ = fn.__name__
+        return wrapper
+
+    for verb in ("do_GET", "do_POST", "do_PUT", "do_PATCH", "do_DELETE"):
+        setattr(H, verb, guarded(getattr(H, verb)))
     return H
 
 

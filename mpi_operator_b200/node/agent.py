@@ -223,6 +223,15 @@ class NodeAgent:
             metrics.gpu_slots_free.set(self.alloc.free_gpus)
             metrics.ranks_active.set(sum(1 for p in self._procs.values() if p.popen is not None and p.popen.poll() is None))
 
+    def _complain(self, key: str, msg: str) -> None:
+        """One warning per object and message, not one per tick."""
+        seen = self.__dict__.setdefault("_complaints", {})
+        if seen.get(key) != msg:
+            seen[key] = msg
+            if len(seen) > 4096:
+                seen.clear()
+            log.warning("%s", msg)
+
     # ------------------------------------------------------- Job controller --
     def _sync_jobs(self) -> None:
         now = time.time()
@@ -241,6 +250,8 @@ class NodeAgent:
             except errors.ApiError as e:
                 if not (errors.is_not_found(e) or errors.is_conflict(e)):
                     raise
+            except Exception as e:  # noqa: BLE001  (a Job object this loop cannot digest must not stop the others)
+                self._complain(M.key_of(job), f"cannot sync job {M.key_of(job)}: {type(e).__name__}: {e}")
 
     def _job_pods(self, job: dict) -> List[dict]:
         snap = getattr(self, "_pods_by_owner", None)
@@ -365,11 +376,19 @@ class NodeAgent:
     # ------------------------------------------------------------ scheduler --
     @staticmethod
     def _gpu_request(pod: dict) -> int:
+        """Sum of the containers' nvidia.com/gpu quantities (limits win over requests). Raises ValueError with the field's
+        path for a quantity that is not a whole number: extended resources cannot be fractional (the apiserver says the same)."""
         n = 0
-        for c in pod["spec"].get("containers", []):
+        for k, c in enumerate(pod["spec"].get("containers") or []):
             res = c.get("resources") or {}
             v = (res.get("limits") or {}).get(C.GPU_RESOURCE, (res.get("requests") or {}).get(C.GPU_RESOURCE, 0))
-            n += int(v)
+            try:
+                q = 0 if v is None else (int(str(v).strip() or 0) if not isinstance(v, bool) else None)
+            except (TypeError, ValueError):
+                q = None
+            if q is None or q < 0:
+                raise ValueError(f"spec.containers[{k}].resources: {C.GPU_RESOURCE}: Invalid value: {v!r}: must be a non-negative integer")
+            n += q
         return n
 
     @staticmethod
@@ -398,7 +417,7 @@ class NodeAgent:
 
     def _schedule(self) -> None:
         pending = [p for p in self.store.list("pods")
-                   if not p["spec"].get("nodeName") and p.get("status", {}).get("phase") in (None, "", "Pending")
+                   if isinstance(p.get("spec"), dict) and not p["spec"].get("nodeName") and (p.get("status") or {}).get("phase") in (None, "", "Pending")
                    and not M.meta(p).get("deletionTimestamp")]
         if not pending:
             return
@@ -413,35 +432,50 @@ class NodeAgent:
             order.append((-self._priority(members[0], pg), min(M.meta(m).get("creationTimestamp", "") for m in members), g, members, pg))
         order.sort(key=lambda t: (t[0], t[1], t[2]))
         now = time.time()
+        # one malformed pod or gang (a quantity that is not a number, a PodGroup with a bad minMember) must not keep every
+        # other pod on the box from being scheduled: it is marked unschedulable with the reason and the loop goes on
         for _, _, g, members, pg in order:
-            all_members = [p for p in self.store.list("pods", M.split_key(g)[0]) if self._group_of(p) == g
-                           and p.get("status", {}).get("phase") not in ("Succeeded", "Failed")]
-            reqs = [SlotRequest(M.key_of(p), self._gpu_request(p), g) for p in all_members]
-            spec = (pg or {}).get("spec", {})
-            min_member = int(spec.get("minMember", len(reqs)) or 0)
-            min_gpus = int((spec.get("minResources") or {}).get(C.GPU_RESOURCE, 0) or 0)
-            feasible = min_gpus <= self.topology.gpu_count if self.topology.gpu_count or min_gpus else True
-            grant = self.alloc.allocate_gang(reqs, min_member, min_gpus) if feasible and pg is not None else None
-            if grant is None:
-                since = self._unsched_since.setdefault(g, now)
-                timeout = int(spec.get("scheduleTimeoutSeconds", 0) or 0)
-                why = "PodGroup not found" if pg is None else (
-                    f"gang of {len(reqs)}/{min_member} members needs {max(min_gpus, sum(r.gpus for r in reqs))} GPUs, {self.alloc.free_gpus} free")
-                if timeout and now - since > timeout:
-                    why += f" (scheduleTimeoutSeconds={timeout} exceeded)"
+            try:
+                self._schedule_gang(g, members, pg, now)
+            except Exception as e:  # noqa: BLE001
+                self._complain("gang " + g, f"cannot schedule gang {g}: {e}")
                 for p in members:
-                    self._mark_unschedulable(p, why)
-                continue
-            self._unsched_since.pop(g, None)
-            for p in members:
-                self._bind(p, grant[M.key_of(p)])
+                    self._mark_unschedulable(p, f"invalid scheduling input: {e}")
         for p in sorted(singles, key=lambda p: M.meta(p).get("creationTimestamp", "")):
-            got = self.alloc.allocate(SlotRequest(M.key_of(p), self._gpu_request(p)))
-            if got is None:
-                self._mark_unschedulable(p, f"needs {self._gpu_request(p)} GPUs, {self.alloc.free_gpus} free")
-            else:
-                self._bind(p, got)
+            try:
+                want = self._gpu_request(p)
+                got = self.alloc.allocate(SlotRequest(M.key_of(p), want))
+                if got is None:
+                    self._mark_unschedulable(p, f"needs {want} GPUs, {self.alloc.free_gpus} free")
+                else:
+                    self._bind(p, got)
+            except Exception as e:  # noqa: BLE001
+                self._complain(M.key_of(p), f"cannot schedule pod {M.key_of(p)}: {e}")
+                self._mark_unschedulable(p, f"invalid scheduling input: {e}")
         self._write_all_slots()
+
+    def _schedule_gang(self, g: str, members: List[dict], pg: Optional[dict], now: float) -> None:
+        all_members = [p for p in self.store.list("pods", M.split_key(g)[0]) if self._group_of(p) == g
+                       and p.get("status", {}).get("phase") not in ("Succeeded", "Failed")]
+        reqs = [SlotRequest(M.key_of(p), self._gpu_request(p), g) for p in all_members]
+        spec = (pg or {}).get("spec", {})
+        min_member = int(spec.get("minMember", len(reqs)) or 0)
+        min_gpus = int((spec.get("minResources") or {}).get(C.GPU_RESOURCE, 0) or 0)
+        feasible = min_gpus <= self.topology.gpu_count if self.topology.gpu_count or min_gpus else True
+        grant = self.alloc.allocate_gang(reqs, min_member, min_gpus) if feasible and pg is not None else None
+        if grant is None:
+            since = self._unsched_since.setdefault(g, now)
+            timeout = int(spec.get("scheduleTimeoutSeconds", 0) or 0)
+            why = "PodGroup not found" if pg is None else (
+                f"gang of {len(reqs)}/{min_member} members needs {max(min_gpus, sum(r.gpus for r in reqs))} GPUs, {self.alloc.free_gpus} free")
+            if timeout and now - since > timeout:
+                why += f" (scheduleTimeoutSeconds={timeout} exceeded)"
+            for p in members:
+                self._mark_unschedulable(p, why)
+            return
+        self._unsched_since.pop(g, None)
+        for p in members:
+            self._bind(p, grant[M.key_of(p)])
 
     def _mark_unschedulable(self, pod: dict, why: str) -> None:
         st = copy.deepcopy(pod.get("status", {}))
@@ -481,9 +515,9 @@ class NodeAgent:
     def _sync_pods(self) -> None:
         for pod in self.store.list("pods"):
             key = M.key_of(pod)
-            if not pod["spec"].get("nodeName"):
+            if not isinstance(pod.get("spec"), dict) or not pod["spec"].get("nodeName"):
                 continue
-            phase = pod.get("status", {}).get("phase")
+            phase = (pod.get("status") or {}).get("phase")
             if phase in ("Succeeded", "Failed"):
                 continue
             try:
@@ -494,6 +528,24 @@ class NodeAgent:
             except errors.ApiError as e:
                 if not (errors.is_not_found(e) or errors.is_conflict(e)):
                     raise
+            except Exception as e:  # noqa: BLE001
+                # kubelet's answer to a pod spec it cannot turn into a container: the pod fails with the reason, the box goes on
+                self._complain(key, f"cannot run pod {key}: {type(e).__name__}: {e}")
+                pr = self._procs.get(key)
+                if pr is None or pr.popen is None:
+                    pr = self._procs.setdefault(key, _Proc())
+                    why = f"{type(e).__name__}: {e}"
+                    try:
+                        self._set_terminal(pod, pr, "Failed", 128, "CreateContainerConfigError", why)
+                    except Exception:  # noqa: BLE001  (not even a container list to report on: the bare phase)
+                        bare = copy.deepcopy(pod)
+                        bare["status"] = {"phase": "Failed", "reason": "CreateContainerConfigError", "message": why}
+                        M.meta(bare).pop("resourceVersion", None)
+                        try:
+                            self.store.update_status("pods", bare)
+                        except errors.ApiError:
+                            pass
+                        self.alloc.release(key)
 
     def pod_dir(self, pod: dict) -> str:
         return os.path.join(self.state_dir, "pods", M.namespace_of(pod), M.name_of(pod))

@@ -142,3 +142,58 @@ def test_scheduling_policy_roundtrip():
     d = sp.to_dict()
     assert d == {"minAvailable": 3, "queue": "q", "minResources": {"nvidia.com/gpu": "4"}, "priorityClass": "high", "scheduleTimeoutSeconds": 30}
     assert SchedulingPolicy.from_dict(d) == sp
+
+
+def test_structural_schema_reports_types_enums_and_quantities_with_field_paths():
+    """api/schema.py: the CRD's openAPIV3Schema applied the way kube-apiserver applies it (types, enums, int-or-string), plus the
+    core/v1 shapes inside the pod templates the CRD leaves open. Every example manifest in the tree is clean."""
+    import glob
+    import os
+
+    import yaml
+
+    from mpi_operator_b200.api.schema import core_structural_errors, structural_errors
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    seen = 0
+    for f in glob.glob(os.path.join(repo, "examples", "*", "*.yaml")):
+        for doc in yaml.safe_load_all(open(f)):
+            if doc and doc.get("kind") == "MPIJob":
+                assert structural_errors(doc) == [], f
+                seen += 1
+    assert seen >= 6
+    tmpl = {"spec": {"containers": [{"name": "c", "command": ["true"], "resources": {"limits": {"nvidia.com/gpu": 1, "cpu": "500m", "memory": "2Gi"}}}]}}
+    ok = {"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "j", "labels": {"a": "b"}},
+          "spec": {"slotsPerWorker": 2, "runPolicy": {"backoffLimit": 3, "suspend": False, "ttlSecondsAfterFinished": None,
+                                                      "schedulingPolicy": {"minAvailable": 2, "minResources": {"nvidia.com/gpu": 8, "cpu": "4"}}},
+                   "mpiImplementation": "Intel", "mpiReplicaSpecs": {"Launcher": {"replicas": 1, "template": tmpl}}}}
+    assert structural_errors(ok) == []
+
+    def broken(path, value):
+        import copy
+        o = copy.deepcopy(ok)
+        cur = o
+        for k in path[:-1]:
+            cur = cur[k]
+        cur[path[-1]] = value
+        return structural_errors(o)
+    assert broken(["spec", "slotsPerWorker"], "2") == ['spec.slotsPerWorker: Invalid value: "string": spec.slotsPerWorker in body must be of type integer: "string"']
+    assert broken(["spec", "slotsPerWorker"], True)[0].startswith('spec.slotsPerWorker: Invalid value: "boolean"')
+    assert "must be of type int32" in broken(["spec", "slotsPerWorker"], 1 << 40)[0]
+    assert broken(["spec", "runPolicy", "suspend"], "yes")[0].startswith("spec.runPolicy.suspend: Invalid value")
+    assert "supported values" in broken(["spec", "launcherCreationPolicy"], "Whenever")[0]
+    assert broken(["spec", "runPolicy", "schedulingPolicy", "minResources", "nvidia.com/gpu"], [8])[0].endswith('must be of type integer or string: "array"')
+    assert "must be an integer" in broken(["spec", "runPolicy", "schedulingPolicy", "minResources", "nvidia.com/gpu"], "1.5")[0]
+    assert broken(["spec", "mpiReplicaSpecs", "Launcher", "template"], "pod")[0].startswith("spec.mpiReplicaSpecs.Launcher.template: Invalid value")
+    assert "template.spec.containers[0].args[1]" in broken(["spec", "mpiReplicaSpecs", "Launcher", "template", "spec", "containers", 0, "args"], ["-np", 2])[0]
+    assert "env[0].value in body must be of type string" in broken(["spec", "mpiReplicaSpecs", "Launcher", "template", "spec", "containers", 0, "env"], [{"name": "A", "value": 1}])[0]
+    assert "quantities must match" in broken(["spec", "mpiReplicaSpecs", "Launcher", "template", "spec", "containers", 0, "resources"], {"limits": {"memory": "2 gigs"}})[0]
+    assert broken(["metadata"], "name")[0].startswith('metadata: Invalid value: "string"')
+    assert structural_errors([]) and structural_errors({"spec": None, "metadata": None}) == []       # nulls are absent fields
+    # core objects: types always, required fields only when the REST admission asks
+    assert core_structural_errors("pods", {"metadata": {"name": "p"}, "spec": {}}) == []
+    assert core_structural_errors("pods", {"metadata": {"name": "p"}, "spec": {}}, required=True) == ["spec.containers: Required value"]
+    assert core_structural_errors("pods", {"metadata": {"name": "p"}, "spec": 3})[0].startswith("spec: Invalid value")
+    assert core_structural_errors("jobs", {"metadata": {"name": "j"}, "spec": {"backoffLimit": "6", "template": tmpl}})[0].startswith("spec.backoffLimit")
+    assert core_structural_errors("configmaps", {"metadata": {"name": "c"}, "data": {"hostfile": 5}})[0].startswith("data.hostfile")
+    assert core_structural_errors("volcano-podgroups", {"metadata": {"name": "g"}, "spec": {"minMember": "3"}})[0].startswith("spec.minMember")
+    assert core_structural_errors("services", {"metadata": {"name": "s"}, "spec": {"clusterIP": "None"}}) == []

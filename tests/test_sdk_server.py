@@ -347,3 +347,63 @@ def test_api_discovery_documents(tmp_path):
         assert "v2beta1.MPIJob" in get("/openapi/v2")["definitions"]
     finally:
         op.stop()
+
+
+def test_malformed_requests_get_a_status_never_a_dropped_connection(tmp_path):
+    """What kube-apiserver does before the reference's controller ever sees an object: bodies that are not JSON objects are
+    400, objects whose fields have the wrong TYPE (CRD structural schema, api/schema.py) or an impossible quantity are 422 with
+    the field path, and no request ends without a response. Found by fuzzing the REST surface."""
+    port = _free_port()
+    op = Operator(ServerOption(fake_gpus=2, leader_elect=False, state_dir=str(tmp_path)))
+    op.serve(f"127.0.0.1:{port}")
+    op.start()
+    coll = f"http://127.0.0.1:{port}/apis/kubeflow.org/v2beta1/namespaces/default/mpijobs"
+    pods = f"http://127.0.0.1:{port}/api/v1/namespaces/default/pods"
+
+    def call(method, url, raw):
+        req = urllib.request.Request(url, data=raw, method=method, headers={"Content-Type": "application/json"})
+        try:
+            with urllib.request.urlopen(req, timeout=10) as r:
+                return r.status, json.load(r)
+        except urllib.error.HTTPError as e:
+            return e.code, json.load(e)
+
+    def job(**spec):
+        base = {"slotsPerWorker": 1, "mpiReplicaSpecs": {"Launcher": {"replicas": 1, "template": {"spec": {"containers": [{"name": "l", "command": ["true"]}]}}}}}
+        base.update(spec)
+        return json.dumps({"apiVersion": "kubeflow.org/v2beta1", "kind": "MPIJob", "metadata": {"name": "m"}, "spec": base}).encode()
+    try:
+        for raw in (b"{", b"[]", b'"text"', b"\xff\xfe", b"7"):
+            for method, url in (("POST", coll), ("PUT", coll + "/m"), ("PATCH", coll + "/m"), ("POST", pods), ("PATCH", f"http://127.0.0.1:{port}/topology")):
+                code, st = call(method, url, raw)
+                assert code == 400 and st["kind"] == "Status" and st["reason"] == "BadRequest", (raw, method, code, st)
+        for body, needle in (
+                (job(slotsPerWorker="two"), "spec.slotsPerWorker in body must be of type integer"),
+                (job(runPolicy={"backoffLimit": {}}), "spec.runPolicy.backoffLimit in body must be of type integer"),
+                (job(runPolicy=[]), "spec.runPolicy in body must be of type object"),
+                (job(mpiImplementation="LAM"), 'supported values: "OpenMPI", "Intel", "MPICH"'),
+                (job(mpiReplicaSpecs={"Launcher": {"replicas": 1.5, "template": {}}}), "spec.mpiReplicaSpecs.Launcher.replicas in body must be of type integer"),
+                (job(mpiReplicaSpecs={"Launcher": {"replicas": 1, "template": {"spec": {"containers": {"name": "l"}}}}}), "template.spec.containers in body must be of type array"),
+                (job(mpiReplicaSpecs={"Launcher": {"replicas": 1, "template": {"spec": {"containers": [{"name": "l", "resources": {"limits": {"nvidia.com/gpu": "lots"}}}]}}}}),
+                 "resources.limits.nvidia.com/gpu: Invalid value: \"lots\": quantities must match"),
+                (job(mpiReplicaSpecs={"Launcher": {"replicas": 1, "template": {"spec": {"containers": [{"name": "l", "resources": {"limits": {"nvidia.com/gpu": "0.5"}}}]}}}}), "must be an integer"),
+                (json.dumps({"kind": "MPIJob", "metadata": 5, "spec": {}}).encode(), ""),
+                (json.dumps({"kind": "MPIJob", "metadata": {"name": "m", "labels": {"a": 1}}, "spec": {"mpiReplicaSpecs": {}}}).encode(), "metadata.labels.a in body must be of type string")):
+            code, st = call("POST", coll, body)
+            assert code in (400, 422) and st["kind"] == "Status" and needle in st["message"], (body, code, st)
+        assert op.store.list("mpijobs") == []
+        code, st = call("POST", pods, json.dumps({"metadata": {"name": "p"}, "spec": {"containers": [{"name": "c", "resources": {"limits": {"nvidia.com/gpu": "x"}}}]}}).encode())
+        assert code == 422 and "quantities must match" in st["message"]
+        code, st = call("POST", pods, json.dumps({"metadata": {"name": "p"}}).encode())
+        assert code == 422 and "spec: Required value" in st["message"]
+        # a well-formed object still goes through, a PATCH that breaks a type does not
+        code, st = call("POST", coll, job(runPolicy={"suspend": True}))
+        assert code == 201
+        code, st = call("PATCH", coll + "/m", json.dumps({"spec": {"slotsPerWorker": "many"}}).encode())
+        assert code == 422 and "spec.slotsPerWorker" in st["message"]
+        with socket.create_connection(("127.0.0.1", port), timeout=10) as sk:      # announced size over the limit: refused before reading it
+            sk.sendall(b"POST /apis/kubeflow.org/v2beta1/namespaces/default/mpijobs HTTP/1.1\r\nHost: x\r\nContent-Type: application/json\r\n"
+                       b"Content-Length: 17825792\r\n\r\n{")
+            assert sk.recv(4096).startswith(b"HTTP/1.1 413")
+    finally:
+        op.stop()
