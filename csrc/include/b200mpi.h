@@ -180,6 +180,10 @@ int b200mpi_reduce_scatter(b200mpi_comm_t comm, const void* in, void* out, size_
                            b200mpi_dtype_t dtype, b200mpi_op_t op, float scale, void* stream);
 int b200mpi_reduce(b200mpi_comm_t comm, const void* in, void* out, size_t count,
                    b200mpi_dtype_t dtype, b200mpi_op_t op, float scale, int root, void* stream);
+/* Adasum allreduce (Horovod op=hvd.Adasum) in one kernel; B200MPI_ERR_UNSUPPORTED when the world is not a power of two or
+ * count * sizeof(dtype) > b200mpi_adasum_max_bytes(): callers then gather and fold the tree themselves */
+int b200mpi_adasum(b200mpi_comm_t comm, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream);
+size_t b200mpi_adasum_max_bytes(b200mpi_comm_t comm, b200mpi_dtype_t dtype);
 /* in/out have world*count elements; block j of in goes to rank j */
 int b200mpi_alltoall(b200mpi_comm_t comm, const void* in, void* out, size_t count,
                      b200mpi_dtype_t dtype, void* stream);

@@ -35,7 +35,9 @@ constexpr size_t kPipeSigOff = kSigWords;
 constexpr size_t kPipeSigWords = 4 * (size_t)kPipeLanes * kMaxRanks;
 constexpr size_t kSigWordsTotal = kSigWords + kPipeSigWords;
 constexpr size_t kPipeEpochOff = kEpochWords;
-constexpr size_t kEpochWordsTotal = kEpochWords + 4 * (size_t)kPipeLanes;
+// Adasum (adasum.cu): counter + generation word of the barrier between the CTAs of one rank's grid
+constexpr size_t kAdaEpochOff = kEpochWords + 4 * (size_t)kPipeLanes;
+constexpr size_t kEpochWordsTotal = kAdaEpochOff + 2;
 
 enum : int { OP_SUM = 0, OP_MAX = 1, OP_MIN = 2 };
 

@@ -91,6 +91,11 @@ cudaError_t launch_reduce_scatter(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_reduce(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_alltoall(const Launch& l, const KArgs& a);
 cudaError_t launch_barrier(const Launch& l, const KArgs& a);
+// Adasum (adasum.cu). Staging layout behind a.buf: [dot board kAdaDotBytes][A: world*per vectors of T][W: world*per vectors as fp32]
+constexpr int kAdaMaxBlocks = 64;                                   // CTAs per rank (all co-resident: spin barriers)
+constexpr size_t kAdaDotBytes = (size_t)96 << 10;                   // >= (kMaxRanks-1) pairs x kMaxRanks x kAdaMaxBlocks x 3 doubles
+static_assert((size_t)(kMaxRanks - 1) * kMaxRanks * kAdaMaxBlocks * 3 * sizeof(double) <= kAdaDotBytes, "dot board too small");
+cudaError_t launch_adasum(const Launch& l, const KArgs& a, int dtype);
 cudaError_t launch_scale_cast(cudaStream_t s, const void* in, int in_dt, void* out, int out_dt,
                               size_t count, float scale);
 cudaError_t launch_fill_u32(cudaStream_t s, uint32_t* p, uint32_t v, size_t n);

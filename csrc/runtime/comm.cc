@@ -1242,6 +1242,42 @@ int b200mpi_allgather(b200mpi_comm_t c, const void* in, void* out, size_t count,
                    });
 }
 
+// Adasum allreduce (adasum.cu): one launch, slice-parallel tree over peer memory. UNSUPPORTED (the caller falls back to the
+// gather + local tree) when the world is not a power of two or the tensor does not fit the staging layout
+// [dot board][A: world*per vectors][W: the same as fp32].
+size_t b200mpi_adasum_max_bytes(b200mpi_comm_t c, b200mpi_dtype_t dtype) {
+  if (!c || dtype < 0 || dtype > 2 || c->twoshot_bytes <= kAdaDotBytes + 4096) return 0;
+  const size_t expand = dtype == B200MPI_F32 ? 1 : 2;                     // fp32 work copy per byte of T
+  const size_t room = c->twoshot_bytes - kAdaDotBytes - 4096;             // slack for the round-up to world * per vectors
+  return room / (1 + expand) / 256 * 256;
+}
+int b200mpi_adasum(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype, void* stream) {
+  if (count == 0) return 0;
+  if (dtype < 0 || dtype > 2) return fail(B200MPI_ERR_UNSUPPORTED, "adasum: f32 / bf16 / f16 only");
+  if (c->world < 2 || (c->world & (c->world - 1))) return fail(B200MPI_ERR_UNSUPPORTED, "adasum kernel: the world must be a power of two >= 2");
+  const size_t nbytes = count * esize(dtype);
+  if (nbytes > b200mpi_adasum_max_bytes(c, dtype)) return fail(B200MPI_ERR_UNSUPPORTED, "adasum kernel: tensor larger than the staging layout");
+  const size_t nvec = (nbytes + 15) / 16;
+  const size_t per = (nvec + c->world - 1) / c->world;
+  int blocks = blocks_for(c, per, 1, std::min(c->max_blocks, kAdaMaxBlocks));
+  if (c->local) blocks = std::min(blocks, emu_max_blocks(c));
+  const auto ranks = my_ranks(c);
+  std::vector<KArgs> args(c->local ? c->world : 1);
+  for (size_t k = 0; k < ranks.size(); k++) {
+    const int r = ranks[k];
+    KArgs& a = args[k];
+    memset(&a, 0, sizeof(a));
+    a.c = dev_comm(c, r);
+    a.buf = win_region(c, c->stage_win, c->twoshot_off);
+    a.in = in_ptr(c, in, r);
+    a.out = out_ptr(c, out, r);
+    a.nbytes = nbytes; a.nvec = nvec; a.per = per; a.scale = 1.0f;
+    a.in_aligned = aligned16(a.in); a.out_aligned = aligned16(a.out);
+  }
+  return run(c, (cudaStream_t)stream, blocks, "adasum", nbytes, B200MPI_ALGO_TWOSHOT, args,
+             [&](const Launch& l, const KArgs& a) { return launch_adasum(l, a, dtype); });
+}
+
 int b200mpi_reduce_scatter(b200mpi_comm_t c, const void* in, void* out, size_t count, b200mpi_dtype_t dtype,
                            b200mpi_op_t op, float scale, void* stream) {
   const size_t total = count * esize(dtype);

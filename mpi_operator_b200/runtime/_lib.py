@@ -86,6 +86,9 @@ def lib() -> C.CDLL:
     L.b200mpi_broadcast_bytes.argtypes = [vp, vp, sz, i, vp]
     L.b200mpi_allgather.argtypes = [vp, vp, vp, sz, i, vp]
     L.b200mpi_reduce_scatter.argtypes = [vp, vp, vp, sz, i, i, f, vp]
+    L.b200mpi_adasum.argtypes = [vp, vp, vp, sz, i, vp]
+    L.b200mpi_adasum_max_bytes.argtypes = [vp, i]
+    L.b200mpi_adasum_max_bytes.restype = sz
     L.b200mpi_reduce.argtypes = [vp, vp, vp, sz, i, i, f, i, vp]
     L.b200mpi_alltoall.argtypes = [vp, vp, vp, sz, i, vp]
     L.b200mpi_barrier.argtypes = [vp, vp]

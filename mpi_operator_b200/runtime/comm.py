@@ -389,6 +389,30 @@ class Communicator:
         check(_lib.lib().b200mpi_allgather(self._h, pin, pout, nbytes // 2, BF16, _stream_ptr(stream)), "allgather")
         return out
 
+    def adasum_max_bytes(self, dtype) -> int:
+        """Largest tensor (bytes) the one-kernel Adasum takes on this communicator; 0 when it cannot run at all (world
+        not a power of two, dtype other than f32 / bf16 / f16, staging window too small)."""
+        if self.world < 2 or self.world & (self.world - 1):
+            return 0
+        try:
+            code = dtype_code(dtype)
+        except Exception:
+            return 0
+        if code not in (F32, BF16, F16):
+            return 0
+        return int(_lib.lib().b200mpi_adasum_max_bytes(self._h, code))
+
+    def adasum(self, tensor, out=None, stream=None):
+        """Adasum allreduce (Horovod ``op=hvd.Adasum``) in ONE kernel (csrc/kernels/adasum.cu): slice-parallel
+        distance-doubling tree over peer memory, dot products exchanged through a board in the staging window.
+        Raises B200MPIError when ``adasum_max_bytes`` says the tensor does not fit; ``hvd/adasum.py`` then gathers
+        and folds the tree with torch ops."""
+        out = tensor if out is None else out
+        pin, t0 = self._ptrs(tensor)
+        pout, _ = self._ptrs(out)
+        check(_lib.lib().b200mpi_adasum(self._h, pin, pout, t0.numel(), dtype_code(t0.dtype), _stream_ptr(stream)), "adasum")
+        return out
+
     def reduce_scatter(self, tensor, out, op: str = "sum", scale: Optional[float] = None, stream=None):
         pin, _ = self._ptrs(tensor)
         pout, o0 = self._ptrs(out)
