@@ -59,6 +59,25 @@ def render_docs(sw):
     return out
 
 
+def render_meta_docs():
+    """The same per-model page for the generic apimachinery models (reference: sdk/python/v2beta1/docs/V1*.md,
+    IoK8sApimachineryPkg*.md, K8sIoApimachineryPkg*.md), rendered from the schema table in mpi_operator_b200/sdk/meta_models.py."""
+    import re
+    from mpi_operator_b200.sdk.meta_models import META_MODELS
+    out = {}
+    for cls_name, cls in sorted(META_MODELS.items()):
+        lines = [f"# {cls_name}", "", (cls.__doc__ or "").strip().splitlines()[0] if cls.__doc__ else "", "", "## Properties",
+                 "Name | Type | Description | Notes", "------------ | ------------- | ------------- | -------------"]
+        for attr in sorted(cls.openapi_types):
+            t = cls.openapi_types[attr]
+            inner = re.sub(r"^list\[(.*)\]$|^dict\(str, (.*)\)$", lambda m: m.group(1) or m.group(2), t)
+            shown = f"[**{t}**]({inner}.md)" if inner in META_MODELS else f"**{t}**"
+            lines.append(f"**{attr}** | {shown} | JSON name `{cls.attribute_map[attr]}` | {'' if attr in cls.required else '[optional]'}")
+        lines += ["", "[[Back to README]](../README.md)", ""]
+        out[f"sdk/python/v2beta1/docs/{cls_name}.md"] = "\n".join(lines)
+    return out
+
+
 def main():
     if "--docs" in sys.argv:
         sw = json.load(open(os.path.join(ROOT, "sdk/python/v2beta1/swagger.json")))

@@ -24,6 +24,7 @@ def render():
         "deploy/v2beta1/mpi-operator.yaml": "# all-in-one: CRD schema + daemon config (hack/generate.py; reference: hack/generate-manifest.sh:24-37)\n---\n" + crd + "---\n" + operator_cfg,
     }
     out.update(gen_sdk.render_docs(openapi.swagger()))  # per-model SDK docs (reference: sdk/python/v2beta1/docs/*.md)
+    out.update(gen_sdk.render_meta_docs())     # ... and of the generic apimachinery models (sdk/meta_models.py)
     return out
 
 

@@ -14,3 +14,5 @@ from .models import (V1Container, V1LabelSelector, V1LabelSelectorRequirement, V
                      V1OwnerReference, V1PodSpec, V1PodTemplateSpec, V2beta1JobCondition, V2beta1JobStatus,
                      V2beta1MPIJob, V2beta1MPIJobList, V2beta1MPIJobSpec, V2beta1ReplicaSpec, V2beta1ReplicaStatus,
                      V2beta1RunPolicy, V2beta1SchedulingPolicy)
+from . import meta_models as _meta_models  # noqa: E402  (the generic apimachinery models, built from a schema table)
+from .meta_models import *  # noqa: E402,F401,F403
