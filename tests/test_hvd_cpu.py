@@ -212,3 +212,69 @@ def test_tf_cnn_benchmarks_train_dir_checkpoints_and_resumes(tmp_path):
     import re
     m = re.search(r"Accuracy @ 1 = ([0-9.]+) Accuracy @ 5 = ([0-9.]+) \[(\d+) examples\]", third.stdout)
     assert m and 0.0 <= float(m.group(1)) <= float(m.group(2)) <= 1.0 and int(m.group(3)) == 3 * 4 * 2
+
+
+def _adasum_kernel_model(vectors, ctas=3):
+    """Host model of csrc/kernels/adasum.cu (same index arithmetic, one Python loop per CTA): rank r owns slice r of every
+    vector in its work area W; per level every (rank, CTA) publishes 3 partial sums per pair in its own board slot, the board
+    is summed over (rank, CTA), the slice is combined in place at W[g] with g = p * 2 * dist, h = g + dist, and the partial
+    dots of the NEXT level are accumulated in the same pass (even pair -> `prev`, odd pair -> dot with `prev`); the last level
+    writes the slice to every rank's A. Returns every rank's A."""
+    import torch
+    world, n = len(vectors), vectors[0].numel()
+    per = -(-n // world)
+    pad = [torch.cat([v.double(), torch.zeros(world * per - n, dtype=torch.float64)]) for v in vectors]
+    A = [torch.stack(pad).clone() for _ in range(world)]                       # A[rank][q] = rank's copy of vector q (phase 0 + barrier)
+    W = [torch.stack([pad[q][r * per:(r + 1) * per] for q in range(world)]) for r in range(world)]   # level-0 pull: slice r of all q
+    chunks = [list(torch.arange(per).chunk(ctas)) for _ in range(world)]
+    # partial dots of the level-0 pairs (2p, 2p+1), per (rank, cta)
+    np_ = world // 2
+    acc = {(r, c): [(float(W[r][2 * p][idx] @ W[r][2 * p + 1][idx]), float(W[r][2 * p][idx] @ W[r][2 * p][idx]),
+                     float(W[r][2 * p + 1][idx] @ W[r][2 * p + 1][idx])) for p in range(np_)]
+           for r in range(world) for c, idx in enumerate(chunks[r])}
+    board, pair_base, dist = {}, 0, 1
+    while dist < world:
+        for (r, c), sums in acc.items():
+            for p, s in enumerate(sums):
+                board[(pair_base + p, r, c)] = s                               # own slot: nothing to zero between levels
+        coef = []
+        for p in range(np_):
+            d, na, nb = (sum(board[(pair_base + p, r, c)][k] for r in range(world) for c in range(len(chunks[r]))) for k in range(3))
+            coef.append((1.0 - d / (2 * na) if na > 0 else 1.0, 1.0 - d / (2 * nb) if nb > 0 else 1.0))
+        last = np_ == 1
+        nxt = {}
+        for r in range(world):
+            for c, idx in enumerate(chunks[r]):
+                sums, prev = [], None
+                for p in range(np_):
+                    g, h = p * 2 * dist, p * 2 * dist + dist
+                    z = coef[p][0] * W[r][g][idx] + coef[p][1] * W[r][h][idx]
+                    if last:
+                        for q in range(world):
+                            A[q][0][r * per + idx] = z                           # slice push: the all-gather half (result lives in row 0 here)
+                    else:
+                        W[r][g][idx] = z
+                        if p & 1:
+                            sums.append((float(prev @ z), float(prev @ prev), float(z @ z)))
+                        else:
+                            prev = z
+                nxt[(r, c)] = sums
+        acc, pair_base, np_, dist = nxt, pair_base + np_, np_ // 2, dist * 2
+    return [a[0][:n] for a in A]
+
+
+def test_adasum_kernel_index_model_matches_tree():
+    """The slice-parallel, level-fused schedule of the device kernel reproduces the pairwise tree (any size, 2/4/8 ranks,
+    more CTAs than elements, zero vectors) - checks the pair / slot / next-level-dot index arithmetic without a GPU."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    for world in (2, 4, 8):
+        for n in (1, 5, 64, 257):
+            vs = [torch.randn(n, generator=g, dtype=torch.float64) * (1 + r) for r in range(world)]
+            if n == 64:
+                vs[1].zero_()
+            want = adasum_tree(vs)
+            for ctas in (1, 3):
+                outs = _adasum_kernel_model(vs, ctas=ctas)
+                for o in outs:
+                    assert torch.allclose(o, want, rtol=1e-12, atol=1e-12), (world, n, ctas)

@@ -38,7 +38,7 @@ def test_adasum_kernel_matches_tree(comm, dtype, n):
         pytest.skip("larger than the staging layout of the emulated communicator")
     for it in range(2):                                   # back to back: board slots and barrier words are reused
         xs = _inputs(comm.world, n, dtype, seed=n + it)
-        want = adasum_tree([x.float() for x in xs])
+        want = adasum_tree([x.double() for x in xs]).float()      # fp64 reference: the kernel sums its dot products in fp64
         outs = [torch.empty_like(x) for x in xs] if it == 0 else xs     # out of place, then in place
         comm.adasum(xs, outs)
         torch.cuda.synchronize()
