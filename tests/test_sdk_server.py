@@ -230,6 +230,50 @@ def test_models_match_the_reference_sdk_when_installed():
     assert mpijob.models.MODEL_CLASSES["IoK8sApimachineryPkgApisMetaV1ObjectMeta"] is mpijob.V1ObjectMeta
 
 
+def test_generic_models_match_the_reference_sdk_when_installed():
+    """The 100 generic apimachinery models (sdk/meta_models.py, one schema table) against the generated files of the
+    UNMODIFIED reference SDK at baseline/_ref: same class names, module names, attribute maps and required fields."""
+    import os
+    import subprocess
+    import sys
+    from mpi_operator_b200.sdk.meta_models import snake
+    ref = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "mpijob")):
+        pytest.skip("reference SDK not installed (baseline/_ref)")
+    code = ("import sys, json, inspect; sys.path.insert(0, %r)\n"
+            "import mpijob.models as m\n"
+            "import importlib, pkgutil\n"
+            "out = {}\n"
+            "for info in pkgutil.iter_modules(m.__path__):            # every generated FILE (the package __init__ lists only half)\n"
+            "    mod = importlib.import_module('mpijob.models.' + info.name)\n"
+            "    cs = [c for c in vars(mod).values() if inspect.isclass(c) and c.__module__ == mod.__name__ and hasattr(c, 'attribute_map')]\n"
+            "    if len(cs) != 1 or cs[0].__name__.startswith('V2beta1'):\n"
+            "        continue\n"
+            "    c, n = cs[0], cs[0].__name__\n"
+            "    req = []\n"
+            "    for a in c.openapi_types:\n"
+            "        try:\n"
+            "            o = c.__new__(c); o.local_vars_configuration = type('C', (), {'client_side_validation': True})()\n"
+            "            setattr(o, a, None)\n"
+            "        except ValueError:\n"
+            "            req.append(a)\n"
+            "        except Exception:\n"
+            "            pass\n"
+            "    out[n] = [c.attribute_map, sorted(req), c.__module__.rsplit('.', 1)[-1]]\n"
+            "print(json.dumps(out))\n") % ref
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    if r.returncode != 0:
+        pytest.skip("reference SDK not importable here: " + r.stderr[-200:])
+    theirs = json.loads(r.stdout)
+    assert len(theirs) == 100
+    for name, (amap, required, module) in theirs.items():
+        ours = mpijob.models.MODEL_CLASSES.get(name)
+        assert ours is not None, name
+        assert snake(name) == module, name
+        assert set(amap.items()) <= set(ours.attribute_map.items()), name      # (the pod-template side may carry more fields)
+        assert sorted(ours.required) == required, name
+
+
 def test_reference_sdk_example_runs_unmodified_through_the_kubernetes_shim(tmp_path):
     """The reference's own SDK example (sdk/python/v2beta1/tensorflow-mnist.py: kubernetes.client models, the stale
     `mpijob.V1ReplicaSpec` import, `config.load_kube_config()`, `CustomObjectsApi().create_namespaced_custom_object`) is
